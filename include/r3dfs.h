@@ -1,0 +1,230 @@
+/*
+ * r3dfs.h — C ABI of libr3dfs.so: the B200 (sm_100a) implementation of the R3DFSSeg / MPTI
+ * episode hot path.  This is the drop-in boundary: plain pointers and sizes, no torch types.
+ *
+ * Conventions (all entry points)
+ *   - every pointer is a DEVICE pointer unless the parameter name starts with `h_`;
+ *   - the caller owns every buffer (inputs, outputs, workspace); the library never allocates,
+ *     frees or keeps a pointer after the call returns, and has no global mutable state;
+ *   - all work is enqueued on `stream`; no call synchronises the device;
+ *   - return 0 on success, a negative R3DFS_E_* for bad arguments, a positive value =
+ *     (int)cudaError_t when a launch failed.  Nothing throws or aborts;
+ *   - results are bit-reproducible run to run (no floating-point atomics);
+ *   - "point-major" = a cloud stored as N rows of C contiguous floats.  The reference's collate
+ *     (dataloaders/loader.py:1662-1684) hands over exactly this memory behind a transposed
+ *     (B, C, N) view, so strided (B, C, N) inputs are accepted everywhere a cloud comes in.
+ *
+ * Reference interface each entry replaces is cited as file:line of Pixie8888/R3DFSSeg.
+ */
+#ifndef R3DFS_H_
+#define R3DFS_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define R3DFS_VERSION 100
+
+#define R3DFS_OK 0
+#define R3DFS_E_BADARG (-1)      /* null pointer, non-positive size                          */
+#define R3DFS_E_UNSUPPORTED (-2) /* shape outside what the kernels are built for (see each)  */
+#define R3DFS_E_WORKSPACE (-3)   /* workspace too small: call the matching *_workspace()     */
+#define R3DFS_E_ALIGN (-4)       /* pointer not aligned as required (16 B unless noted)      */
+
+typedef void* r3dfs_stream_t; /* cudaStream_t */
+
+int r3dfs_version(void);
+const char* r3dfs_strerror(int code);
+
+/* ------------------------------------------------------------------------------------------
+ * DGCNN pieces (reference models/dgcnn.py)
+ * ---------------------------------------------------------------------------------------- */
+
+/* knn(x, k) — models/dgcnn.py:17-23.  x: (B, C, N) fp32 with element strides (sb, sc, sn).
+ * idx_out: (B, N, k) int64, the k nearest points INCLUDING the point itself, nearest first
+ * (ranking key = -|xi|^2 + 2 xi.xj - |xj|^2 exactly as the reference forms it).  1 <= k <= 32. */
+size_t r3dfs_knn_workspace(int64_t B, int64_t C, int64_t N, int k);
+int r3dfs_knn(const float* x, int64_t B, int64_t C, int64_t N, int64_t sb, int64_t sc,
+              int64_t sn, int k, int64_t* idx_out, void* ws, size_t ws_bytes,
+              r3dfs_stream_t stream);
+
+/* get_edge_feature(x, K, idx) — models/dgcnn.py:26-42.  Materialises the (B, 2C, N, K)
+ * contiguous edge tensor cat(x_j - x_i, x_i).  idx: (B, N, K) int64 contiguous. */
+int r3dfs_edge_feature(const float* x, int64_t B, int64_t C, int64_t N, int64_t sb, int64_t sc,
+                       int64_t sn, const int64_t* idx, int K, float* out, r3dfs_stream_t stream);
+
+/* Weights of the episode model, eval mode.  Every BatchNorm is folded by the host into a
+ * per-channel (scale, shift) pair: y = act(scale * (W x) + shift)  (conv bias folded into shift).
+ *   EdgeConv block i (models/dgcnn.py:45-61,116-119):  ec_w1[i] (64, 2*Cin_i) row-major,
+ *       ec_w2[i] (64, 64); LeakyReLU(0.2) after both; Cin = {in_dim, 64, 64}.
+ *   point MLP (models/dgcnn.py:121-122): mlp_w[0] (512, 192), mlp_w[1] (256, 512), LeakyReLU(0.2).
+ *   BaseLearner (models/mpti.py:18-40): bl_w[0] (128, 256) + ReLU, bl_w[1] (64, 128) no act.
+ *   SelfAttention (models/attention.py:32-48): att_wqkv (192, 256) = [q_map; k_map; v_map].
+ * Widths are the reference defaults (eval_noise.py:198-217); other widths -> R3DFS_E_UNSUPPORTED. */
+typedef struct r3dfs_weights {
+  int32_t in_dim;  /* 9  */
+  int32_t dgcnn_k; /* 20 */
+  const float* ec_w1[3];
+  const float* ec_s1[3];
+  const float* ec_t1[3];
+  const float* ec_w2[3];
+  const float* ec_s2[3];
+  const float* ec_t2[3];
+  const float* mlp_w[2];
+  const float* mlp_s[2];
+  const float* mlp_t[2];
+  const float* bl_w[2];
+  const float* bl_s[2];
+  const float* bl_t[2];
+  const float* att_wqkv;
+} r3dfs_weights_t;
+
+/* 1x1 conv + folded BatchNorm + activation on point-major rows — the building block of the
+ * reference's conv1d / conv2d stacks (models/dgcnn.py:45-80) and BaseLearner (models/mpti.py:31-39):
+ *   y[m][n] = act(s[n] * sum_k x[m][k] w[n][k] + t[n]),  act: 0 none, 1 ReLU, 2 LeakyReLU(0.2).
+ * x: (M, K) rows ldx floats apart; w: (Nout, K) row-major; s, t: (Nout) or NULL (= 1, 0);
+ * y: (M, Nout) rows ldy floats apart. */
+int r3dfs_linear(const float* x, int64_t ldx, const float* w, const float* s, const float* t,
+                 int act, int64_t M, int64_t K, int64_t Nout, float* y, int64_t ldy,
+                 r3dfs_stream_t stream);
+
+/* One fused EdgeConv block, eval BN: knn -> gather -> (W1, BN, LReLU) -> (W2, BN, LReLU) -> max
+ * over k (models/dgcnn.py:115-118).  The (B, 2C, N, k) edge tensor is never formed.
+ * x: (B, C, N) strided; y: (B, N, 64) point-major contiguous; idx_out: optional (B, N, k) int64. */
+size_t r3dfs_edgeconv_workspace(int64_t B, int64_t C, int64_t N, int k);
+int r3dfs_edgeconv(const float* x, int64_t B, int64_t C, int64_t N, int64_t sb, int64_t sc,
+                   int64_t sn, int k, const float* w1, const float* s1, const float* t1,
+                   const float* w2, const float* s2, const float* t2, float* y, int64_t* idx_out,
+                   void* ws, size_t ws_bytes, r3dfs_stream_t stream);
+
+/* getFeatures(x) — models/mpti.py:579-589 (use_attention=True): DGCNN (models/dgcnn.py:113-127)
+ * + BaseLearner + SelfAttention, concatenated [level1(64) | attention(64) | base(64)].
+ * x: (B, in_dim, N) strided.  feat: (B, N, 192) point-major contiguous.
+ * level2 (optional, may be NULL): (B, N, 256) point-major = DGCNN's second output. */
+size_t r3dfs_features_workspace(int64_t B, int64_t N);
+int r3dfs_features(const r3dfs_weights_t* h_w, const float* x, int64_t B, int64_t N, int64_t sb,
+                   int64_t sc, int64_t sn, float* feat, float* level2, void* ws, size_t ws_bytes,
+                   r3dfs_stream_t stream);
+
+/* SelfAttention.forward, eval (dropout off) — models/attention.py:32-48, out_channel = 64.
+ * x: (B, N, Cin) point-major; wqkv: (192, Cin); y: (B, N, 64) point-major. */
+size_t r3dfs_attention_workspace(int64_t B, int64_t N);
+int r3dfs_attention(const float* x, int64_t B, int64_t N, int64_t Cin, const float* wqkv, float* y,
+                    void* ws, size_t ws_bytes, r3dfs_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Multi-prototype generation (reference models/mpti.py:597-634)
+ * ---------------------------------------------------------------------------------------- */
+
+/* torch_cluster.fps(feat, None, ratio=m/n, random_start=False) as called at models/mpti.py:613,
+ * for `n_sets` independent sets in one launch.  Set s = rows [set_off[s], set_off[s]+set_n[s])
+ * of feat (rows of D contiguous floats, D % 4 == 0, D <= 256).  Start at local index 0;
+ * dist_i = min(dist_i, sum_d (x_id - x_last,d)^2) in fp32 (direct differences);
+ * next = argmax (lowest index on ties).  idx_out: (n_sets, m_max) int32 local indices in
+ * selection order; count per set = min(m_max, n).  n_cap = host-known upper bound of every
+ * set_n[s] (sizes the per-CTA shared-memory slice; set sizes themselves stay on the device). */
+int r3dfs_fps(const float* feat, int64_t D, const int32_t* set_off, const int32_t* set_n,
+              int n_sets, int64_t n_cap, int m_max, int32_t* idx_out, r3dfs_stream_t stream);
+
+/* getMutiplePrototypes(feat, k) — models/mpti.py:597-634, for `n_sets` sets in one call:
+ * m = ceil(fp32(n) * fp32(k / n)) FPS seeds (k or k+1), sorted + deduplicated (`.unique()`),
+ * assignment = argmin_j || f - seed_j + 1e-6 ||_2 (torch<=1.8 pairwise_distance, first minimum),
+ * prototype = mean of members; n <= k -> every point is its own prototype.
+ * proto_out: (n_sets, k+1, D); proto_count: (n_sets) int32; assign_out: int32 per feat row (local
+ * prototype index); seed_idx_out: (n_sets, k+1) int32 sorted local seed indices (-1 padded). */
+size_t r3dfs_multi_prototypes_workspace(int64_t total_rows, int n_sets, int k);
+int r3dfs_multi_prototypes(const float* feat, int64_t D, const int32_t* set_off,
+                           const int32_t* set_n, int n_sets, int64_t total_rows, int k,
+                           float* proto_out, int32_t* proto_count, int32_t* assign_out,
+                           int32_t* seed_idx_out, void* ws, size_t ws_bytes,
+                           r3dfs_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Affinity graph + label propagation (reference models/mpti.py:717-776)
+ * ---------------------------------------------------------------------------------------- */
+
+/* calculateLocalConstrainedAffinity (models/mpti.py:717-756) in sparse form, `n_graphs` graphs
+ * per call, each with n_max node slots of which those with valid[g][i] != 0 exist.
+ *   nbr: (n_graphs, n_max, k) int32 — the k nearest OTHER valid nodes by squared L2 (the
+ *        faiss.IndexFlatL2 search of k+1 with column 0 = the node itself dropped, :733-736);
+ *   sim: (n_graphs, n_max, k) fp32 — exp(-0.5 (||f_i - f_j + 1e-6||_2 / sigma)^2) (:745-746).
+ * node_feat: (n_graphs, n_max, D) fp32, D % 4 == 0.  Requires k < #valid nodes, k <= 1024. */
+size_t r3dfs_affinity_workspace(int n_graphs, int64_t n_max, int64_t D, int k);
+int r3dfs_affinity_knn(const float* node_feat, const uint8_t* valid, int n_graphs, int64_t n_max,
+                       int64_t D, int k, float sigma, int32_t* nbr, float* sim, void* ws,
+                       size_t ws_bytes, r3dfs_stream_t stream);
+
+/* label_propagate (models/mpti.py:758-776):  W = A + A^T with A the k-sparse matrix (nbr, sim),
+ * zero diagonal; S = D^-1/2 W D^-1/2 with D = rowsum(W) + eps; solve (I - alpha S) Z = Y by FP32
+ * conjugate gradients on the sparse graph (the reference inverts the dense matrix).
+ * Y, Z: (n_graphs, n_max, n_cls) fp32, n_cls <= 8.  Rows of invalid nodes are written as 0.
+ * iters_out (n_graphs) int32 / resid_out (n_graphs) fp32: optional CG diagnostics (may be NULL). */
+size_t r3dfs_label_propagate_workspace(int n_graphs, int64_t n_max, int k, int n_cls);
+int r3dfs_label_propagate(const int32_t* nbr, const float* sim, const uint8_t* valid, int n_graphs,
+                          int64_t n_max, int k, const float* Y, int n_cls, float alpha, float tol,
+                          int max_iter, float* Z, int32_t* iters_out, float* resid_out, void* ws,
+                          size_t ws_bytes, r3dfs_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Whole episode(s): MPTI_SelfAtten.forward, eval path (reference models/mpti.py:414-577)
+ * ---------------------------------------------------------------------------------------- */
+
+typedef struct r3dfs_episode_cfg {
+  int32_t n_way;
+  int32_t k_shot;
+  int32_t n_query;         /* number of query clouds = n_way * n_queries                        */
+  int32_t n_points;        /* 2048; multiple of 64                                               */
+  int32_t n_subprototypes; /* 100  (<= 127)                                                     */
+  int32_t k_connect;       /* 200                                                               */
+  float sigma;             /* 1.0                                                               */
+  float alpha;             /* 0.99 (models/mpti.py:758)                                         */
+  int32_t mdns;            /* 1 = multi-scale degree-based noise suppression (forward eval=True) */
+  int32_t cg_max_iter;     /* e.g. 200                                                          */
+  float cg_tol;            /* relative residual, e.g. 1e-6                                      */
+} r3dfs_episode_cfg_t;
+
+/* Device-side per-episode diagnostics (all optional: pass NULL to skip). */
+typedef struct r3dfs_episode_diag {
+  int32_t* proto_count; /* (E, n_way + 1): prototypes of [bg, way 0, ...]                      */
+  float* clean_flag;    /* (E, n_way, k_shot): MDNS clean flag (1 = kept), models/mpti.py:201-221;
+                           written only when cfg.mdns = 1                                       */
+  int32_t* cg_iters;    /* (E)                                                                  */
+  float* cg_resid;      /* (E)                                                                  */
+} r3dfs_episode_diag_t;
+
+size_t r3dfs_mpti_workspace(const r3dfs_episode_cfg_t* h_cfg, int n_episodes);
+
+/* E = n_episodes independent episodes in one call (reference: one per forward call).
+ *   support_x: (E, n_way, k_shot, in_dim, N) with element strides (s_e, s_cloud, s_c, s_n) —
+ *              clouds of an episode are n_way*k_shot consecutive `s_cloud` steps;
+ *   support_y: (E, n_way, k_shot, N) int32 contiguous, non-zero = foreground;
+ *   query_x:   (E, n_query, in_dim, N) strides (q_e, q_cloud, q_c, q_n);
+ *   query_y:   (E, n_query, N) int64 contiguous in [0, n_way] (may be NULL -> loss not computed);
+ *   logits:    (E, n_query, N, n_way+1) fp32 — Z rows of the query nodes (the reference returns
+ *              this buffer viewed as (n_query, n_way+1, N), models/mpti.py:558-559);
+ *   loss:      (E) fp32 cross-entropy of logits vs query_y (models/mpti.py:571);
+ *   pred:      (E, n_query, N) int32 argmax labels (models/mpti_learner.py:98); may be NULL. */
+int r3dfs_mpti_forward(const r3dfs_episode_cfg_t* h_cfg, const r3dfs_weights_t* h_w,
+                       int n_episodes, const float* support_x, int64_t s_e, int64_t s_cloud,
+                       int64_t s_c, int64_t s_n, const int32_t* support_y, const float* query_x,
+                       int64_t q_e, int64_t q_cloud, int64_t q_c, int64_t q_n,
+                       const int64_t* query_y, float* logits, float* loss, int32_t* pred,
+                       const r3dfs_episode_diag_t* h_diag, void* ws, size_t ws_bytes,
+                       r3dfs_stream_t stream);
+
+/* evaluate_metric counters (reference eval_noise.py:35-62): for every query point, map the
+ * episode-local label to its slot in the test-class list and accumulate gt / predicted /
+ * true-positive counts.  class_slot: (E, n_way) int32 = test_classes.index(sampled_class) + 1.
+ * counters: (3, n_slots) int64, accumulated in place (zero them before the first call); they
+ * are what NCCL sum-all-reduces across ranks. */
+int r3dfs_confusion_accumulate(const int32_t* pred, const int64_t* gt, const int32_t* class_slot,
+                               int n_episodes, int n_way, int64_t pts_per_episode, int n_slots,
+                               int64_t* counters, r3dfs_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* R3DFS_H_ */

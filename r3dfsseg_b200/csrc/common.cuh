@@ -1,0 +1,90 @@
+// Shared device/host helpers for libr3dfs (sm_100a).  Internal — the public surface is include/r3dfs.h.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+
+#include "../../include/r3dfs.h"
+
+#define R3DFS_FEAT_DIM 192
+#define R3DFS_EC_WIDTH 64
+
+#define R3DFS_CHECK_LAUNCH()                       \
+  do {                                             \
+    cudaError_t e__ = cudaGetLastError();          \
+    if (e__ != cudaSuccess) return (int)e__;       \
+  } while (0)
+
+#define R3DFS_TRY(expr)                            \
+  do {                                             \
+    int rc__ = (expr);                             \
+    if (rc__ != 0) return rc__;                    \
+  } while (0)
+
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// Bump allocator over the caller's workspace.  Never owns memory.
+struct WsBump {
+  char* base;
+  size_t cap;
+  size_t off;
+  __host__ WsBump(void* p, size_t c) : base((char*)p), cap(c), off(0) {}
+  template <typename T>
+  __host__ T* take(size_t n) {
+    off = align_up(off, 256);
+    T* r = (T*)(base + off);
+    off += n * sizeof(T);
+    return r;
+  }
+  __host__ bool ok() const { return off <= cap; }
+};
+
+// Row mapping for per-cloud outputs that land inside the per-episode node matrix:
+// row(b, i) = (b / cpe) * ep_rows + row_off + (b % cpe) * n + i.   cpe == 0 -> identity b*n+i.
+struct RowMap {
+  int cpe;
+  int n;
+  int64_t ep_rows;
+  int64_t row_off;
+  __host__ __device__ inline int64_t operator()(int64_t m) const {
+    if (cpe == 0) return m;
+    int64_t b = m / n, i = m - b * n;
+    return (b / cpe) * ep_rows + row_off + (b % cpe) * (int64_t)n + i;
+  }
+};
+static inline RowMap identity_map() { return RowMap{0, 1, 0, 0}; }
+
+enum Act { ACT_NONE = 0, ACT_RELU = 1, ACT_LRELU = 2 };
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+  if (act == ACT_RELU) return fmaxf(v, 0.f);
+  if (act == ACT_LRELU) return v > 0.f ? v : 0.2f * v;
+  return v;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// internal launchers (defined in the .cu files)
+int launch_to_point_major(const float* x, int64_t B, int64_t C, int64_t N, int64_t sb, int64_t sc,
+                          int64_t sn, float* out, cudaStream_t st);
+int launch_row_norms(const float* x, int64_t rows, int ld, int C, float* out, cudaStream_t st);
+int launch_knn(const float* x, int ld, int C, const float* xx, int64_t B, int N, int k,
+               int32_t* idx32, int64_t* idx64, cudaStream_t st);
+int launch_linear(const float* X, int ldx, const float* W, const float* s, const float* t, int act,
+                  int64_t M, int K, int Nout, float* Y, int ldy, RowMap map, cudaStream_t st);
+int launch_edge_mlp(const float* PQ, const int32_t* idx, const float* w2, const float* s2,
+                    const float* t2, int64_t B, int N, int k, float* Y, int ldy, RowMap map,
+                    float* w2t_scratch, cudaStream_t st);
+int launch_edge_feature(const float* x, int64_t B, int64_t C, int64_t N, int64_t sb, int64_t sc,
+                        int64_t sn, const int64_t* idx, int K, float* out, cudaStream_t st);
+int launch_attention(const float* qkv, int ld, int64_t B, int N, float* Y, int ldy, RowMap map,
+                     cudaStream_t st);
+int launch_fold_edge_w1(const float* w1, const float* s1, const float* t1, int C, float* wpq,
+                        float* spq, float* tpq, cudaStream_t st);
+
+int launch_fps(const float* feat, int D, const int32_t* set_off, const int32_t* set_n, int n_sets,
+               int m_max, int k_for_count, int32_t* idx_out, cudaStream_t st);

@@ -1,0 +1,744 @@
+// Affinity graph (reference models/mpti.py:717-756) and label propagation (models/mpti.py:758-776)
+// in sparse form, plus the query loss / prediction / confusion counters.
+#include <cooperative_groups.h>
+
+#include "common.cuh"
+#include "lp.cuh"
+
+namespace cg = cooperative_groups;
+
+// --------------------------------------------------------------------------------------------
+// Squared-L2 matrix of one graph's nodes, Gram form (what faiss.IndexFlatL2 ranks by,
+// models/mpti.py:733-735):  D2[i][j] = |f_i|^2 + |f_j|^2 - 2 f_i.f_j .   128 x 64 tiles.
+// --------------------------------------------------------------------------------------------
+#define GD_BM 128
+#define GD_BN 64
+#define GD_BK 16
+
+template <int ROWS, int KC>
+__device__ __forceinline__ void lp_load_tile_T(float* __restrict__ dst,
+                                               const float* __restrict__ src, int ld, int64_t row0,
+                                               int64_t rows_end, int k0, int k_end) {
+  constexpr int KG = KC / 8;
+  constexpr int PAIRS = (ROWS / 4) * KG;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int nw = blockDim.x >> 5;
+  const int r_lo = lane & 3, k_lo = lane >> 2;
+  for (int p = w; p < PAIRS; p += nw) {
+    int kg = p % KG, rg = p / KG;
+    int row = 4 * rg + r_lo, kk = 8 * kg + k_lo;
+    int64_t gr = row0 + row;
+    int gk = k0 + kk;
+    float v = 0.f;
+    if (gr < rows_end && gk < k_end) v = src[gr * (int64_t)ld + gk];
+    dst[kk * ROWS + (row ^ (k_lo << 2))] = v;
+  }
+}
+
+__global__ __launch_bounds__(256) void gram_dist_kernel(const float* __restrict__ F,
+                                                        int64_t graph_rows, int64_t row_off,
+                                                        int nn, int D,
+                                                        const float* __restrict__ norms,
+                                                        float* __restrict__ D2) {
+  __shared__ __align__(16) float As[GD_BK * GD_BM];
+  __shared__ __align__(16) float Bs[GD_BK * GD_BN];
+  const int g = blockIdx.z;
+  const float* Fg = F + ((int64_t)g * graph_rows + row_off) * D;
+  const float* ng = norms + (int64_t)g * nn;
+  float* Dg = D2 + (int64_t)g * nn * nn;
+  const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+  const int m0 = blockIdx.x * GD_BM, n0 = blockIdx.y * GD_BN;
+  float acc[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  for (int k0 = 0; k0 < D; k0 += GD_BK) {
+    __syncthreads();
+    lp_load_tile_T<GD_BM, GD_BK>(As, Fg, D, m0, nn, k0, D);
+    lp_load_tile_T<GD_BN, GD_BK>(Bs, Fg, D, n0, nn, k0, D);
+    __syncthreads();
+    const int kend = min(GD_BK, D - k0);
+#pragma unroll 4
+    for (int kk = 0; kk < kend; ++kk) {
+      const int sw = (kk & 7) << 2;
+      float4 a0 = *reinterpret_cast<const float4*>(&As[kk * GD_BM + ((8 * ty) ^ sw)]);
+      float4 a1 = *reinterpret_cast<const float4*>(&As[kk * GD_BM + ((8 * ty + 4) ^ sw)]);
+      float4 bb = *reinterpret_cast<const float4*>(&Bs[kk * GD_BN + ((4 * tx) ^ sw)]);
+      float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      float bv[4] = {bb.x, bb.y, bb.z, bb.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+  }
+  const int n = n0 + 4 * tx;
+  if (n >= nn) return;
+  float nj[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) nj[j] = (n + j < nn) ? ng[n + j] : 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int m = m0 + 8 * ty + i;
+    if (m >= nn) continue;
+    const float ni = ng[m];
+    float4 o;
+    o.x = (ni + nj[0]) - 2.f * acc[i][0];
+    o.y = (ni + nj[1]) - 2.f * acc[i][1];
+    o.z = (ni + nj[2]) - 2.f * acc[i][2];
+    o.w = (ni + nj[3]) - 2.f * acc[i][3];
+    if (n + 3 < nn && (nn & 3) == 0) {
+      *reinterpret_cast<float4*>(Dg + (int64_t)m * nn + n) = o;
+    } else {
+      float ov[4] = {o.x, o.y, o.z, o.w};
+      for (int j = 0; j < 4; ++j)
+        if (n + j < nn) Dg[(int64_t)m * nn + n + j] = ov[j];
+    }
+  }
+}
+
+// --------------------------------------------------------------------------------------------
+// Per-row selection of the k nearest other valid nodes: 4-pass 8-bit radix select on the row's
+// order-preserving integer keys in shared memory, then an ordered compaction (ties at the k-th
+// distance -> lowest index).  One CTA per row.
+// --------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned f2key(float f) {
+  unsigned u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+#define SEL_THREADS 256
+
+__global__ __launch_bounds__(SEL_THREADS) void knn_select_kernel(const float* __restrict__ D2,
+                                                                 const uint8_t* __restrict__ valid,
+                                                                 int nn, int k,
+                                                                 int32_t* __restrict__ nbr) {
+  extern __shared__ unsigned s_key[];  // [nn]
+  __shared__ int s_hist[256];
+  __shared__ unsigned s_prefix, s_mask;
+  __shared__ int s_need;
+  __shared__ int s_w[2][SEL_THREADS / 32];
+  const int g = blockIdx.y, i = blockIdx.x;
+  const uint8_t* vg = valid + (int64_t)g * nn;
+  if (!vg[i]) return;
+  const float* row = D2 + ((int64_t)g * nn + i) * nn;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  for (int j = tid; j < nn; j += SEL_THREADS) {
+    unsigned key = 0xffffffffu;
+    if (j != i && vg[j]) {
+      key = f2key(row[j]);
+      if (key == 0xffffffffu) key = 0xfffffffeu;
+    }
+    s_key[j] = key;
+  }
+  if (tid == 0) {
+    s_prefix = 0;
+    s_mask = 0;
+    s_need = k;
+  }
+  for (int pass = 3; pass >= 0; --pass) {
+    const int shift = 8 * pass;
+    s_hist[tid] = 0;  // SEL_THREADS == 256
+    __syncthreads();
+    const unsigned prefix = s_prefix, mask = s_mask;
+    for (int j = tid; j < nn; j += SEL_THREADS) {
+      const unsigned key = s_key[j];
+      if ((key & mask) == prefix) atomicAdd(&s_hist[(key >> shift) & 255], 1);
+    }
+    __syncthreads();
+    if (tid == 0) {
+      int need = s_need, cum = 0, b = 0;
+      for (; b < 255; ++b) {
+        if (cum + s_hist[b] >= need) break;
+        cum += s_hist[b];
+      }
+      s_need = need - cum;
+      s_prefix = prefix | ((unsigned)b << shift);
+      s_mask = mask | (255u << shift);
+    }
+    __syncthreads();
+  }
+  const unsigned T = s_prefix;
+  const int need_eq = s_need;
+  int32_t* out = nbr + ((int64_t)g * nn + i) * k;
+  int run_eq = 0, run_sel = 0;
+  for (int c0 = 0; c0 < nn; c0 += SEL_THREADS) {
+    const int j = c0 + tid;
+    const unsigned key = j < nn ? s_key[j] : 0xffffffffu;
+    const bool lt = key < T, eq = key == T;
+    const unsigned beq = __ballot_sync(0xffffffffu, eq);
+    if (lane == 0) s_w[0][w] = __popc(beq);
+    __syncthreads();
+    int eoff = run_eq, etot = 0;
+    for (int q = 0; q < SEL_THREADS / 32; ++q) {
+      if (q < w) eoff += s_w[0][q];
+      etot += s_w[0][q];
+    }
+    const int erank = eoff + __popc(beq & ((1u << lane) - 1));
+    const bool sel = lt || (eq && erank < need_eq);
+    const unsigned bsel = __ballot_sync(0xffffffffu, sel);
+    if (lane == 0) s_w[1][w] = __popc(bsel);
+    __syncthreads();
+    int soff = run_sel, stot = 0;
+    for (int q = 0; q < SEL_THREADS / 32; ++q) {
+      if (q < w) soff += s_w[1][q];
+      stot += s_w[1][q];
+    }
+    if (sel) {
+      const int pos = soff + __popc(bsel & ((1u << lane) - 1));
+      if (pos < k) out[pos] = j;
+    }
+    run_eq += etot;
+    run_sel += stot;
+    __syncthreads();
+  }
+}
+
+// --------------------------------------------------------------------------------------------
+// Gaussian similarity of the kept edges (models/mpti.py:745-746) with torch<=1.8
+// pairwise_distance: dist = || f_i - f_j + 1e-6 ||_2 by direct differences, sim = exp(-0.5 (dist/sigma)^2).
+// One warp per node, 8 lanes per neighbour.
+// --------------------------------------------------------------------------------------------
+#define LP_MAX_F4 8
+
+__global__ __launch_bounds__(256) void edge_sim_kernel(const float* __restrict__ F,
+                                                       int64_t graph_rows, int64_t row_off, int nn,
+                                                       int D, const uint8_t* __restrict__ valid,
+                                                       const int32_t* __restrict__ nbr, int k,
+                                                       float sigma, float* __restrict__ sim) {
+  const int g = blockIdx.y;
+  const int i = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (i >= nn) return;
+  if (!valid[(int64_t)g * nn + i]) return;
+  const int lane = threadIdx.x & 31, sub = lane & 7, grp = lane >> 3;
+  const float* Fg = F + ((int64_t)g * graph_rows + row_off) * D;
+  const int D4 = D >> 2;
+  float4 xf[LP_MAX_F4];
+  const float4* xrow = reinterpret_cast<const float4*>(Fg + (int64_t)i * D);
+#pragma unroll
+  for (int u = 0; u < LP_MAX_F4; ++u) {
+    int c4 = sub + 8 * u;
+    xf[u] = (c4 < D4) ? xrow[c4] : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  const int32_t* nb = nbr + ((int64_t)g * nn + i) * k;
+  float* so = sim + ((int64_t)g * nn + i) * k;
+  for (int t0 = 0; t0 < k; t0 += 4) {
+    const int t = t0 + grp;
+    const bool ok = t < k;
+    const int j = ok ? nb[t] : i;
+    const float4* yrow = reinterpret_cast<const float4*>(Fg + (int64_t)j * D);
+    float acc = 0.f;
+#pragma unroll
+    for (int u = 0; u < LP_MAX_F4; ++u) {
+      int c4 = sub + 8 * u;
+      if (c4 < D4) {
+        float4 y = yrow[c4];
+        float d0 = __fadd_rn(xf[u].x - y.x, 1e-6f), d1 = __fadd_rn(xf[u].y - y.y, 1e-6f),
+              d2 = __fadd_rn(xf[u].z - y.z, 1e-6f), d3 = __fadd_rn(xf[u].w - y.w, 1e-6f);
+        acc = fmaf(d0, d0, acc);
+        acc = fmaf(d1, d1, acc);
+        acc = fmaf(d2, d2, acc);
+        acc = fmaf(d3, d3, acc);
+      }
+    }
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+    if (ok && sub == 0) {
+      const float tt = sqrtf(acc) / sigma;
+      so[t] = expf(-0.5f * (tt * tt));
+    }
+  }
+}
+
+// --------------------------------------------------------------------------------------------
+// In-edge lists (the A^T half of W = A + A^T, models/mpti.py:752): count, scan, fill, then sort
+// each column's list by source so the result does not depend on atomic ordering.
+// --------------------------------------------------------------------------------------------
+__global__ void in_count_kernel(const int32_t* __restrict__ nbr, const uint8_t* __restrict__ valid,
+                                int nn, int k, int32_t* __restrict__ in_cnt) {
+  const int g = blockIdx.y;
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= (int64_t)nn * k) return;
+  const int i = (int)(e / k);
+  if (!valid[(int64_t)g * nn + i]) return;
+  const int j = nbr[(int64_t)g * nn * k + e];
+  atomicAdd(&in_cnt[(int64_t)g * nn + j], 1);
+}
+
+// exclusive scan of in_cnt -> in_ptr (nn + 1 entries per graph); also zeroes the fill cursors
+__global__ __launch_bounds__(1024) void in_scan_kernel(int32_t* __restrict__ in_cnt, int nn,
+                                                       int32_t* __restrict__ in_ptr) {
+  __shared__ int s_part[1024];
+  const int g = blockIdx.x, tid = threadIdx.x;
+  int32_t* cnt = in_cnt + (int64_t)g * nn;
+  int32_t* ptr = in_ptr + (int64_t)g * (nn + 1);
+  const int per = (nn + 1023) / 1024;
+  const int lo = min(nn, tid * per), hi = min(nn, lo + per);
+  int s = 0;
+  for (int i = lo; i < hi; ++i) s += cnt[i];
+  s_part[tid] = s;
+  __syncthreads();
+  // Hillis-Steele inclusive scan over 1024 partials
+  for (int o = 1; o < 1024; o <<= 1) {
+    int v = tid >= o ? s_part[tid - o] : 0;
+    __syncthreads();
+    s_part[tid] += v;
+    __syncthreads();
+  }
+  int run = tid == 0 ? 0 : s_part[tid - 1];
+  for (int i = lo; i < hi; ++i) {
+    ptr[i] = run;
+    run += cnt[i];
+    cnt[i] = 0;  // reused as the fill cursor
+  }
+  if (tid == 1023) ptr[nn] = s_part[1023];
+}
+
+__global__ void in_fill_kernel(const int32_t* __restrict__ nbr, const float* __restrict__ sim,
+                               const uint8_t* __restrict__ valid, int nn, int k,
+                               const int32_t* __restrict__ in_ptr, int32_t* __restrict__ cursor,
+                               int32_t* __restrict__ in_src, float* __restrict__ in_w) {
+  const int g = blockIdx.y;
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= (int64_t)nn * k) return;
+  const int i = (int)(e / k);
+  if (!valid[(int64_t)g * nn + i]) return;
+  const int64_t ge = (int64_t)g * nn * k + e;
+  const int j = nbr[ge];
+  const int pos = in_ptr[(int64_t)g * (nn + 1) + j] + atomicAdd(&cursor[(int64_t)g * nn + j], 1);
+  in_src[(int64_t)g * nn * k + pos] = i;
+  in_w[(int64_t)g * nn * k + pos] = sim[ge];
+}
+
+__global__ __launch_bounds__(256) void in_sort_kernel(const int32_t* __restrict__ in_ptr, int nn,
+                                                      int k, int32_t* __restrict__ in_src,
+                                                      float* __restrict__ in_w) {
+  extern __shared__ __align__(8) unsigned char s_raw[];
+  const int g = blockIdx.y, j = blockIdx.x;
+  const int32_t* ptr = in_ptr + (int64_t)g * (nn + 1);
+  const int lo = ptr[j], L = ptr[j + 1] - lo;
+  if (L <= 1) return;
+  int P = 2;
+  while (P < L) P <<= 1;
+  int* s_src = reinterpret_cast<int*>(s_raw);
+  float* s_val = reinterpret_cast<float*>(s_raw) + P;
+  int32_t* src = in_src + (int64_t)g * nn * k + lo;
+  float* val = in_w + (int64_t)g * nn * k + lo;
+  const int tid = threadIdx.x;
+  for (int t = tid; t < P; t += 256) {
+    s_src[t] = t < L ? src[t] : 0x7fffffff;
+    s_val[t] = t < L ? val[t] : 0.f;
+  }
+  __syncthreads();
+  for (int ksz = 2; ksz <= P; ksz <<= 1)
+    for (int jj = ksz >> 1; jj > 0; jj >>= 1) {
+      for (int t = tid; t < P; t += 256) {
+        const int x = t ^ jj;
+        if (x > t) {
+          const bool up = (t & ksz) == 0;
+          const int a = s_src[t], b = s_src[x];
+          if ((a > b) == up) {
+            s_src[t] = b;
+            s_src[x] = a;
+            const float va = s_val[t];
+            s_val[t] = s_val[x];
+            s_val[x] = va;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  for (int t = tid; t < L; t += 256) {
+    src[t] = s_src[t];
+    val[t] = s_val[t];
+  }
+}
+
+// degree and D^-1/2 (models/mpti.py:767-770): D = rowsum(A + A^T), D^-1/2 = sqrt(1 / (D + eps))
+__global__ __launch_bounds__(256) void degree_kernel(const float* __restrict__ sim,
+                                                     const int32_t* __restrict__ in_ptr,
+                                                     const float* __restrict__ in_w,
+                                                     const uint8_t* __restrict__ valid, int nn,
+                                                     int k, float* __restrict__ dinv) {
+  const int g = blockIdx.y;
+  const int i = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (i >= nn) return;
+  const int lane = threadIdx.x & 31;
+  float d = 0.f;
+  if (valid[(int64_t)g * nn + i]) {
+    const float* so = sim + ((int64_t)g * nn + i) * k;
+    for (int t = lane; t < k; t += 32) d += so[t];
+    const int32_t* ptr = in_ptr + (int64_t)g * (nn + 1);
+    const float* w = in_w + (int64_t)g * nn * k;
+    for (int t = ptr[i] + lane; t < ptr[i + 1]; t += 32) d += w[t];
+    d = warp_sum(d);
+    d = sqrtf(1.0f / (d + 2.220446049250313e-16f));
+  }
+  if (lane == 0) dinv[(int64_t)g * nn + i] = d;
+}
+
+// S = D^-1/2 W D^-1/2 on the stored pattern (models/mpti.py:772)
+__global__ void normalize_kernel(const int32_t* __restrict__ nbr, float* __restrict__ sim,
+                                 const int32_t* __restrict__ in_ptr,
+                                 const int32_t* __restrict__ in_src, float* __restrict__ in_w,
+                                 const uint8_t* __restrict__ valid, const float* __restrict__ dinv,
+                                 int nn, int k) {
+  const int g = blockIdx.y;
+  const int i = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (i >= nn) return;
+  if (!valid[(int64_t)g * nn + i]) return;
+  const int lane = threadIdx.x & 31;
+  const float* dg = dinv + (int64_t)g * nn;
+  const float di = dg[i];
+  const int64_t ob = ((int64_t)g * nn + i) * k;
+  for (int t = lane; t < k; t += 32) sim[ob + t] = (di * sim[ob + t]) * dg[nbr[ob + t]];
+  const int32_t* ptr = in_ptr + (int64_t)g * (nn + 1);
+  const int64_t ib = (int64_t)g * nn * k;
+  for (int t = ptr[i] + lane; t < ptr[i + 1]; t += 32)
+    in_w[ib + t] = (di * in_w[ib + t]) * dg[in_src[ib + t]];
+}
+
+// --------------------------------------------------------------------------------------------
+// Label propagation: (I - alpha S) Z = Y by conjugate gradients, all n_cls right-hand sides at
+// once, one thread-block cluster per graph.  Rows are sliced over the cluster's CTAs; the search
+// direction P is the only vector other CTAs read (through L2); dot products are exchanged through
+// distributed shared memory and summed in rank order, so every CTA sees identical scalars.
+// --------------------------------------------------------------------------------------------
+#define CG_THREADS 512
+#define CG_CL 8
+#define CG_MAXC 8
+
+struct CgExchange {
+  float slot[2][CG_CL][CG_MAXC];
+};
+
+__device__ __forceinline__ void cg_allreduce(cg::cluster_group& cluster, CgExchange* ex,
+                                             float* s_warp /*[16][8]*/, const float* part, int nc,
+                                             int& xcnt, float* total) {
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int rank = cluster.block_rank(), CL = cluster.num_blocks();
+  float v[CG_MAXC];
+#pragma unroll
+  for (int c = 0; c < CG_MAXC; ++c) v[c] = warp_sum(part[c]);
+  if (lane == 0) {
+#pragma unroll
+    for (int c = 0; c < CG_MAXC; ++c) s_warp[w * CG_MAXC + c] = v[c];
+  }
+  __syncthreads();
+  const int par = xcnt & 1;
+  if (tid < CG_MAXC) {
+    float s = 0.f;
+    for (int q = 0; q < CG_THREADS / 32; ++q) s += s_warp[q * CG_MAXC + tid];
+    for (int r = 0; r < CL; ++r) {
+      float* dst = cluster.map_shared_rank(&ex->slot[par][rank][tid], r);
+      *dst = s;
+    }
+  }
+  cluster.sync();
+#pragma unroll
+  for (int c = 0; c < CG_MAXC; ++c) {
+    float s = 0.f;
+    for (int r = 0; r < CL; ++r) s += ex->slot[par][r][c];
+    total[c] = s;
+  }
+  (void)nc;
+  ++xcnt;
+}
+
+__global__ __launch_bounds__(CG_THREADS) void lp_cg_kernel(
+    const int32_t* __restrict__ nbr, const float* __restrict__ sval,
+    const int32_t* __restrict__ in_ptr, const int32_t* __restrict__ in_src,
+    const float* __restrict__ in_sval, const uint8_t* __restrict__ valid, int nn, int k,
+    const float* __restrict__ Y, int nc, float alpha, float tol, int max_iter,
+    float* __restrict__ X, float* __restrict__ R, float* __restrict__ Pv, float* __restrict__ AP,
+    int32_t* __restrict__ iters_out, float* __restrict__ resid_out) {
+  cg::cluster_group cluster = cg::this_cluster();
+  const int CL = cluster.num_blocks(), rank = cluster.block_rank();
+  const int g = blockIdx.y;
+  __shared__ CgExchange ex;
+  __shared__ float s_warp[(CG_THREADS / 32) * CG_MAXC];
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int64_t vb = (int64_t)g * nn;
+  const uint8_t* vg = valid + vb;
+  const float* Yg = Y + vb * nc;
+  float* Xg = X + vb * nc;
+  float* Rg = R + vb * nc;
+  float* Pg = Pv + vb * nc;
+  float* APg = AP + vb * nc;
+  const int32_t* nb = nbr + vb * k;
+  const float* sv = sval + vb * k;
+  const int32_t* ip = in_ptr + (int64_t)g * (nn + 1);
+  const int32_t* is = in_src + vb * k;
+  const float* iv = in_sval + vb * k;
+  const int chunk = (nn + CL - 1) / CL;
+  const int lo = min(nn, rank * chunk), hi = min(nn, lo + chunk);
+  int xcnt = 0;
+
+  float part[CG_MAXC], bb[CG_MAXC], rs[CG_MAXC], tot[CG_MAXC];
+#pragma unroll
+  for (int c = 0; c < CG_MAXC; ++c) part[c] = 0.f;
+  for (int row = lo + tid; row < hi; row += CG_THREADS) {
+    const bool ok = vg[row];
+#pragma unroll
+    for (int c = 0; c < CG_MAXC; ++c)
+      if (c < nc) {
+        const float y = ok ? Yg[(int64_t)row * nc + c] : 0.f;
+        Xg[(int64_t)row * nc + c] = 0.f;
+        Rg[(int64_t)row * nc + c] = y;
+        Pg[(int64_t)row * nc + c] = y;
+        part[c] = fmaf(y, y, part[c]);
+      }
+  }
+  cg_allreduce(cluster, &ex, s_warp, part, nc, xcnt, bb);
+  bool done[CG_MAXC];
+  bool all_done = true;
+#pragma unroll
+  for (int c = 0; c < CG_MAXC; ++c) {
+    rs[c] = bb[c];
+    done[c] = !(c < nc) || !(bb[c] > 0.f);
+    all_done = all_done && done[c];
+  }
+  const float tol2 = tol * tol;
+  int it = 0;
+  while (!all_done && it < max_iter) {
+    // ---- AP = P - alpha * S P  on my rows; partial P.AP
+#pragma unroll
+    for (int c = 0; c < CG_MAXC; ++c) part[c] = 0.f;
+    for (int row = lo + w; row < hi; row += CG_THREADS / 32) {
+      if (!vg[row]) continue;  // warp-uniform
+      float acc[CG_MAXC];
+#pragma unroll
+      for (int c = 0; c < CG_MAXC; ++c) acc[c] = 0.f;
+      for (int t = lane; t < k; t += 32) {
+        const int j = nb[(int64_t)row * k + t];
+        const float v = sv[(int64_t)row * k + t];
+#pragma unroll
+        for (int c = 0; c < CG_MAXC; ++c)
+          if (c < nc) acc[c] = fmaf(v, __ldcg(Pg + (int64_t)j * nc + c), acc[c]);
+      }
+      for (int t = ip[row] + lane; t < ip[row + 1]; t += 32) {
+        const int j = is[t];
+        const float v = iv[t];
+#pragma unroll
+        for (int c = 0; c < CG_MAXC; ++c)
+          if (c < nc) acc[c] = fmaf(v, __ldcg(Pg + (int64_t)j * nc + c), acc[c]);
+      }
+#pragma unroll
+      for (int c = 0; c < CG_MAXC; ++c)
+        if (c < nc) {
+          const float s = warp_sum(acc[c]);
+          const float p = __ldcg(Pg + (int64_t)row * nc + c);
+          const float ap = p - alpha * s;
+          if (lane == 0) {
+            APg[(int64_t)row * nc + c] = ap;
+            part[c] = fmaf(p, ap, part[c]);
+          }
+        }
+    }
+    cg_allreduce(cluster, &ex, s_warp, part, nc, xcnt, tot);
+    float a[CG_MAXC];
+#pragma unroll
+    for (int c = 0; c < CG_MAXC; ++c) a[c] = (!done[c] && tot[c] > 0.f) ? rs[c] / tot[c] : 0.f;
+    // ---- X += a P ; R -= a AP ; partial R.R
+#pragma unroll
+    for (int c = 0; c < CG_MAXC; ++c) part[c] = 0.f;
+    for (int row = lo + tid; row < hi; row += CG_THREADS) {
+#pragma unroll
+      for (int c = 0; c < CG_MAXC; ++c)
+        if (c < nc) {
+          const int64_t o = (int64_t)row * nc + c;
+          const float p = __ldcg(Pg + o);
+          const float r = Rg[o] - a[c] * APg[o];
+          Xg[o] = fmaf(a[c], p, Xg[o]);
+          Rg[o] = r;
+          part[c] = fmaf(r, r, part[c]);
+        }
+    }
+    __syncthreads();  // AP (written by lane 0 of each warp) was read above by other threads
+    cg_allreduce(cluster, &ex, s_warp, part, nc, xcnt, tot);
+    float beta[CG_MAXC];
+    all_done = true;
+#pragma unroll
+    for (int c = 0; c < CG_MAXC; ++c) {
+      beta[c] = (!done[c] && rs[c] > 0.f) ? tot[c] / rs[c] : 0.f;
+      if (!done[c]) {
+        rs[c] = tot[c];
+        if (tot[c] <= tol2 * bb[c]) done[c] = true;
+      }
+      all_done = all_done && done[c];
+    }
+    // ---- P = R + beta P   (frozen for finished columns)
+    for (int row = lo + tid; row < hi; row += CG_THREADS) {
+#pragma unroll
+      for (int c = 0; c < CG_MAXC; ++c)
+        if (c < nc && !done[c]) {
+          const int64_t o = (int64_t)row * nc + c;
+          Pg[o] = fmaf(beta[c], __ldcg(Pg + o), Rg[o]);
+        }
+    }
+    ++it;
+    cluster.sync();  // publish P
+  }
+  if (rank == 0 && tid == 0) {
+    if (iters_out) iters_out[g] = it;
+    if (resid_out) {
+      float m = 0.f;
+      for (int c = 0; c < nc; ++c)
+        if (bb[c] > 0.f) m = fmaxf(m, sqrtf(rs[c] / bb[c]));
+      resid_out[g] = m;
+    }
+  }
+  cluster.sync();
+}
+
+// --------------------------------------------------------------------------------------------
+// Query rows of Z -> logits, argmax prediction (models/mpti_learner.py:98) and the mean
+// cross-entropy (models/mpti.py:571).  One CTA per episode, fixed-order reduction.
+// --------------------------------------------------------------------------------------------
+__global__ __launch_bounds__(1024) void query_head_kernel(const float* __restrict__ Z, int nn,
+                                                          int q_off, int nq, int nc,
+                                                          const int64_t* __restrict__ qy,
+                                                          float* __restrict__ logits,
+                                                          float* __restrict__ loss,
+                                                          int32_t* __restrict__ pred) {
+  __shared__ float s_red[32];
+  const int g = blockIdx.x, tid = threadIdx.x;
+  const float* Zg = Z + ((int64_t)g * nn + q_off) * nc;
+  float part = 0.f;
+  for (int i = tid; i < nq; i += 1024) {
+    float mx = -INFINITY;
+    int am = 0;
+    for (int c = 0; c < nc; ++c) {
+      const float v = Zg[(int64_t)i * nc + c];
+      logits[((int64_t)g * nq + i) * nc + c] = v;
+      if (v > mx) {
+        mx = v;
+        am = c;
+      }
+    }
+    if (pred) pred[(int64_t)g * nq + i] = am;
+    if (qy) {
+      float se = 0.f;
+      for (int c = 0; c < nc; ++c) se += expf(Zg[(int64_t)i * nc + c] - mx);
+      const int y = (int)qy[(int64_t)g * nq + i];
+      part += (mx + logf(se)) - Zg[(int64_t)i * nc + y];
+    }
+  }
+  part = warp_sum(part);
+  if ((tid & 31) == 0) s_red[tid >> 5] = part;
+  __syncthreads();
+  if (tid == 0 && loss) {
+    float s = 0.f;
+    for (int q = 0; q < 32; ++q) s += s_red[q];
+    loss[g] = qy ? s / (float)nq : 0.f;
+  }
+}
+
+// evaluate_metric counters (reference eval_noise.py:43-62)
+__global__ void confusion_kernel(const int32_t* __restrict__ pred, const int64_t* __restrict__ gt,
+                                 const int32_t* __restrict__ class_slot, int n_way,
+                                 int64_t pts_per_episode, int64_t total, int n_slots,
+                                 unsigned long long* __restrict__ counters) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= total) return;
+  const int64_t ep = e / pts_per_episode;
+  const int g = (int)gt[e], p = pred[e];
+  const int gi = g == 0 ? 0 : class_slot[ep * n_way + g - 1];
+  const int pi = p == 0 ? 0 : class_slot[ep * n_way + p - 1];
+  atomicAdd(&counters[gi], 1ull);
+  atomicAdd(&counters[n_slots + pi], 1ull);
+  if (g == p) atomicAdd(&counters[2 * n_slots + gi], 1ull);
+}
+
+// --------------------------------------------------------------------------------------------
+// launchers
+// --------------------------------------------------------------------------------------------
+int launch_affinity(const float* F, int64_t graph_rows, int64_t row_off, const uint8_t* valid,
+                    int G, int nn, int D, int k, float sigma, float* norms, float* D2, int32_t* nbr,
+                    float* sim, cudaStream_t st) {
+  if (D % 4 != 0 || D > 32 * LP_MAX_F4 || k > 1024 || nn > 65535) return R3DFS_E_UNSUPPORTED;
+  for (int g = 0; g < G; ++g)
+    R3DFS_TRY(launch_row_norms(F + ((int64_t)g * graph_rows + row_off) * D, nn, D, D,
+                               norms + (int64_t)g * nn, st));
+  dim3 gd((nn + GD_BM - 1) / GD_BM, (nn + GD_BN - 1) / GD_BN, G);
+  gram_dist_kernel<<<gd, 256, 0, st>>>(F, graph_rows, row_off, nn, D, norms, D2);
+  R3DFS_CHECK_LAUNCH();
+  size_t smem = sizeof(unsigned) * (size_t)nn;
+  cudaError_t e = cudaFuncSetAttribute(knn_select_kernel,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  knn_select_kernel<<<dim3(nn, G), SEL_THREADS, smem, st>>>(D2, valid, nn, k, nbr);
+  R3DFS_CHECK_LAUNCH();
+  edge_sim_kernel<<<dim3((nn + 7) / 8, G), 256, 0, st>>>(F, graph_rows, row_off, nn, D, valid, nbr,
+                                                        k, sigma, sim);
+  R3DFS_CHECK_LAUNCH();
+  return 0;
+}
+
+int launch_label_propagate(const int32_t* nbr, float* sim, const uint8_t* valid, int G, int nn,
+                           int k, const float* Y, int nc, float alpha, float tol, int max_iter,
+                           int32_t* in_cnt, int32_t* in_ptr, int32_t* in_src, float* in_w,
+                           float* dinv, float* X, float* R, float* P, float* AP, int32_t* iters_out,
+                           float* resid_out, cudaStream_t st) {
+  if (nc > CG_MAXC || nc < 1 || nn > 8192) return R3DFS_E_UNSUPPORTED;
+  cudaError_t e = cudaMemsetAsync(in_cnt, 0, sizeof(int32_t) * (size_t)G * nn, st);
+  if (e != cudaSuccess) return (int)e;
+  const int64_t edges = (int64_t)nn * k;
+  dim3 ge((unsigned)((edges + 255) / 256), G);
+  in_count_kernel<<<ge, 256, 0, st>>>(nbr, valid, nn, k, in_cnt);
+  R3DFS_CHECK_LAUNCH();
+  in_scan_kernel<<<G, 1024, 0, st>>>(in_cnt, nn, in_ptr);
+  R3DFS_CHECK_LAUNCH();
+  in_fill_kernel<<<ge, 256, 0, st>>>(nbr, sim, valid, nn, k, in_ptr, in_cnt, in_src, in_w);
+  R3DFS_CHECK_LAUNCH();
+  size_t smem = 8 * 8192;
+  e = cudaFuncSetAttribute(in_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  in_sort_kernel<<<dim3(nn, G), 256, smem, st>>>(in_ptr, nn, k, in_src, in_w);
+  R3DFS_CHECK_LAUNCH();
+  dim3 gr((nn + 7) / 8, G);
+  degree_kernel<<<gr, 256, 0, st>>>(sim, in_ptr, in_w, valid, nn, k, dinv);
+  R3DFS_CHECK_LAUNCH();
+  normalize_kernel<<<gr, 256, 0, st>>>(nbr, sim, in_ptr, in_src, in_w, valid, dinv, nn, k);
+  R3DFS_CHECK_LAUNCH();
+
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(CG_CL, G, 1);
+  cfg.blockDim = dim3(CG_THREADS, 1, 1);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG_CL;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  const float* simc = sim;
+  const int32_t* in_ptrc = in_ptr;
+  const int32_t* in_srcc = in_src;
+  const float* in_wc = in_w;
+  e = cudaLaunchKernelEx(&cfg, lp_cg_kernel, nbr, simc, in_ptrc, in_srcc, in_wc, valid, nn, k, Y,
+                         nc, alpha, tol, max_iter, X, R, P, AP, iters_out, resid_out);
+  if (e != cudaSuccess) return (int)e;
+  return 0;
+}
+
+int launch_query_head(const float* Z, int G, int nn, int q_off, int nq, int nc, const int64_t* qy,
+                      float* logits, float* loss, int32_t* pred, cudaStream_t st) {
+  query_head_kernel<<<G, 1024, 0, st>>>(Z, nn, q_off, nq, nc, qy, logits, loss, pred);
+  R3DFS_CHECK_LAUNCH();
+  return 0;
+}
+
+int launch_confusion(const int32_t* pred, const int64_t* gt, const int32_t* class_slot, int E,
+                     int n_way, int64_t pts, int n_slots, int64_t* counters, cudaStream_t st) {
+  const int64_t total = (int64_t)E * pts;
+  confusion_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
+      pred, gt, class_slot, n_way, pts, total, n_slots,
+      reinterpret_cast<unsigned long long*>(counters));
+  R3DFS_CHECK_LAUNCH();
+  return 0;
+}

@@ -1,0 +1,20 @@
+// internal launchers of proto.cu
+#pragma once
+#include "common.cuh"
+
+int launch_fps_ex(const float* feat, int D, const int32_t* set_off, const int32_t* set_n,
+                  int n_sets, int n_cap, int m_max, int k_for_count, int32_t* idx_out,
+                  int32_t* cnt_out, cudaStream_t st);
+int launch_multi_prototypes(const float* feat, int D, const int32_t* set_off,
+                            const int32_t* set_n, int n_sets, int n_cap, int k, int32_t* picks,
+                            int32_t* pick_cnt, int32_t* seeds, int32_t* proto_cnt,
+                            int32_t* assign, int sets_per_group, int64_t group_rows,
+                            float* proto_out, int ld_out, cudaStream_t st);
+int launch_set_compaction(const float* F, int64_t ep_rows, int64_t sup_row_off, int E, int n_way,
+                          int k_shot, int N, int D, const int32_t* sy, const int32_t* keep,
+                          int32_t* fg_cnt, int32_t* set_off, int32_t* set_n, int32_t* cloud_bg_off,
+                          int32_t* cloud_fg_off, float* setfeat, cudaStream_t st);
+int launch_mdns(const float* sx, int64_t s_e, int64_t s_cloud, int64_t s_c, int64_t s_n,
+                const int32_t* sy, const float* F, int64_t ep_rows, int64_t sup_row_off, int E,
+                int n_way, int k_shot, int N, int D, float* cell_mean, int32_t* cell_cnt,
+                int32_t* fg_cnt, int32_t* keep, float* clean_flag, cudaStream_t st);
