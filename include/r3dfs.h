@@ -215,6 +215,18 @@ int r3dfs_mpti_forward(const r3dfs_episode_cfg_t* h_cfg, const r3dfs_weights_t* 
                        const r3dfs_episode_diag_t* h_diag, void* ws, size_t ws_bytes,
                        r3dfs_stream_t stream);
 
+/* The same episode(s) from precomputed features: everything after getFeatures
+ * (models/mpti.py:440-571).  support_feat: (E, n_way*k_shot*N, 192) point-major rows in
+ * (way, shot, point) order; query_feat: (E, n_query*N, 192).  support_x is still needed for the
+ * xyz channels the noise suppression grids over (models/mpti.py:116).  Workspace and outputs as
+ * r3dfs_mpti_forward.  Used by the stage-wise parity tests and by callers that cache features. */
+int r3dfs_mpti_forward_features(const r3dfs_episode_cfg_t* h_cfg, int n_episodes,
+                                const float* support_x, int64_t s_e, int64_t s_cloud, int64_t s_c,
+                                int64_t s_n, const int32_t* support_y, const float* support_feat,
+                                const float* query_feat, const int64_t* query_y, float* logits,
+                                float* loss, int32_t* pred, const r3dfs_episode_diag_t* h_diag,
+                                void* ws, size_t ws_bytes, r3dfs_stream_t stream);
+
 /* evaluate_metric counters (reference eval_noise.py:35-62): for every query point, map the
  * episode-local label to its slot in the test-class list and accumulate gt / predicted /
  * true-positive counts.  class_slot: (E, n_way) int32 = test_classes.index(sampled_class) + 1.

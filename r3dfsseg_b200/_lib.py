@@ -76,6 +76,9 @@ SIGNATURES = {
                                      vp, i64, i64, i64, i64, vp,
                                      vp, i64, i64, i64, i64, vp,
                                      vp, vp, vp, C.POINTER(EpisodeDiag), vp, sz, vp]),
+    "r3dfs_mpti_forward_features": (C.c_int, [C.POINTER(EpisodeCfg), i32, vp, i64, i64, i64, i64, vp,
+                                              vp, vp, vp, vp, vp, vp, C.POINTER(EpisodeDiag), vp,
+                                              sz, vp]),
     "r3dfs_confusion_accumulate": (C.c_int, [vp, vp, vp, i32, i32, i64, i32, vp, vp]),
 }
 

@@ -489,6 +489,55 @@ size_t r3dfs_mpti_workspace(const r3dfs_episode_cfg_t* cfg, int n_episodes) {
   return ws.off + 4096;
 }
 
+// graph half of the episode: F already holds the query + support features (rows ppad.. of every
+// episode block); everything after getFeatures in models/mpti.py:440-571.
+static int episode_graph_half(const r3dfs_episode_cfg_t* cfg, const EpisodeDims& d, int E,
+                              const EpisodeWs& w, const float* support_x, int64_t s_e,
+                              int64_t s_cloud, int64_t s_c, int64_t s_n, const int32_t* support_y,
+                              const int64_t* query_y, float* logits, float* loss, int32_t* pred,
+                              const r3dfs_episode_diag_t* diag, cudaStream_t st) {
+  const int N = cfg->n_points, D = R3DFS_FEAT_DIM;
+  cudaError_t ce = cudaMemset2DAsync(w.F, sizeof(float) * d.ep_rows * D, 0,
+                                     sizeof(float) * (size_t)d.ppad * D, E, st);
+  if (ce != cudaSuccess) return (int)ce;
+  // noise suppression over support shots (eval only, models/mpti.py:440-442)
+  const int64_t sup_off = d.nn;
+  if (cfg->mdns) {
+    R3DFS_TRY(launch_mdns(support_x, s_e, s_cloud, s_c, s_n, support_y, w.F, d.ep_rows, sup_off, E,
+                          cfg->n_way, cfg->k_shot, N, D, w.cell_mean, w.cell_cnt, w.fg_cnt, w.keep,
+                          diag ? diag->clean_flag : nullptr, st));
+  } else {
+    fill_i32_kernel<<<nblk((int64_t)E * d.C), 256, 0, st>>>(w.keep, (int64_t)E * d.C, 1);
+    R3DFS_CHECK_LAUNCH();
+  }
+  // prototype sets -> FPS seeds -> assignment -> means, into the prototype slots of F
+  R3DFS_TRY(launch_set_compaction(w.F, d.ep_rows, sup_off, E, cfg->n_way, cfg->k_shot, N, D,
+                                  support_y, w.keep, w.fg_cnt, w.set_off, w.set_n, w.cloud_bg_off,
+                                  w.cloud_fg_off, w.setfeat, st));
+  R3DFS_TRY(launch_multi_prototypes(w.setfeat, D, w.set_off, w.set_n, E * d.S, d.ns_pts,
+                                    cfg->n_subprototypes, w.picks, w.pick_cnt, w.seeds,
+                                    w.proto_cnt, w.assign, d.S, d.ep_rows, w.F, D, st));
+  // graph: nodes = [prototype slots | query points]
+  graph_init_kernel<<<dim3(nblk(d.nn), E), 256, 0, st>>>(w.proto_cnt, d.S, d.slot, d.ppad, d.nn,
+                                                         d.nc, w.valid, w.Y);
+  R3DFS_CHECK_LAUNCH();
+  R3DFS_TRY(launch_affinity(w.F, d.ep_rows, 0, w.valid, E, d.nn, D, cfg->k_connect, cfg->sigma,
+                            w.norms, w.D2, w.nbr, w.sim, st));
+  R3DFS_TRY(launch_label_propagate(w.nbr, w.sim, w.valid, E, d.nn, cfg->k_connect, w.Y, d.nc,
+                                   cfg->alpha, cfg->cg_tol, cfg->cg_max_iter, w.in_cnt, w.in_ptr,
+                                   w.in_src, w.in_w, w.dinv, w.X, w.R, w.P, w.AP,
+                                   diag ? diag->cg_iters : nullptr,
+                                   diag ? diag->cg_resid : nullptr, st));
+  // query rows -> logits / loss / prediction
+  R3DFS_TRY(launch_query_head(w.X, E, d.nn, d.ppad, d.nq_pts, d.nc, query_y, logits, loss, pred, st));
+  if (diag && diag->proto_count) {
+    ce = cudaMemcpyAsync(diag->proto_count, w.proto_cnt, sizeof(int32_t) * (size_t)E * d.S,
+                         cudaMemcpyDeviceToDevice, st);
+    if (ce != cudaSuccess) return (int)ce;
+  }
+  return 0;
+}
+
 int r3dfs_mpti_forward(const r3dfs_episode_cfg_t* cfg, const r3dfs_weights_t* hw, int E,
                        const float* support_x, int64_t s_e, int64_t s_cloud, int64_t s_c,
                        int64_t s_n, const int32_t* support_y, const float* query_x, int64_t q_e,
@@ -502,66 +551,58 @@ int r3dfs_mpti_forward(const r3dfs_episode_cfg_t* cfg, const r3dfs_weights_t* hw
   if ((int64_t)E * d.cpe > 65535) return R3DFS_E_UNSUPPORTED;
   if (ws_bytes < r3dfs_mpti_workspace(cfg, E)) return R3DFS_E_WORKSPACE;
   cudaStream_t st = (cudaStream_t)stream;
-  const int N = cfg->n_points, D = R3DFS_FEAT_DIM, in_dim = hw->in_dim;
+  const int N = cfg->n_points, in_dim = hw->in_dim;
   WsBump ws(wsp, ws_bytes);
   EpisodeWs w;
   carve_episode(ws, cfg, d, E, in_dim, hw->dgcnn_k, w);
   if (!ws.ok()) return R3DFS_E_WORKSPACE;
   const int64_t B = (int64_t)E * d.cpe;
-
-  // 1. clouds -> point-major, episode-major order [queries | supports] (matches F's row layout)
-  {
-    int64_t tq = (int64_t)E * cfg->n_query * N * in_dim;
-    gather_clouds_kernel<<<nblk(tq), 256, 0, st>>>(query_x, cfg->n_query, in_dim, N, q_e, q_cloud,
-                                                   q_c, q_n, d.cpe, 0, w.xp, tq);
-    R3DFS_CHECK_LAUNCH();
-    int64_t tsup = (int64_t)E * d.C * N * in_dim;
-    gather_clouds_kernel<<<nblk(tsup), 256, 0, st>>>(support_x, d.C, in_dim, N, s_e, s_cloud, s_c,
-                                                     s_n, d.cpe, cfg->n_query, w.xp, tsup);
-    R3DFS_CHECK_LAUNCH();
-  }
-  // 2. features of every cloud (models/mpti.py:433-437), written straight into the node matrix
+  // clouds -> point-major, episode-major order [queries | supports] (matches F's row layout)
+  int64_t tq = (int64_t)E * cfg->n_query * N * in_dim;
+  gather_clouds_kernel<<<nblk(tq), 256, 0, st>>>(query_x, cfg->n_query, in_dim, N, q_e, q_cloud,
+                                                 q_c, q_n, d.cpe, 0, w.xp, tq);
+  R3DFS_CHECK_LAUNCH();
+  int64_t tsup = (int64_t)E * d.C * N * in_dim;
+  gather_clouds_kernel<<<nblk(tsup), 256, 0, st>>>(support_x, d.C, in_dim, N, s_e, s_cloud, s_c,
+                                                   s_n, d.cpe, cfg->n_query, w.xp, tsup);
+  R3DFS_CHECK_LAUNCH();
+  // features of every cloud (models/mpti.py:433-437), written straight into the node matrix
   RowMap fmap{d.cpe, N, d.ep_rows, (int64_t)d.ppad};
   R3DFS_TRY(encoder_forward(hw, w.xp, B, N, w.enc, w.F, fmap, nullptr, st));
-  cudaError_t ce = cudaMemset2DAsync(w.F, sizeof(float) * d.ep_rows * D, 0,
-                                     sizeof(float) * (size_t)d.ppad * D, E, st);
+  return episode_graph_half(cfg, d, E, w, support_x, s_e, s_cloud, s_c, s_n, support_y, query_y,
+                            logits, loss, pred, diag, st);
+}
+
+int r3dfs_mpti_forward_features(const r3dfs_episode_cfg_t* cfg, int E, const float* support_x,
+                                int64_t s_e, int64_t s_cloud, int64_t s_c, int64_t s_n,
+                                const int32_t* support_y, const float* support_feat,
+                                const float* query_feat, const int64_t* query_y, float* logits,
+                                float* loss, int32_t* pred, const r3dfs_episode_diag_t* diag,
+                                void* wsp, size_t ws_bytes, r3dfs_stream_t stream) {
+  EpisodeDims d;
+  R3DFS_TRY(episode_dims(cfg, d));
+  if (!support_x || !support_y || !support_feat || !query_feat || !logits || !wsp || E <= 0)
+    return R3DFS_E_BADARG;
+  if ((int64_t)E * d.cpe > 65535) return R3DFS_E_UNSUPPORTED;
+  if (ws_bytes < r3dfs_mpti_workspace(cfg, E)) return R3DFS_E_WORKSPACE;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int D = R3DFS_FEAT_DIM;
+  WsBump ws(wsp, ws_bytes);
+  EpisodeWs w;
+  carve_episode(ws, cfg, d, E, 64, 32, w);
+  if (!ws.ok()) return R3DFS_E_WORKSPACE;
+  const size_t pitch = sizeof(float) * d.ep_rows * D;
+  cudaError_t ce = cudaMemcpy2DAsync(w.F + (size_t)d.ppad * D, pitch, query_feat,
+                                     sizeof(float) * (size_t)d.nq_pts * D,
+                                     sizeof(float) * (size_t)d.nq_pts * D, E,
+                                     cudaMemcpyDeviceToDevice, st);
   if (ce != cudaSuccess) return (int)ce;
-  // 3. noise suppression over support shots (eval only, models/mpti.py:440-442)
-  const int64_t sup_off = d.nn;
-  if (cfg->mdns) {
-    R3DFS_TRY(launch_mdns(support_x, s_e, s_cloud, s_c, s_n, support_y, w.F, d.ep_rows, sup_off, E,
-                          cfg->n_way, cfg->k_shot, N, D, w.cell_mean, w.cell_cnt, w.fg_cnt, w.keep,
-                          diag ? diag->clean_flag : nullptr, st));
-  } else {
-    fill_i32_kernel<<<nblk((int64_t)E * d.C), 256, 0, st>>>(w.keep, (int64_t)E * d.C, 1);
-    R3DFS_CHECK_LAUNCH();
-  }
-  // 4. prototype sets -> FPS seeds -> assignment -> means, into the prototype slots of F
-  R3DFS_TRY(launch_set_compaction(w.F, d.ep_rows, sup_off, E, cfg->n_way, cfg->k_shot, N, D,
-                                  support_y, w.keep, w.fg_cnt, w.set_off, w.set_n, w.cloud_bg_off,
-                                  w.cloud_fg_off, w.setfeat, st));
-  R3DFS_TRY(launch_multi_prototypes(w.setfeat, D, w.set_off, w.set_n, E * d.S, d.ns_pts,
-                                    cfg->n_subprototypes, w.picks, w.pick_cnt, w.seeds,
-                                    w.proto_cnt, w.assign, d.S, d.ep_rows, w.F, D, st));
-  // 5. graph: nodes = [prototype slots | query points]
-  graph_init_kernel<<<dim3(nblk(d.nn), E), 256, 0, st>>>(w.proto_cnt, d.S, d.slot, d.ppad, d.nn,
-                                                         d.nc, w.valid, w.Y);
-  R3DFS_CHECK_LAUNCH();
-  R3DFS_TRY(launch_affinity(w.F, d.ep_rows, 0, w.valid, E, d.nn, D, cfg->k_connect, cfg->sigma,
-                            w.norms, w.D2, w.nbr, w.sim, st));
-  R3DFS_TRY(launch_label_propagate(w.nbr, w.sim, w.valid, E, d.nn, cfg->k_connect, w.Y, d.nc,
-                                   cfg->alpha, cfg->cg_tol, cfg->cg_max_iter, w.in_cnt, w.in_ptr,
-                                   w.in_src, w.in_w, w.dinv, w.X, w.R, w.P, w.AP,
-                                   diag ? diag->cg_iters : nullptr,
-                                   diag ? diag->cg_resid : nullptr, st));
-  // 6. query rows -> logits / loss / prediction
-  R3DFS_TRY(launch_query_head(w.X, E, d.nn, d.ppad, d.nq_pts, d.nc, query_y, logits, loss, pred, st));
-  if (diag && diag->proto_count) {
-    ce = cudaMemcpyAsync(diag->proto_count, w.proto_cnt, sizeof(int32_t) * (size_t)E * d.S,
-                         cudaMemcpyDeviceToDevice, st);
-    if (ce != cudaSuccess) return (int)ce;
-  }
-  return 0;
+  ce = cudaMemcpy2DAsync(w.F + (size_t)d.nn * D, pitch, support_feat,
+                         sizeof(float) * (size_t)d.ns_pts * D,
+                         sizeof(float) * (size_t)d.ns_pts * D, E, cudaMemcpyDeviceToDevice, st);
+  if (ce != cudaSuccess) return (int)ce;
+  return episode_graph_half(cfg, d, E, w, support_x, s_e, s_cloud, s_c, s_n, support_y, query_y,
+                            logits, loss, pred, diag, st);
 }
 
 }  // extern "C"

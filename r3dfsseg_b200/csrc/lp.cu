@@ -507,7 +507,10 @@ __global__ __launch_bounds__(CG_THREADS) void lp_cg_kernel(
 #pragma unroll
     for (int c = 0; c < CG_MAXC; ++c) part[c] = 0.f;
     for (int row = lo + w; row < hi; row += CG_THREADS / 32) {
-      if (!vg[row]) continue;  // warp-uniform
+      if (!vg[row]) {  // warp-uniform; keep AP defined for the vector updates below
+        if (lane < nc) APg[(int64_t)row * nc + lane] = 0.f;
+        continue;
+      }
       float acc[CG_MAXC];
 #pragma unroll
       for (int c = 0; c < CG_MAXC; ++c) acc[c] = 0.f;

@@ -95,14 +95,17 @@ class MPTI_SelfAtten(nn.Module):
 
     # ---------------------------------------------------------------------------------------
     def forward_episodes(self, support_x, support_y, query_x, query_y=None, eval=True,
-                         want_diag=False, workspace=None):
+                         want_diag=False, workspace=None, support_feat=None, query_feat=None):
         """Batch of E independent episodes (leading dim E on every tensor).
-        Returns dict(logits (E, n_query, N, n_way+1), loss (E), pred (E, n_query, N))."""
+        Returns dict(logits (E, n_query, N, n_way+1), loss (E), pred (E, n_query, N)).
+        With `support_feat` (E, n_way*k_shot*N, 192) / `query_feat` (E, n_query*N, 192) given,
+        the encoder is skipped and only the graph half runs on those features."""
         if self.training:
             raise NotImplementedError("r3dfsseg_b200: training path not built yet; call .eval()")
         cfg = self._cfg(query_x.shape[1], mdns=bool(eval))
         return ops.mpti_forward(self._weights(), cfg, support_x, support_y, query_x, query_y,
-                                want_diag=want_diag, workspace=workspace)
+                                want_diag=want_diag, workspace=workspace,
+                                support_feat=support_feat, query_feat=query_feat)
 
     def forward(self, support_x, support_y, query_x, query_y, gt_support_y=None, gt_query_y=None,
                 train=False, logger=None, step=None, path=None, sampled_classes=None,

@@ -314,9 +314,11 @@ def make_cfg(n_way: int, k_shot: int, n_query: int, n_points: int, n_subprototyp
                       float(alpha), int(bool(mdns)), int(cg_max_iter), float(cg_tol))
 
 
-def mpti_forward(pw: PackedWeights, cfg: EpisodeCfg, support_x: torch.Tensor,
+def mpti_forward(pw: Optional[PackedWeights], cfg: EpisodeCfg, support_x: torch.Tensor,
                  support_y: torch.Tensor, query_x: torch.Tensor, query_y: Optional[torch.Tensor],
-                 want_diag: bool = False, workspace: Optional[torch.Tensor] = None):
+                 want_diag: bool = False, workspace: Optional[torch.Tensor] = None,
+                 support_feat: Optional[torch.Tensor] = None,
+                 query_feat: Optional[torch.Tensor] = None):
     """E episodes in one call.
     support_x (E, n_way, k_shot, C, N) any strides with uniform cloud stride; support_y
     (E, n_way, k_shot, N) int32; query_x (E, n_query, C, N); query_y (E, n_query, N) int64.
@@ -352,6 +354,23 @@ def mpti_forward(pw: PackedWeights, cfg: EpisodeCfg, support_x: torch.Tensor,
         }
         dstruct = EpisodeDiag(diag["proto_count"].data_ptr(), diag["clean_flag"].data_ptr(),
                               diag["cg_iters"].data_ptr(), diag["cg_resid"].data_ptr())
+    if support_feat is not None:
+        # precomputed features (point-major (E, rows, 192)): graph half only
+        support_feat = _f32(support_feat).contiguous()
+        query_feat = _f32(query_feat).contiguous()
+        assert support_feat.shape == (E, n_way * k_shot * N, 192)
+        assert query_feat.shape == (E, nq * N, 192)
+        with torch.cuda.device(dev):
+            check(L.r3dfs_mpti_forward_features(
+                C.byref(cfg), E, _p(support_x), support_x.stride(0), support_x.stride(2),
+                support_x.stride(3), support_x.stride(4), _p(support_y), _p(support_feat),
+                _p(query_feat), _p(query_y), _p(logits), _p(loss), _p(pred),
+                C.byref(dstruct) if dstruct is not None else None, _p(ws), ws.numel(), _stream()),
+                "r3dfs_mpti_forward_features")
+        out = {"logits": logits, "loss": loss, "pred": pred}
+        if diag is not None:
+            out["diag"] = diag
+        return out
     with torch.cuda.device(dev):
         check(L.r3dfs_mpti_forward(
             C.byref(cfg), C.byref(pw.struct), E,

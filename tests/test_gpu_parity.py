@@ -1,0 +1,464 @@
+"""GPU parity: the CUDA path (through the C ABI, via r3dfsseg_b200.ops / models) against the CPU
+oracle on the same seeded inputs and against the committed reference goldens.
+Tolerances follow BASELINE.json's north_star: FPS indices identical (ties adjudicated in fp64),
+kNN indices identical except at tied distances, logits within 1e-3 relative, labels >= 99.9 %."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import mpti_oracle as O
+from r3dfsseg_b200.episodes import default_args, make_episode
+from tests.helpers import knn_sets_match
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda:0"
+
+
+@pytest.fixture(scope="module")
+def model(fixture_sd):
+    from r3dfsseg_b200.models import MPTI_SelfAtten
+    ms = {}
+
+    def get(n_way, k_shot):
+        key = (n_way, k_shot)
+        if key not in ms:
+            m = MPTI_SelfAtten(default_args(n_way, k_shot))
+            m.load_state_dict(fixture_sd)
+            ms[key] = m.to(DEV).eval()
+        return ms[key]
+    return get
+
+
+def test_library_loaded():
+    from r3dfsseg_b200 import _lib
+    assert _lib.lib().r3dfs_version() == 100
+
+
+def test_cpu_tensor_is_rejected():
+    from r3dfsseg_b200 import ops
+    with pytest.raises(RuntimeError):
+        ops.knn(torch.rand(1, 9, 64), 4)
+
+
+# ---------------------------------------------------------------------------------------------
+# A1 knn
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("key", ["x9", "x64"])
+def test_knn_golden(golden_dgcnn, key):
+    from r3dfsseg_b200 import ops
+    x = golden_dgcnn[key]
+    idx = ops.knn(x.to(DEV), 20).cpu()
+    assert idx.dtype == torch.int64 and idx.shape == (2, 256, 20)
+    ok, bad = knn_sets_match(idx, golden_dgcnn["knn_" + key], O.knn_scores(x), largest=True)
+    assert ok, f"{bad} rows differ beyond ties"
+    assert (idx[:, :, 0] == torch.arange(256)).all()  # self first
+
+
+@pytest.mark.parametrize("C,N,k", [(9, 2048, 20), (64, 2048, 20), (3, 100, 5), (130, 333, 32)])
+def test_knn_random(C, N, k):
+    from r3dfsseg_b200 import ops
+    g = torch.Generator().manual_seed(C * 1000 + N)
+    x = torch.randn((3, C, N), generator=g) if C != 9 else torch.rand((3, C, N), generator=g)
+    idx = ops.knn(x.to(DEV), k).cpu()
+    ok, bad = knn_sets_match(idx, O.knn(x, k), O.knn_scores(x), largest=True)
+    assert ok, f"{bad} rows differ beyond ties"
+    # sorted nearest-first (up to ties)
+    sc = O.knn_scores(x).gather(2, idx)
+    assert (sc[:, :, :-1] - sc[:, :, 1:] >= -1e-5 * sc.abs().clamp(min=1)[:, :, 1:]).all()
+
+
+def test_knn_point_major_strides():
+    """The reference hands over a transposed view of point-major memory (loader.py:1666)."""
+    from r3dfsseg_b200 import ops
+    g = torch.Generator().manual_seed(5)
+    pm = torch.rand((2, 512, 9), generator=g)
+    x = pm.transpose(1, 2)
+    assert not x.is_contiguous()
+    a = ops.knn(x.to(DEV), 20).cpu()           # .to keeps the strides
+    b = ops.knn(x.contiguous().to(DEV), 20).cpu()
+    assert torch.equal(a, b)
+
+
+# ---------------------------------------------------------------------------------------------
+# A2 get_edge_feature
+# ---------------------------------------------------------------------------------------------
+def test_edge_feature_exact(golden_dgcnn):
+    from r3dfsseg_b200 import ops
+    x, idx = golden_dgcnn["x9"], golden_dgcnn["knn_x9"]
+    e = ops.get_edge_feature(x.to(DEV), 20, idx.to(DEV)).cpu()
+    assert torch.equal(e, golden_dgcnn["edge_x9"])
+    assert ops.get_graph_feature is ops.get_edge_feature
+
+
+def test_edge_feature_odd_shapes():
+    from r3dfsseg_b200 import ops
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn((2, 5, 77), generator=g)
+    idx = torch.randint(0, 77, (2, 77, 7), generator=g)
+    e = ops.get_edge_feature(x.to(DEV), 7, idx.to(DEV)).cpu()
+    assert torch.equal(e, O.get_edge_feature(x, 7, idx))
+
+
+# ---------------------------------------------------------------------------------------------
+# A3/A4 EdgeConv block, DGCNN, getFeatures
+# ---------------------------------------------------------------------------------------------
+def _rows_equal_knn(x_cpu, k=20):
+    """mask (B, N) of points whose CUDA and oracle neighbour SETS coincide; the others must be
+    adjudicated ties (checked by the knn tests), and EdgeConv outputs may differ there."""
+    from r3dfsseg_b200 import ops
+    a = ops.knn(x_cpu.to(DEV), k).cpu().sort(-1)[0]
+    b = O.knn(x_cpu, k).sort(-1)[0]
+    return (a == b).all(-1)
+
+
+def test_dgcnn_golden_first_level(golden_dgcnn, model):
+    """DGCNN.forward outputs vs the reference golden.  Level 1 is compared strictly.  Level 2 sits
+    behind two DYNAMIC graphs: a neighbour tie broken differently (fp32 summation order) changes a
+    few points' features, so it is compared statistically here and strictly in the teacher-forced
+    block tests below."""
+    m = model(2, 5)
+    l1, l2 = m.encoder(golden_dgcnn["dgcnn_x"].to(DEV))
+    assert l1.shape == (2, 64, 512) and l2.shape == (2, 256, 512)
+    ref1, ref2 = golden_dgcnn["dgcnn_l1"], golden_dgcnn["dgcnn_l2"]
+    assert (l1.cpu() - ref1).abs().max() / ref1.abs().max() < 1e-5
+    e2 = (l2.cpu() - ref2).abs().amax(1) / ref2.abs().max()
+    assert e2.median() < 1e-5 and (e2 > 1e-4).float().mean() < 0.10, (e2.median(), e2.max())
+
+
+@pytest.mark.parametrize("blk", [0, 1, 2])
+def test_edgeconv_blocks_teacher_forced(golden_dgcnn, fixture_sd, model, blk):
+    """Each EdgeConv block on the ORACLE's input for that block: wherever the neighbour sets
+    coincide the outputs must agree to fp32 rounding."""
+    from r3dfsseg_b200 import ops
+    x = golden_dgcnn["dgcnn_x"]
+    for i in range(blk):
+        x = O.edgeconv_block(x, fixture_sd, f"encoder.edge_convs.{i}", 20)
+    ref = O.edgeconv_block(x, fixture_sd, f"encoder.edge_convs.{blk}", 20)
+    same = _rows_equal_knn(x)
+    assert same.float().mean() > 0.99
+    stages = model(2, 5).encoder.edge_convs[blk]._stages()
+    (c1, b1, _), (c2, b2, _) = stages
+    s1, t1 = ops.fold_bn(b1)
+    s2, t2 = ops.fold_bn(b2)
+    y = ops.edgeconv(x.to(DEV), c1.weight, s1, t1, c2.weight, s2, t2, 20).cpu()
+    err = ((y - ref).abs().amax(1) / ref.abs().max())[same]
+    assert err.max() < 1e-5, err.max()
+
+
+def test_point_mlp_base_attention_teacher_forced(fixture_sd, model):
+    """Everything after the EdgeConv stack on the oracle's concatenated EdgeConv outputs."""
+    ep = make_episode(5, 2, 1)
+    x, outs = ep.query_x, []
+    for i in range(3):
+        x = O.edgeconv_block(x, fixture_sd, f"encoder.edge_convs.{i}", 20)
+        outs.append(x)
+    cat = torch.cat(outs, 1)
+    _, l2_ref = O.dgcnn_forward(ep.query_x, fixture_sd)
+    m = model(2, 1)
+    l2 = m.encoder.conv(cat.to(DEV))
+    assert (l2.cpu() - l2_ref).abs().max() / l2_ref.abs().max() < 1e-5
+    base = m.base_learner(l2_ref.to(DEV)).cpu()
+    att = m.att_learner(l2_ref.to(DEV)).cpu()
+    rb, ra = O.base_learner(l2_ref, fixture_sd), O.self_attention(l2_ref, fixture_sd)
+    assert (base - rb).abs().max() / rb.abs().max() < 1e-5
+    assert (att - ra).abs().max() / ra.abs().max() < 2e-5
+
+
+def test_edgeconv_block_vs_oracle(fixture_sd):
+    from r3dfsseg_b200 import ops
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn((2, 64, 1024), generator=g)
+    p = "encoder.edge_convs.1"
+    ref = O.edgeconv_block(x, fixture_sd, p, 20)
+
+    class BN:
+        pass
+    def fold(pref):
+        bn = BN()
+        s = fixture_sd[pref + ".weight"] / torch.sqrt(fixture_sd[pref + ".running_var"] + 1e-5)
+        return s.to(DEV), (fixture_sd[pref + ".bias"] - fixture_sd[pref + ".running_mean"] * s).to(DEV)
+    s1, t1 = fold(p + ".layer.1")
+    s2, t2 = fold(p + ".layer.4")
+    y = ops.edgeconv(x.to(DEV), fixture_sd[p + ".layer.0.weight"].to(DEV), s1, t1,
+                     fixture_sd[p + ".layer.3.weight"].to(DEV), s2, t2, 20).cpu()
+    err = (y - ref).abs().max() / ref.abs().max()
+    assert err < 1e-4, err
+
+
+def test_features_vs_oracle(fixture_sd, model):
+    """getFeatures end to end.  Level 1 (one static graph) is strict except at tied neighbours;
+    the attention / base groups sit behind the dynamic graphs (see above) -> statistical."""
+    ep = make_episode(5, 2, 1)
+    x = ep.query_x
+    ref = O.get_features(x, fixture_sd)
+    got = model(2, 1).getFeatures(x.to(DEV)).cpu()
+    assert got.shape == ref.shape == (2, 192, 2048)
+    same = _rows_equal_knn(x)
+    e1 = (got[:, :64] - ref[:, :64]).abs().amax(1) / ref[:, :64].abs().max()
+    assert same.float().mean() > 0.995 and e1[same].max() < 1e-5
+    for lo, hi in ((64, 128), (128, 192)):
+        e = (got[:, lo:hi] - ref[:, lo:hi]).abs().amax(1) / ref[:, lo:hi].abs().max()
+        assert e.median() < 2e-5, (lo, e.median())
+
+
+def test_attention_module_vs_oracle(fixture_sd, model):
+    g = torch.Generator().manual_seed(9)
+    x = torch.randn((2, 256, 777), generator=g) * 0.5
+    ref = O.self_attention(x, fixture_sd)
+    got = model(2, 1).att_learner(x.to(DEV)).cpu()
+    err = (got - ref).abs().max() / ref.abs().max()
+    assert err < 1e-4, err
+
+
+def test_training_mode_fails_loudly(model):
+    m = model(2, 1)
+    m.train()
+    try:
+        with pytest.raises(NotImplementedError):
+            m.getFeatures(torch.rand(1, 9, 2048, device=DEV))
+    finally:
+        m.eval()
+
+
+# ---------------------------------------------------------------------------------------------
+# A11 FPS / multi-prototypes
+# ---------------------------------------------------------------------------------------------
+def _fps_adjudicate(feat, got, ref):
+    """Identical sequences, or the first divergence is a tie within 4 ulp(fp32) in fp64."""
+    got, ref = got.tolist(), ref.tolist()
+    if got == ref:
+        return True, -1
+    i = next(j for j in range(len(ref)) if got[j] != ref[j])
+    f = feat.double()
+    dist = torch.full((f.shape[0],), float("inf"), dtype=torch.float64)
+    for s in ref[:i]:
+        dist = torch.minimum(dist, (f - f[s]).pow(2).sum(1))
+    a, b = float(dist[got[i]]), float(dist[ref[i]])
+    return abs(a - b) <= 4 * np.spacing(np.float32(max(a, b))), i
+
+
+@pytest.mark.parametrize("n,D,m", [(3000, 192, 100), (15000, 192, 101), (257, 192, 50), (64, 16, 64)])
+def test_fps_sequence(n, D, m):
+    from r3dfsseg_b200 import ops
+    g = torch.Generator().manual_seed(n)
+    feat = torch.randn((n, D), generator=g) * 0.2
+    got = ops.fps(feat.to(DEV), torch.tensor([0], device=DEV), torch.tensor([n], device=DEV), m).cpu()[0]
+    ref = O.fps(feat, m)
+    ok, where = _fps_adjudicate(feat, got.long(), ref)
+    assert ok, f"FPS diverges at pick {where} beyond a tie"
+
+
+def test_fps_many_sets_and_prefix_property():
+    from r3dfsseg_b200 import ops
+    g = torch.Generator().manual_seed(21)
+    sizes = [500, 1, 37, 4096, 130]
+    feat = torch.randn((sum(sizes), 192), generator=g)
+    off = torch.tensor([0] + list(np.cumsum(sizes)[:-1]), dtype=torch.int32)
+    n = torch.tensor(sizes, dtype=torch.int32)
+    a = ops.fps(feat.to(DEV), off.to(DEV), n.to(DEV), 64).cpu()
+    b = ops.fps(feat.to(DEV), off.to(DEV), n.to(DEV), 32).cpu()
+    for s, sz in enumerate(sizes):
+        cnt = min(64, sz)
+        ref = O.fps(feat[off[s]:off[s] + sz], cnt)
+        ok, where = _fps_adjudicate(feat[off[s]:off[s] + sz], a[s, :cnt].long(), ref)
+        assert ok, (s, where)
+        assert torch.equal(a[s, :min(32, sz)], b[s, :min(32, sz)])  # prefix property
+
+
+def test_multi_prototypes_vs_oracle():
+    from r3dfsseg_b200 import ops
+    g = torch.Generator().manual_seed(4)
+    sizes = [2500, 60, 9000]
+    feat = torch.randn((sum(sizes), 192), generator=g) * 0.2
+    off = torch.tensor([0, 2500, 2560], dtype=torch.int32)
+    n = torch.tensor(sizes, dtype=torch.int32)
+    proto, cnt, assign, seeds = ops.multi_prototypes(feat.to(DEV), off.to(DEV), n.to(DEV), 100)
+    proto, cnt, assign, seeds = proto.cpu(), cnt.cpu(), assign.cpu(), seeds.cpu()
+    for s, sz in enumerate(sizes):
+        f = feat[off[s]:off[s] + sz]
+        p_ref, a_ref, m_ref, s_ref = O.multi_prototypes(f, 100)
+        assert int(cnt[s]) == m_ref
+        assert torch.equal(seeds[s, :m_ref].long(), s_ref)
+        a_got = assign[off[s]:off[s] + sz].long()
+        mism = (a_got != a_ref).float().mean()
+        assert mism < 1e-3, mism  # argmin ties only
+        if mism == 0:
+            err = (proto[s, :m_ref] - p_ref).abs().max() / p_ref.abs().max()
+            assert err < 1e-5, err
+
+
+# ---------------------------------------------------------------------------------------------
+# A13/A14 affinity graph + label propagation
+# ---------------------------------------------------------------------------------------------
+def _random_graph_inputs(n=1500, D=192, seed=0, n_invalid=7):
+    g = torch.Generator().manual_seed(seed)
+    centers = torch.randn((6, D), generator=g) * 0.15
+    feat = centers[torch.randint(0, 6, (n,), generator=g)] + torch.randn((n, D), generator=g) * 0.06
+    valid = torch.ones(n, dtype=torch.uint8)
+    valid[torch.randperm(n, generator=g)[:n_invalid]] = 0
+    return feat, valid
+
+
+def test_affinity_knn_vs_oracle():
+    from r3dfsseg_b200 import ops
+    feat, valid = _random_graph_inputs()
+    k = 200
+    nbr, sim = ops.affinity_knn(feat[None].to(DEV), valid[None].to(DEV), k, 1.0)
+    nbr, sim = nbr.cpu()[0], sim.cpu()[0]
+    vi = torch.nonzero(valid).flatten()
+    sub = feat[vi]
+    I_ref, d2 = O.knn_graph_exact(sub, k)
+    _, _, sim_ref = O.affinity_dense(sub, k, 1.0, I_ref)
+    # map local (valid-only) indices back
+    I_ref_g = vi[I_ref]
+    d2_full = torch.full((feat.shape[0], feat.shape[0]), float("inf"), dtype=torch.float64)
+    d2_full[vi[:, None], vi[None, :]] = d2
+    ok, bad = knn_sets_match(nbr[vi], I_ref_g, d2_full[vi], largest=False)
+    assert ok, f"{bad} rows differ beyond ties"
+    assert (nbr[vi] != vi[:, None]).all()          # no self edges
+    assert valid[nbr[vi].long()].all()             # only valid neighbours
+    # similarity values: compare per (row, neighbour) through a dense scatter
+    n = feat.shape[0]
+    A_got = torch.zeros((n, n)).index_put_((vi[:, None].expand(-1, k), nbr[vi].long()), sim[vi])
+    A_ref = torch.zeros((n, n)).index_put_((vi[:, None].expand(-1, k), I_ref_g), sim_ref)
+    both = (A_got > 0) & (A_ref > 0)
+    assert both.float().sum() > 0.999 * (A_ref > 0).float().sum()
+    assert torch.allclose(A_got[both], A_ref[both], rtol=1e-5, atol=1e-7)
+
+
+def test_label_propagate_vs_dense_solve():
+    """CG on the sparse graph cross-checked against a dense fp64 solve (Cholesky-grade answer)
+    and the reference's fp32 dense inverse."""
+    from r3dfsseg_b200 import ops
+    feat, valid = _random_graph_inputs(n=1200, seed=1, n_invalid=5)
+    k, nc = 200, 3
+    vi = torch.nonzero(valid).flatten()
+    n = feat.shape[0]
+    g = torch.Generator().manual_seed(2)
+    Y = torch.zeros((n, nc))
+    lab = torch.randint(0, nc, (150,), generator=g)
+    Y[vi[:150], lab] = 1.0
+    nbr, sim = ops.affinity_knn(feat[None].to(DEV), valid[None].to(DEV), k, 1.0)
+    Z, iters, resid = ops.label_propagate(nbr, sim, valid[None].to(DEV), Y[None].to(DEV))
+    Z = Z.cpu()[0]
+    assert 5 < int(iters[0]) < 200 and float(resid[0]) <= 1.1e-6
+    # dense system from the SAME sparse graph
+    nbr_c, sim_c = nbr.cpu()[0].long(), sim.cpu()[0]
+    A = torch.zeros((n, n), dtype=torch.float64)
+    A.index_put_((vi[:, None].expand(-1, k), nbr_c[vi]), sim_c[vi].double())
+    A = A + A.t()
+    A.fill_diagonal_(0)
+    Z64 = O.label_propagate_dense(A[vi][:, vi], Y[vi], dtype=torch.float64)
+    Z32 = O.label_propagate_dense(A[vi][:, vi].float(), Y[vi], dtype=torch.float32)
+    scale = Z64.abs().max()
+    err_cg = (Z[vi].double() - Z64).abs().max() / scale
+    err_ref = (Z32.double() - Z64).abs().max() / scale
+    assert err_cg < 1e-4, (err_cg, err_ref)
+    assert (Z[vi].argmax(1) == Z64.argmax(1)).float().mean() > 0.999
+    assert (Z[valid == 0] == 0).all()
+
+
+# ---------------------------------------------------------------------------------------------
+# whole episodes
+# ---------------------------------------------------------------------------------------------
+EPISODES = ["s3dis_2way_1shot", "s3dis_2way_5shot_mdns", "s3dis_2way_5shot_noisy_mdns",
+            "scannet_3way_5shot_ood_mdns"]
+
+
+def _oracle_features(sd, ep, n_way, k_shot):
+    """Oracle features as point-major rows: support (C*N, 192) in (way, shot, point) order,
+    query (n_query*N, 192)."""
+    with torch.no_grad():
+        sf = O.get_features(ep.support_x.reshape(n_way * k_shot, 9, -1), sd)
+        qf = O.get_features(ep.query_x, sd)
+    return (sf.transpose(1, 2).reshape(1, -1, 192).contiguous(),
+            qf.transpose(1, 2).reshape(1, -1, 192).contiguous())
+
+
+@pytest.mark.parametrize("name", EPISODES)
+def test_episode_graph_half_golden(golden_episodes, fixture_sd, model, name):
+    """Strict parity of everything after getFeatures (noise suppression, FPS multi-prototypes,
+    affinity graph, label propagation, loss) against the REFERENCE's golden output, fed with the
+    oracle's features so that the comparison is not blurred by the encoder's tie-sensitive graphs:
+    logits within 1e-3 relative, labels >= 99.9 % identical, clean flags and prototype count exact."""
+    c = golden_episodes[name]
+    n_way, k_shot = c["n_way"], c["k_shot"]
+    ep = make_episode(c["seed"], n_way, k_shot, dataset=c["dataset"], noise_ratio=c["noise_ratio"])
+    sf, qf = _oracle_features(fixture_sd, ep, n_way, k_shot)
+    m = model(n_way, k_shot)
+    out = m.forward_episodes(ep.support_x.to(DEV)[None], ep.support_y.to(DEV)[None],
+                             ep.query_x.to(DEV)[None], ep.query_y.to(DEV)[None], eval=c["eval"],
+                             want_diag=True, support_feat=sf.to(DEV), query_feat=qf.to(DEV))
+    ref = c["query_pred"]
+    pred = out["logits"][0].transpose(1, 2).cpu()
+    assert int(out["diag"]["proto_count"][0].sum()) == c["num_prototypes"]
+    if c["eval"]:
+        assert torch.equal(out["diag"]["clean_flag"][0].cpu(), c["clean_flag"])
+    err = (pred - ref).abs().max() / ref.abs().max()
+    agree = (pred.argmax(1) == ref.argmax(1)).float().mean()
+    assert err < 1e-3, (err, agree)
+    assert agree >= 0.999, (err, agree)
+    assert abs(float(out["loss"][0]) - float(c["loss"])) < 1e-4
+    assert int(out["diag"]["cg_iters"][0]) < 200 and float(out["diag"]["cg_resid"][0]) <= 1.1e-6
+
+
+@pytest.mark.parametrize("name", EPISODES)
+def test_episode_end_to_end_golden(golden_episodes, model, name):
+    """The drop-in forward() from raw clouds against the reference golden.  The three dynamic kNN
+    graphs of DGCNN break fp32 ties by summation order, which the reference itself does not pin,
+    so a handful of points legitimately differ (and FPS, being chaotic, then picks different seeds):
+    labels must agree on >= 99.9 % of the points, >= 90 % of the logits must be within 1e-3
+    relative and the median logit error must be below 1e-4.  The strict 1e-3 bound is enforced on
+    the graph half above and on each encoder block (teacher-forced tests)."""
+    c = golden_episodes[name]
+    ep = make_episode(c["seed"], c["n_way"], c["k_shot"], dataset=c["dataset"],
+                      noise_ratio=c["noise_ratio"])
+    m = model(c["n_way"], c["k_shot"])
+    pred, loss = m(ep.support_x.to(DEV), ep.support_y.to(DEV), ep.query_x.to(DEV),
+                   ep.query_y.to(DEV), gt_support_y=ep.gt_support_y.to(DEV), eval=c["eval"])
+    ref = c["query_pred"]
+    assert pred.shape == ref.shape and not pred.is_contiguous()
+    assert abs(m.num_prototypes - c["num_prototypes"]) <= 1
+    pred = pred.cpu()
+    rel = (pred - ref).abs() / ref.abs().max()
+    agree = (pred.argmax(1) == ref.argmax(1)).float().mean()
+    assert agree >= 0.999, (rel.max(), agree)
+    assert (rel < 1e-3).float().mean() >= 0.90, ((rel < 1e-3).float().mean(), rel.max())
+    assert rel.median() < 1e-4 and rel.max() < 0.1, (rel.median(), rel.max())
+    assert abs(float(loss) - float(c["loss"])) < 2e-3
+    assert int(m._last_diag["cg_iters"][0]) < 200
+
+
+def test_episode_batch_equals_single_and_is_deterministic(model):
+    m = model(2, 5)
+    eps = [make_episode(s, 2, 5, noise_ratio=0.4 if s % 2 else 0.0) for s in (11, 12, 13)]
+    sx = torch.stack([e.support_x.transpose(2, 3) for e in eps]).to(DEV).transpose(3, 4)
+    sy = torch.stack([e.support_y for e in eps]).to(DEV)
+    qx = torch.stack([e.query_x.transpose(1, 2) for e in eps]).to(DEV).transpose(2, 3)
+    qy = torch.stack([e.query_y for e in eps]).to(DEV)
+    a = m.forward_episodes(sx, sy, qx, qy, eval=True)
+    b = m.forward_episodes(sx, sy, qx, qy, eval=True)
+    assert torch.equal(a["logits"], b["logits"]) and torch.equal(a["loss"], b["loss"])
+    for i, e in enumerate(eps):
+        pred, loss = m(e.support_x.to(DEV), e.support_y.to(DEV), e.query_x.to(DEV),
+                       e.query_y.to(DEV), eval=True)
+        assert torch.equal(pred, a["logits"][i].transpose(1, 2))
+        assert torch.equal(loss, a["loss"][i])
+
+
+def test_confusion_counters_vs_oracle():
+    from r3dfsseg_b200 import ops
+    g = torch.Generator().manual_seed(0)
+    E, n_way, P = 5, 2, 4096
+    test_classes = [3, 11, 10, 0, 8, 4]
+    pred = torch.randint(0, n_way + 1, (E, P), generator=g, dtype=torch.int32)
+    gt = torch.randint(0, n_way + 1, (E, P), generator=g)
+    sampled = [np.array(test_classes)[torch.randperm(6, generator=g)[:n_way].numpy()] for _ in range(E)]
+    slot = torch.tensor([[test_classes.index(int(c)) + 1 for c in s] for s in sampled], dtype=torch.int32)
+    counters = torch.zeros((3, 7), dtype=torch.int64, device=DEV)
+    ops.confusion_accumulate(pred.to(DEV), gt.to(DEV), slot.to(DEV), counters)
+    ref = O.confusion_counts([p.numpy() for p in pred], [q.numpy() for q in gt], sampled, test_classes)
+    assert np.array_equal(counters.cpu().numpy(), ref)
