@@ -1,0 +1,444 @@
+#!/usr/bin/env python
+"""bench.py — MPTI episodes/s (2-way 5-shot, 2048 pts) on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+A "step" = one pass of the episode hot path over one batch of `--episodes` (default 100) synthetic
+S3DIS-shape 2-way 5-shot episodes (BASELINE.json configs[2]), fed to the C ABI in chunks of
+`--chunk` episodes per call.  Episodes are independent: with N ranks every rank runs its own 100
+episodes per step (weak scaling) and the only collective is the NCCL sum of the confusion counters.
+
+One JSON line on stdout (rank 0):
+  value      episodes/s with the inputs already resident in HBM (device-timed, max over ranks)
+  e2e        the same through the public module API from pinned HOST buffers, H2D + D2H in the
+             timed region
+  roofline   the dominant kernel stage: algorithmic FLOPs (or bytes) per launch / CUDA-event time
+  cpu_baseline  the CPU oracle (restatement of the reference's path) on this box's host cores
+`--impl reference` times that CPU path alone (the reference is Python: oracle/mpti_oracle.py is
+its restatement; the reference tree itself cannot travel to the GPU box).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+N_WAY, K_SHOT, N_QUERY, N_PTS = 2, 5, 2, 2048
+METRIC = "MPTI episodes/s (2-way 5-shot, 2048 pts)"
+UNIT = "episodes/s"
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"],
+                "bf16_tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0,
+            "source": "fallback"}
+
+
+# ------------------------------------------------------------------------------------------------
+# synthetic episodes
+# ------------------------------------------------------------------------------------------------
+def build_host_batch(n_episodes: int, seed0: int):
+    """Pinned host tensors laid out like the reference's collate output, batched:
+    support (E, n_way, k_shot, N, 9) point-major, masks int32, query (E, n_q, N, 9), labels int64."""
+    from r3dfsseg_b200.episodes import make_episode
+    sx = torch.empty((n_episodes, N_WAY, K_SHOT, N_PTS, 9), dtype=torch.float32).pin_memory()
+    sy = torch.empty((n_episodes, N_WAY, K_SHOT, N_PTS), dtype=torch.int32).pin_memory()
+    qx = torch.empty((n_episodes, N_QUERY, N_PTS, 9), dtype=torch.float32).pin_memory()
+    qy = torch.empty((n_episodes, N_QUERY, N_PTS), dtype=torch.int64).pin_memory()
+    classes = np.zeros((n_episodes, N_WAY), dtype=np.int32)
+    for i in range(n_episodes):
+        ep = make_episode(seed0 + i, N_WAY, K_SHOT)
+        sx[i] = ep.support_x.transpose(2, 3)
+        sy[i] = ep.support_y
+        qx[i] = ep.query_x.transpose(1, 2)
+        qy[i] = ep.query_y
+        classes[i] = ep.sampled_classes
+    return sx, sy, qx, qy, classes
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampler (nvidia-smi during the timed region)
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.samples = []
+        self.proc = None
+        self.thread = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
+                 str(self.index), "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL,
+                text=True)
+        except OSError:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._read, daemon=True)
+        self.thread.start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) >= 7:
+                self.samples.append(parts)
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for p in self.samples:
+            try:
+                sm.append(float(p[0]))
+                mx.append(float(p[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
+                                "sw_power_cap"), p[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": float(max(mx)) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU path (oracle = restatement of the reference's implementation)
+# ------------------------------------------------------------------------------------------------
+def cpu_episodes_per_s(n_episodes: int, seed0: int, threads: int):
+    from oracle import mpti_oracle as O
+    from r3dfsseg_b200.episodes import make_episode
+    torch.set_num_threads(threads)
+    sd = torch.load(os.path.join(ROOT, "tests", "golden", "weights_fixture.pt"))
+    eps = [make_episode(seed0 + i, N_WAY, K_SHOT) for i in range(n_episodes)]
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        for ep in eps:
+            O.forward_episode(sd, ep.support_x, ep.support_y, ep.query_x, ep.query_y, eval_mdns=True)
+    dt = time.perf_counter() - t0
+    return n_episodes / dt, dt
+
+
+def run_reference_arm(args):
+    """The reference's CPU implementation of the path (oracle port), all host threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    per_step = args.ref_episodes_per_step
+    for _ in range(args.warmup):
+        cpu_episodes_per_s(per_step, 900, threads)
+    t_tot, n_tot = 0.0, 0
+    for s in range(args.steps):
+        _, dt = cpu_episodes_per_s(per_step, 1000 + s * per_step, threads)
+        t_tot += dt
+        n_tot += per_step
+    v = n_tot / t_tot
+    sample = (f"{per_step} episode(s) per step x {args.steps} steps of the same 2-way 5-shot "
+              f"workload (MDNS on), torch CPU fp32, {threads} threads")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_tot / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": "S3DIS-shape 2-way 5-shot MPTI eval (BASELINE.json configs[2]), "
+                               "CPU oracle port of the reference path", "episodes_per_step": per_step,
+                   "n_points": N_PTS, "n_subprototypes": 100, "k_connect": 200},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# algorithmic work per stage and per call of `E` episodes (DESIGN.md "kernels" table)
+# ------------------------------------------------------------------------------------------------
+def stage_work(E: int):
+    B = E * (N_QUERY + N_WAY * K_SHOT)          # clouds
+    M = B * N_PTS                               # points
+    k = 20
+    nn = 320 + N_QUERY * N_PTS                  # node slots per graph
+    n_sup = N_WAY * K_SHOT * N_PTS
+    w = {}
+    for i, C in enumerate((9, 64, 64)):
+        w[f"knn{i}"] = dict(flops=2.0 * B * N_PTS * N_PTS * C + 3.0 * B * N_PTS * N_PTS,
+                            bytes=4.0 * M * C + 4.0 * M * k, bound="tensor")
+        w[f"pq{i}"] = dict(flops=2.0 * M * C * 128, bytes=4.0 * M * (C + 128), bound="tensor")
+        w[f"edge{i}"] = dict(flops=2.0 * 64 * 64 * M * k, bytes=4.0 * M * (128 + 64) + 4.0 * M * k,
+                             bound="tensor")
+    w["mlp"] = dict(flops=2.0 * M * (192 * 512 + 512 * 256), bytes=4.0 * M * (192 + 256), bound="tensor")
+    w["base"] = dict(flops=2.0 * M * (256 * 128 + 128 * 64), bytes=4.0 * M * (256 + 64), bound="tensor")
+    w["qkv"] = dict(flops=2.0 * M * 256 * 192, bytes=4.0 * M * (256 + 192), bound="tensor")
+    w["att"] = dict(flops=4.0 * B * N_PTS * N_PTS * 64, bytes=4.0 * M * (192 + 64), bound="tensor")
+    # FPS: every pick re-sweeps the set (4*n*D bytes per pick); sets of one episode = all support pts
+    w["fps"] = dict(flops=3.0 * 100 * E * n_sup * 192, bytes=4.0 * 100 * E * n_sup * 192, bound="hbm")
+    w["proto"] = dict(flops=3.0 * 100 * E * n_sup * 192, bytes=2 * 4.0 * E * n_sup * 192, bound="hbm")
+    w["mdns"] = dict(flops=2.0 * E * n_sup * 192, bytes=4.0 * E * n_sup * 192, bound="hbm")
+    w["sets"] = dict(flops=0.0, bytes=2 * 4.0 * E * n_sup * 192, bound="hbm")
+    w["dist"] = dict(flops=2.0 * E * nn * nn * 192, bytes=4.0 * E * nn * (192 + nn), bound="tensor")
+    w["select"] = dict(flops=0.0, bytes=4.0 * E * nn * nn + 4.0 * E * nn * 200, bound="hbm")
+    w["sim"] = dict(flops=3.0 * E * nn * 200 * 192, bytes=4.0 * E * nn * 200 * 192, bound="hbm")
+    w["sym"] = dict(flops=0.0, bytes=6 * 8.0 * E * nn * 200, bound="hbm")
+    w["cg"] = dict(flops=0.0, bytes=None, bound="hbm")  # filled from the measured iteration count
+    w["input"] = dict(flops=0.0, bytes=2 * 4.0 * M * 9, bound="hbm")
+    w["head"] = dict(flops=0.0, bytes=2 * 4.0 * E * N_QUERY * N_PTS * 3, bound="hbm")
+    return w
+
+
+# ------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--episodes", type=int, default=100, help="episodes per step per GPU")
+    ap.add_argument("--chunk", type=int, default=20, help="episodes per C-ABI call")
+    ap.add_argument("--cpu-episodes", type=int, default=3, help="cpu_baseline sample size")
+    ap.add_argument("--ref-episodes-per-step", type=int, default=1)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "b200":
+        args.warmup = 3  # timing rule: W >= 3
+
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback for the product path)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    from r3dfsseg_b200 import _lib, ops
+    from r3dfsseg_b200.episodes import default_args
+    from r3dfsseg_b200.models import MPTI_SelfAtten
+
+    sd = torch.load(os.path.join(ROOT, "tests", "golden", "weights_fixture.pt"))
+    model = MPTI_SelfAtten(default_args(N_WAY, K_SHOT))
+    model.load_state_dict(sd)
+    model = model.to(dev).eval()
+
+    E_step, chunk = args.episodes, min(args.chunk, args.episodes)
+    h_sx, h_sy, h_qx, h_qy, classes = build_host_batch(E_step, seed0=10_000 * (rank + 1))
+    test_classes = list(range(6))
+    slot_host = torch.tensor(classes + 1, dtype=torch.int32)  # test_classes.index(c) + 1
+    d_sx, d_sy, d_qx, d_qy = (t.to(dev) for t in (h_sx, h_sy, h_qx, h_qy))
+    d_slot = slot_host.to(dev)
+    counters = torch.zeros((3, len(test_classes) + 1), dtype=torch.int64, device=dev)
+    step_counters = torch.zeros_like(counters)
+    cfg = model._cfg(N_QUERY, mdns=True)
+    ws = torch.empty(_lib.lib().r3dfs_mpti_workspace(cfg, chunk), dtype=torch.uint8, device=dev)
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    chunks = [(s, min(s + chunk, E_step)) for s in range(0, E_step, chunk)]
+    n_stage = len(_lib.STAGES)
+
+    def new_events():
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(n_stage)]
+        for e in evs:
+            e.record()  # materialise the cudaEvent_t handle
+        return evs
+
+    def run_step_resident(stage_ev=None):
+        for ci, (a, b) in enumerate(chunks):
+            out = model.forward_episodes(d_sx[a:b].transpose(3, 4), d_sy[a:b],
+                                         d_qx[a:b].transpose(2, 3), d_qy[a:b], eval=True,
+                                         workspace=ws,
+                                         stage_events=None if stage_ev is None else stage_ev[ci])
+            ops.confusion_accumulate(out["pred"], d_qy[a:b], d_slot[a:b], step_counters)
+        if dist is not None:
+            dist.all_reduce(step_counters, op=dist.ReduceOp.SUM)  # the path's only collective
+        counters.add_(step_counters)
+        step_counters.zero_()
+
+    h_pred = torch.empty((E_step, N_QUERY, N_PTS), dtype=torch.int32).pin_memory()
+    h_loss = torch.empty((E_step,), dtype=torch.float32).pin_memory()
+
+    def run_step_e2e():
+        for a, b in chunks:
+            sx = h_sx[a:b].to(dev, non_blocking=True)
+            sy = h_sy[a:b].to(dev, non_blocking=True)
+            qx = h_qx[a:b].to(dev, non_blocking=True)
+            qy = h_qy[a:b].to(dev, non_blocking=True)
+            out = model.forward_episodes(sx.transpose(3, 4), sy, qx.transpose(2, 3), qy, eval=True,
+                                         workspace=ws)
+            h_pred[a:b].copy_(out["pred"], non_blocking=True)
+            h_loss[a:b].copy_(out["loss"], non_blocking=True)
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---- warm-up ------------------------------------------------------------------------------
+    for _ in range(args.warmup):
+        run_step_resident()
+    for _ in range(2):
+        run_step_e2e()
+    sync_all()
+
+    # ---- timed: K steps, device-timed per step, L2 flushed between steps ------------------------
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    time.sleep(0.3)
+    L = _lib.lib()
+    step_events = [[new_events() for _ in chunks] for _ in range(args.steps)]
+    t_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            for _ in range(args.steps)]
+    sync_all()
+    launches0 = L.r3dfs_launch_count()
+    wall0 = time.perf_counter()
+    for s in range(args.steps):
+        flush.zero_()
+        t_ev[s][0].record()
+        run_step_resident(step_events[s])
+        t_ev[s][1].record()
+    sync_all()
+    wall_resident = time.perf_counter() - wall0
+    launches = L.r3dfs_launch_count() - launches0
+    ms_steps = [a.elapsed_time(b) for a, b in t_ev]
+    total_ms = float(sum(ms_steps))
+
+    # ---- timed: e2e (pinned host -> device -> host) ----------------------------------------------
+    e_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            for _ in range(args.steps)]
+    sync_all()
+    for s in range(args.steps):
+        flush.zero_()
+        e_ev[s][0].record()
+        run_step_e2e()
+        e_ev[s][1].record()
+    sync_all()
+    e2e_ms = float(sum(a.elapsed_time(b) for a, b in e_ev))
+    clocks = sampler.stop()
+
+    if dist is not None:
+        t = torch.tensor([total_ms, e2e_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms, e2e_ms = float(t[0]), float(t[1])
+
+    # ---- per-stage device times (rank 0), averaged per call ---------------------------------------
+    stage_ms = {name: 0.0 for name in _lib.STAGES[1:]}
+    n_calls = 0
+    for s in range(args.steps):
+        for evs in step_events[s]:
+            n_calls += 1
+            for i in range(1, n_stage):
+                stage_ms[_lib.STAGES[i]] += evs[i - 1].elapsed_time(evs[i])
+    stage_ms = {k: v / n_calls for k, v in stage_ms.items()}
+    diag = model.forward_episodes(d_sx[:chunk].transpose(3, 4), d_sy[:chunk],
+                                  d_qx[:chunk].transpose(2, 3), d_qy[:chunk], eval=True,
+                                  workspace=ws, want_diag=True)["diag"]
+    cg_iters = float(diag["cg_iters"].float().mean())
+    torch.cuda.synchronize()
+
+    peaks = load_peaks()
+    work = stage_work(chunk)
+    nn = 320 + N_QUERY * N_PTS
+    # CG: per iteration 8 B per stored non-zero (2 lists of nn*200) + vectors
+    work["cg"]["bytes"] = chunk * cg_iters * (8.0 * 2 * nn * 200 + 7 * 4.0 * nn * 3)
+    stages = {}
+    for name, ms in stage_ms.items():
+        wk = work.get(name)
+        if wk is None or ms <= 0:
+            continue
+        ent = {"ms_per_call": round(ms, 4), "bound": wk["bound"]}
+        if wk["bound"] == "tensor":
+            ent["tflops"] = round(wk["flops"] / (ms * 1e-3) / 1e12, 3)
+            ent["frac"] = round(ent["tflops"] / peaks["bf16_tflops_sustained"], 5)
+        else:
+            ent["gbs"] = round(wk["bytes"] / (ms * 1e-3) / 1e9, 2)
+            ent["frac"] = round(ent["gbs"] / peaks["hbm_gbs"], 5)
+        stages[name] = ent
+    top = max(stages, key=lambda k: stages[k]["ms_per_call"])
+    tw, te = work[top], stages[top]
+    if te["bound"] == "tensor":
+        roof = {"bound": "tensor", "achieved": te["tflops"], "peak": peaks["bf16_tflops_sustained"],
+                "unit": "TFLOP/s", "frac": te["frac"], "traffic": None}
+    else:
+        roof = {"bound": "hbm", "achieved": te["gbs"], "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                "frac": te["frac"], "traffic": None}
+    roof.update(kernel=top, peak_source=peaks["source"] + (" (sustained bf16)" if te["bound"] == "tensor" else ""),
+                launches_per_call=1, ms_per_launch=te["ms_per_call"],
+                share_of_step=round(te["ms_per_call"] / sum(stage_ms.values()), 4))
+
+    n_total = world * E_step * args.steps
+    value = n_total / (total_ms * 1e-3)
+    e2e_value = n_total / (e2e_ms * 1e-3)
+    h2d = int(sum(t.numel() * t.element_size() for t in (h_sx, h_sy, h_qx, h_qy)))
+    d2h = int(h_pred.numel() * 4 + h_loss.numel() * 4)
+
+    cpu_base = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        v, dt = cpu_episodes_per_s(args.cpu_episodes, 10_000, threads)
+        cpu_base = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+                    "sample": f"{args.cpu_episodes} episodes of the same workload (seeds 10000..), "
+                              f"oracle/mpti_oracle.py (CPU restatement of the reference path), "
+                              f"torch fp32, {threads} threads, {dt:.1f} s"}
+
+    if rank == 0:
+        cnt = counters.cpu().numpy().astype(np.float64)
+        iou = cnt[2] / np.maximum(cnt[0] + cnt[1] - cnt[2], 1)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "S3DIS-shape 2-way 5-shot MPTI eval, MDNS on, 100 sub-prototypes/"
+                                   "way, k_connect 200 (BASELINE.json configs[2])",
+                       "episodes_per_step_per_gpu": E_step, "episodes_per_call": chunk,
+                       "n_points": N_PTS, "weights": "seeded fixture (tests/golden/weights_fixture.pt)",
+                       "l2": "512 MiB flush write between timed steps", "sharding": "episodes"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h},
+            "gpu_launches": int(launches),
+            "roofline": roof,
+            "cpu_baseline": cpu_base,
+            "clocks": clocks,
+            "stages": stages,
+            "cg_iters_mean": cg_iters,
+            "mean_iou_synthetic": float(np.mean(iou[1:])),
+            "wall_s_timed_region": wall_resident,
+        }
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

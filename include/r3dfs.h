@@ -186,6 +186,32 @@ typedef struct r3dfs_episode_cfg {
   float cg_tol;            /* relative residual, e.g. 1e-6                                      */
 } r3dfs_episode_cfg_t;
 
+/* Stage boundaries of r3dfs_mpti_forward, for profiling: when diag.stage_events is given, event i
+ * is recorded on the stream when stage i has been enqueued completely (event 0 before any work),
+ * so elapsed(event[i-1], event[i]) is the device time of stage i. */
+enum r3dfs_stage {
+  R3DFS_ST_BEGIN = 0,
+  R3DFS_ST_INPUT,   /* clouds -> point-major                                        */
+  R3DFS_ST_KNN0, R3DFS_ST_PQ0, R3DFS_ST_EDGE0, /* EdgeConv 1: kNN, per-point W1, gather+W2+max */
+  R3DFS_ST_KNN1, R3DFS_ST_PQ1, R3DFS_ST_EDGE1,
+  R3DFS_ST_KNN2, R3DFS_ST_PQ2, R3DFS_ST_EDGE2,
+  R3DFS_ST_MLP,     /* point MLP 192 -> 512 -> 256                                  */
+  R3DFS_ST_BASE,    /* BaseLearner                                                  */
+  R3DFS_ST_QKV,     /* q/k/v projections                                            */
+  R3DFS_ST_ATT,     /* attention                                                    */
+  R3DFS_ST_MDNS,    /* multi-scale degree-based noise suppression                   */
+  R3DFS_ST_SETS,    /* fg/bg set compaction                                         */
+  R3DFS_ST_FPS,     /* farthest point sampling                                      */
+  R3DFS_ST_PROTO,   /* seed sort/unique, assignment, cluster means                  */
+  R3DFS_ST_DIST,    /* node distance matrix                                         */
+  R3DFS_ST_SELECT,  /* k_connect nearest per node                                   */
+  R3DFS_ST_SIM,     /* Gaussian similarities                                        */
+  R3DFS_ST_SYM,     /* in-edge lists, degrees, normalisation                        */
+  R3DFS_ST_CG,      /* conjugate-gradient solve                                     */
+  R3DFS_ST_HEAD,    /* logits / loss / prediction                                   */
+  R3DFS_N_STAGES
+};
+
 /* Device-side per-episode diagnostics (all optional: pass NULL to skip). */
 typedef struct r3dfs_episode_diag {
   int32_t* proto_count; /* (E, n_way + 1): prototypes of [bg, way 0, ...]                      */
@@ -193,7 +219,11 @@ typedef struct r3dfs_episode_diag {
                            written only when cfg.mdns = 1                                       */
   int32_t* cg_iters;    /* (E)                                                                  */
   float* cg_resid;      /* (E)                                                                  */
+  void** h_stage_events; /* HOST array of R3DFS_N_STAGES cudaEvent_t owned by the caller, or NULL */
 } r3dfs_episode_diag_t;
+
+/* Number of kernels this thread has launched through the library so far (diagnostic counter). */
+long long r3dfs_launch_count(void);
 
 size_t r3dfs_mpti_workspace(const r3dfs_episode_cfg_t* h_cfg, int n_episodes);
 

@@ -41,7 +41,13 @@ class EpisodeCfg(C.Structure):
 class EpisodeDiag(C.Structure):
     """r3dfs_episode_diag_t"""
     _fields_ = [("proto_count", C.c_void_p), ("clean_flag", C.c_void_p),
-                ("cg_iters", C.c_void_p), ("cg_resid", C.c_void_p)]
+                ("cg_iters", C.c_void_p), ("cg_resid", C.c_void_p),
+                ("h_stage_events", C.POINTER(C.c_void_p))]
+
+
+STAGES = ["begin", "input", "knn0", "pq0", "edge0", "knn1", "pq1", "edge1", "knn2", "pq2", "edge2",
+          "mlp", "base", "qkv", "att", "mdns", "sets", "fps", "proto", "dist", "select", "sim",
+          "sym", "cg", "head"]
 
 
 i64, i32, f32, vp, sz = C.c_int64, C.c_int, C.c_float, C.c_void_p, C.c_size_t
@@ -50,6 +56,7 @@ i64, i32, f32, vp, sz = C.c_int64, C.c_int, C.c_float, C.c_void_p, C.c_size_t
 SIGNATURES = {
     "r3dfs_version": (C.c_int, []),
     "r3dfs_strerror": (C.c_char_p, [C.c_int]),
+    "r3dfs_launch_count": (C.c_longlong, []),
     "r3dfs_knn_workspace": (sz, [i64, i64, i64, i32]),
     "r3dfs_knn": (C.c_int, [vp, i64, i64, i64, i64, i64, i64, i32, vp, vp, sz, vp]),
     "r3dfs_edge_feature": (C.c_int, [vp, i64, i64, i64, i64, i64, i64, vp, i32, vp, vp]),

@@ -66,6 +66,8 @@ __global__ void i32_to_i64_kernel(const int32_t* __restrict__ a, int64_t* __rest
   if (e < n) b[e] = a[e];
 }
 
+thread_local long long r3dfs_launches = 0;
+
 static inline unsigned nblk(int64_t n, int t = 256) { return (unsigned)((n + t - 1) / t); }
 
 // ---------------------------------------------------------------------------------------------
@@ -117,7 +119,7 @@ static int check_weights(const r3dfs_weights_t* w) {
 // xp: (B*N, in_dim) point-major.  F: feature rows (ld 192) addressed through `map`.
 static int encoder_forward(const r3dfs_weights_t* w, const float* xp, int64_t B, int N,
                            const EncoderWs& e, float* F, RowMap map, float* level2,
-                           cudaStream_t st) {
+                           cudaStream_t st, const StageRec* sr = nullptr) {
   const int64_t M = B * N;
   const int k = w->dgcnn_k;
   for (int i = 0; i < 3; ++i) {
@@ -126,11 +128,14 @@ static int encoder_forward(const r3dfs_weights_t* w, const float* xp, int64_t B,
     const int C = i == 0 ? w->in_dim : 64;
     R3DFS_TRY(launch_row_norms(in, M, ld, C, e.xx, st));
     R3DFS_TRY(launch_knn(in, ld, C, e.xx, B, N, k, e.idx, nullptr, st));
+    if (sr) sr->mark(R3DFS_ST_KNN0 + 3 * i, st);
     R3DFS_TRY(launch_fold_edge_w1(w->ec_w1[i], w->ec_s1[i], w->ec_t1[i], C, e.wpq, e.spq, e.tpq, st));
     R3DFS_TRY(launch_linear(in, ld, e.wpq, e.spq, e.tpq, ACT_NONE, M, C, 128, e.PQ, 128,
                             identity_map(), st));
+    if (sr) sr->mark(R3DFS_ST_PQ0 + 3 * i, st);
     R3DFS_TRY(launch_edge_mlp(e.PQ, e.idx, w->ec_w2[i], w->ec_s2[i], w->ec_t2[i], B, N, k,
                               e.ecat + 64 * i, 192, identity_map(), nullptr, st));
+    if (sr) sr->mark(R3DFS_ST_EDGE0 + 3 * i, st);
   }
   // level-1 feature = first EdgeConv output (models/dgcnn.py:127, models/mpti.py:586-589)
   copy_cols_kernel<<<nblk(M * 16), 256, 0, st>>>(e.ecat, 192, M, 64, F, 192, map);
@@ -139,6 +144,7 @@ static int encoder_forward(const r3dfs_weights_t* w, const float* xp, int64_t B,
                           512, e.h512, 512, identity_map(), st));
   R3DFS_TRY(launch_linear(e.h512, 512, w->mlp_w[1], w->mlp_s[1], w->mlp_t[1], ACT_LRELU, M, 512,
                           256, e.l2, 256, identity_map(), st));
+  if (sr) sr->mark(R3DFS_ST_MLP, st);
   if (level2) {
     cudaError_t ce = cudaMemcpyAsync(level2, e.l2, sizeof(float) * M * 256,
                                      cudaMemcpyDeviceToDevice, st);
@@ -148,9 +154,12 @@ static int encoder_forward(const r3dfs_weights_t* w, const float* xp, int64_t B,
                           e.h128, 128, identity_map(), st));
   R3DFS_TRY(launch_linear(e.h128, 128, w->bl_w[1], w->bl_s[1], w->bl_t[1], ACT_NONE, M, 128, 64,
                           F + 128, 192, map, st));
+  if (sr) sr->mark(R3DFS_ST_BASE, st);
   R3DFS_TRY(launch_linear(e.l2, 256, w->att_wqkv, nullptr, nullptr, ACT_NONE, M, 256, 192, e.qkv,
                           192, identity_map(), st));
+  if (sr) sr->mark(R3DFS_ST_QKV, st);
   R3DFS_TRY(launch_attention(e.qkv, 192, B, N, F + 64, 192, map, st));
+  if (sr) sr->mark(R3DFS_ST_ATT, st);
   return 0;
 }
 
@@ -160,6 +169,8 @@ static int encoder_forward(const r3dfs_weights_t* w, const float* xp, int64_t B,
 extern "C" {
 
 int r3dfs_version(void) { return R3DFS_VERSION; }
+
+long long r3dfs_launch_count(void) { return r3dfs_launches; }
 
 const char* r3dfs_strerror(int code) {
   switch (code) {
@@ -497,6 +508,8 @@ static int episode_graph_half(const r3dfs_episode_cfg_t* cfg, const EpisodeDims&
                               const int64_t* query_y, float* logits, float* loss, int32_t* pred,
                               const r3dfs_episode_diag_t* diag, cudaStream_t st) {
   const int N = cfg->n_points, D = R3DFS_FEAT_DIM;
+  StageRec srv{diag ? (cudaEvent_t*)diag->h_stage_events : nullptr};
+  const StageRec* sr = srv.ev ? &srv : nullptr;
   cudaError_t ce = cudaMemset2DAsync(w.F, sizeof(float) * d.ep_rows * D, 0,
                                      sizeof(float) * (size_t)d.ppad * D, E, st);
   if (ce != cudaSuccess) return (int)ce;
@@ -510,26 +523,30 @@ static int episode_graph_half(const r3dfs_episode_cfg_t* cfg, const EpisodeDims&
     fill_i32_kernel<<<nblk((int64_t)E * d.C), 256, 0, st>>>(w.keep, (int64_t)E * d.C, 1);
     R3DFS_CHECK_LAUNCH();
   }
+  if (sr) sr->mark(R3DFS_ST_MDNS, st);
   // prototype sets -> FPS seeds -> assignment -> means, into the prototype slots of F
   R3DFS_TRY(launch_set_compaction(w.F, d.ep_rows, sup_off, E, cfg->n_way, cfg->k_shot, N, D,
                                   support_y, w.keep, w.fg_cnt, w.set_off, w.set_n, w.cloud_bg_off,
                                   w.cloud_fg_off, w.setfeat, st));
+  if (sr) sr->mark(R3DFS_ST_SETS, st);
   R3DFS_TRY(launch_multi_prototypes(w.setfeat, D, w.set_off, w.set_n, E * d.S, d.ns_pts,
                                     cfg->n_subprototypes, w.picks, w.pick_cnt, w.seeds,
-                                    w.proto_cnt, w.assign, d.S, d.ep_rows, w.F, D, st));
+                                    w.proto_cnt, w.assign, d.S, d.ep_rows, w.F, D, st, sr));
+  if (sr) sr->mark(R3DFS_ST_PROTO, st);
   // graph: nodes = [prototype slots | query points]
   graph_init_kernel<<<dim3(nblk(d.nn), E), 256, 0, st>>>(w.proto_cnt, d.S, d.slot, d.ppad, d.nn,
                                                          d.nc, w.valid, w.Y);
   R3DFS_CHECK_LAUNCH();
   R3DFS_TRY(launch_affinity(w.F, d.ep_rows, 0, w.valid, E, d.nn, D, cfg->k_connect, cfg->sigma,
-                            w.norms, w.D2, w.nbr, w.sim, st));
+                            w.norms, w.D2, w.nbr, w.sim, st, sr));
   R3DFS_TRY(launch_label_propagate(w.nbr, w.sim, w.valid, E, d.nn, cfg->k_connect, w.Y, d.nc,
                                    cfg->alpha, cfg->cg_tol, cfg->cg_max_iter, w.in_cnt, w.in_ptr,
                                    w.in_src, w.in_w, w.dinv, w.X, w.R, w.P, w.AP,
                                    diag ? diag->cg_iters : nullptr,
-                                   diag ? diag->cg_resid : nullptr, st));
+                                   diag ? diag->cg_resid : nullptr, st, sr));
   // query rows -> logits / loss / prediction
   R3DFS_TRY(launch_query_head(w.X, E, d.nn, d.ppad, d.nq_pts, d.nc, query_y, logits, loss, pred, st));
+  if (sr) sr->mark(R3DFS_ST_HEAD, st);
   if (diag && diag->proto_count) {
     ce = cudaMemcpyAsync(diag->proto_count, w.proto_cnt, sizeof(int32_t) * (size_t)E * d.S,
                          cudaMemcpyDeviceToDevice, st);
@@ -557,6 +574,9 @@ int r3dfs_mpti_forward(const r3dfs_episode_cfg_t* cfg, const r3dfs_weights_t* hw
   carve_episode(ws, cfg, d, E, in_dim, hw->dgcnn_k, w);
   if (!ws.ok()) return R3DFS_E_WORKSPACE;
   const int64_t B = (int64_t)E * d.cpe;
+  StageRec srv{diag ? (cudaEvent_t*)diag->h_stage_events : nullptr};
+  const StageRec* sr = srv.ev ? &srv : nullptr;
+  if (sr) sr->mark(R3DFS_ST_BEGIN, st);
   // clouds -> point-major, episode-major order [queries | supports] (matches F's row layout)
   int64_t tq = (int64_t)E * cfg->n_query * N * in_dim;
   gather_clouds_kernel<<<nblk(tq), 256, 0, st>>>(query_x, cfg->n_query, in_dim, N, q_e, q_cloud,
@@ -566,9 +586,10 @@ int r3dfs_mpti_forward(const r3dfs_episode_cfg_t* cfg, const r3dfs_weights_t* hw
   gather_clouds_kernel<<<nblk(tsup), 256, 0, st>>>(support_x, d.C, in_dim, N, s_e, s_cloud, s_c,
                                                    s_n, d.cpe, cfg->n_query, w.xp, tsup);
   R3DFS_CHECK_LAUNCH();
+  if (sr) sr->mark(R3DFS_ST_INPUT, st);
   // features of every cloud (models/mpti.py:433-437), written straight into the node matrix
   RowMap fmap{d.cpe, N, d.ep_rows, (int64_t)d.ppad};
-  R3DFS_TRY(encoder_forward(hw, w.xp, B, N, w.enc, w.F, fmap, nullptr, st));
+  R3DFS_TRY(encoder_forward(hw, w.xp, B, N, w.enc, w.F, fmap, nullptr, st, sr));
   return episode_graph_half(cfg, d, E, w, support_x, s_e, s_cloud, s_c, s_n, support_y, query_y,
                             logits, loss, pred, diag, st);
 }

@@ -9,11 +9,22 @@
 #define R3DFS_FEAT_DIM 192
 #define R3DFS_EC_WIDTH 64
 
+extern thread_local long long r3dfs_launches;  // diagnostic: kernels launched by this thread
+
 #define R3DFS_CHECK_LAUNCH()                       \
   do {                                             \
     cudaError_t e__ = cudaGetLastError();          \
     if (e__ != cudaSuccess) return (int)e__;       \
+    ++r3dfs_launches;                              \
   } while (0)
+
+// optional stage-boundary events (r3dfs_episode_diag_t::h_stage_events)
+struct StageRec {
+  cudaEvent_t* ev;
+  inline void mark(int stage, cudaStream_t st) const {
+    if (ev && ev[stage]) cudaEventRecord(ev[stage], st);
+  }
+};
 
 #define R3DFS_TRY(expr)                            \
   do {                                             \

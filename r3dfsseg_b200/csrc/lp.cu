@@ -660,7 +660,7 @@ __global__ void confusion_kernel(const int32_t* __restrict__ pred, const int64_t
 // --------------------------------------------------------------------------------------------
 int launch_affinity(const float* F, int64_t graph_rows, int64_t row_off, const uint8_t* valid,
                     int G, int nn, int D, int k, float sigma, float* norms, float* D2, int32_t* nbr,
-                    float* sim, cudaStream_t st) {
+                    float* sim, cudaStream_t st, const StageRec* sr) {
   if (D % 4 != 0 || D > 32 * LP_MAX_F4 || k > 1024 || nn > 65535) return R3DFS_E_UNSUPPORTED;
   for (int g = 0; g < G; ++g)
     R3DFS_TRY(launch_row_norms(F + ((int64_t)g * graph_rows + row_off) * D, nn, D, D,
@@ -668,15 +668,18 @@ int launch_affinity(const float* F, int64_t graph_rows, int64_t row_off, const u
   dim3 gd((nn + GD_BM - 1) / GD_BM, (nn + GD_BN - 1) / GD_BN, G);
   gram_dist_kernel<<<gd, 256, 0, st>>>(F, graph_rows, row_off, nn, D, norms, D2);
   R3DFS_CHECK_LAUNCH();
+  if (sr) sr->mark(R3DFS_ST_DIST, st);
   size_t smem = sizeof(unsigned) * (size_t)nn;
   cudaError_t e = cudaFuncSetAttribute(knn_select_kernel,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
   knn_select_kernel<<<dim3(nn, G), SEL_THREADS, smem, st>>>(D2, valid, nn, k, nbr);
   R3DFS_CHECK_LAUNCH();
+  if (sr) sr->mark(R3DFS_ST_SELECT, st);
   edge_sim_kernel<<<dim3((nn + 7) / 8, G), 256, 0, st>>>(F, graph_rows, row_off, nn, D, valid, nbr,
                                                         k, sigma, sim);
   R3DFS_CHECK_LAUNCH();
+  if (sr) sr->mark(R3DFS_ST_SIM, st);
   return 0;
 }
 
@@ -684,7 +687,7 @@ int launch_label_propagate(const int32_t* nbr, float* sim, const uint8_t* valid,
                            int k, const float* Y, int nc, float alpha, float tol, int max_iter,
                            int32_t* in_cnt, int32_t* in_ptr, int32_t* in_src, float* in_w,
                            float* dinv, float* X, float* R, float* P, float* AP, int32_t* iters_out,
-                           float* resid_out, cudaStream_t st) {
+                           float* resid_out, cudaStream_t st, const StageRec* sr) {
   if (nc > CG_MAXC || nc < 1 || nn > 8192) return R3DFS_E_UNSUPPORTED;
   cudaError_t e = cudaMemsetAsync(in_cnt, 0, sizeof(int32_t) * (size_t)G * nn, st);
   if (e != cudaSuccess) return (int)e;
@@ -706,6 +709,7 @@ int launch_label_propagate(const int32_t* nbr, float* sim, const uint8_t* valid,
   R3DFS_CHECK_LAUNCH();
   normalize_kernel<<<gr, 256, 0, st>>>(nbr, sim, in_ptr, in_src, in_w, valid, dinv, nn, k);
   R3DFS_CHECK_LAUNCH();
+  if (sr) sr->mark(R3DFS_ST_SYM, st);
 
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(CG_CL, G, 1);
@@ -726,6 +730,8 @@ int launch_label_propagate(const int32_t* nbr, float* sim, const uint8_t* valid,
   e = cudaLaunchKernelEx(&cfg, lp_cg_kernel, nbr, simc, in_ptrc, in_srcc, in_wc, valid, nn, k, Y,
                          nc, alpha, tol, max_iter, X, R, P, AP, iters_out, resid_out);
   if (e != cudaSuccess) return (int)e;
+  ++r3dfs_launches;
+  if (sr) sr->mark(R3DFS_ST_CG, st);
   return 0;
 }
 

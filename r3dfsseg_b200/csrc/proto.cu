@@ -190,6 +190,7 @@ int launch_fps_ex(const float* feat, int D, const int32_t* set_off, const int32_
   e = cudaLaunchKernelEx(&cfg, fps_kernel, feat, D, set_off, set_n, m_max, k_for_count, idx_out,
                          cnt_out);
   if (e != cudaSuccess) return (int)e;
+  ++r3dfs_launches;
   return 0;
 }
 
@@ -370,10 +371,11 @@ int launch_multi_prototypes(const float* feat, int D, const int32_t* set_off,
                             const int32_t* set_n, int n_sets, int n_cap, int k, int32_t* picks,
                             int32_t* pick_cnt, int32_t* seeds, int32_t* proto_cnt,
                             int32_t* assign, int sets_per_group, int64_t group_rows,
-                            float* proto_out, int ld_out, cudaStream_t st) {
+                            float* proto_out, int ld_out, cudaStream_t st, const StageRec* sr) {
   const int m_max = k + 1;
   if (m_max > 128 || D > MEAN_THREADS) return R3DFS_E_UNSUPPORTED;
   R3DFS_TRY(launch_fps_ex(feat, D, set_off, set_n, n_sets, n_cap, m_max, k, picks, pick_cnt, st));
+  if (sr) sr->mark(R3DFS_ST_FPS, st);
   seeds_unique_kernel<<<n_sets, 128, 0, st>>>(picks, pick_cnt, set_n, m_max, k, seeds, proto_cnt);
   R3DFS_CHECK_LAUNCH();
   size_t smem = sizeof(float) * (size_t)m_max * D;

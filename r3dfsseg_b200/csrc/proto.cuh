@@ -9,7 +9,8 @@ int launch_multi_prototypes(const float* feat, int D, const int32_t* set_off,
                             const int32_t* set_n, int n_sets, int n_cap, int k, int32_t* picks,
                             int32_t* pick_cnt, int32_t* seeds, int32_t* proto_cnt,
                             int32_t* assign, int sets_per_group, int64_t group_rows,
-                            float* proto_out, int ld_out, cudaStream_t st);
+                            float* proto_out, int ld_out, cudaStream_t st,
+                            const StageRec* sr = nullptr);
 int launch_set_compaction(const float* F, int64_t ep_rows, int64_t sup_row_off, int E, int n_way,
                           int k_shot, int N, int D, const int32_t* sy, const int32_t* keep,
                           int32_t* fg_cnt, int32_t* set_off, int32_t* set_n, int32_t* cloud_bg_off,

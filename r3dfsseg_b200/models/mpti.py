@@ -95,7 +95,8 @@ class MPTI_SelfAtten(nn.Module):
 
     # ---------------------------------------------------------------------------------------
     def forward_episodes(self, support_x, support_y, query_x, query_y=None, eval=True,
-                         want_diag=False, workspace=None, support_feat=None, query_feat=None):
+                         want_diag=False, workspace=None, support_feat=None, query_feat=None,
+                         stage_events=None):
         """Batch of E independent episodes (leading dim E on every tensor).
         Returns dict(logits (E, n_query, N, n_way+1), loss (E), pred (E, n_query, N)).
         With `support_feat` (E, n_way*k_shot*N, 192) / `query_feat` (E, n_query*N, 192) given,
@@ -105,7 +106,8 @@ class MPTI_SelfAtten(nn.Module):
         cfg = self._cfg(query_x.shape[1], mdns=bool(eval))
         return ops.mpti_forward(self._weights(), cfg, support_x, support_y, query_x, query_y,
                                 want_diag=want_diag, workspace=workspace,
-                                support_feat=support_feat, query_feat=query_feat)
+                                support_feat=support_feat, query_feat=query_feat,
+                                stage_events=stage_events)
 
     def forward(self, support_x, support_y, query_x, query_y, gt_support_y=None, gt_query_y=None,
                 train=False, logger=None, step=None, path=None, sampled_classes=None,

@@ -318,7 +318,8 @@ def mpti_forward(pw: Optional[PackedWeights], cfg: EpisodeCfg, support_x: torch.
                  support_y: torch.Tensor, query_x: torch.Tensor, query_y: Optional[torch.Tensor],
                  want_diag: bool = False, workspace: Optional[torch.Tensor] = None,
                  support_feat: Optional[torch.Tensor] = None,
-                 query_feat: Optional[torch.Tensor] = None):
+                 query_feat: Optional[torch.Tensor] = None,
+                 stage_events: Optional[Sequence["torch.cuda.Event"]] = None):
     """E episodes in one call.
     support_x (E, n_way, k_shot, C, N) any strides with uniform cloud stride; support_y
     (E, n_way, k_shot, N) int32; query_x (E, n_query, C, N); query_y (E, n_query, N) int64.
@@ -345,6 +346,14 @@ def mpti_forward(pw: Optional[PackedWeights], cfg: EpisodeCfg, support_x: torch.
     ws = workspace if workspace is not None and workspace.numel() >= need else _ws(need, dev)
     diag = None
     dstruct = None
+    ev_arr = None
+    if stage_events is not None:
+        # raw cudaEvent_t handles of caller-owned torch events (created by a first record())
+        if len(stage_events) != len(_lib.STAGES):
+            raise ValueError(f"need {len(_lib.STAGES)} stage events")
+        ev_arr = (C.c_void_p * len(stage_events))(*[int(e.cuda_event) for e in stage_events])
+    if want_diag or ev_arr is not None:
+        dstruct = EpisodeDiag(None, None, None, None, None)
     if want_diag:
         diag = {
             "proto_count": torch.zeros((E, nc), dtype=torch.int32, device=dev),
@@ -352,8 +361,12 @@ def mpti_forward(pw: Optional[PackedWeights], cfg: EpisodeCfg, support_x: torch.
             "cg_iters": torch.zeros((E,), dtype=torch.int32, device=dev),
             "cg_resid": torch.zeros((E,), dtype=torch.float32, device=dev),
         }
-        dstruct = EpisodeDiag(diag["proto_count"].data_ptr(), diag["clean_flag"].data_ptr(),
-                              diag["cg_iters"].data_ptr(), diag["cg_resid"].data_ptr())
+        dstruct.proto_count = diag["proto_count"].data_ptr()
+        dstruct.clean_flag = diag["clean_flag"].data_ptr()
+        dstruct.cg_iters = diag["cg_iters"].data_ptr()
+        dstruct.cg_resid = diag["cg_resid"].data_ptr()
+    if ev_arr is not None:
+        dstruct.h_stage_events = C.cast(ev_arr, C.POINTER(C.c_void_p))
     if support_feat is not None:
         # precomputed features (point-major (E, rows, 192)): graph half only
         support_feat = _f32(support_feat).contiguous()
