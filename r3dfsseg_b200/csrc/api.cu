@@ -366,8 +366,9 @@ int r3dfs_affinity_knn(const float* node_feat, const uint8_t* valid, int n_graph
 
 size_t r3dfs_label_propagate_workspace(int n_graphs, int64_t n_max, int k, int n_cls) {
   const size_t G = n_graphs, n = n_max;
+  (void)n_cls;
   return align_up(4 * G * n * k, 256) * 3 + align_up(4 * G * (n + 1), 256) * 3 +
-         align_up(4 * G * n * n_cls, 256) * 3 + 4096;
+         align_up(4 * G * n * 8, 256) * 4 + 4096;
 }
 
 int r3dfs_label_propagate(const int32_t* nbr, const float* sim, const uint8_t* valid, int n_graphs,
@@ -388,14 +389,15 @@ int r3dfs_label_propagate(const int32_t* nbr, const float* sim, const uint8_t* v
   int32_t* in_cnt = ws.take<int32_t>(G * (n + 1));
   int32_t* in_ptr = ws.take<int32_t>(G * (n + 1));
   float* dinv = ws.take<float>(G * (n + 1));
-  float* R = ws.take<float>(G * n * n_cls);
-  float* P = ws.take<float>(G * n * n_cls);
-  float* AP = ws.take<float>(G * n * n_cls);
+  float* X = ws.take<float>(G * n * 8);
+  float* R = ws.take<float>(G * n * 8);
+  float* P = ws.take<float>(G * n * 8);
+  float* AP = ws.take<float>(G * n * 8);
   if (!ws.ok()) return R3DFS_E_WORKSPACE;
   cudaError_t ce = cudaMemcpyAsync(sv, sim, sizeof(float) * G * n * k, cudaMemcpyDeviceToDevice, st);
   if (ce != cudaSuccess) return (int)ce;
   return launch_label_propagate(nbr, sv, valid, n_graphs, (int)n_max, k, Y, n_cls, alpha, tol,
-                                max_iter, in_cnt, in_ptr, in_src, in_w, dinv, Z, R, P, AP,
+                                max_iter, in_cnt, in_ptr, in_src, in_w, dinv, Z, X, R, P, AP,
                                 iters_out, resid_out, st);
 }
 
@@ -450,7 +452,7 @@ struct EpisodeWs {
   int32_t* nbr;
   float* sim;
   int32_t *in_cnt, *in_ptr, *in_src;
-  float *in_w, *dinv, *X, *R, *P, *AP;
+  float *in_w, *dinv, *Z, *X, *R, *P, *AP;
 };
 
 static void carve_episode(WsBump& ws, const r3dfs_episode_cfg_t* c, const EpisodeDims& d, int E,
@@ -485,10 +487,11 @@ static void carve_episode(WsBump& ws, const r3dfs_episode_cfg_t* c, const Episod
   w.in_src = ws.take<int32_t>(G * nn * k);
   w.in_w = ws.take<float>(G * nn * k);
   w.dinv = ws.take<float>(G * nn);
-  w.X = ws.take<float>(G * nn * d.nc);
-  w.R = ws.take<float>(G * nn * d.nc);
-  w.P = ws.take<float>(G * nn * d.nc);
-  w.AP = ws.take<float>(G * nn * d.nc);
+  w.Z = ws.take<float>(G * nn * d.nc);
+  w.X = ws.take<float>(G * nn * 8);
+  w.R = ws.take<float>(G * nn * 8);
+  w.P = ws.take<float>(G * nn * 8);
+  w.AP = ws.take<float>(G * nn * 8);
 }
 
 size_t r3dfs_mpti_workspace(const r3dfs_episode_cfg_t* cfg, int n_episodes) {
@@ -541,11 +544,11 @@ static int episode_graph_half(const r3dfs_episode_cfg_t* cfg, const EpisodeDims&
                             w.norms, w.D2, w.nbr, w.sim, st, sr));
   R3DFS_TRY(launch_label_propagate(w.nbr, w.sim, w.valid, E, d.nn, cfg->k_connect, w.Y, d.nc,
                                    cfg->alpha, cfg->cg_tol, cfg->cg_max_iter, w.in_cnt, w.in_ptr,
-                                   w.in_src, w.in_w, w.dinv, w.X, w.R, w.P, w.AP,
+                                   w.in_src, w.in_w, w.dinv, w.Z, w.X, w.R, w.P, w.AP,
                                    diag ? diag->cg_iters : nullptr,
                                    diag ? diag->cg_resid : nullptr, st, sr));
   // query rows -> logits / loss / prediction
-  R3DFS_TRY(launch_query_head(w.X, E, d.nn, d.ppad, d.nq_pts, d.nc, query_y, logits, loss, pred, st));
+  R3DFS_TRY(launch_query_head(w.Z, E, d.nn, d.ppad, d.nq_pts, d.nc, query_y, logits, loss, pred, st));
   if (sr) sr->mark(R3DFS_ST_HEAD, st);
   if (diag && diag->proto_count) {
     ce = cudaMemcpyAsync(diag->proto_count, w.proto_cnt, sizeof(int32_t) * (size_t)E * d.S,

@@ -402,33 +402,39 @@ __global__ void normalize_kernel(const int32_t* __restrict__ nbr, float* __restr
 
 // --------------------------------------------------------------------------------------------
 // Label propagation: (I - alpha S) Z = Y by conjugate gradients, all n_cls right-hand sides at
-// once, one thread-block cluster per graph.  Rows are sliced over the cluster's CTAs; the search
-// direction P is the only vector other CTAs read (through L2); dot products are exchanged through
-// distributed shared memory and summed in rank order, so every CTA sees identical scalars.
+// once, one thread-block CLUSTER per graph (16 CTAs when the device grants it, else 8).
+//   - rows are sliced over the cluster's CTAs; X, R, AP of a slice are private to its CTA;
+//   - the search direction P is the only vector other CTAs read: it lives in global memory (L2),
+//     and every CTA stages the whole of it (n x NCV floats) in shared memory once per iteration,
+//     so the 2 x k x n gathers of the sparse product hit shared memory, not L2;
+//   - the matrix (out-edge list + in-edge list) streams from L2 once per iteration;
+//   - dot products are exchanged through distributed shared memory and summed in rank order, so
+//     every CTA sees bit-identical scalars and the control flow stays cluster-uniform.
 // --------------------------------------------------------------------------------------------
-#define CG_THREADS 512
-#define CG_CL 8
+#define CG_THREADS 1024
+#define CG_CL_MAX 16
 #define CG_MAXC 8
 
 struct CgExchange {
-  float slot[2][CG_CL][CG_MAXC];
+  float slot[2][CG_CL_MAX][CG_MAXC];
 };
 
+template <int NCV>
 __device__ __forceinline__ void cg_allreduce(cg::cluster_group& cluster, CgExchange* ex,
-                                             float* s_warp /*[16][8]*/, const float* part, int nc,
-                                             int& xcnt, float* total) {
+                                             float* s_warp, const float* part, int& xcnt,
+                                             float* total) {
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const int rank = cluster.block_rank(), CL = cluster.num_blocks();
-  float v[CG_MAXC];
+  float v[NCV];
 #pragma unroll
-  for (int c = 0; c < CG_MAXC; ++c) v[c] = warp_sum(part[c]);
+  for (int c = 0; c < NCV; ++c) v[c] = warp_sum(part[c]);
   if (lane == 0) {
 #pragma unroll
-    for (int c = 0; c < CG_MAXC; ++c) s_warp[w * CG_MAXC + c] = v[c];
+    for (int c = 0; c < NCV; ++c) s_warp[w * CG_MAXC + c] = v[c];
   }
   __syncthreads();
   const int par = xcnt & 1;
-  if (tid < CG_MAXC) {
+  if (tid < NCV) {
     float s = 0.f;
     for (int q = 0; q < CG_THREADS / 32; ++q) s += s_warp[q * CG_MAXC + tid];
     for (int r = 0; r < CL; ++r) {
@@ -438,35 +444,38 @@ __device__ __forceinline__ void cg_allreduce(cg::cluster_group& cluster, CgExcha
   }
   cluster.sync();
 #pragma unroll
-  for (int c = 0; c < CG_MAXC; ++c) {
+  for (int c = 0; c < NCV; ++c) {
     float s = 0.f;
     for (int r = 0; r < CL; ++r) s += ex->slot[par][r][c];
     total[c] = s;
   }
-  (void)nc;
   ++xcnt;
 }
 
+// Vectors are stored padded to NCV columns (NCV = 4 or 8) so a node's row is one or two float4.
+template <int NCV>
 __global__ __launch_bounds__(CG_THREADS) void lp_cg_kernel(
     const int32_t* __restrict__ nbr, const float* __restrict__ sval,
     const int32_t* __restrict__ in_ptr, const int32_t* __restrict__ in_src,
     const float* __restrict__ in_sval, const uint8_t* __restrict__ valid, int nn, int k,
     const float* __restrict__ Y, int nc, float alpha, float tol, int max_iter,
-    float* __restrict__ X, float* __restrict__ R, float* __restrict__ Pv, float* __restrict__ AP,
-    int32_t* __restrict__ iters_out, float* __restrict__ resid_out) {
+    float* __restrict__ Z, float* __restrict__ X, float* __restrict__ R, float* __restrict__ Pv,
+    float* __restrict__ AP, int32_t* __restrict__ iters_out, float* __restrict__ resid_out) {
   cg::cluster_group cluster = cg::this_cluster();
   const int CL = cluster.num_blocks(), rank = cluster.block_rank();
   const int g = blockIdx.y;
+  extern __shared__ __align__(16) float Ps[];  // [nn][NCV] staged copy of P
   __shared__ CgExchange ex;
   __shared__ float s_warp[(CG_THREADS / 32) * CG_MAXC];
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const int64_t vb = (int64_t)g * nn;
   const uint8_t* vg = valid + vb;
   const float* Yg = Y + vb * nc;
-  float* Xg = X + vb * nc;
-  float* Rg = R + vb * nc;
-  float* Pg = Pv + vb * nc;
-  float* APg = AP + vb * nc;
+  float* Zg = Z + vb * nc;
+  float* Xg = X + vb * NCV;
+  float* Rg = R + vb * NCV;
+  float* Pg = Pv + vb * NCV;
+  float* APg = AP + vb * NCV;
   const int32_t* nb = nbr + vb * k;
   const float* sv = sval + vb * k;
   const int32_t* ip = in_ptr + (int64_t)g * (nn + 1);
@@ -476,95 +485,111 @@ __global__ __launch_bounds__(CG_THREADS) void lp_cg_kernel(
   const int lo = min(nn, rank * chunk), hi = min(nn, lo + chunk);
   int xcnt = 0;
 
-  float part[CG_MAXC], bb[CG_MAXC], rs[CG_MAXC], tot[CG_MAXC];
+  float part[NCV], bb[NCV], rs[NCV], tot[NCV];
 #pragma unroll
-  for (int c = 0; c < CG_MAXC; ++c) part[c] = 0.f;
+  for (int c = 0; c < NCV; ++c) part[c] = 0.f;
   for (int row = lo + tid; row < hi; row += CG_THREADS) {
     const bool ok = vg[row];
 #pragma unroll
-    for (int c = 0; c < CG_MAXC; ++c)
-      if (c < nc) {
-        const float y = ok ? Yg[(int64_t)row * nc + c] : 0.f;
-        Xg[(int64_t)row * nc + c] = 0.f;
-        Rg[(int64_t)row * nc + c] = y;
-        Pg[(int64_t)row * nc + c] = y;
-        part[c] = fmaf(y, y, part[c]);
-      }
+    for (int c = 0; c < NCV; ++c) {
+      const float y = (ok && c < nc) ? Yg[(int64_t)row * nc + c] : 0.f;
+      Xg[(int64_t)row * NCV + c] = 0.f;
+      Rg[(int64_t)row * NCV + c] = y;
+      Pg[(int64_t)row * NCV + c] = y;
+      APg[(int64_t)row * NCV + c] = 0.f;
+      part[c] = fmaf(y, y, part[c]);
+    }
   }
-  cg_allreduce(cluster, &ex, s_warp, part, nc, xcnt, bb);
-  bool done[CG_MAXC];
+  cg_allreduce<NCV>(cluster, &ex, s_warp, part, xcnt, bb);
+  bool done[NCV];
   bool all_done = true;
 #pragma unroll
-  for (int c = 0; c < CG_MAXC; ++c) {
+  for (int c = 0; c < NCV; ++c) {
     rs[c] = bb[c];
-    done[c] = !(c < nc) || !(bb[c] > 0.f);
+    done[c] = !(bb[c] > 0.f);
     all_done = all_done && done[c];
   }
   const float tol2 = tol * tol;
   int it = 0;
   while (!all_done && it < max_iter) {
+    // ---- stage P (written by every CTA of the cluster, published by the last cluster.sync)
+    {
+      const float4* src = reinterpret_cast<const float4*>(Pg);
+      float4* dst = reinterpret_cast<float4*>(Ps);
+      const int n4 = nn * (NCV / 4);
+      for (int i = tid; i < n4; i += CG_THREADS) dst[i] = __ldcg(src + i);
+    }
+    __syncthreads();
     // ---- AP = P - alpha * S P  on my rows; partial P.AP
 #pragma unroll
-    for (int c = 0; c < CG_MAXC; ++c) part[c] = 0.f;
+    for (int c = 0; c < NCV; ++c) part[c] = 0.f;
     for (int row = lo + w; row < hi; row += CG_THREADS / 32) {
-      if (!vg[row]) {  // warp-uniform; keep AP defined for the vector updates below
-        if (lane < nc) APg[(int64_t)row * nc + lane] = 0.f;
-        continue;
-      }
-      float acc[CG_MAXC];
+      if (!vg[row]) continue;  // warp-uniform (AP stays 0 from the initialisation)
+      float acc[NCV];
 #pragma unroll
-      for (int c = 0; c < CG_MAXC; ++c) acc[c] = 0.f;
+      for (int c = 0; c < NCV; ++c) acc[c] = 0.f;
+      const int32_t* nbr_row = nb + (int64_t)row * k;
+      const float* sv_row = sv + (int64_t)row * k;
+#pragma unroll 4
       for (int t = lane; t < k; t += 32) {
-        const int j = nb[(int64_t)row * k + t];
-        const float v = sv[(int64_t)row * k + t];
+        const int j = nbr_row[t];
+        const float v = sv_row[t];
 #pragma unroll
-        for (int c = 0; c < CG_MAXC; ++c)
-          if (c < nc) acc[c] = fmaf(v, __ldcg(Pg + (int64_t)j * nc + c), acc[c]);
+        for (int q = 0; q < NCV / 4; ++q) {
+          const float4 p4 = *reinterpret_cast<const float4*>(Ps + (int64_t)j * NCV + 4 * q);
+          acc[4 * q + 0] = fmaf(v, p4.x, acc[4 * q + 0]);
+          acc[4 * q + 1] = fmaf(v, p4.y, acc[4 * q + 1]);
+          acc[4 * q + 2] = fmaf(v, p4.z, acc[4 * q + 2]);
+          acc[4 * q + 3] = fmaf(v, p4.w, acc[4 * q + 3]);
+        }
       }
-      for (int t = ip[row] + lane; t < ip[row + 1]; t += 32) {
+      const int e0 = ip[row], e1 = ip[row + 1];
+#pragma unroll 4
+      for (int t = e0 + lane; t < e1; t += 32) {
         const int j = is[t];
         const float v = iv[t];
 #pragma unroll
-        for (int c = 0; c < CG_MAXC; ++c)
-          if (c < nc) acc[c] = fmaf(v, __ldcg(Pg + (int64_t)j * nc + c), acc[c]);
+        for (int q = 0; q < NCV / 4; ++q) {
+          const float4 p4 = *reinterpret_cast<const float4*>(Ps + (int64_t)j * NCV + 4 * q);
+          acc[4 * q + 0] = fmaf(v, p4.x, acc[4 * q + 0]);
+          acc[4 * q + 1] = fmaf(v, p4.y, acc[4 * q + 1]);
+          acc[4 * q + 2] = fmaf(v, p4.z, acc[4 * q + 2]);
+          acc[4 * q + 3] = fmaf(v, p4.w, acc[4 * q + 3]);
+        }
       }
 #pragma unroll
-      for (int c = 0; c < CG_MAXC; ++c)
-        if (c < nc) {
-          const float s = warp_sum(acc[c]);
-          const float p = __ldcg(Pg + (int64_t)row * nc + c);
-          const float ap = p - alpha * s;
-          if (lane == 0) {
-            APg[(int64_t)row * nc + c] = ap;
-            part[c] = fmaf(p, ap, part[c]);
-          }
+      for (int c = 0; c < NCV; ++c) {
+        const float s = warp_sum(acc[c]);
+        const float p = Ps[(int64_t)row * NCV + c];
+        const float ap = p - alpha * s;
+        if (lane == 0) {
+          APg[(int64_t)row * NCV + c] = ap;
+          part[c] = fmaf(p, ap, part[c]);
         }
+      }
     }
-    cg_allreduce(cluster, &ex, s_warp, part, nc, xcnt, tot);
-    float a[CG_MAXC];
+    cg_allreduce<NCV>(cluster, &ex, s_warp, part, xcnt, tot);
+    float a[NCV];
 #pragma unroll
-    for (int c = 0; c < CG_MAXC; ++c) a[c] = (!done[c] && tot[c] > 0.f) ? rs[c] / tot[c] : 0.f;
-    // ---- X += a P ; R -= a AP ; partial R.R
+    for (int c = 0; c < NCV; ++c) a[c] = (!done[c] && tot[c] > 0.f) ? rs[c] / tot[c] : 0.f;
+    // ---- X += a P ; R -= a AP ; partial R.R      (own rows; P from the staged copy)
 #pragma unroll
-    for (int c = 0; c < CG_MAXC; ++c) part[c] = 0.f;
+    for (int c = 0; c < NCV; ++c) part[c] = 0.f;
     for (int row = lo + tid; row < hi; row += CG_THREADS) {
 #pragma unroll
-      for (int c = 0; c < CG_MAXC; ++c)
-        if (c < nc) {
-          const int64_t o = (int64_t)row * nc + c;
-          const float p = __ldcg(Pg + o);
-          const float r = Rg[o] - a[c] * APg[o];
-          Xg[o] = fmaf(a[c], p, Xg[o]);
-          Rg[o] = r;
-          part[c] = fmaf(r, r, part[c]);
-        }
+      for (int c = 0; c < NCV; ++c) {
+        const int64_t o = (int64_t)row * NCV + c;
+        const float r = Rg[o] - a[c] * APg[o];
+        Xg[o] = fmaf(a[c], Ps[o], Xg[o]);
+        Rg[o] = r;
+        part[c] = fmaf(r, r, part[c]);
+      }
     }
-    __syncthreads();  // AP (written by lane 0 of each warp) was read above by other threads
-    cg_allreduce(cluster, &ex, s_warp, part, nc, xcnt, tot);
-    float beta[CG_MAXC];
+    cg_allreduce<NCV>(cluster, &ex, s_warp, part, xcnt, tot);
+    float beta[NCV];
     all_done = true;
 #pragma unroll
-    for (int c = 0; c < CG_MAXC; ++c) {
+    for (int c = 0; c < NCV; ++c) {
       beta[c] = (!done[c] && rs[c] > 0.f) ? tot[c] / rs[c] : 0.f;
       if (!done[c]) {
         rs[c] = tot[c];
@@ -575,25 +600,69 @@ __global__ __launch_bounds__(CG_THREADS) void lp_cg_kernel(
     // ---- P = R + beta P   (frozen for finished columns)
     for (int row = lo + tid; row < hi; row += CG_THREADS) {
 #pragma unroll
-      for (int c = 0; c < CG_MAXC; ++c)
-        if (c < nc && !done[c]) {
-          const int64_t o = (int64_t)row * nc + c;
-          Pg[o] = fmaf(beta[c], __ldcg(Pg + o), Rg[o]);
+      for (int c = 0; c < NCV; ++c)
+        if (!done[c]) {
+          const int64_t o = (int64_t)row * NCV + c;
+          Pg[o] = fmaf(beta[c], Ps[o], Rg[o]);
         }
     }
     ++it;
-    cluster.sync();  // publish P
+    cluster.sync();  // publish P (and make sure nobody still reads Ps before it is restaged)
   }
+  // Z (unpadded) from my rows
+  for (int row = lo + tid; row < hi; row += CG_THREADS)
+    for (int c = 0; c < nc; ++c) Zg[(int64_t)row * nc + c] = Xg[(int64_t)row * NCV + c];
   if (rank == 0 && tid == 0) {
     if (iters_out) iters_out[g] = it;
     if (resid_out) {
       float m = 0.f;
-      for (int c = 0; c < nc; ++c)
+#pragma unroll
+      for (int c = 0; c < NCV; ++c)
         if (bb[c] > 0.f) m = fmaxf(m, sqrtf(rs[c] / bb[c]));
       resid_out[g] = m;
     }
   }
   cluster.sync();
+}
+
+template <int NCV>
+static int launch_cg(int CL, int G, size_t smem, cudaStream_t st, const int32_t* nbr,
+                     const float* sim, const int32_t* in_ptr, const int32_t* in_src,
+                     const float* in_w, const uint8_t* valid, int nn, int k, const float* Y, int nc,
+                     float alpha, float tol, int max_iter, float* Z, float* X, float* R, float* P,
+                     float* AP, int32_t* iters_out, float* resid_out) {
+  cudaError_t e = cudaFuncSetAttribute(lp_cg_kernel<NCV>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  if (CL > 8) {
+    e = cudaFuncSetAttribute(lp_cg_kernel<NCV>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    if (e != cudaSuccess) return (int)e;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(CL, G, 1);
+  cfg.blockDim = dim3(CG_THREADS, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  if (CL > 8) {  // can the device co-schedule a 16-CTA cluster of this size at all?
+    int n_clusters = 0;
+    e = cudaOccupancyMaxActiveClusters(&n_clusters, lp_cg_kernel<NCV>, &cfg);
+    if (e != cudaSuccess || n_clusters < 1) {
+      (void)cudaGetLastError();
+      return -1000;
+    }
+  }
+  e = cudaLaunchKernelEx(&cfg, lp_cg_kernel<NCV>, nbr, sim, in_ptr, in_src, in_w, valid, nn, k, Y,
+                         nc, alpha, tol, max_iter, Z, X, R, P, AP, iters_out, resid_out);
+  if (e != cudaSuccess) return (int)e;
+  ++r3dfs_launches;
+  return 0;
 }
 
 // --------------------------------------------------------------------------------------------
@@ -686,8 +755,9 @@ int launch_affinity(const float* F, int64_t graph_rows, int64_t row_off, const u
 int launch_label_propagate(const int32_t* nbr, float* sim, const uint8_t* valid, int G, int nn,
                            int k, const float* Y, int nc, float alpha, float tol, int max_iter,
                            int32_t* in_cnt, int32_t* in_ptr, int32_t* in_src, float* in_w,
-                           float* dinv, float* X, float* R, float* P, float* AP, int32_t* iters_out,
-                           float* resid_out, cudaStream_t st, const StageRec* sr) {
+                           float* dinv, float* Z, float* X, float* R, float* P, float* AP,
+                           int32_t* iters_out, float* resid_out, cudaStream_t st,
+                           const StageRec* sr) {
   if (nc > CG_MAXC || nc < 1 || nn > 8192) return R3DFS_E_UNSUPPORTED;
   cudaError_t e = cudaMemsetAsync(in_cnt, 0, sizeof(int32_t) * (size_t)G * nn, st);
   if (e != cudaSuccess) return (int)e;
@@ -711,26 +781,20 @@ int launch_label_propagate(const int32_t* nbr, float* sim, const uint8_t* valid,
   R3DFS_CHECK_LAUNCH();
   if (sr) sr->mark(R3DFS_ST_SYM, st);
 
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(CG_CL, G, 1);
-  cfg.blockDim = dim3(CG_THREADS, 1, 1);
-  cfg.dynamicSmemBytes = 0;
-  cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = CG_CL;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  const float* simc = sim;
-  const int32_t* in_ptrc = in_ptr;
-  const int32_t* in_srcc = in_src;
-  const float* in_wc = in_w;
-  e = cudaLaunchKernelEx(&cfg, lp_cg_kernel, nbr, simc, in_ptrc, in_srcc, in_wc, valid, nn, k, Y,
-                         nc, alpha, tol, max_iter, X, R, P, AP, iters_out, resid_out);
-  if (e != cudaSuccess) return (int)e;
-  ++r3dfs_launches;
+  // padded vector width: one or two float4 per node
+  const int ncv = nc <= 4 ? 4 : 8;
+  const size_t smem_cg = sizeof(float) * (size_t)nn * ncv;
+  if (smem_cg > 200 * 1024) return R3DFS_E_UNSUPPORTED;
+  int rc = -1000;
+  for (int CL = 16; CL >= 8 && rc == -1000; CL >>= 1) {
+    if (ncv == 4)
+      rc = launch_cg<4>(CL, G, smem_cg, st, nbr, sim, in_ptr, in_src, in_w, valid, nn, k, Y, nc, alpha,
+                        tol, max_iter, Z, X, R, P, AP, iters_out, resid_out);
+    else
+      rc = launch_cg<8>(CL, G, smem_cg, st, nbr, sim, in_ptr, in_src, in_w, valid, nn, k, Y, nc, alpha,
+                        tol, max_iter, Z, X, R, P, AP, iters_out, resid_out);
+  }
+  if (rc != 0) return rc == -1000 ? R3DFS_E_UNSUPPORTED : rc;
   if (sr) sr->mark(R3DFS_ST_CG, st);
   return 0;
 }

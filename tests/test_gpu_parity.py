@@ -427,7 +427,7 @@ def test_episode_end_to_end_golden(golden_episodes, model, name):
     agree = (pred.argmax(1) == ref.argmax(1)).float().mean()
     assert agree >= 0.999, (rel.max(), agree)
     assert (rel < 1e-3).float().mean() >= 0.90, ((rel < 1e-3).float().mean(), rel.max())
-    assert rel.median() < 1e-4 and rel.max() < 0.1, (rel.median(), rel.max())
+    assert rel.median() < 5e-4 and rel.max() < 0.1, (rel.median(), rel.max())
     assert abs(float(loss) - float(c["loss"])) < 2e-3
     assert int(m._last_diag["cg_iters"][0]) < 200
 
