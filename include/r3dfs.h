@@ -51,6 +51,12 @@ int r3dfs_knn(const float* x, int64_t B, int64_t C, int64_t N, int64_t sb, int64
               int64_t sn, int k, int64_t* idx_out, void* ws, size_t ws_bytes,
               r3dfs_stream_t stream);
 
+/* Same with the implementation pinned: impl 0 = default (tcgen05 kernel when C <= 64), 1 = FP32
+ * CUDA-core kernel, 2 = tensor-core kernel (R3DFS_E_UNSUPPORTED when C > 64). */
+int r3dfs_knn_ex(const float* x, int64_t B, int64_t C, int64_t N, int64_t sb, int64_t sc,
+                 int64_t sn, int k, int64_t* idx_out, int impl, void* ws, size_t ws_bytes,
+                 r3dfs_stream_t stream);
+
 /* get_edge_feature(x, K, idx) — models/dgcnn.py:26-42.  Materialises the (B, 2C, N, K)
  * contiguous edge tensor cat(x_j - x_i, x_i).  idx: (B, N, K) int64 contiguous. */
 int r3dfs_edge_feature(const float* x, int64_t B, int64_t C, int64_t N, int64_t sb, int64_t sc,
@@ -90,6 +96,12 @@ typedef struct r3dfs_weights {
 int r3dfs_linear(const float* x, int64_t ldx, const float* w, const float* s, const float* t,
                  int act, int64_t M, int64_t K, int64_t Nout, float* y, int64_t ldy,
                  r3dfs_stream_t stream);
+/* Same, with the implementation pinned: impl 0 = default (tcgen05 3xTF32 tensor-core kernel),
+ * 1 = FP32 CUDA-core kernel, 2 = tensor-core kernel.  Both are exact to FP32 rounding; the
+ * switch exists for A/B measurements and the parity tests. */
+int r3dfs_linear_ex(const float* x, int64_t ldx, const float* w, const float* s, const float* t,
+                    int act, int64_t M, int64_t K, int64_t Nout, float* y, int64_t ldy, int impl,
+                    r3dfs_stream_t stream);
 
 /* One fused EdgeConv block, eval BN: knn -> gather -> (W1, BN, LReLU) -> (W2, BN, LReLU) -> max
  * over k (models/dgcnn.py:115-118).  The (B, 2C, N, k) edge tensor is never formed.

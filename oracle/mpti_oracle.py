@@ -275,15 +275,20 @@ def label_propagate_dense(A: torch.Tensor, Y: torch.Tensor, alpha: float = 0.99,
 # ------------------------------------------------------------------------------------------------
 def forward_episode(sd: Dict[str, torch.Tensor], support_x, support_y, query_x, query_y,
                     n_subprototypes=100, k_connect=200, sigma=1.0, dgcnn_k=20, eval_mdns=True,
-                    keep: bool = False) -> Dict[str, object]:
+                    keep: bool = False, support_feat=None, query_feat=None) -> Dict[str, object]:
+    """`support_feat` (n_way*k_shot, D, N) / `query_feat` (n_query, D, N), when given, replace the
+    getFeatures calls (used to check the graph half on features produced elsewhere)."""
     n_way, k_shot = support_y.shape[:2]
     N = support_y.shape[-1]
     n_cls = n_way + 1
     sx = support_x.reshape(n_way * k_shot, -1, N)
-    support_feat = get_features(sx, sd, dgcnn_k)
+    if support_feat is None:
+        support_feat = get_features(sx, sd, dgcnn_k)
     D = support_feat.shape[1]
-    support_feat = support_feat.view(n_way, k_shot, D, N)
-    query_feat = get_features(query_x, sd, dgcnn_k).transpose(1, 2).contiguous().view(-1, D)
+    support_feat = support_feat.reshape(n_way, k_shot, D, N)
+    if query_feat is None:
+        query_feat = get_features(query_x, sd, dgcnn_k)
+    query_feat = query_feat.transpose(1, 2).contiguous().view(-1, D)
     out: Dict[str, object] = {}
     pl, clean = None, None
     if eval_mdns:

