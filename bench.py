@@ -221,6 +221,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--episodes", type=int, default=100, help="episodes per step per GPU")
     ap.add_argument("--chunk", type=int, default=20, help="episodes per C-ABI call")
+    ap.add_argument("--streams", type=int, default=2,
+                    help="CUDA streams the chunks of a step are spread over (independent episodes)")
     ap.add_argument("--cpu-episodes", type=int, default=3, help="cpu_baseline sample size")
     ap.add_argument("--ref-episodes-per-step", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -265,6 +267,7 @@ def main():
     ws = torch.empty(_lib.lib().r3dfs_mpti_workspace(cfg, chunk), dtype=torch.uint8, device=dev)
     flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
     chunks = [(s, min(s + chunk, E_step)) for s in range(0, E_step, chunk)]
+    preds = [None] * len(chunks)
     n_stage = len(_lib.STAGES)
 
     def new_events():
@@ -273,13 +276,36 @@ def main():
             e.record()  # materialise the cudaEvent_t handle
         return evs
 
+    n_streams = max(1, min(args.streams, len(chunks)))
+    streams = [torch.cuda.Stream(device=dev) for _ in range(n_streams)]
+    wss = [ws] + [torch.empty_like(ws) for _ in range(n_streams - 1)]
+
     def run_step_resident(stage_ev=None):
-        for ci, (a, b) in enumerate(chunks):
-            out = model.forward_episodes(d_sx[a:b].transpose(3, 4), d_sy[a:b],
-                                         d_qx[a:b].transpose(2, 3), d_qy[a:b], eval=True,
-                                         workspace=ws,
-                                         stage_events=None if stage_ev is None else stage_ev[ci])
-            ops.confusion_accumulate(out["pred"], d_qy[a:b], d_slot[a:b], step_counters)
+        """Chunks are independent episodes: they are spread round-robin over `n_streams` streams
+        (each with its own workspace) so latency-bound kernels of one chunk overlap the other's.
+        With stage events the chunks run serialised on the current stream (clean per-stage times)."""
+        if stage_ev is not None or n_streams == 1:
+            for ci, (a, b) in enumerate(chunks):
+                out = model.forward_episodes(d_sx[a:b].transpose(3, 4), d_sy[a:b],
+                                             d_qx[a:b].transpose(2, 3), d_qy[a:b], eval=True,
+                                             workspace=ws,
+                                             stage_events=None if stage_ev is None else stage_ev[ci])
+                ops.confusion_accumulate(out["pred"], d_qy[a:b], d_slot[a:b], step_counters)
+        else:
+            cur = torch.cuda.current_stream()
+            for s in streams:
+                s.wait_stream(cur)
+            for ci, (a, b) in enumerate(chunks):
+                s = streams[ci % n_streams]
+                with torch.cuda.stream(s):
+                    out = model.forward_episodes(d_sx[a:b].transpose(3, 4), d_sy[a:b],
+                                                 d_qx[a:b].transpose(2, 3), d_qy[a:b], eval=True,
+                                                 workspace=wss[ci % n_streams])
+                    preds[ci] = out["pred"]
+            for s in streams:
+                cur.wait_stream(s)
+            for ci, (a, b) in enumerate(chunks):
+                ops.confusion_accumulate(preds[ci], d_qy[a:b], d_slot[a:b], step_counters)
         if dist is not None:
             dist.all_reduce(step_counters, op=dist.ReduceOp.SUM)  # the path's only collective
         counters.add_(step_counters)
@@ -289,15 +315,24 @@ def main():
     h_loss = torch.empty((E_step,), dtype=torch.float32).pin_memory()
 
     def run_step_e2e():
-        for a, b in chunks:
-            sx = h_sx[a:b].to(dev, non_blocking=True)
-            sy = h_sy[a:b].to(dev, non_blocking=True)
-            qx = h_qx[a:b].to(dev, non_blocking=True)
-            qy = h_qy[a:b].to(dev, non_blocking=True)
-            out = model.forward_episodes(sx.transpose(3, 4), sy, qx.transpose(2, 3), qy, eval=True,
-                                         workspace=ws)
-            h_pred[a:b].copy_(out["pred"], non_blocking=True)
-            h_loss[a:b].copy_(out["loss"], non_blocking=True)
+        cur = torch.cuda.current_stream()
+        for s in streams:
+            s.wait_stream(cur)
+        for ci, (a, b) in enumerate(chunks):
+            s = streams[ci % n_streams]
+            with torch.cuda.stream(s):
+                sx = h_sx[a:b].to(dev, non_blocking=True)
+                sy = h_sy[a:b].to(dev, non_blocking=True)
+                qx = h_qx[a:b].to(dev, non_blocking=True)
+                qy = h_qy[a:b].to(dev, non_blocking=True)
+                out = model.forward_episodes(sx.transpose(3, 4), sy, qx.transpose(2, 3), qy,
+                                             eval=True, workspace=wss[ci % n_streams])
+                h_pred[a:b].copy_(out["pred"], non_blocking=True)
+                h_loss[a:b].copy_(out["loss"], non_blocking=True)
+                for t_ in (sx, sy, qx, qy, out["pred"], out["loss"], out["logits"]):
+                    t_.record_stream(s)
+        for s in streams:
+            cur.wait_stream(s)
 
     def sync_all():
         torch.cuda.synchronize()
@@ -326,11 +361,16 @@ def main():
     for s in range(args.steps):
         flush.zero_()
         t_ev[s][0].record()
-        run_step_resident(step_events[s])
+        run_step_resident()
         t_ev[s][1].record()
     sync_all()
     wall_resident = time.perf_counter() - wall0
     launches = L.r3dfs_launch_count() - launches0
+    # per-stage device times: the same K steps again, serialised on one stream with stage events
+    for s in range(args.steps):
+        flush.zero_()
+        run_step_resident(step_events[s])
+    sync_all()
     ms_steps = [a.elapsed_time(b) for a, b in t_ev]
     total_ms = float(sum(ms_steps))
 
@@ -423,7 +463,8 @@ def main():
                                    "way, k_connect 200 (BASELINE.json configs[2])",
                        "episodes_per_step_per_gpu": E_step, "episodes_per_call": chunk,
                        "n_points": N_PTS, "weights": "seeded fixture (tests/golden/weights_fixture.pt)",
-                       "l2": "512 MiB flush write between timed steps", "sharding": "episodes"},
+                       "l2": "512 MiB flush write between timed steps", "sharding": "episodes",
+                       "streams": n_streams},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches),

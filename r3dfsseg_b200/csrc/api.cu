@@ -70,7 +70,7 @@ __global__ void i32_to_i64_kernel(const int32_t* __restrict__ a, int64_t* __rest
 
 thread_local long long r3dfs_launches = 0;
 
-static bool simt_gemm_forced() {
+bool simt_gemm_forced() {
   static const bool v = [] {
     const char* e = getenv("R3DFS_SIMT_GEMM");
     return e && e[0] == '1';
@@ -84,6 +84,14 @@ int launch_knn_auto(const float* x, int ld, int C, const float* xx, int64_t B, i
   if (impl == 0 && !simt_gemm_forced() && C <= 64)
     return launch_knn_tc(x, ld, C, xx, B, N, k, idx32, idx64, st);
   return launch_knn(x, ld, C, xx, B, N, k, idx32, idx64, st);
+}
+
+int launch_edge_mlp_auto(const float* PQ, const int32_t* idx, const float* w2, const float* s2,
+                         const float* t2, int64_t B, int N, int k, float* Y, int ldy, RowMap map,
+                         cudaStream_t st) {
+  if (simt_gemm_forced())
+    return launch_edge_mlp(PQ, idx, w2, s2, t2, B, N, k, Y, ldy, map, nullptr, st);
+  return launch_edge_mlp_tc(PQ, idx, w2, s2, t2, B, N, k, Y, ldy, map, st);
 }
 
 int launch_linear_auto(const float* X, int ldx, const float* W, const float* s, const float* t,
@@ -159,8 +167,8 @@ static int encoder_forward(const r3dfs_weights_t* w, const float* xp, int64_t B,
     R3DFS_TRY(launch_linear_auto(in, ld, e.wpq, e.spq, e.tpq, ACT_NONE, M, C, 128, e.PQ, 128,
                             identity_map(), st));
     if (sr) sr->mark(R3DFS_ST_PQ0 + 3 * i, st);
-    R3DFS_TRY(launch_edge_mlp(e.PQ, e.idx, w->ec_w2[i], w->ec_s2[i], w->ec_t2[i], B, N, k,
-                              e.ecat + 64 * i, 192, identity_map(), nullptr, st));
+    R3DFS_TRY(launch_edge_mlp_auto(e.PQ, e.idx, w->ec_w2[i], w->ec_s2[i], w->ec_t2[i], B, N, k,
+                                   e.ecat + 64 * i, 192, identity_map(), st));
     if (sr) sr->mark(R3DFS_ST_EDGE0 + 3 * i, st);
   }
   // level-1 feature = first EdgeConv output (models/dgcnn.py:127, models/mpti.py:586-589)
@@ -305,7 +313,7 @@ int r3dfs_edgeconv(const float* x, int64_t B, int64_t C, int64_t N, int64_t sb, 
   R3DFS_TRY(launch_fold_edge_w1(w1, s1, t1, (int)C, wpq, spq, tpq, st));
   R3DFS_TRY(launch_linear_auto(xp, (int)C, wpq, spq, tpq, ACT_NONE, M, (int)C, 128, PQ, 128,
                                identity_map(), st));
-  return launch_edge_mlp(PQ, idx, w2, s2, t2, B, (int)N, k, y, 64, identity_map(), nullptr, st);
+  return launch_edge_mlp_auto(PQ, idx, w2, s2, t2, B, (int)N, k, y, 64, identity_map(), st);
 }
 
 // ---- attention ----------------------------------------------------------------------------------

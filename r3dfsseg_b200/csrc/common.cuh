@@ -99,6 +99,15 @@ int launch_linear_tc(const float* X, int ldx, const float* W, const float* s, co
 int launch_linear_auto(const float* X, int ldx, const float* W, const float* s, const float* t,
                        int act, int64_t M, int K, int Nout, float* Y, int ldy, RowMap map,
                        cudaStream_t st);
+int launch_gram_dist_tc(const float* F, int64_t graph_rows, int64_t row_off, int G, int nn, int D,
+                        const float* norms, float* D2, cudaStream_t st);
+int launch_edge_mlp_tc(const float* PQ, const int32_t* idx, const float* w2, const float* s2,
+                       const float* t2, int64_t B, int N, int k, float* Y, int ldy, RowMap map,
+                       cudaStream_t st);
+int launch_edge_mlp_auto(const float* PQ, const int32_t* idx, const float* w2, const float* s2,
+                         const float* t2, int64_t B, int N, int k, float* Y, int ldy, RowMap map,
+                         cudaStream_t st);
+bool simt_gemm_forced();
 int launch_edge_mlp(const float* PQ, const int32_t* idx, const float* w2, const float* s2,
                     const float* t2, int64_t B, int N, int k, float* Y, int ldy, RowMap map,
                     float* w2t_scratch, cudaStream_t st);

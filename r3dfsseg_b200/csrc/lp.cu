@@ -734,9 +734,13 @@ int launch_affinity(const float* F, int64_t graph_rows, int64_t row_off, const u
   for (int g = 0; g < G; ++g)
     R3DFS_TRY(launch_row_norms(F + ((int64_t)g * graph_rows + row_off) * D, nn, D, D,
                                norms + (int64_t)g * nn, st));
-  dim3 gd((nn + GD_BM - 1) / GD_BM, (nn + GD_BN - 1) / GD_BN, G);
-  gram_dist_kernel<<<gd, 256, 0, st>>>(F, graph_rows, row_off, nn, D, norms, D2);
-  R3DFS_CHECK_LAUNCH();
+  if (simt_gemm_forced()) {
+    dim3 gd((nn + GD_BM - 1) / GD_BM, (nn + GD_BN - 1) / GD_BN, G);
+    gram_dist_kernel<<<gd, 256, 0, st>>>(F, graph_rows, row_off, nn, D, norms, D2);
+    R3DFS_CHECK_LAUNCH();
+  } else {
+    R3DFS_TRY(launch_gram_dist_tc(F, graph_rows, row_off, G, nn, D, norms, D2, st));
+  }
   if (sr) sr->mark(R3DFS_ST_DIST, st);
   size_t smem = sizeof(unsigned) * (size_t)nn;
   cudaError_t e = cudaFuncSetAttribute(knn_select_kernel,

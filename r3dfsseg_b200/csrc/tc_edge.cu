@@ -1,0 +1,229 @@
+// EdgeConv tail on the tensor cores (reference models/dgcnn.py:56-57 second conv + BN + LeakyReLU,
+// :118 max over the k neighbours), fused with the neighbour gather:
+//     h1(i, j) = LReLU(P[nbr(i, j)] + Q[i])           (first conv already applied per point)
+//     y(i)     = max_j LReLU(s2 * (W2 h1(i, j)) + t2)
+// The (B, 64, N, k) edge activations only ever exist as UMMA operand tiles in shared memory and as
+// accumulators in TMEM.
+//
+// One CTA walks over groups of 32 points.  A 128-row MMA tile = 4 neighbour slots x 32 points
+// (row = slot_in_tile * 32 + point), so TMEM lane quarter q (epilogue warp q) holds neighbour slot
+// 4t + q of tile t for the 32 points, one point per thread: the max over neighbours is a running
+// max in registers across the ceil(k/4) tiles plus one 4-way exchange through shared memory.
+//   warps 4-11: gather P rows, add Q, LeakyReLU, TF32 hi/lo split, store the A tile (2 stages);
+//              one thread issues 3 x 8 tcgen05.mma (3xTF32, K = 64) per tile against the resident
+//              W2 tile and commits to an mbarrier;
+//   warps 0-3: tcgen05.ld the 64 output channels of their row, BN affine + LeakyReLU, running max.
+#include "common.cuh"
+#include "tc.cuh"
+
+#define ET_THREADS 384  // warps 0-3 epilogue, warps 4-11 producers
+#define ET_PRODUCERS 256
+#define ET_GROUP 32  // points per group
+
+struct EdgeTcSmem {
+  static constexpr int A_TILE = tc::tile_bytes(128, 16);  // one of hi / lo, K = 64
+  static constexpr int W_TILE = tc::tile_bytes(64, 16);
+  static constexpr int A_OFF = 0;                   // 2 stages x (hi, lo)
+  static constexpr int W_OFF = 4 * A_TILE;          // W2 hi, lo
+  static constexpr int X_OFF = W_OFF + 2 * W_TILE;  // exchange [4][64][32] float
+  static constexpr int TOTAL = X_OFF + 4 * 64 * 32 * 4 + 64;
+};
+
+__device__ __forceinline__ void et_mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc::smem_u32(bar)) : "memory");
+}
+
+__global__ __launch_bounds__(ET_THREADS, 1) void edge_tc_kernel(
+    const float* __restrict__ PQ, const int32_t* __restrict__ idx, const float* __restrict__ w2,
+    const float* __restrict__ s2, const float* __restrict__ t2, int N, int k, int groups_per_cta,
+    float* __restrict__ Y, int ldy, RowMap map) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  using S = EdgeTcSmem;
+  __shared__ uint64_t bar_full[2];
+  __shared__ uint64_t bar_tfree[2];
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int b = blockIdx.y;
+  const int64_t base = (int64_t)b * N;
+  const int n_groups = (N + ET_GROUP - 1) / ET_GROUP;
+  const int g_begin = blockIdx.x * groups_per_cta;
+  const int g_end = min(n_groups, g_begin + groups_per_cta);
+  const int TPG = (k + 3) / 4;  // tiles per group
+  const int U = (g_end - g_begin) * TPG;
+  constexpr int LBO_A = tc::tile_lbo(128), LBO_W = tc::tile_lbo(64);
+  constexpr uint32_t IDESC = tc::make_idesc_tf32(128, 64);
+
+  if (tid == 0) {
+    tc::mbar_init(&bar_full[0], 1);
+    tc::mbar_init(&bar_full[1], 1);
+    tc::mbar_init(&bar_tfree[0], 128);
+    tc::mbar_init(&bar_tfree[1], 128);
+    tc::mbar_fence_init();
+  }
+  if (w == 0) tc::tmem_alloc(&tmem_base_s, 128);
+  // resident W2 (64 x 64, row-major [c][kk] = K-major) as hi / lo tiles
+  for (int c = tid; c < 64 * 16; c += ET_THREADS) {
+    const int r = c >> 4, kc = c & 15;
+    const float4 v = *reinterpret_cast<const float4*>(w2 + r * 64 + 4 * kc);
+    float4 hi, lo;
+    tc::split4(v, hi, lo);
+    *reinterpret_cast<float4*>(smem + S::W_OFF + kc * LBO_W + r * 16) = hi;
+    *reinterpret_cast<float4*>(smem + S::W_OFF + S::W_TILE + kc * LBO_W + r * 16) = lo;
+  }
+  tc::fence_async_smem();
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_d = tmem_base_s;
+  if (U <= 0) {
+    if (w == 0) tc::tmem_dealloc(tmem_d, 128);
+    return;
+  }
+
+  if (w >= 4) {
+    // --------------------------- producers + MMA issue --------------------------------------
+    const int lt = tid - 128;
+    constexpr int NCH = 128 * 16 / ET_PRODUCERS;  // float4 chunks per producer thread per tile (8)
+    // neighbour indices are fetched one tile ahead so the gather below never waits on them
+    int nb[NCH];
+    auto load_nb = [&](int u2) {
+      const int g2 = g_begin + u2 / TPG, t2i = u2 % TPG;
+#pragma unroll
+      for (int i = 0; i < NCH; ++i) {
+        const int r = (lt + i * ET_PRODUCERS) >> 4;
+        const int p = g2 * ET_GROUP + (r & 31), j = 4 * t2i + (r >> 5);
+        nb[i] = (u2 < U && p < N && j < k) ? idx[(base + p) * k + j] : -1;
+      }
+    };
+    load_nb(0);
+    for (int u = 0; u < U; ++u) {
+      const int st = u & 1;
+      const int g = g_begin + u / TPG;
+      const int p0 = g * ET_GROUP;
+      float4 hv[NCH];
+#pragma unroll
+      for (int i = 0; i < NCH; ++i) {
+        const int c = lt + i * ET_PRODUCERS;
+        const int r = c >> 4, kc = c & 15;
+        const int p = p0 + (r & 31);
+        float4 h = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (nb[i] >= 0) {
+          const float4 a = *reinterpret_cast<const float4*>(PQ + (base + nb[i]) * 128 + 4 * kc);
+          const float4 q = *reinterpret_cast<const float4*>(PQ + (base + p) * 128 + 64 + 4 * kc);
+          h.x = a.x + q.x; h.y = a.y + q.y; h.z = a.z + q.z; h.w = a.w + q.w;
+          h.x = h.x > 0.f ? h.x : 0.2f * h.x;
+          h.y = h.y > 0.f ? h.y : 0.2f * h.y;
+          h.z = h.z > 0.f ? h.z : 0.2f * h.z;
+          h.w = h.w > 0.f ? h.w : 0.2f * h.w;
+        }
+        hv[i] = h;
+      }
+      load_nb(u + 1);
+      if (u >= 2) tc::mbar_wait(&bar_full[st], ((u >> 1) - 1) & 1);  // stage's MMAs finished
+      unsigned char* a_hi = smem + S::A_OFF + st * 2 * S::A_TILE;
+      unsigned char* a_lo = a_hi + S::A_TILE;
+#pragma unroll
+      for (int i = 0; i < NCH; ++i) {
+        const int c = lt + i * ET_PRODUCERS;
+        const int r = c >> 4, kc = c & 15;
+        float4 hi, lo;
+        tc::split4(hv[i], hi, lo);
+        *reinterpret_cast<float4*>(a_hi + kc * LBO_A + r * 16) = hi;
+        *reinterpret_cast<float4*>(a_lo + kc * LBO_A + r * 16) = lo;
+      }
+      tc::fence_async_smem();
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (lt == 0) {
+        if (u >= 2) tc::mbar_wait(&bar_tfree[st], ((u >> 1) - 1) & 1);  // accumulator drained
+        tc::tc_fence_after();
+        const uint32_t ah = tc::smem_u32(a_hi), al = ah + S::A_TILE;
+        const uint32_t wh = tc::smem_u32(smem + S::W_OFF), wl = wh + S::W_TILE;
+        const uint32_t d = tmem_d + st * 64;
+#pragma unroll 1
+        for (int ks = 0; ks < 8; ++ks) {
+          const uint64_t dah = tc::make_desc(ah + ks * 2 * LBO_A, LBO_A, 128);
+          const uint64_t dal = tc::make_desc(al + ks * 2 * LBO_A, LBO_A, 128);
+          const uint64_t dwh = tc::make_desc(wh + ks * 2 * LBO_W, LBO_W, 128);
+          const uint64_t dwl = tc::make_desc(wl + ks * 2 * LBO_W, LBO_W, 128);
+          tc::mma_tf32(d, dal, dwh, IDESC, ks != 0);
+          tc::mma_tf32(d, dah, dwl, IDESC, 1);
+          tc::mma_tf32(d, dah, dwh, IDESC, 1);
+        }
+        tc::mma_commit(&bar_full[st]);
+      }
+    }
+  } else {
+    // --------------------------- epilogue: thread = (neighbour slot q, point) -----------------
+    float* xch = reinterpret_cast<float*>(smem + S::X_OFF);  // [4][64][32]
+    float mx[64];
+    for (int u = 0; u < U; ++u) {
+      const int st = u & 1;
+      const int g = g_begin + u / TPG, t = u % TPG;
+      if (t == 0) {
+#pragma unroll
+        for (int c = 0; c < 64; ++c) mx[c] = -INFINITY;
+      }
+      tc::mbar_wait(&bar_full[st], (u >> 1) & 1);
+      tc::tc_fence_after();
+      const bool live = (4 * t + w) < k;  // warp-uniform
+#pragma unroll
+      for (int cc = 0; cc < 64; cc += 32) {
+        float v[32];
+        tc::tmem_ld32(tmem_d + ((uint32_t)(32 * w) << 16) + (uint32_t)(st * 64 + cc), v);
+        if (live) {
+#pragma unroll
+          for (int e = 0; e < 32; ++e) {
+            float y = fmaf(__ldg(s2 + cc + e), v[e], __ldg(t2 + cc + e));
+            y = y > 0.f ? y : 0.2f * y;
+            mx[cc + e] = fmaxf(mx[cc + e], y);
+          }
+        }
+      }
+      tc::tc_fence_before();
+      et_mbar_arrive(&bar_tfree[st]);
+      if (t == TPG - 1) {
+        // 4-way max across the neighbour-slot warps, then each thread writes 16 channels of a point
+#pragma unroll
+        for (int c = 0; c < 64; ++c) xch[(w * 64 + c) * 32 + lane] = mx[c];
+        asm volatile("bar.sync 2, 128;" ::: "memory");
+        const int p = g * ET_GROUP + lane;
+        if (p < N) {
+          float o[16];
+#pragma unroll
+          for (int c = 0; c < 16; ++c) {
+            const int ch = 16 * w + c;
+            o[c] = fmaxf(fmaxf(xch[(0 * 64 + ch) * 32 + lane], xch[(1 * 64 + ch) * 32 + lane]),
+                         fmaxf(xch[(2 * 64 + ch) * 32 + lane], xch[(3 * 64 + ch) * 32 + lane]));
+          }
+          float* y = Y + map(base + p) * (int64_t)ldy + 16 * w;
+#pragma unroll
+          for (int c = 0; c < 16; c += 4)
+            *reinterpret_cast<float4*>(y + c) = make_float4(o[c], o[c + 1], o[c + 2], o[c + 3]);
+        }
+        asm volatile("bar.sync 2, 128;" ::: "memory");  // exchange buffer free for the next group
+      }
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (w == 0) tc::tmem_dealloc(tmem_d, 128);
+}
+
+int launch_edge_mlp_tc(const float* PQ, const int32_t* idx, const float* w2, const float* s2,
+                       const float* t2, int64_t B, int N, int k, float* Y, int ldy, RowMap map,
+                       cudaStream_t st) {
+  if (k < 1 || k > 32) return R3DFS_E_UNSUPPORTED;
+  cudaError_t e = cudaFuncSetAttribute(edge_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       EdgeTcSmem::TOTAL);
+  if (e != cudaSuccess) return (int)e;
+  const int n_groups = (N + ET_GROUP - 1) / ET_GROUP;
+  // enough CTAs to fill the machine a few times over, but several groups per CTA so the W2 tile,
+  // the TMEM allocation and the pipeline prologue are amortised
+  int gpc = 4;
+  while (gpc > 1 && (int64_t)B * ((n_groups + gpc - 1) / gpc) < 2 * 148) gpc >>= 1;
+  dim3 grid((n_groups + gpc - 1) / gpc, (unsigned)B);
+  edge_tc_kernel<<<grid, ET_THREADS, EdgeTcSmem::TOTAL, st>>>(PQ, idx, w2, s2, t2, N, k, gpc, Y,
+                                                             ldy, map);
+  R3DFS_CHECK_LAUNCH();
+  return 0;
+}

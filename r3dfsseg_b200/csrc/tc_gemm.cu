@@ -41,12 +41,20 @@ __device__ __forceinline__ float4 ld_chunk(const float* __restrict__ src, int64_
   return v;
 }
 
-template <int BN>
+// DIST = true turns the epilogue into the squared-distance form used by the affinity graph:
+//     Y[m][n] = (s[m] + t[n]) - 2 * acc      with s = t = squared row norms,
+// and blockIdx.z walks over independent problems `zs` elements apart (X, W, s, t, Y alike).
+template <int BN, bool DIST>
 __global__ __launch_bounds__(TCG_THREADS, 1) void linear_tc_kernel(
     const float* __restrict__ X, int ldx, const float* __restrict__ W, const float* __restrict__ s,
     const float* __restrict__ t, int act, int64_t M, int K, int Nout, float* __restrict__ Y,
-    int ldy, RowMap map) {
+    int ldy, RowMap map, int64_t zs_x, int64_t zs_w, int64_t zs_v, int64_t zs_y) {
   extern __shared__ __align__(128) unsigned char smem[];
+  X += blockIdx.z * zs_x;
+  W += blockIdx.z * zs_w;
+  Y += blockIdx.z * zs_y;
+  if (s) s += blockIdx.z * zs_v;
+  if (t) t += blockIdx.z * zs_v;
   using S = TcgSmem<BN>;
   __shared__ uint64_t bar_mma[2];
   __shared__ uint32_t tmem_base_s;
@@ -155,8 +163,12 @@ __global__ __launch_bounds__(TCG_THREADS, 1) void linear_tc_kernel(
         for (int j = 0; j < 32; ++j) {
           const int n = nb + j;
           if (n < Nout) {
-            const float sc = s ? s[n] : 1.f, sh = t ? t[n] : 0.f;
-            v[j] = apply_act(fmaf(sc, v[j], sh), act);
+            if (DIST) {
+              v[j] = (s[m] + t[n]) - 2.f * v[j];
+            } else {
+              const float sc = s ? s[n] : 1.f, sh = t ? t[n] : 0.f;
+              v[j] = apply_act(fmaf(sc, v[j], sh), act);
+            }
           }
         }
         if (vec_y) {
@@ -180,12 +192,28 @@ static int launch_linear_tc_bn(const float* X, int ldx, const float* W, const fl
                                const float* t, int act, int64_t M, int K, int Nout, float* Y,
                                int ldy, RowMap map, cudaStream_t st) {
   using S = TcgSmem<BN>;
-  cudaError_t e = cudaFuncSetAttribute(linear_tc_kernel<BN>,
+  cudaError_t e = cudaFuncSetAttribute(linear_tc_kernel<BN, false>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
   if (e != cudaSuccess) return (int)e;
   dim3 grid((unsigned)((M + TCG_BM - 1) / TCG_BM), (Nout + BN - 1) / BN);
-  linear_tc_kernel<BN><<<grid, TCG_THREADS, S::TOTAL, st>>>(X, ldx, W, s, t, act, M, K, Nout, Y,
-                                                            ldy, map);
+  linear_tc_kernel<BN, false><<<grid, TCG_THREADS, S::TOTAL, st>>>(X, ldx, W, s, t, act, M, K, Nout,
+                                                                   Y, ldy, map, 0, 0, 0, 0);
+  R3DFS_CHECK_LAUNCH();
+  return 0;
+}
+
+// D2[g][i][j] = |f_i|^2 + |f_j|^2 - 2 f_i.f_j for G graphs of nn nodes (rows of D floats)
+int launch_gram_dist_tc(const float* F, int64_t graph_rows, int64_t row_off, int G, int nn, int D,
+                        const float* norms, float* D2, cudaStream_t st) {
+  using S = TcgSmem<128>;
+  cudaError_t e = cudaFuncSetAttribute(linear_tc_kernel<128, true>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
+  if (e != cudaSuccess) return (int)e;
+  const float* F0 = F + row_off * D;
+  dim3 grid((nn + TCG_BM - 1) / TCG_BM, (nn + 127) / 128, G);
+  linear_tc_kernel<128, true><<<grid, TCG_THREADS, S::TOTAL, st>>>(
+      F0, D, F0, norms, norms, 0, nn, D, nn, D2, nn, identity_map(), graph_rows * D,
+      graph_rows * D, nn, (int64_t)nn * nn);
   R3DFS_CHECK_LAUNCH();
   return 0;
 }

@@ -15,16 +15,16 @@
 
 #define KT_TQ 128
 #define KT_TC 128
-#define KT_THREADS 256
+#define KT_THREADS 384  // warps 0-7 selectors (2 per TMEM lane quarter), warps 8-11 loaders
 
 template <int KC4>
 struct KnnTcSmem {
   static constexpr int TILE = tc::tile_bytes(128, KC4);  // one of hi / lo
   static constexpr int Q_OFF = 0;                        // Q hi, Q lo
   static constexpr int B_OFF = 2 * TILE;                 // 2 stages x (hi, lo)
-  static constexpr int QV_OFF = B_OFF + 4 * TILE;        // queue values  [32][128] float
-  static constexpr int QI_OFF = QV_OFF + 32 * 128 * 4;   // queue columns [32][128] uint8
-  static constexpr int TOTAL = QI_OFF + 32 * 128 + 64;
+  static constexpr int QV_OFF = B_OFF + 4 * TILE;        // queue values  [16][256] float
+  static constexpr int QI_OFF = QV_OFF + 16 * 256 * 4;   // queue columns [16][256] uint8
+  static constexpr int TOTAL = QI_OFF + 16 * 256 + 64;   // (the queue is reused for the final merge)
 };
 
 template <int KC4>
@@ -104,8 +104,8 @@ __global__ __launch_bounds__(KT_THREADS, 1) void knn_tc_kernel(const float* __re
   if (tid == 0) {
     tc::mbar_init(&bar_full[0], 1);
     tc::mbar_init(&bar_full[1], 1);
-    tc::mbar_init(&bar_tfree[0], 128);
-    tc::mbar_init(&bar_tfree[1], 128);
+    tc::mbar_init(&bar_tfree[0], 256);
+    tc::mbar_init(&bar_tfree[1], 256);
     tc::mbar_fence_init();
   }
   if (w == 0) tc::tmem_alloc(&tmem_base_s, 2 * KT_TC);
@@ -118,9 +118,9 @@ __global__ __launch_bounds__(KT_THREADS, 1) void knn_tc_kernel(const float* __re
   tc::tc_fence_after();
   const uint32_t tmem_d = tmem_base_s;
 
-  if (w >= 4) {
+  if (w >= 8) {
     // ------------------------------ loaders + MMA issue -------------------------------------
-    const int lt = tid - 128;
+    const int lt = tid - 256;
     for (int j = 0; j < T; ++j) {
       const int st = j & 1;
       if (j >= 2) tc::mbar_wait(&bar_full[st], ((j >> 1) - 1) & 1);  // stage's previous MMAs done
@@ -148,11 +148,17 @@ __global__ __launch_bounds__(KT_THREADS, 1) void knn_tc_kernel(const float* __re
       }
     }
   } else {
-    // ------------------------------ selectors: thread = query row ------------------------------
+    // ------------------------------ selectors ------------------------------------------------
+    // thread = (query row, column half): warps w and w+4 share TMEM lane quarter w%4; warp w < 4
+    // scans columns 0..63 of every tile, warp w >= 4 columns 64..127; the two partial k-lists of a
+    // row are merged through shared memory at the end.
     float* qv = reinterpret_cast<float*>(smem + S::QV_OFF);
     unsigned char* qi = smem + S::QI_OFF;
-    const int q = q0 + tid;
+    const int row = 32 * (w & 3) + lane;
+    const int half = w >> 2;
+    const int q = q0 + row;
     const float nq = (q < N) ? -xx[base + q] : 0.f;
+    const bool vecn = (N & 3) == 0;
     float lv[KL];
     int li[KL];
 #pragma unroll
@@ -166,54 +172,76 @@ __global__ __launch_bounds__(KT_THREADS, 1) void knn_tc_kernel(const float* __re
       tc::tc_fence_after();
       const int c0 = j * KT_TC;
 #pragma unroll 1
-      for (int cc = 0; cc < KT_TC; cc += 32) {
+      for (int cc = 64 * half; cc < 64 * half + 64; cc += 32) {
         float v[32];
-        tc::tmem_ld32(tmem_d + ((uint32_t)(32 * w) << 16) + (uint32_t)(st * KT_TC + cc), v);
-        const float thr = lv[KL - 1];
-        int cnt = 0;
+        tc::tmem_ld32(tmem_d + ((uint32_t)(32 * (w & 3)) << 16) + (uint32_t)(st * KT_TC + cc), v);
+        // 16 columns at a time: queue what beats the current k-th best, then merge the queue
 #pragma unroll
-        for (int u = 0; u < 32; u += 4) {
-          const int cg = c0 + cc + u;
-          float4 cn = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (cg + 3 < N && (N & 3) == 0) {
-            cn = __ldg(reinterpret_cast<const float4*>(xx + base + cg));
-          } else {
-            if (cg + 0 < N) cn.x = xx[base + cg + 0];
-            if (cg + 1 < N) cn.y = xx[base + cg + 1];
-            if (cg + 2 < N) cn.z = xx[base + cg + 2];
-            if (cg + 3 < N) cn.w = xx[base + cg + 3];
-          }
-          const float cnv[4] = {cn.x, cn.y, cn.z, cn.w};
+        for (int hh = 0; hh < 32; hh += 16) {
+          const float thr = lv[KL - 1];
+          int cnt = 0;
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            // reference key: -xx_i - (-2 x_i.x_j) - xx_j
-            const float inner = -2.f * v[u + e];
-            const float key = (nq - inner) - cnv[e];
-            if (key > thr && cg + e < N) {
-              qv[cnt * 128 + tid] = key;
-              qi[cnt * 128 + tid] = (unsigned char)(cc + u + e);
-              ++cnt;
+          for (int u = hh; u < hh + 16; u += 4) {
+            const int cg = c0 + cc + u;
+            float4 cn = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (cg + 3 < N && vecn) {
+              cn = __ldg(reinterpret_cast<const float4*>(xx + base + cg));
+            } else {
+              if (cg + 0 < N) cn.x = xx[base + cg + 0];
+              if (cg + 1 < N) cn.y = xx[base + cg + 1];
+              if (cg + 2 < N) cn.z = xx[base + cg + 2];
+              if (cg + 3 < N) cn.w = xx[base + cg + 3];
+            }
+            const float cnv[4] = {cn.x, cn.y, cn.z, cn.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              // reference key: -xx_i - (-2 x_i.x_j) - xx_j
+              const float inner = -2.f * v[u + e];
+              const float key = (nq - inner) - cnv[e];
+              if (key > thr && cg + e < N) {
+                qv[cnt * 256 + tid] = key;
+                qi[cnt * 256 + tid] = (unsigned char)(cc + u + e);
+                ++cnt;
+              }
             }
           }
-        }
-        const int mx = __reduce_max_sync(0xffffffffu, cnt);
-        for (int e = 0; e < mx; ++e) {
-          if (e < cnt) {
-            const float key = qv[e * 128 + tid];
-            if (key > lv[KL - 1]) list_insert<KL>(lv, li, key, c0 + (int)qi[e * 128 + tid]);
+          const int mx = __reduce_max_sync(0xffffffffu, cnt);
+          for (int e = 0; e < mx; ++e) {
+            if (e < cnt) {
+              const float key = qv[e * 256 + tid];
+              if (key > lv[KL - 1]) list_insert<KL>(lv, li, key, c0 + (int)qi[e * 256 + tid]);
+            }
           }
         }
       }
       tc::tc_fence_before();
       mbar_arrive(&bar_tfree[st]);
     }
-    if (q < N) {
+    // merge: the upper-half warps publish their lists, the lower-half warps absorb them
+    int* mi = reinterpret_cast<int*>(smem + S::B_OFF);  // loaders are done with the B stages by now
+    asm volatile("bar.sync 2, 256;" ::: "memory");      // every selector has consumed its last tile
+    if (half == 1) {
 #pragma unroll
       for (int i = 0; i < KL; ++i) {
-        if (i < k) {
-          const int64_t o = (base + q) * k + i;
-          if (idx32) idx32[o] = li[i];
-          if (idx64) idx64[o] = li[i];
+        qv[i * 128 + row] = lv[i];
+        mi[i * 128 + row] = li[i];
+      }
+    }
+    asm volatile("bar.sync 2, 256;" ::: "memory");
+    if (half == 0) {
+#pragma unroll 1
+      for (int i = 0; i < KL; ++i) {
+        const float key = qv[i * 128 + row];
+        if (key > lv[KL - 1]) list_insert<KL>(lv, li, key, mi[i * 128 + row]);
+      }
+      if (q < N) {
+#pragma unroll
+        for (int i = 0; i < KL; ++i) {
+          if (i < k) {
+            const int64_t o = (base + q) * k + i;
+            if (idx32) idx32[o] = li[i];
+            if (idx64) idx64[o] = li[i];
+          }
         }
       }
     }
