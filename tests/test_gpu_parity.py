@@ -511,3 +511,27 @@ def test_linear_tensor_core_vs_fp64(M, K, N, act):
         err = (y.double() - ref).abs().max() / ref.abs().max()
         assert err < (3e-6 if impl == 1 else 1e-5), (impl, err)  # TMEM accumulation is not RN
     assert (outs[1] - outs[2]).abs().max() / ref.abs().max() < 1e-5
+
+
+def test_episode_evaluator_matches_reference_metric(model):
+    """The sharded eval driver (evaluate.py = eval_noise.py:23-113): device-side counters and mean
+    loss equal what the reference's evaluate_metric computes from the same predictions, and the
+    two-rank sharding of the same episodes adds up to the single-rank counters exactly."""
+    from r3dfsseg_b200.evaluate import EpisodeEvaluator, iou_from_counters
+    m = model(2, 5)
+    eps = [make_episode(200 + i, 2, 5, noise_ratio=0.4 if i % 2 else 0.0) for i in range(5)]
+    test_classes = list(range(6))
+    ev = EpisodeEvaluator(m, test_classes, batch=2)
+    full = ev.run(eps)
+    preds, gts, l2c = [], [], []
+    for e in eps:
+        pred, _ = m(e.support_x.to(DEV), e.support_y.to(DEV), e.query_x.to(DEV), e.query_y.to(DEV),
+                    eval=True)
+        preds.append(pred.argmax(1).cpu().numpy())
+        gts.append(e.query_y.numpy())
+        l2c.append(e.sampled_classes)
+    ref = O.confusion_counts(preds, gts, l2c, test_classes)
+    assert np.array_equal(full["counters"].numpy(), ref)
+    assert abs(full["mean_iou"] - O.mean_iou(ref)) < 1e-12 or np.isnan(full["mean_iou"])
+    parts = [ev.run(eps, rank=r, world=2)["counters"] for r in range(2)]
+    assert torch.equal(parts[0] + parts[1], full["counters"])

@@ -1,0 +1,151 @@
+"""CPU tests of the host-side logic: the C-ABI library loads and exports what include/r3dfs.h
+declares, episode sharding + the counter all-reduce (gloo, world_size 2), mIoU arithmetic, the
+synthetic episode contract.  No kernel is launched here."""
+import os
+import re
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from r3dfsseg_b200 import _lib
+    header = open(os.path.join(ROOT, "include", "r3dfs.h")).read()
+    declared = set(re.findall(r"\b(r3dfs_[a-z0-9_]+)\s*\(", header))
+    assert "r3dfs_mpti_forward" in declared and "r3dfs_knn" in declared
+    handle = _lib.lib()
+    for name in declared:
+        assert hasattr(handle, name), f"{name} declared in r3dfs.h but not exported"
+    for name in _lib.SIGNATURES:
+        assert name in declared, f"{name} bound in _lib.py but not declared in r3dfs.h"
+    assert handle.r3dfs_version() == 100
+    assert b"workspace" in handle.r3dfs_strerror(-3)
+
+
+def test_workspace_queries_are_pure_host_calls():
+    from r3dfsseg_b200 import _lib, ops
+    L = _lib.lib()
+    cfg = ops.make_cfg(2, 5, 2, 2048)
+    one = L.r3dfs_mpti_workspace(cfg, 1)
+    many = L.r3dfs_mpti_workspace(cfg, 8)
+    assert 0 < one < many <= 8 * one + (1 << 20)
+    bad = ops.make_cfg(9, 5, 2, 2048)   # n_way > 7 is outside the kernels' range
+    assert L.r3dfs_mpti_workspace(bad, 1) == 0
+    assert L.r3dfs_knn_workspace(4, 9, 2048, 20) > 0
+
+
+def test_product_path_rejects_cpu_tensors():
+    from r3dfsseg_b200 import ops
+    with pytest.raises(RuntimeError, match="CUDA tensors only"):
+        ops.knn(torch.rand(1, 9, 64), 4)
+    with pytest.raises(RuntimeError, match="CUDA tensors only"):
+        ops.get_edge_feature(torch.rand(1, 9, 64), 4, torch.zeros(1, 64, 4, dtype=torch.long))
+
+
+def test_module_state_dict_matches_reference_names(fixture_sd):
+    from r3dfsseg_b200.episodes import default_args
+    from r3dfsseg_b200.models import MPTI_SelfAtten
+    m = MPTI_SelfAtten(default_args(2, 5))
+    assert set(m.state_dict().keys()) == set(fixture_sd.keys())
+    m.load_state_dict(fixture_sd)          # strict
+    assert sum(p.numel() for p in m.parameters()) == 376896
+    with pytest.raises(NotImplementedError):
+        m.train()
+        m.getFeatures(torch.rand(1, 9, 2048))
+
+
+def test_sharding_partitions_episodes():
+    from r3dfsseg_b200.evaluate import shard_indices
+    for world in (1, 2, 3, 4, 8):
+        seen = sorted(i for r in range(world) for i in shard_indices(101, r, world))
+        assert seen == list(range(101))
+        sizes = [len(shard_indices(101, r, world)) for r in range(world)]
+        assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        shard_indices(10, 2, 2)
+
+
+def test_miou_matches_reference_metric():
+    """evaluate_metric (reference eval_noise.py:23-72) restated by the oracle vs evaluate.py."""
+    from oracle import mpti_oracle as O
+    from r3dfsseg_b200.evaluate import class_slots, iou_from_counters
+    rng = np.random.default_rng(0)
+    test_classes = [3, 11, 10, 0, 8, 4]
+    preds = [rng.integers(0, 3, (2, 512)) for _ in range(24)]
+    gts = [rng.integers(0, 3, (2, 512)) for _ in range(24)]
+    l2c = [rng.choice(test_classes, 2, replace=False) for _ in range(24)]
+    counters = O.confusion_counts(preds, gts, l2c, test_classes)
+    # brute-force restatement of the reference's per-point loop
+    ref = np.zeros((3, 7), dtype=np.int64)
+    for p, g, c in zip(preds, gts, l2c):
+        slot = [0] + class_slots(c, test_classes)
+        for pv, gv in zip(p.reshape(-1), g.reshape(-1)):
+            ref[0, slot[gv]] += 1
+            ref[1, slot[pv]] += 1
+            ref[2, slot[gv]] += int(pv == gv)
+    assert np.array_equal(counters, ref)
+    res = iou_from_counters(torch.from_numpy(counters))
+    assert (counters[0] > 0).all()
+    assert abs(res["mean_iou"] - O.mean_iou(counters)) < 1e-12
+
+
+def _gloo_worker(rank, world, port, q):
+    import torch.distributed as dist
+    from oracle import mpti_oracle as O
+    from r3dfsseg_b200.evaluate import all_reduce_eval_state, shard_indices
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.default_rng(123)      # same stream on every rank
+    test_classes = list(range(6))
+    n = 25
+    preds = [rng.integers(0, 3, (2, 256)) for _ in range(n)]
+    gts = [rng.integers(0, 3, (2, 256)) for _ in range(n)]
+    l2c = [rng.choice(test_classes, 2, replace=False) for _ in range(n)]
+    losses = rng.random(n)
+    mine = shard_indices(n, rank, world)
+    part = O.confusion_counts([preds[i] for i in mine], [gts[i] for i in mine],
+                              [l2c[i] for i in mine], test_classes)
+    counters = torch.from_numpy(part.copy())
+    loss_sum = torch.tensor(float(sum(losses[i] for i in mine)), dtype=torch.float64)
+    cnt = torch.tensor(float(len(mine)), dtype=torch.float64)
+    all_reduce_eval_state(counters, loss_sum, cnt)
+    full = O.confusion_counts(preds, gts, l2c, test_classes)
+    ok = bool(np.array_equal(counters.numpy(), full)) and abs(float(loss_sum) - losses.sum()) < 1e-9 \
+        and int(cnt) == n
+    q.put((rank, ok))
+    dist.destroy_process_group()
+
+
+def test_counter_allreduce_gloo_world2():
+    """The N>1 path on CPU: shard, reduce, compare with the single-rank counters (exact ints)."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(results) == [(0, True), (1, True)]
+
+
+def test_synthetic_episode_contract():
+    """Shapes / dtypes / strides the reference's collate produces (loader.py:1662-1684)."""
+    from r3dfsseg_b200.episodes import make_episode
+    ep = make_episode(3, 3, 5, dataset="scannet", noise_ratio=0.4)
+    assert ep.support_x.shape == (3, 5, 9, 2048) and not ep.support_x.is_contiguous()
+    assert ep.support_x.transpose(2, 3).is_contiguous()           # point-major memory
+    assert ep.support_y.dtype == torch.int32 and ep.query_y.dtype == torch.int64
+    assert ep.query_x.shape == (3, 9, 2048) and int(ep.query_y.max()) <= 3
+    assert (ep.support_y.sum(-1) >= 1).all()                       # >= 1 fg point per shot
+    noisy = (ep.gt_support_y.sum(-1) == 0).sum(1)
+    assert (noisy == 2).all()                                      # round(5 * 0.4) OOD shots per way
+    again = make_episode(3, 3, 5, dataset="scannet", noise_ratio=0.4)
+    assert torch.equal(ep.support_x, again.support_x)
