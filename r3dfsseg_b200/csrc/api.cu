@@ -94,6 +94,12 @@ int launch_edge_mlp_auto(const float* PQ, const int32_t* idx, const float* w2, c
   return launch_edge_mlp_tc(PQ, idx, w2, s2, t2, B, N, k, Y, ldy, map, st);
 }
 
+int launch_attention_auto(const float* qkv, int ld, int64_t B, int N, float* Y, int ldy,
+                          RowMap map, cudaStream_t st) {
+  if (simt_gemm_forced()) return launch_attention(qkv, ld, B, N, Y, ldy, map, st);
+  return launch_attention_tc(qkv, ld, B, N, Y, ldy, map, st);
+}
+
 int launch_linear_auto(const float* X, int ldx, const float* W, const float* s, const float* t,
                        int act, int64_t M, int K, int Nout, float* Y, int ldy, RowMap map,
                        cudaStream_t st) {
@@ -192,7 +198,7 @@ static int encoder_forward(const r3dfs_weights_t* w, const float* xp, int64_t B,
   R3DFS_TRY(launch_linear_auto(e.l2, 256, w->att_wqkv, nullptr, nullptr, ACT_NONE, M, 256, 192, e.qkv,
                           192, identity_map(), st));
   if (sr) sr->mark(R3DFS_ST_QKV, st);
-  R3DFS_TRY(launch_attention(e.qkv, 192, B, N, F + 64, 192, map, st));
+  R3DFS_TRY(launch_attention_auto(e.qkv, 192, B, N, F + 64, 192, map, st));
   if (sr) sr->mark(R3DFS_ST_ATT, st);
   return 0;
 }
@@ -331,7 +337,7 @@ int r3dfs_attention(const float* x, int64_t B, int64_t N, int64_t Cin, const flo
   float* qkv = ws.take<float>(B * N * 192);
   R3DFS_TRY(launch_linear_auto(x, (int)Cin, wqkv, nullptr, nullptr, ACT_NONE, B * N, (int)Cin, 192,
                                qkv, 192, identity_map(), st));
-  return launch_attention(qkv, 192, B, (int)N, y, 64, identity_map(), st);
+  return launch_attention_auto(qkv, 192, B, (int)N, y, 64, identity_map(), st);
 }
 
 // ---- getFeatures --------------------------------------------------------------------------------
@@ -421,8 +427,8 @@ int r3dfs_affinity_knn(const float* node_feat, const uint8_t* valid, int n_graph
 size_t r3dfs_label_propagate_workspace(int n_graphs, int64_t n_max, int k, int n_cls) {
   const size_t G = n_graphs, n = n_max;
   (void)n_cls;
-  return align_up(4 * G * n * k, 256) * 3 + align_up(4 * G * (n + 1), 256) * 3 +
-         align_up(4 * G * n * 8, 256) * 4 + 4096;
+  return align_up(4 * G * n * k, 256) * 3 + align_up(4 * G * (n + 1), 256) * 6 +
+         align_up(4 * G * n * 8, 256) * 4 + align_up(6 * G * n * k * 2, 256) + 8192;
 }
 
 int r3dfs_label_propagate(const int32_t* nbr, const float* sim, const uint8_t* valid, int n_graphs,
@@ -443,6 +449,11 @@ int r3dfs_label_propagate(const int32_t* nbr, const float* sim, const uint8_t* v
   int32_t* in_cnt = ws.take<int32_t>(G * (n + 1));
   int32_t* in_ptr = ws.take<int32_t>(G * (n + 1));
   float* dinv = ws.take<float>(G * (n + 1));
+  int32_t* rowptr = ws.take<int32_t>(G * n);
+  int32_t* rowlen = ws.take<int32_t>(G * n);
+  int32_t* cursor = ws.take<int32_t>(G);
+  uint16_t* mcol = ws.take<uint16_t>(G * n * k * 2);
+  float* mval = ws.take<float>(G * n * k * 2);
   float* X = ws.take<float>(G * n * 8);
   float* R = ws.take<float>(G * n * 8);
   float* P = ws.take<float>(G * n * 8);
@@ -451,8 +462,8 @@ int r3dfs_label_propagate(const int32_t* nbr, const float* sim, const uint8_t* v
   cudaError_t ce = cudaMemcpyAsync(sv, sim, sizeof(float) * G * n * k, cudaMemcpyDeviceToDevice, st);
   if (ce != cudaSuccess) return (int)ce;
   return launch_label_propagate(nbr, sv, valid, n_graphs, (int)n_max, k, Y, n_cls, alpha, tol,
-                                max_iter, in_cnt, in_ptr, in_src, in_w, dinv, Z, X, R, P, AP,
-                                iters_out, resid_out, st);
+                                max_iter, in_cnt, in_ptr, in_src, in_w, dinv, rowptr, rowlen, cursor,
+                                mcol, mval, Z, X, R, P, AP, iters_out, resid_out, st);
 }
 
 // ---- confusion counters ----------------------------------------------------------------------------
@@ -507,6 +518,9 @@ struct EpisodeWs {
   float* sim;
   int32_t *in_cnt, *in_ptr, *in_src;
   float *in_w, *dinv, *Z, *X, *R, *P, *AP;
+  int32_t *rowptr, *rowlen, *cursor;
+  uint16_t* mcol;
+  float* mval;
 };
 
 static void carve_episode(WsBump& ws, const r3dfs_episode_cfg_t* c, const EpisodeDims& d, int E,
@@ -541,6 +555,11 @@ static void carve_episode(WsBump& ws, const r3dfs_episode_cfg_t* c, const Episod
   w.in_src = ws.take<int32_t>(G * nn * k);
   w.in_w = ws.take<float>(G * nn * k);
   w.dinv = ws.take<float>(G * nn);
+  w.rowptr = ws.take<int32_t>(G * nn);
+  w.rowlen = ws.take<int32_t>(G * nn);
+  w.cursor = ws.take<int32_t>(G);
+  w.mcol = ws.take<uint16_t>(G * nn * k * 2);
+  w.mval = ws.take<float>(G * nn * k * 2);
   w.Z = ws.take<float>(G * nn * d.nc);
   w.X = ws.take<float>(G * nn * 8);
   w.R = ws.take<float>(G * nn * 8);
@@ -598,7 +617,8 @@ static int episode_graph_half(const r3dfs_episode_cfg_t* cfg, const EpisodeDims&
                             w.norms, w.D2, w.nbr, w.sim, st, sr));
   R3DFS_TRY(launch_label_propagate(w.nbr, w.sim, w.valid, E, d.nn, cfg->k_connect, w.Y, d.nc,
                                    cfg->alpha, cfg->cg_tol, cfg->cg_max_iter, w.in_cnt, w.in_ptr,
-                                   w.in_src, w.in_w, w.dinv, w.Z, w.X, w.R, w.P, w.AP,
+                                   w.in_src, w.in_w, w.dinv, w.rowptr, w.rowlen, w.cursor, w.mcol,
+                                   w.mval, w.Z, w.X, w.R, w.P, w.AP,
                                    diag ? diag->cg_iters : nullptr,
                                    diag ? diag->cg_resid : nullptr, st, sr));
   // query rows -> logits / loss / prediction

@@ -401,6 +401,138 @@ __global__ void normalize_kernel(const int32_t* __restrict__ nbr, float* __restr
 }
 
 // --------------------------------------------------------------------------------------------
+// Merged symmetric rows: W = A + A^T (models/mpti.py:752) stored once per row as (col u16, val)
+// with the mutual pairs combined (W_ij = a_ij + a_ji, exactly the reference's sum).  Row i =
+// its k out-edges in index order (mutual in-weights added in), then the non-mutual in-edges in
+// source order.  One warp per row; each in-edge is looked up in the sorted out-list by bisection.
+// Row segments are handed out with an atomic cursor: their placement may differ run to run, the
+// contents (and so every sum taken over a row) do not.
+// --------------------------------------------------------------------------------------------
+__global__ __launch_bounds__(256) void merge_rows_kernel(
+    const int32_t* __restrict__ nbr, const float* __restrict__ sim,
+    const int32_t* __restrict__ in_ptr, const int32_t* __restrict__ in_src,
+    const float* __restrict__ in_w, const uint8_t* __restrict__ valid, int nn, int k,
+    int32_t* __restrict__ cursor, int32_t* __restrict__ rowptr, int32_t* __restrict__ rowlen,
+    uint16_t* __restrict__ mcol, float* __restrict__ mval) {
+  extern __shared__ __align__(16) unsigned char s_raw[];
+  const int g = blockIdx.y, wi = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int i = blockIdx.x * 8 + wi;
+  int* s_idx = reinterpret_cast<int*>(s_raw) + wi * k;
+  float* s_val = reinterpret_cast<float*>(s_raw) + 8 * k + wi * k;
+  if (i >= nn) return;
+  const int64_t vb = (int64_t)g * nn;
+  if (!valid[vb + i]) {
+    if (lane == 0) {
+      rowptr[vb + i] = 0;
+      rowlen[vb + i] = 0;
+    }
+    return;
+  }
+  const int64_t ob = (vb + i) * k;
+  for (int t = lane; t < k; t += 32) {
+    s_idx[t] = nbr[ob + t];
+    s_val[t] = sim[ob + t];
+  }
+  __syncwarp();
+  const int32_t* ptr = in_ptr + (int64_t)g * (nn + 1);
+  const int64_t ib = vb * k;
+  const int e0 = ptr[i], e1 = ptr[i + 1];
+  // pass 1: how many in-edges are not mutual
+  int keep = 0;
+  for (int t0 = e0; t0 < e1; t0 += 32) {
+    const int t = t0 + lane;
+    bool kp = false;
+    if (t < e1) {
+      const int s = in_src[ib + t];
+      int lo = 0, hi = k;
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (s_idx[mid] < s) lo = mid + 1; else hi = mid;
+      }
+      kp = !(lo < k && s_idx[lo] == s);
+    }
+    keep += __popc(__ballot_sync(0xffffffffu, kp));
+  }
+  const int total = k + keep;
+  int start = 0;
+  if (lane == 0) start = atomicAdd(&cursor[g], total);
+  start = __shfl_sync(0xffffffffu, start, 0);
+  const int64_t mb = vb * k * 2 + start;
+  // pass 2: fold mutual in-weights into the out entries, append the rest
+  int run = 0;
+  for (int t0 = e0; t0 < e1; t0 += 32) {
+    const int t = t0 + lane;
+    bool kp = false;
+    int s = 0;
+    float wv = 0.f;
+    if (t < e1) {
+      s = in_src[ib + t];
+      wv = in_w[ib + t];
+      int lo = 0, hi = k;
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (s_idx[mid] < s) lo = mid + 1; else hi = mid;
+      }
+      if (lo < k && s_idx[lo] == s) s_val[lo] += wv; else kp = true;
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, kp);
+    if (kp) {
+      const int pos = k + run + __popc(bal & ((1u << lane) - 1));
+      mcol[mb + pos] = (uint16_t)s;
+      mval[mb + pos] = wv;
+    }
+    run += __popc(bal);
+  }
+  __syncwarp();
+  for (int t = lane; t < k; t += 32) {
+    mcol[mb + t] = (uint16_t)s_idx[t];
+    mval[mb + t] = s_val[t];
+  }
+  if (lane == 0) {
+    rowptr[vb + i] = start;
+    rowlen[vb + i] = total;
+  }
+}
+
+// D = rowsum(W) ; D^-1/2 = sqrt(1 / (D + eps))      (models/mpti.py:767-770)
+__global__ __launch_bounds__(256) void degree_merged_kernel(const int32_t* __restrict__ rowptr,
+                                                            const int32_t* __restrict__ rowlen,
+                                                            const float* __restrict__ mval, int nn,
+                                                            int k, float* __restrict__ dinv) {
+  const int g = blockIdx.y;
+  const int i = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (i >= nn) return;
+  const int lane = threadIdx.x & 31;
+  const int64_t vb = (int64_t)g * nn;
+  const int L = rowlen[vb + i];
+  float d = 0.f;
+  if (L > 0) {
+    const float* v = mval + vb * k * 2 + rowptr[vb + i];
+    for (int t = lane; t < L; t += 32) d += v[t];
+    d = warp_sum(d);
+    d = sqrtf(1.0f / (d + 2.220446049250313e-16f));
+  }
+  if (lane == 0) dinv[vb + i] = d;
+}
+
+// S = D^-1/2 W D^-1/2 on the stored pattern (models/mpti.py:772)
+__global__ void normalize_merged_kernel(const int32_t* __restrict__ rowptr,
+                                        const int32_t* __restrict__ rowlen,
+                                        const uint16_t* __restrict__ mcol, float* __restrict__ mval,
+                                        const float* __restrict__ dinv, int nn, int k) {
+  const int g = blockIdx.y;
+  const int i = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (i >= nn) return;
+  const int lane = threadIdx.x & 31;
+  const int64_t vb = (int64_t)g * nn;
+  const int L = rowlen[vb + i];
+  const float* dg = dinv + vb;
+  const float di = dg[i];
+  const int64_t mb = vb * k * 2 + rowptr[vb + i];
+  for (int t = lane; t < L; t += 32) mval[mb + t] = (di * mval[mb + t]) * dg[mcol[mb + t]];
+}
+
+// --------------------------------------------------------------------------------------------
 // Label propagation: (I - alpha S) Z = Y by conjugate gradients, all n_cls right-hand sides at
 // once, one thread-block CLUSTER per graph (16 CTAs when the device grants it, else 8).
 //   - rows are sliced over the cluster's CTAs; X, R, AP of a slice are private to its CTA;
@@ -455,9 +587,9 @@ __device__ __forceinline__ void cg_allreduce(cg::cluster_group& cluster, CgExcha
 // Vectors are stored padded to NCV columns (NCV = 4 or 8) so a node's row is one or two float4.
 template <int NCV>
 __global__ __launch_bounds__(CG_THREADS) void lp_cg_kernel(
-    const int32_t* __restrict__ nbr, const float* __restrict__ sval,
-    const int32_t* __restrict__ in_ptr, const int32_t* __restrict__ in_src,
-    const float* __restrict__ in_sval, const uint8_t* __restrict__ valid, int nn, int k,
+    const int32_t* __restrict__ rowptr, const int32_t* __restrict__ rowlen,
+    const uint16_t* __restrict__ mcol, const float* __restrict__ mval,
+    const uint8_t* __restrict__ valid, int nn, int k,
     const float* __restrict__ Y, int nc, float alpha, float tol, int max_iter,
     float* __restrict__ Z, float* __restrict__ X, float* __restrict__ R, float* __restrict__ Pv,
     float* __restrict__ AP, int32_t* __restrict__ iters_out, float* __restrict__ resid_out) {
@@ -476,11 +608,10 @@ __global__ __launch_bounds__(CG_THREADS) void lp_cg_kernel(
   float* Rg = R + vb * NCV;
   float* Pg = Pv + vb * NCV;
   float* APg = AP + vb * NCV;
-  const int32_t* nb = nbr + vb * k;
-  const float* sv = sval + vb * k;
-  const int32_t* ip = in_ptr + (int64_t)g * (nn + 1);
-  const int32_t* is = in_src + vb * k;
-  const float* iv = in_sval + vb * k;
+  const int32_t* rp = rowptr + vb;
+  const int32_t* rl = rowlen + vb;
+  const uint16_t* mc = mcol + vb * k * 2;
+  const float* mv = mval + vb * k * 2;
   const int chunk = (nn + CL - 1) / CL;
   const int lo = min(nn, rank * chunk), hi = min(nn, lo + chunk);
   int xcnt = 0;
@@ -528,33 +659,30 @@ __global__ __launch_bounds__(CG_THREADS) void lp_cg_kernel(
       float acc[NCV];
 #pragma unroll
       for (int c = 0; c < NCV; ++c) acc[c] = 0.f;
-      const int32_t* nbr_row = nb + (int64_t)row * k;
-      const float* sv_row = sv + (int64_t)row * k;
-#pragma unroll 4
-      for (int t = lane; t < k; t += 32) {
-        const int j = nbr_row[t];
-        const float v = sv_row[t];
+      // one merged row: (col, val) pairs streamed with 8 independent loads in flight per lane
+      const int L = rl[row];
+      const uint16_t* crow = mc + rp[row];
+      const float* vrow = mv + rp[row];
+      for (int t0 = 0; t0 < L; t0 += 256) {
+        int cj[8];
+        float cv[8];
 #pragma unroll
-        for (int q = 0; q < NCV / 4; ++q) {
-          const float4 p4 = *reinterpret_cast<const float4*>(Ps + (int64_t)j * NCV + 4 * q);
-          acc[4 * q + 0] = fmaf(v, p4.x, acc[4 * q + 0]);
-          acc[4 * q + 1] = fmaf(v, p4.y, acc[4 * q + 1]);
-          acc[4 * q + 2] = fmaf(v, p4.z, acc[4 * q + 2]);
-          acc[4 * q + 3] = fmaf(v, p4.w, acc[4 * q + 3]);
+        for (int u = 0; u < 8; ++u) {
+          const int t = t0 + lane + 32 * u;
+          const bool ok = t < L;
+          cj[u] = ok ? (int)crow[t] : 0;
+          cv[u] = ok ? vrow[t] : 0.f;
         }
-      }
-      const int e0 = ip[row], e1 = ip[row + 1];
-#pragma unroll 4
-      for (int t = e0 + lane; t < e1; t += 32) {
-        const int j = is[t];
-        const float v = iv[t];
 #pragma unroll
-        for (int q = 0; q < NCV / 4; ++q) {
-          const float4 p4 = *reinterpret_cast<const float4*>(Ps + (int64_t)j * NCV + 4 * q);
-          acc[4 * q + 0] = fmaf(v, p4.x, acc[4 * q + 0]);
-          acc[4 * q + 1] = fmaf(v, p4.y, acc[4 * q + 1]);
-          acc[4 * q + 2] = fmaf(v, p4.z, acc[4 * q + 2]);
-          acc[4 * q + 3] = fmaf(v, p4.w, acc[4 * q + 3]);
+        for (int u = 0; u < 8; ++u) {
+#pragma unroll
+          for (int q = 0; q < NCV / 4; ++q) {
+            const float4 p4 = *reinterpret_cast<const float4*>(Ps + (int64_t)cj[u] * NCV + 4 * q);
+            acc[4 * q + 0] = fmaf(cv[u], p4.x, acc[4 * q + 0]);
+            acc[4 * q + 1] = fmaf(cv[u], p4.y, acc[4 * q + 1]);
+            acc[4 * q + 2] = fmaf(cv[u], p4.z, acc[4 * q + 2]);
+            acc[4 * q + 3] = fmaf(cv[u], p4.w, acc[4 * q + 3]);
+          }
         }
       }
 #pragma unroll
@@ -626,9 +754,9 @@ __global__ __launch_bounds__(CG_THREADS) void lp_cg_kernel(
 }
 
 template <int NCV>
-static int launch_cg(int CL, int G, size_t smem, cudaStream_t st, const int32_t* nbr,
-                     const float* sim, const int32_t* in_ptr, const int32_t* in_src,
-                     const float* in_w, const uint8_t* valid, int nn, int k, const float* Y, int nc,
+static int launch_cg(int CL, int G, size_t smem, cudaStream_t st, const int32_t* rowptr,
+                     const int32_t* rowlen, const uint16_t* mcol, const float* mval,
+                     const uint8_t* valid, int nn, int k, const float* Y, int nc,
                      float alpha, float tol, int max_iter, float* Z, float* X, float* R, float* P,
                      float* AP, int32_t* iters_out, float* resid_out) {
   cudaError_t e = cudaFuncSetAttribute(lp_cg_kernel<NCV>,
@@ -658,8 +786,8 @@ static int launch_cg(int CL, int G, size_t smem, cudaStream_t st, const int32_t*
       return -1000;
     }
   }
-  e = cudaLaunchKernelEx(&cfg, lp_cg_kernel<NCV>, nbr, sim, in_ptr, in_src, in_w, valid, nn, k, Y,
-                         nc, alpha, tol, max_iter, Z, X, R, P, AP, iters_out, resid_out);
+  e = cudaLaunchKernelEx(&cfg, lp_cg_kernel<NCV>, rowptr, rowlen, mcol, mval, valid, nn, k, Y, nc,
+                         alpha, tol, max_iter, Z, X, R, P, AP, iters_out, resid_out);
   if (e != cudaSuccess) return (int)e;
   ++r3dfs_launches;
   return 0;
@@ -759,8 +887,9 @@ int launch_affinity(const float* F, int64_t graph_rows, int64_t row_off, const u
 int launch_label_propagate(const int32_t* nbr, float* sim, const uint8_t* valid, int G, int nn,
                            int k, const float* Y, int nc, float alpha, float tol, int max_iter,
                            int32_t* in_cnt, int32_t* in_ptr, int32_t* in_src, float* in_w,
-                           float* dinv, float* Z, float* X, float* R, float* P, float* AP,
-                           int32_t* iters_out, float* resid_out, cudaStream_t st,
+                           float* dinv, int32_t* rowptr, int32_t* rowlen, int32_t* cursor,
+                           uint16_t* mcol, float* mval, float* Z, float* X, float* R, float* P,
+                           float* AP, int32_t* iters_out, float* resid_out, cudaStream_t st,
                            const StageRec* sr) {
   if (nc > CG_MAXC || nc < 1 || nn > 8192) return R3DFS_E_UNSUPPORTED;
   cudaError_t e = cudaMemsetAsync(in_cnt, 0, sizeof(int32_t) * (size_t)G * nn, st);
@@ -779,9 +908,18 @@ int launch_label_propagate(const int32_t* nbr, float* sim, const uint8_t* valid,
   in_sort_kernel<<<dim3(nn, G), 256, smem, st>>>(in_ptr, nn, k, in_src, in_w);
   R3DFS_CHECK_LAUNCH();
   dim3 gr((nn + 7) / 8, G);
-  degree_kernel<<<gr, 256, 0, st>>>(sim, in_ptr, in_w, valid, nn, k, dinv);
+  e = cudaMemsetAsync(cursor, 0, sizeof(int32_t) * (size_t)G, st);
+  if (e != cudaSuccess) return (int)e;
+  const size_t smem_m = (size_t)8 * k * 8;
+  e = cudaFuncSetAttribute(merge_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           (int)smem_m);
+  if (e != cudaSuccess) return (int)e;
+  merge_rows_kernel<<<gr, 256, smem_m, st>>>(nbr, sim, in_ptr, in_src, in_w, valid, nn, k, cursor,
+                                            rowptr, rowlen, mcol, mval);
   R3DFS_CHECK_LAUNCH();
-  normalize_kernel<<<gr, 256, 0, st>>>(nbr, sim, in_ptr, in_src, in_w, valid, dinv, nn, k);
+  degree_merged_kernel<<<gr, 256, 0, st>>>(rowptr, rowlen, mval, nn, k, dinv);
+  R3DFS_CHECK_LAUNCH();
+  normalize_merged_kernel<<<gr, 256, 0, st>>>(rowptr, rowlen, mcol, mval, dinv, nn, k);
   R3DFS_CHECK_LAUNCH();
   if (sr) sr->mark(R3DFS_ST_SYM, st);
 
@@ -792,10 +930,10 @@ int launch_label_propagate(const int32_t* nbr, float* sim, const uint8_t* valid,
   int rc = -1000;
   for (int CL = 16; CL >= 8 && rc == -1000; CL >>= 1) {
     if (ncv == 4)
-      rc = launch_cg<4>(CL, G, smem_cg, st, nbr, sim, in_ptr, in_src, in_w, valid, nn, k, Y, nc, alpha,
+      rc = launch_cg<4>(CL, G, smem_cg, st, rowptr, rowlen, mcol, mval, valid, nn, k, Y, nc, alpha,
                         tol, max_iter, Z, X, R, P, AP, iters_out, resid_out);
     else
-      rc = launch_cg<8>(CL, G, smem_cg, st, nbr, sim, in_ptr, in_src, in_w, valid, nn, k, Y, nc, alpha,
+      rc = launch_cg<8>(CL, G, smem_cg, st, rowptr, rowlen, mcol, mval, valid, nn, k, Y, nc, alpha,
                         tol, max_iter, Z, X, R, P, AP, iters_out, resid_out);
   }
   if (rc != 0) return rc == -1000 ? R3DFS_E_UNSUPPORTED : rc;

@@ -8,9 +8,11 @@ int launch_affinity(const float* F, int64_t graph_rows, int64_t row_off, const u
 int launch_label_propagate(const int32_t* nbr, float* sim, const uint8_t* valid, int G, int nn,
                            int k, const float* Y, int nc, float alpha, float tol, int max_iter,
                            int32_t* in_cnt, int32_t* in_ptr, int32_t* in_src, float* in_w,
-                           float* dinv, float* Z, float* X, float* R, float* P, float* AP,
-                           int32_t* iters_out, float* resid_out, cudaStream_t st,
-                           const StageRec* sr = nullptr);  // X, R, P, AP: (G, nn, 8) scratch
+                           float* dinv, int32_t* rowptr, int32_t* rowlen, int32_t* cursor,
+                           uint16_t* mcol, float* mval, float* Z, float* X, float* R, float* P,
+                           float* AP, int32_t* iters_out, float* resid_out, cudaStream_t st,
+                           const StageRec* sr = nullptr);
+// X, R, P, AP: (G, nn, 8) scratch; rowptr/rowlen: (G, nn); cursor: (G); mcol/mval: (G, 2*nn*k)
 int launch_query_head(const float* Z, int G, int nn, int q_off, int nq, int nc, const int64_t* qy,
                       float* logits, float* loss, int32_t* pred, cudaStream_t st);
 int launch_confusion(const int32_t* pred, const int64_t* gt, const int32_t* class_slot, int E,

@@ -1,0 +1,286 @@
+// SelfAttention (eval) on the tensor cores  (reference models/attention.py:39-48):
+//     y = softmax((q / 8)^T k) v ,  single head, d = 64, per cloud of N points.
+// One CTA = 128 query points; thread = (query row, column half) for everything read from TMEM.
+// Two sweeps over the key tiles (64 keys each), both with 3xTF32 tcgen05.mma:
+//   sweep 1:  S = Q K^T  -> running row maximum m            (no exponentials)
+//   sweep 2:  S again (bit-identical), P = exp(S - m) written as a K-major UMMA A tile (hi/lo),
+//             l += rowsum(P),  O += P V  with V^T staged as the K-major B tile; O stays in TMEM.
+// Knowing m before the second sweep means O never has to be rescaled inside TMEM.
+// The (N, N) attention map exists only as 128 x 64 tiles in TMEM / shared memory.
+#include "common.cuh"
+#include "tc.cuh"
+
+#define AT_THREADS 256
+#define AT_BQ 128
+#define AT_BK 64
+
+struct AttTcSmem {
+  static constexpr int Q_TILE = tc::tile_bytes(128, 16);  // hi or lo, 128 rows x 64 (d)
+  static constexpr int K_TILE = tc::tile_bytes(64, 16);   // 64 keys x 64 (d)
+  static constexpr int V_TILE = tc::tile_bytes(64, 16);   // 64 (d) rows x 64 keys  (V^T)
+  static constexpr int P_TILE = tc::tile_bytes(128, 16);  // 128 rows x 64 keys
+  static constexpr int Q_OFF = 0;
+  static constexpr int K_OFF = Q_OFF + 2 * Q_TILE;
+  static constexpr int V_OFF = K_OFF + 2 * K_TILE;
+  static constexpr int P_OFF = V_OFF + 2 * V_TILE;
+  static constexpr int X_OFF = P_OFF + 2 * P_TILE;  // exchange: 2 x 128 floats
+  static constexpr int TOTAL = X_OFF + 2 * 128 * 4 + 64;
+};
+
+// 64 rows x 64 columns of `src` (row stride ld, starting column col_off) -> K-major hi/lo tiles
+__device__ __forceinline__ void at_load_rows(float4 (&v)[4], const float* __restrict__ src, int ld,
+                                             int64_t row0, int64_t rows_end, int col_off, int tid) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int c = tid + i * AT_THREADS;
+    const int r = c >> 4, kc = c & 15;
+    v[i] = (row0 + r < rows_end)
+               ? *reinterpret_cast<const float4*>(src + (row0 + r) * (int64_t)ld + col_off + 4 * kc)
+               : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+__device__ __forceinline__ void at_store_rows(const float4 (&v)[4], unsigned char* hi,
+                                              unsigned char* lo, int tid) {
+  constexpr int LBO = tc::tile_lbo(64);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int c = tid + i * AT_THREADS;
+    const int r = c >> 4, kc = c & 15;
+    float4 h, l;
+    tc::split4(v[i], h, l);
+    *reinterpret_cast<float4*>(hi + kc * LBO + r * 16) = h;
+    *reinterpret_cast<float4*>(lo + kc * LBO + r * 16) = l;
+  }
+}
+// V rows (keys) -> V^T tile: element (d, key) at (key/4)*LBO + d*16 + (key%4)*4
+__device__ __forceinline__ void at_load_v(float4 (&v)[4], const float* __restrict__ src, int ld,
+                                          int64_t row0, int64_t rows_end, int tid) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int c = tid + i * AT_THREADS;
+    const int key = c & 63, d4 = c >> 6;
+    v[i] = (row0 + key < rows_end)
+               ? *reinterpret_cast<const float4*>(src + (row0 + key) * (int64_t)ld + 128 + 4 * d4)
+               : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+__device__ __forceinline__ void at_store_vT(const float4 (&v)[4], unsigned char* hi,
+                                            unsigned char* lo, int tid) {
+  constexpr int LBO = tc::tile_lbo(64);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int c = tid + i * AT_THREADS;
+    const int key = c & 63, d4 = c >> 6;
+    float4 h, l;
+    tc::split4(v[i], h, l);
+    const int base = (key >> 2) * LBO + (key & 3) * 4 + (4 * d4) * 16;
+    *reinterpret_cast<float*>(hi + base) = h.x;
+    *reinterpret_cast<float*>(hi + base + 16) = h.y;
+    *reinterpret_cast<float*>(hi + base + 32) = h.z;
+    *reinterpret_cast<float*>(hi + base + 48) = h.w;
+    *reinterpret_cast<float*>(lo + base) = l.x;
+    *reinterpret_cast<float*>(lo + base + 16) = l.y;
+    *reinterpret_cast<float*>(lo + base + 32) = l.z;
+    *reinterpret_cast<float*>(lo + base + 48) = l.w;
+  }
+}
+
+__global__ __launch_bounds__(AT_THREADS, 1) void attention_tc_kernel(const float* __restrict__ qkv,
+                                                                     int ld, int N,
+                                                                     float* __restrict__ Y, int ldy,
+                                                                     RowMap map) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  using S = AttTcSmem;
+  __shared__ uint64_t bar_s, bar_pv;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int b = blockIdx.y;
+  const int q0 = blockIdx.x * AT_BQ;
+  const int64_t base = (int64_t)b * N;
+  constexpr int LBO_Q = tc::tile_lbo(128), LBO_K = tc::tile_lbo(64);
+  constexpr uint32_t IDESC = tc::make_idesc_tf32(128, 64);
+  const int T = (N + AT_BK - 1) / AT_BK;
+  const int row = 32 * (w & 3) + lane;  // TMEM lane = query row
+  const int half = w >> 2;              // columns [32*half, 32*half+32) of every 64-wide tile
+  float* xch = reinterpret_cast<float*>(smem + S::X_OFF);
+
+  if (tid == 0) {
+    tc::mbar_init(&bar_s, 1);
+    tc::mbar_init(&bar_pv, 1);
+    tc::mbar_fence_init();
+  }
+  if (w == 0) tc::tmem_alloc(&tmem_base_s, 128);
+  // Q tile (pre-divided by the temperature 8 = sqrt(64), exactly as the reference does)
+  for (int c = tid; c < 128 * 16; c += AT_THREADS) {
+    const int r = c >> 4, kc = c & 15;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (q0 + r < N) v = *reinterpret_cast<const float4*>(qkv + (base + q0 + r) * (int64_t)ld + 4 * kc);
+    v.x /= 8.f; v.y /= 8.f; v.z /= 8.f; v.w /= 8.f;
+    float4 h, l;
+    tc::split4(v, h, l);
+    *reinterpret_cast<float4*>(smem + S::Q_OFF + kc * LBO_Q + r * 16) = h;
+    *reinterpret_cast<float4*>(smem + S::Q_OFF + S::Q_TILE + kc * LBO_Q + r * 16) = l;
+  }
+  tc::fence_async_smem();
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_s = tmem_base_s, tmem_o = tmem_base_s + 64;
+  const uint32_t q_hi = tc::smem_u32(smem + S::Q_OFF), q_lo = q_hi + S::Q_TILE;
+  unsigned char* k_hi_p = smem + S::K_OFF;
+  unsigned char* k_lo_p = k_hi_p + S::K_TILE;
+  unsigned char* v_hi_p = smem + S::V_OFF;
+  unsigned char* v_lo_p = v_hi_p + S::V_TILE;
+  unsigned char* p_hi_p = smem + S::P_OFF;
+  unsigned char* p_lo_p = p_hi_p + S::P_TILE;
+  const uint32_t k_hi = tc::smem_u32(k_hi_p), k_lo = tc::smem_u32(k_lo_p);
+  const uint32_t v_hi = tc::smem_u32(v_hi_p), v_lo = tc::smem_u32(v_lo_p);
+  const uint32_t p_hi = tc::smem_u32(p_hi_p), p_lo = tc::smem_u32(p_lo_p);
+
+  auto issue_s = [&]() {  // S[128 x 64] = Q . K^T  (K = 64 -> 8 k-steps)
+#pragma unroll 1
+    for (int ks = 0; ks < 8; ++ks) {
+      const uint64_t dqh = tc::make_desc(q_hi + ks * 2 * LBO_Q, LBO_Q, 128);
+      const uint64_t dql = tc::make_desc(q_lo + ks * 2 * LBO_Q, LBO_Q, 128);
+      const uint64_t dkh = tc::make_desc(k_hi + ks * 2 * LBO_K, LBO_K, 128);
+      const uint64_t dkl = tc::make_desc(k_lo + ks * 2 * LBO_K, LBO_K, 128);
+      tc::mma_tf32(tmem_s, dql, dkh, IDESC, ks != 0);
+      tc::mma_tf32(tmem_s, dqh, dkl, IDESC, 1);
+      tc::mma_tf32(tmem_s, dqh, dkh, IDESC, 1);
+    }
+    tc::mma_commit(&bar_s);
+  };
+
+  uint32_t ph_s = 0, ph_pv = 0;
+  // ---------------- sweep 1: row maxima -------------------------------------------------------
+  float m_run = -INFINITY;
+  {
+    float4 kv[4];
+    at_load_rows(kv, qkv, ld, base, base + N, 64, tid);
+    for (int j = 0; j < T; ++j) {
+      at_store_rows(kv, k_hi_p, k_lo_p, tid);
+      tc::fence_async_smem();
+      tc::tc_fence_before();
+      __syncthreads();  // K tile complete; everybody has finished reading S of the previous tile
+      if (tid == 0) {
+        tc::tc_fence_after();
+        issue_s();
+      }
+      if (j + 1 < T) at_load_rows(kv, qkv, ld, base + (int64_t)(j + 1) * AT_BK, base + N, 64, tid);
+      tc::mbar_wait(&bar_s, ph_s);
+      ph_s ^= 1;
+      tc::tc_fence_after();
+      float v[32];
+      tc::tmem_ld32(tmem_s + ((uint32_t)(32 * (w & 3)) << 16) + (uint32_t)(32 * half), v);
+      const int c0 = j * AT_BK + 32 * half;
+#pragma unroll
+      for (int e = 0; e < 32; ++e)
+        if (c0 + e < N) m_run = fmaxf(m_run, v[e]);
+    }
+  }
+  // combine the two column halves of every row
+  xch[half * 128 + row] = m_run;
+  tc::tc_fence_before();
+  __syncthreads();
+  const float m_row = fmaxf(xch[row], xch[128 + row]);
+  __syncthreads();
+
+  // ---------------- sweep 2: P = exp(S - m), l, O += P V ---------------------------------------
+  float l_run = 0.f;
+  {
+    float4 kv[4], vv[4];
+    at_load_rows(kv, qkv, ld, base, base + N, 64, tid);
+    at_load_v(vv, qkv, ld, base, base + N, tid);
+    for (int j = 0; j < T; ++j) {
+      // K, V^T and P buffers are free once the previous tile's P.V MMAs have completed
+      if (j > 0) {
+        tc::mbar_wait(&bar_pv, ph_pv);
+        ph_pv ^= 1;
+      }
+      at_store_rows(kv, k_hi_p, k_lo_p, tid);
+      at_store_vT(vv, v_hi_p, v_lo_p, tid);
+      tc::fence_async_smem();
+      tc::tc_fence_before();
+      __syncthreads();
+      if (tid == 0) {
+        tc::tc_fence_after();
+        issue_s();
+      }
+      if (j + 1 < T) {
+        at_load_rows(kv, qkv, ld, base + (int64_t)(j + 1) * AT_BK, base + N, 64, tid);
+        at_load_v(vv, qkv, ld, base + (int64_t)(j + 1) * AT_BK, base + N, tid);
+      }
+      tc::mbar_wait(&bar_s, ph_s);
+      ph_s ^= 1;
+      tc::tc_fence_after();
+      float v[32];
+      tc::tmem_ld32(tmem_s + ((uint32_t)(32 * (w & 3)) << 16) + (uint32_t)(32 * half), v);
+      const int c0 = j * AT_BK + 32 * half;
+#pragma unroll
+      for (int e = 0; e < 32; e += 4) {
+        float4 p;
+        p.x = (c0 + e + 0 < N) ? expf(v[e + 0] - m_row) : 0.f;
+        p.y = (c0 + e + 1 < N) ? expf(v[e + 1] - m_row) : 0.f;
+        p.z = (c0 + e + 2 < N) ? expf(v[e + 2] - m_row) : 0.f;
+        p.w = (c0 + e + 3 < N) ? expf(v[e + 3] - m_row) : 0.f;
+        l_run += (p.x + p.y) + (p.z + p.w);
+        float4 h, l;
+        tc::split4(p, h, l);
+        const int kc = (32 * half + e) >> 2;  // 16-byte chunk along the key dimension
+        *reinterpret_cast<float4*>(p_hi_p + kc * LBO_Q + row * 16) = h;
+        *reinterpret_cast<float4*>(p_lo_p + kc * LBO_Q + row * 16) = l;
+      }
+      tc::fence_async_smem();
+      tc::tc_fence_before();
+      __syncthreads();  // P complete, S consumed
+      if (tid == 0) {
+        tc::tc_fence_after();
+#pragma unroll 1
+        for (int ks = 0; ks < 8; ++ks) {  // O[128 x 64] += P[128 x 64 keys] . V[64 keys x 64]
+          const uint64_t dph = tc::make_desc(p_hi + ks * 2 * LBO_Q, LBO_Q, 128);
+          const uint64_t dpl = tc::make_desc(p_lo + ks * 2 * LBO_Q, LBO_Q, 128);
+          const uint64_t dvh = tc::make_desc(v_hi + ks * 2 * LBO_K, LBO_K, 128);
+          const uint64_t dvl = tc::make_desc(v_lo + ks * 2 * LBO_K, LBO_K, 128);
+          tc::mma_tf32(tmem_o, dpl, dvh, IDESC, (j | ks) != 0);
+          tc::mma_tf32(tmem_o, dph, dvl, IDESC, 1);
+          tc::mma_tf32(tmem_o, dph, dvh, IDESC, 1);
+        }
+        tc::mma_commit(&bar_pv);
+      }
+    }
+  }
+  // ---------------- epilogue: O / l ------------------------------------------------------------
+  xch[half * 128 + row] = l_run;
+  tc::mbar_wait(&bar_pv, ph_pv);
+  tc::tc_fence_after();
+  __syncthreads();
+  const float inv = 1.f / (xch[row] + xch[128 + row]);
+  {
+    float v[32];
+    tc::tmem_ld32(tmem_o + ((uint32_t)(32 * (w & 3)) << 16) + (uint32_t)(32 * half), v);
+    const int q = q0 + row;
+    if (q < N) {
+      float* y = Y + map(base + q) * (int64_t)ldy + 32 * half;
+#pragma unroll
+      for (int e = 0; e < 32; e += 4)
+        *reinterpret_cast<float4*>(y + e) =
+            make_float4(v[e] * inv, v[e + 1] * inv, v[e + 2] * inv, v[e + 3] * inv);
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (w == 0) tc::tmem_dealloc(tmem_base_s, 128);
+}
+
+int launch_attention_tc(const float* qkv, int ld, int64_t B, int N, float* Y, int ldy, RowMap map,
+                        cudaStream_t st) {
+  if ((ld & 3) != 0 || (ldy & 3) != 0) return R3DFS_E_UNSUPPORTED;
+  cudaError_t e = cudaFuncSetAttribute(attention_tc_kernel,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       AttTcSmem::TOTAL);
+  if (e != cudaSuccess) return (int)e;
+  dim3 grid((N + AT_BQ - 1) / AT_BQ, (unsigned)B);
+  attention_tc_kernel<<<grid, AT_THREADS, AttTcSmem::TOTAL, st>>>(qkv, ld, N, Y, ldy, map);
+  R3DFS_CHECK_LAUNCH();
+  return 0;
+}
