@@ -220,7 +220,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--episodes", type=int, default=100, help="episodes per step per GPU")
-    ap.add_argument("--chunk", type=int, default=20, help="episodes per C-ABI call")
+    ap.add_argument("--chunk", type=int, default=25, help="episodes per C-ABI call")
     ap.add_argument("--streams", type=int, default=2,
                     help="CUDA streams the chunks of a step are spread over (independent episodes)")
     ap.add_argument("--cpu-episodes", type=int, default=3, help="cpu_baseline sample size")
@@ -244,7 +244,19 @@ def main():
     dist = None
     if world > 1:
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=dev)
+        # NCCL may print its version banner on stdout; keep stdout for the one JSON line
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            warm = torch.zeros(1, device=dev)
+            dist.all_reduce(warm)
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
 
     from r3dfsseg_b200 import _lib, ops
     from r3dfsseg_b200.episodes import default_args

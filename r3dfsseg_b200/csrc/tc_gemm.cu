@@ -11,7 +11,7 @@
 #include "tc.cuh"
 
 #define TCG_BM 128
-#define TCG_BK 32             // floats per k-block
+#define TCG_BK 16             // floats per k-block (small stages -> 3 CTAs per SM hide the load latency)
 #define TCG_KC4 (TCG_BK / 4)  // 16-byte chunks per k-block
 #define TCG_THREADS 256
 
@@ -45,7 +45,7 @@ __device__ __forceinline__ float4 ld_chunk(const float* __restrict__ src, int64_
 //     Y[m][n] = (s[m] + t[n]) - 2 * acc      with s = t = squared row norms,
 // and blockIdx.z walks over independent problems `zs` elements apart (X, W, s, t, Y alike).
 template <int BN, bool DIST>
-__global__ __launch_bounds__(TCG_THREADS, 1) void linear_tc_kernel(
+__global__ __launch_bounds__(TCG_THREADS, 3) void linear_tc_kernel(
     const float* __restrict__ X, int ldx, const float* __restrict__ W, const float* __restrict__ s,
     const float* __restrict__ t, int act, int64_t M, int K, int Nout, float* __restrict__ Y,
     int ldy, RowMap map, int64_t zs_x, int64_t zs_w, int64_t zs_v, int64_t zs_y) {
@@ -58,9 +58,15 @@ __global__ __launch_bounds__(TCG_THREADS, 1) void linear_tc_kernel(
   using S = TcgSmem<BN>;
   __shared__ uint64_t bar_mma[2];
   __shared__ uint32_t tmem_base_s;
+  __shared__ float s_sc[BN], s_sh[BN];
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const int64_t m0 = (int64_t)blockIdx.x * TCG_BM;
   const int n0 = blockIdx.y * BN;
+  if (!DIST && tid < BN) {
+    const int n = n0 + tid;
+    s_sc[tid] = (s && n < Nout) ? s[n] : 1.f;
+    s_sh[tid] = (t && n < Nout) ? t[n] : 0.f;
+  }
   constexpr int LBO_A = tc::tile_lbo(TCG_BM), LBO_B = tc::tile_lbo(BN);
   constexpr uint32_t IDESC = tc::make_idesc_tf32(TCG_BM, BN);
   constexpr int A_CH = TCG_BM * TCG_KC4 / TCG_THREADS;  // chunks per thread per k-block (4)
@@ -88,13 +94,13 @@ __global__ __launch_bounds__(TCG_THREADS, 1) void linear_tc_kernel(
 #pragma unroll
     for (int i = 0; i < A_CH; ++i) {
       const int c = tid + i * TCG_THREADS;
-      const int r = c >> 3, kc = c & 7;
+      const int r = c / TCG_KC4, kc = c % TCG_KC4;
       av[i] = ld_chunk(X, ldx, m0 + r, M, k0 + 4 * kc, K, vec_x);
     }
 #pragma unroll
     for (int i = 0; i < B_CH; ++i) {
       const int c = tid + i * TCG_THREADS;
-      const int r = c >> 3, kc = c & 7;
+      const int r = c / TCG_KC4, kc = c % TCG_KC4;
       bv[i] = ld_chunk(W, K, n0 + r, Nout, k0 + 4 * kc, K, vec_w);
     }
     // the MMAs that read this stage two k-blocks ago must have finished
@@ -106,7 +112,7 @@ __global__ __launch_bounds__(TCG_THREADS, 1) void linear_tc_kernel(
 #pragma unroll
     for (int i = 0; i < A_CH; ++i) {
       const int c = tid + i * TCG_THREADS;
-      const int r = c >> 3, kc = c & 7;
+      const int r = c / TCG_KC4, kc = c % TCG_KC4;
       float4 hi, lo;
       tc::split4(av[i], hi, lo);
       *reinterpret_cast<float4*>(sA_hi + kc * LBO_A + r * 16) = hi;
@@ -115,7 +121,7 @@ __global__ __launch_bounds__(TCG_THREADS, 1) void linear_tc_kernel(
 #pragma unroll
     for (int i = 0; i < B_CH; ++i) {
       const int c = tid + i * TCG_THREADS;
-      const int r = c >> 3, kc = c & 7;
+      const int r = c / TCG_KC4, kc = c % TCG_KC4;
       float4 hi, lo;
       tc::split4(bv[i], hi, lo);
       *reinterpret_cast<float4*>(sB_hi + kc * LBO_B + r * 16) = hi;
@@ -166,8 +172,7 @@ __global__ __launch_bounds__(TCG_THREADS, 1) void linear_tc_kernel(
             if (DIST) {
               v[j] = (s[m] + t[n]) - 2.f * v[j];
             } else {
-              const float sc = s ? s[n] : 1.f, sh = t ? t[n] : 0.f;
-              v[j] = apply_act(fmaf(sc, v[j], sh), act);
+              v[j] = apply_act(fmaf(s_sc[cbase + cc + j], v[j], s_sh[cbase + cc + j]), act);
             }
           }
         }
