@@ -448,52 +448,66 @@ int launch_edge_mlp(const float* PQ, const int32_t* idx, const float* w2, const 
 }
 
 // --------------------------------------------------------------------------------------------
-// get_edge_feature (reference models/dgcnn.py:26-42), materialising: out (B, 2C, N, K).
-// One thread per 4 consecutive (n, j) outputs of one channel; pure HBM write stream.
+// get_edge_feature (reference models/dgcnn.py:26-42), materialising: out (B, 2C, N, K) =
+// cat(x_j - x_i, x_i).  Pure HBM write stream (the output is 2K x the input).  One thread owns 4
+// consecutive (n, j) positions and walks over the channels: the neighbour indices are read once,
+// every channel iteration issues two 128-bit streaming stores, and a warp writes 512 contiguous
+// bytes per channel plane.
 // --------------------------------------------------------------------------------------------
-__global__ void edge_feature_kernel(const float* __restrict__ x, int64_t C, int64_t N, int64_t sb,
-                                    int64_t sc, int64_t sn, const int64_t* __restrict__ idx, int K,
-                                    float* __restrict__ out, int64_t quads_per_plane) {
+__global__ __launch_bounds__(256) void edge_feature_kernel(const float* __restrict__ x, int C,
+                                                           int64_t N, int64_t sb, int64_t sc,
+                                                           int64_t sn,
+                                                           const int64_t* __restrict__ idx, int K,
+                                                           float* __restrict__ out,
+                                                           int64_t quads_per_plane) {
   const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= quads_per_plane) return;
-  const int64_t c = blockIdx.y, b = blockIdx.z;
+  const int64_t b = blockIdx.y;
   const int64_t NK = N * K;
-  const float* xc = x + b * sb + c * sc;
+  const float* xb = x + b * sb;
   const int64_t* ib = idx + b * NK;
-  float d[4], ctr[4];
+  int64_t nbo[4], cto[4];
+  bool ok[4];
 #pragma unroll
   for (int u = 0; u < 4; ++u) {
-    int64_t e = 4 * q + u;
-    if (e < NK) {
-      int64_t n = e / K;
-      float cv = xc[n * sn];
-      float nv = xc[ib[e] * sn];
-      d[u] = nv - cv;
-      ctr[u] = cv;
-    } else {
-      d[u] = 0.f;
-      ctr[u] = 0.f;
-    }
+    const int64_t e = 4 * q + u;
+    ok[u] = e < NK;
+    const int64_t ee = ok[u] ? e : 0;
+    cto[u] = (ee / K) * sn;
+    nbo[u] = ib[ee] * sn;
   }
-  float* o1 = out + ((b * 2 * C + c) * NK);
-  float* o2 = out + ((b * 2 * C + C + c) * NK);
-  if (4 * q + 3 < NK && (NK & 3) == 0) {
-    *reinterpret_cast<float4*>(o1 + 4 * q) = make_float4(d[0], d[1], d[2], d[3]);
-    *reinterpret_cast<float4*>(o2 + 4 * q) = make_float4(ctr[0], ctr[1], ctr[2], ctr[3]);
-  } else {
-    for (int u = 0; u < 4; ++u)
-      if (4 * q + u < NK) {
-        o1[4 * q + u] = d[u];
-        o2[4 * q + u] = ctr[u];
-      }
+  const bool vec = (4 * q + 3 < NK) && ((NK & 3) == 0);
+  float* o1 = out + (b * 2 * C) * NK + 4 * q;
+  float* o2 = o1 + (int64_t)C * NK;
+  for (int c = 0; c < C; ++c) {
+    const float* xc = xb + c * sc;
+    float d[4], ct[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      ct[u] = xc[cto[u]];
+      d[u] = xc[nbo[u]] - ct[u];
+    }
+    if (vec) {
+      __stcs(reinterpret_cast<float4*>(o1), make_float4(d[0], d[1], d[2], d[3]));
+      __stcs(reinterpret_cast<float4*>(o2), make_float4(ct[0], ct[1], ct[2], ct[3]));
+    } else {
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (ok[u]) {
+          o1[u] = d[u];
+          o2[u] = ct[u];
+        }
+    }
+    o1 += NK;
+    o2 += NK;
   }
 }
 
 int launch_edge_feature(const float* x, int64_t B, int64_t C, int64_t N, int64_t sb, int64_t sc,
                         int64_t sn, const int64_t* idx, int K, float* out, cudaStream_t st) {
   int64_t quads = (N * K + 3) / 4;
-  dim3 grid((unsigned)((quads + 255) / 256), (unsigned)C, (unsigned)B);
-  edge_feature_kernel<<<grid, 256, 0, st>>>(x, C, N, sb, sc, sn, idx, K, out, quads);
+  dim3 grid((unsigned)((quads + 255) / 256), (unsigned)B);
+  edge_feature_kernel<<<grid, 256, 0, st>>>(x, (int)C, N, sb, sc, sn, idx, K, out, quads);
   R3DFS_CHECK_LAUNCH();
   return 0;
 }

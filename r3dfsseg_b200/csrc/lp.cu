@@ -312,14 +312,17 @@ __global__ void in_fill_kernel(const int32_t* __restrict__ nbr, const float* __r
   in_w[(int64_t)g * nn * k + pos] = sim[ge];
 }
 
+// Launched twice: a small-capacity pass (segments up to `cap_hi` entries, little shared memory ->
+// many resident CTAs) and a large-capacity pass for the few hub columns (cap_lo < L <= cap_hi).
 __global__ __launch_bounds__(256) void in_sort_kernel(const int32_t* __restrict__ in_ptr, int nn,
                                                       int k, int32_t* __restrict__ in_src,
-                                                      float* __restrict__ in_w) {
+                                                      float* __restrict__ in_w, int cap_lo,
+                                                      int cap_hi) {
   extern __shared__ __align__(8) unsigned char s_raw[];
   const int g = blockIdx.y, j = blockIdx.x;
   const int32_t* ptr = in_ptr + (int64_t)g * (nn + 1);
   const int lo = ptr[j], L = ptr[j + 1] - lo;
-  if (L <= 1) return;
+  if (L <= 1 || L <= cap_lo || L > cap_hi) return;
   int P = 2;
   while (P < L) P <<= 1;
   int* s_src = reinterpret_cast<int*>(s_raw);
@@ -902,10 +905,11 @@ int launch_label_propagate(const int32_t* nbr, float* sim, const uint8_t* valid,
   R3DFS_CHECK_LAUNCH();
   in_fill_kernel<<<ge, 256, 0, st>>>(nbr, sim, valid, nn, k, in_ptr, in_cnt, in_src, in_w);
   R3DFS_CHECK_LAUNCH();
-  size_t smem = 8 * 8192;
-  e = cudaFuncSetAttribute(in_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  e = cudaFuncSetAttribute(in_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 8192);
   if (e != cudaSuccess) return (int)e;
-  in_sort_kernel<<<dim3(nn, G), 256, smem, st>>>(in_ptr, nn, k, in_src, in_w);
+  in_sort_kernel<<<dim3(nn, G), 256, 8 * 1024, st>>>(in_ptr, nn, k, in_src, in_w, 0, 1024);
+  R3DFS_CHECK_LAUNCH();
+  in_sort_kernel<<<dim3(nn, G), 256, 8 * 8192, st>>>(in_ptr, nn, k, in_src, in_w, 1024, 8192);
   R3DFS_CHECK_LAUNCH();
   dim3 gr((nn + 7) / 8, G);
   e = cudaMemsetAsync(cursor, 0, sizeof(int32_t) * (size_t)G, st);
