@@ -100,17 +100,28 @@ __global__ __launch_bounds__(ET_THREADS, 1) void edge_tc_kernel(
       const int st = u & 1;
       const int g = g_begin + u / TPG;
       const int p0 = g * ET_GROUP;
-      float4 hv[NCH];
+      // phase 1: every gather of the tile in flight before anything is consumed
+      float4 hv[NCH], qv4[NCH];
 #pragma unroll
       for (int i = 0; i < NCH; ++i) {
         const int c = lt + i * ET_PRODUCERS;
         const int r = c >> 4, kc = c & 15;
-        const int p = p0 + (r & 31);
+        const int p = min(p0 + (r & 31), N - 1);
+        const int nbi = nb[i] >= 0 ? nb[i] : 0;
+        hv[i] = __ldg(reinterpret_cast<const float4*>(PQ + (base + nbi) * 128 + 4 * kc));
+        qv4[i] = __ldg(reinterpret_cast<const float4*>(PQ + (base + p) * 128 + 64 + 4 * kc));
+      }
+      int nb_live = 0;
+#pragma unroll
+      for (int i = 0; i < NCH; ++i) nb_live |= (nb[i] >= 0) << i;
+      load_nb(u + 1);
+      // phase 2: h1 = LReLU(P_j + Q_i)
+#pragma unroll
+      for (int i = 0; i < NCH; ++i) {
         float4 h = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (nb[i] >= 0) {
-          const float4 a = *reinterpret_cast<const float4*>(PQ + (base + nb[i]) * 128 + 4 * kc);
-          const float4 q = *reinterpret_cast<const float4*>(PQ + (base + p) * 128 + 64 + 4 * kc);
-          h.x = a.x + q.x; h.y = a.y + q.y; h.z = a.z + q.z; h.w = a.w + q.w;
+        if ((nb_live >> i) & 1) {
+          h.x = hv[i].x + qv4[i].x; h.y = hv[i].y + qv4[i].y;
+          h.z = hv[i].z + qv4[i].z; h.w = hv[i].w + qv4[i].w;
           h.x = h.x > 0.f ? h.x : 0.2f * h.x;
           h.y = h.y > 0.f ? h.y : 0.2f * h.y;
           h.z = h.z > 0.f ? h.z : 0.2f * h.z;
@@ -118,7 +129,6 @@ __global__ __launch_bounds__(ET_THREADS, 1) void edge_tc_kernel(
         }
         hv[i] = h;
       }
-      load_nb(u + 1);
       if (u >= 2) tc::mbar_wait(&bar_full[st], ((u >> 1) - 1) & 1);  // stage's MMAs finished
       unsigned char* a_hi = smem + S::A_OFF + st * 2 * S::A_TILE;
       unsigned char* a_lo = a_hi + S::A_TILE;
