@@ -318,7 +318,7 @@ __global__ __launch_bounds__(256) void in_sort_kernel(const int32_t* __restrict_
                                                       int k, int32_t* __restrict__ in_src,
                                                       float* __restrict__ in_w, int cap_lo,
                                                       int cap_hi) {
-  extern __shared__ __align__(8) unsigned char s_raw[];
+  extern __shared__ __align__(16) unsigned char s_raw[];
   const int g = blockIdx.y, j = blockIdx.x;
   const int32_t* ptr = in_ptr + (int64_t)g * (nn + 1);
   const int lo = ptr[j], L = ptr[j + 1] - lo;
@@ -357,50 +357,6 @@ __global__ __launch_bounds__(256) void in_sort_kernel(const int32_t* __restrict_
     src[t] = s_src[t];
     val[t] = s_val[t];
   }
-}
-
-// degree and D^-1/2 (models/mpti.py:767-770): D = rowsum(A + A^T), D^-1/2 = sqrt(1 / (D + eps))
-__global__ __launch_bounds__(256) void degree_kernel(const float* __restrict__ sim,
-                                                     const int32_t* __restrict__ in_ptr,
-                                                     const float* __restrict__ in_w,
-                                                     const uint8_t* __restrict__ valid, int nn,
-                                                     int k, float* __restrict__ dinv) {
-  const int g = blockIdx.y;
-  const int i = blockIdx.x * 8 + (threadIdx.x >> 5);
-  if (i >= nn) return;
-  const int lane = threadIdx.x & 31;
-  float d = 0.f;
-  if (valid[(int64_t)g * nn + i]) {
-    const float* so = sim + ((int64_t)g * nn + i) * k;
-    for (int t = lane; t < k; t += 32) d += so[t];
-    const int32_t* ptr = in_ptr + (int64_t)g * (nn + 1);
-    const float* w = in_w + (int64_t)g * nn * k;
-    for (int t = ptr[i] + lane; t < ptr[i + 1]; t += 32) d += w[t];
-    d = warp_sum(d);
-    d = sqrtf(1.0f / (d + 2.220446049250313e-16f));
-  }
-  if (lane == 0) dinv[(int64_t)g * nn + i] = d;
-}
-
-// S = D^-1/2 W D^-1/2 on the stored pattern (models/mpti.py:772)
-__global__ void normalize_kernel(const int32_t* __restrict__ nbr, float* __restrict__ sim,
-                                 const int32_t* __restrict__ in_ptr,
-                                 const int32_t* __restrict__ in_src, float* __restrict__ in_w,
-                                 const uint8_t* __restrict__ valid, const float* __restrict__ dinv,
-                                 int nn, int k) {
-  const int g = blockIdx.y;
-  const int i = blockIdx.x * 8 + (threadIdx.x >> 5);
-  if (i >= nn) return;
-  if (!valid[(int64_t)g * nn + i]) return;
-  const int lane = threadIdx.x & 31;
-  const float* dg = dinv + (int64_t)g * nn;
-  const float di = dg[i];
-  const int64_t ob = ((int64_t)g * nn + i) * k;
-  for (int t = lane; t < k; t += 32) sim[ob + t] = (di * sim[ob + t]) * dg[nbr[ob + t]];
-  const int32_t* ptr = in_ptr + (int64_t)g * (nn + 1);
-  const int64_t ib = (int64_t)g * nn * k;
-  for (int t = ptr[i] + lane; t < ptr[i + 1]; t += 32)
-    in_w[ib + t] = (di * in_w[ib + t]) * dg[in_src[ib + t]];
 }
 
 // --------------------------------------------------------------------------------------------
