@@ -246,7 +246,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--episodes", type=int, default=100, help="episodes per step per GPU")
     ap.add_argument("--chunk", type=int, default=25, help="episodes per C-ABI call")
-    ap.add_argument("--streams", type=int, default=2,
+    ap.add_argument("--streams", type=int, default=4,
                     help="CUDA streams the chunks of a step are spread over (independent episodes)")
     ap.add_argument("--cpu-episodes", type=int, default=3, help="cpu_baseline sample size")
     ap.add_argument("--ref-episodes-per-step", type=int, default=1)

@@ -1,6 +1,6 @@
 // SelfAttention (eval) on the tensor cores  (reference models/attention.py:39-48):
 //     y = softmax((q / 8)^T k) v ,  single head, d = 64, per cloud of N points.
-// One CTA = 128 query points; thread = (query row, column half) for everything read from TMEM.
+// One CTA = 128 query points; thread = (query row, 16-column quarter) for everything read from TMEM.
 // Two sweeps over the key tiles (64 keys each), both with 3xTF32 tcgen05.mma:
 //   sweep 1:  S = Q K^T  -> running row maximum m            (no exponentials)
 //   sweep 2:  S again (bit-identical), P = exp(S - m) written as a K-major UMMA A tile (hi/lo),
@@ -10,7 +10,7 @@
 #include "common.cuh"
 #include "tc.cuh"
 
-#define AT_THREADS 256
+#define AT_THREADS 512  // 16 warps: TMEM lane quarter = w % 4, 16-column quarter = w / 4
 #define AT_BQ 128
 #define AT_BK 64
 
@@ -23,15 +23,15 @@ struct AttTcSmem {
   static constexpr int K_OFF = Q_OFF + 2 * Q_TILE;
   static constexpr int V_OFF = K_OFF + 2 * K_TILE;
   static constexpr int P_OFF = V_OFF + 2 * V_TILE;
-  static constexpr int X_OFF = P_OFF + 2 * P_TILE;  // exchange: 2 x 128 floats
-  static constexpr int TOTAL = X_OFF + 2 * 128 * 4 + 64;
+  static constexpr int X_OFF = P_OFF + 2 * P_TILE;  // exchange: 4 x 128 floats
+  static constexpr int TOTAL = X_OFF + 4 * 128 * 4 + 64;
 };
 
 // 64 rows x 64 columns of `src` (row stride ld, starting column col_off) -> K-major hi/lo tiles
-__device__ __forceinline__ void at_load_rows(float4 (&v)[4], const float* __restrict__ src, int ld,
+__device__ __forceinline__ void at_load_rows(float4 (&v)[2], const float* __restrict__ src, int ld,
                                              int64_t row0, int64_t rows_end, int col_off, int tid) {
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
+  for (int i = 0; i < 2; ++i) {
     const int c = tid + i * AT_THREADS;
     const int r = c >> 4, kc = c & 15;
     v[i] = (row0 + r < rows_end)
@@ -39,11 +39,11 @@ __device__ __forceinline__ void at_load_rows(float4 (&v)[4], const float* __rest
                : make_float4(0.f, 0.f, 0.f, 0.f);
   }
 }
-__device__ __forceinline__ void at_store_rows(const float4 (&v)[4], unsigned char* hi,
+__device__ __forceinline__ void at_store_rows(const float4 (&v)[2], unsigned char* hi,
                                               unsigned char* lo, int tid) {
   constexpr int LBO = tc::tile_lbo(64);
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
+  for (int i = 0; i < 2; ++i) {
     const int c = tid + i * AT_THREADS;
     const int r = c >> 4, kc = c & 15;
     float4 h, l;
@@ -53,10 +53,10 @@ __device__ __forceinline__ void at_store_rows(const float4 (&v)[4], unsigned cha
   }
 }
 // V rows (keys) -> V^T tile: element (d, key) at (key/4)*LBO + d*16 + (key%4)*4
-__device__ __forceinline__ void at_load_v(float4 (&v)[4], const float* __restrict__ src, int ld,
+__device__ __forceinline__ void at_load_v(float4 (&v)[2], const float* __restrict__ src, int ld,
                                           int64_t row0, int64_t rows_end, int tid) {
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
+  for (int i = 0; i < 2; ++i) {
     const int c = tid + i * AT_THREADS;
     const int key = c & 63, d4 = c >> 6;
     v[i] = (row0 + key < rows_end)
@@ -64,11 +64,11 @@ __device__ __forceinline__ void at_load_v(float4 (&v)[4], const float* __restric
                : make_float4(0.f, 0.f, 0.f, 0.f);
   }
 }
-__device__ __forceinline__ void at_store_vT(const float4 (&v)[4], unsigned char* hi,
+__device__ __forceinline__ void at_store_vT(const float4 (&v)[2], unsigned char* hi,
                                             unsigned char* lo, int tid) {
   constexpr int LBO = tc::tile_lbo(64);
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
+  for (int i = 0; i < 2; ++i) {
     const int c = tid + i * AT_THREADS;
     const int key = c & 63, d4 = c >> 6;
     float4 h, l;
@@ -101,7 +101,7 @@ __global__ __launch_bounds__(AT_THREADS, 1) void attention_tc_kernel(const float
   constexpr uint32_t IDESC = tc::make_idesc_tf32(128, 64);
   const int T = (N + AT_BK - 1) / AT_BK;
   const int row = 32 * (w & 3) + lane;  // TMEM lane = query row
-  const int half = w >> 2;              // columns [32*half, 32*half+32) of every 64-wide tile
+  const int quarter = w >> 2;           // columns [16*quarter, 16*quarter+16) of every 64-wide tile
   float* xch = reinterpret_cast<float*>(smem + S::X_OFF);
 
   if (tid == 0) {
@@ -155,7 +155,7 @@ __global__ __launch_bounds__(AT_THREADS, 1) void attention_tc_kernel(const float
   // ---------------- sweep 1: row maxima -------------------------------------------------------
   float m_run = -INFINITY;
   {
-    float4 kv[4];
+    float4 kv[2];
     at_load_rows(kv, qkv, ld, base, base + N, 64, tid);
     for (int j = 0; j < T; ++j) {
       at_store_rows(kv, k_hi_p, k_lo_p, tid);
@@ -170,25 +170,25 @@ __global__ __launch_bounds__(AT_THREADS, 1) void attention_tc_kernel(const float
       tc::mbar_wait(&bar_s, ph_s);
       ph_s ^= 1;
       tc::tc_fence_after();
-      float v[32];
-      tc::tmem_ld32(tmem_s + ((uint32_t)(32 * (w & 3)) << 16) + (uint32_t)(32 * half), v);
-      const int c0 = j * AT_BK + 32 * half;
+      float v[16];
+      tc::tmem_ld16(tmem_s + ((uint32_t)(32 * (w & 3)) << 16) + (uint32_t)(16 * quarter), v);
+      const int c0 = j * AT_BK + 16 * quarter;
 #pragma unroll
-      for (int e = 0; e < 32; ++e)
+      for (int e = 0; e < 16; ++e)
         if (c0 + e < N) m_run = fmaxf(m_run, v[e]);
     }
   }
   // combine the two column halves of every row
-  xch[half * 128 + row] = m_run;
+  xch[quarter * 128 + row] = m_run;
   tc::tc_fence_before();
   __syncthreads();
-  const float m_row = fmaxf(xch[row], xch[128 + row]);
+  const float m_row = fmaxf(fmaxf(xch[row], xch[128 + row]), fmaxf(xch[256 + row], xch[384 + row]));
   __syncthreads();
 
   // ---------------- sweep 2: P = exp(S - m), l, O += P V ---------------------------------------
   float l_run = 0.f;
   {
-    float4 kv[4], vv[4];
+    float4 kv[2], vv[2];
     at_load_rows(kv, qkv, ld, base, base + N, 64, tid);
     at_load_v(vv, qkv, ld, base, base + N, tid);
     for (int j = 0; j < T; ++j) {
@@ -213,11 +213,11 @@ __global__ __launch_bounds__(AT_THREADS, 1) void attention_tc_kernel(const float
       tc::mbar_wait(&bar_s, ph_s);
       ph_s ^= 1;
       tc::tc_fence_after();
-      float v[32];
-      tc::tmem_ld32(tmem_s + ((uint32_t)(32 * (w & 3)) << 16) + (uint32_t)(32 * half), v);
-      const int c0 = j * AT_BK + 32 * half;
+      float v[16];
+      tc::tmem_ld16(tmem_s + ((uint32_t)(32 * (w & 3)) << 16) + (uint32_t)(16 * quarter), v);
+      const int c0 = j * AT_BK + 16 * quarter;
 #pragma unroll
-      for (int e = 0; e < 32; e += 4) {
+      for (int e = 0; e < 16; e += 4) {
         float4 p;
         p.x = (c0 + e + 0 < N) ? expf(v[e + 0] - m_row) : 0.f;
         p.y = (c0 + e + 1 < N) ? expf(v[e + 1] - m_row) : 0.f;
@@ -226,7 +226,7 @@ __global__ __launch_bounds__(AT_THREADS, 1) void attention_tc_kernel(const float
         l_run += (p.x + p.y) + (p.z + p.w);
         float4 h, l;
         tc::split4(p, h, l);
-        const int kc = (32 * half + e) >> 2;  // 16-byte chunk along the key dimension
+        const int kc = (16 * quarter + e) >> 2;  // 16-byte chunk along the key dimension
         *reinterpret_cast<float4*>(p_hi_p + kc * LBO_Q + row * 16) = h;
         *reinterpret_cast<float4*>(p_lo_p + kc * LBO_Q + row * 16) = l;
       }
@@ -250,19 +250,19 @@ __global__ __launch_bounds__(AT_THREADS, 1) void attention_tc_kernel(const float
     }
   }
   // ---------------- epilogue: O / l ------------------------------------------------------------
-  xch[half * 128 + row] = l_run;
+  xch[quarter * 128 + row] = l_run;
   tc::mbar_wait(&bar_pv, ph_pv);
   tc::tc_fence_after();
   __syncthreads();
-  const float inv = 1.f / (xch[row] + xch[128 + row]);
+  const float inv = 1.f / ((xch[row] + xch[128 + row]) + (xch[256 + row] + xch[384 + row]));
   {
-    float v[32];
-    tc::tmem_ld32(tmem_o + ((uint32_t)(32 * (w & 3)) << 16) + (uint32_t)(32 * half), v);
+    float v[16];
+    tc::tmem_ld16(tmem_o + ((uint32_t)(32 * (w & 3)) << 16) + (uint32_t)(16 * quarter), v);
     const int q = q0 + row;
     if (q < N) {
-      float* y = Y + map(base + q) * (int64_t)ldy + 32 * half;
+      float* y = Y + map(base + q) * (int64_t)ldy + 16 * quarter;
 #pragma unroll
-      for (int e = 0; e < 32; e += 4)
+      for (int e = 0; e < 16; e += 4)
         *reinterpret_cast<float4*>(y + e) =
             make_float4(v[e] * inv, v[e + 1] * inv, v[e + 2] * inv, v[e + 3] * inv);
     }
