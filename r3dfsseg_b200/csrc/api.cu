@@ -377,9 +377,12 @@ int r3dfs_fps(const float* feat, int64_t D, const int32_t* set_off, const int32_
 
 // ---- getMutiplePrototypes -------------------------------------------------------------------------
 size_t r3dfs_multi_prototypes_workspace(int64_t total_rows, int n_sets, int k) {
-  (void)total_rows;
+  const size_t ch = multi_prototypes_chunks((int)total_rows);
   return align_up(sizeof(int32_t) * (size_t)n_sets * (k + 1), 256) +
-         align_up(sizeof(int32_t) * (size_t)n_sets, 256) + 1024;
+         align_up(sizeof(int32_t) * (size_t)n_sets, 256) +
+         align_up(sizeof(float) * (size_t)n_sets * ch * (k + 1) * 256, 256) +
+         align_up(sizeof(int32_t) * (size_t)n_sets * ch * (k + 1), 256) +
+         align_up(sizeof(float) * (size_t)n_sets * 256, 256) + 2048;
 }
 
 int r3dfs_multi_prototypes(const float* feat, int64_t D, const int32_t* set_off,
@@ -395,9 +398,15 @@ int r3dfs_multi_prototypes(const float* feat, int64_t D, const int32_t* set_off,
   WsBump ws(wsp, ws_bytes);
   int32_t* picks = ws.take<int32_t>((size_t)n_sets * (k + 1));
   int32_t* pick_cnt = ws.take<int32_t>(n_sets);
+  const size_t ch = multi_prototypes_chunks((int)total_rows);
+  float* partial = ws.take<float>((size_t)n_sets * ch * (k + 1) * D);
+  int32_t* pcount = ws.take<int32_t>((size_t)n_sets * ch * (k + 1));
+  float* seed_stats = ws.take<float>((size_t)n_sets * 256);
+  if (!ws.ok()) return R3DFS_E_WORKSPACE;
   // n_cap: no set can be larger than the whole buffer
   return launch_multi_prototypes(feat, (int)D, set_off, set_n, n_sets, (int)total_rows, k, picks,
-                                 pick_cnt, seed_idx_out, proto_count, assign_out, n_sets,
+                                 pick_cnt, seed_idx_out, proto_count, assign_out, partial, pcount,
+                                 seed_stats, n_sets,
                                  (int64_t)n_sets * (k + 1), proto_out, (int)D,
                                  (cudaStream_t)stream);
 }
@@ -509,7 +518,8 @@ struct EpisodeWs {
   float* F;
   int32_t *fg_cnt, *keep, *set_off, *set_n, *cloud_bg_off, *cloud_fg_off;
   float* setfeat;
-  int32_t *picks, *pick_cnt, *seeds, *proto_cnt, *assign;
+  int32_t *picks, *pick_cnt, *seeds, *proto_cnt, *assign, *pcount;
+  float *partial, *seed_stats;
   float* cell_mean;
   int32_t* cell_cnt;
   uint8_t* valid;
@@ -542,6 +552,12 @@ static void carve_episode(WsBump& ws, const r3dfs_episode_cfg_t* c, const Episod
   w.seeds = ws.take<int32_t>(G * d.S * d.slot);
   w.proto_cnt = ws.take<int32_t>(G * d.S);
   w.assign = ws.take<int32_t>(G * d.ns_pts);
+  {
+    const size_t ch = multi_prototypes_chunks(d.ns_pts);
+    w.partial = ws.take<float>(G * d.S * ch * d.slot * R3DFS_FEAT_DIM);
+    w.pcount = ws.take<int32_t>(G * d.S * ch * d.slot);
+    w.seed_stats = ws.take<float>(G * d.S * 256);
+  }
   w.cell_mean = ws.take<float>(G * d.C * 5 * R3DFS_FEAT_DIM);
   w.cell_cnt = ws.take<int32_t>(G * d.C * 5);
   w.valid = ws.take<uint8_t>(G * nn);
@@ -607,7 +623,8 @@ static int episode_graph_half(const r3dfs_episode_cfg_t* cfg, const EpisodeDims&
   if (sr) sr->mark(R3DFS_ST_SETS, st);
   R3DFS_TRY(launch_multi_prototypes(w.setfeat, D, w.set_off, w.set_n, E * d.S, d.ns_pts,
                                     cfg->n_subprototypes, w.picks, w.pick_cnt, w.seeds,
-                                    w.proto_cnt, w.assign, d.S, d.ep_rows, w.F, D, st, sr));
+                                    w.proto_cnt, w.assign, w.partial, w.pcount, w.seed_stats, d.S,
+                                    d.ep_rows, w.F, D, st, sr));
   if (sr) sr->mark(R3DFS_ST_PROTO, st);
   // graph: nodes = [prototype slots | query points]
   graph_init_kernel<<<dim3(nblk(d.nn), E), 256, 0, st>>>(w.proto_cnt, d.S, d.slot, d.ppad, d.nn,

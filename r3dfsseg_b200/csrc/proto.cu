@@ -317,78 +317,112 @@ __global__ __launch_bounds__(ASSIGN_THREADS) void assign_kernel(
 }
 
 // --------------------------------------------------------------------------------------------
-// Prototype = mean of its members (models/mpti.py:625-629).  One CTA per (set, prototype):
-// ordered compaction of the members chunk by chunk, then thread d sums dimension d over the
-// members in index order (deterministic; no floating-point atomics).
+// Prototype = mean of its members (models/mpti.py:625-629), deterministic, in two steps:
+//   1. one CTA per (set, chunk of 2048 points): thread d walks the chunk's points in order and
+//      adds dimension d of each point to its prototype's accumulator in shared memory;
+//   2. one CTA per (set, prototype): chunk partials are added in chunk order, divided by the count.
+// Every feature row is read exactly once; no floating-point atomics.
 // --------------------------------------------------------------------------------------------
 #define MEAN_THREADS 256
+#define PM_CHUNK 2048
 
-__global__ __launch_bounds__(MEAN_THREADS) void proto_mean_kernel(
+__global__ __launch_bounds__(MEAN_THREADS) void proto_partial_kernel(
     const float* __restrict__ feat, int D, const int32_t* __restrict__ set_off,
     const int32_t* __restrict__ set_n, const int32_t* __restrict__ proto_cnt,
-    const int32_t* __restrict__ assign, int slot, int sets_per_group, int64_t group_rows,
-    float* __restrict__ proto_out, int ld_out) {
-  __shared__ int s_list[MEAN_THREADS];
-  __shared__ int s_wcnt[MEAN_THREADS / 32];
-  __shared__ int s_total;
+    const int32_t* __restrict__ assign, int m_max, int n_chunks, float* __restrict__ partial,
+    int32_t* __restrict__ pcount) {
+  extern __shared__ __align__(16) float s_acc[];  // [m_max][D] then [m_max] counts
+  const int set = blockIdx.y, chunk = blockIdx.x;
+  const int n = set_n[set];
+  const int p0 = chunk * PM_CHUNK;
+  if (p0 >= n) return;
+  const int p1 = min(n, p0 + PM_CHUNK);
+  const int m = proto_cnt[set];
+  const int64_t row0 = set_off[set];
+  const int tid = threadIdx.x;
+  int* s_cnt = reinterpret_cast<int*>(s_acc + (size_t)m_max * D);
+  for (int e = tid; e < m * D; e += MEAN_THREADS) s_acc[e] = 0.f;
+  for (int e = tid; e < m; e += MEAN_THREADS) s_cnt[e] = 0;
+  __syncthreads();
+  if (tid < D) {
+    const float* f = feat + (row0 + p0) * (int64_t)D + tid;
+    const int32_t* a = assign + row0 + p0;
+#pragma unroll 4
+    for (int i = 0; i < p1 - p0; ++i) {
+      const int p = a[i];
+      s_acc[p * D + tid] += f[(int64_t)i * D];
+    }
+  } else if (tid == MEAN_THREADS - 1) {
+    const int32_t* a = assign + row0 + p0;
+    for (int i = 0; i < p1 - p0; ++i) s_cnt[a[i]] += 1;
+  }
+  __syncthreads();
+  float* out = partial + ((int64_t)set * n_chunks + chunk) * m_max * D;
+  for (int e = tid; e < m * D; e += MEAN_THREADS) out[e] = s_acc[e];
+  int32_t* oc = pcount + ((int64_t)set * n_chunks + chunk) * m_max;
+  for (int e = tid; e < m; e += MEAN_THREADS) oc[e] = s_cnt[e];
+}
+
+__global__ __launch_bounds__(MEAN_THREADS) void proto_reduce_kernel(
+    const float* __restrict__ partial, const int32_t* __restrict__ pcount, int D,
+    const int32_t* __restrict__ set_n, const int32_t* __restrict__ proto_cnt, int m_max,
+    int n_chunks, int slot, int sets_per_group, int64_t group_rows, float* __restrict__ proto_out,
+    int ld_out) {
   const int set = blockIdx.y, p = blockIdx.x;
   if (p >= proto_cnt[set]) return;
-  const int n = set_n[set];
-  const int64_t row0 = set_off[set];
-  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int nch = (set_n[set] + PM_CHUNK - 1) / PM_CHUNK;
+  const int tid = threadIdx.x;
+  if (tid >= D) return;
   float acc = 0.f;
   int count = 0;
-  for (int c0 = 0; c0 < n; c0 += MEAN_THREADS) {
-    const int i = c0 + tid;
-    const bool f = (i < n) && (assign[row0 + i] == p);
-    const unsigned bal = __ballot_sync(0xffffffffu, f);
-    if (lane == 0) s_wcnt[w] = __popc(bal);
-    __syncthreads();
-    int woff = 0;
-    for (int q = 0; q < w; ++q) woff += s_wcnt[q];
-    if (tid == 0) {
-      int t = 0;
-      for (int q = 0; q < MEAN_THREADS / 32; ++q) t += s_wcnt[q];
-      s_total = t;
-    }
-    if (f) s_list[woff + __popc(bal & ((1u << lane) - 1))] = i;
-    __syncthreads();
-    const int tot = s_total;
-    if (tid < D) {
-      for (int q = 0; q < tot; ++q) acc += feat[(row0 + s_list[q]) * (int64_t)D + tid];
-    }
-    count += tot;
-    __syncthreads();
+  for (int c = 0; c < nch; ++c) {
+    const int64_t b = (int64_t)set * n_chunks + c;
+    acc += partial[(b * m_max + p) * D + tid];
+    count += pcount[b * m_max + p];
   }
-  if (tid < D) {
-    int64_t orow = (int64_t)(set / sets_per_group) * group_rows +
-                   (int64_t)(set % sets_per_group) * slot + p;
-    proto_out[orow * ld_out + tid] = acc / (float)count;
-  }
+  const int64_t orow = (int64_t)(set / sets_per_group) * group_rows +
+                       (int64_t)(set % sets_per_group) * slot + p;
+  proto_out[orow * ld_out + tid] = acc / (float)count;
 }
+
+int multi_prototypes_chunks(int n_cap) { return (n_cap + PM_CHUNK - 1) / PM_CHUNK; }
 
 int launch_multi_prototypes(const float* feat, int D, const int32_t* set_off,
                             const int32_t* set_n, int n_sets, int n_cap, int k, int32_t* picks,
                             int32_t* pick_cnt, int32_t* seeds, int32_t* proto_cnt,
-                            int32_t* assign, int sets_per_group, int64_t group_rows,
-                            float* proto_out, int ld_out, cudaStream_t st, const StageRec* sr) {
+                            int32_t* assign, float* partial, int32_t* pcount, float* seed_stats,
+                            int sets_per_group, int64_t group_rows, float* proto_out, int ld_out,
+                            cudaStream_t st, const StageRec* sr) {
   const int m_max = k + 1;
   if (m_max > 128 || D > MEAN_THREADS) return R3DFS_E_UNSUPPORTED;
   R3DFS_TRY(launch_fps_ex(feat, D, set_off, set_n, n_sets, n_cap, m_max, k, picks, pick_cnt, st));
   if (sr) sr->mark(R3DFS_ST_FPS, st);
   seeds_unique_kernel<<<n_sets, 128, 0, st>>>(picks, pick_cnt, set_n, m_max, k, seeds, proto_cnt);
   R3DFS_CHECK_LAUNCH();
-  size_t smem = sizeof(float) * (size_t)m_max * D;
-  cudaError_t e = cudaFuncSetAttribute(assign_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)smem);
+  cudaError_t e = cudaSuccess;
+  if (simt_gemm_forced()) {  // FP32 CUDA-core evaluation of every (point, seed) pair
+    size_t smem = sizeof(float) * (size_t)m_max * D;
+    e = cudaFuncSetAttribute(assign_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    dim3 ga((n_cap + ASSIGN_PTS_PER_CTA - 1) / ASSIGN_PTS_PER_CTA, n_sets);
+    assign_kernel<<<ga, ASSIGN_THREADS, smem, st>>>(feat, D, set_off, set_n, seeds, proto_cnt,
+                                                    m_max, k, assign);
+    R3DFS_CHECK_LAUNCH();
+  } else {  // tensor-core filter + exact verify (tc_assign.cu)
+    R3DFS_TRY(launch_assign_tc(feat, D, set_off, set_n, seeds, proto_cnt, n_sets, n_cap, m_max, k,
+                               seed_stats, seed_stats + (size_t)n_sets * 128, assign, st));
+  }
+  const int n_chunks = multi_prototypes_chunks(n_cap);
+  const size_t smem_p = sizeof(float) * (size_t)m_max * D + sizeof(int) * (size_t)m_max;
+  e = cudaFuncSetAttribute(proto_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           (int)smem_p);
   if (e != cudaSuccess) return (int)e;
-  dim3 ga((n_cap + ASSIGN_PTS_PER_CTA - 1) / ASSIGN_PTS_PER_CTA, n_sets);
-  assign_kernel<<<ga, ASSIGN_THREADS, smem, st>>>(feat, D, set_off, set_n, seeds, proto_cnt, m_max,
-                                                  k, assign);
+  proto_partial_kernel<<<dim3(n_chunks, n_sets), MEAN_THREADS, smem_p, st>>>(
+      feat, D, set_off, set_n, proto_cnt, assign, m_max, n_chunks, partial, pcount);
   R3DFS_CHECK_LAUNCH();
-  dim3 gm(m_max, n_sets);
-  proto_mean_kernel<<<gm, MEAN_THREADS, 0, st>>>(feat, D, set_off, set_n, proto_cnt, assign, m_max,
-                                                 sets_per_group, group_rows, proto_out, ld_out);
+  proto_reduce_kernel<<<dim3(m_max, n_sets), MEAN_THREADS, 0, st>>>(
+      partial, pcount, D, set_n, proto_cnt, m_max, n_chunks, m_max, sets_per_group, group_rows,
+      proto_out, ld_out);
   R3DFS_CHECK_LAUNCH();
   return 0;
 }

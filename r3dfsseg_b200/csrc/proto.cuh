@@ -8,9 +8,16 @@ int launch_fps_ex(const float* feat, int D, const int32_t* set_off, const int32_
 int launch_multi_prototypes(const float* feat, int D, const int32_t* set_off,
                             const int32_t* set_n, int n_sets, int n_cap, int k, int32_t* picks,
                             int32_t* pick_cnt, int32_t* seeds, int32_t* proto_cnt,
-                            int32_t* assign, int sets_per_group, int64_t group_rows,
-                            float* proto_out, int ld_out, cudaStream_t st,
-                            const StageRec* sr = nullptr);
+                            int32_t* assign, float* partial, int32_t* pcount, float* seed_stats,
+                            int sets_per_group, int64_t group_rows, float* proto_out, int ld_out,
+                            cudaStream_t st, const StageRec* sr = nullptr);
+// seed_stats: (2, n_sets, 128) floats of scratch
+int launch_assign_tc(const float* feat, int D, const int32_t* set_off, const int32_t* set_n,
+                     const int32_t* seeds, const int32_t* proto_cnt, int n_sets, int n_cap,
+                     int m_max, int k, float* sn, float* ss, int32_t* assign, cudaStream_t st);
+// scratch: partial (n_sets, chunks, k+1, D) floats and pcount (n_sets, chunks, k+1) ints with
+// chunks = multi_prototypes_chunks(n_cap)
+int multi_prototypes_chunks(int n_cap);
 int launch_set_compaction(const float* F, int64_t ep_rows, int64_t sup_row_off, int E, int n_way,
                           int k_shot, int N, int D, const int32_t* sy, const int32_t* keep,
                           int32_t* fg_cnt, int32_t* set_off, int32_t* set_n, int32_t* cloud_bg_off,
