@@ -162,36 +162,52 @@ __global__ __launch_bounds__(SEL_THREADS) void knn_select_kernel(const float* __
   const unsigned T = s_prefix;
   const int need_eq = s_need;
   int32_t* out = nbr + ((int64_t)g * nn + i) * k;
-  int run_eq = 0, run_sel = 0;
-  for (int c0 = 0; c0 < nn; c0 += SEL_THREADS) {
-    const int j = c0 + tid;
-    const unsigned key = j < nn ? s_key[j] : 0xffffffffu;
-    const bool lt = key < T, eq = key == T;
-    const unsigned beq = __ballot_sync(0xffffffffu, eq);
-    if (lane == 0) s_w[0][w] = __popc(beq);
-    __syncthreads();
-    int eoff = run_eq, etot = 0;
-    for (int q = 0; q < SEL_THREADS / 32; ++q) {
-      if (q < w) eoff += s_w[0][q];
-      etot += s_w[0][q];
+  // ordered compaction with two barriers: every thread owns a contiguous run of `per` keys (odd
+  // stride -> conflict-free), counts its (< T) and (== T) keys, a block-wide exclusive scan gives
+  // its output offset and its rank among the ties, then it writes its selected indices in order.
+  int per = (nn + SEL_THREADS - 1) / SEL_THREADS;
+  per |= 1;
+  const int j0 = tid * per, j1 = min(nn, j0 + per);
+  int c_lt = 0, c_eq = 0;
+  for (int j = j0; j < j1; ++j) {
+    const unsigned key = s_key[j];
+    c_lt += key < T;
+    c_eq += key == T;
+  }
+  // warp inclusive scans
+  int s_lt = c_lt, s_eq = c_eq;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int a = __shfl_up_sync(0xffffffffu, s_lt, o), b2 = __shfl_up_sync(0xffffffffu, s_eq, o);
+    if (lane >= o) {
+      s_lt += a;
+      s_eq += b2;
     }
-    const int erank = eoff + __popc(beq & ((1u << lane) - 1));
-    const bool sel = lt || (eq && erank < need_eq);
-    const unsigned bsel = __ballot_sync(0xffffffffu, sel);
-    if (lane == 0) s_w[1][w] = __popc(bsel);
-    __syncthreads();
-    int soff = run_sel, stot = 0;
-    for (int q = 0; q < SEL_THREADS / 32; ++q) {
-      if (q < w) soff += s_w[1][q];
-      stot += s_w[1][q];
+  }
+  if (lane == 31) {
+    s_w[0][w] = s_lt;
+    s_w[1][w] = s_eq;
+  }
+  __syncthreads();
+  int off_lt = s_lt - c_lt, off_eq = s_eq - c_eq;
+  for (int q = 0; q < w; ++q) {
+    off_lt += s_w[0][q];
+    off_eq += s_w[1][q];
+  }
+  // output position of my first selected key = (#lt before me) + min(#eq before me, need_eq)
+  int pos = off_lt + min(off_eq, need_eq);
+  int eq_rank = off_eq;
+  for (int j = j0; j < j1; ++j) {
+    const unsigned key = s_key[j];
+    bool sel = key < T;
+    if (key == T) {
+      sel = eq_rank < need_eq;
+      ++eq_rank;
     }
     if (sel) {
-      const int pos = soff + __popc(bsel & ((1u << lane) - 1));
       if (pos < k) out[pos] = j;
+      ++pos;
     }
-    run_eq += etot;
-    run_sel += stot;
-    __syncthreads();
   }
 }
 
