@@ -97,8 +97,9 @@ int r3dfs_linear(const float* x, int64_t ldx, const float* w, const float* s, co
                  int act, int64_t M, int64_t K, int64_t Nout, float* y, int64_t ldy,
                  r3dfs_stream_t stream);
 /* Same, with the implementation pinned: impl 0 = default (tcgen05 3xTF32 tensor-core kernel),
- * 1 = FP32 CUDA-core kernel, 2 = tensor-core kernel.  Both are exact to FP32 rounding; the
- * switch exists for A/B measurements and the parity tests. */
+ * 1 = FP32 CUDA-core kernel, 2 = tensor-core kernel fed through registers, 3 = tensor-core kernel
+ * fed by TMA (R3DFS_E_UNSUPPORTED unless ldx % 4 == 0, K % 4 == 0 and 16-byte aligned pointers).
+ * All are exact to FP32 rounding; the switch exists for A/B measurements and the parity tests. */
 int r3dfs_linear_ex(const float* x, int64_t ldx, const float* w, const float* s, const float* t,
                     int act, int64_t M, int64_t K, int64_t Nout, float* y, int64_t ldy, int impl,
                     r3dfs_stream_t stream);

@@ -105,6 +105,9 @@ int launch_linear_auto(const float* X, int ldx, const float* W, const float* s, 
                        cudaStream_t st) {
   if (simt_gemm_forced())
     return launch_linear(X, ldx, W, s, t, act, M, K, Nout, Y, ldy, map, st);
+  // TMA-fed kernel when the operands meet TMA's alignment rules, register-fed kernel otherwise
+  const int rc = launch_linear_tma(X, ldx, W, s, t, act, M, K, Nout, Y, ldy, map, st);
+  if (rc != R3DFS_E_UNSUPPORTED) return rc;
   return launch_linear_tc(X, ldx, W, s, t, act, M, K, Nout, Y, ldy, map, st);
 }
 
@@ -267,7 +270,7 @@ int r3dfs_linear_ex(const float* x, int64_t ldx, const float* w, const float* s,
                     r3dfs_stream_t stream) {
   if (!x || !w || !y || M <= 0 || K <= 0 || Nout <= 0 || ldx < K || ldy < Nout)
     return R3DFS_E_BADARG;
-  if (act < 0 || act > 2 || Nout > 65535 * 64 || impl < 0 || impl > 2) return R3DFS_E_UNSUPPORTED;
+  if (act < 0 || act > 2 || Nout > 65535 * 64 || impl < 0 || impl > 3) return R3DFS_E_UNSUPPORTED;
   cudaStream_t st = (cudaStream_t)stream;
   if (impl == 1)
     return launch_linear(x, (int)ldx, w, s, t, act, M, (int)K, (int)Nout, y, (int)ldy,
@@ -275,6 +278,9 @@ int r3dfs_linear_ex(const float* x, int64_t ldx, const float* w, const float* s,
   if (impl == 2)
     return launch_linear_tc(x, (int)ldx, w, s, t, act, M, (int)K, (int)Nout, y, (int)ldy,
                             identity_map(), st);
+  if (impl == 3)
+    return launch_linear_tma(x, (int)ldx, w, s, t, act, M, (int)K, (int)Nout, y, (int)ldy,
+                             identity_map(), st);
   return launch_linear_auto(x, (int)ldx, w, s, t, act, M, (int)K, (int)Nout, y, (int)ldy,
                             identity_map(), st);
 }

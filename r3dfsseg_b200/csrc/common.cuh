@@ -95,6 +95,9 @@ int launch_linear(const float* X, int ldx, const float* W, const float* s, const
 int launch_linear_tc(const float* X, int ldx, const float* W, const float* s, const float* t,
                      int act, int64_t M, int K, int Nout, float* Y, int ldy, RowMap map,
                      cudaStream_t st);
+int launch_linear_tma(const float* X, int ldx, const float* W, const float* s, const float* t,
+                      int act, int64_t M, int K, int Nout, float* Y, int ldy, RowMap map,
+                      cudaStream_t st);
 // tensor-core path unless R3DFS_SIMT_GEMM=1 is set in the environment (A/B measurements)
 int launch_linear_auto(const float* X, int ldx, const float* W, const float* s, const float* t,
                        int act, int64_t M, int K, int Nout, float* Y, int ldy, RowMap map,

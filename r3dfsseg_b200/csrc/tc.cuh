@@ -145,6 +145,37 @@ __device__ __forceinline__ void split4(const float4& x, float4& hi, float4& lo) 
   lo.z = tf32_rn(x.z - hi.z); lo.w = tf32_rn(x.w - hi.w);
 }
 
+// Coalesced row-major store of a warp's 32 x 32 accumulator chunk: thread `lane` holds row `lane`
+// (32 consecutive columns in v[]).  The chunk is transposed through a per-warp shared-memory
+// buffer (32 x 33 floats) so that every store instruction writes 4 rows x 128 contiguous bytes.
+// `rowptr(r)` returns the output pointer of the chunk's row r at its first column (or nullptr).
+template <class RowPtr>
+__device__ __forceinline__ void store_chunk_coalesced(float* wbuf, const float (&v)[32], int lane,
+                                                      int ncols_valid, bool vec_ok, RowPtr rowptr) {
+#pragma unroll
+  for (int j = 0; j < 32; ++j) wbuf[lane * 33 + j] = v[j];
+  __syncwarp();
+  const int rsub = lane >> 3, c4 = (lane & 7) * 4;
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const int r = it * 4 + rsub;
+    float* dst = rowptr(r);
+    const float a = wbuf[r * 33 + c4], b = wbuf[r * 33 + c4 + 1], c = wbuf[r * 33 + c4 + 2],
+                d = wbuf[r * 33 + c4 + 3];
+    if (dst) {
+      if (vec_ok && c4 + 3 < ncols_valid) {
+        *reinterpret_cast<float4*>(dst + c4) = make_float4(a, b, c, d);
+      } else {
+        if (c4 + 0 < ncols_valid) dst[c4 + 0] = a;
+        if (c4 + 1 < ncols_valid) dst[c4 + 1] = b;
+        if (c4 + 2 < ncols_valid) dst[c4 + 2] = c;
+        if (c4 + 3 < ncols_valid) dst[c4 + 3] = d;
+      }
+    }
+  }
+  __syncwarp();
+}
+
 // byte size of one operand tile (ROWS rows x KC4 16-byte chunks) in the layout above
 __host__ __device__ constexpr int tile_lbo(int rows) { return rows * 16 + 16; }
 __host__ __device__ constexpr int tile_bytes(int rows, int kc4) { return kc4 * tile_lbo(rows); }

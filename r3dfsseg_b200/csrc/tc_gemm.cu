@@ -152,39 +152,32 @@ __global__ __launch_bounds__(TCG_THREADS, 3) void linear_tc_kernel(
 
   // epilogue: warp w reads TMEM lanes 32*(w%4).., columns half (w/4)
   {
-    const int row_l = 32 * (w & 3) + lane;
-    const int64_t m = m0 + row_l;
+    // all MMAs are complete, so the operand stages are free: reuse them as per-warp transpose
+    // buffers for coalesced stores
+    float* wbuf = reinterpret_cast<float*>(smem) + w * (32 * 33);
+    const int rbase = 32 * (w & 3);
     constexpr int HALF = BN / 2;
     const int cbase = (w >> 2) * HALF;
-    float* yrow = (m < M) ? Y + map(m) * (int64_t)ldy : nullptr;
+    const bool vec_y = ((ldy & 3) == 0) && ((reinterpret_cast<uintptr_t>(Y) & 15) == 0);
 #pragma unroll
     for (int cc = 0; cc < HALF; cc += 32) {
       float v[32];
-      tc::tmem_ld32(tmem_d + ((uint32_t)(32 * (w & 3)) << 16) + (uint32_t)(cbase + cc), v);
-      if (yrow) {
-        const int nb = n0 + cbase + cc;
-        const bool vec_y = ((ldy & 3) == 0) && ((reinterpret_cast<uintptr_t>(Y) & 15) == 0) &&
-                           (nb + 31 < Nout);
+      tc::tmem_ld32(tmem_d + ((uint32_t)rbase << 16) + (uint32_t)(cbase + cc), v);
+      const int nb = n0 + cbase + cc;
+      if (DIST) {
+        const int64_t m = m0 + rbase + lane;
+        const float sm = (m < M) ? s[m] : 0.f;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int n = nb + j;
-          if (n < Nout) {
-            if (DIST) {
-              v[j] = (s[m] + t[n]) - 2.f * v[j];
-            } else {
-              v[j] = apply_act(fmaf(s_sc[cbase + cc + j], v[j], s_sh[cbase + cc + j]), act);
-            }
-          }
-        }
-        if (vec_y) {
+        for (int j = 0; j < 32; ++j) v[j] = (sm + ((nb + j < Nout) ? t[nb + j] : 0.f)) - 2.f * v[j];
+      } else {
 #pragma unroll
-          for (int j = 0; j < 32; j += 4)
-            *reinterpret_cast<float4*>(yrow + nb + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-        } else {
-          for (int j = 0; j < 32; ++j)
-            if (nb + j < Nout) yrow[nb + j] = v[j];
-        }
+        for (int j = 0; j < 32; ++j)
+          v[j] = apply_act(fmaf(s_sc[cbase + cc + j], v[j], s_sh[cbase + cc + j]), act);
       }
+      tc::store_chunk_coalesced(wbuf, v, lane, Nout - nb, vec_y, [&](int r) -> float* {
+        const int64_t m = m0 + rbase + r;
+        return (m < M) ? Y + map(m) * (int64_t)ldy + nb : nullptr;
+      });
     }
   }
   tc::tc_fence_before();

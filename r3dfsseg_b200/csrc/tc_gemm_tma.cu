@@ -1,0 +1,245 @@
+// linear layer on the tensor cores with TMA-fed operands:
+//     Y[map(m)][n] = act(s[n] * sum_k X[m][k] W[n][k] + t[n])
+// Same math as tc_gemm.cu (3xTF32 tcgen05.mma, TMEM accumulator); the difference is the feed:
+//   - one thread issues cp.async.bulk.tensor (TMA) loads of raw FP32 tiles of X and W, 4 k-blocks
+//     ahead, completing on mbarriers — no registers and no thread is blocked on global memory;
+//   - all threads turn a landed raw tile into the TF32 hi / lo UMMA operand tiles (2 stages);
+//   - one thread issues the MMAs; tcgen05.commit releases the operand stage.
+// Out-of-range rows / columns / k are zero-filled by the TMA unit itself.
+#include <cuda.h>
+
+#include "common.cuh"
+#include "tc.cuh"
+
+#define TM_BM 128
+#define TM_BK 16
+#define TM_KC4 (TM_BK / 4)
+#define TM_THREADS 256
+#define TM_RAW_STAGES 2
+
+template <int BN>
+struct TmaSmem {
+  static constexpr int RAW_A = TM_BM * TM_BK * 4;  // 8 KB
+  static constexpr int RAW_B = BN * TM_BK * 4;
+  static constexpr int RAW_STAGE = RAW_A + RAW_B;
+  static constexpr int OP_A = tc::tile_bytes(TM_BM, TM_KC4);
+  static constexpr int OP_B = tc::tile_bytes(BN, TM_KC4);
+  static constexpr int OP_STAGE = 2 * OP_A + 2 * OP_B;
+  static constexpr int RAW_OFF = 0;
+  static constexpr int OP_OFF = TM_RAW_STAGES * RAW_STAGE;
+  static constexpr int TOTAL = OP_OFF + 2 * OP_STAGE + 1024;  // +1024: manual 1 KB alignment
+};
+
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, int c0, int c1,
+                                            uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, "
+      "%3}], [%4];" ::"r"(tc::smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(tc::smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(tc::smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+
+template <int BN>
+__global__ __launch_bounds__(TM_THREADS, 2) void linear_tma_kernel(
+    const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
+    const float* __restrict__ s, const float* __restrict__ t, int act, int64_t M, int K, int Nout,
+    float* __restrict__ Y, int ldy, RowMap map) {
+  extern __shared__ unsigned char smem_raw[];
+  using S = TmaSmem<BN>;
+  unsigned char* smem = reinterpret_cast<unsigned char*>(
+      (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ uint64_t bar_full[TM_RAW_STAGES];
+  __shared__ uint64_t bar_mma[2];
+  __shared__ uint32_t tmem_base_s;
+  __shared__ float s_sc[BN], s_sh[BN];
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int m0 = blockIdx.x * TM_BM;
+  const int n0 = blockIdx.y * BN;
+  constexpr int LBO_A = tc::tile_lbo(TM_BM), LBO_B = tc::tile_lbo(BN);
+  constexpr uint32_t IDESC = tc::make_idesc_tf32(TM_BM, BN);
+  constexpr int A_CH = TM_BM * TM_KC4 / TM_THREADS;  // 2
+  constexpr int B_CH = BN * TM_KC4 / TM_THREADS;     // 2 (BN=128) or 1 (BN=64)
+  const int KB = (K + TM_BK - 1) / TM_BK;
+
+  if (tid < BN) {
+    const int n = n0 + tid;
+    s_sc[tid] = (s && n < Nout) ? s[n] : 1.f;
+    s_sh[tid] = (t && n < Nout) ? t[n] : 0.f;
+  }
+  if (tid == 0) {
+    for (int i = 0; i < TM_RAW_STAGES; ++i) tc::mbar_init(&bar_full[i], 1);
+    tc::mbar_init(&bar_mma[0], 1);
+    tc::mbar_init(&bar_mma[1], 1);
+    tc::mbar_fence_init();
+  }
+  if (w == 0) tc::tmem_alloc(&tmem_base_s, BN);
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_d = tmem_base_s;
+
+  auto issue_tma = [&](int kb) {  // thread 0 only
+    const int rs = kb % TM_RAW_STAGES;
+    unsigned char* ra = smem + S::RAW_OFF + rs * S::RAW_STAGE;
+    mbar_expect_tx(&bar_full[rs], S::RAW_STAGE);
+    tma_load_2d(ra, &tmX, kb * TM_BK, m0, &bar_full[rs]);
+    tma_load_2d(ra + S::RAW_A, &tmW, kb * TM_BK, n0, &bar_full[rs]);
+  };
+  if (tid == 0)
+    for (int kb = 0; kb < min(KB, TM_RAW_STAGES); ++kb) issue_tma(kb);
+
+  for (int kb = 0; kb < KB; ++kb) {
+    const int rs = kb % TM_RAW_STAGES, os = kb & 1;
+    tc::mbar_wait(&bar_full[rs], (kb / TM_RAW_STAGES) & 1);
+    const unsigned char* ra = smem + S::RAW_OFF + rs * S::RAW_STAGE;
+    const unsigned char* rb = ra + S::RAW_A;
+    float4 av[A_CH], bv[B_CH];
+#pragma unroll
+    for (int i = 0; i < A_CH; ++i) {
+      const int c = tid + i * TM_THREADS;  // raw tile is row-major [row][16 floats]
+      av[i] = *reinterpret_cast<const float4*>(ra + c * 16);
+    }
+#pragma unroll
+    for (int i = 0; i < B_CH; ++i) {
+      const int c = tid + i * TM_THREADS;
+      bv[i] = *reinterpret_cast<const float4*>(rb + c * 16);
+    }
+    if (kb >= 2) tc::mbar_wait(&bar_mma[os], ((kb >> 1) - 1) & 1);
+    unsigned char* a_hi = smem + S::OP_OFF + os * S::OP_STAGE;
+    unsigned char* a_lo = a_hi + S::OP_A;
+    unsigned char* b_hi = a_lo + S::OP_A;
+    unsigned char* b_lo = b_hi + S::OP_B;
+#pragma unroll
+    for (int i = 0; i < A_CH; ++i) {
+      const int c = tid + i * TM_THREADS;
+      const int r = c / TM_KC4, kc = c % TM_KC4;
+      float4 hi, lo;
+      tc::split4(av[i], hi, lo);
+      *reinterpret_cast<float4*>(a_hi + kc * LBO_A + r * 16) = hi;
+      *reinterpret_cast<float4*>(a_lo + kc * LBO_A + r * 16) = lo;
+    }
+#pragma unroll
+    for (int i = 0; i < B_CH; ++i) {
+      const int c = tid + i * TM_THREADS;
+      const int r = c / TM_KC4, kc = c % TM_KC4;
+      float4 hi, lo;
+      tc::split4(bv[i], hi, lo);
+      *reinterpret_cast<float4*>(b_hi + kc * LBO_B + r * 16) = hi;
+      *reinterpret_cast<float4*>(b_lo + kc * LBO_B + r * 16) = lo;
+    }
+    tc::fence_async_smem();
+    __syncthreads();  // operand stage complete; raw stage rs fully consumed
+    if (tid == 0) {
+      tc::tc_fence_after();
+      const uint32_t ah = tc::smem_u32(a_hi), al = tc::smem_u32(a_lo);
+      const uint32_t bh = tc::smem_u32(b_hi), bl = tc::smem_u32(b_lo);
+      const int ksteps = min(TM_BK, K - kb * TM_BK + 7) / 8;
+      for (int ks = 0; ks < ksteps; ++ks) {
+        const uint64_t dah = tc::make_desc(ah + ks * 2 * LBO_A, LBO_A, 128);
+        const uint64_t dal = tc::make_desc(al + ks * 2 * LBO_A, LBO_A, 128);
+        const uint64_t dbh = tc::make_desc(bh + ks * 2 * LBO_B, LBO_B, 128);
+        const uint64_t dbl = tc::make_desc(bl + ks * 2 * LBO_B, LBO_B, 128);
+        tc::mma_tf32(tmem_d, dal, dbh, IDESC, (kb | ks) != 0);
+        tc::mma_tf32(tmem_d, dah, dbl, IDESC, 1);
+        tc::mma_tf32(tmem_d, dah, dbh, IDESC, 1);
+      }
+      tc::mma_commit(&bar_mma[os]);
+      if (kb + TM_RAW_STAGES < KB) issue_tma(kb + TM_RAW_STAGES);
+    }
+  }
+  tc::mbar_wait(&bar_mma[(KB - 1) & 1], ((KB - 1) >> 1) & 1);
+  tc::tc_fence_after();
+  {
+    // all MMAs are complete, so the operand stages are free: reuse them as per-warp transpose
+    // buffers for coalesced stores
+    float* wbuf = reinterpret_cast<float*>(smem + S::OP_OFF) + w * (32 * 33);
+    const int rbase = 32 * (w & 3);
+    constexpr int HALF = BN / 2;
+    const int cbase = (w >> 2) * HALF;
+    const bool vec_y = ((ldy & 3) == 0) && ((reinterpret_cast<uintptr_t>(Y) & 15) == 0);
+#pragma unroll
+    for (int cc = 0; cc < HALF; cc += 32) {
+      float v[32];
+      tc::tmem_ld32(tmem_d + ((uint32_t)rbase << 16) + (uint32_t)(cbase + cc), v);
+      const int nb = n0 + cbase + cc;
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        v[j] = apply_act(fmaf(s_sc[cbase + cc + j], v[j], s_sh[cbase + cc + j]), act);
+      tc::store_chunk_coalesced(wbuf, v, lane, Nout - nb, vec_y, [&](int r) -> float* {
+        const int64_t m = (int64_t)m0 + rbase + r;
+        return (m < M) ? Y + map(m) * (int64_t)ldy + nb : nullptr;
+      });
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (w == 0) tc::tmem_dealloc(tmem_d, BN);
+}
+
+// ---- host side: tensor maps through the driver entry point (no link-time libcuda dependency) ----
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      p = nullptr;
+    return (EncodeTiledFn)p;
+  }();
+  return fn;
+}
+
+// 2-D fp32 tensor (rows x K, row stride ld floats), box = 16 (k) x box_rows
+static bool make_map(CUtensorMap* m, const float* base, int64_t rows, int K, int64_t ld,
+                     int box_rows) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return false;
+  cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t box[2] = {TM_BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  return fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+            CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <int BN>
+static int launch_tma_bn(const CUtensorMap& tx, const CUtensorMap& tw, const float* s,
+                         const float* t, int act, int64_t M, int K, int Nout, float* Y, int ldy,
+                         RowMap map, cudaStream_t st) {
+  using S = TmaSmem<BN>;
+  cudaError_t e = cudaFuncSetAttribute(linear_tma_kernel<BN>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
+  if (e != cudaSuccess) return (int)e;
+  dim3 grid((unsigned)((M + TM_BM - 1) / TM_BM), (Nout + BN - 1) / BN);
+  linear_tma_kernel<BN><<<grid, TM_THREADS, S::TOTAL, st>>>(tx, tw, s, t, act, M, K, Nout, Y, ldy,
+                                                            map);
+  R3DFS_CHECK_LAUNCH();
+  return 0;
+}
+
+// returns R3DFS_E_UNSUPPORTED when the operands do not meet TMA's alignment rules (the caller
+// then uses the register-fed kernel of tc_gemm.cu)
+int launch_linear_tma(const float* X, int ldx, const float* W, const float* s, const float* t,
+                      int act, int64_t M, int K, int Nout, float* Y, int ldy, RowMap map,
+                      cudaStream_t st) {
+  if ((ldx & 3) != 0 || (K & 3) != 0 || (reinterpret_cast<uintptr_t>(X) & 15) != 0 ||
+      (reinterpret_cast<uintptr_t>(W) & 15) != 0 || M >= (1ll << 31))
+    return R3DFS_E_UNSUPPORTED;
+  const int bn = (Nout > 64) ? 128 : 64;
+  CUtensorMap tx, tw;
+  if (!make_map(&tx, X, M, K, ldx, TM_BM) || !make_map(&tw, W, Nout, K, K, bn))
+    return R3DFS_E_UNSUPPORTED;
+  if (bn == 128) return launch_tma_bn<128>(tx, tw, s, t, act, M, K, Nout, Y, ldy, map, st);
+  return launch_tma_bn<64>(tx, tw, s, t, act, M, K, Nout, Y, ldy, map, st);
+}
