@@ -538,3 +538,51 @@ def test_episode_evaluator_matches_reference_metric(model):
     assert abs(full["mean_iou"] - O.mean_iou(ref)) < 1e-12 or np.isnan(full["mean_iou"])
     parts = [ev.run(eps, rank=r, world=2)["counters"] for r in range(2)]
     assert torch.equal(parts[0] + parts[1], full["counters"])
+
+
+# ---------------------------------------------------------------------------------------------
+# ragged / unusual episode shapes
+# ---------------------------------------------------------------------------------------------
+def _custom_args(n_way, k_shot, n_pts, n_sub, k_conn):
+    return default_args(n_way, k_shot, pc_npts=n_pts, n_subprototypes=n_sub, k_connect=k_conn)
+
+
+@pytest.mark.parametrize("n_way,k_shot,n_pts,n_sub,k_conn,few_fg", [
+    (3, 2, 1000, 50, 100, False),    # N not a multiple of the 128-row tiles, smaller graph
+    (1, 3, 512, 100, 150, False),    # single way
+    (2, 2, 768, 100, 120, True),     # a way with fewer foreground points than sub-prototypes
+])
+def test_episode_ragged_shapes_vs_oracle(fixture_sd, n_way, k_shot, n_pts, n_sub, k_conn, few_fg):
+    """Whole episodes at shapes the headline config never exercises, against the oracle's graph
+    half on the CUDA features (strict) — including the `n <= k` branch of getMutiplePrototypes
+    where every point is its own prototype (reference models/mpti.py:631-634)."""
+    from r3dfsseg_b200.models import MPTI_SelfAtten
+    args = _custom_args(n_way, k_shot, n_pts, n_sub, k_conn)
+    m = MPTI_SelfAtten(args)
+    m.load_state_dict(fixture_sd)
+    m = m.to(DEV).eval()
+    ep = make_episode(77 + n_way, n_way, k_shot, n_pts=n_pts)
+    sy = ep.support_y.clone()
+    if few_fg:   # way 0: keep only 20 foreground points per shot (40 <= n_sub points in total)
+        for s in range(k_shot):
+            fg = torch.nonzero(sy[0, s]).flatten()
+            sy[0, s, fg[20:]] = 0
+    pred, loss = m(ep.support_x.to(DEV), sy.to(DEV), ep.query_x.to(DEV), ep.query_y.to(DEV),
+                   eval=True)
+    sf = m.getFeatures(ep.support_x.reshape(n_way * k_shot, 9, -1).to(DEV)).cpu()
+    qf = m.getFeatures(ep.query_x.to(DEV)).cpu()
+    with torch.no_grad():
+        ref = O.forward_episode(fixture_sd, ep.support_x, sy, ep.query_x, ep.query_y,
+                                n_subprototypes=n_sub, k_connect=k_conn, eval_mdns=True,
+                                support_feat=sf, query_feat=qf)
+    rp = ref["query_pred"]
+    pred = pred.cpu()
+    assert pred.shape == rp.shape == (n_way, n_way + 1, n_pts)
+    assert m._last_diag["proto_count"][0].cpu().tolist() == ref["proto_count"]
+    if few_fg:
+        assert ref["proto_count"][1] in (20, 40)   # identity branch: one or both shots kept by MDNS
+    assert torch.equal(m._last_diag["clean_flag"][0].cpu(), ref["clean_flag"])
+    err = (pred - rp).abs().max() / rp.abs().max()
+    agree = (pred.argmax(1) == rp.argmax(1)).float().mean()
+    assert err < 1e-3 and agree >= 0.999, (err, agree)
+    assert abs(float(loss) - float(ref["loss"])) < 1e-4
