@@ -5,28 +5,29 @@
 // The (B, 64, N, k) edge activations only ever exist as UMMA operand tiles in shared memory and as
 // accumulators in TMEM.
 //
-// One CTA walks over groups of 32 points.  A 128-row MMA tile = 4 neighbour slots x 32 points
-// (row = slot_in_tile * 32 + point), so TMEM lane quarter q (epilogue warp q) holds neighbour slot
-// 4t + q of tile t for the 32 points, one point per thread: the max over neighbours is a running
-// max in registers across the ceil(k/4) tiles plus one 4-way exchange through shared memory.
-//   warps 4-11: gather P rows, add Q, LeakyReLU, TF32 hi/lo split, store the A tile (2 stages);
-//              one thread issues 3 x 8 tcgen05.mma (3xTF32, K = 64) per tile against the resident
-//              W2 tile and commits to an mbarrier;
-//   warps 0-3: tcgen05.ld the 64 output channels of their row, BN affine + LeakyReLU, running max.
+// One CTA walks over groups of 128 points.  MMA tile t of a group = neighbour slot t of its 128
+// points (row = point), so a TMEM lane always belongs to the same point: the max over neighbours
+// is a running max in the registers of the thread that owns (point, channel half) — no exchange.
+//   warps 8-15: producers.  Each thread owns 8 fixed (row, 16-byte chunk) cells of the A tile; its
+//               Q values stay in registers for the whole group, per tile it gathers P[nbr] (indices
+//               prefetched one tile ahead), adds, LeakyReLU, TF32 hi/lo split, stores (2 stages).
+//               One thread issues 3 x 8 tcgen05.mma (3xTF32, K = 64) against the resident W2 tile
+//               and commits to an mbarrier.
+//   warps 0-7:  epilogue.  tcgen05.ld 32 of the 64 output channels of their row, BN affine +
+//               LeakyReLU, running max; after the last slot the row is written out.
 #include "common.cuh"
 #include "tc.cuh"
 
-#define ET_THREADS 384  // warps 0-3 epilogue, warps 4-11 producers
+#define ET_THREADS 512
 #define ET_PRODUCERS 256
-#define ET_GROUP 32  // points per group
+#define ET_GROUP 128  // points per group (= MMA rows)
 
 struct EdgeTcSmem {
   static constexpr int A_TILE = tc::tile_bytes(128, 16);  // one of hi / lo, K = 64
   static constexpr int W_TILE = tc::tile_bytes(64, 16);
-  static constexpr int A_OFF = 0;                   // 2 stages x (hi, lo)
-  static constexpr int W_OFF = 4 * A_TILE;          // W2 hi, lo
-  static constexpr int X_OFF = W_OFF + 2 * W_TILE;  // exchange [4][64][32] float
-  static constexpr int TOTAL = X_OFF + 4 * 64 * 32 * 4 + 64;
+  static constexpr int A_OFF = 0;           // 2 stages x (hi, lo)
+  static constexpr int W_OFF = 4 * A_TILE;  // W2 hi, lo
+  static constexpr int TOTAL = W_OFF + 2 * W_TILE + 64;
 };
 
 __device__ __forceinline__ void et_mbar_arrive(uint64_t* bar) {
@@ -48,16 +49,15 @@ __global__ __launch_bounds__(ET_THREADS, 1) void edge_tc_kernel(
   const int n_groups = (N + ET_GROUP - 1) / ET_GROUP;
   const int g_begin = blockIdx.x * groups_per_cta;
   const int g_end = min(n_groups, g_begin + groups_per_cta);
-  const int TPG = (k + 3) / 4;  // tiles per group
-  const int U = (g_end - g_begin) * TPG;
+  const int U = (g_end - g_begin) * k;  // one tile per (group, neighbour slot)
   constexpr int LBO_A = tc::tile_lbo(128), LBO_W = tc::tile_lbo(64);
   constexpr uint32_t IDESC = tc::make_idesc_tf32(128, 64);
 
   if (tid == 0) {
     tc::mbar_init(&bar_full[0], 1);
     tc::mbar_init(&bar_full[1], 1);
-    tc::mbar_init(&bar_tfree[0], 128);
-    tc::mbar_init(&bar_tfree[1], 128);
+    tc::mbar_init(&bar_tfree[0], 256);
+    tc::mbar_init(&bar_tfree[1], 256);
     tc::mbar_fence_init();
   }
   if (w == 0) tc::tmem_alloc(&tmem_base_s, 128);
@@ -80,46 +80,47 @@ __global__ __launch_bounds__(ET_THREADS, 1) void edge_tc_kernel(
     return;
   }
 
-  if (w >= 4) {
+  if (w >= 8) {
     // --------------------------- producers + MMA issue --------------------------------------
-    const int lt = tid - 128;
-    constexpr int NCH = 128 * 16 / ET_PRODUCERS;  // float4 chunks per producer thread per tile (8)
-    // neighbour indices are fetched one tile ahead so the gather below never waits on them
+    const int lt = tid - 256;
+    constexpr int NCH = 128 * 16 / ET_PRODUCERS;  // 8 cells per thread: rows (lt>>4) + 16 i
+    const int kc = lt & 15;
+    const int r0 = lt >> 4;
     int nb[NCH];
-    auto load_nb = [&](int u2) {
-      const int g2 = g_begin + u2 / TPG, t2i = u2 % TPG;
+    float4 qv4[NCH];
+    auto load_nb = [&](int u2) {  // neighbour indices of tile u2 (prefetched one tile ahead)
+      const int g2 = g_begin + u2 / k, j = u2 % k;
 #pragma unroll
       for (int i = 0; i < NCH; ++i) {
-        const int r = (lt + i * ET_PRODUCERS) >> 4;
-        const int p = g2 * ET_GROUP + (r & 31), j = 4 * t2i + (r >> 5);
-        nb[i] = (u2 < U && p < N && j < k) ? idx[(base + p) * k + j] : -1;
+        const int p = g2 * ET_GROUP + r0 + 16 * i;
+        nb[i] = (u2 < U && p < N) ? idx[(base + p) * k + j] : -1;
       }
     };
     load_nb(0);
     for (int u = 0; u < U; ++u) {
       const int st = u & 1;
-      const int g = g_begin + u / TPG;
-      const int p0 = g * ET_GROUP;
-      // phase 1: every gather of the tile in flight before anything is consumed
-      float4 hv[NCH], qv4[NCH];
+      const int g = g_begin + u / k;
+      if (u % k == 0) {  // new group: this thread's Q cells stay in registers for all k tiles
+#pragma unroll
+        for (int i = 0; i < NCH; ++i) {
+          const int p = min(g * ET_GROUP + r0 + 16 * i, N - 1);
+          qv4[i] = __ldg(reinterpret_cast<const float4*>(PQ + (base + p) * 128 + 64 + 4 * kc));
+        }
+      }
+      // every gather of the tile in flight before anything is consumed
+      float4 hv[NCH];
+      int live = 0;
 #pragma unroll
       for (int i = 0; i < NCH; ++i) {
-        const int c = lt + i * ET_PRODUCERS;
-        const int r = c >> 4, kc = c & 15;
-        const int p = min(p0 + (r & 31), N - 1);
         const int nbi = nb[i] >= 0 ? nb[i] : 0;
+        live |= (nb[i] >= 0) << i;
         hv[i] = __ldg(reinterpret_cast<const float4*>(PQ + (base + nbi) * 128 + 4 * kc));
-        qv4[i] = __ldg(reinterpret_cast<const float4*>(PQ + (base + p) * 128 + 64 + 4 * kc));
       }
-      int nb_live = 0;
-#pragma unroll
-      for (int i = 0; i < NCH; ++i) nb_live |= (nb[i] >= 0) << i;
       load_nb(u + 1);
-      // phase 2: h1 = LReLU(P_j + Q_i)
 #pragma unroll
       for (int i = 0; i < NCH; ++i) {
         float4 h = make_float4(0.f, 0.f, 0.f, 0.f);
-        if ((nb_live >> i) & 1) {
+        if ((live >> i) & 1) {
           h.x = hv[i].x + qv4[i].x; h.y = hv[i].y + qv4[i].y;
           h.z = hv[i].z + qv4[i].z; h.w = hv[i].w + qv4[i].w;
           h.x = h.x > 0.f ? h.x : 0.2f * h.x;
@@ -134,8 +135,7 @@ __global__ __launch_bounds__(ET_THREADS, 1) void edge_tc_kernel(
       unsigned char* a_lo = a_hi + S::A_TILE;
 #pragma unroll
       for (int i = 0; i < NCH; ++i) {
-        const int c = lt + i * ET_PRODUCERS;
-        const int r = c >> 4, kc = c & 15;
+        const int r = r0 + 16 * i;
         float4 hi, lo;
         tc::split4(hv[i], hi, lo);
         *reinterpret_cast<float4*>(a_hi + kc * LBO_A + r * 16) = hi;
@@ -163,54 +163,42 @@ __global__ __launch_bounds__(ET_THREADS, 1) void edge_tc_kernel(
       }
     }
   } else {
-    // --------------------------- epilogue: thread = (neighbour slot q, point) -----------------
-    float* xch = reinterpret_cast<float*>(smem + S::X_OFF);  // [4][64][32]
-    float mx[64];
+    // --------------------------- epilogue: thread = (point row, channel half) -----------------
+    const int row = 32 * (w & 3) + lane;
+    const int ch0 = 32 * (w >> 2);
+    float sc[32], sh[32], mx[32];
+#pragma unroll
+    for (int c = 0; c < 32; ++c) {
+      sc[c] = __ldg(s2 + ch0 + c);
+      sh[c] = __ldg(t2 + ch0 + c);
+    }
     for (int u = 0; u < U; ++u) {
       const int st = u & 1;
-      const int g = g_begin + u / TPG, t = u % TPG;
-      if (t == 0) {
+      const int g = g_begin + u / k, j = u % k;
+      if (j == 0) {
 #pragma unroll
-        for (int c = 0; c < 64; ++c) mx[c] = -INFINITY;
+        for (int c = 0; c < 32; ++c) mx[c] = -INFINITY;
       }
       tc::mbar_wait(&bar_full[st], (u >> 1) & 1);
       tc::tc_fence_after();
-      const bool live = (4 * t + w) < k;  // warp-uniform
-#pragma unroll
-      for (int cc = 0; cc < 64; cc += 32) {
-        float v[32];
-        tc::tmem_ld32(tmem_d + ((uint32_t)(32 * w) << 16) + (uint32_t)(st * 64 + cc), v);
-        if (live) {
-#pragma unroll
-          for (int e = 0; e < 32; ++e) {
-            float y = fmaf(__ldg(s2 + cc + e), v[e], __ldg(t2 + cc + e));
-            y = y > 0.f ? y : 0.2f * y;
-            mx[cc + e] = fmaxf(mx[cc + e], y);
-          }
-        }
-      }
+      float v[32];
+      tc::tmem_ld32(tmem_d + ((uint32_t)(32 * (w & 3)) << 16) + (uint32_t)(st * 64 + ch0), v);
       tc::tc_fence_before();
       et_mbar_arrive(&bar_tfree[st]);
-      if (t == TPG - 1) {
-        // 4-way max across the neighbour-slot warps, then each thread writes 16 channels of a point
 #pragma unroll
-        for (int c = 0; c < 64; ++c) xch[(w * 64 + c) * 32 + lane] = mx[c];
-        asm volatile("bar.sync 2, 128;" ::: "memory");
-        const int p = g * ET_GROUP + lane;
+      for (int c = 0; c < 32; ++c) {
+        float y = fmaf(sc[c], v[c], sh[c]);
+        y = y > 0.f ? y : 0.2f * y;
+        mx[c] = fmaxf(mx[c], y);
+      }
+      if (j == k - 1) {
+        const int p = g * ET_GROUP + row;
         if (p < N) {
-          float o[16];
+          float* y = Y + map(base + p) * (int64_t)ldy + ch0;
 #pragma unroll
-          for (int c = 0; c < 16; ++c) {
-            const int ch = 16 * w + c;
-            o[c] = fmaxf(fmaxf(xch[(0 * 64 + ch) * 32 + lane], xch[(1 * 64 + ch) * 32 + lane]),
-                         fmaxf(xch[(2 * 64 + ch) * 32 + lane], xch[(3 * 64 + ch) * 32 + lane]));
-          }
-          float* y = Y + map(base + p) * (int64_t)ldy + 16 * w;
-#pragma unroll
-          for (int c = 0; c < 16; c += 4)
-            *reinterpret_cast<float4*>(y + c) = make_float4(o[c], o[c + 1], o[c + 2], o[c + 3]);
+          for (int c = 0; c < 32; c += 4)
+            *reinterpret_cast<float4*>(y + c) = make_float4(mx[c], mx[c + 1], mx[c + 2], mx[c + 3]);
         }
-        asm volatile("bar.sync 2, 128;" ::: "memory");  // exchange buffer free for the next group
       }
     }
   }
@@ -222,15 +210,15 @@ __global__ __launch_bounds__(ET_THREADS, 1) void edge_tc_kernel(
 int launch_edge_mlp_tc(const float* PQ, const int32_t* idx, const float* w2, const float* s2,
                        const float* t2, int64_t B, int N, int k, float* Y, int ldy, RowMap map,
                        cudaStream_t st) {
-  if (k < 1 || k > 32) return R3DFS_E_UNSUPPORTED;
+  if (k < 1 || k > 64) return R3DFS_E_UNSUPPORTED;
   cudaError_t e = cudaFuncSetAttribute(edge_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        EdgeTcSmem::TOTAL);
   if (e != cudaSuccess) return (int)e;
   const int n_groups = (N + ET_GROUP - 1) / ET_GROUP;
-  // enough CTAs to fill the machine a few times over, but several groups per CTA so the W2 tile,
-  // the TMEM allocation and the pipeline prologue are amortised
-  int gpc = 4;
-  while (gpc > 1 && (int64_t)B * ((n_groups + gpc - 1) / gpc) < 2 * 148) gpc >>= 1;
+  // several groups per CTA (W2 tile, TMEM allocation and pipeline prologue amortised) as long as
+  // the grid still fills the machine a few times over
+  int gpc = 2;
+  while (gpc > 1 && (int64_t)B * ((n_groups + gpc - 1) / gpc) < 4 * 148) gpc >>= 1;
   dim3 grid((n_groups + gpc - 1) / gpc, (unsigned)B);
   edge_tc_kernel<<<grid, ET_THREADS, EdgeTcSmem::TOTAL, st>>>(PQ, idx, w2, s2, t2, N, k, gpc, Y,
                                                              ldy, map);
