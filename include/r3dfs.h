@@ -279,6 +279,130 @@ int r3dfs_confusion_accumulate(const int32_t* pred, const int64_t* gt, const int
                                int n_episodes, int n_way, int64_t pts_per_episode, int n_slots,
                                int64_t* counters, r3dfs_stream_t stream);
 
+
+/* ------------------------------------------------------------------------------------------
+ * Meta-training step (reference models/mpti_learner.py:50-79 around
+ * MPTI_SelfAtten.forward(train=True), models/mpti.py:414-577, loss = lp + 0.1 * way-contrast)
+ * ---------------------------------------------------------------------------------------- */
+
+/* Trainable tensors, in the order of the reference's named_parameters(); every tensor keeps the
+ * reference's shape, flattened row-major, and all of them live back to back in ONE flat fp32
+ * buffer (376 896 floats at in_dim = 9) — the same buffer is the gradient bucket NCCL all-reduces
+ * and the range the fused Adam kernel walks.  r3dfs_train_param_layout() gives the offsets. */
+enum r3dfs_param {
+  R3DFS_P_EC0_W1 = 0, /* encoder.edge_convs.0.layer.0.weight (64, 2*in_dim)                     */
+  R3DFS_P_EC0_G1,     /* .layer.1.weight   (BatchNorm gamma)                                    */
+  R3DFS_P_EC0_B1,     /* .layer.1.bias     (BatchNorm beta)                                     */
+  R3DFS_P_EC0_W2,     /* .layer.3.weight (64, 64)                                               */
+  R3DFS_P_EC0_G2,     /* .layer.4.weight                                                        */
+  R3DFS_P_EC0_B2,     /* .layer.4.bias                                                          */
+  /* edge_convs.1 and .2 follow with the same six entries each (W1 is (64, 128))               */
+  R3DFS_P_MLP0_W = 18, /* encoder.conv.layer.0.weight (512, 192)                                */
+  R3DFS_P_MLP0_G, R3DFS_P_MLP0_B,
+  R3DFS_P_MLP1_W,      /* encoder.conv.layer.3.weight (256, 512)                                */
+  R3DFS_P_MLP1_G, R3DFS_P_MLP1_B,
+  R3DFS_P_BL0_W,       /* base_learner.convs.0.0.weight (128, 256)                              */
+  R3DFS_P_BL0_BIAS, R3DFS_P_BL0_G, R3DFS_P_BL0_B,
+  R3DFS_P_BL1_W,       /* base_learner.convs.1.0.weight (64, 128)                               */
+  R3DFS_P_BL1_BIAS, R3DFS_P_BL1_G, R3DFS_P_BL1_B,
+  R3DFS_P_ATT_Q,       /* att_learner.{q,k,v}_map.weight (64, 256) each, contiguous = (192, 256) */
+  R3DFS_P_ATT_K, R3DFS_P_ATT_V,
+  R3DFS_P_PROJ_W,      /* proj.weight (128, 192)                                                */
+  R3DFS_P_PROJ_B,      /* proj.bias (128)                                                       */
+  R3DFS_N_PARAMS
+};
+/* offsets[i] = first float of tensor i, offsets[R3DFS_N_PARAMS] = total; returns the index of
+ * the first non-encoder tensor's offset (the learning-rate group boundary, mpti_learner.py:27). */
+int64_t r3dfs_train_param_layout(int in_dim, int64_t* offsets);
+
+/* BatchNorm layers in forward order: edge_convs.i.layer.{1,4} (i = 0..2), conv.layer.{1,4},
+ * base_learner.convs.{0,1}.1.  Running statistics live in one flat buffer: for layer b with C_b
+ * channels, floats [2*off_b, 2*off_b + C_b) = running_mean, the next C_b = running_var;
+ * offsets[R3DFS_N_BN] = total channels (1344). */
+#define R3DFS_N_BN 10
+void r3dfs_train_bn_layout(int64_t* offsets);
+
+/* Forward of one training episode.  BatchNorm uses batch statistics, separately over the support
+ * clouds and over the query clouds (two getFeatures calls, models/mpti.py:434-436); bn_running
+ * (may be NULL) is updated in place with momentum 0.1 for both.  Attention dropout
+ * (models/attention.py:45): keep_support (n_way*k_shot, N, N) / keep_query (n_query, N, N) are
+ * 0/1 keep masks (r3dfs_dropout_mask), NULL = no dropout; kept entries are scaled 1/(1-dropout_p).
+ * support_flag: (n_way, k_shot) int32 absolute class of each shot (way-contrast labels).
+ * losses[0] = label-propagation cross-entropy, losses[1] = way-contrast loss (fps_k = 4, temp 0.1).
+ * cfg->mdns is ignored (noise suppression is eval-only, models/mpti.py:440).  The workspace keeps
+ * every activation the backward needs: pass the SAME, untouched workspace to
+ * r3dfs_mpti_train_backward. */
+size_t r3dfs_mpti_train_workspace(const r3dfs_episode_cfg_t* h_cfg, int in_dim, int dgcnn_k);
+int r3dfs_mpti_train_forward(const r3dfs_episode_cfg_t* h_cfg, int in_dim, int dgcnn_k,
+                             const float* params, float* bn_running, const float* support_x,
+                             int64_t s_cloud, int64_t s_c, int64_t s_n, const int32_t* support_y,
+                             const int32_t* support_flag, const float* query_x, int64_t q_cloud,
+                             int64_t q_c, int64_t q_n, const int64_t* query_y, float dropout_p,
+                             const uint8_t* keep_support, const uint8_t* keep_query, float* logits,
+                             float* losses, int32_t* cg_iters, void* ws, size_t ws_bytes,
+                             r3dfs_stream_t stream);
+
+/* Backward of w_lp * losses[0] + w_contrast * losses[1] wrt every trainable tensor: grads (flat,
+ * same layout as params) is overwritten.  Gradients flow through the prototype means, the Gaussian
+ * affinities, the degree normalisation and the label-propagation solve (adjoint by the same CG),
+ * not through kNN / FPS / argmin indices — as under autograd in the reference.  The EdgeConv and
+ * affinity gather adjoints use float atomics: results are reproducible to rounding, not bitwise. */
+int r3dfs_mpti_train_backward(const r3dfs_episode_cfg_t* h_cfg, int in_dim, int dgcnn_k,
+                              const float* params, const int32_t* support_y,
+                              const int32_t* support_flag, const int64_t* query_y, float dropout_p,
+                              const uint8_t* keep_support, const uint8_t* keep_query, float w_lp,
+                              float w_contrast, float* grads, void* ws, size_t ws_bytes,
+                              r3dfs_stream_t stream);
+
+/* Diagnostics for the parity tests: copies the discrete decisions of the last
+ * r3dfs_mpti_train_forward out of its workspace, so that a reference implementation can be run
+ * with the same neighbour lists / cluster assignments (they carry no gradient, but FP32 ties in
+ * them make an end-to-end comparison chaotic).  Every pointer is a device buffer or NULL (skipped):
+ *   knn_support[i] (n_way*k_shot*N*dgcnn_k) / knn_query[i] (n_query*N*dgcnn_k): EdgeConv i neighbours,
+ *       cloud-local indices;
+ *   set_off / set_n / proto_cnt (n_way+1): rows of the compacted support buffer holding the
+ *       background set (0) and each way's foreground set (1+w), and their prototype counts;
+ *   assign (n_way*k_shot*N): prototype of every compacted row (local index within its set);
+ *   cloud_fg_off / fg_cnt / cproto_cnt (n_way*k_shot): each shot's foreground rows and the number
+ *       of way-contrast prototypes;  cassign: as assign, for the way-contrast prototypes;
+ *   nbr (nn * k_connect), valid (nn): affinity neighbours in node-slot numbering, with
+ *       nn = roundup64((n_way+1)*(n_subprototypes+1)) + n_query*N; prototype p of set s is node
+ *       s*(n_subprototypes+1) + p, query point q is node nn - n_query*N + q. */
+typedef struct r3dfs_train_export {
+  int32_t* knn_support[3];
+  int32_t* knn_query[3];
+  int32_t* set_off;
+  int32_t* set_n;
+  int32_t* proto_cnt;
+  int32_t* assign;
+  int32_t* cloud_fg_off;
+  int32_t* fg_cnt;
+  int32_t* cproto_cnt;
+  int32_t* cassign;
+  int32_t* nbr;
+  uint8_t* valid;
+} r3dfs_train_export_t;
+int r3dfs_mpti_train_export(const r3dfs_episode_cfg_t* h_cfg, int in_dim, int dgcnn_k,
+                            const r3dfs_train_export_t* h_out, void* ws, size_t ws_bytes,
+                            r3dfs_stream_t stream);
+
+/* torch.optim.Adam step (defaults of models/mpti_learner.py:26-32) over the flat buffers:
+ * floats [0, n_group0) use lr0 (encoder, 1e-4), the rest lr1 (args.lr); step = 1, 2, ...;
+ * grad_scale multiplies the gradient first (1 / world_size after a sum all-reduce). */
+int r3dfs_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
+                    int64_t n_group0, float lr0, float lr1, float beta1, float beta2, float eps,
+                    int64_t step, float grad_scale, r3dfs_stream_t stream);
+
+/* Counter-based dropout keep mask: mask[i] = 1 iff u(seed, i) >= p. */
+int r3dfs_dropout_mask(uint64_t seed, int64_t n, float p, uint8_t* mask, r3dfs_stream_t stream);
+
+/* C (M, N; rows ldc apart) = alpha * A * B + beta * C in FP32 with element strides
+ * A(m, k) = A[m*sAm + k*sAk], B(k, n) = B[k*sBk + n*sBn] — the gradient GEMM of the training path,
+ * exposed for its parity test.  ws: sgemm scratch of at least ws_bytes (split-K partials). */
+int r3dfs_sgemm(const float* A, int64_t sAm, int64_t sAk, const float* B, int64_t sBk, int64_t sBn,
+                float* C, int64_t ldc, int64_t M, int64_t N, int64_t K, float alpha, float beta,
+                void* ws, size_t ws_bytes, r3dfs_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -45,6 +45,15 @@ class EpisodeDiag(C.Structure):
                 ("h_stage_events", C.POINTER(C.c_void_p))]
 
 
+class TrainExport(C.Structure):
+    """r3dfs_train_export_t"""
+    _fields_ = [("knn_support", C.c_void_p * 3), ("knn_query", C.c_void_p * 3),
+                ("set_off", C.c_void_p), ("set_n", C.c_void_p), ("proto_cnt", C.c_void_p),
+                ("assign", C.c_void_p), ("cloud_fg_off", C.c_void_p), ("fg_cnt", C.c_void_p),
+                ("cproto_cnt", C.c_void_p), ("cassign", C.c_void_p), ("nbr", C.c_void_p),
+                ("valid", C.c_void_p)]
+
+
 STAGES = ["begin", "input", "knn0", "pq0", "edge0", "knn1", "pq1", "edge1", "knn2", "pq2", "edge2",
           "mlp", "base", "qkv", "att", "mdns", "sets", "fps", "proto", "dist", "select", "sim",
           "sym", "cg", "head"]
@@ -89,7 +98,26 @@ SIGNATURES = {
                                               vp, vp, vp, vp, vp, vp, C.POINTER(EpisodeDiag), vp,
                                               sz, vp]),
     "r3dfs_confusion_accumulate": (C.c_int, [vp, vp, vp, i32, i32, i64, i32, vp, vp]),
+    # meta-training step
+    "r3dfs_train_param_layout": (i64, [i32, C.POINTER(i64)]),
+    "r3dfs_train_bn_layout": (None, [C.POINTER(i64)]),
+    "r3dfs_mpti_train_workspace": (sz, [C.POINTER(EpisodeCfg), i32, i32]),
+    "r3dfs_mpti_train_forward": (C.c_int, [C.POINTER(EpisodeCfg), i32, i32, vp, vp,
+                                           vp, i64, i64, i64, vp, vp,
+                                           vp, i64, i64, i64, vp,
+                                           f32, vp, vp, vp, vp, vp, vp, sz, vp]),
+    "r3dfs_mpti_train_backward": (C.c_int, [C.POINTER(EpisodeCfg), i32, i32, vp, vp, vp, vp,
+                                            f32, vp, vp, f32, f32, vp, vp, sz, vp]),
+    "r3dfs_mpti_train_export": (C.c_int, [C.POINTER(EpisodeCfg), i32, i32, C.POINTER(TrainExport), vp,
+                                          sz, vp]),
+    "r3dfs_adam_step": (C.c_int, [vp, vp, vp, vp, i64, i64, f32, f32, f32, f32, f32, i64, f32, vp]),
+    "r3dfs_dropout_mask": (C.c_int, [C.c_uint64, i64, f32, vp, vp]),
+    "r3dfs_sgemm": (C.c_int, [vp, i64, i64, vp, i64, i64, vp, i64, i64, i64, i64, f32, f32, vp, sz,
+                              vp]),
 }
+
+N_PARAMS = 37
+N_BN = 10
 
 _lib = None
 

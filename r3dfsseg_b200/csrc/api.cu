@@ -6,6 +6,7 @@
 #include "common.cuh"
 #include "lp.cuh"
 #include "proto.cuh"
+#include "episode.cuh"
 
 // ---------------------------------------------------------------------------------------------
 // small glue kernels
@@ -116,21 +117,7 @@ static inline unsigned nblk(int64_t n, int t = 256) { return (unsigned)((n + t -
 // ---------------------------------------------------------------------------------------------
 // encoder (getFeatures): DGCNN + BaseLearner + SelfAttention
 // ---------------------------------------------------------------------------------------------
-struct EncoderWs {
-  float* xx;
-  int32_t* idx;
-  float* wpq;
-  float* spq;
-  float* tpq;
-  float* PQ;
-  float* ecat;
-  float* h512;
-  float* l2;
-  float* h128;
-  float* qkv;
-};
-
-static void carve_encoder(WsBump& ws, int64_t M, int k, EncoderWs& e) {
+void carve_encoder(WsBump& ws, int64_t M, int k, EncoderWs& e) {
   e.xx = ws.take<float>(M);
   e.idx = ws.take<int32_t>(M * k);
   e.wpq = ws.take<float>(128 * 64);
@@ -144,7 +131,7 @@ static void carve_encoder(WsBump& ws, int64_t M, int k, EncoderWs& e) {
   e.qkv = ws.take<float>(M * 192);
 }
 
-static int check_weights(const r3dfs_weights_t* w) {
+int check_weights(const r3dfs_weights_t* w) {
   if (!w) return R3DFS_E_BADARG;
   if (w->in_dim < 1 || w->in_dim > 64 || w->dgcnn_k < 1 || w->dgcnn_k > 32)
     return R3DFS_E_UNSUPPORTED;
@@ -160,9 +147,9 @@ static int check_weights(const r3dfs_weights_t* w) {
 }
 
 // xp: (B*N, in_dim) point-major.  F: feature rows (ld 192) addressed through `map`.
-static int encoder_forward(const r3dfs_weights_t* w, const float* xp, int64_t B, int N,
+int encoder_forward(const r3dfs_weights_t* w, const float* xp, int64_t B, int N,
                            const EncoderWs& e, float* F, RowMap map, float* level2,
-                           cudaStream_t st, const StageRec* sr = nullptr) {
+                           cudaStream_t st, const StageRec* sr) {
   const int64_t M = B * N;
   const int k = w->dgcnn_k;
   for (int i = 0; i < 3; ++i) {
@@ -493,12 +480,9 @@ int r3dfs_confusion_accumulate(const int32_t* pred, const int64_t* gt, const int
 }
 
 // ---- whole episodes ---------------------------------------------------------------------------------
-struct EpisodeDims {
-  int S, slot, ppad, nq_pts, nn, ns_pts, cpe, C, nc;
-  int64_t ep_rows;
-};
+}  // extern "C"
 
-static int episode_dims(const r3dfs_episode_cfg_t* c, EpisodeDims& d) {
+int episode_dims(const r3dfs_episode_cfg_t* c, EpisodeDims& d) {
   if (!c) return R3DFS_E_BADARG;
   if (c->n_way < 1 || c->n_way > 7 || c->k_shot < 1 || c->k_shot > 32 || c->n_query < 1 ||
       c->n_points < 64 || c->n_subprototypes < 1 || c->n_subprototypes > 127 || c->k_connect < 1 ||
@@ -518,28 +502,7 @@ static int episode_dims(const r3dfs_episode_cfg_t* c, EpisodeDims& d) {
   return 0;
 }
 
-struct EpisodeWs {
-  float* xp;
-  EncoderWs enc;
-  float* F;
-  int32_t *fg_cnt, *keep, *set_off, *set_n, *cloud_bg_off, *cloud_fg_off;
-  float* setfeat;
-  int32_t *picks, *pick_cnt, *seeds, *proto_cnt, *assign, *pcount;
-  float *partial, *seed_stats;
-  float* cell_mean;
-  int32_t* cell_cnt;
-  uint8_t* valid;
-  float *Y, *norms, *D2;
-  int32_t* nbr;
-  float* sim;
-  int32_t *in_cnt, *in_ptr, *in_src;
-  float *in_w, *dinv, *Z, *X, *R, *P, *AP;
-  int32_t *rowptr, *rowlen, *cursor;
-  uint16_t* mcol;
-  float* mval;
-};
-
-static void carve_episode(WsBump& ws, const r3dfs_episode_cfg_t* c, const EpisodeDims& d, int E,
+void carve_episode(WsBump& ws, const r3dfs_episode_cfg_t* c, const EpisodeDims& d, int E,
                           int in_dim, int dg_k, EpisodeWs& w) {
   const int64_t M = (int64_t)E * d.cpe * c->n_points;
   const size_t G = E, nn = d.nn, k = c->k_connect;
@@ -600,7 +563,7 @@ size_t r3dfs_mpti_workspace(const r3dfs_episode_cfg_t* cfg, int n_episodes) {
 
 // graph half of the episode: F already holds the query + support features (rows ppad.. of every
 // episode block); everything after getFeatures in models/mpti.py:440-571.
-static int episode_graph_half(const r3dfs_episode_cfg_t* cfg, const EpisodeDims& d, int E,
+int episode_graph_half(const r3dfs_episode_cfg_t* cfg, const EpisodeDims& d, int E,
                               const EpisodeWs& w, const float* support_x, int64_t s_e,
                               int64_t s_cloud, int64_t s_c, int64_t s_n, const int32_t* support_y,
                               const int64_t* query_y, float* logits, float* loss, int32_t* pred,
@@ -654,6 +617,8 @@ static int episode_graph_half(const r3dfs_episode_cfg_t* cfg, const EpisodeDims&
   }
   return 0;
 }
+
+extern "C" {
 
 int r3dfs_mpti_forward(const r3dfs_episode_cfg_t* cfg, const r3dfs_weights_t* hw, int E,
                        const float* support_x, int64_t s_e, int64_t s_cloud, int64_t s_c,

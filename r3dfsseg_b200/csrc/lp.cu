@@ -859,6 +859,30 @@ int launch_affinity(const float* F, int64_t graph_rows, int64_t row_off, const u
   return 0;
 }
 
+// (I - alpha S) X = RHS on merged rows that are already built and normalised (the label-propagation
+// solve itself, and its adjoint in the training backward: S is symmetric).
+int launch_lp_solve(const int32_t* rowptr, const int32_t* rowlen, const uint16_t* mcol,
+                    const float* mval, const uint8_t* valid, int G, int nn, int k, const float* Y,
+                    int nc, float alpha, float tol, int max_iter, float* Z, float* X, float* R,
+                    float* P, float* AP, int32_t* iters_out, float* resid_out, cudaStream_t st) {
+  if (nc > CG_MAXC || nc < 1 || nn > 8192) return R3DFS_E_UNSUPPORTED;
+  // padded vector width: one or two float4 per node
+  const int ncv = nc <= 4 ? 4 : 8;
+  const size_t smem_cg = sizeof(float) * (size_t)nn * ncv;
+  if (smem_cg > 200 * 1024) return R3DFS_E_UNSUPPORTED;
+  int rc = -1000;
+  for (int CL = 16; CL >= 8 && rc == -1000; CL >>= 1) {
+    if (ncv == 4)
+      rc = launch_cg<4>(CL, G, smem_cg, st, rowptr, rowlen, mcol, mval, valid, nn, k, Y, nc, alpha,
+                        tol, max_iter, Z, X, R, P, AP, iters_out, resid_out);
+    else
+      rc = launch_cg<8>(CL, G, smem_cg, st, rowptr, rowlen, mcol, mval, valid, nn, k, Y, nc, alpha,
+                        tol, max_iter, Z, X, R, P, AP, iters_out, resid_out);
+  }
+  if (rc != 0) return rc == -1000 ? R3DFS_E_UNSUPPORTED : rc;
+  return 0;
+}
+
 int launch_label_propagate(const int32_t* nbr, float* sim, const uint8_t* valid, int G, int nn,
                            int k, const float* Y, int nc, float alpha, float tol, int max_iter,
                            int32_t* in_cnt, int32_t* in_ptr, int32_t* in_src, float* in_w,
@@ -899,20 +923,8 @@ int launch_label_propagate(const int32_t* nbr, float* sim, const uint8_t* valid,
   R3DFS_CHECK_LAUNCH();
   if (sr) sr->mark(R3DFS_ST_SYM, st);
 
-  // padded vector width: one or two float4 per node
-  const int ncv = nc <= 4 ? 4 : 8;
-  const size_t smem_cg = sizeof(float) * (size_t)nn * ncv;
-  if (smem_cg > 200 * 1024) return R3DFS_E_UNSUPPORTED;
-  int rc = -1000;
-  for (int CL = 16; CL >= 8 && rc == -1000; CL >>= 1) {
-    if (ncv == 4)
-      rc = launch_cg<4>(CL, G, smem_cg, st, rowptr, rowlen, mcol, mval, valid, nn, k, Y, nc, alpha,
-                        tol, max_iter, Z, X, R, P, AP, iters_out, resid_out);
-    else
-      rc = launch_cg<8>(CL, G, smem_cg, st, rowptr, rowlen, mcol, mval, valid, nn, k, Y, nc, alpha,
-                        tol, max_iter, Z, X, R, P, AP, iters_out, resid_out);
-  }
-  if (rc != 0) return rc == -1000 ? R3DFS_E_UNSUPPORTED : rc;
+  R3DFS_TRY(launch_lp_solve(rowptr, rowlen, mcol, mval, valid, G, nn, k, Y, nc, alpha, tol, max_iter,
+                            Z, X, R, P, AP, iters_out, resid_out, st));
   if (sr) sr->mark(R3DFS_ST_CG, st);
   return 0;
 }

@@ -73,6 +73,9 @@ class MPTI_SelfAtten(nn.Module):
         self._packed = None
         self._packed_sig = None
         self._last_diag = None
+        self._flat_state = None       # training: parameters as views of one flat buffer
+        self._train_ws = None
+        self._train_step = 0
 
     # ---------------------------------------------------------------------------------------
     def _weights(self) -> ops.PackedWeights:
@@ -113,12 +116,38 @@ class MPTI_SelfAtten(nn.Module):
                 train=False, logger=None, step=None, path=None, sampled_classes=None,
                 bg_pcd_x=None, bg_pcd_y=None, support_c=None, support_flag=None, pcd_1024=None,
                 label_1024=None, pcd_cutout=None, label_cutout=None, eval=False):
-        """Same contract as reference models/mpti.py:414-577 for train=False:
-        returns (query_pred (n_query, n_way+1, N), lp_loss)."""
-        if train or self.training:
-            raise NotImplementedError(
-                "r3dfsseg_b200: the meta-training forward/backward (way-contrast loss, batch-stat "
-                "BN, LP adjoint) is not built yet; there is deliberately no PyTorch fallback")
+        """Same contract as reference models/mpti.py:414-577.
+        train=False: returns (query_pred (n_query, n_way+1, N), lp_loss).
+        train=True (module in .train() mode): returns the reference's 7-tuple (query_pred, lp_loss,
+        contrast_loss, query_acc_LP, query_acc_original, clean_ratio_LP_avg,
+        clean_ratio_original_avg); lp_loss / contrast_loss carry gradients to the parameters through
+        r3dfs_mpti_train_backward.  The two clean-ratio entries are logging-only diagnostics in the
+        reference (:520-546); clean_ratio_original is computed, clean_ratio_LP is reported as NaN."""
+        if train:
+            if not self.training:
+                raise RuntimeError("forward(train=True) needs the module in .train() mode "
+                                   "(reference models/mpti_learner.py:61)")
+            if support_flag is None:
+                raise ValueError("forward(train=True) needs support_flag (way-contrast labels)")
+            from ..train import train_episode
+            query_pred, lp_loss, contrast = train_episode(self, support_x, support_y, query_x,
+                                                          query_y, support_flag)
+            with torch.no_grad():
+                pl = query_pred.argmax(1)
+                gq = gt_query_y if gt_query_y is not None else query_y
+                denom = float(self.n_way * self.n_points)
+                acc_lp = (pl == gq).sum().float() / denom
+                acc_orig = (query_y == gq).sum().float() / denom
+                ratio_orig = torch.zeros((), device=query_pred.device)
+                if gt_support_y is not None:
+                    for w in range(self.n_way):
+                        given = support_y[w].reshape(-1) == 1
+                        ratio_orig += (gt_support_y[w].reshape(-1)[given] == 1).float().mean()
+                    ratio_orig /= self.n_way
+                ratio_lp = torch.full((), float("nan"), device=query_pred.device)
+            return query_pred, lp_loss, contrast, acc_lp, acc_orig, ratio_lp, ratio_orig
+        if self.training:
+            raise RuntimeError("call forward(..., train=True) in training mode, or .eval() first")
         sx = support_x.reshape(self.n_way, self.k_shot, self.in_channels, self.n_points) \
             if support_x.dim() != 4 else support_x
         out = self.forward_episodes(sx.unsqueeze(0), support_y.unsqueeze(0), query_x.unsqueeze(0),
