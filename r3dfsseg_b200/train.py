@@ -268,6 +268,17 @@ def export_decisions(model) -> Dict[str, object]:
     return out
 
 
+def all_reduce_gradients(flat_grad: torch.Tensor) -> float:
+    """Data-parallel episodes (one per rank): sum-all-reduce the ONE flat gradient bucket in place
+    (NCCL over NVLink on GPUs) and return the factor that turns the sum into the mean — the Adam
+    kernel applies it, so no separate scaling pass runs.  1.0 when not distributed."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(flat_grad, op=dist.ReduceOp.SUM)
+        return 1.0 / dist.get_world_size()
+    return 1.0
+
+
 class FusedAdam(torch.optim.Optimizer):
     """torch.optim.Adam as configured at reference models/mpti_learner.py:26-32 (encoder lr 1e-4,
     everything else args.lr; betas (0.9, 0.999), eps 1e-8, no weight decay) as one kernel over the
@@ -301,11 +312,7 @@ class FusedAdam(torch.optim.Optimizer):
         if self.exp_avg.data_ptr() == 0 or self.exp_avg.numel() != fs.flat.numel():
             raise RuntimeError("optimizer state does not match the model")
         g = self._flat_grad(fs)
-        scale = 1.0
-        import torch.distributed as dist
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-            dist.all_reduce(g, op=dist.ReduceOp.SUM)  # NCCL over NVLink: one 1.5 MB bucket
-            scale = 1.0 / dist.get_world_size()
+        scale = all_reduce_gradients(g)
         self.step_count += 1
         self.model._packed = None  # folded eval weights are stale after the update
         b1, b2 = self.defaults["betas"]

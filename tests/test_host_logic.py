@@ -149,3 +149,49 @@ def test_synthetic_episode_contract():
     assert (noisy == 2).all()                                      # round(5 * 0.4) OOD shots per way
     again = make_episode(3, 3, 5, dataset="scannet", noise_ratio=0.4)
     assert torch.equal(ep.support_x, again.support_x)
+
+
+def test_train_parameter_layout_matches_reference_order(fixture_sd):
+    """The flat parameter buffer of the training path = the reference's named_parameters() order and
+    sizes (376 896 floats, encoder/rest learning-rate split at 261 504: models/mpti_learner.py:26-32)."""
+    from r3dfsseg_b200 import train as T
+    off, group0 = T.param_layout(9)
+    names = [k for k in fixture_sd if not (k.endswith("running_mean") or k.endswith("running_var")
+                                           or k.endswith("num_batches_tracked"))]
+    assert names == T.PARAM_NAMES
+    assert [off[i + 1] - off[i] for i in range(len(names))] == [fixture_sd[k].numel() for k in names]
+    assert off[-1] == 376896 and group0 == 261504
+    assert all(o % 4 == 0 for o in off)           # every tensor 16-byte aligned in the bucket
+    bn = T.bn_layout()
+    chans = [fixture_sd[p + ".running_mean"].numel() for p in T.BN_PREFIXES]
+    assert [bn[i + 1] - bn[i] for i in range(len(chans))] == chans and bn[-1] == 1344
+
+
+def _gloo_grad_worker(rank, world, port, q):
+    import torch.distributed as dist
+    from r3dfsseg_b200.train import all_reduce_gradients
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    g = torch.Generator().manual_seed(5)
+    per_rank = [torch.randn(376896, generator=g) for _ in range(world)]
+    bucket = per_rank[rank].clone()
+    scale = all_reduce_gradients(bucket)
+    mean = torch.stack(per_rank).sum(0) / world
+    q.put((rank, bool(torch.allclose(bucket * scale, mean, atol=1e-6)) and scale == 1.0 / world))
+    dist.destroy_process_group()
+
+
+def test_gradient_bucket_allreduce_gloo_world2():
+    """Meta-training N>1 path on CPU: one flat bucket, sum all-reduce, mean folded into the scale."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_gloo_grad_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(results) == [(0, True), (1, True)]

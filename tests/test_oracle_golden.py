@@ -57,3 +57,33 @@ def test_episode_matches_reference(golden_episodes, fixture_sd, name):
     agree = (out["query_pred"].argmax(1) == ref.argmax(1)).float().mean()
     assert agree >= 0.999, agree
     assert abs(float(out["loss"]) - float(c["loss"])) < 1e-4
+
+
+def test_train_oracle_vs_reference_golden(fixture_sd):
+    """oracle/mpti_train_oracle.py (training forward + autograd) against the numbers the REFERENCE's
+    own forward(train=True) + backward produced (oracle/make_golden_train.py)."""
+    import os
+    from oracle import mpti_train_oracle as TO
+    torch.set_num_threads(os.cpu_count())
+    gold = torch.load(os.path.join(os.path.dirname(__file__), "golden", "golden_train.pt"))
+    name = "train_s3dis_2way_5shot_clean"
+    g = gold[name]
+    ep = make_episode(g["seed"], g["n_way"], g["k_shot"], dataset=g["dataset"],
+                      noise_ratio=g["noise_ratio"])
+    P, running = TO.split_state_dict(fixture_sd)
+    out = TO.forward_train(P, ep.support_x, ep.support_y, ep.query_x, ep.query_y, ep.support_flag,
+                           running=running)
+    (out["lp_loss"] + 0.1 * out["contrast_loss"]).backward()
+    assert abs(float(out["lp_loss"]) - float(g["lp_loss"])) < 1e-5
+    assert abs(float(out["contrast_loss"]) - float(g["contrast_loss"])) < 1e-5
+    for k, p in P.items():
+        if k.endswith("0.bias") and k.startswith("base_learner"):
+            continue  # exactly-zero gradient (bias ahead of batch-stat BN): rounding noise only
+        s = p.grad.reshape(-1)[::29]
+        ref = g["grad_sample"][k]
+        assert float((s - ref).abs().max()) <= 2e-5 * float(ref.abs().max()) + 1e-9, k
+    for k, v in running.items():
+        if v.dtype.is_floating_point:
+            assert float((v - g["running"][k]).abs().max()) < 1e-5, k
+        else:
+            assert int(v) == int(g["running"][k])
