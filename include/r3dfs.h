@@ -9,7 +9,8 @@
  *   - all work is enqueued on `stream`; no call synchronises the device;
  *   - return 0 on success, a negative R3DFS_E_* for bad arguments, a positive value =
  *     (int)cudaError_t when a launch failed.  Nothing throws or aborts;
- *   - results are bit-reproducible run to run (no floating-point atomics);
+ *   - results are bit-reproducible run to run (no floating-point atomics); the one exception is
+ *     r3dfs_mpti_train_backward (two gather adjoints use float atomics, stated there);
  *   - "point-major" = a cloud stored as N rows of C contiguous floats.  The reference's collate
  *     (dataloaders/loader.py:1662-1684) hands over exactly this memory behind a transposed
  *     (B, C, N) view, so strided (B, C, N) inputs are accepted everywhere a cloud comes in.

@@ -215,16 +215,41 @@ static inline void col_reduce_grid(int64_t rows, int C, dim3& grid, int64_t& rpb
   grid = dim3(C / 64, (unsigned)nb);
 }
 
-__global__ void bn_stats_finish_kernel(const double* __restrict__ partial, int nb, int C,
+// Sums the per-row-block partials of one channel: 16 slices of blocks per channel (64 channels x 16
+// slices = 1024 threads), slices combined in slice order -> deterministic.  Returns the totals to
+// the slice-0 thread of every channel (other threads get zeros and `lead` = false).
+__device__ __forceinline__ void finish_partials(const double* __restrict__ partial, int nb, int C,
+                                                int c, double& s, double& q, bool& lead) {
+  __shared__ double f0[1024], f1[1024];
+  const int tid = threadIdx.x, sl = tid >> 6;
+  const int per = (nb + 15) / 16;
+  const int b0 = sl * per, b1 = min(nb, b0 + per);
+  double a0 = 0.0, a1 = 0.0;
+  for (int b = b0; b < b1; ++b) {
+    a0 += partial[((int64_t)b * 2) * C + c];
+    a1 += partial[((int64_t)b * 2 + 1) * C + c];
+  }
+  f0[tid] = a0;
+  f1[tid] = a1;
+  __syncthreads();
+  lead = sl == 0;
+  s = q = 0.0;
+  if (lead) {
+    for (int t = 0; t < 16; ++t) {
+      s += f0[tid + 64 * t];
+      q += f1[tid + 64 * t];
+    }
+  }
+}
+
+__global__ __launch_bounds__(1024) void bn_stats_finish_kernel(const double* __restrict__ partial, int nb, int C,
                                        int64_t rows, float eps, float momentum,
                                        float* __restrict__ running, float* __restrict__ stats) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  double s = 0.0, q = 0.0;
-  for (int b = 0; b < nb; ++b) {
-    s += partial[((int64_t)b * 2) * C + c];
-    q += partial[((int64_t)b * 2 + 1) * C + c];
-  }
+  const int c = blockIdx.x * 64 + (threadIdx.x & 63);
+  double s, q;
+  bool lead;
+  finish_partials(partial, nb, C, c, s, q, lead);
+  if (!lead) return;
   const double mean = s / (double)rows;
   double var = q / (double)rows - mean * mean;
   if (var < 0.0) var = 0.0;
@@ -246,7 +271,7 @@ int launch_bn_stats(const float* x, int64_t ldx, int64_t rows, int C, float eps,
   col_reduce_kernel<0><<<grid, 256, 0, st>>>(x, ldx, nullptr, 0, rows, C, rpb, nullptr, nullptr,
                                             nullptr, 0, scratch);
   R3DFS_CHECK_LAUNCH();
-  bn_stats_finish_kernel<<<(C + 127) / 128, 128, 0, st>>>(scratch, (int)grid.y, C, rows, eps,
+  bn_stats_finish_kernel<<<C / 64, 1024, 0, st>>>(scratch, (int)grid.y, C, rows, eps,
                                                          momentum, running, stats);
   R3DFS_CHECK_LAUNCH();
   return 0;
@@ -283,16 +308,14 @@ int launch_bn_act(const float* x, int64_t ldx, int64_t rows, int C, const float*
 }
 
 // sums -> coefficients (sum dz / rows, sum dz xhat / rows) in coef[2C]; dgamma += , dbeta +=
-__global__ void bn_bwd_finish_kernel(const double* __restrict__ partial, int nb, int C, int64_t rows,
-                                     float* __restrict__ coef, float* __restrict__ dgamma,
-                                     float* __restrict__ dbeta) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  double s = 0.0, q = 0.0;
-  for (int b = 0; b < nb; ++b) {
-    s += partial[((int64_t)b * 2) * C + c];
-    q += partial[((int64_t)b * 2 + 1) * C + c];
-  }
+__global__ __launch_bounds__(1024) void bn_bwd_finish_kernel(
+    const double* __restrict__ partial, int nb, int C, int64_t rows, float* __restrict__ coef,
+    float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  const int c = blockIdx.x * 64 + (threadIdx.x & 63);
+  double s, q;
+  bool lead;
+  finish_partials(partial, nb, C, c, s, q, lead);
+  if (!lead) return;
   coef[c] = (float)(s / (double)rows);
   coef[C + c] = (float)(q / (double)rows);
   if (dbeta) dbeta[c] += (float)s;
@@ -337,7 +360,7 @@ int launch_bn_act_bwd(const float* dy, int64_t ld_dy, const float* x, int64_t ld
                                             act, scratch);
   R3DFS_CHECK_LAUNCH();
   float* coef = reinterpret_cast<float*>(scratch + (size_t)2 * 512 * BN_MAX_BLOCKS);
-  bn_bwd_finish_kernel<<<(C + 127) / 128, 128, 0, st>>>(scratch, (int)grid.y, C, rows, coef, dgamma,
+  bn_bwd_finish_kernel<<<C / 64, 1024, 0, st>>>(scratch, (int)grid.y, C, rows, coef, dgamma,
                                                        dbeta);
   R3DFS_CHECK_LAUNCH();
   const int64_t total = rows * (C >> 2);
@@ -347,13 +370,13 @@ int launch_bn_act_bwd(const float* dy, int64_t ld_dy, const float* x, int64_t ld
   return 0;
 }
 
-__global__ void col_sum_finish_kernel(const double* __restrict__ partial, int nb, int C,
-                                      float* __restrict__ out) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  double s = 0.0;
-  for (int b = 0; b < nb; ++b) s += partial[((int64_t)b * 2) * C + c];
-  out[c] += (float)s;
+__global__ __launch_bounds__(1024) void col_sum_finish_kernel(const double* __restrict__ partial,
+                                                              int nb, int C, float* __restrict__ out) {
+  const int c = blockIdx.x * 64 + (threadIdx.x & 63);
+  double s, q;
+  bool lead;
+  finish_partials(partial, nb, C, c, s, q, lead);
+  if (lead) out[c] += (float)s;
 }
 
 int launch_col_sum_acc(const float* x, int64_t ldx, int64_t rows, int C, float* out, double* scratch,
@@ -365,7 +388,7 @@ int launch_col_sum_acc(const float* x, int64_t ldx, int64_t rows, int C, float* 
   col_reduce_kernel<2><<<grid, 256, 0, st>>>(x, ldx, nullptr, 0, rows, C, rpb, nullptr, nullptr,
                                             nullptr, 0, scratch);
   R3DFS_CHECK_LAUNCH();
-  col_sum_finish_kernel<<<(C + 127) / 128, 128, 0, st>>>(scratch, (int)grid.y, C, out);
+  col_sum_finish_kernel<<<C / 64, 1024, 0, st>>>(scratch, (int)grid.y, C, out);
   R3DFS_CHECK_LAUNCH();
   return 0;
 }
