@@ -124,6 +124,34 @@ __device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t a_desc, uint6
       "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Same, accumulate flag as a compile-time constant (no predicate setup in the issue loop), and the
+// descriptor of k-step `ks` derived from the k-step-0 descriptor by one add: the start-address
+// field (bits 0-13, units of 16 B) advances by 2 chunks = 2 * LBO bytes per tf32 k-step of 8.
+template <bool ACC>
+__device__ __forceinline__ void mma_tf32_c(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc,
+                                           uint32_t idesc) {
+  if (ACC) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.eq.b32 p, 0, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d),
+        "l"(a_desc), "l"(b_desc), "r"(idesc)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, 0, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d),
+        "l"(a_desc), "l"(b_desc), "r"(idesc)
+        : "memory");
+  }
+}
+__host__ __device__ constexpr uint64_t desc_kstep(int lbo_bytes) { return (uint64_t)((2 * lbo_bytes) >> 4); }
+
 // all MMAs issued so far by this thread arrive on `bar` when they have completed
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
@@ -134,10 +162,13 @@ __device__ __forceinline__ void mma_commit(uint64_t* bar) {
 // ---- 3xTF32 split ---------------------------------------------------------------------------------
 // x = hi + lo with hi = tf32(x), lo = tf32(x - hi);  A.B ~= Ahi.Bhi + Ahi.Blo + Alo.Bhi keeps
 // FP32-level accuracy on the tensor cores (error ~ 2^-21 relative per product).
+// Round to TF32 (10-bit mantissa), nearest with ties away from zero — what cvt.rna.tf32.f32 returns
+// for every finite input, done on the bit pattern: add half a TF32 ulp, clear the 13 low bits (a
+// carry out of the mantissa bumps the exponent, as rounding should).  cvt.rna.tf32.f32 itself is
+// not a single SASS instruction on sm_100 (~5 with its NaN/Inf handling); this is 2 integer ops,
+// and the operand split below runs once per element of every tensor-core operand tile.
 __device__ __forceinline__ float tf32_rn(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return __uint_as_float(r);
+  return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
 }
 __device__ __forceinline__ void split4(const float4& x, float4& hi, float4& lo) {
   hi.x = tf32_rn(x.x); hi.y = tf32_rn(x.y); hi.z = tf32_rn(x.z); hi.w = tf32_rn(x.w);

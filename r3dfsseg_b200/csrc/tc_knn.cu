@@ -10,6 +10,8 @@
 //              the reference's ranking key, queue the candidates that beat the row's current k-th
 //              best, then merge the queue into a sorted k-list kept in registers.
 // While the selectors work on tile j the tensor core computes tile j+1 and the loaders fetch j+2.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "tc.cuh"
 
@@ -24,7 +26,8 @@ struct KnnTcSmem {
   static constexpr int B_OFF = 2 * TILE;                 // 2 stages x (hi, lo)
   static constexpr int QV_OFF = B_OFF + 4 * TILE;        // queue values  [16][256] float
   static constexpr int QI_OFF = QV_OFF + 16 * 256 * 4;   // queue columns [16][256] uint8
-  static constexpr int TOTAL = QI_OFF + 16 * 256 + 64;   // (the queue is reused for the final merge)
+  static constexpr int XS_OFF = QI_OFF + 16 * 256;       // |x_j|^2 of 4 tiles in flight [4][128]
+  static constexpr int TOTAL = XS_OFF + 4 * 128 * 4 + 64;  // (the queue is reused for the final merge)
 };
 
 template <int KC4>
@@ -53,6 +56,56 @@ __device__ __forceinline__ void knn_store_tile(unsigned char* hi_base, unsigned 
     }
     float4 hi, lo;
     tc::split4(v, hi, lo);
+    *reinterpret_cast<float4*>(hi_base + kc * LBO + r * 16) = hi;
+    *reinterpret_cast<float4*>(lo_base + kc * LBO + r * 16) = lo;
+  }
+}
+
+// Candidate-tile loader split in two so that a thread's global loads of the NEXT tile are all in
+// flight while the current tile is converted and the MMAs are issued (the straight loop above
+// serialises one L2 round trip per 16-byte chunk, which is what used to bound the whole kernel).
+template <int KC4, int ROWS, int NTHR>
+struct TileRegs {
+  static constexpr int NCH = ROWS * KC4 / NTHR;
+  float4 v[NCH];
+};
+
+template <int KC4, int ROWS, int NTHR>
+__device__ __forceinline__ void tile_load(TileRegs<KC4, ROWS, NTHR>& tr, const float* __restrict__ x,
+                                          int ld, int C, int64_t row0, int64_t rows_end, int t,
+                                          bool vec_ok) {
+#pragma unroll
+  for (int i = 0; i < TileRegs<KC4, ROWS, NTHR>::NCH; ++i) {
+    const int c = t + i * NTHR;
+    const int r = c / KC4, kc = c % KC4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int64_t row = row0 + r;
+    const int k = 4 * kc;
+    if (row < rows_end && k < C) {
+      const float* p = x + row * (int64_t)ld + k;
+      if (vec_ok && k + 3 < C) {
+        v = __ldg(reinterpret_cast<const float4*>(p));
+      } else {
+        v.x = __ldg(p);
+        if (k + 1 < C) v.y = __ldg(p + 1);
+        if (k + 2 < C) v.z = __ldg(p + 2);
+        if (k + 3 < C) v.w = __ldg(p + 3);
+      }
+    }
+    tr.v[i] = v;
+  }
+}
+
+template <int KC4, int ROWS, int NTHR>
+__device__ __forceinline__ void tile_store(const TileRegs<KC4, ROWS, NTHR>& tr,
+                                           unsigned char* hi_base, unsigned char* lo_base, int t) {
+  constexpr int LBO = tc::tile_lbo(ROWS);
+#pragma unroll
+  for (int i = 0; i < TileRegs<KC4, ROWS, NTHR>::NCH; ++i) {
+    const int c = t + i * NTHR;
+    const int r = c / KC4, kc = c % KC4;
+    float4 hi, lo;
+    tc::split4(tr.v[i], hi, lo);
     *reinterpret_cast<float4*>(hi_base + kc * LBO + r * 16) = hi;
     *reinterpret_cast<float4*>(lo_base + kc * LBO + r * 16) = lo;
   }
@@ -121,12 +174,24 @@ __global__ __launch_bounds__(KT_THREADS, 1) void knn_tc_kernel(const float* __re
   if (w >= 8) {
     // ------------------------------ loaders + MMA issue -------------------------------------
     const int lt = tid - 256;
+    TileRegs<KC4, 128, 128> tr;
+    float* xs = reinterpret_cast<float*>(smem + S::XS_OFF);
+    tile_load(tr, x, ld, C, base, base + N, lt, vec_ok);
+    float xn = lt < N ? __ldg(xx + base + lt) : 0.f;
     for (int j = 0; j < T; ++j) {
       const int st = j & 1;
       if (j >= 2) tc::mbar_wait(&bar_full[st], ((j >> 1) - 1) & 1);  // stage's previous MMAs done
       unsigned char* hi = smem + S::B_OFF + st * 2 * S::TILE;
       unsigned char* lo = hi + S::TILE;
-      knn_store_tile<KC4>(hi, lo, x, ld, C, base + (int64_t)j * KT_TC, base + N, lt, 128, vec_ok);
+      tile_store(tr, hi, lo, lt);
+      // the tile's |x_j|^2 travel with it (ring of 4: slot j is rewritten by tile j + 4, whose
+      // loaders have waited for MMA j + 2, which was issued after the selectors released tile j)
+      xs[(j & 3) * KT_TC + lt] = xn;
+      if (j + 1 < T) {
+        tile_load(tr, x, ld, C, base + (int64_t)(j + 1) * KT_TC, base + N, lt, vec_ok);
+        const int cn_ = (j + 1) * KT_TC + lt;
+        xn = cn_ < N ? __ldg(xx + base + cn_) : 0.f;
+      }
       tc::fence_async_smem();
       asm volatile("bar.sync 1, 128;" ::: "memory");
       if (lt == 0) {
@@ -135,14 +200,20 @@ __global__ __launch_bounds__(KT_THREADS, 1) void knn_tc_kernel(const float* __re
         const uint32_t q_hi = tc::smem_u32(smem + S::Q_OFF), q_lo = q_hi + S::TILE;
         const uint32_t b_hi = tc::smem_u32(hi), b_lo = b_hi + S::TILE;
         const uint32_t d = tmem_d + st * KT_TC;
-        for (int ks = 0; ks < ksteps; ++ks) {
-          const uint64_t dqh = tc::make_desc(q_hi + ks * 2 * LBO, LBO, 128);
-          const uint64_t dql = tc::make_desc(q_lo + ks * 2 * LBO, LBO, 128);
-          const uint64_t dbh = tc::make_desc(b_hi + ks * 2 * LBO, LBO, 128);
-          const uint64_t dbl = tc::make_desc(b_lo + ks * 2 * LBO, LBO, 128);
-          tc::mma_tf32(d, dql, dbh, IDESC, ks != 0);
-          tc::mma_tf32(d, dqh, dbl, IDESC, 1);
-          tc::mma_tf32(d, dqh, dbh, IDESC, 1);
+        // one descriptor per operand tile; k-step ks is a constant added to its address field
+        const uint64_t dqh = tc::make_desc(q_hi, LBO, 128), dql = tc::make_desc(q_lo, LBO, 128);
+        const uint64_t dbh = tc::make_desc(b_hi, LBO, 128), dbl = tc::make_desc(b_lo, LBO, 128);
+        constexpr uint64_t KS = tc::desc_kstep(LBO);
+        tc::mma_tf32_c<false>(d, dql, dbh, IDESC);
+        tc::mma_tf32_c<true>(d, dqh, dbl, IDESC);
+        tc::mma_tf32_c<true>(d, dqh, dbh, IDESC);
+#pragma unroll
+        for (int ks = 1; ks < 2 * KC4 / 4; ++ks) {
+          if (ks < ksteps) {
+            tc::mma_tf32_c<true>(d, dql + ks * KS, dbh + ks * KS, IDESC);
+            tc::mma_tf32_c<true>(d, dqh + ks * KS, dbl + ks * KS, IDESC);
+            tc::mma_tf32_c<true>(d, dqh + ks * KS, dbh + ks * KS, IDESC);
+          }
         }
         tc::mma_commit(&bar_full[st]);
       }
@@ -158,7 +229,7 @@ __global__ __launch_bounds__(KT_THREADS, 1) void knn_tc_kernel(const float* __re
     const int half = w >> 2;
     const int q = q0 + row;
     const float nq = (q < N) ? -xx[base + q] : 0.f;
-    const bool vecn = (N & 3) == 0;
+    const float* xs = reinterpret_cast<const float*>(smem + S::XS_OFF);
     float lv[KL];
     int li[KL];
 #pragma unroll
@@ -183,15 +254,7 @@ __global__ __launch_bounds__(KT_THREADS, 1) void knn_tc_kernel(const float* __re
 #pragma unroll
           for (int u = hh; u < hh + 16; u += 4) {
             const int cg = c0 + cc + u;
-            float4 cn = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (cg + 3 < N && vecn) {
-              cn = __ldg(reinterpret_cast<const float4*>(xx + base + cg));
-            } else {
-              if (cg + 0 < N) cn.x = xx[base + cg + 0];
-              if (cg + 1 < N) cn.y = xx[base + cg + 1];
-              if (cg + 2 < N) cn.z = xx[base + cg + 2];
-              if (cg + 3 < N) cn.w = xx[base + cg + 3];
-            }
+            const float4 cn = *reinterpret_cast<const float4*>(xs + (j & 3) * KT_TC + cc + u);
             const float cnv[4] = {cn.x, cn.y, cn.z, cn.w};
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
@@ -251,6 +314,325 @@ __global__ __launch_bounds__(KT_THREADS, 1) void knn_tc_kernel(const float* __re
   if (w == 0) tc::tmem_dealloc(tmem_d, 2 * KT_TC);
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Two-pass variant (k <= 20, 1024 <= N <= 65535): the per-row selection above pays one
+// warp-divergent 120-instruction list insertion for each of the ~k (1 + ln(N / k)) candidates that
+// beat a running threshold.  Here the distance GEMM runs TWICE (it is cheap: the tensor pipe idles
+// otherwise) and the first pass only produces a tight, exact lower bound of every row's k-th best
+// key:  the row's candidates are cut into 64 groups, the k-th largest of the 64 group maxima is
+// <= the k-th largest key, and only ~k (1 + 1/3) keys lie above it.  The second pass recomputes the
+// keys (bit-identical), appends the few that reach the bound to a per-thread queue in shared
+// memory, and the 20-lists are built once at the end, all lanes inserting together.
+//   candidate tiles are 64 wide here (two 33 KB operand stages instead of 66 KB) to make room for
+//   the queues; warps 0-7 = (TMEM lane quarter, 32-column half), warps 8-11 loaders + MMA issue.
+// ---------------------------------------------------------------------------------------------
+#define K2_TC 64
+#define K2_CAP 56  // queue entries per selector thread; drained when fewer than 32 slots remain
+#define K2_G 32    // group maxima per selector thread (64 per row)
+
+template <int KC4>
+struct Knn2Smem {
+  static constexpr int TQ = tc::tile_bytes(128, KC4);
+  static constexpr int TB = tc::tile_bytes(K2_TC, KC4);
+  static constexpr int Q_OFF = 0;                            // Q hi, Q lo
+  static constexpr int B_OFF = 2 * TQ;                       // 2 stages x (hi, lo)
+  static constexpr int QK_OFF = B_OFF + 4 * TB;              // queue keys [CAP][256] float
+  static constexpr int QC_OFF = QK_OFF + K2_CAP * 256 * 4;   // queue columns [CAP][256] u16
+  static constexpr int XS_OFF = QC_OFF + K2_CAP * 256 * 2;   // |x_j|^2 of 4 tiles in flight [4][64]
+  static constexpr int TOTAL = XS_OFF + 4 * K2_TC * 4 + 64;
+};
+
+template <int KC4, int ROWS>
+__device__ __forceinline__ void knn_store_tile_r(unsigned char* hi_base, unsigned char* lo_base,
+                                                 const float* __restrict__ x, int ld, int C,
+                                                 int64_t row0, int64_t rows_end, int t, int nthr,
+                                                 bool vec_ok) {
+  constexpr int LBO = tc::tile_lbo(ROWS);
+  constexpr int CH = ROWS * KC4;
+  for (int c = t; c < CH; c += nthr) {
+    const int r = c / KC4, kc = c % KC4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int64_t row = row0 + r;
+    const int k = 4 * kc;
+    if (row < rows_end && k < C) {
+      const float* p = x + row * (int64_t)ld + k;
+      if (vec_ok && k + 3 < C) {
+        v = *reinterpret_cast<const float4*>(p);
+      } else {
+        v.x = p[0];
+        if (k + 1 < C) v.y = p[1];
+        if (k + 2 < C) v.z = p[2];
+        if (k + 3 < C) v.w = p[3];
+      }
+    }
+    float4 hi, lo;
+    tc::split4(v, hi, lo);
+    *reinterpret_cast<float4*>(hi_base + kc * LBO + r * 16) = hi;
+    *reinterpret_cast<float4*>(lo_base + kc * LBO + r * 16) = lo;
+  }
+}
+
+// descending bitonic sort of 64 registers (fully unrolled: every index is a compile-time constant)
+__device__ __forceinline__ void sort64_desc(float (&v)[64]) {
+#pragma unroll
+  for (int size = 2; size <= 64; size <<= 1) {
+#pragma unroll
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+#pragma unroll
+      for (int i = 0; i < 64; ++i) {
+        const int j = i ^ stride;
+        if (j > i) {
+          const bool desc = (i & size) == 0;
+          const float a = v[i], b = v[j];
+          v[i] = desc ? fmaxf(a, b) : fminf(a, b);
+          v[j] = desc ? fminf(a, b) : fmaxf(a, b);
+        }
+      }
+    }
+  }
+}
+
+// the reference's ranking keys of 32 consecutive candidates: -xx_i - (-2 x_i.x_j) - xx_j
+__device__ __forceinline__ void knn_keys32(float (&v)[32], float nq, const float* xs32) {
+#pragma unroll
+  for (int u = 0; u < 32; u += 4) {
+    const float4 cn = *reinterpret_cast<const float4*>(xs32 + u);
+    v[u + 0] = (nq - (-2.f * v[u + 0])) - cn.x;
+    v[u + 1] = (nq - (-2.f * v[u + 1])) - cn.y;
+    v[u + 2] = (nq - (-2.f * v[u + 2])) - cn.z;
+    v[u + 3] = (nq - (-2.f * v[u + 3])) - cn.w;
+  }
+}
+
+template <int KC4>
+__global__ __launch_bounds__(KT_THREADS, 1) void knn_tc2_kernel(const float* __restrict__ x, int ld,
+                                                                int C, const float* __restrict__ xx,
+                                                                int N, int k,
+                                                                int32_t* __restrict__ idx32,
+                                                                int64_t* __restrict__ idx64) {
+  constexpr int KL = 20;
+  extern __shared__ __align__(128) unsigned char smem[];
+  using S = Knn2Smem<KC4>;
+  __shared__ uint64_t bar_full[2];
+  __shared__ uint64_t bar_tfree[2];
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int b = blockIdx.y;
+  const int q0 = blockIdx.x * KT_TQ;
+  const int64_t base = (int64_t)b * N;
+  constexpr int LBOQ = tc::tile_lbo(128), LBOB = tc::tile_lbo(K2_TC);
+  constexpr uint32_t IDESC = tc::make_idesc_tf32(128, K2_TC);
+  const bool vec_ok = ((ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
+  const int T = (N + K2_TC - 1) / K2_TC;
+  const int ksteps = (min(C, 4 * KC4) + 7) / 8;
+
+  if (tid == 0) {
+    tc::mbar_init(&bar_full[0], 1);
+    tc::mbar_init(&bar_full[1], 1);
+    tc::mbar_init(&bar_tfree[0], 256);
+    tc::mbar_init(&bar_tfree[1], 256);
+    tc::mbar_fence_init();
+  }
+  if (w == 0) tc::tmem_alloc(&tmem_base_s, 2 * K2_TC);
+  knn_store_tile_r<KC4, 128>(smem + S::Q_OFF, smem + S::Q_OFF + S::TQ, x, ld, C, base + q0,
+                             base + N, tid, KT_THREADS, vec_ok);
+  tc::fence_async_smem();
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_d = tmem_base_s;
+
+  if (w >= 8) {
+    // ------------------------------ loaders + MMA issue: every tile twice ---------------------
+    const int lt = tid - 256;
+    TileRegs<KC4, K2_TC, 128> tr;
+    float* xs = reinterpret_cast<float*>(smem + S::XS_OFF);
+    tile_load(tr, x, ld, C, base, base + N, lt, vec_ok);
+    float xn = (lt < K2_TC && lt < N) ? __ldg(xx + base + lt) : 0.f;
+    for (int j = 0; j < 2 * T; ++j) {
+      const int st = j & 1;
+      if (j >= 2) tc::mbar_wait(&bar_full[st], ((j >> 1) - 1) & 1);
+      unsigned char* hi = smem + S::B_OFF + st * 2 * S::TB;
+      unsigned char* lo = hi + S::TB;
+      tile_store(tr, hi, lo, lt);
+      if (lt < K2_TC) xs[(j & 3) * K2_TC + lt] = xn;  // ring of 4, see knn_tc_kernel
+      if (j + 1 < 2 * T) {
+        const int jn = j + 1 < T ? j + 1 : j + 1 - T;
+        tile_load(tr, x, ld, C, base + (int64_t)jn * K2_TC, base + N, lt, vec_ok);
+        const int cn_ = jn * K2_TC + lt;
+        xn = (lt < K2_TC && cn_ < N) ? __ldg(xx + base + cn_) : 0.f;
+      }
+      tc::fence_async_smem();
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (lt == 0) {
+        if (j >= 2) tc::mbar_wait(&bar_tfree[st], ((j >> 1) - 1) & 1);
+        tc::tc_fence_after();
+        const uint32_t q_hi = tc::smem_u32(smem + S::Q_OFF), q_lo = q_hi + S::TQ;
+        const uint32_t b_hi = tc::smem_u32(hi), b_lo = b_hi + S::TB;
+        const uint32_t d = tmem_d + st * K2_TC;
+        const uint64_t dqh = tc::make_desc(q_hi, LBOQ, 128), dql = tc::make_desc(q_lo, LBOQ, 128);
+        const uint64_t dbh = tc::make_desc(b_hi, LBOB, 128), dbl = tc::make_desc(b_lo, LBOB, 128);
+        constexpr uint64_t KQ = tc::desc_kstep(LBOQ), KB = tc::desc_kstep(LBOB);
+        tc::mma_tf32_c<false>(d, dql, dbh, IDESC);
+        tc::mma_tf32_c<true>(d, dqh, dbl, IDESC);
+        tc::mma_tf32_c<true>(d, dqh, dbh, IDESC);
+#pragma unroll
+        for (int ks = 1; ks < 2 * KC4 / 4; ++ks) {
+          if (ks < ksteps) {
+            tc::mma_tf32_c<true>(d, dql + ks * KQ, dbh + ks * KB, IDESC);
+            tc::mma_tf32_c<true>(d, dqh + ks * KQ, dbl + ks * KB, IDESC);
+            tc::mma_tf32_c<true>(d, dqh + ks * KQ, dbh + ks * KB, IDESC);
+          }
+        }
+        tc::mma_commit(&bar_full[st]);
+      }
+    }
+  } else {
+    // ------------------------------ selectors ------------------------------------------------
+    float* qk = reinterpret_cast<float*>(smem + S::QK_OFF);
+    unsigned short* qc = reinterpret_cast<unsigned short*>(smem + S::QC_OFF);
+    const int row = 32 * (w & 3) + lane;
+    const int half = w >> 2;
+    const int q = q0 + row;
+    const float nq = (q < N) ? -xx[base + q] : 0.f;
+    const float* xs = reinterpret_cast<const float*>(smem + S::XS_OFF) + 32 * half;
+    const uint32_t taddr = tmem_d + ((uint32_t)(32 * (w & 3)) << 16) + (uint32_t)(32 * half);
+    // ---- pass 1: group maxima --------------------------------------------------------------
+#pragma unroll 1
+    for (int s = 0; s < K2_G; ++s) qk[s * 256 + tid] = -INFINITY;
+#pragma unroll 1
+    for (int j = 0; j < T; ++j) {
+      const int st = j & 1;
+      tc::mbar_wait(&bar_full[st], (j >> 1) & 1);
+      tc::tc_fence_after();
+      float v[32];
+      tc::tmem_ld32(taddr + (uint32_t)(st * K2_TC), v);
+      const int c0 = j * K2_TC + 32 * half;
+      knn_keys32(v, nq, xs + (j & 3) * K2_TC);
+      tc::tc_fence_before();
+      mbar_arrive(&bar_tfree[st]);  // accumulator buffer and the tile's norms are consumed
+      float m = -INFINITY;
+      if (c0 + 32 <= N) {
+#pragma unroll
+        for (int e = 0; e < 32; ++e) m = fmaxf(m, v[e]);
+      } else {
+#pragma unroll
+        for (int e = 0; e < 32; ++e)
+          if (c0 + e < N) m = fmaxf(m, v[e]);
+      }
+      float* g = qk + (j & (K2_G - 1)) * 256 + tid;
+      *g = fmaxf(*g, m);
+    }
+    // ---- bound: k-th largest of the row's 64 group maxima ---------------------------------------
+    asm volatile("bar.sync 2, 256;" ::: "memory");
+    float tau;
+    {
+      float gm[64];
+#pragma unroll
+      for (int s = 0; s < K2_G; ++s) {
+        gm[s] = qk[s * 256 + tid];
+        gm[K2_G + s] = qk[s * 256 + (tid ^ 128)];
+      }
+      sort64_desc(gm);
+      tau = gm[0];
+#pragma unroll
+      for (int i = 1; i < KL; ++i)
+        if (i == k - 1) tau = gm[i];
+    }
+    asm volatile("bar.sync 2, 256;" ::: "memory");  // the maxima are read: the region becomes the queue
+    // ---- pass 2: queue everything that reaches the bound, build the lists lazily -------------------
+    float lv[KL];
+    int li[KL];
+#pragma unroll
+    for (int i = 0; i < KL; ++i) {
+      lv[i] = -INFINITY;
+      li[i] = 0;
+    }
+    int qcnt = 0;
+    auto drain = [&]() {
+      const int mx = __reduce_max_sync(0xffffffffu, qcnt);
+      for (int e = 0; e < mx; ++e) {
+        if (e < qcnt) {
+          const float key = qk[e * 256 + tid];
+          if (key > lv[KL - 1]) list_insert<KL>(lv, li, key, (int)qc[e * 256 + tid]);
+        }
+      }
+      qcnt = 0;
+    };
+#pragma unroll 1
+    for (int j2 = 0; j2 < T; ++j2) {
+      const int j = T + j2;
+      const int st = j & 1;
+      tc::mbar_wait(&bar_full[st], (j >> 1) & 1);
+      tc::tc_fence_after();
+      float v[32];
+      tc::tmem_ld32(taddr + (uint32_t)(st * K2_TC), v);
+      const int c0 = j2 * K2_TC + 32 * half;
+      knn_keys32(v, nq, xs + (j & 3) * K2_TC);
+      tc::tc_fence_before();
+      mbar_arrive(&bar_tfree[st]);
+      const float thr = lv[KL - 1];
+      const int nvalid = N - c0;
+#pragma unroll
+      for (int e = 0; e < 32; ++e) {
+        if (v[e] >= tau && v[e] > thr && e < nvalid) {
+          qk[qcnt * 256 + tid] = v[e];
+          qc[qcnt * 256 + tid] = (unsigned short)(c0 + e);
+          ++qcnt;
+        }
+      }
+      if (__any_sync(0xffffffffu, qcnt > K2_CAP - 32)) drain();
+    }
+    drain();
+    // merge the two column halves of every row (as in knn_tc_kernel)
+    float* qv = qk;
+    int* mi = reinterpret_cast<int*>(smem + S::B_OFF);
+    asm volatile("bar.sync 2, 256;" ::: "memory");
+    if (half == 1) {
+#pragma unroll
+      for (int i = 0; i < KL; ++i) {
+        qv[i * 128 + row] = lv[i];
+        mi[i * 128 + row] = li[i];
+      }
+    }
+    asm volatile("bar.sync 2, 256;" ::: "memory");
+    if (half == 0) {
+#pragma unroll 1
+      for (int i = 0; i < KL; ++i) {
+        const float key = qv[i * 128 + row];
+        if (key > lv[KL - 1]) list_insert<KL>(lv, li, key, mi[i * 128 + row]);
+      }
+      if (q < N) {
+#pragma unroll
+        for (int i = 0; i < KL; ++i) {
+          if (i < k) {
+            const int64_t o = (base + q) * k + i;
+            if (idx32) idx32[o] = li[i];
+            if (idx64) idx64[o] = li[i];
+          }
+        }
+      }
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (w == 0) tc::tmem_dealloc(tmem_d, 2 * K2_TC);
+}
+
+template <int KC4>
+static int launch_knn_tc2_t(const float* x, int ld, int C, const float* xx, int64_t B, int N, int k,
+                            int32_t* idx32, int64_t* idx64, cudaStream_t st) {
+  using S = Knn2Smem<KC4>;
+  cudaError_t e = cudaFuncSetAttribute(knn_tc2_kernel<KC4>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
+  if (e != cudaSuccess) return (int)e;
+  dim3 grid((N + KT_TQ - 1) / KT_TQ, (unsigned)B);
+  knn_tc2_kernel<KC4><<<grid, KT_THREADS, S::TOTAL, st>>>(x, ld, C, xx, N, k, idx32, idx64);
+  R3DFS_CHECK_LAUNCH();
+  return 0;
+}
+
 template <int KC4, int KL>
 static int launch_knn_tc_t(const float* x, int ld, int C, const float* xx, int64_t B, int N, int k,
                            int32_t* idx32, int64_t* idx64, cudaStream_t st) {
@@ -264,10 +646,34 @@ static int launch_knn_tc_t(const float* x, int ld, int C, const float* xx, int64
   return 0;
 }
 
+static bool knn_single_pass_forced() {  // A/B switch: R3DFS_KNN_SINGLE_PASS=1
+  static const bool v = [] {
+    const char* e = getenv("R3DFS_KNN_SINGLE_PASS");
+    return e && e[0] == '1';
+  }();
+  return v;
+}
+
+static bool knn_two_pass_forced() {
+  static const bool v = [] {
+    const char* e = getenv("R3DFS_KNN_TWO_PASS");
+    return e && e[0] == '1';
+  }();
+  return v;
+}
+
 // returns R3DFS_E_UNSUPPORTED for shapes the tensor-core kernel is not built for (C > 64)
 int launch_knn_tc(const float* x, int ld, int C, const float* xx, int64_t B, int N, int k,
                   int32_t* idx32, int64_t* idx64, cudaStream_t st) {
   if (k < 1 || k > 32 || C > 64 || N < k) return R3DFS_E_UNSUPPORTED;
+  // two-pass selection where the second GEMM is cheap (C <= 16: measured 2.56 vs 3.05 ms per 300
+  // clouds of 2048); at C = 64 the doubled operand conversion costs more than the selection saves
+  // (4.84 vs 3.5 ms).  R3DFS_KNN_TWO_PASS=1 forces it for every C (A/B measurements, tests).
+  if (k <= 20 && N >= 1024 && N <= 65535 && !knn_single_pass_forced() &&
+      (C <= 16 || knn_two_pass_forced())) {
+    if (C <= 16) return launch_knn_tc2_t<4>(x, ld, C, xx, B, N, k, idx32, idx64, st);
+    return launch_knn_tc2_t<16>(x, ld, C, xx, B, N, k, idx32, idx64, st);
+  }
   if (C <= 16) {
     if (k <= 20) return launch_knn_tc_t<4, 20>(x, ld, C, xx, B, N, k, idx32, idx64, st);
     return launch_knn_tc_t<4, 32>(x, ld, C, xx, B, N, k, idx32, idx64, st);
