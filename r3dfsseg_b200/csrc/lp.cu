@@ -2,6 +2,8 @@
 // in sparse form, plus the query loss / prediction / confusion counters.
 #include <cooperative_groups.h>
 
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "lp.cuh"
 
@@ -871,7 +873,12 @@ int launch_lp_solve(const int32_t* rowptr, const int32_t* rowlen, const uint16_t
   const size_t smem_cg = sizeof(float) * (size_t)nn * ncv;
   if (smem_cg > 200 * 1024) return R3DFS_E_UNSUPPORTED;
   int rc = -1000;
-  for (int CL = 16; CL >= 8 && rc == -1000; CL >>= 1) {
+  static const int cl_first = [] {  // A/B switch: R3DFS_CG_CLUSTER = 16 | 8 | 4 | 2
+    const char* e = getenv("R3DFS_CG_CLUSTER");
+    const int v = e ? atoi(e) : 0;
+    return (v == 16 || v == 8 || v == 4 || v == 2) ? v : 8;
+  }();
+  for (int CL = cl_first; CL >= 2 && rc == -1000; CL >>= 1) {
     if (ncv == 4)
       rc = launch_cg<4>(CL, G, smem_cg, st, rowptr, rowlen, mcol, mval, valid, nn, k, Y, nc, alpha,
                         tol, max_iter, Z, X, R, P, AP, iters_out, resid_out);
