@@ -467,7 +467,7 @@ def main():
         stages[name] = ent
     # dominant KERNEL = the kernel with the largest summed device time per call (several stages
     # are launches of the same kernel)
-    kernel_of = {"knn0": "knn_tc_kernel", "knn1": "knn_tc_kernel", "knn2": "knn_tc_kernel",
+    kernel_of = {"knn0": "knn_tc2_kernel", "knn1": "knn_tc_kernel", "knn2": "knn_tc_kernel",
                  "edge0": "edge_tc_kernel", "edge1": "edge_tc_kernel", "edge2": "edge_tc_kernel",
                  "pq0": "linear_tc_kernel", "pq1": "linear_tc_kernel", "pq2": "linear_tc_kernel",
                  "mlp": "linear_tc_kernel", "base": "linear_tc_kernel", "qkv": "linear_tc_kernel",
@@ -503,6 +503,16 @@ def main():
         ach = gt["bytes"] / (gt["ms"] * 1e-3) / 1e9
         roof = {"bound": "hbm", "achieved": round(ach, 2), "peak": peaks["hbm_gbs"], "unit": "GB/s",
                 "frac": round(ach / peaks["hbm_gbs"], 5), "traffic": None}
+    # DRAM bytes per launch of that kernel from the committed ncu --set full capture (same workload)
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        ent = tr["kernels"].get(top.split("<")[0])
+        if ent and tr["episodes_per_call"] == chunk and args.workload == "s3dis_2way_5shot":
+            roof["traffic"] = ent["read"] + ent["write"]
+            roof["traffic_source"] = "profiles/ncu_traffic.json (ncu dram__bytes_read+write per launch)"
+            roof["algorithmic_bytes_per_launch"] = gt["bytes"] / gt["launches"]
+    except (OSError, ValueError, KeyError):
+        pass
     roof.update(kernel=top, stages=gt["stages"], peak_source=peaks["source"],
                 launches_per_call=gt["launches"],
                 ms_per_launch=round(gt["ms"] / gt["launches"], 4),

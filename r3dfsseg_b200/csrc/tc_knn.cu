@@ -259,8 +259,7 @@ __global__ __launch_bounds__(KT_THREADS, 1) void knn_tc_kernel(const float* __re
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               // reference key: -xx_i - (-2 x_i.x_j) - xx_j
-              const float inner = -2.f * v[u + e];
-              const float key = (nq - inner) - cnv[e];
+              const float key = fmaf(2.f, v[u + e], nq) - cnv[e];  // = (nq - (-2 v)) - cn exactly
               if (key > thr && cg + e < N) {
                 qv[cnt * 256 + tid] = key;
                 qi[cnt * 256 + tid] = (unsigned char)(cc + u + e);
@@ -398,10 +397,11 @@ __device__ __forceinline__ void knn_keys32(float (&v)[32], float nq, const float
 #pragma unroll
   for (int u = 0; u < 32; u += 4) {
     const float4 cn = *reinterpret_cast<const float4*>(xs32 + u);
-    v[u + 0] = (nq - (-2.f * v[u + 0])) - cn.x;
-    v[u + 1] = (nq - (-2.f * v[u + 1])) - cn.y;
-    v[u + 2] = (nq - (-2.f * v[u + 2])) - cn.z;
-    v[u + 3] = (nq - (-2.f * v[u + 3])) - cn.w;
+    // (nq - (-2 v)) - cn: the doubling is exact, so one FMA gives the reference's rounding
+    v[u + 0] = fmaf(2.f, v[u + 0], nq) - cn.x;
+    v[u + 1] = fmaf(2.f, v[u + 1], nq) - cn.y;
+    v[u + 2] = fmaf(2.f, v[u + 2], nq) - cn.z;
+    v[u + 3] = fmaf(2.f, v[u + 3], nq) - cn.w;
   }
 }
 
