@@ -876,9 +876,12 @@ int launch_lp_solve(const int32_t* rowptr, const int32_t* rowlen, const uint16_t
   static const int cl_first = [] {  // A/B switch: R3DFS_CG_CLUSTER = 16 | 8 | 4 | 2
     const char* e = getenv("R3DFS_CG_CLUSTER");
     const int v = e ? atoi(e) : 0;
-    return (v == 16 || v == 8 || v == 4 || v == 2) ? v : 8;
+    return (v == 16 || v == 8 || v == 4 || v == 2) ? v : 0;
   }();
-  for (int CL = cl_first; CL >= 2 && rc == -1000; CL >>= 1) {
+  // many graphs: 8-CTA clusters (about twice as many clusters are co-resident as with 16);
+  // a handful of graphs (the training step solves one): 16 CTAs per graph to cut the latency
+  const int cl_start = cl_first ? cl_first : (G <= 4 ? 16 : 8);
+  for (int CL = cl_start; CL >= 2 && rc == -1000; CL >>= 1) {
     if (ncv == 4)
       rc = launch_cg<4>(CL, G, smem_cg, st, rowptr, rowlen, mcol, mval, valid, nn, k, Y, nc, alpha,
                         tol, max_iter, Z, X, R, P, AP, iters_out, resid_out);

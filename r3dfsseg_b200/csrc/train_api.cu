@@ -65,6 +65,9 @@ struct TrainWs {
   GroupWs grp[2];  // 0 = support clouds, 1 = query clouds
   float* wpq[3];
   float *ones, *zeros;
+  // transposed weights for the tensor-core input-gradient GEMMs: W2 of the 3 EdgeConvs, MLP0, MLP1,
+  // BL1, Wqkv
+  float* wT[7];
   // shared scratch
   float *xx, *PQ, *edgeA, *edgeB, *dS, *dqkv, *dl2, *d512, *decat, *d128, *d64, *dPQ, *dWf;
   double* bn_scratch;
@@ -114,6 +117,10 @@ static void carve_train(WsBump& ws, const r3dfs_episode_cfg_t* c, const EpisodeD
   for (int i = 0; i < 3; ++i) t.wpq[i] = ws.take<float>(128 * 64);
   t.ones = ws.take<float>(512);
   t.zeros = ws.take<float>(512);
+  {
+    const size_t wt_sz[7] = {64 * 64, 64 * 64, 64 * 64, 512 * 192, 256 * 512, 64 * 128, 192 * 256};
+    for (int i = 0; i < 7; ++i) t.wT[i] = ws.take<float>(wt_sz[i]);
+  }
   t.xx = ws.take<float>(Mm);
   t.PQ = ws.take<float>(Mm * 128);
   t.edgeA = ws.take<float>(Em * 64);
@@ -200,6 +207,13 @@ static int lin_bwd_x(const TrainCtx& c, const TrainWs& t, const float* dY, int l
                      int64_t M, int K, int Nout, float* dX, int ld_dx, float beta) {
   return launch_sgemm(dY, ld_dy, 1, 0, W, K, 1, 0, dX, ld_dx, 0, (int)M, K, Nout, 1, 1.f, beta, 1,
                       t.partial, c.st);
+}
+
+// dX (M x K) = dY (M x Nout) W with W^T (K x Nout, row-major) given: the forward tensor-core kernel
+static int lin_bwd_x_tc(const TrainCtx& c, const float* dY, int ld_dy, const float* WT, int64_t M,
+                        int K, int Nout, float* dX, int ld_dx) {
+  return launch_linear_auto(dY, ld_dy, WT, nullptr, nullptr, ACT_NONE, M, Nout, K, dX, ld_dx,
+                            identity_map(), c.st);
 }
 
 // dW (Nout x K) += dY^T X, reduced over M rows (split-K, fixed order)
@@ -314,12 +328,12 @@ static int group_backward(const TrainCtx& c, const TrainWs& t, const GroupWs& g,
   R3DFS_TRY(launch_sgemm(t.dS, 1, N, ps, g.qkv, 192, 1, cs, t.dqkv + 64, 192, cs, N, 64, N, (int)g.B,
                          0.125f, 0.f, 1, t.partial, st));
   R3DFS_TRY(lin_bwd_w(c, t, t.dqkv, 192, g.l2, 256, M, 256, 192, c.G(R3DFS_P_ATT_Q)));
-  R3DFS_TRY(lin_bwd_x(c, t, t.dqkv, 192, c.P(R3DFS_P_ATT_Q), M, 256, 192, t.dl2, 256, 0.f));
+  R3DFS_TRY(lin_bwd_x_tc(c, t.dqkv, 192, t.wT[6], M, 256, 192, t.dl2, 256));
   // ---- BaseLearner ------------------------------------------------------------------------------
   R3DFS_TRY(bn_bwd(c, t, g, 9, dF + 128, 192, g.bl1pre, 64, M, ACT_NONE, t.d64, 64));
   R3DFS_TRY(lin_bwd_w(c, t, t.d64, 64, g.bl0a, 128, M, 128, 64, c.G(R3DFS_P_BL1_W)));
   R3DFS_TRY(launch_col_sum_acc(t.d64, 64, M, 64, c.G(R3DFS_P_BL1_BIAS), t.bn_scratch, st));
-  R3DFS_TRY(lin_bwd_x(c, t, t.d64, 64, c.P(R3DFS_P_BL1_W), M, 128, 64, t.d128, 128, 0.f));
+  R3DFS_TRY(lin_bwd_x_tc(c, t.d64, 64, t.wT[5], M, 128, 64, t.d128, 128));
   R3DFS_TRY(bn_bwd(c, t, g, 8, t.d128, 128, g.bl0pre, 128, M, ACT_RELU, t.d128, 128));
   R3DFS_TRY(lin_bwd_w(c, t, t.d128, 128, g.l2, 256, M, 256, 128, c.G(R3DFS_P_BL0_W)));
   R3DFS_TRY(launch_col_sum_acc(t.d128, 128, M, 128, c.G(R3DFS_P_BL0_BIAS), t.bn_scratch, st));
@@ -327,10 +341,10 @@ static int group_backward(const TrainCtx& c, const TrainWs& t, const GroupWs& g,
   // ---- point MLP --------------------------------------------------------------------------------
   R3DFS_TRY(bn_bwd(c, t, g, 7, t.dl2, 256, g.l2pre, 256, M, ACT_LRELU, t.dl2, 256));
   R3DFS_TRY(lin_bwd_w(c, t, t.dl2, 256, g.a512, 512, M, 512, 256, c.G(R3DFS_P_MLP1_W)));
-  R3DFS_TRY(lin_bwd_x(c, t, t.dl2, 256, c.P(R3DFS_P_MLP1_W), M, 512, 256, t.d512, 512, 0.f));
+  R3DFS_TRY(lin_bwd_x_tc(c, t.dl2, 256, t.wT[4], M, 512, 256, t.d512, 512));
   R3DFS_TRY(bn_bwd(c, t, g, 6, t.d512, 512, g.h512pre, 512, M, ACT_LRELU, t.d512, 512));
   R3DFS_TRY(lin_bwd_w(c, t, t.d512, 512, g.ecat, 192, M, 192, 512, c.G(R3DFS_P_MLP0_W)));
-  R3DFS_TRY(lin_bwd_x(c, t, t.d512, 512, c.P(R3DFS_P_MLP0_W), M, 192, 512, t.decat, 192, 0.f));
+  R3DFS_TRY(lin_bwd_x_tc(c, t.d512, 512, t.wT[3], M, 192, 512, t.decat, 192));
   R3DFS_TRY(launch_add_cols(dF, 192, M, 64, t.decat, 192, st));  // level-1 feature
   // ---- EdgeConv blocks, last to first -------------------------------------------------------------
   for (int i = 2; i >= 0; --i) {
@@ -346,7 +360,7 @@ static int group_backward(const TrainCtx& c, const TrainWs& t, const GroupWs& g,
     R3DFS_TRY(launch_bn_act(g.h1pre[i], 64, Ek, 64, g.stats[2 * i], c.P(gi), c.P(bi), ACT_LRELU,
                             t.edgeA, 64, st));
     R3DFS_TRY(lin_bwd_w(c, t, t.edgeB, 64, t.edgeA, 64, Ek, 64, 64, c.G(pw + R3DFS_P_EC0_W2)));
-    R3DFS_TRY(lin_bwd_x(c, t, t.edgeB, 64, c.P(pw + R3DFS_P_EC0_W2), Ek, 64, 64, t.edgeA, 64, 0.f));
+    R3DFS_TRY(lin_bwd_x_tc(c, t.edgeB, 64, t.wT[i], Ek, 64, 64, t.edgeA, 64));
     R3DFS_TRY(bn_bwd(c, t, g, 2 * i, t.edgeA, 64, g.h1pre[i], 64, Ek, ACT_LRELU, t.edgeA, 64));
     R3DFS_TRY(launch_edge_pre_bwd(t.edgeA, g.idx[i], g.B, N, k, t.dPQ, st));
     // d[W1a ; W1b - W1a] = dPQ^T x, unfolded into dW1
@@ -482,6 +496,12 @@ int r3dfs_mpti_train_backward(const r3dfs_episode_cfg_t* cfg_in, int in_dim, int
   if (ce != cudaSuccess) return (int)ce;
   ce = cudaMemsetAsync(t.dF, 0, sizeof(float) * (size_t)d.ep_rows * D, st);
   if (ce != cudaSuccess) return (int)ce;
+  for (int i = 0; i < 3; ++i)
+    R3DFS_TRY(launch_transpose(c.P(6 * i + R3DFS_P_EC0_W2), 64, 64, t.wT[i], st));
+  R3DFS_TRY(launch_transpose(c.P(R3DFS_P_MLP0_W), 512, 192, t.wT[3], st));
+  R3DFS_TRY(launch_transpose(c.P(R3DFS_P_MLP1_W), 256, 512, t.wT[4], st));
+  R3DFS_TRY(launch_transpose(c.P(R3DFS_P_BL1_W), 64, 128, t.wT[5], st));
+  R3DFS_TRY(launch_transpose(c.P(R3DFS_P_ATT_Q), 192, 256, t.wT[6], st));
   // cross-entropy -> dZ -> adjoint solve G = (I - alpha S)^-1 dZ -> per-edge gradients -> node rows
   R3DFS_TRY(launch_ce_grad(w.Z, nn, d.ppad, d.nq_pts, nc, query_y, w_lp, t.dZ, st));
   R3DFS_TRY(launch_lp_solve(w.rowptr, w.rowlen, w.mcol, w.mval, w.valid, 1, nn, kc, t.dZ, nc,

@@ -293,7 +293,7 @@ int launch_support_grad(const float* dFnode, int slot, const int32_t* assign,
 #define CT_MAXK 64
 #define CT_PD 128  // projection width
 
-__global__ __launch_bounds__(256) void contrast_kernel(
+__global__ __launch_bounds__(1024) void contrast_kernel(
     const float* __restrict__ cproto, const int32_t* __restrict__ cproto_cnt, int cslot, int D,
     const int32_t* __restrict__ support_flag, int n_way, int k_shot, int way,
     const float* __restrict__ proj_w, const float* __restrict__ proj_b, float temp,
@@ -339,7 +339,7 @@ __global__ __launch_bounds__(256) void contrast_kernel(
   __syncthreads();
   const int K = s_K;
   // u = W p + b
-  for (int e = tid; e < K * CT_PD; e += 256) {
+  for (int e = tid; e < K * CT_PD; e += blockDim.x) {
     const int a = e / CT_PD, o = e % CT_PD;
     const float* p = cproto + (int64_t)s_src[a] * D;
     const float* wr = proj_w + (int64_t)o * D;
@@ -354,9 +354,9 @@ __global__ __launch_bounds__(256) void contrast_kernel(
     s_norm[tid] = fmaxf(sqrtf(s), 1e-12f);
   }
   __syncthreads();
-  for (int e = tid; e < K * CT_PD; e += 256) s_z[e] /= s_norm[e / CT_PD];
+  for (int e = tid; e < K * CT_PD; e += blockDim.x) s_z[e] /= s_norm[e / CT_PD];
   __syncthreads();
-  for (int e = tid; e < K * K; e += 256) {
+  for (int e = tid; e < K * K; e += blockDim.x) {
     const int a = e / K, b = e % K;
     float s = 0.f;
     for (int o = 0; o < CT_PD; ++o) s += s_z[a * CT_PD + o] * s_z[b * CT_PD + o];
@@ -387,7 +387,7 @@ __global__ __launch_bounds__(256) void contrast_kernel(
   if (!backward) return;
   __syncthreads();
   // dlogits_ab = (w / K) (softmax_ab - mask_ab / npos_a), zero diagonal
-  for (int e = tid; e < K * K; e += 256) {
+  for (int e = tid; e < K * K; e += blockDim.x) {
     const int a = e / K, b = e % K;
     float g = 0.f;
     if (a != b) {
@@ -399,7 +399,7 @@ __global__ __launch_bounds__(256) void contrast_kernel(
   }
   __syncthreads();
   // dz_a = sum_b (dl_ab + dl_ba) z_b / temp ; du_a = (dz_a - z_a (z_a . dz_a)) / norm_a
-  for (int e = tid; e < K * CT_PD; e += 256) {
+  for (int e = tid; e < K * CT_PD; e += blockDim.x) {
     const int a = e / CT_PD, o = e % CT_PD;
     float s = 0.f;
     for (int b = 0; b < K; ++b) s += (s_l[a * CT_MAXK + b] + s_l[b * CT_MAXK + a]) * s_z[b * CT_PD + o];
@@ -412,24 +412,24 @@ __global__ __launch_bounds__(256) void contrast_kernel(
     s_row[tid] = dot;
   }
   __syncthreads();
-  for (int e = tid; e < K * CT_PD; e += 256) {
+  for (int e = tid; e < K * CT_PD; e += blockDim.x) {
     const int a = e / CT_PD;
     s_du[e] = (s_du[e] - s_z[e] * s_row[a]) / s_norm[a];
   }
   __syncthreads();
   // dW[o][d] += sum_a du[a][o] p_a[d] ;  db[o] += sum_a du[a][o] ;  dp_a[d] += sum_o W[o][d] du[a][o]
-  for (int e = tid; e < CT_PD * D; e += 256) {
+  for (int e = tid; e < CT_PD * D; e += blockDim.x) {
     const int o = e / D, d = e % D;
     float s = 0.f;
     for (int a = 0; a < K; ++a) s += s_du[a * CT_PD + o] * cproto[(int64_t)s_src[a] * D + d];
     dproj_w[e] += s;
   }
-  for (int o = tid; o < CT_PD; o += 256) {
+  for (int o = tid; o < CT_PD; o += blockDim.x) {
     float s = 0.f;
     for (int a = 0; a < K; ++a) s += s_du[a * CT_PD + o];
     dproj_b[o] += s;
   }
-  for (int e = tid; e < K * D; e += 256) {
+  for (int e = tid; e < K * D; e += blockDim.x) {
     const int a = e / D, d = e % D;
     float s = 0.f;
     for (int o = 0; o < CT_PD; ++o) s += proj_w[(int64_t)o * D + d] * s_du[a * CT_PD + o];
@@ -447,7 +447,7 @@ int launch_contrast(const float* cproto, const int32_t* cproto_cnt, int cslot, i
   cudaError_t e = cudaFuncSetAttribute(contrast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)smem);
   if (e != cudaSuccess) return (int)e;
-  contrast_kernel<<<1, 256, smem, st>>>(cproto, cproto_cnt, cslot, D, support_flag, n_way, k_shot,
+  contrast_kernel<<<1, 1024, smem, st>>>(cproto, cproto_cnt, cslot, D, support_flag, n_way, k_shot,
                                         way, proj_w, proj_b, temp, loss_way, backward, w, dproj_w,
                                         dproj_b, dcproto);
   R3DFS_CHECK_LAUNCH();
