@@ -119,9 +119,9 @@ int launch_edge_feature(const float* x, int64_t B, int64_t C, int64_t N, int64_t
 int launch_attention(const float* qkv, int ld, int64_t B, int N, float* Y, int ldy, RowMap map,
                      cudaStream_t st);
 int launch_attention_tc(const float* qkv, int ld, int64_t B, int N, float* Y, int ldy, RowMap map,
-                        cudaStream_t st);
+                        cudaStream_t st, float* kmax_ws = nullptr);
 int launch_attention_auto(const float* qkv, int ld, int64_t B, int N, float* Y, int ldy,
-                          RowMap map, cudaStream_t st);
+                          RowMap map, cudaStream_t st, float* kmax_ws = nullptr);
 int launch_fold_edge_w1(const float* w1, const float* s1, const float* t1, int C, float* wpq,
                         float* spq, float* tpq, cudaStream_t st);
 

@@ -6,6 +6,10 @@
 //   sweep 2:  S again (bit-identical), P = exp(S - m) written as a K-major UMMA A tile (hi/lo),
 //             l += rowsum(P),  O += P V  with V^T staged as the K-major B tile; O stays in TMEM.
 // Knowing m before the second sweep means O never has to be rescaled inside TMEM.
+// Sweep 1 is normally SKIPPED: softmax is shift invariant, so any m' >= max_j S_ij works as long as
+// exp(S - m') stays in the normal FP32 range.  m' = |q_i / 8| * max_j |k_j| (Cauchy-Schwarz, the
+// per-cloud key-norm maximum comes from a small pre-kernel) is used when it is <= 60 for every row
+// of the CTA (exp(-60) = 9e-27, far above FP32's 1e-38); otherwise the CTA runs the exact sweep.
 // The (N, N) attention map exists only as 128 x 64 tiles in TMEM / shared memory.
 #include "common.cuh"
 #include "tc.cuh"
@@ -85,10 +89,40 @@ __device__ __forceinline__ void at_store_vT(const float4 (&v)[2], unsigned char*
   }
 }
 
+// max_j |k_j|^2 per cloud (k = columns 64..127 of the qkv rows)
+__global__ __launch_bounds__(256) void att_kmax_kernel(const float* __restrict__ qkv, int ld, int N,
+                                                       float* __restrict__ kmax2) {
+  __shared__ float s_red[8];
+  const int b = blockIdx.x;
+  float mx = 0.f;
+  for (int r = threadIdx.x; r < N; r += 256) {
+    const float4* p = reinterpret_cast<const float4*>(qkv + ((int64_t)b * N + r) * ld + 64);
+    float s = 0.f;
+#pragma unroll
+    for (int c = 0; c < 16; ++c) {
+      const float4 v = __ldg(p + c);
+      s = fmaf(v.x, v.x, s);
+      s = fmaf(v.y, v.y, s);
+      s = fmaf(v.z, v.z, s);
+      s = fmaf(v.w, v.w, s);
+    }
+    mx = fmaxf(mx, s);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int q = 1; q < 8; ++q) mx = fmaxf(mx, s_red[q]);
+    kmax2[b] = mx;
+  }
+}
+
 __global__ __launch_bounds__(AT_THREADS, 1) void attention_tc_kernel(const float* __restrict__ qkv,
                                                                      int ld, int N,
                                                                      float* __restrict__ Y, int ldy,
-                                                                     RowMap map) {
+                                                                     RowMap map,
+                                                                     const float* __restrict__ kmax2) {
   extern __shared__ __align__(128) unsigned char smem[];
   using S = AttTcSmem;
   __shared__ uint64_t bar_s, bar_pv;
@@ -152,37 +186,65 @@ __global__ __launch_bounds__(AT_THREADS, 1) void attention_tc_kernel(const float
   };
 
   uint32_t ph_s = 0, ph_pv = 0;
-  // ---------------- sweep 1: row maxima -------------------------------------------------------
-  float m_run = -INFINITY;
-  {
-    float4 kv[2];
-    at_load_rows(kv, qkv, ld, base, base + N, 64, tid);
-    for (int j = 0; j < T; ++j) {
-      at_store_rows(kv, k_hi_p, k_lo_p, tid);
-      tc::fence_async_smem();
-      tc::tc_fence_before();
-      __syncthreads();  // K tile complete; everybody has finished reading S of the previous tile
-      if (tid == 0) {
-        tc::tc_fence_after();
-        issue_s();
-      }
-      if (j + 1 < T) at_load_rows(kv, qkv, ld, base + (int64_t)(j + 1) * AT_BK, base + N, 64, tid);
-      tc::mbar_wait(&bar_s, ph_s);
-      ph_s ^= 1;
-      tc::tc_fence_after();
-      float v[16];
-      tc::tmem_ld16(tmem_s + ((uint32_t)(32 * (w & 3)) << 16) + (uint32_t)(16 * quarter), v);
-      const int c0 = j * AT_BK + 16 * quarter;
+  // ---------------- row bound m' = |q/8| max|k| (or exact row maxima when the bound is too loose) ---
+  float m_row;
+  bool exact = kmax2 == nullptr;
+  if (!exact) {
+    float qs = 0.f;
+    if (q0 + row < N) {
+      const float4* qp =
+          reinterpret_cast<const float4*>(qkv + (base + q0 + row) * (int64_t)ld + 16 * quarter);
 #pragma unroll
-      for (int e = 0; e < 16; ++e)
-        if (c0 + e < N) m_run = fmaxf(m_run, v[e]);
+      for (int c = 0; c < 4; ++c) {
+        float4 v = __ldg(qp + c);
+        v.x /= 8.f; v.y /= 8.f; v.z /= 8.f; v.w /= 8.f;
+        qs = fmaf(v.x, v.x, qs);
+        qs = fmaf(v.y, v.y, qs);
+        qs = fmaf(v.z, v.z, qs);
+        qs = fmaf(v.w, v.w, qs);
+      }
     }
+    xch[quarter * 128 + row] = qs;
+    __syncthreads();
+    const float q2 = (xch[row] + xch[128 + row]) + (xch[256 + row] + xch[384 + row]);
+    // 1e-4 relative + 1e-6 absolute slack covers the rounding of the norms and of the 3xTF32 S
+    m_row = sqrtf(q2) * sqrtf(__ldg(kmax2 + b)) * 1.0001f + 1e-6f;
+    exact = __syncthreads_or(!(m_row <= 60.f));
   }
-  // combine the two column halves of every row
-  xch[quarter * 128 + row] = m_run;
-  tc::tc_fence_before();
-  __syncthreads();
-  const float m_row = fmaxf(fmaxf(xch[row], xch[128 + row]), fmaxf(xch[256 + row], xch[384 + row]));
+  if (exact) {
+    // ---------------- sweep 1: row maxima -----------------------------------------------------
+    float m_run = -INFINITY;
+    {
+      float4 kv[2];
+      at_load_rows(kv, qkv, ld, base, base + N, 64, tid);
+      for (int j = 0; j < T; ++j) {
+        at_store_rows(kv, k_hi_p, k_lo_p, tid);
+        tc::fence_async_smem();
+        tc::tc_fence_before();
+        __syncthreads();  // K tile complete; everybody has finished reading S of the previous tile
+        if (tid == 0) {
+          tc::tc_fence_after();
+          issue_s();
+        }
+        if (j + 1 < T) at_load_rows(kv, qkv, ld, base + (int64_t)(j + 1) * AT_BK, base + N, 64, tid);
+        tc::mbar_wait(&bar_s, ph_s);
+        ph_s ^= 1;
+        tc::tc_fence_after();
+        float v[16];
+        tc::tmem_ld16(tmem_s + ((uint32_t)(32 * (w & 3)) << 16) + (uint32_t)(16 * quarter), v);
+        const int c0 = j * AT_BK + 16 * quarter;
+#pragma unroll
+        for (int e = 0; e < 16; ++e)
+          if (c0 + e < N) m_run = fmaxf(m_run, v[e]);
+      }
+    }
+    // combine the four column quarters of every row
+    __syncthreads();
+    xch[quarter * 128 + row] = m_run;
+    tc::tc_fence_before();
+    __syncthreads();
+    m_row = fmaxf(fmaxf(xch[row], xch[128 + row]), fmaxf(xch[256 + row], xch[384 + row]));
+  }
   __syncthreads();
 
   // ---------------- sweep 2: P = exp(S - m), l, O += P V ---------------------------------------
@@ -272,15 +334,21 @@ __global__ __launch_bounds__(AT_THREADS, 1) void attention_tc_kernel(const float
   if (w == 0) tc::tmem_dealloc(tmem_base_s, 128);
 }
 
+// kmax_ws: B floats of scratch for the per-cloud key-norm maxima; nullptr -> always two sweeps
 int launch_attention_tc(const float* qkv, int ld, int64_t B, int N, float* Y, int ldy, RowMap map,
-                        cudaStream_t st) {
+                        cudaStream_t st, float* kmax_ws) {
   if ((ld & 3) != 0 || (ldy & 3) != 0) return R3DFS_E_UNSUPPORTED;
+  if (kmax_ws) {
+    att_kmax_kernel<<<(unsigned)B, 256, 0, st>>>(qkv, ld, N, kmax_ws);
+    R3DFS_CHECK_LAUNCH();
+  }
   cudaError_t e = cudaFuncSetAttribute(attention_tc_kernel,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        AttTcSmem::TOTAL);
   if (e != cudaSuccess) return (int)e;
   dim3 grid((N + AT_BQ - 1) / AT_BQ, (unsigned)B);
-  attention_tc_kernel<<<grid, AT_THREADS, AttTcSmem::TOTAL, st>>>(qkv, ld, N, Y, ldy, map);
+  attention_tc_kernel<<<grid, AT_THREADS, AttTcSmem::TOTAL, st>>>(qkv, ld, N, Y, ldy, map,
+                                                                  kmax_ws);
   R3DFS_CHECK_LAUNCH();
   return 0;
 }

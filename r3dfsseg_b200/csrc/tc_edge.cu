@@ -96,7 +96,24 @@ __global__ __launch_bounds__(ET_THREADS, 1) void edge_tc_kernel(
         nb[i] = (u2 < U && p < N) ? idx[(base + p) * k + j] : -1;
       }
     };
+    // Software pipeline: the gathers of tile u + 1 are issued as soon as tile u has been written
+    // to its stage (their registers are free again), so their L2 round trip overlaps the fence,
+    // the producers' barrier, the MMA issue and the wait for the next stage; the neighbour
+    // indices run one tile further ahead.
+    float4 hv[NCH];
+    int live = 0;
+    auto issue_gather = [&]() {  // rows nb[] of P -> hv (all loads in flight together)
+      live = 0;
+#pragma unroll
+      for (int i = 0; i < NCH; ++i) {
+        const int nbi = nb[i] >= 0 ? nb[i] : 0;
+        live |= (nb[i] >= 0) << i;
+        hv[i] = __ldg(reinterpret_cast<const float4*>(PQ + (base + nbi) * 128 + 4 * kc));
+      }
+    };
     load_nb(0);
+    issue_gather();
+    load_nb(1);
     for (int u = 0; u < U; ++u) {
       const int st = u & 1;
       const int g = g_begin + u / k;
@@ -107,16 +124,6 @@ __global__ __launch_bounds__(ET_THREADS, 1) void edge_tc_kernel(
           qv4[i] = __ldg(reinterpret_cast<const float4*>(PQ + (base + p) * 128 + 64 + 4 * kc));
         }
       }
-      // every gather of the tile in flight before anything is consumed
-      float4 hv[NCH];
-      int live = 0;
-#pragma unroll
-      for (int i = 0; i < NCH; ++i) {
-        const int nbi = nb[i] >= 0 ? nb[i] : 0;
-        live |= (nb[i] >= 0) << i;
-        hv[i] = __ldg(reinterpret_cast<const float4*>(PQ + (base + nbi) * 128 + 4 * kc));
-      }
-      load_nb(u + 1);
 #pragma unroll
       for (int i = 0; i < NCH; ++i) {
         float4 h = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -141,6 +148,10 @@ __global__ __launch_bounds__(ET_THREADS, 1) void edge_tc_kernel(
         *reinterpret_cast<float4*>(a_hi + kc * LBO_A + r * 16) = hi;
         *reinterpret_cast<float4*>(a_lo + kc * LBO_A + r * 16) = lo;
       }
+      if (u + 1 < U) {
+        issue_gather();  // nb holds the indices of tile u + 1
+        load_nb(u + 2);
+      }
       tc::fence_async_smem();
       asm volatile("bar.sync 1, 256;" ::: "memory");
       if (lt == 0) {
@@ -149,15 +160,17 @@ __global__ __launch_bounds__(ET_THREADS, 1) void edge_tc_kernel(
         const uint32_t ah = tc::smem_u32(a_hi), al = ah + S::A_TILE;
         const uint32_t wh = tc::smem_u32(smem + S::W_OFF), wl = wh + S::W_TILE;
         const uint32_t d = tmem_d + st * 64;
-#pragma unroll 1
-        for (int ks = 0; ks < 8; ++ks) {
-          const uint64_t dah = tc::make_desc(ah + ks * 2 * LBO_A, LBO_A, 128);
-          const uint64_t dal = tc::make_desc(al + ks * 2 * LBO_A, LBO_A, 128);
-          const uint64_t dwh = tc::make_desc(wh + ks * 2 * LBO_W, LBO_W, 128);
-          const uint64_t dwl = tc::make_desc(wl + ks * 2 * LBO_W, LBO_W, 128);
-          tc::mma_tf32(d, dal, dwh, IDESC, ks != 0);
-          tc::mma_tf32(d, dah, dwl, IDESC, 1);
-          tc::mma_tf32(d, dah, dwh, IDESC, 1);
+        const uint64_t dah = tc::make_desc(ah, LBO_A, 128), dal = tc::make_desc(al, LBO_A, 128);
+        const uint64_t dwh = tc::make_desc(wh, LBO_W, 128), dwl = tc::make_desc(wl, LBO_W, 128);
+        constexpr uint64_t KA = tc::desc_kstep(LBO_A), KW = tc::desc_kstep(LBO_W);
+        tc::mma_tf32_c<false>(d, dal, dwh, IDESC);
+        tc::mma_tf32_c<true>(d, dah, dwl, IDESC);
+        tc::mma_tf32_c<true>(d, dah, dwh, IDESC);
+#pragma unroll
+        for (int ks = 1; ks < 8; ++ks) {
+          tc::mma_tf32_c<true>(d, dal + ks * KA, dwh + ks * KW, IDESC);
+          tc::mma_tf32_c<true>(d, dah + ks * KA, dwl + ks * KW, IDESC);
+          tc::mma_tf32_c<true>(d, dah + ks * KA, dwh + ks * KW, IDESC);
         }
         tc::mma_commit(&bar_full[st]);
       }
