@@ -98,7 +98,11 @@ class Episode:
 
 def make_episode(seed: int, n_way: int = 2, k_shot: int = 5, n_queries: int = 1,
                  dataset: str = "s3dis", noise_ratio: float = 0.0,
-                 n_pts: int = N_POINTS) -> Episode:
+                 n_pts: int = N_POINTS, noise_type: str = "ood") -> Episode:
+    """noise_type (reference dataloaders/loader.py:675-686): "ood" — a noisy shot's foreground
+    object is a test class outside the sampled ways; "sym" — it is one of the OTHER sampled ways."""
+    if noise_type not in ("ood", "sym"):
+        raise ValueError("noise_type must be 'ood' or 'sym'")
     pool = CLASS_POOL[dataset]
     rng = np.random.default_rng(seed)
     sampled = rng.choice(pool, size=n_way, replace=False)
@@ -123,7 +127,10 @@ def make_episode(seed: int, n_way: int = 2, k_shot: int = 5, n_queries: int = 1,
         wx, wy, wg, wf = [], [], [], []
         for k in range(k_shot):
             noisy = k >= k_shot - n_noise
-            fg_cls = int(rng.choice(others)) if noisy else int(c)
+            if noisy and noise_type == "sym" and n_way > 1:
+                fg_cls = int(rng.choice([s_ for s_ in sampled if s_ != c]))
+            else:
+                fg_cls = int(rng.choice(others)) if noisy else int(c)
             objs = [fg_cls]
             if rng.uniform() < 0.3 and others:
                 extra = int(rng.choice(others))

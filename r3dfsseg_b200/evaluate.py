@@ -78,7 +78,11 @@ class EpisodeEvaluator:
                 qx.to(dev, non_blocking=True).transpose(2, 3), qy.to(dev, non_blocking=True),
                 slot.to(dev, non_blocking=True))
 
-    def run(self, episodes: Sequence, rank: int = 0, world: int = 1) -> Dict[str, object]:
+    def run(self, episodes: Sequence, rank: int = 0, world: int = 1, logger=None,
+            log_every: int = 50) -> Dict[str, object]:
+        """logger: optional object with `.cprint(str)` (the reference's utils.logger); it gets the
+        reference's progress line every `log_every` episodes (eval_noise.py:94-95) and the
+        per-class IoU printout at the end (:64-68)."""
         from . import ops
         mine = [episodes[i] for i in shard_indices(len(episodes), rank, world)]
         n_slots = len(self.test_classes) + 1
@@ -89,8 +93,40 @@ class EpisodeEvaluator:
             out = self.model.forward_episodes(sx, sy, qx, qy, eval=self.eval_mdns)
             ops.confusion_accumulate(out["pred"], qy, slot, counters)
             loss_sum += out["loss"].double().sum()
+            done = min(s + self.batch, len(mine))
+            if logger is not None and done // log_every > s // log_every:
+                from datetime import datetime
+                logger.cprint("[Eval] Iter: %d | Loss: %.4f | %s" % (
+                    done, float(out["loss"][-1]), str(datetime.now())))
         n = torch.tensor(float(len(mine)), dtype=torch.float64, device=self.device)
         all_reduce_eval_state(counters, loss_sum, n)
         res = iou_from_counters(counters)
         res.update(counters=counters.cpu(), mean_loss=float(loss_sum / n), n_episodes=int(n))
+        if logger is not None and rank == 0:
+            for c in range(n_slots):
+                logger.cprint("class %d: iou %f" % (c, res["iou"][c]))
+            logger.cprint("mean IoU: %f\n" % res["mean_iou"])
         return res
+
+
+class _ItemEpisode:
+    """Adapter: (data list, sampled_classes) as the reference's test loader yields them."""
+
+    def __init__(self, data, sampled_classes):
+        self.support_x, self.support_y, self.query_x, self.query_y = data[0], data[1], data[2], data[3]
+        self.sampled_classes = np.asarray(sampled_classes).reshape(-1)
+
+
+def test_few_shot(test_loader, learner, logger, test_classes, path=None, eval=False, batch: int = 16):
+    """Drop-in for reference eval_noise.py:75-113: same arguments, returns (mean_loss, mean_IoU).
+    `test_loader` yields (data, sampled_classes) per episode exactly as the reference's DataLoader
+    (batch_size 1, `batch_test_task_collate_test`); episodes are run `batch` at a time through one
+    C-ABI call each and — under torch.distributed — sharded over the ranks."""
+    import torch.distributed as dist
+    rank = dist.get_rank() if dist.is_available() and dist.is_initialized() else 0
+    world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+    episodes = [_ItemEpisode(data, classes) for data, classes in test_loader]
+    learner.model.eval()
+    ev = EpisodeEvaluator(learner.model, test_classes, batch=batch, eval_mdns=bool(eval))
+    res = ev.run(episodes, rank, world, logger=logger)
+    return res["mean_loss"], res["mean_iou"]

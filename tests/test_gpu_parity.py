@@ -586,3 +586,31 @@ def test_episode_ragged_shapes_vs_oracle(fixture_sd, n_way, k_shot, n_pts, n_sub
     agree = (pred.argmax(1) == rp.argmax(1)).float().mean()
     assert err < 1e-3 and agree >= 0.999, (err, agree)
     assert abs(float(loss) - float(ref["loss"])) < 1e-4
+
+
+def test_drop_in_test_few_shot_matches_per_episode_loop(model, fixture_sd):
+    """evaluate.test_few_shot (reference eval_noise.py:75-113 signature) on a loader of collated
+    episodes == the reference's own loop: learner.test per episode + evaluate_metric."""
+    from r3dfsseg_b200 import episode_io as IO
+    from r3dfsseg_b200.evaluate import test_few_shot
+    from r3dfsseg_b200.train import MPTILearner_V3
+    m = model(2, 5)
+    learner = MPTILearner_V3(default_args(2, 5), mode="test", model=m)
+    eps = [make_episode(300 + i, 2, 5, noise_ratio=0.4) for i in range(5)]
+    loader = [IO.collate_test(IO.episode_arrays(e)) for e in eps]
+    test_classes = list(range(6))
+    lines = []
+
+    class Log:
+        def cprint(self, s):
+            lines.append(s)
+    mean_loss, mean_iou = test_few_shot(loader, learner, Log(), test_classes, eval=True, batch=2)
+    preds, gts, l2c, losses = [], [], [], []
+    for data, classes in loader:
+        pred, loss, _ = learner.test([t.to(DEV) for t in data], classes, eval=True)
+        preds.append(pred.cpu().numpy()); gts.append(data[3].numpy()); l2c.append(classes)
+        losses.append(float(loss))
+    ref = O.mean_iou(O.confusion_counts(preds, gts, l2c, test_classes))
+    assert abs(mean_iou - ref) < 1e-9
+    assert abs(mean_loss - float(np.mean(losses))) < 1e-5
+    assert any("mean IoU" in s for s in lines)

@@ -195,3 +195,46 @@ def test_gradient_bucket_allreduce_gloo_world2():
     for p in procs:
         p.join(timeout=60)
     assert sorted(results) == [(0, True), (1, True)]
+
+
+def test_episode_file_round_trip(tmp_path):
+    """The reference's episode schema (dataloaders/loader.py:1687-1721) survives write -> read, and
+    the collate leaves the clouds point-major behind (.., 9, N) views (loader.py:1676-1684)."""
+    from r3dfsseg_b200 import episode_io as IO
+    from r3dfsseg_b200.episodes import make_episode
+    ep = make_episode(5, 2, 5, noise_ratio=0.4)
+    arrays = IO.episode_arrays(ep)
+    assert [a.dtype.name for a in arrays] == [IO.SCHEMA[k] for k in IO.ORDER]
+    path = IO.write_episode(str(tmp_path / "0.h5"), arrays)
+    back = IO.read_episode(path)
+    for a, b in zip(arrays, back):
+        assert a.shape == b.shape and a.dtype == b.dtype and np.array_equal(a, b)
+    data, classes = IO.collate_test(back)
+    assert data[0].shape == (2, 5, 9, 2048) and data[0].transpose(2, 3).is_contiguous()
+    assert data[2].shape == (2, 9, 2048) and data[3].dtype == torch.int64
+    assert torch.equal(data[0], ep.support_x) and torch.equal(data[3], ep.query_y)
+    assert np.array_equal(classes, ep.sampled_classes)
+    folder = IO.EpisodeFolder(str(tmp_path))
+    assert len(folder) == 1
+    (d2, c2), = list(folder)
+    assert torch.equal(d2[2], ep.query_x)
+    sx, sy, qx, qy, cls = IO.stage_batch([back, back], pin=False)
+    assert sx.shape == (2, 2, 5, 2048, 9) and qy.shape == (2, 2, 2048) and cls.shape == (2, 2)
+
+
+def test_symmetric_noise_episode():
+    """'sym' noise (reference dataloaders/loader.py:677-678): noisy shots show another sampled way."""
+    from r3dfsseg_b200.episodes import make_episode
+    ep = make_episode(9, 3, 5, dataset="scannet", noise_ratio=0.4, noise_type="sym")
+    sampled = set(int(c) for c in ep.sampled_classes)
+    noisy = ep.gt_support_y.sum(-1) == 0
+    assert (noisy.sum(1) == 2).all()
+    for w in range(3):
+        for k in range(5):
+            cls = int(ep.support_flag[w, k])
+            if noisy[w, k]:
+                assert cls in sampled and cls != int(ep.sampled_classes[w])
+            else:
+                assert cls == int(ep.sampled_classes[w])
+    clean = make_episode(9, 3, 5, dataset="scannet", noise_ratio=0.4)   # default stays 'ood'
+    assert not torch.equal(clean.support_flag, ep.support_flag)
