@@ -640,15 +640,18 @@ __global__ __launch_bounds__(CG_THREADS) void lp_cg_kernel(
       const int L = rl[row];
       const uint16_t* crow = mc + rp[row];
       const float* vrow = mv + rp[row];
-      for (int t0 = 0; t0 < L; t0 += 256) {
+      // full blocks of 256 entries: 8 unguarded (col, val) pairs per lane in flight; the remainder
+      // (rows average ~264 entries, so usually a handful) goes 32 at a time instead of paying for
+      // another predicated 8-deep block
+      int t0 = 0;
+      for (; t0 + 256 <= L; t0 += 256) {
         int cj[8];
         float cv[8];
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
           const int t = t0 + lane + 32 * u;
-          const bool ok = t < L;
-          cj[u] = ok ? (int)crow[t] : 0;
-          cv[u] = ok ? vrow[t] : 0.f;
+          cj[u] = (int)crow[t];
+          cv[u] = vrow[t];
         }
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
@@ -659,6 +662,43 @@ __global__ __launch_bounds__(CG_THREADS) void lp_cg_kernel(
             acc[4 * q + 1] = fmaf(cv[u], p4.y, acc[4 * q + 1]);
             acc[4 * q + 2] = fmaf(cv[u], p4.z, acc[4 * q + 2]);
             acc[4 * q + 3] = fmaf(cv[u], p4.w, acc[4 * q + 3]);
+          }
+        }
+      }
+      // tail: up to 255 entries, 4 then 1 lane-steps at a time
+      for (; t0 + 128 <= L; t0 += 128) {
+        int cj[4];
+        float cv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int t = t0 + lane + 32 * u;
+          cj[u] = (int)crow[t];
+          cv[u] = vrow[t];
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+#pragma unroll
+          for (int q = 0; q < NCV / 4; ++q) {
+            const float4 p4 = *reinterpret_cast<const float4*>(Ps + (int64_t)cj[u] * NCV + 4 * q);
+            acc[4 * q + 0] = fmaf(cv[u], p4.x, acc[4 * q + 0]);
+            acc[4 * q + 1] = fmaf(cv[u], p4.y, acc[4 * q + 1]);
+            acc[4 * q + 2] = fmaf(cv[u], p4.z, acc[4 * q + 2]);
+            acc[4 * q + 3] = fmaf(cv[u], p4.w, acc[4 * q + 3]);
+          }
+        }
+      }
+      for (; t0 < L; t0 += 32) {
+        const int t = t0 + lane;
+        if (t < L) {
+          const int cj = (int)crow[t];
+          const float cv = vrow[t];
+#pragma unroll
+          for (int q = 0; q < NCV / 4; ++q) {
+            const float4 p4 = *reinterpret_cast<const float4*>(Ps + (int64_t)cj * NCV + 4 * q);
+            acc[4 * q + 0] = fmaf(cv, p4.x, acc[4 * q + 0]);
+            acc[4 * q + 1] = fmaf(cv, p4.y, acc[4 * q + 1]);
+            acc[4 * q + 2] = fmaf(cv, p4.z, acc[4 * q + 2]);
+            acc[4 * q + 3] = fmaf(cv, p4.w, acc[4 * q + 3]);
           }
         }
       }
