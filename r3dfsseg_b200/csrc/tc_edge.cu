@@ -7,18 +7,20 @@
 //
 // One CTA walks over groups of 128 points.  MMA tile t of a group = neighbour slot t of its 128
 // points (row = point), so a TMEM lane always belongs to the same point: the max over neighbours
-// is a running max in the registers of the thread that owns (point, channel half) — no exchange.
-//   warps 8-15: producers.  Each thread owns 8 fixed (row, 16-byte chunk) cells of the A tile; its
+// is a running max in the registers of the thread that owns the point — no exchange.
+//   warps 4-11: producers.  Each thread owns 8 fixed (row, 16-byte chunk) cells of the A tile; its
 //               Q values stay in registers for the whole group, per tile it gathers P[nbr] (indices
-//               prefetched one tile ahead), adds, LeakyReLU, TF32 hi/lo split, stores (2 stages).
-//               One thread issues 3 x 8 tcgen05.mma (3xTF32, K = 64) against the resident W2 tile
-//               and commits to an mbarrier.
-//   warps 0-7:  epilogue.  tcgen05.ld 32 of the 64 output channels of their row, BN affine +
+//               and rows gathered one tile ahead), adds, LeakyReLU, TF32 hi/lo split, stores
+//               (2 stages), arrives on the stage's mbarrier.
+//   warp 12:    one thread issues 3 x 8 tcgen05.mma (3xTF32, K = 64) per tile against the resident
+//               W2 tile as soon as the stage is full and the accumulator buffer is drained
+//               (decoupled from the producers by mbarriers) and commits to an mbarrier.
+//   warps 0-3:  epilogue.  tcgen05.ld the 64 output channels of their row, BN affine +
 //               LeakyReLU, running max; after the last slot the row is written out.
 #include "common.cuh"
 #include "tc.cuh"
 
-#define ET_THREADS 512
+#define ET_THREADS 416  // warps 0-3 epilogue, 4-11 producers, 12 MMA issue
 #define ET_PRODUCERS 256
 #define ET_GROUP 128  // points per group (= MMA rows)
 
@@ -40,8 +42,10 @@ __global__ __launch_bounds__(ET_THREADS, 1) void edge_tc_kernel(
     float* __restrict__ Y, int ldy, RowMap map) {
   extern __shared__ __align__(128) unsigned char smem[];
   using S = EdgeTcSmem;
-  __shared__ uint64_t bar_full[2];
-  __shared__ uint64_t bar_tfree[2];
+  __shared__ uint64_t bar_full[2];   // accumulator b ready (also: operand stage b free again)
+  __shared__ uint64_t bar_tfree[2];  // accumulator b drained by the 128 epilogue threads
+  __shared__ float s_aff[128];       // BN scale (0..63) and shift (64..127) of the second conv
+  __shared__ uint64_t bar_sfull[2];  // operand stage b written by the 256 producer threads
   __shared__ uint32_t tmem_base_s;
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const int b = blockIdx.y;
@@ -56,11 +60,15 @@ __global__ __launch_bounds__(ET_THREADS, 1) void edge_tc_kernel(
   if (tid == 0) {
     tc::mbar_init(&bar_full[0], 1);
     tc::mbar_init(&bar_full[1], 1);
-    tc::mbar_init(&bar_tfree[0], 256);
-    tc::mbar_init(&bar_tfree[1], 256);
+    tc::mbar_init(&bar_tfree[0], 128);
+    tc::mbar_init(&bar_tfree[1], 128);
+    tc::mbar_init(&bar_sfull[0], ET_PRODUCERS);
+    tc::mbar_init(&bar_sfull[1], ET_PRODUCERS);
     tc::mbar_fence_init();
   }
   if (w == 0) tc::tmem_alloc(&tmem_base_s, 128);
+  if (tid < 64) s_aff[tid] = __ldg(s2 + tid);
+  else if (tid < 128) s_aff[tid] = __ldg(t2 + tid - 64);
   // resident W2 (64 x 64, row-major [c][kk] = K-major) as hi / lo tiles
   for (int c = tid; c < 64 * 16; c += ET_THREADS) {
     const int r = c >> 4, kc = c & 15;
@@ -80,9 +88,37 @@ __global__ __launch_bounds__(ET_THREADS, 1) void edge_tc_kernel(
     return;
   }
 
-  if (w >= 8) {
-    // --------------------------- producers + MMA issue --------------------------------------
-    const int lt = tid - 256;
+  if (w == 12) {
+    // --------------------------- MMA issue: its own warp ----------------------------------------
+    // (a producer thread issuing the MMAs holds its whole producer group at the tile barrier for
+    // as long as the tensor pipe takes to accept them, so staging and MMAs could not overlap)
+    if (lane == 0) {
+      const uint32_t wh = tc::smem_u32(smem + S::W_OFF), wl = wh + S::W_TILE;
+      const uint64_t dwh = tc::make_desc(wh, LBO_W, 128), dwl = tc::make_desc(wl, LBO_W, 128);
+      constexpr uint64_t KA = tc::desc_kstep(LBO_A), KW = tc::desc_kstep(LBO_W);
+      for (int u = 0; u < U; ++u) {
+        const int st = u & 1;
+        tc::mbar_wait(&bar_sfull[st], (u >> 1) & 1);                      // A tile staged
+        if (u >= 2) tc::mbar_wait(&bar_tfree[st], ((u >> 1) - 1) & 1);    // accumulator drained
+        tc::tc_fence_after();
+        const uint32_t ah = tc::smem_u32(smem + S::A_OFF + st * 2 * S::A_TILE), al = ah + S::A_TILE;
+        const uint32_t d = tmem_d + st * 64;
+        const uint64_t dah = tc::make_desc(ah, LBO_A, 128), dal = tc::make_desc(al, LBO_A, 128);
+        tc::mma_tf32_c<false>(d, dal, dwh, IDESC);
+        tc::mma_tf32_c<true>(d, dah, dwl, IDESC);
+        tc::mma_tf32_c<true>(d, dah, dwh, IDESC);
+#pragma unroll
+        for (int ks = 1; ks < 8; ++ks) {
+          tc::mma_tf32_c<true>(d, dal + ks * KA, dwh + ks * KW, IDESC);
+          tc::mma_tf32_c<true>(d, dah + ks * KA, dwl + ks * KW, IDESC);
+          tc::mma_tf32_c<true>(d, dah + ks * KA, dwh + ks * KW, IDESC);
+        }
+        tc::mma_commit(&bar_full[st]);
+      }
+    }
+  } else if (w >= 4) {
+    // --------------------------- producers -----------------------------------------------------
+    const int lt = tid - 128;
     constexpr int NCH = 128 * 16 / ET_PRODUCERS;  // 8 cells per thread: rows (lt>>4) + 16 i
     const int kc = lt & 15;
     const int r0 = lt >> 4;
@@ -153,63 +189,42 @@ __global__ __launch_bounds__(ET_THREADS, 1) void edge_tc_kernel(
         load_nb(u + 2);
       }
       tc::fence_async_smem();
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      if (lt == 0) {
-        if (u >= 2) tc::mbar_wait(&bar_tfree[st], ((u >> 1) - 1) & 1);  // accumulator drained
-        tc::tc_fence_after();
-        const uint32_t ah = tc::smem_u32(a_hi), al = ah + S::A_TILE;
-        const uint32_t wh = tc::smem_u32(smem + S::W_OFF), wl = wh + S::W_TILE;
-        const uint32_t d = tmem_d + st * 64;
-        const uint64_t dah = tc::make_desc(ah, LBO_A, 128), dal = tc::make_desc(al, LBO_A, 128);
-        const uint64_t dwh = tc::make_desc(wh, LBO_W, 128), dwl = tc::make_desc(wl, LBO_W, 128);
-        constexpr uint64_t KA = tc::desc_kstep(LBO_A), KW = tc::desc_kstep(LBO_W);
-        tc::mma_tf32_c<false>(d, dal, dwh, IDESC);
-        tc::mma_tf32_c<true>(d, dah, dwl, IDESC);
-        tc::mma_tf32_c<true>(d, dah, dwh, IDESC);
-#pragma unroll
-        for (int ks = 1; ks < 8; ++ks) {
-          tc::mma_tf32_c<true>(d, dal + ks * KA, dwh + ks * KW, IDESC);
-          tc::mma_tf32_c<true>(d, dah + ks * KA, dwl + ks * KW, IDESC);
-          tc::mma_tf32_c<true>(d, dah + ks * KA, dwh + ks * KW, IDESC);
-        }
-        tc::mma_commit(&bar_full[st]);
-      }
+      et_mbar_arrive(&bar_sfull[st]);
     }
   } else {
-    // --------------------------- epilogue: thread = (point row, channel half) -----------------
-    const int row = 32 * (w & 3) + lane;
-    const int ch0 = 32 * (w >> 2);
-    float sc[32], sh[32], mx[32];
-#pragma unroll
-    for (int c = 0; c < 32; ++c) {
-      sc[c] = __ldg(s2 + ch0 + c);
-      sh[c] = __ldg(t2 + ch0 + c);
-    }
+    // --------------------------- epilogue: thread = point row, all 64 channels ------------------
+    const int row = 32 * w + lane;
+    float mx[64];
     for (int u = 0; u < U; ++u) {
       const int st = u & 1;
       const int g = g_begin + u / k, j = u % k;
       if (j == 0) {
 #pragma unroll
-        for (int c = 0; c < 32; ++c) mx[c] = -INFINITY;
+        for (int c = 0; c < 64; ++c) mx[c] = -INFINITY;
       }
       tc::mbar_wait(&bar_full[st], (u >> 1) & 1);
       tc::tc_fence_after();
-      float v[32];
-      tc::tmem_ld32(tmem_d + ((uint32_t)(32 * (w & 3)) << 16) + (uint32_t)(st * 64 + ch0), v);
-      tc::tc_fence_before();
-      et_mbar_arrive(&bar_tfree[st]);
 #pragma unroll
-      for (int c = 0; c < 32; ++c) {
-        float y = fmaf(sc[c], v[c], sh[c]);
-        y = y > 0.f ? y : 0.2f * y;
-        mx[c] = fmaxf(mx[c], y);
+      for (int hh = 0; hh < 2; ++hh) {
+        float v[32];
+        tc::tmem_ld32(tmem_d + ((uint32_t)(32 * w) << 16) + (uint32_t)(st * 64 + 32 * hh), v);
+        if (hh == 1) {  // both halves are in registers: the accumulator buffer is free
+          tc::tc_fence_before();
+          et_mbar_arrive(&bar_tfree[st]);
+        }
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+          float y = fmaf(s_aff[32 * hh + c], v[c], s_aff[64 + 32 * hh + c]);
+          y = fmaxf(y, 0.2f * y);  // LeakyReLU(0.2)
+          mx[32 * hh + c] = fmaxf(mx[32 * hh + c], y);
+        }
       }
       if (j == k - 1) {
         const int p = g * ET_GROUP + row;
         if (p < N) {
-          float* y = Y + map(base + p) * (int64_t)ldy + ch0;
+          float* y = Y + map(base + p) * (int64_t)ldy;
 #pragma unroll
-          for (int c = 0; c < 32; c += 4)
+          for (int c = 0; c < 64; c += 4)
             *reinterpret_cast<float4*>(y + c) = make_float4(mx[c], mx[c + 1], mx[c + 2], mx[c + 3]);
         }
       }

@@ -329,6 +329,7 @@ __global__ __launch_bounds__(KT_THREADS, 1) void knn_tc_kernel(const float* __re
 #define K2_TC 64
 #define K2_CAP 56  // queue entries per selector thread; drained when fewer than 32 slots remain
 #define K2_G 32    // group maxima per selector thread (64 per row)
+#define K2_THREADS 416  // warps 0-7 selectors, 8-11 loaders, 12 MMA issue
 
 template <int KC4>
 struct Knn2Smem {
@@ -406,7 +407,7 @@ __device__ __forceinline__ void knn_keys32(float (&v)[32], float nq, const float
 }
 
 template <int KC4>
-__global__ __launch_bounds__(KT_THREADS, 1) void knn_tc2_kernel(const float* __restrict__ x, int ld,
+__global__ __launch_bounds__(K2_THREADS, 1) void knn_tc2_kernel(const float* __restrict__ x, int ld,
                                                                 int C, const float* __restrict__ xx,
                                                                 int N, int k,
                                                                 int32_t* __restrict__ idx32,
@@ -414,8 +415,9 @@ __global__ __launch_bounds__(KT_THREADS, 1) void knn_tc2_kernel(const float* __r
   constexpr int KL = 20;
   extern __shared__ __align__(128) unsigned char smem[];
   using S = Knn2Smem<KC4>;
-  __shared__ uint64_t bar_full[2];
-  __shared__ uint64_t bar_tfree[2];
+  __shared__ uint64_t bar_full[2];   // accumulator b ready = its MMAs done (also: operand stage b free)
+  __shared__ uint64_t bar_tfree[2];  // accumulator b drained by the 256 selector threads
+  __shared__ uint64_t bar_sfull[2];  // operand stage b written by the 128 loader threads
   __shared__ uint32_t tmem_base_s;
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const int b = blockIdx.y;
@@ -432,48 +434,36 @@ __global__ __launch_bounds__(KT_THREADS, 1) void knn_tc2_kernel(const float* __r
     tc::mbar_init(&bar_full[1], 1);
     tc::mbar_init(&bar_tfree[0], 256);
     tc::mbar_init(&bar_tfree[1], 256);
+    tc::mbar_init(&bar_sfull[0], 128);
+    tc::mbar_init(&bar_sfull[1], 128);
     tc::mbar_fence_init();
   }
   if (w == 0) tc::tmem_alloc(&tmem_base_s, 2 * K2_TC);
   knn_store_tile_r<KC4, 128>(smem + S::Q_OFF, smem + S::Q_OFF + S::TQ, x, ld, C, base + q0,
-                             base + N, tid, KT_THREADS, vec_ok);
+                             base + N, tid, K2_THREADS, vec_ok);
   tc::fence_async_smem();
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
   const uint32_t tmem_d = tmem_base_s;
 
-  if (w >= 8) {
-    // ------------------------------ loaders + MMA issue: every tile twice ---------------------
-    const int lt = tid - 256;
-    TileRegs<KC4, K2_TC, 128> tr;
-    float* xs = reinterpret_cast<float*>(smem + S::XS_OFF);
-    tile_load(tr, x, ld, C, base, base + N, lt, vec_ok);
-    float xn = (lt < K2_TC && lt < N) ? __ldg(xx + base + lt) : 0.f;
-    for (int j = 0; j < 2 * T; ++j) {
-      const int st = j & 1;
-      if (j >= 2) tc::mbar_wait(&bar_full[st], ((j >> 1) - 1) & 1);
-      unsigned char* hi = smem + S::B_OFF + st * 2 * S::TB;
-      unsigned char* lo = hi + S::TB;
-      tile_store(tr, hi, lo, lt);
-      if (lt < K2_TC) xs[(j & 3) * K2_TC + lt] = xn;  // ring of 4, see knn_tc_kernel
-      if (j + 1 < 2 * T) {
-        const int jn = j + 1 < T ? j + 1 : j + 1 - T;
-        tile_load(tr, x, ld, C, base + (int64_t)jn * K2_TC, base + N, lt, vec_ok);
-        const int cn_ = jn * K2_TC + lt;
-        xn = (lt < K2_TC && cn_ < N) ? __ldg(xx + base + cn_) : 0.f;
-      }
-      tc::fence_async_smem();
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (lt == 0) {
-        if (j >= 2) tc::mbar_wait(&bar_tfree[st], ((j >> 1) - 1) & 1);
+  if (w == 12) {
+    // ------------------------------ MMA issue: its own warp ------------------------------------
+    // (when a loader thread issued the MMAs, the loaders stood still for as long as the tensor
+    // pipe took to accept the 24 instructions of a tile, and the next tile's conversion could not
+    // overlap them: MMA and operand staging ran back to back instead of side by side)
+    if (lane == 0) {
+      const uint32_t q_hi = tc::smem_u32(smem + S::Q_OFF), q_lo = q_hi + S::TQ;
+      const uint64_t dqh = tc::make_desc(q_hi, LBOQ, 128), dql = tc::make_desc(q_lo, LBOQ, 128);
+      constexpr uint64_t KQ = tc::desc_kstep(LBOQ), KB = tc::desc_kstep(LBOB);
+      for (int j = 0; j < 2 * T; ++j) {
+        const int st = j & 1;
+        tc::mbar_wait(&bar_sfull[st], (j >> 1) & 1);                      // operands staged
+        if (j >= 2) tc::mbar_wait(&bar_tfree[st], ((j >> 1) - 1) & 1);    // accumulator drained
         tc::tc_fence_after();
-        const uint32_t q_hi = tc::smem_u32(smem + S::Q_OFF), q_lo = q_hi + S::TQ;
-        const uint32_t b_hi = tc::smem_u32(hi), b_lo = b_hi + S::TB;
+        const uint32_t b_hi = tc::smem_u32(smem + S::B_OFF + st * 2 * S::TB), b_lo = b_hi + S::TB;
         const uint32_t d = tmem_d + st * K2_TC;
-        const uint64_t dqh = tc::make_desc(q_hi, LBOQ, 128), dql = tc::make_desc(q_lo, LBOQ, 128);
         const uint64_t dbh = tc::make_desc(b_hi, LBOB, 128), dbl = tc::make_desc(b_lo, LBOB, 128);
-        constexpr uint64_t KQ = tc::desc_kstep(LBOQ), KB = tc::desc_kstep(LBOB);
         tc::mma_tf32_c<false>(d, dql, dbh, IDESC);
         tc::mma_tf32_c<true>(d, dqh, dbl, IDESC);
         tc::mma_tf32_c<true>(d, dqh, dbh, IDESC);
@@ -487,6 +477,29 @@ __global__ __launch_bounds__(KT_THREADS, 1) void knn_tc2_kernel(const float* __r
         }
         tc::mma_commit(&bar_full[st]);
       }
+    }
+  } else if (w >= 8) {
+    // ------------------------------ loaders: every tile twice ----------------------------------
+    const int lt = tid - 256;
+    TileRegs<KC4, K2_TC, 128> tr;
+    float* xs = reinterpret_cast<float*>(smem + S::XS_OFF);
+    tile_load(tr, x, ld, C, base, base + N, lt, vec_ok);
+    float xn = (lt < K2_TC && lt < N) ? __ldg(xx + base + lt) : 0.f;
+    for (int j = 0; j < 2 * T; ++j) {
+      const int st = j & 1;
+      if (j >= 2) tc::mbar_wait(&bar_full[st], ((j >> 1) - 1) & 1);  // stage's previous MMAs done
+      unsigned char* hi = smem + S::B_OFF + st * 2 * S::TB;
+      unsigned char* lo = hi + S::TB;
+      tile_store(tr, hi, lo, lt);
+      if (lt < K2_TC) xs[(j & 3) * K2_TC + lt] = xn;  // ring of 4, see knn_tc_kernel
+      if (j + 1 < 2 * T) {
+        const int jn = j + 1 < T ? j + 1 : j + 1 - T;
+        tile_load(tr, x, ld, C, base + (int64_t)jn * K2_TC, base + N, lt, vec_ok);
+        const int cn_ = jn * K2_TC + lt;
+        xn = (lt < K2_TC && cn_ < N) ? __ldg(xx + base + cn_) : 0.f;
+      }
+      tc::fence_async_smem();
+      mbar_arrive(&bar_sfull[st]);
     }
   } else {
     // ------------------------------ selectors ------------------------------------------------
@@ -628,7 +641,7 @@ static int launch_knn_tc2_t(const float* x, int ld, int C, const float* xx, int6
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
   if (e != cudaSuccess) return (int)e;
   dim3 grid((N + KT_TQ - 1) / KT_TQ, (unsigned)B);
-  knn_tc2_kernel<KC4><<<grid, KT_THREADS, S::TOTAL, st>>>(x, ld, C, xx, N, k, idx32, idx64);
+  knn_tc2_kernel<KC4><<<grid, K2_THREADS, S::TOTAL, st>>>(x, ld, C, xx, N, k, idx32, idx64);
   R3DFS_CHECK_LAUNCH();
   return 0;
 }
@@ -654,23 +667,13 @@ static bool knn_single_pass_forced() {  // A/B switch: R3DFS_KNN_SINGLE_PASS=1
   return v;
 }
 
-static bool knn_two_pass_forced() {
-  static const bool v = [] {
-    const char* e = getenv("R3DFS_KNN_TWO_PASS");
-    return e && e[0] == '1';
-  }();
-  return v;
-}
-
 // returns R3DFS_E_UNSUPPORTED for shapes the tensor-core kernel is not built for (C > 64)
 int launch_knn_tc(const float* x, int ld, int C, const float* xx, int64_t B, int N, int k,
                   int32_t* idx32, int64_t* idx64, cudaStream_t st) {
   if (k < 1 || k > 32 || C > 64 || N < k) return R3DFS_E_UNSUPPORTED;
-  // two-pass selection where the second GEMM is cheap (C <= 16: measured 2.56 vs 3.05 ms per 300
-  // clouds of 2048); at C = 64 the doubled operand conversion costs more than the selection saves
-  // (4.84 vs 3.5 ms).  R3DFS_KNN_TWO_PASS=1 forces it for every C (A/B measurements, tests).
-  if (k <= 20 && N >= 1024 && N <= 65535 && !knn_single_pass_forced() &&
-      (C <= 16 || knn_two_pass_forced())) {
+  // two-pass selection (measured per 300 clouds of 2048 points: C = 9: 2.03 vs 3.05 ms single
+  // pass, C = 64: 3.20 vs 3.43 ms); R3DFS_KNN_SINGLE_PASS=1 switches it off (A/B measurements).
+  if (k <= 20 && N >= 1024 && N <= 65535 && !knn_single_pass_forced()) {
     if (C <= 16) return launch_knn_tc2_t<4>(x, ld, C, xx, B, N, k, idx32, idx64, st);
     return launch_knn_tc2_t<16>(x, ld, C, xx, B, N, k, idx32, idx64, st);
   }
