@@ -3,8 +3,9 @@
 // Same math as tc_gemm.cu (3xTF32 tcgen05.mma, TMEM accumulator); the difference is the feed:
 //   - one thread issues cp.async.bulk.tensor (TMA) loads of raw FP32 tiles of X and W, 4 k-blocks
 //     ahead, completing on mbarriers — no registers and no thread is blocked on global memory;
-//   - all threads turn a landed raw tile into the TF32 hi / lo UMMA operand tiles (2 stages);
-//   - one thread issues the MMAs; tcgen05.commit releases the operand stage.
+//   - warps 0-7 turn a landed raw tile into the TF32 hi / lo UMMA operand tiles (2 stages) and
+//     hand the stage over through an mbarrier;
+//   - one thread of warp 8 issues the TMA loads and the MMAs; tcgen05.commit releases the stage.
 // Out-of-range rows / columns / k are zero-filled by the TMA unit itself.
 #include <cuda.h>
 
@@ -14,7 +15,8 @@
 #define TM_BM 128
 #define TM_BK 16
 #define TM_KC4 (TM_BK / 4)
-#define TM_THREADS 256
+#define TM_THREADS 256       // operand converters / epilogue (warps 0-7)
+#define TM_ALL_THREADS 288   // + warp 8: TMA and MMA issue
 #define TM_RAW_STAGES 2
 
 template <int BN>
@@ -45,7 +47,7 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 }
 
 template <int BN>
-__global__ __launch_bounds__(TM_THREADS, 2) void linear_tma_kernel(
+__global__ __launch_bounds__(TM_ALL_THREADS, 2) void linear_tma_kernel(
     const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
     const float* __restrict__ s, const float* __restrict__ t, int act, int64_t M, int K, int Nout,
     float* __restrict__ Y, int ldy, RowMap map) {
@@ -53,8 +55,9 @@ __global__ __launch_bounds__(TM_THREADS, 2) void linear_tma_kernel(
   using S = TmaSmem<BN>;
   unsigned char* smem = reinterpret_cast<unsigned char*>(
       (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  __shared__ uint64_t bar_full[TM_RAW_STAGES];
-  __shared__ uint64_t bar_mma[2];
+  __shared__ uint64_t bar_full[TM_RAW_STAGES];  // raw tile landed (TMA transaction bytes)
+  __shared__ uint64_t bar_mma[2];                // operand stage's MMAs done -> stage free
+  __shared__ uint64_t bar_op[2];                 // operand stage written by the 256 converters
   __shared__ uint32_t tmem_base_s;
   __shared__ float s_sc[BN], s_sh[BN];
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
@@ -75,6 +78,8 @@ __global__ __launch_bounds__(TM_THREADS, 2) void linear_tma_kernel(
     for (int i = 0; i < TM_RAW_STAGES; ++i) tc::mbar_init(&bar_full[i], 1);
     tc::mbar_init(&bar_mma[0], 1);
     tc::mbar_init(&bar_mma[1], 1);
+    tc::mbar_init(&bar_op[0], TM_THREADS);
+    tc::mbar_init(&bar_op[1], TM_THREADS);
     tc::mbar_fence_init();
   }
   if (w == 0) tc::tmem_alloc(&tmem_base_s, BN);
@@ -83,78 +88,93 @@ __global__ __launch_bounds__(TM_THREADS, 2) void linear_tma_kernel(
   tc::tc_fence_after();
   const uint32_t tmem_d = tmem_base_s;
 
-  auto issue_tma = [&](int kb) {  // thread 0 only
+  auto issue_tma = [&](int kb) {  // issue thread only
     const int rs = kb % TM_RAW_STAGES;
     unsigned char* ra = smem + S::RAW_OFF + rs * S::RAW_STAGE;
     mbar_expect_tx(&bar_full[rs], S::RAW_STAGE);
     tma_load_2d(ra, &tmX, kb * TM_BK, m0, &bar_full[rs]);
     tma_load_2d(ra + S::RAW_A, &tmW, kb * TM_BK, n0, &bar_full[rs]);
   };
-  if (tid == 0)
-    for (int kb = 0; kb < min(KB, TM_RAW_STAGES); ++kb) issue_tma(kb);
 
-  for (int kb = 0; kb < KB; ++kb) {
-    const int rs = kb % TM_RAW_STAGES, os = kb & 1;
-    tc::mbar_wait(&bar_full[rs], (kb / TM_RAW_STAGES) & 1);
-    const unsigned char* ra = smem + S::RAW_OFF + rs * S::RAW_STAGE;
-    const unsigned char* rb = ra + S::RAW_A;
-    float4 av[A_CH], bv[B_CH];
-#pragma unroll
-    for (int i = 0; i < A_CH; ++i) {
-      const int c = tid + i * TM_THREADS;  // raw tile is row-major [row][16 floats]
-      av[i] = *reinterpret_cast<const float4*>(ra + c * 16);
-    }
-#pragma unroll
-    for (int i = 0; i < B_CH; ++i) {
-      const int c = tid + i * TM_THREADS;
-      bv[i] = *reinterpret_cast<const float4*>(rb + c * 16);
-    }
-    if (kb >= 2) tc::mbar_wait(&bar_mma[os], ((kb >> 1) - 1) & 1);
-    unsigned char* a_hi = smem + S::OP_OFF + os * S::OP_STAGE;
-    unsigned char* a_lo = a_hi + S::OP_A;
-    unsigned char* b_hi = a_lo + S::OP_A;
-    unsigned char* b_lo = b_hi + S::OP_B;
-#pragma unroll
-    for (int i = 0; i < A_CH; ++i) {
-      const int c = tid + i * TM_THREADS;
-      const int r = c / TM_KC4, kc = c % TM_KC4;
-      float4 hi, lo;
-      tc::split4(av[i], hi, lo);
-      *reinterpret_cast<float4*>(a_hi + kc * LBO_A + r * 16) = hi;
-      *reinterpret_cast<float4*>(a_lo + kc * LBO_A + r * 16) = lo;
-    }
-#pragma unroll
-    for (int i = 0; i < B_CH; ++i) {
-      const int c = tid + i * TM_THREADS;
-      const int r = c / TM_KC4, kc = c % TM_KC4;
-      float4 hi, lo;
-      tc::split4(bv[i], hi, lo);
-      *reinterpret_cast<float4*>(b_hi + kc * LBO_B + r * 16) = hi;
-      *reinterpret_cast<float4*>(b_lo + kc * LBO_B + r * 16) = lo;
-    }
-    tc::fence_async_smem();
-    __syncthreads();  // operand stage complete; raw stage rs fully consumed
-    if (tid == 0) {
-      tc::tc_fence_after();
-      const uint32_t ah = tc::smem_u32(a_hi), al = tc::smem_u32(a_lo);
-      const uint32_t bh = tc::smem_u32(b_hi), bl = tc::smem_u32(b_lo);
-      const int ksteps = min(TM_BK, K - kb * TM_BK + 7) / 8;
-      for (int ks = 0; ks < ksteps; ++ks) {
-        const uint64_t dah = tc::make_desc(ah + ks * 2 * LBO_A, LBO_A, 128);
-        const uint64_t dal = tc::make_desc(al + ks * 2 * LBO_A, LBO_A, 128);
-        const uint64_t dbh = tc::make_desc(bh + ks * 2 * LBO_B, LBO_B, 128);
-        const uint64_t dbl = tc::make_desc(bl + ks * 2 * LBO_B, LBO_B, 128);
-        tc::mma_tf32(tmem_d, dal, dbh, IDESC, (kb | ks) != 0);
-        tc::mma_tf32(tmem_d, dah, dbl, IDESC, 1);
-        tc::mma_tf32(tmem_d, dah, dbh, IDESC, 1);
+  if (w == 8) {
+    // ---- TMA + MMA issue: one thread of its own warp, so the converters never stand still while
+    // the tensor pipe accepts a k-block's MMAs (they used to wait for the issuing thread at a
+    // CTA-wide barrier every k-block)
+    if (lane == 0) {
+      for (int kb = 0; kb < min(KB, TM_RAW_STAGES); ++kb) issue_tma(kb);
+      constexpr uint64_t KA = tc::desc_kstep(LBO_A), KBs = tc::desc_kstep(LBO_B);
+      for (int kb = 0; kb < KB; ++kb) {
+        const int os = kb & 1;
+        tc::mbar_wait(&bar_op[os], (kb >> 1) & 1);  // stage converted; raw stage kb fully read
+        tc::tc_fence_after();
+        if (kb + TM_RAW_STAGES < KB) issue_tma(kb + TM_RAW_STAGES);
+        unsigned char* a_hi = smem + S::OP_OFF + os * S::OP_STAGE;
+        const uint32_t ah = tc::smem_u32(a_hi), al = ah + S::OP_A;
+        const uint32_t bh = al + S::OP_A, bl = bh + S::OP_B;
+        const uint64_t dah = tc::make_desc(ah, LBO_A, 128), dal = tc::make_desc(al, LBO_A, 128);
+        const uint64_t dbh = tc::make_desc(bh, LBO_B, 128), dbl = tc::make_desc(bl, LBO_B, 128);
+        const int ksteps = min(TM_BK, K - kb * TM_BK + 7) / 8;
+        if (kb == 0) tc::mma_tf32_c<false>(tmem_d, dal, dbh, IDESC);
+        else tc::mma_tf32_c<true>(tmem_d, dal, dbh, IDESC);
+        tc::mma_tf32_c<true>(tmem_d, dah, dbl, IDESC);
+        tc::mma_tf32_c<true>(tmem_d, dah, dbh, IDESC);
+        if (ksteps > 1) {
+          tc::mma_tf32_c<true>(tmem_d, dal + KA, dbh + KBs, IDESC);
+          tc::mma_tf32_c<true>(tmem_d, dah + KA, dbl + KBs, IDESC);
+          tc::mma_tf32_c<true>(tmem_d, dah + KA, dbh + KBs, IDESC);
+        }
+        tc::mma_commit(&bar_mma[os]);
       }
-      tc::mma_commit(&bar_mma[os]);
-      if (kb + TM_RAW_STAGES < KB) issue_tma(kb + TM_RAW_STAGES);
+    }
+  } else {
+    // ---- converters: raw FP32 tile -> TF32 hi / lo UMMA operand tiles ----------------------------
+    for (int kb = 0; kb < KB; ++kb) {
+      const int rs = kb % TM_RAW_STAGES, os = kb & 1;
+      tc::mbar_wait(&bar_full[rs], (kb / TM_RAW_STAGES) & 1);
+      const unsigned char* ra = smem + S::RAW_OFF + rs * S::RAW_STAGE;
+      const unsigned char* rb = ra + S::RAW_A;
+      float4 av[A_CH], bv[B_CH];
+#pragma unroll
+      for (int i = 0; i < A_CH; ++i) {
+        const int c = tid + i * TM_THREADS;  // raw tile is row-major [row][16 floats]
+        av[i] = *reinterpret_cast<const float4*>(ra + c * 16);
+      }
+#pragma unroll
+      for (int i = 0; i < B_CH; ++i) {
+        const int c = tid + i * TM_THREADS;
+        bv[i] = *reinterpret_cast<const float4*>(rb + c * 16);
+      }
+      if (kb >= 2) tc::mbar_wait(&bar_mma[os], ((kb >> 1) - 1) & 1);
+      unsigned char* a_hi = smem + S::OP_OFF + os * S::OP_STAGE;
+      unsigned char* a_lo = a_hi + S::OP_A;
+      unsigned char* b_hi = a_lo + S::OP_A;
+      unsigned char* b_lo = b_hi + S::OP_B;
+#pragma unroll
+      for (int i = 0; i < A_CH; ++i) {
+        const int c = tid + i * TM_THREADS;
+        const int r = c / TM_KC4, kc = c % TM_KC4;
+        float4 hi, lo;
+        tc::split4(av[i], hi, lo);
+        *reinterpret_cast<float4*>(a_hi + kc * LBO_A + r * 16) = hi;
+        *reinterpret_cast<float4*>(a_lo + kc * LBO_A + r * 16) = lo;
+      }
+#pragma unroll
+      for (int i = 0; i < B_CH; ++i) {
+        const int c = tid + i * TM_THREADS;
+        const int r = c / TM_KC4, kc = c % TM_KC4;
+        float4 hi, lo;
+        tc::split4(bv[i], hi, lo);
+        *reinterpret_cast<float4*>(b_hi + kc * LBO_B + r * 16) = hi;
+        *reinterpret_cast<float4*>(b_lo + kc * LBO_B + r * 16) = lo;
+      }
+      tc::fence_async_smem();
+      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc::smem_u32(&bar_op[os]))
+                   : "memory");
     }
   }
   tc::mbar_wait(&bar_mma[(KB - 1) & 1], ((KB - 1) >> 1) & 1);
   tc::tc_fence_after();
-  {
+  if (w < 8) {
     // all MMAs are complete, so the operand stages are free: reuse them as per-warp transpose
     // buffers for coalesced stores
     float* wbuf = reinterpret_cast<float*>(smem + S::OP_OFF) + w * (32 * 33);
@@ -222,7 +242,7 @@ static int launch_tma_bn(const CUtensorMap& tx, const CUtensorMap& tw, const flo
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
   if (e != cudaSuccess) return (int)e;
   dim3 grid((unsigned)((M + TM_BM - 1) / TM_BM), (Nout + BN - 1) / BN);
-  linear_tma_kernel<BN><<<grid, TM_THREADS, S::TOTAL, st>>>(tx, tw, s, t, act, M, K, Nout, Y, ldy,
+  linear_tma_kernel<BN><<<grid, TM_ALL_THREADS, S::TOTAL, st>>>(tx, tw, s, t, act, M, K, Nout, Y, ldy,
                                                             map);
   R3DFS_CHECK_LAUNCH();
   return 0;
