@@ -6,10 +6,13 @@
 //   sweep 2:  S again (bit-identical), P = exp(S - m) written as a K-major UMMA A tile (hi/lo),
 //             l += rowsum(P),  O += P V  with V^T staged as the K-major B tile; O stays in TMEM.
 // Knowing m before the second sweep means O never has to be rescaled inside TMEM.
-// Sweep 1 is normally SKIPPED: softmax is shift invariant, so any m' >= max_j S_ij works as long as
-// exp(S - m') stays in the normal FP32 range.  m' = |q_i / 8| * max_j |k_j| (Cauchy-Schwarz, the
-// per-cloud key-norm maximum comes from a small pre-kernel) is used when it is <= 60 for every row
-// of the CTA (exp(-60) = 9e-27, far above FP32's 1e-38); otherwise the CTA runs the exact sweep.
+// Softmax is shift invariant, so sweep 1 only has to deliver SOME m' >= max_j S_ij that keeps
+// exp(S - m') in the normal FP32 range:
+//   - if b = |q_i / 8| * max_j |k_j| (Cauchy-Schwarz; the per-cloud key-norm maximum comes from a
+//     small pre-kernel) is <= 60 for every row of the CTA, m' = b and sweep 1 is skipped
+//     (exp(-60) = 9e-27 is far above FP32's 1e-38);
+//   - otherwise sweep 1 runs with ONE TF32 product per k-step (Qhi.Khi, a third of the MMAs, no lo
+//     tiles) and m' = its row maximum + 2^-10 b, which bounds what the dropped products can add.
 // The (N, N) attention map exists only as 128 x 64 tiles in TMEM / shared memory.
 #include "common.cuh"
 #include "tc.cuh"
@@ -54,6 +57,19 @@ __device__ __forceinline__ void at_store_rows(const float4 (&v)[2], unsigned cha
     tc::split4(v[i], h, l);
     *reinterpret_cast<float4*>(hi + kc * LBO + r * 16) = h;
     *reinterpret_cast<float4*>(lo + kc * LBO + r * 16) = l;
+  }
+}
+// TF32 hi parts only (the approximate first sweep does not need the lo tile)
+__device__ __forceinline__ void at_store_rows_hi(const float4 (&v)[2], unsigned char* hi, int tid) {
+  constexpr int LBO = tc::tile_lbo(64);
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int c = tid + i * AT_THREADS;
+    const int r = c >> 4, kc = c & 15;
+    float4 h;
+    h.x = tc::tf32_rn(v[i].x); h.y = tc::tf32_rn(v[i].y);
+    h.z = tc::tf32_rn(v[i].z); h.w = tc::tf32_rn(v[i].w);
+    *reinterpret_cast<float4*>(hi + kc * LBO + r * 16) = h;
   }
 }
 // V rows (keys) -> V^T tile: element (d, key) at (key/4)*LBO + d*16 + (key%4)*4
@@ -185,11 +201,21 @@ __global__ __launch_bounds__(AT_THREADS, 1) void attention_tc_kernel(const float
     tc::mma_commit(&bar_s);
   };
 
+  auto issue_s_hi = [&]() {  // S ~= Qhi . Khi^T only (1 of the 3 TF32 products): row-max estimate
+    const uint64_t dqh = tc::make_desc(q_hi, LBO_Q, 128), dkh = tc::make_desc(k_hi, LBO_K, 128);
+    constexpr uint64_t KQ = tc::desc_kstep(LBO_Q), KK = tc::desc_kstep(LBO_K);
+    tc::mma_tf32_c<false>(tmem_s, dqh, dkh, IDESC);
+#pragma unroll
+    for (int ks = 1; ks < 8; ++ks) tc::mma_tf32_c<true>(tmem_s, dqh + ks * KQ, dkh + ks * KK, IDESC);
+    tc::mma_commit(&bar_s);
+  };
+
   uint32_t ph_s = 0, ph_pv = 0;
   // ---------------- row bound m' = |q/8| max|k| (or exact row maxima when the bound is too loose) ---
-  float m_row;
-  bool exact = kmax2 == nullptr;
-  if (!exact) {
+  float m_row = 0.f, margin = 0.f;
+  bool sweep1 = true;              // run a first sweep for the row maxima?
+  const bool approx = kmax2 != nullptr;  // ... with single-TF32 MMAs (needs the norm bound)
+  if (approx) {
     float qs = 0.f;
     if (q0 + row < N) {
       const float4* qp =
@@ -207,24 +233,29 @@ __global__ __launch_bounds__(AT_THREADS, 1) void attention_tc_kernel(const float
     xch[quarter * 128 + row] = qs;
     __syncthreads();
     const float q2 = (xch[row] + xch[128 + row]) + (xch[256 + row] + xch[384 + row]);
-    // 1e-4 relative + 1e-6 absolute slack covers the rounding of the norms and of the 3xTF32 S
+    // |q_i / 8| max_j |k_j| >= max_j S_ij (Cauchy-Schwarz); 1e-4 relative + 1e-6 absolute slack
+    // covers the rounding of the norms and of the 3xTF32 S
     m_row = sqrtf(q2) * sqrtf(__ldg(kmax2 + b)) * 1.0001f + 1e-6f;
-    exact = __syncthreads_or(!(m_row <= 60.f));
+    // Qhi.Khi drops q_lo.k + q_hi.k_lo: |error| <= 2 * 2^-11 |q||k|  (TF32 rounding is 2^-11 relative)
+    margin = m_row * (1.0f / 1024.0f) * 1.01f + 1e-6f;
+    sweep1 = __syncthreads_or(!(m_row <= 60.f));
   }
-  if (exact) {
-    // ---------------- sweep 1: row maxima -----------------------------------------------------
+  if (sweep1) {
+    // ---------------- sweep 1: row maxima (approximate + safety margin, or exact) ----------------
     float m_run = -INFINITY;
     {
       float4 kv[2];
       at_load_rows(kv, qkv, ld, base, base + N, 64, tid);
       for (int j = 0; j < T; ++j) {
-        at_store_rows(kv, k_hi_p, k_lo_p, tid);
+        if (approx) at_store_rows_hi(kv, k_hi_p, tid);
+        else at_store_rows(kv, k_hi_p, k_lo_p, tid);
         tc::fence_async_smem();
         tc::tc_fence_before();
         __syncthreads();  // K tile complete; everybody has finished reading S of the previous tile
         if (tid == 0) {
           tc::tc_fence_after();
-          issue_s();
+          if (approx) issue_s_hi();
+          else issue_s();
         }
         if (j + 1 < T) at_load_rows(kv, qkv, ld, base + (int64_t)(j + 1) * AT_BK, base + N, 64, tid);
         tc::mbar_wait(&bar_s, ph_s);
@@ -243,7 +274,7 @@ __global__ __launch_bounds__(AT_THREADS, 1) void attention_tc_kernel(const float
     xch[quarter * 128 + row] = m_run;
     tc::tc_fence_before();
     __syncthreads();
-    m_row = fmaxf(fmaxf(xch[row], xch[128 + row]), fmaxf(xch[256 + row], xch[384 + row]));
+    m_row = fmaxf(fmaxf(xch[row], xch[128 + row]), fmaxf(xch[256 + row], xch[384 + row])) + margin;
   }
   __syncthreads();
 
