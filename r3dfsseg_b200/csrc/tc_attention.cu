@@ -17,7 +17,8 @@
 #include "common.cuh"
 #include "tc.cuh"
 
-#define AT_THREADS 512  // 16 warps: TMEM lane quarter = w % 4, 16-column quarter = w / 4
+#define AT_THREADS 512  // 16 worker warps: TMEM lane quarter = w % 4, 16-column quarter = w / 4
+#define AT_ALL_THREADS 544  // + warp 16: MMA issue
 #define AT_BQ 128
 #define AT_BK 64
 
@@ -134,7 +135,7 @@ __global__ __launch_bounds__(256) void att_kmax_kernel(const float* __restrict__
   }
 }
 
-__global__ __launch_bounds__(AT_THREADS, 1) void attention_tc_kernel(const float* __restrict__ qkv,
+__global__ __launch_bounds__(AT_ALL_THREADS, 1) void attention_tc_kernel(const float* __restrict__ qkv,
                                                                      int ld, int N,
                                                                      float* __restrict__ Y, int ldy,
                                                                      RowMap map,
@@ -159,9 +160,9 @@ __global__ __launch_bounds__(AT_THREADS, 1) void attention_tc_kernel(const float
     tc::mbar_init(&bar_pv, 1);
     tc::mbar_fence_init();
   }
-  if (w == 0) tc::tmem_alloc(&tmem_base_s, 128);
+  if (w == 0) tc::tmem_alloc(&tmem_base_s, 256);  // S0 | S1 | O | (unused)
   // Q tile (pre-divided by the temperature 8 = sqrt(64), exactly as the reference does)
-  for (int c = tid; c < 128 * 16; c += AT_THREADS) {
+  for (int c = tid; c < 128 * 16; c += AT_ALL_THREADS) {
     const int r = c >> 4, kc = c & 15;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
     if (q0 + r < N) v = *reinterpret_cast<const float4*>(qkv + (base + q0 + r) * (int64_t)ld + 4 * kc);
@@ -175,7 +176,9 @@ __global__ __launch_bounds__(AT_THREADS, 1) void attention_tc_kernel(const float
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
-  const uint32_t tmem_s = tmem_base_s, tmem_o = tmem_base_s + 64;
+  const uint32_t tmem_s = tmem_base_s, tmem_o = tmem_base_s + 128;
+  const bool worker = w < 16;             // warps 0-15 move data; warp 16 only issues MMAs
+  const bool issuer = tid == AT_THREADS;  // lane 0 of warp 16
   const uint32_t q_hi = tc::smem_u32(smem + S::Q_OFF), q_lo = q_hi + S::Q_TILE;
   unsigned char* k_hi_p = smem + S::K_OFF;
   unsigned char* k_lo_p = k_hi_p + S::K_TILE;
@@ -187,7 +190,7 @@ __global__ __launch_bounds__(AT_THREADS, 1) void attention_tc_kernel(const float
   const uint32_t v_hi = tc::smem_u32(v_hi_p), v_lo = tc::smem_u32(v_lo_p);
   const uint32_t p_hi = tc::smem_u32(p_hi_p), p_lo = tc::smem_u32(p_lo_p);
 
-  auto issue_s = [&]() {  // S[128 x 64] = Q . K^T  (K = 64 -> 8 k-steps)
+  auto issue_s = [&](uint32_t tmem_s) {  // S[128 x 64] = Q . K^T  (K = 64 -> 8 k-steps)
 #pragma unroll 1
     for (int ks = 0; ks < 8; ++ks) {
       const uint64_t dqh = tc::make_desc(q_hi + ks * 2 * LBO_Q, LBO_Q, 128);
@@ -217,7 +220,7 @@ __global__ __launch_bounds__(AT_THREADS, 1) void attention_tc_kernel(const float
   const bool approx = kmax2 != nullptr;  // ... with single-TF32 MMAs (needs the norm bound)
   if (approx) {
     float qs = 0.f;
-    if (q0 + row < N) {
+    if (worker && q0 + row < N) {
       const float4* qp =
           reinterpret_cast<const float4*>(qkv + (base + q0 + row) * (int64_t)ld + 16 * quarter);
 #pragma unroll
@@ -230,9 +233,10 @@ __global__ __launch_bounds__(AT_THREADS, 1) void attention_tc_kernel(const float
         qs = fmaf(v.w, v.w, qs);
       }
     }
-    xch[quarter * 128 + row] = qs;
+    if (worker) xch[quarter * 128 + row] = qs;
     __syncthreads();
-    const float q2 = (xch[row] + xch[128 + row]) + (xch[256 + row] + xch[384 + row]);
+    const int xr = worker ? row : 0;
+    const float q2 = (xch[xr] + xch[128 + xr]) + (xch[256 + xr] + xch[384 + xr]);
     // |q_i / 8| max_j |k_j| >= max_j S_ij (Cauchy-Schwarz); 1e-4 relative + 1e-6 absolute slack
     // covers the rounding of the norms and of the 3xTF32 S
     m_row = sqrtf(q2) * sqrtf(__ldg(kmax2 + b)) * 1.0001f + 1e-6f;
@@ -245,110 +249,144 @@ __global__ __launch_bounds__(AT_THREADS, 1) void attention_tc_kernel(const float
     float m_run = -INFINITY;
     {
       float4 kv[2];
-      at_load_rows(kv, qkv, ld, base, base + N, 64, tid);
+      if (worker) at_load_rows(kv, qkv, ld, base, base + N, 64, tid);
       for (int j = 0; j < T; ++j) {
-        if (approx) at_store_rows_hi(kv, k_hi_p, tid);
-        else at_store_rows(kv, k_hi_p, k_lo_p, tid);
+        if (worker) {
+          if (approx) at_store_rows_hi(kv, k_hi_p, tid);
+          else at_store_rows(kv, k_hi_p, k_lo_p, tid);
+        }
         tc::fence_async_smem();
         tc::tc_fence_before();
         __syncthreads();  // K tile complete; everybody has finished reading S of the previous tile
-        if (tid == 0) {
+        if (issuer) {
           tc::tc_fence_after();
           if (approx) issue_s_hi();
-          else issue_s();
+          else issue_s(tmem_s);
         }
-        if (j + 1 < T) at_load_rows(kv, qkv, ld, base + (int64_t)(j + 1) * AT_BK, base + N, 64, tid);
+        if (worker && j + 1 < T)
+          at_load_rows(kv, qkv, ld, base + (int64_t)(j + 1) * AT_BK, base + N, 64, tid);
         tc::mbar_wait(&bar_s, ph_s);
         ph_s ^= 1;
         tc::tc_fence_after();
-        float v[16];
-        tc::tmem_ld16(tmem_s + ((uint32_t)(32 * (w & 3)) << 16) + (uint32_t)(16 * quarter), v);
-        const int c0 = j * AT_BK + 16 * quarter;
+        if (worker) {
+          float v[16];
+          tc::tmem_ld16(tmem_s + ((uint32_t)(32 * (w & 3)) << 16) + (uint32_t)(16 * quarter), v);
+          const int c0 = j * AT_BK + 16 * quarter;
 #pragma unroll
-        for (int e = 0; e < 16; ++e)
-          if (c0 + e < N) m_run = fmaxf(m_run, v[e]);
+          for (int e = 0; e < 16; ++e)
+            if (c0 + e < N) m_run = fmaxf(m_run, v[e]);
+        }
       }
     }
     // combine the four column quarters of every row
     __syncthreads();
-    xch[quarter * 128 + row] = m_run;
+    if (worker) xch[quarter * 128 + row] = m_run;
     tc::tc_fence_before();
     __syncthreads();
-    m_row = fmaxf(fmaxf(xch[row], xch[128 + row]), fmaxf(xch[256 + row], xch[384 + row])) + margin;
+    const int xr = worker ? row : 0;
+    m_row = fmaxf(fmaxf(xch[xr], xch[128 + xr]), fmaxf(xch[256 + xr], xch[384 + xr])) + margin;
   }
   __syncthreads();
 
   // ---------------- sweep 2: P = exp(S - m), l, O += P V ---------------------------------------
+  // Software pipeline over the key tiles: S lives in two TMEM buffers, so S(j+1) = Q K(j+1)^T is
+  // issued as soon as S(j) has landed (which also frees the K tile) and runs on the tensor pipe
+  // while the workers turn S(j) into P(j); P(j).V(j) is queued behind it.  The tensor pipe then
+  // always has the next MMA batch waiting: per tile it is busy for both GEMMs back to back.
   float l_run = 0.f;
   {
     float4 kv[2], vv[2];
-    at_load_rows(kv, qkv, ld, base, base + N, 64, tid);
-    at_load_v(vv, qkv, ld, base, base + N, tid);
+    if (worker) {
+      at_load_rows(kv, qkv, ld, base, base + N, 64, tid);
+      at_load_v(vv, qkv, ld, base, base + N, tid);
+      at_store_rows(kv, k_hi_p, k_lo_p, tid);
+      if (T > 1) at_load_rows(kv, qkv, ld, base + AT_BK, base + N, 64, tid);
+    }
+    tc::fence_async_smem();
+    tc::tc_fence_before();
+    __syncthreads();
+    if (issuer) {
+      tc::tc_fence_after();
+      issue_s(tmem_s);
+    }
     for (int j = 0; j < T; ++j) {
-      // K, V^T and P buffers are free once the previous tile's P.V MMAs have completed
+      const uint32_t s_cur = tmem_s + (uint32_t)((j & 1) * 64);
+      tc::mbar_wait(&bar_s, ph_s);  // S(j) complete: its K tile is free
+      ph_s ^= 1;
+      tc::tc_fence_after();
+      if (worker && j + 1 < T) at_store_rows(kv, k_hi_p, k_lo_p, tid);  // K(j+1)
+      tc::fence_async_smem();
+      tc::tc_fence_before();
+      __syncthreads();
+      if (issuer && j + 1 < T) {
+        tc::tc_fence_after();
+        issue_s(tmem_s + (uint32_t)(((j + 1) & 1) * 64));
+      }
+      float4 pv4[4];
+      if (worker) {
+        if (j + 2 < T)
+          at_load_rows(kv, qkv, ld, base + (int64_t)(j + 2) * AT_BK, base + N, 64, tid);
+        float v[16];
+        tc::tmem_ld16(s_cur + ((uint32_t)(32 * (w & 3)) << 16) + (uint32_t)(16 * quarter), v);
+        const int c0 = j * AT_BK + 16 * quarter;
+#pragma unroll
+        for (int e = 0; e < 16; e += 4) {
+          float4 p;
+          p.x = (c0 + e + 0 < N) ? expf(v[e + 0] - m_row) : 0.f;
+          p.y = (c0 + e + 1 < N) ? expf(v[e + 1] - m_row) : 0.f;
+          p.z = (c0 + e + 2 < N) ? expf(v[e + 2] - m_row) : 0.f;
+          p.w = (c0 + e + 3 < N) ? expf(v[e + 3] - m_row) : 0.f;
+          l_run += (p.x + p.y) + (p.z + p.w);
+          pv4[e >> 2] = p;
+        }
+      }
+      // V^T and P buffers are free once the previous tile's P.V MMAs have completed
       if (j > 0) {
         tc::mbar_wait(&bar_pv, ph_pv);
         ph_pv ^= 1;
       }
-      at_store_rows(kv, k_hi_p, k_lo_p, tid);
-      at_store_vT(vv, v_hi_p, v_lo_p, tid);
-      tc::fence_async_smem();
-      tc::tc_fence_before();
-      __syncthreads();
-      if (tid == 0) {
-        tc::tc_fence_after();
-        issue_s();
-      }
-      if (j + 1 < T) {
-        at_load_rows(kv, qkv, ld, base + (int64_t)(j + 1) * AT_BK, base + N, 64, tid);
-        at_load_v(vv, qkv, ld, base + (int64_t)(j + 1) * AT_BK, base + N, tid);
-      }
-      tc::mbar_wait(&bar_s, ph_s);
-      ph_s ^= 1;
-      tc::tc_fence_after();
-      float v[16];
-      tc::tmem_ld16(tmem_s + ((uint32_t)(32 * (w & 3)) << 16) + (uint32_t)(16 * quarter), v);
-      const int c0 = j * AT_BK + 16 * quarter;
+      if (worker) {
+        at_store_vT(vv, v_hi_p, v_lo_p, tid);
+        if (j + 1 < T) at_load_v(vv, qkv, ld, base + (int64_t)(j + 1) * AT_BK, base + N, tid);
 #pragma unroll
-      for (int e = 0; e < 16; e += 4) {
-        float4 p;
-        p.x = (c0 + e + 0 < N) ? expf(v[e + 0] - m_row) : 0.f;
-        p.y = (c0 + e + 1 < N) ? expf(v[e + 1] - m_row) : 0.f;
-        p.z = (c0 + e + 2 < N) ? expf(v[e + 2] - m_row) : 0.f;
-        p.w = (c0 + e + 3 < N) ? expf(v[e + 3] - m_row) : 0.f;
-        l_run += (p.x + p.y) + (p.z + p.w);
-        float4 h, l;
-        tc::split4(p, h, l);
-        const int kc = (16 * quarter + e) >> 2;  // 16-byte chunk along the key dimension
-        *reinterpret_cast<float4*>(p_hi_p + kc * LBO_Q + row * 16) = h;
-        *reinterpret_cast<float4*>(p_lo_p + kc * LBO_Q + row * 16) = l;
+        for (int e = 0; e < 16; e += 4) {
+          float4 h, l;
+          tc::split4(pv4[e >> 2], h, l);
+          const int kc = (16 * quarter + e) >> 2;  // 16-byte chunk along the key dimension
+          *reinterpret_cast<float4*>(p_hi_p + kc * LBO_Q + row * 16) = h;
+          *reinterpret_cast<float4*>(p_lo_p + kc * LBO_Q + row * 16) = l;
+        }
       }
       tc::fence_async_smem();
       tc::tc_fence_before();
-      __syncthreads();  // P complete, S consumed
-      if (tid == 0) {
+      __syncthreads();  // P and V^T complete, S(j) consumed
+      if (issuer) {
         tc::tc_fence_after();
-#pragma unroll 1
-        for (int ks = 0; ks < 8; ++ks) {  // O[128 x 64] += P[128 x 64 keys] . V[64 keys x 64]
-          const uint64_t dph = tc::make_desc(p_hi + ks * 2 * LBO_Q, LBO_Q, 128);
-          const uint64_t dpl = tc::make_desc(p_lo + ks * 2 * LBO_Q, LBO_Q, 128);
-          const uint64_t dvh = tc::make_desc(v_hi + ks * 2 * LBO_K, LBO_K, 128);
-          const uint64_t dvl = tc::make_desc(v_lo + ks * 2 * LBO_K, LBO_K, 128);
-          tc::mma_tf32(tmem_o, dpl, dvh, IDESC, (j | ks) != 0);
-          tc::mma_tf32(tmem_o, dph, dvl, IDESC, 1);
-          tc::mma_tf32(tmem_o, dph, dvh, IDESC, 1);
+        const uint64_t dph = tc::make_desc(p_hi, LBO_Q, 128), dpl = tc::make_desc(p_lo, LBO_Q, 128);
+        const uint64_t dvh = tc::make_desc(v_hi, LBO_K, 128), dvl = tc::make_desc(v_lo, LBO_K, 128);
+        constexpr uint64_t KP = tc::desc_kstep(LBO_Q), KV = tc::desc_kstep(LBO_K);
+        // O[128 x 64] += P[128 x 64 keys] . V[64 keys x 64]
+        if (j == 0) tc::mma_tf32_c<false>(tmem_o, dpl, dvh, IDESC);
+        else tc::mma_tf32_c<true>(tmem_o, dpl, dvh, IDESC);
+        tc::mma_tf32_c<true>(tmem_o, dph, dvl, IDESC);
+        tc::mma_tf32_c<true>(tmem_o, dph, dvh, IDESC);
+#pragma unroll
+        for (int ks = 1; ks < 8; ++ks) {
+          tc::mma_tf32_c<true>(tmem_o, dpl + ks * KP, dvh + ks * KV, IDESC);
+          tc::mma_tf32_c<true>(tmem_o, dph + ks * KP, dvl + ks * KV, IDESC);
+          tc::mma_tf32_c<true>(tmem_o, dph + ks * KP, dvh + ks * KV, IDESC);
         }
         tc::mma_commit(&bar_pv);
       }
     }
   }
   // ---------------- epilogue: O / l ------------------------------------------------------------
-  xch[quarter * 128 + row] = l_run;
+  if (worker) xch[quarter * 128 + row] = l_run;
   tc::mbar_wait(&bar_pv, ph_pv);
   tc::tc_fence_after();
   __syncthreads();
-  const float inv = 1.f / ((xch[row] + xch[128 + row]) + (xch[256 + row] + xch[384 + row]));
-  {
+  if (worker) {
+    const float inv = 1.f / ((xch[row] + xch[128 + row]) + (xch[256 + row] + xch[384 + row]));
     float v[16];
     tc::tmem_ld16(tmem_o + ((uint32_t)(32 * (w & 3)) << 16) + (uint32_t)(16 * quarter), v);
     const int q = q0 + row;
@@ -362,7 +400,7 @@ __global__ __launch_bounds__(AT_THREADS, 1) void attention_tc_kernel(const float
   }
   tc::tc_fence_before();
   __syncthreads();
-  if (w == 0) tc::tmem_dealloc(tmem_base_s, 128);
+  if (w == 0) tc::tmem_dealloc(tmem_base_s, 256);
 }
 
 // kmax_ws: B floats of scratch for the per-cloud key-norm maxima; nullptr -> always two sweeps
@@ -378,7 +416,7 @@ int launch_attention_tc(const float* qkv, int ld, int64_t B, int N, float* Y, in
                                        AttTcSmem::TOTAL);
   if (e != cudaSuccess) return (int)e;
   dim3 grid((N + AT_BQ - 1) / AT_BQ, (unsigned)B);
-  attention_tc_kernel<<<grid, AT_THREADS, AttTcSmem::TOTAL, st>>>(qkv, ld, N, Y, ldy, map,
+  attention_tc_kernel<<<grid, AT_ALL_THREADS, AttTcSmem::TOTAL, st>>>(qkv, ld, N, Y, ldy, map,
                                                                   kmax_ws);
   R3DFS_CHECK_LAUNCH();
   return 0;
