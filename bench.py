@@ -464,6 +464,9 @@ def main():
         else:
             ent["gbs"] = round(wk["bytes"] / (ms * 1e-3) / 1e9, 2)
             ent["frac"] = round(ent["gbs"] / peaks["hbm_gbs"], 5)
+            if name in ("sim", "cg", "fps"):
+                ent["note"] = "algorithmic bytes are L2-level (re-swept / gathered data that partly " \
+                              "or wholly stays in L2); frac is relative to the HBM copy peak"
         stages[name] = ent
     # dominant KERNEL = the kernel with the largest summed device time per call (several stages
     # are launches of the same kernel)
