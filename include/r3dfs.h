@@ -59,9 +59,14 @@ int r3dfs_knn_ex(const float* x, int64_t B, int64_t C, int64_t N, int64_t sb, in
                  r3dfs_stream_t stream);
 
 /* get_edge_feature(x, K, idx) — models/dgcnn.py:26-42.  Materialises the (B, 2C, N, K)
- * contiguous edge tensor cat(x_j - x_i, x_i).  idx: (B, N, K) int64 contiguous. */
+ * contiguous edge tensor cat(x_j - x_i, x_i).  idx: (B, N, K) int64 contiguous.
+ * ws (optional, may be NULL / 0): r3dfs_edge_feature_workspace() bytes of scratch; with it a
+ * channel-major x is first brought into point-major form so that the neighbour gathers read whole
+ * rows (a point-major x behind a transposed view — the reference's collate layout — needs none). */
+size_t r3dfs_edge_feature_workspace(int64_t B, int64_t C, int64_t N);
 int r3dfs_edge_feature(const float* x, int64_t B, int64_t C, int64_t N, int64_t sb, int64_t sc,
-                       int64_t sn, const int64_t* idx, int K, float* out, r3dfs_stream_t stream);
+                       int64_t sn, const int64_t* idx, int K, float* out, void* ws, size_t ws_bytes,
+                       r3dfs_stream_t stream);
 
 /* Weights of the episode model, eval mode.  Every BatchNorm is folded by the host into a
  * per-channel (scale, shift) pair: y = act(scale * (W x) + shift)  (conv bias folded into shift).

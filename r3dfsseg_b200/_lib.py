@@ -69,7 +69,8 @@ SIGNATURES = {
     "r3dfs_knn_workspace": (sz, [i64, i64, i64, i32]),
     "r3dfs_knn": (C.c_int, [vp, i64, i64, i64, i64, i64, i64, i32, vp, vp, sz, vp]),
     "r3dfs_knn_ex": (C.c_int, [vp, i64, i64, i64, i64, i64, i64, i32, vp, i32, vp, sz, vp]),
-    "r3dfs_edge_feature": (C.c_int, [vp, i64, i64, i64, i64, i64, i64, vp, i32, vp, vp]),
+    "r3dfs_edge_feature_workspace": (sz, [i64, i64, i64]),
+    "r3dfs_edge_feature": (C.c_int, [vp, i64, i64, i64, i64, i64, i64, vp, i32, vp, vp, sz, vp]),
     "r3dfs_linear": (C.c_int, [vp, i64, vp, vp, vp, i32, i64, i64, i64, vp, i64, vp]),
     "r3dfs_linear_ex": (C.c_int, [vp, i64, vp, vp, vp, i32, i64, i64, i64, vp, i64, i32, vp]),
     "r3dfs_edgeconv_workspace": (sz, [i64, i64, i64, i32]),

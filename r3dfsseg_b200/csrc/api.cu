@@ -243,12 +243,17 @@ int r3dfs_knn_ex(const float* x, int64_t B, int64_t C, int64_t N, int64_t sb, in
 }
 
 // ---- get_edge_feature --------------------------------------------------------------------------
+size_t r3dfs_edge_feature_workspace(int64_t B, int64_t C, int64_t N) {
+  return edge_feature_scratch_bytes(B, C, N);
+}
+
 int r3dfs_edge_feature(const float* x, int64_t B, int64_t C, int64_t N, int64_t sb, int64_t sc,
-                       int64_t sn, const int64_t* idx, int K, float* out, r3dfs_stream_t stream) {
+                       int64_t sn, const int64_t* idx, int K, float* out, void* ws, size_t ws_bytes,
+                       r3dfs_stream_t stream) {
   if (!x || !idx || !out || B <= 0 || C <= 0 || N <= 0 || K <= 0) return R3DFS_E_BADARG;
   if (C > 65535 || B > 65535) return R3DFS_E_UNSUPPORTED;
   if (((uintptr_t)out & 15) != 0) return R3DFS_E_ALIGN;
-  return launch_edge_feature(x, B, C, N, sb, sc, sn, idx, K, out, (cudaStream_t)stream);
+  return launch_edge_feature(x, B, C, N, sb, sc, sn, idx, K, out, (cudaStream_t)stream, ws, ws_bytes);
 }
 
 // ---- linear ---------------------------------------------------------------------------------

@@ -115,7 +115,9 @@ int launch_edge_mlp(const float* PQ, const int32_t* idx, const float* w2, const 
                     const float* t2, int64_t B, int N, int k, float* Y, int ldy, RowMap map,
                     float* w2t_scratch, cudaStream_t st);
 int launch_edge_feature(const float* x, int64_t B, int64_t C, int64_t N, int64_t sb, int64_t sc,
-                        int64_t sn, const int64_t* idx, int K, float* out, cudaStream_t st);
+                        int64_t sn, const int64_t* idx, int K, float* out, cudaStream_t st,
+                        void* ws = nullptr, size_t ws_bytes = 0);
+size_t edge_feature_scratch_bytes(int64_t B, int64_t C, int64_t N);
 int launch_attention(const float* qkv, int ld, int64_t B, int N, float* Y, int ldy, RowMap map,
                      cudaStream_t st);
 int launch_attention_tc(const float* qkv, int ld, int64_t B, int N, float* Y, int ldy, RowMap map,

@@ -503,8 +503,150 @@ __global__ __launch_bounds__(256) void edge_feature_kernel(const float* __restri
   }
 }
 
+// Row-gather variant (x point-major: channels contiguous).  One CTA = EF_EB consecutive (n, j)
+// positions x all channels:
+//   1. the neighbour rows x[nbr] (C contiguous floats, one or a few full sectors each) and the few
+//      centre rows are gathered into a shared-memory tile, transposed to [channel][position];
+//   2. every channel plane of the output receives EF_EB contiguous floats with 128-bit streaming
+//      stores (a warp writes 512 contiguous bytes).
+// The 4-byte random gathers of the kernel above (up to 32 L1 wavefronts per load instruction, the
+// real limiter of this otherwise pure write stream) become a few conflict-light LDS.
+#define EF_EB 128
+#define EF_THREADS 256
+#define EF_TS (EF_EB + 4)  // tile row stride: rows stay 16-byte aligned for the LDS.128 of step 2
+// position of (channel c, slot e): the 16-byte groups of a row are XOR-swizzled with bits of c, so
+// the transposing scalar stores of step 1 (16 lanes = 16 channel quads of one slot) fall in 8
+// bank groups instead of 2, while a row's groups stay a permutation (step 2 is conflict-free)
+__device__ __forceinline__ int ef_pos(int c, int e) {
+  return c * EF_TS + ((((e >> 2) ^ ((c >> 3) & 7))) << 2) + (e & 3);
+}
+
+template <int CT>  // CT = 64: channel count known at compile time (shifts instead of divisions)
+__global__ __launch_bounds__(EF_THREADS) void edge_feature_pm_kernel(
+    const float* __restrict__ xp, int C_rt, int64_t N, int64_t sb, int64_t sn,
+    const int64_t* __restrict__ idx, int K, float* __restrict__ out) {
+  const int C = CT ? CT : C_rt;
+  extern __shared__ __align__(16) float ef_smem[];
+  float* T = ef_smem;                 // [C][EF_TS]     x[nbr] transposed
+  float* Ct = T + (size_t)C * EF_TS;  // [C][EF_TS]     x[centre] transposed (per position)
+  __shared__ int s_nb[EF_EB], s_ct[EF_EB];  // neighbour / centre point of every slot
+  const int tid = threadIdx.x;
+  const int64_t b = blockIdx.y;
+  const int64_t NK = N * K;
+  const int64_t e0 = (int64_t)blockIdx.x * EF_EB;
+  const int ne = (int)min((int64_t)EF_EB, NK - e0);
+  const float* xb = xp + b * sb;
+  for (int e = tid; e < ne; e += EF_THREADS) {
+    s_nb[e] = (int)idx[b * NK + e0 + e];
+    s_ct[e] = (int)((e0 + e) / K);
+  }
+  __syncthreads();
+  const bool vec_in = (C & 3) == 0 && (sn & 3) == 0 && (reinterpret_cast<uintptr_t>(xb) & 15) == 0;
+  if (CT == 64 && vec_in && ne == EF_EB) {
+    // full tile, 64 channels: every thread's 2 x 8 row chunks are in flight before the first one
+    // is used (a plain loop would pay one L2 round trip per iteration)
+    constexpr int R = EF_EB * 16 / EF_THREADS;
+    float4 v[R], ct[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int i = tid + r * EF_THREADS, e = i >> 4, c4 = i & 15;
+      v[r] = __ldg(reinterpret_cast<const float4*>(xb + (int64_t)s_nb[e] * sn) + c4);
+      ct[r] = __ldg(reinterpret_cast<const float4*>(xb + (int64_t)s_ct[e] * sn) + c4);
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int i = tid + r * EF_THREADS, e = i >> 4, c4 = i & 15;
+      const int p0 = ef_pos(4 * c4, e);
+      T[p0] = v[r].x; T[p0 + EF_TS] = v[r].y; T[p0 + 2 * EF_TS] = v[r].z; T[p0 + 3 * EF_TS] = v[r].w;
+      Ct[p0] = ct[r].x; Ct[p0 + EF_TS] = ct[r].y; Ct[p0 + 2 * EF_TS] = ct[r].z;
+      Ct[p0 + 3 * EF_TS] = ct[r].w;
+    }
+  } else if (vec_in) {
+    const int C4 = C >> 2;
+    for (int i = tid; i < ne * C4; i += EF_THREADS) {
+      const int e = i / C4, c4 = i - e * C4;
+      const float4 v = __ldg(reinterpret_cast<const float4*>(xb + (int64_t)s_nb[e] * sn) + c4);
+      const float4 ct = __ldg(reinterpret_cast<const float4*>(xb + (int64_t)s_ct[e] * sn) + c4);
+      const int p0 = ef_pos(4 * c4, e);  // channels 4 c4 .. 4 c4 + 3 share (c >> 3): same swizzle
+      T[p0] = v.x; T[p0 + EF_TS] = v.y; T[p0 + 2 * EF_TS] = v.z; T[p0 + 3 * EF_TS] = v.w;
+      Ct[p0] = ct.x; Ct[p0 + EF_TS] = ct.y; Ct[p0 + 2 * EF_TS] = ct.z; Ct[p0 + 3 * EF_TS] = ct.w;
+    }
+  } else {
+    for (int i = tid; i < ne * C; i += EF_THREADS) {
+      const int e = i / C, c = i - e * C;
+      T[ef_pos(c, e)] = __ldg(xb + (int64_t)s_nb[e] * sn + c);
+      Ct[ef_pos(c, e)] = __ldg(xb + (int64_t)s_ct[e] * sn + c);
+    }
+  }
+  __syncthreads();
+  float* o1 = out + (b * 2 * C) * NK + e0;  // plane c: x_j - x_i ; plane C + c: x_i
+  const bool vec = ne == EF_EB && (NK & 3) == 0;
+  if (vec) {
+    for (int i = tid; i < C * (EF_EB / 4); i += EF_THREADS) {
+      const int c = i / (EF_EB / 4), q = i - c * (EF_EB / 4);
+      const int p0 = ef_pos(c, 4 * q);
+      const float4 t = *reinterpret_cast<const float4*>(T + p0);
+      const float4 ct = *reinterpret_cast<const float4*>(Ct + p0);
+      const float4 d = make_float4(t.x - ct.x, t.y - ct.y, t.z - ct.z, t.w - ct.w);
+      __stcs(reinterpret_cast<float4*>(o1 + (int64_t)c * NK) + q, d);
+      __stcs(reinterpret_cast<float4*>(o1 + (int64_t)(C + c) * NK) + q, ct);
+    }
+  } else {
+    for (int i = tid; i < C * ne; i += EF_THREADS) {
+      const int c = i / ne, e = i - c * ne;
+      const float ct = Ct[ef_pos(c, e)];
+      o1[(int64_t)c * NK + e] = T[ef_pos(c, e)] - ct;
+      o1[(int64_t)(C + c) * NK + e] = ct;
+    }
+  }
+}
+
+size_t edge_feature_scratch_bytes(int64_t B, int64_t C, int64_t N) {
+  return sizeof(float) * (size_t)B * C * N + 256;
+}
+
+// ws (may be NULL): scratch of edge_feature_scratch_bytes() used to bring a channel-major x into
+// point-major form first.  Without it (or when the tile would not fit in shared memory) the
+// 4-positions-per-thread kernel above runs on the strided input directly.
 int launch_edge_feature(const float* x, int64_t B, int64_t C, int64_t N, int64_t sb, int64_t sc,
-                        int64_t sn, const int64_t* idx, int K, float* out, cudaStream_t st) {
+                        int64_t sn, const int64_t* idx, int K, float* out, cudaStream_t st,
+                        void* ws, size_t ws_bytes) {
+  const size_t smem = sizeof(float) * 2 * (size_t)C * EF_TS;
+  // whole-row gathers pay off for rows of >= 128 bytes (measured at B = 64, C = 64, k = 20, with
+  // the transpose pass of a channel-major x included: N = 8192 2.36 -> 1.37 ms = 62 % of the HBM
+  // copy peak, N = 2048 0.39 -> 0.36 ms = 59 %)
+  const bool fits = smem <= 200 * 1024 && N * K < ((int64_t)1 << 31) * EF_EB && (C & 3) == 0 &&
+                    C >= 32 && (sc == 1 || N >= 1024);
+  const float* xp = nullptr;
+  int64_t psb = 0, psn = 0;
+  if (fits && sc == 1) {  // already point-major behind the view (the reference's collate layout)
+    xp = x;
+    psb = sb;
+    psn = sn;
+  } else if (fits && ws && ws_bytes >= edge_feature_scratch_bytes(B, C, N)) {
+    float* t = reinterpret_cast<float*>(ws);
+    R3DFS_TRY(launch_to_point_major(x, B, C, N, sb, sc, sn, t, st));
+    xp = t;
+    psb = N * C;
+    psn = C;
+  }
+  if (xp) {
+    dim3 grid((unsigned)((N * K + EF_EB - 1) / EF_EB), (unsigned)B);
+    cudaError_t e;
+    if (C == 64) {
+      e = cudaFuncSetAttribute(edge_feature_pm_kernel<64>,
+                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return (int)e;
+      edge_feature_pm_kernel<64><<<grid, EF_THREADS, smem, st>>>(xp, 64, N, psb, psn, idx, K, out);
+    } else {
+      e = cudaFuncSetAttribute(edge_feature_pm_kernel<0>,
+                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return (int)e;
+      edge_feature_pm_kernel<0><<<grid, EF_THREADS, smem, st>>>(xp, (int)C, N, psb, psn, idx, K, out);
+    }
+    R3DFS_CHECK_LAUNCH();
+    return 0;
+  }
   int64_t quads = (N * K + 3) / 4;
   dim3 grid((unsigned)((quads + 255) / 256), (unsigned)B);
   edge_feature_kernel<<<grid, 256, 0, st>>>(x, (int)C, N, sb, sc, sn, idx, K, out, quads);

@@ -75,9 +75,11 @@ def get_edge_feature(x: torch.Tensor, K: int = 20, idx: Optional[torch.Tensor] =
     idx = idx.to(torch.int64).contiguous()
     out = torch.empty((B, 2 * Cc, N, K), dtype=torch.float32, device=dev)
     L = _lib.lib()
+    ws = None if x.stride(1) == 1 else _ws(L.r3dfs_edge_feature_workspace(B, Cc, N), dev)
     with torch.cuda.device(dev):
         check(L.r3dfs_edge_feature(_p(x), B, Cc, N, x.stride(0), x.stride(1), x.stride(2), _p(idx),
-                                   K, _p(out), _stream()), "r3dfs_edge_feature")
+                                   K, _p(out), _p(ws), 0 if ws is None else ws.numel(), _stream()),
+              "r3dfs_edge_feature")
     return out
 
 

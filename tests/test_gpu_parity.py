@@ -100,6 +100,24 @@ def test_edge_feature_exact(golden_dgcnn):
     assert ops.get_graph_feature is ops.get_edge_feature
 
 
+@pytest.mark.parametrize("B,C,N,K", [(3, 64, 2048, 20), (2, 9, 2048, 20), (2, 5, 333, 7),
+                                     (1, 64, 1000, 20), (2, 130, 257, 3)])
+@pytest.mark.parametrize("layout", ["channel_major", "point_major_view"])
+def test_edge_feature_layouts(B, C, N, K, layout):
+    """Both input layouts of the row-gather kernel: channel-major (B, C, N) contiguous (brought to
+    point-major through the workspace) and the reference collate's point-major memory behind a
+    transposed view; ragged tails (N*K not a multiple of the 256-slot tile), C not a multiple of 4,
+    and a C too wide for the shared-memory tile (falls back to the strided kernel).  Bit-exact."""
+    from r3dfsseg_b200 import ops
+    g = torch.Generator().manual_seed(B * 100 + C)
+    xpm = torch.randn((B, N, C), generator=g)
+    x = xpm.transpose(1, 2) if layout == "point_major_view" else xpm.transpose(1, 2).contiguous()
+    idx = torch.randint(0, N, (B, N, K), generator=g)
+    e = ops.get_edge_feature(x.to(DEV) if layout == "channel_major" else xpm.to(DEV).transpose(1, 2),
+                             K, idx.to(DEV)).cpu()
+    assert torch.equal(e, O.get_edge_feature(x, K, idx))
+
+
 def test_edge_feature_odd_shapes():
     from r3dfsseg_b200 import ops
     g = torch.Generator().manual_seed(11)
