@@ -149,15 +149,39 @@ __global__ __launch_bounds__(SEL_THREADS) void knn_select_kernel(const float* __
       if ((key & mask) == prefix) atomicAdd(&s_hist[(key >> shift) & 255], 1);
     }
     __syncthreads();
-    if (tid == 0) {
-      int need = s_need, cum = 0, b = 0;
-      for (; b < 255; ++b) {
-        if (cum + s_hist[b] >= need) break;
-        cum += s_hist[b];
+    if (w == 0) {
+      // which bin holds the need-th smallest key: warp scan over 8 bins per lane (a single thread
+      // walking the 256 bins was ~25 % of the kernel's instructions)
+      int h[8], local = 0;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        h[q] = s_hist[8 * lane + q];
+        local += h[q];
       }
-      s_need = need - cum;
-      s_prefix = prefix | ((unsigned)b << shift);
-      s_mask = mask | (255u << shift);
+      int incl = local;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int a = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += a;
+      }
+      const int need = s_need, excl = incl - local;
+      const int total = __shfl_sync(0xffffffffu, incl, 31);
+      // first bin b (< 255) with cum(b) + hist[b] >= need, else b = 255 — as the serial walk
+      bool mine = excl < need && need <= incl;
+      if (total < need) mine = lane == 31;
+      __syncwarp();
+      if (mine) {
+        int cum = excl, b = 8 * lane;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          if (b == 255 || cum + h[q] >= need) break;
+          cum += h[q];
+          ++b;
+        }
+        s_need = need - cum;
+        s_prefix = prefix | ((unsigned)b << shift);
+        s_mask = mask | (255u << shift);
+      }
     }
     __syncthreads();
   }
