@@ -59,7 +59,9 @@ def test_knn_golden(golden_dgcnn, key):
 
 @pytest.mark.parametrize("impl", [1, 2])
 @pytest.mark.parametrize("C,N,k", [(9, 2048, 20), (64, 2048, 20), (3, 100, 5), (130, 333, 32),
-                                   (64, 8192, 20), (17, 1000, 32), (64, 130, 7)])
+                                   (64, 8192, 20), (17, 1000, 32), (64, 130, 7),
+                                   # two-pass kernel (k <= 20, N >= 1024) with ragged tiles / k < 20
+                                   (9, 1100, 20), (64, 1030, 13), (33, 1501, 20), (64, 1024, 1)])
 def test_knn_random(C, N, k, impl):
     """impl 1 = FP32 CUDA-core kernel, 2 = tcgen05 3xTF32 kernel (C <= 64)."""
     from r3dfsseg_b200 import ops
