@@ -223,3 +223,145 @@ int launch_linear_tc(const float* X, int ldx, const float* W, const float* s, co
     return launch_linear_tc_bn<128>(X, ldx, W, s, t, act, M, K, Nout, Y, ldy, map, st);
   return launch_linear_tc_bn<64>(X, ldx, W, s, t, act, M, K, Nout, Y, ldy, map, st);
 }
+
+
+// ---------------------------------------------------------------------------------------------
+// "TN" product for the weight gradients of the training path:  C[m][n] = sum_r A[r][m] * B[r][n]
+// with A (R x M) and B (R x N) row-major — the reduction runs over the ROWS (R = points or edges,
+// 24 576 ... 409 600), so R is cut into `splits` ranges (blockIdx.z), each CTA writes its partial
+// 128 x 128 tile to partial[split][M][N] and a fixed-order reduce kernel adds them (deterministic).
+// Same 3xTF32 tcgen05 pipeline as linear_tc_kernel; the only difference is the loader, which builds
+// each 16-byte K-major chunk from four consecutive rows of one column (a warp reads 128 contiguous
+// bytes of a row at a time).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float4 ld_chunk_t(const float* __restrict__ src, int64_t ld, int col,
+                                             int ncols, int64_t r, int64_t r_end) {
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (col < ncols) {
+    const float* p = src + r * ld + col;
+    if (r + 0 < r_end) v.x = __ldg(p);
+    if (r + 1 < r_end) v.y = __ldg(p + ld);
+    if (r + 2 < r_end) v.z = __ldg(p + 2 * ld);
+    if (r + 3 < r_end) v.w = __ldg(p + 3 * ld);
+  }
+  return v;
+}
+
+__global__ __launch_bounds__(TCG_THREADS, 3) void gemm_tn_tc_kernel(
+    const float* __restrict__ A, int64_t lda, const float* __restrict__ B, int64_t ldb, int M,
+    int N, int64_t R, int64_t rchunk, float* __restrict__ partial) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  using S = TcgSmem<128>;
+  __shared__ uint64_t bar_mma[2];
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int m0 = blockIdx.x * TCG_BM, n0 = blockIdx.y * 128;
+  const int64_t r_begin = (int64_t)blockIdx.z * rchunk, r_end = min(R, r_begin + rchunk);
+  constexpr int LBO = tc::tile_lbo(128);
+  constexpr uint32_t IDESC = tc::make_idesc_tf32(128, 128);
+  constexpr int CH = 128 * TCG_KC4 / TCG_THREADS;  // 2 chunks of each operand per thread
+  if (tid == 0) {
+    tc::mbar_init(&bar_mma[0], 1);
+    tc::mbar_init(&bar_mma[1], 1);
+    tc::mbar_fence_init();
+  }
+  if (w == 0) tc::tmem_alloc(&tmem_base_s, 128);
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_d = tmem_base_s;
+  const int KB = (int)((r_end - r_begin + TCG_BK - 1) / TCG_BK);
+  for (int kb = 0; kb < KB; ++kb) {
+    const int st = kb & 1;
+    const int64_t r0 = r_begin + (int64_t)kb * TCG_BK;
+    float4 av[CH], bv[CH];
+#pragma unroll
+    for (int i = 0; i < CH; ++i) {
+      const int c = tid + i * TCG_THREADS;  // chunk (kc, col): col fastest -> coalesced row reads
+      const int col = c & 127, kc = c >> 7;
+      av[i] = ld_chunk_t(A, lda, m0 + col, M, r0 + 4 * kc, r_end);
+      bv[i] = ld_chunk_t(B, ldb, n0 + col, N, r0 + 4 * kc, r_end);
+    }
+    if (kb >= 2) tc::mbar_wait(&bar_mma[st], ((kb >> 1) - 1) & 1);
+    unsigned char* sA_hi = smem + st * S::STAGE;
+    unsigned char* sA_lo = sA_hi + S::A_BYTES;
+    unsigned char* sB_hi = sA_lo + S::A_BYTES;
+    unsigned char* sB_lo = sB_hi + S::B_BYTES;
+#pragma unroll
+    for (int i = 0; i < CH; ++i) {
+      const int c = tid + i * TCG_THREADS;
+      const int col = c & 127, kc = c >> 7;
+      float4 hi, lo;
+      tc::split4(av[i], hi, lo);
+      *reinterpret_cast<float4*>(sA_hi + kc * LBO + col * 16) = hi;
+      *reinterpret_cast<float4*>(sA_lo + kc * LBO + col * 16) = lo;
+      tc::split4(bv[i], hi, lo);
+      *reinterpret_cast<float4*>(sB_hi + kc * LBO + col * 16) = hi;
+      *reinterpret_cast<float4*>(sB_lo + kc * LBO + col * 16) = lo;
+    }
+    tc::fence_async_smem();
+    __syncthreads();
+    if (tid == 0) {
+      tc::tc_fence_after();
+      const uint64_t dah = tc::make_desc(tc::smem_u32(sA_hi), LBO, 128);
+      const uint64_t dal = tc::make_desc(tc::smem_u32(sA_lo), LBO, 128);
+      const uint64_t dbh = tc::make_desc(tc::smem_u32(sB_hi), LBO, 128);
+      const uint64_t dbl = tc::make_desc(tc::smem_u32(sB_lo), LBO, 128);
+      constexpr uint64_t KS = tc::desc_kstep(LBO);
+      if (kb == 0) tc::mma_tf32_c<false>(tmem_d, dal, dbh, IDESC);
+      else tc::mma_tf32_c<true>(tmem_d, dal, dbh, IDESC);
+      tc::mma_tf32_c<true>(tmem_d, dah, dbl, IDESC);
+      tc::mma_tf32_c<true>(tmem_d, dah, dbh, IDESC);
+      tc::mma_tf32_c<true>(tmem_d, dal + KS, dbh + KS, IDESC);  // rows beyond r_end are zeros
+      tc::mma_tf32_c<true>(tmem_d, dah + KS, dbl + KS, IDESC);
+      tc::mma_tf32_c<true>(tmem_d, dah + KS, dbh + KS, IDESC);
+      tc::mma_commit(&bar_mma[st]);
+    }
+  }
+  if (KB > 0) tc::mbar_wait(&bar_mma[(KB - 1) & 1], ((KB - 1) >> 1) & 1);
+  tc::tc_fence_after();
+  {
+    float* out = partial + (int64_t)blockIdx.z * M * N;
+    const int rbase = 32 * (w & 3), cbase = (w >> 2) * 64;
+    const int m = m0 + rbase + lane;
+#pragma unroll
+    for (int cc = 0; cc < 64; cc += 32) {
+      float v[32];
+      tc::tmem_ld32(tmem_d + ((uint32_t)rbase << 16) + (uint32_t)(cbase + cc), v);
+      if (m < M) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int n = n0 + cbase + cc + j;
+          if (n < N) out[(int64_t)m * N + n] = KB > 0 ? v[j] : 0.f;
+        }
+      }
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (w == 0) tc::tmem_dealloc(tmem_d, 128);
+}
+
+// partial: splits * M * N floats; returns the number of splits used through *splits_out
+int launch_gemm_tn_tc(const float* A, int64_t lda, const float* B, int64_t ldb, int M, int N,
+                      int64_t R, int max_splits, float* partial, int* splits_out, cudaStream_t st) {
+  using S = TcgSmem<128>;
+  if (M <= 0 || N <= 0 || R <= 0 || max_splits < 1) return R3DFS_E_BADARG;
+  const int tiles = ((M + 127) / 128) * ((N + 127) / 128);
+  int64_t splits = (3 * 148 * 2 + tiles - 1) / tiles;  // ~2 waves of 3 CTAs per SM
+  const int64_t by_r = (R + 511) / 512;
+  if (splits > by_r) splits = by_r;
+  if (splits > max_splits) splits = max_splits;
+  if (splits < 1) splits = 1;
+  int64_t rchunk = (R + splits - 1) / splits;
+  rchunk = (rchunk + TCG_BK - 1) / TCG_BK * TCG_BK;
+  splits = (R + rchunk - 1) / rchunk;
+  cudaError_t e = cudaFuncSetAttribute(gemm_tn_tc_kernel,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
+  if (e != cudaSuccess) return (int)e;
+  dim3 grid((M + 127) / 128, (N + 127) / 128, (unsigned)splits);
+  gemm_tn_tc_kernel<<<grid, TCG_THREADS, S::TOTAL, st>>>(A, lda, B, ldb, M, N, R, rchunk, partial);
+  R3DFS_CHECK_LAUNCH();
+  *splits_out = (int)splits;
+  return 0;
+}

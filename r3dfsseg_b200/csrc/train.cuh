@@ -9,6 +9,12 @@
 int launch_sgemm(const float* A, int64_t sAm, int64_t sAk, int64_t bsA, const float* B, int64_t sBk,
                  int64_t sBn, int64_t bsB, float* C, int64_t ldc, int64_t bsC, int M, int N, int K,
                  int batch, float alpha, float beta, int splits, float* partial, cudaStream_t st);
+// C = alpha * sum over splits of partial[split] (M x N each, dense) + beta * C, fixed order
+int launch_sgemm_reduce(const float* partial, int M, int N, int splits, float alpha, float beta,
+                        float* C, int64_t ldc, cudaStream_t st);
+// tensor-core C[m][n] = sum_r A[r][m] B[r][n] into split partials (tc_gemm.cu)
+int launch_gemm_tn_tc(const float* A, int64_t lda, const float* B, int64_t ldb, int M, int N,
+                      int64_t R, int max_splits, float* partial, int* splits_out, cudaStream_t st);
 // number of K ranges launch_sgemm should use for a (M x N) output reduced over K
 int sgemm_splits(int M, int N, int64_t K, int batch);
 

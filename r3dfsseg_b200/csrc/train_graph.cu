@@ -338,14 +338,15 @@ __global__ __launch_bounds__(1024) void contrast_kernel(
   }
   __syncthreads();
   const int K = s_K;
-  // u = W p + b
-  for (int e = tid; e < K * CT_PD; e += blockDim.x) {
+  // u = W p + b: one warp per output, lanes along the input dimension (coalesced weight rows)
+  for (int e = tid >> 5; e < K * CT_PD; e += blockDim.x >> 5) {
     const int a = e / CT_PD, o = e % CT_PD;
     const float* p = cproto + (int64_t)s_src[a] * D;
     const float* wr = proj_w + (int64_t)o * D;
-    float s = proj_b[o];
-    for (int d = 0; d < D; ++d) s = fmaf(wr[d], p[d], s);
-    s_z[e] = s;
+    float s = 0.f;
+    for (int d = tid & 31; d < D; d += 32) s = fmaf(wr[d], p[d], s);
+    s = warp_sum(s);
+    if ((tid & 31) == 0) s_z[e] = s + proj_b[o];
   }
   __syncthreads();
   if (tid < K) {

@@ -110,6 +110,14 @@ __global__ void sgemm_reduce_kernel(const float* __restrict__ partial, int M, in
   *c = alpha * s + (beta != 0.f ? beta * *c : 0.f);
 }
 
+int launch_sgemm_reduce(const float* partial, int M, int N, int splits, float alpha, float beta,
+                        float* C, int64_t ldc, cudaStream_t st) {
+  sgemm_reduce_kernel<<<dim3((M * N + 255) / 256, 1), 256, 0, st>>>(partial, M, N, splits, alpha,
+                                                                   beta, C, ldc, 0);
+  R3DFS_CHECK_LAUNCH();
+  return 0;
+}
+
 int sgemm_splits(int M, int N, int64_t K, int batch) {
   const int64_t tiles = (int64_t)((M + SG_BM - 1) / SG_BM) * ((N + SG_BN - 1) / SG_BN) * batch;
   if (tiles >= 148 || K < 2048) return 1;
