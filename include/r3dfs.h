@@ -276,6 +276,23 @@ int r3dfs_mpti_forward_features(const r3dfs_episode_cfg_t* h_cfg, int n_episodes
                                 float* loss, int32_t* pred, const r3dfs_episode_diag_t* h_diag,
                                 void* ws, size_t ws_bytes, r3dfs_stream_t stream);
 
+/* ProtoNet + MDNS (reference models/protonet.py:357-945 ProtoNet_Contrast.forward, train=False):
+ * same encoder and noise suppression as MPTI, then masked average pooling of the support
+ * features (:878-890), one prototype per way from the kept shots + one background prototype
+ * (:892-915) and the similarity of every query point to every prototype (:917-940).
+ * dist_method 0 = 'cosine' (x 10), the only one that runs in the reference: 'euclidean' reduces
+ * over the point axis and fails in the loss, the scripts' default 'gaussian' raises
+ * NotImplementedError; anything else returns R3DFS_E_UNSUPPORTED.  Arguments, outputs and workspace
+ * (r3dfs_mpti_workspace) as r3dfs_mpti_forward; cfg->mdns = 0 keeps every shot; clean_flag:
+ * optional (E, n_way, k_shot) fp32 output of the noise suppression. */
+int r3dfs_protonet_forward(const r3dfs_episode_cfg_t* h_cfg, const r3dfs_weights_t* h_w,
+                           int n_episodes, const float* support_x, int64_t s_e, int64_t s_cloud,
+                           int64_t s_c, int64_t s_n, const int32_t* support_y, const float* query_x,
+                           int64_t q_e, int64_t q_cloud, int64_t q_c, int64_t q_n,
+                           const int64_t* query_y, int dist_method, float* logits, float* loss,
+                           int32_t* pred, float* clean_flag, void* ws, size_t ws_bytes,
+                           r3dfs_stream_t stream);
+
 /* evaluate_metric counters (reference eval_noise.py:35-62): for every query point, map the
  * episode-local label to its slot in the test-class list and accumulate gt / predicted /
  * true-positive counts.  class_slot: (E, n_way) int32 = test_classes.index(sampled_class) + 1.

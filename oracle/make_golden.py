@@ -5,6 +5,8 @@ Build container only.  Run:  python -m oracle.make_golden
 Files (small on purpose; episodes are regenerated from their seed, only outputs are stored):
   golden_dgcnn.pt      knn / get_edge_feature / DGCNN.forward on small random clouds
   golden_episodes.pt   MPTI_SelfAtten.forward outputs for the three episode configurations
+  golden_protonet.pt   ProtoNet_Contrast.forward (eval) outputs; `python -m oracle.make_golden protonet`
+                       writes only this file
 """
 import os
 import sys
@@ -27,10 +29,44 @@ EPISODE_CASES = [
 ]
 
 
+PROTONET_CASES = [
+    ("s3dis_2way_5shot_noisy", 3, 2, 5, "s3dis", 0.4),
+    ("scannet_3way_5shot_ood", 2, 3, 5, "scannet", 0.4),
+    ("s3dis_2way_1shot", 0, 2, 1, "s3dis", 0.0),
+]
+
+
+def protonet(ref, sd):
+    """ProtoNet_Contrast (models/protonet.py:357) in eval: query_pred, loss, clean flags."""
+    out = {}
+    for name, seed, n_way, k_shot, ds, noise in PROTONET_CASES:
+        args = default_args(n_way, k_shot, dist_method="cosine")
+        m = ref.protonet.ProtoNet_Contrast(args)
+        m.load_state_dict(sd)
+        m.eval()
+        ep = make_episode(seed, n_way, k_shot, dataset=ds, noise_ratio=noise)
+        with torch.no_grad(), ref_shims.quiet():
+            pred, loss = m(ep.support_x, ep.support_y, ep.query_x, ep.query_y,
+                           gt_support_y=ep.gt_support_y)
+            sf = m.getFeatures(ep.support_x.reshape(n_way * k_shot, 9, -1)).view(
+                n_way, k_shot, 192, -1)
+            _, clean = m.Mean_pl_support_y_multi_scale(sf, ep.support_y, ep.gt_support_y,
+                                                       ep.support_x)
+        out[name] = dict(seed=seed, n_way=n_way, k_shot=k_shot, dataset=ds, noise_ratio=noise,
+                         query_pred=pred.contiguous().clone(), loss=loss.clone(),
+                         clean_flag=clean.clone())
+        print(name, "loss", float(loss), "acc",
+              float((pred.argmax(1) == ep.query_y).float().mean()), "clean", clean.tolist())
+    torch.save(out, os.path.join(GOLD, "golden_protonet.pt"))
+    print("golden_protonet.pt written")
+
+
 def main():
     ref = ref_shims.load_reference()
     torch.set_num_threads(os.cpu_count())
     sd = torch.load(os.path.join(GOLD, "weights_fixture.pt"))
+    if sys.argv[1:] == ["protonet"]:
+        return protonet(ref, sd)
 
     # ---- DGCNN pieces -----------------------------------------------------------------------
     g = torch.Generator().manual_seed(7)
@@ -77,6 +113,7 @@ def main():
               "clean", None if clean is None else clean.tolist())
     torch.save(eps, os.path.join(GOLD, "golden_episodes.pt"))
     print("golden_episodes.pt written")
+    protonet(ref, sd)
 
 
 if __name__ == "__main__":

@@ -86,7 +86,7 @@ _loaded = None
 
 def load_reference():
     """Returns a namespace with the reference's `dgcnn`, `attention`, `mpti`,
-    `mpti_learner` modules and `evaluate_metric`."""
+    `mpti_learner`, `protonet` modules and `evaluate_metric`."""
     global _loaded
     if _loaded is not None:
         return _loaded
@@ -114,10 +114,11 @@ def load_reference():
         import models.attention as attention
         import models.mpti as mpti
         import models.mpti_learner as mpti_learner
+        import models.protonet as protonet
     finally:
         sys.path.remove(REFERENCE_ROOT)
     ns = types.SimpleNamespace(dgcnn=dgcnn, attention=attention, mpti=mpti,
-                               mpti_learner=mpti_learner)
+                               mpti_learner=mpti_learner, protonet=protonet)
     # evaluate_metric lives in a script with heavy imports (h5py...): exec just that function
     src = open(os.path.join(REFERENCE_ROOT, "eval_noise.py")).read()
     start = src.index("def evaluate_metric")

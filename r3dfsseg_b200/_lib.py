@@ -99,6 +99,10 @@ SIGNATURES = {
                                               vp, vp, vp, vp, vp, vp, C.POINTER(EpisodeDiag), vp,
                                               sz, vp]),
     "r3dfs_confusion_accumulate": (C.c_int, [vp, vp, vp, i32, i32, i64, i32, vp, vp]),
+    "r3dfs_protonet_forward": (C.c_int, [C.POINTER(EpisodeCfg), C.POINTER(Weights), i32,
+                                         vp, i64, i64, i64, i64, vp,
+                                         vp, i64, i64, i64, i64, vp,
+                                         i32, vp, vp, vp, vp, vp, sz, vp]),
     # meta-training step
     "r3dfs_train_param_layout": (i64, [i32, C.POINTER(i64)]),
     "r3dfs_train_bn_layout": (None, [C.POINTER(i64)]),

@@ -665,6 +665,52 @@ int r3dfs_mpti_forward(const r3dfs_episode_cfg_t* cfg, const r3dfs_weights_t* hw
                             logits, loss, pred, diag, st);
 }
 
+int r3dfs_protonet_forward(const r3dfs_episode_cfg_t* cfg, const r3dfs_weights_t* hw, int E,
+                           const float* support_x, int64_t s_e, int64_t s_cloud, int64_t s_c,
+                           int64_t s_n, const int32_t* support_y, const float* query_x, int64_t q_e,
+                           int64_t q_cloud, int64_t q_c, int64_t q_n, const int64_t* query_y,
+                           int dist_method, float* logits, float* loss, int32_t* pred,
+                           float* clean_flag, void* wsp, size_t ws_bytes, r3dfs_stream_t stream) {
+  EpisodeDims d;
+  R3DFS_TRY(episode_dims(cfg, d));
+  R3DFS_TRY(check_weights(hw));
+  if (!support_x || !support_y || !query_x || !logits || !wsp || E <= 0) return R3DFS_E_BADARG;
+  if (dist_method != 0 || (int64_t)E * d.cpe > 65535) return R3DFS_E_UNSUPPORTED;
+  if (ws_bytes < r3dfs_mpti_workspace(cfg, E)) return R3DFS_E_WORKSPACE;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int N = cfg->n_points, in_dim = hw->in_dim, D = R3DFS_FEAT_DIM;
+  WsBump ws(wsp, ws_bytes);
+  EpisodeWs w;
+  carve_episode(ws, cfg, d, E, in_dim, hw->dgcnn_k, w);
+  if (!ws.ok()) return R3DFS_E_WORKSPACE;
+  const int64_t B = (int64_t)E * d.cpe;
+  int64_t tq = (int64_t)E * cfg->n_query * N * in_dim;
+  gather_clouds_kernel<<<nblk(tq), 256, 0, st>>>(query_x, cfg->n_query, in_dim, N, q_e, q_cloud,
+                                                 q_c, q_n, d.cpe, 0, w.xp, tq);
+  R3DFS_CHECK_LAUNCH();
+  int64_t tsup = (int64_t)E * d.C * N * in_dim;
+  gather_clouds_kernel<<<nblk(tsup), 256, 0, st>>>(support_x, d.C, in_dim, N, s_e, s_cloud, s_c,
+                                                   s_n, d.cpe, cfg->n_query, w.xp, tsup);
+  R3DFS_CHECK_LAUNCH();
+  RowMap fmap{d.cpe, N, d.ep_rows, (int64_t)d.ppad};
+  R3DFS_TRY(encoder_forward(hw, w.xp, B, N, w.enc, w.F, fmap, nullptr, st));
+  const int32_t* keep = nullptr;
+  if (cfg->mdns) {  // Mean_pl_support_y_multi_scale (models/protonet.py:491-536) = the MPTI kernels
+    R3DFS_TRY(launch_mdns(support_x, s_e, s_cloud, s_c, s_n, support_y, w.F, d.ep_rows, d.nn, E,
+                          cfg->n_way, cfg->k_shot, N, D, w.cell_mean, w.cell_cnt, w.fg_cnt, w.keep,
+                          clean_flag, st));
+    keep = w.keep;
+  }
+  // pooled vectors and prototypes live in the (otherwise unused) compacted-set buffer
+  float* fg = w.setfeat;
+  float* bg = fg + (size_t)E * d.C * D;
+  float* proto = bg + (size_t)E * d.C * D;
+  R3DFS_TRY(launch_protonet_head(w.F, d.ep_rows, d.nn, d.ppad, E, cfg->n_way, cfg->k_shot, N,
+                                 d.nq_pts, D, support_y, keep, dist_method, fg, bg, proto, w.Z, d.nn,
+                                 st));
+  return launch_query_head(w.Z, E, d.nn, d.ppad, d.nq_pts, d.nc, query_y, logits, loss, pred, st);
+}
+
 int r3dfs_mpti_forward_features(const r3dfs_episode_cfg_t* cfg, int E, const float* support_x,
                                 int64_t s_e, int64_t s_cloud, int64_t s_c, int64_t s_n,
                                 const int32_t* support_y, const float* support_feat,

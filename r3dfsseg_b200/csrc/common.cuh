@@ -127,5 +127,10 @@ int launch_attention_auto(const float* qkv, int ld, int64_t B, int N, float* Y, 
 int launch_fold_edge_w1(const float* w1, const float* s1, const float* t1, int C, float* wpq,
                         float* spq, float* tpq, cudaStream_t st);
 
+int launch_protonet_head(const float* F, int64_t ep_rows, int64_t sup_row_off, int64_t q_row_off,
+                         int E, int n_way, int k_shot, int N, int nq, int D, const int32_t* sy,
+                         const int32_t* keep, int method, float* fg, float* bg, float* proto,
+                         float* Z, int nn, cudaStream_t st);
+
 int launch_fps(const float* feat, int D, const int32_t* set_off, const int32_t* set_n, int n_sets,
                int m_max, int k_for_count, int32_t* idx_out, cudaStream_t st);

@@ -403,6 +403,50 @@ def mpti_forward(pw: Optional[PackedWeights], cfg: EpisodeCfg, support_x: torch.
     return out
 
 
+def protonet_forward(pw: PackedWeights, cfg: EpisodeCfg, support_x: torch.Tensor,
+                     support_y: torch.Tensor, query_x: torch.Tensor,
+                     query_y: Optional[torch.Tensor], dist_method: str = "cosine",
+                     workspace: Optional[torch.Tensor] = None):
+    """E ProtoNet(+MDNS when cfg.mdns) episodes in one call (reference models/protonet.py:780-858).
+    Tensors as `mpti_forward`.  Returns dict(logits (E, n_query, N, n_way+1), loss (E),
+    pred (E, n_query, N) int32, clean_flag (E, n_way, k_shot))."""
+    if dist_method != "cosine":
+        # the reference's 'euclidean' branch reduces over the point axis and fails in the loss; any
+        # other name (the scripts' default is 'gaussian') raises there too (models/protonet.py:933-939)
+        raise NotImplementedError(
+            "Error! Distance computation method (%s) is unknown!" % dist_method)
+    dev = _need_cuda(support_x, support_y, query_x, query_y)
+    support_x, query_x = _f32(support_x), _f32(query_x)
+    E, n_way, k_shot, Cin, N = support_x.shape
+    nq = query_x.shape[1]
+    if (n_way, k_shot, nq, N) != (cfg.n_way, cfg.k_shot, cfg.n_query, cfg.n_points):
+        raise ValueError("episode tensors do not match the episode configuration")
+    if support_x.stride(1) != k_shot * support_x.stride(2):
+        support_x = support_x.contiguous()
+    support_y = support_y.to(torch.int32).contiguous()
+    if query_y is not None:
+        query_y = query_y.to(torch.int64).contiguous()
+    nc = n_way + 1
+    logits = torch.empty((E, nq, N, nc), dtype=torch.float32, device=dev)
+    loss = torch.zeros((E,), dtype=torch.float32, device=dev)
+    pred = torch.empty((E, nq, N), dtype=torch.int32, device=dev)
+    clean = torch.ones((E, n_way, k_shot), dtype=torch.float32, device=dev)
+    L = _lib.lib()
+    need = L.r3dfs_mpti_workspace(C.byref(cfg), E)
+    if need == 0:
+        raise _lib.R3dfsError("episode configuration not supported by libr3dfs")
+    ws = workspace if workspace is not None and workspace.numel() >= need else _ws(need, dev)
+    with torch.cuda.device(dev):
+        check(L.r3dfs_protonet_forward(
+            C.byref(cfg), C.byref(pw.struct), E,
+            _p(support_x), support_x.stride(0), support_x.stride(2), support_x.stride(3),
+            support_x.stride(4), _p(support_y),
+            _p(query_x), query_x.stride(0), query_x.stride(1), query_x.stride(2), query_x.stride(3),
+            _p(query_y), 0, _p(logits), _p(loss), _p(pred), _p(clean), _p(ws), ws.numel(),
+            _stream()), "r3dfs_protonet_forward")
+    return {"logits": logits, "loss": loss, "pred": pred, "clean_flag": clean}
+
+
 def confusion_accumulate(pred: torch.Tensor, gt: torch.Tensor, class_slot: torch.Tensor,
                          counters: torch.Tensor) -> None:
     """evaluate_metric counters (eval_noise.py:35-62), accumulated in place into the (3, n_slots)

@@ -654,3 +654,80 @@ def test_drop_in_test_few_shot_matches_per_episode_loop(model, fixture_sd):
     assert abs(mean_iou - ref) < 1e-9
     assert abs(mean_loss - float(np.mean(losses))) < 1e-5
     assert any("mean IoU" in s for s in lines)
+
+
+# ---- ProtoNet + MDNS (reference models/protonet.py:357-945, eval) ------------------------------
+@pytest.mark.parametrize("name", ["s3dis_2way_5shot_noisy", "scannet_3way_5shot_ood",
+                                  "s3dis_2way_1shot"])
+def test_protonet_episode(fixture_sd, name):
+    """ProtoNet_Contrast.forward (eval) through r3dfs_protonet_forward:
+    (a) against the oracle's head run on the features the CUDA encoder produced (1e-4 relative,
+        labels identical up to near-ties, clean flags exact);
+    (b) against the REFERENCE's golden output from raw clouds.  There is no farthest point sampling
+        on this path, so a kNN tie in the encoder only perturbs the few points it touches and the
+        prototypes are plain means: median error < 1e-4 relative, 99th percentile < 3e-3, 99.9th
+        < 1e-2, no point beyond 5e-2, >= 99.8 % labels."""
+    from oracle import protonet_oracle as PO
+    from r3dfsseg_b200.models import ProtoNet_Contrast
+    c = torch.load(os.path.join(os.path.dirname(__file__), "golden", "golden_protonet.pt"))[name]
+    n_way, k_shot = c["n_way"], c["k_shot"]
+    ep = make_episode(c["seed"], n_way, k_shot, dataset=c["dataset"], noise_ratio=c["noise_ratio"])
+    m = ProtoNet_Contrast(default_args(n_way, k_shot, dist_method="cosine"))
+    m.load_state_dict(fixture_sd)
+    m = m.to(DEV).eval()
+    pred, loss = m(ep.support_x.to(DEV), ep.support_y.to(DEV), ep.query_x.to(DEV),
+                   ep.query_y.to(DEV), gt_support_y=ep.gt_support_y.to(DEV))
+    assert pred.shape == c["query_pred"].shape
+    pred = pred.cpu()
+    sf = m.getFeatures(ep.support_x.reshape(n_way * k_shot, 9, -1).to(DEV)).cpu()
+    qf = m.getFeatures(ep.query_x.to(DEV)).cpu()
+    with torch.no_grad():
+        ref = PO.forward_episode(fixture_sd, ep.support_x, ep.support_y, ep.query_x, ep.query_y,
+                                 support_feat=sf, query_feat=qf)
+    assert torch.equal(m.clean_flag.cpu(), ref["clean_flag"])
+    rp = ref["query_pred"]
+    err = (pred - rp).abs().max() / rp.abs().max()
+    agree = (pred.argmax(1) == rp.argmax(1)).float().mean()
+    assert err < 1e-4 and agree >= 0.9995, (err, agree)
+    assert abs(float(loss) - float(ref["loss"])) < 1e-5
+    gold = c["query_pred"]
+    assert torch.equal(m.clean_flag.cpu(), c["clean_flag"])
+    rel = ((pred - gold).abs() / gold.abs().max()).reshape(-1)
+    agree_g = (pred.argmax(1) == gold.argmax(1)).float().mean()
+    q99, q999 = torch.quantile(rel, 0.99), torch.quantile(rel, 0.999)
+    assert rel.median() < 1e-4 and q99 < 3e-3 and q999 < 1e-2 and rel.max() < 5e-2 \
+        and agree_g >= 0.998, (rel.median(), q99, q999, rel.max(), agree_g)
+    assert abs(float(loss) - float(c["loss"])) < 1e-3
+
+
+def test_protonet_batch_no_mdns_and_bad_method(fixture_sd):
+    """A batch of episodes equals the per-episode loop bit for bit; mdns off = plain ProtoNet
+    prototypes (models/protonet.py:911-912); any dist_method but 'cosine' raises as the reference."""
+    from oracle import protonet_oracle as PO
+    from r3dfsseg_b200.models import ProtoNet_Contrast
+    m = ProtoNet_Contrast(default_args(2, 5, dist_method="cosine"))
+    m.load_state_dict(fixture_sd)
+    m = m.to(DEV).eval()
+    eps = [make_episode(s, 2, 5, noise_ratio=0.4) for s in (21, 22, 23)]
+    sx = torch.stack([e.support_x for e in eps]).to(DEV)
+    sy = torch.stack([e.support_y for e in eps]).to(DEV)
+    qx = torch.stack([e.query_x for e in eps]).to(DEV)
+    qy = torch.stack([e.query_y for e in eps]).to(DEV)
+    out = m.forward_episodes(sx, sy, qx, qy)
+    for i in range(3):
+        one = m.forward_episodes(sx[i:i + 1], sy[i:i + 1], qx[i:i + 1], qy[i:i + 1])
+        assert torch.equal(one["logits"][0], out["logits"][i])
+        assert torch.equal(one["loss"][0], out["loss"][i])
+    m.mdns = False
+    o2 = m.forward_episodes(sx[:1], sy[:1], qx[:1], qy[:1])
+    e = eps[0]
+    sf = m.getFeatures(e.support_x.reshape(10, 9, -1).to(DEV)).cpu()
+    qf = m.getFeatures(e.query_x.to(DEV)).cpu()
+    ref = PO.forward_episode(fixture_sd, e.support_x, e.support_y, e.query_x, e.query_y, mdns=False,
+                             support_feat=sf, query_feat=qf)
+    p = o2["logits"][0].transpose(1, 2).cpu()
+    assert (p - ref["query_pred"]).abs().max() / ref["query_pred"].abs().max() < 1e-4
+    assert float(o2["clean_flag"].min()) == 1.0
+    m.dist_method = "gaussian"
+    with pytest.raises(NotImplementedError):
+        m.forward_episodes(sx[:1], sy[:1], qx[:1], qy[:1])

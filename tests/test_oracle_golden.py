@@ -87,3 +87,24 @@ def test_train_oracle_vs_reference_golden(fixture_sd):
             assert float((v - g["running"][k]).abs().max()) < 1e-5, k
         else:
             assert int(v) == int(g["running"][k])
+
+
+@pytest.mark.parametrize("name", ["s3dis_2way_5shot_noisy", "scannet_3way_5shot_ood",
+                                  "s3dis_2way_1shot"])
+def test_protonet_oracle_matches_reference(fixture_sd, name):
+    """oracle/protonet_oracle.py against the REFERENCE's ProtoNet_Contrast.forward (eval) outputs
+    (models/protonet.py:780-858; written by `python -m oracle.make_golden protonet`)."""
+    import os
+    from oracle import protonet_oracle as PO
+    gold = torch.load(os.path.join(os.path.dirname(__file__), "golden", "golden_protonet.pt"))
+    c = gold[name]
+    ep = make_episode(c["seed"], c["n_way"], c["k_shot"], dataset=c["dataset"],
+                      noise_ratio=c["noise_ratio"])
+    with torch.no_grad():
+        out = PO.forward_episode(fixture_sd, ep.support_x, ep.support_y, ep.query_x, ep.query_y)
+    assert torch.equal(out["clean_flag"], c["clean_flag"])
+    ref = c["query_pred"]
+    err = (out["query_pred"] - ref).abs().max() / ref.abs().max()
+    assert err < 1e-5, err
+    assert torch.equal(out["query_pred"].argmax(1), ref.argmax(1))
+    assert abs(float(out["loss"]) - float(c["loss"])) < 1e-5
