@@ -237,6 +237,317 @@ __global__ __launch_bounds__(SEL_THREADS) void knn_select_kernel(const float* __
   }
 }
 
+// Same selection, one WARP per row with the row's keys in registers (KPL per lane, j = lane + 32 t):
+// the k-th smallest key is found by narrowing [lo, hi] eight bits at a time from the row's actual
+// key range (the top radix digits of distances that span two or three binades carry no
+// information), stopping as soon as the boundary bin is taken whole; the ordered compaction is a
+// ballot per 32 keys.  No block barrier anywhere.  Output identical to knn_select_kernel.
+#define SELW_WARPS 8
+
+template <int KPL>
+__global__ __launch_bounds__(SELW_WARPS * 32) void knn_select_warp_kernel(
+    const float* __restrict__ D2, const uint8_t* __restrict__ valid, int nn, int k,
+    int32_t* __restrict__ nbr) {
+  __shared__ int s_hist[SELW_WARPS][256];
+  __shared__ unsigned s_vbits[KPL];  // validity of the graph's nodes, one bit per node
+  const int g = blockIdx.y, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int i = blockIdx.x * SELW_WARPS + w;
+  const uint8_t* vg = valid + (int64_t)g * nn;
+  for (int t = w; t < KPL; t += SELW_WARPS) {
+    const int j = lane + 32 * t;
+    const unsigned bits = __ballot_sync(0xffffffffu, j < nn && vg[j] != 0);
+    if (lane == 0) s_vbits[t] = bits;
+  }
+  __syncthreads();
+  if (i >= nn) return;
+  if (!((s_vbits[i >> 5] >> (i & 31)) & 1u)) return;
+  const float* row = D2 + ((int64_t)g * nn + i) * nn;
+  int* hist = s_hist[w];
+  // every load of the row is issued before the first use (no load sits behind a validity branch)
+  float v[KPL];
+#pragma unroll
+  for (int t = 0; t < KPL; ++t) v[t] = __ldcs(row + min(lane + 32 * t, nn - 1));
+  unsigned key[KPL];
+  unsigned lo = 0xffffffffu, hi = 0u;
+  int n_real = 0;
+#pragma unroll
+  for (int t = 0; t < KPL; ++t) {
+    const int j = lane + 32 * t;
+    unsigned kk = f2key(v[t]);
+    if (kk == 0xffffffffu) kk = 0xfffffffeu;
+    const bool real = ((s_vbits[t] >> lane) & 1u) && j != i;
+    lo = real ? min(lo, kk) : lo;
+    hi = real ? max(hi, kk) : hi;
+    n_real += real;
+    key[t] = real ? kk : 0xffffffffu;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+    hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    n_real += __shfl_xor_sync(0xffffffffu, n_real, o);
+  }
+  unsigned T;
+  int need_eq;
+  if (n_real < k) {  // every real key, then the lowest-index fillers
+    T = 0xffffffffu;
+    need_eq = k - n_real;
+  } else {
+    int need = k;
+    while (true) {
+      const unsigned range = hi - lo;
+      if (range == 0) {
+        T = lo;
+        need_eq = need;
+        break;
+      }
+      const int sh = max(0, 24 - (int)__clz(range));  // (key - lo) >> sh  in [0, 255]
+#pragma unroll
+      for (int q = 0; q < 8; ++q) hist[lane + 32 * q] = 0;
+      __syncwarp();
+#pragma unroll
+      for (int t = 0; t < KPL; ++t)
+        if (key[t] >= lo && key[t] <= hi) atomicAdd(&hist[(key[t] - lo) >> sh], 1);
+      __syncwarp();
+      int h[8], local = 0;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        h[q] = hist[8 * lane + q];
+        local += h[q];
+      }
+      int incl = local;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int a = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += a;
+      }
+      const int excl = incl - local;
+      const bool mine = excl < need && need <= incl;  // exactly one lane: total >= need
+      int b = 0, cum = 0, hb = 0;
+      if (mine) {
+        cum = excl;
+        b = 8 * lane;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          hb = h[q];
+          if (cum + h[q] >= need) break;
+          cum += h[q];
+          ++b;
+        }
+      }
+      const unsigned owner = __ballot_sync(0xffffffffu, mine);
+      const int src = __ffs(owner) - 1;
+      b = __shfl_sync(0xffffffffu, b, src);
+      cum = __shfl_sync(0xffffffffu, cum, src);
+      hb = __shfl_sync(0xffffffffu, hb, src);
+      __syncwarp();
+      need -= cum;
+      const unsigned nlo = lo + ((unsigned)b << sh);
+      const unsigned nhi = min(hi, nlo + ((1u << sh) - 1u));
+      if (hb == need) {  // the whole boundary bin is taken: nothing ties at the cut
+        T = nhi + 1u;    // nhi <= 0xfffffffe
+        need_eq = 0;
+        break;
+      }
+      if (sh == 0) {     // the bin is a single key value
+        T = nlo;
+        need_eq = need;
+        break;
+      }
+      lo = nlo;
+      hi = nhi;
+    }
+  }
+  int32_t* out = nbr + ((int64_t)g * nn + i) * k;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  int pos = 0, eq_seen = 0;
+#pragma unroll
+  for (int t = 0; t < KPL; ++t) {
+    const bool is_eq = key[t] == T && (lane + 32 * t) < nn;
+    const unsigned eqb = __ballot_sync(0xffffffffu, is_eq);
+    bool sel = key[t] < T;
+    if (is_eq) sel = eq_seen + __popc(eqb & lt_mask) < need_eq;
+    const unsigned sb = __ballot_sync(0xffffffffu, sel);
+    if (sel) {
+      const int p = pos + __popc(sb & lt_mask);
+      if (p < k) out[p] = lane + 32 * t;
+    }
+    pos += __popc(sb);
+    eq_seen += __popc(eqb);
+  }
+}
+
+// Rows too long for one warp's registers (nn up to 31 * 256): one CTA per row, every thread keeps a
+// contiguous run of the row's keys in registers (staged through shared memory so the global loads
+// stay coalesced), the same range narrowing with ONE barrier per pass (three rotating histograms,
+// every warp scans the bins for itself), then the ordered compaction of knn_select_kernel.
+template <int KPT>
+__global__ __launch_bounds__(SEL_THREADS, KPT <= 20 ? 4 : 2) void knn_select_reg_kernel(
+    const float* __restrict__ D2, const uint8_t* __restrict__ valid, int nn, int k,
+    int32_t* __restrict__ nbr) {
+  extern __shared__ unsigned s_key[];  // [nn]
+  __shared__ int s_hist[3][256];
+  __shared__ unsigned s_lo[SEL_THREADS / 32], s_hi[SEL_THREADS / 32];
+  __shared__ int s_cnt[SEL_THREADS / 32];
+  __shared__ int s_w[2][SEL_THREADS / 32];
+  const int g = blockIdx.y, i = blockIdx.x;
+  const uint8_t* vg = valid + (int64_t)g * nn;
+  if (!vg[i]) return;
+  const float* row = D2 + ((int64_t)g * nn + i) * nn;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  unsigned lo = 0xffffffffu, hi = 0u;
+  int n_real = 0;
+  for (int j = tid; j < nn; j += SEL_THREADS) {
+    const float v = __ldcs(row + j);
+    const bool real = vg[j] != 0 && j != i;
+    unsigned kk = f2key(v);
+    if (kk == 0xffffffffu) kk = 0xfffffffeu;
+    lo = real ? min(lo, kk) : lo;
+    hi = real ? max(hi, kk) : hi;
+    n_real += real;
+    s_key[j] = real ? kk : 0xffffffffu;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+    hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    n_real += __shfl_xor_sync(0xffffffffu, n_real, o);
+  }
+  if (lane == 0) {
+    s_lo[w] = lo;
+    s_hi[w] = hi;
+    s_cnt[w] = n_real;
+  }
+  s_hist[0][tid] = 0;  // SEL_THREADS == 256
+  __syncthreads();
+  n_real = 0;
+#pragma unroll
+  for (int q = 0; q < SEL_THREADS / 32; ++q) {
+    lo = min(lo, s_lo[q]);
+    hi = max(hi, s_hi[q]);
+    n_real += s_cnt[q];
+  }
+  // my contiguous run (odd length -> conflict-free shared-memory reads)
+  int per = (nn + SEL_THREADS - 1) / SEL_THREADS;
+  per |= 1;
+  const int j0 = tid * per;
+  unsigned key[KPT];
+#pragma unroll
+  for (int t = 0; t < KPT; ++t) key[t] = (t < per && j0 + t < nn) ? s_key[j0 + t] : 0xffffffffu;
+  unsigned T;
+  int need_eq;
+  if (n_real < k) {
+    T = 0xffffffffu;
+    need_eq = k - n_real;
+  } else {
+    int need = k, p = 0;
+    while (true) {
+      const unsigned range = hi - lo;
+      if (range == 0) {
+        T = lo;
+        need_eq = need;
+        break;
+      }
+      const int sh = max(0, 24 - (int)__clz(range));
+      int* hist = s_hist[p % 3];
+      s_hist[(p + 1) % 3][tid] = 0;  // last read two passes ago
+#pragma unroll
+      for (int t = 0; t < KPT; ++t)
+        if (key[t] >= lo && key[t] <= hi) atomicAdd(&hist[(key[t] - lo) >> sh], 1);
+      __syncthreads();
+      int h[8], local = 0;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        h[q] = hist[8 * lane + q];
+        local += h[q];
+      }
+      int incl = local;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int a = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += a;
+      }
+      const int excl = incl - local;
+      const bool mine = excl < need && need <= incl;
+      int b = 0, cum = 0, hb = 0;
+      if (mine) {
+        cum = excl;
+        b = 8 * lane;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          hb = h[q];
+          if (cum + h[q] >= need) break;
+          cum += h[q];
+          ++b;
+        }
+      }
+      const int src = __ffs(__ballot_sync(0xffffffffu, mine)) - 1;
+      b = __shfl_sync(0xffffffffu, b, src);
+      cum = __shfl_sync(0xffffffffu, cum, src);
+      hb = __shfl_sync(0xffffffffu, hb, src);
+      need -= cum;
+      const unsigned nlo = lo + ((unsigned)b << sh);
+      const unsigned nhi = min(hi, nlo + ((1u << sh) - 1u));
+      if (hb == need) {
+        T = nhi + 1u;
+        need_eq = 0;
+        break;
+      }
+      if (sh == 0) {
+        T = nlo;
+        need_eq = need;
+        break;
+      }
+      lo = nlo;
+      hi = nhi;
+      ++p;
+    }
+  }
+  int32_t* out = nbr + ((int64_t)g * nn + i) * k;
+  int c_lt = 0, c_eq = 0;
+#pragma unroll
+  for (int t = 0; t < KPT; ++t) {
+    const bool in = t < per && j0 + t < nn;
+    c_lt += in && key[t] < T;
+    c_eq += in && key[t] == T;
+  }
+  int s_lt = c_lt, s_eq = c_eq;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int a = __shfl_up_sync(0xffffffffu, s_lt, o), b2 = __shfl_up_sync(0xffffffffu, s_eq, o);
+    if (lane >= o) {
+      s_lt += a;
+      s_eq += b2;
+    }
+  }
+  if (lane == 31) {
+    s_w[0][w] = s_lt;
+    s_w[1][w] = s_eq;
+  }
+  __syncthreads();
+  int off_lt = s_lt - c_lt, off_eq = s_eq - c_eq;
+  for (int q = 0; q < w; ++q) {
+    off_lt += s_w[0][q];
+    off_eq += s_w[1][q];
+  }
+  int pos = off_lt + min(off_eq, need_eq);
+  int eq_rank = off_eq;
+#pragma unroll
+  for (int t = 0; t < KPT; ++t) {
+    if (t < per && j0 + t < nn) {
+      bool sel = key[t] < T;
+      if (key[t] == T) {
+        sel = eq_rank < need_eq;
+        ++eq_rank;
+      }
+      if (sel) {
+        if (pos < k) out[pos] = j0 + t;
+        ++pos;
+      }
+    }
+  }
+}
+
 // --------------------------------------------------------------------------------------------
 // Gaussian similarity of the kept edges (models/mpti.py:745-746) with torch<=1.8
 // pairwise_distance: dist = || f_i - f_j + 1e-6 ||_2 by direct differences, sim = exp(-0.5 (dist/sigma)^2).
@@ -978,12 +1289,29 @@ int launch_affinity(const float* F, int64_t graph_rows, int64_t row_off, const u
     R3DFS_TRY(launch_gram_dist_tc(F, graph_rows, row_off, G, nn, D, norms, D2, st));
   }
   if (sr) sr->mark(R3DFS_ST_DIST, st);
-  size_t smem = sizeof(unsigned) * (size_t)nn;
-  cudaError_t e = cudaFuncSetAttribute(knn_select_kernel,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return (int)e;
-  knn_select_kernel<<<dim3(nn, G), SEL_THREADS, smem, st>>>(D2, valid, nn, k, nbr);
-  R3DFS_CHECK_LAUNCH();
+  static const bool sel_block = getenv("R3DFS_SELECT_BLOCK") != nullptr;
+  if (nn <= 32 * 80 && !sel_block) {
+    const dim3 gs((nn + SELW_WARPS - 1) / SELW_WARPS, G);
+    if (nn <= 32 * 40)
+      knn_select_warp_kernel<40><<<gs, SELW_WARPS * 32, 0, st>>>(D2, valid, nn, k, nbr);
+    else
+      knn_select_warp_kernel<80><<<gs, SELW_WARPS * 32, 0, st>>>(D2, valid, nn, k, nbr);
+    R3DFS_CHECK_LAUNCH();
+  } else if (nn <= 31 * SEL_THREADS && !sel_block) {
+    const size_t smem = sizeof(unsigned) * (size_t)nn;  // <= 31 KB
+    if (nn <= 19 * SEL_THREADS)
+      knn_select_reg_kernel<20><<<dim3(nn, G), SEL_THREADS, smem, st>>>(D2, valid, nn, k, nbr);
+    else
+      knn_select_reg_kernel<32><<<dim3(nn, G), SEL_THREADS, smem, st>>>(D2, valid, nn, k, nbr);
+    R3DFS_CHECK_LAUNCH();
+  } else {
+    size_t smem = sizeof(unsigned) * (size_t)nn;
+    cudaError_t e = cudaFuncSetAttribute(knn_select_kernel,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    knn_select_kernel<<<dim3(nn, G), SEL_THREADS, smem, st>>>(D2, valid, nn, k, nbr);
+    R3DFS_CHECK_LAUNCH();
+  }
   if (sr) sr->mark(R3DFS_ST_SELECT, st);
   edge_sim_kernel<<<dim3((nn + 7) / 8, G), 256, 0, st>>>(F, graph_rows, row_off, nn, D, valid, nbr,
                                                         k, sigma, sim);
