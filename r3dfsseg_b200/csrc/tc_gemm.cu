@@ -42,7 +42,7 @@ __device__ __forceinline__ float4 ld_chunk(const float* __restrict__ src, int64_
 }
 
 // DIST = true turns the epilogue into the squared-distance form used by the affinity graph:
-//     Y[m][n] = (s[m] + t[n]) - 2 * acc      with s = t = squared row norms,
+//     Y[m][n] = (s[m] + t[n]) - 2 * acc      with s = t = squared row norms, X = W (square, BN = 128),
 // and blockIdx.z walks over independent problems `zs` elements apart (X, W, s, t, Y alike).
 template <int BN, bool DIST>
 __global__ __launch_bounds__(TCG_THREADS, 3) void linear_tc_kernel(
@@ -50,6 +50,10 @@ __global__ __launch_bounds__(TCG_THREADS, 3) void linear_tc_kernel(
     const float* __restrict__ t, int act, int64_t M, int K, int Nout, float* __restrict__ Y,
     int ldy, RowMap map, int64_t zs_x, int64_t zs_w, int64_t zs_v, int64_t zs_y) {
   extern __shared__ __align__(128) unsigned char smem[];
+  // the distance matrix is symmetric: only the tiles on and above the diagonal are computed, an
+  // off-diagonal tile is stored twice (as is, and transposed) — half the operand conversion and
+  // tensor work for the same bytes written
+  if (DIST && blockIdx.y < blockIdx.x) return;
   X += blockIdx.z * zs_x;
   W += blockIdx.z * zs_w;
   Y += blockIdx.z * zs_y;
@@ -169,6 +173,13 @@ __global__ __launch_bounds__(TCG_THREADS, 3) void linear_tc_kernel(
         const float sm = (m < M) ? s[m] : 0.f;
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = (sm + ((nb + j < Nout) ? t[nb + j] : 0.f)) - 2.f * v[j];
+        if (blockIdx.y > blockIdx.x && m < M) {
+          // mirrored tile: a lane holds one row, so for a fixed column the warp's 32 values are
+          // consecutive in the transposed row — coalesced as they stand
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (nb + j < Nout) Y[(int64_t)(nb + j) * ldy + m] = v[j];
+        }
       } else {
 #pragma unroll
         for (int j = 0; j < 32; ++j)
