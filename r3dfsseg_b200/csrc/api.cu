@@ -612,7 +612,8 @@ int episode_graph_half(const r3dfs_episode_cfg_t* cfg, const EpisodeDims& d, int
                                    w.in_src, w.in_w, w.dinv, w.rowptr, w.rowlen, w.cursor, w.mcol,
                                    w.mval, w.Z, w.X, w.R, w.P, w.AP,
                                    diag ? diag->cg_iters : nullptr,
-                                   diag ? diag->cg_resid : nullptr, st, sr));
+                                   diag ? diag->cg_resid : nullptr, st, sr, w.D2,
+                                   sizeof(float) * (size_t)E * d.nn * d.nn));  // D2 is dead here
   // query rows -> logits / loss / prediction
   R3DFS_TRY(launch_query_head(w.Z, E, d.nn, d.ppad, d.nq_pts, d.nc, query_y, logits, loss, pred, st));
   if (sr) sr->mark(R3DFS_ST_HEAD, st);

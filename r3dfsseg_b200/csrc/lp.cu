@@ -665,6 +665,67 @@ __global__ void in_fill_kernel(const int32_t* __restrict__ nbr, const float* __r
   in_w[(int64_t)g * nn * k + pos] = sim[ge];
 }
 
+// Sort-free variant of the same lists.  The transposed adjacency is first written as a BIT matrix
+// (bits[j] has bit i set when i -> j; atomicOr is order-independent), a row's word-prefix popcounts
+// give every in-edge its rank among the sources of its column, and the fill writes (source,
+// weight) straight to that rank: the lists come out sorted by source with no atomics on the
+// position and nothing to sort afterwards.
+__global__ void in_bits_kernel(const int32_t* __restrict__ nbr, const uint8_t* __restrict__ valid,
+                               int nn, int k, int W, uint32_t* __restrict__ bits) {
+  const int g = blockIdx.y;
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= (int64_t)nn * k) return;
+  const int i = (int)(e / k);
+  if (!valid[(int64_t)g * nn + i]) return;
+  const int j = nbr[(int64_t)g * nn * k + e];
+  atomicOr(&bits[((int64_t)g * nn + j) * W + (i >> 5)], 1u << (i & 31));
+}
+
+// one warp per column j: exclusive popcount prefix of its words -> pre (uint16), total -> in_cnt
+__global__ __launch_bounds__(256) void in_rank_kernel(const uint32_t* __restrict__ bits, int nn,
+                                                      int W, uint16_t* __restrict__ pre,
+                                                      int32_t* __restrict__ in_cnt) {
+  const int g = blockIdx.y, lane = threadIdx.x & 31;
+  const int j = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (j >= nn) return;
+  const uint32_t* b = bits + ((int64_t)g * nn + j) * W;
+  uint16_t* p = pre + ((int64_t)g * nn + j) * W;
+  int base = 0;
+  for (int w0 = 0; w0 < W; w0 += 32) {
+    const int w = w0 + lane;
+    const int c = w < W ? __popc(b[w]) : 0;
+    int incl = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int a = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += a;
+    }
+    if (w < W) p[w] = (uint16_t)(base + incl - c);
+    base += __shfl_sync(0xffffffffu, incl, 31);
+  }
+  if (lane == 0) in_cnt[(int64_t)g * nn + j] = base;
+}
+
+__global__ void in_fill_rank_kernel(const int32_t* __restrict__ nbr, const float* __restrict__ sim,
+                                    const uint8_t* __restrict__ valid, int nn, int k, int W,
+                                    const uint32_t* __restrict__ bits,
+                                    const uint16_t* __restrict__ pre,
+                                    const int32_t* __restrict__ in_ptr,
+                                    int32_t* __restrict__ in_src, float* __restrict__ in_w) {
+  const int g = blockIdx.y;
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= (int64_t)nn * k) return;
+  const int i = (int)(e / k);
+  if (!valid[(int64_t)g * nn + i]) return;
+  const int64_t ge = (int64_t)g * nn * k + e;
+  const int j = nbr[ge];
+  const int64_t o = ((int64_t)g * nn + j) * W + (i >> 5);
+  const int rank = (int)pre[o] + __popc(bits[o] & ((1u << (i & 31)) - 1u));
+  const int pos = in_ptr[(int64_t)g * (nn + 1) + j] + rank;
+  in_src[(int64_t)g * nn * k + pos] = i;
+  in_w[(int64_t)g * nn * k + pos] = sim[ge];
+}
+
 // Launched twice: a small-capacity pass (segments up to `cap_hi` entries, little shared memory ->
 // many resident CTAs) and a large-capacity pass for the few hub columns (cap_lo < L <= cap_hi).
 __global__ __launch_bounds__(256) void in_sort_kernel(const int32_t* __restrict__ in_ptr, int nn,
@@ -1358,26 +1419,48 @@ int launch_label_propagate(const int32_t* nbr, float* sim, const uint8_t* valid,
                            float* dinv, int32_t* rowptr, int32_t* rowlen, int32_t* cursor,
                            uint16_t* mcol, float* mval, float* Z, float* X, float* R, float* P,
                            float* AP, int32_t* iters_out, float* resid_out, cudaStream_t st,
-                           const StageRec* sr) {
+                           const StageRec* sr, void* scratch, size_t scratch_bytes) {
   if (nc > CG_MAXC || nc < 1 || nn > 8192) return R3DFS_E_UNSUPPORTED;
-  cudaError_t e = cudaMemsetAsync(in_cnt, 0, sizeof(int32_t) * (size_t)G * nn, st);
-  if (e != cudaSuccess) return (int)e;
+  cudaError_t e;
   const int64_t edges = (int64_t)nn * k;
   dim3 ge((unsigned)((edges + 255) / 256), G);
-  in_count_kernel<<<ge, 256, 0, st>>>(nbr, valid, nn, k, in_cnt);
-  R3DFS_CHECK_LAUNCH();
-  in_scan_kernel<<<G, 1024, 0, st>>>(in_cnt, nn, in_ptr);
-  R3DFS_CHECK_LAUNCH();
-  in_fill_kernel<<<ge, 256, 0, st>>>(nbr, sim, valid, nn, k, in_ptr, in_cnt, in_src, in_w);
-  R3DFS_CHECK_LAUNCH();
-  e = cudaFuncSetAttribute(in_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 8192);
-  if (e != cudaSuccess) return (int)e;
-  in_sort_warp_kernel<<<dim3((nn + 7) / 8, G), 256, 0, st>>>(in_ptr, nn, k, in_src, in_w);
-  R3DFS_CHECK_LAUNCH();
-  in_sort_kernel<<<dim3(nn, G), 256, 8 * 1024, st>>>(in_ptr, nn, k, in_src, in_w, 256, 1024);
-  R3DFS_CHECK_LAUNCH();
-  in_sort_kernel<<<dim3(nn, G), 256, 8 * 8192, st>>>(in_ptr, nn, k, in_src, in_w, 1024, 8192);
-  R3DFS_CHECK_LAUNCH();
+  const int W = (nn + 31) / 32;
+  const size_t bits_bytes = sizeof(uint32_t) * (size_t)G * nn * W;
+  const size_t pre_bytes = sizeof(uint16_t) * (size_t)G * nn * W;
+  static const bool force_sort = getenv("R3DFS_INEDGE_SORT") != nullptr;
+  if (scratch && scratch_bytes >= bits_bytes + pre_bytes && !force_sort) {
+    // sort-free: bit matrix of the transposed adjacency -> ranks -> ordered fill
+    uint32_t* bits = reinterpret_cast<uint32_t*>(scratch);
+    uint16_t* pre = reinterpret_cast<uint16_t*>(reinterpret_cast<unsigned char*>(scratch) + bits_bytes);
+    e = cudaMemsetAsync(bits, 0, bits_bytes, st);
+    if (e != cudaSuccess) return (int)e;
+    in_bits_kernel<<<ge, 256, 0, st>>>(nbr, valid, nn, k, W, bits);
+    R3DFS_CHECK_LAUNCH();
+    in_rank_kernel<<<dim3((nn + 7) / 8, G), 256, 0, st>>>(bits, nn, W, pre, in_cnt);
+    R3DFS_CHECK_LAUNCH();
+    in_scan_kernel<<<G, 1024, 0, st>>>(in_cnt, nn, in_ptr);
+    R3DFS_CHECK_LAUNCH();
+    in_fill_rank_kernel<<<ge, 256, 0, st>>>(nbr, sim, valid, nn, k, W, bits, pre, in_ptr, in_src,
+                                            in_w);
+    R3DFS_CHECK_LAUNCH();
+  } else {
+    e = cudaMemsetAsync(in_cnt, 0, sizeof(int32_t) * (size_t)G * nn, st);
+    if (e != cudaSuccess) return (int)e;
+    in_count_kernel<<<ge, 256, 0, st>>>(nbr, valid, nn, k, in_cnt);
+    R3DFS_CHECK_LAUNCH();
+    in_scan_kernel<<<G, 1024, 0, st>>>(in_cnt, nn, in_ptr);
+    R3DFS_CHECK_LAUNCH();
+    in_fill_kernel<<<ge, 256, 0, st>>>(nbr, sim, valid, nn, k, in_ptr, in_cnt, in_src, in_w);
+    R3DFS_CHECK_LAUNCH();
+    e = cudaFuncSetAttribute(in_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 8192);
+    if (e != cudaSuccess) return (int)e;
+    in_sort_warp_kernel<<<dim3((nn + 7) / 8, G), 256, 0, st>>>(in_ptr, nn, k, in_src, in_w);
+    R3DFS_CHECK_LAUNCH();
+    in_sort_kernel<<<dim3(nn, G), 256, 8 * 1024, st>>>(in_ptr, nn, k, in_src, in_w, 256, 1024);
+    R3DFS_CHECK_LAUNCH();
+    in_sort_kernel<<<dim3(nn, G), 256, 8 * 8192, st>>>(in_ptr, nn, k, in_src, in_w, 1024, 8192);
+    R3DFS_CHECK_LAUNCH();
+  }
   dim3 gr((nn + 7) / 8, G);
   e = cudaMemsetAsync(cursor, 0, sizeof(int32_t) * (size_t)G, st);
   if (e != cudaSuccess) return (int)e;

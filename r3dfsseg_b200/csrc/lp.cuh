@@ -11,7 +11,9 @@ int launch_label_propagate(const int32_t* nbr, float* sim, const uint8_t* valid,
                            float* dinv, int32_t* rowptr, int32_t* rowlen, int32_t* cursor,
                            uint16_t* mcol, float* mval, float* Z, float* X, float* R, float* P,
                            float* AP, int32_t* iters_out, float* resid_out, cudaStream_t st,
-                           const StageRec* sr = nullptr);
+                           const StageRec* sr = nullptr, void* scratch = nullptr,
+                           size_t scratch_bytes = 0);
+// scratch (optional): >= 6 * G * nn * ceil(nn / 32) bytes enables the sort-free in-edge build
 int launch_lp_solve(const int32_t* rowptr, const int32_t* rowlen, const uint16_t* mcol,
                     const float* mval, const uint8_t* valid, int G, int nn, int k, const float* Y,
                     int nc, float alpha, float tol, int max_iter, float* Z, float* X, float* R,

@@ -373,7 +373,12 @@ def test_affinity_knn_vs_oracle():
     A_ref = torch.zeros((n, n)).index_put_((vi[:, None].expand(-1, k), I_ref_g), sim_ref)
     both = (A_got > 0) & (A_ref > 0)
     assert both.float().sum() > 0.999 * (A_ref > 0).float().sum()
-    assert torch.allclose(A_got[both], A_ref[both], rtol=1e-5, atol=1e-7)
+    # sim = exp(-d2 / 2): an FP32 rounding difference eps in the 192-term sum d2 (summation order;
+    # the CPU side's order even changes with torch's thread count) shows up as a RELATIVE error
+    # d2 / 2 * eps in sim, so the comparison is made on d2 = -2 log(sim) at FP32-sum accuracy
+    d2_got, d2_ref = -2 * torch.log(A_got[both].double()), -2 * torch.log(A_ref[both].double())
+    assert torch.allclose(d2_got, d2_ref, rtol=2e-5, atol=2e-5)
+    assert torch.allclose(A_got[both], A_ref[both], rtol=3e-4, atol=1e-7)
 
 
 def test_label_propagate_vs_dense_solve():
