@@ -470,13 +470,15 @@ def main():
         stages[name] = ent
     # dominant KERNEL = the kernel with the largest summed device time per call (several stages
     # are launches of the same kernel)
-    kernel_of = {"knn0": "knn_tc2_kernel", "knn1": "knn_tc_kernel", "knn2": "knn_tc_kernel",
+    kernel_of = {"knn0": "knn_tc2_kernel<4>", "knn1": "knn_tc2_kernel<16>",
+                 "knn2": "knn_tc2_kernel<16>",
                  "edge0": "edge_tc_kernel", "edge1": "edge_tc_kernel", "edge2": "edge_tc_kernel",
                  "pq0": "linear_tc_kernel", "pq1": "linear_tc_kernel", "pq2": "linear_tc_kernel",
                  "mlp": "linear_tc_kernel", "base": "linear_tc_kernel", "qkv": "linear_tc_kernel",
                  "att": "attention_tc_kernel", "fps": "fps_kernel", "cg": "lp_cg_kernel",
-                 "dist": "linear_tc_kernel<DIST>", "select": "knn_select_kernel",
-                 "proto": "assign_kernel+proto_mean_kernel", "sym": "in_*_kernel+merge_rows_kernel",
+                 "dist": "linear_tc_kernel<DIST>", "select": "knn_select_reg_kernel",
+                 "proto": "assign_kernel+proto_mean_kernel",
+                 "sym": "in_bits/in_rank/in_fill_rank/merge_rows kernels",
                  "sim": "edge_sim_kernel"}
     launches_of = {"mlp": 2, "base": 2}
     groups = {}

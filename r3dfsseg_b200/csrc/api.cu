@@ -435,8 +435,10 @@ int r3dfs_affinity_knn(const float* node_feat, const uint8_t* valid, int n_graph
 size_t r3dfs_label_propagate_workspace(int n_graphs, int64_t n_max, int k, int n_cls) {
   const size_t G = n_graphs, n = n_max;
   (void)n_cls;
+  const size_t W = (n + 31) / 32;  // bit matrix + rank prefixes of the sort-free in-edge build
   return align_up(4 * G * n * k, 256) * 3 + align_up(4 * G * (n + 1), 256) * 6 +
-         align_up(4 * G * n * 8, 256) * 4 + align_up(6 * G * n * k * 2, 256) + 8192;
+         align_up(4 * G * n * 8, 256) * 4 + align_up(6 * G * n * k * 2, 256) +
+         align_up(6 * G * n * W, 256) + 8192;
 }
 
 int r3dfs_label_propagate(const int32_t* nbr, const float* sim, const uint8_t* valid, int n_graphs,
@@ -466,12 +468,15 @@ int r3dfs_label_propagate(const int32_t* nbr, const float* sim, const uint8_t* v
   float* R = ws.take<float>(G * n * 8);
   float* P = ws.take<float>(G * n * 8);
   float* AP = ws.take<float>(G * n * 8);
+  const size_t scratch_bytes = 6 * G * n * ((n + 31) / 32);
+  unsigned char* scratch = ws.take<unsigned char>(scratch_bytes);
   if (!ws.ok()) return R3DFS_E_WORKSPACE;
   cudaError_t ce = cudaMemcpyAsync(sv, sim, sizeof(float) * G * n * k, cudaMemcpyDeviceToDevice, st);
   if (ce != cudaSuccess) return (int)ce;
   return launch_label_propagate(nbr, sv, valid, n_graphs, (int)n_max, k, Y, n_cls, alpha, tol,
                                 max_iter, in_cnt, in_ptr, in_src, in_w, dinv, rowptr, rowlen, cursor,
-                                mcol, mval, Z, X, R, P, AP, iters_out, resid_out, st);
+                                mcol, mval, Z, X, R, P, AP, iters_out, resid_out, st, nullptr,
+                                scratch, scratch_bytes);
 }
 
 // ---- confusion counters ----------------------------------------------------------------------------
@@ -573,7 +578,7 @@ int episode_graph_half(const r3dfs_episode_cfg_t* cfg, const EpisodeDims& d, int
                               const EpisodeWs& w, const float* support_x, int64_t s_e,
                               int64_t s_cloud, int64_t s_c, int64_t s_n, const int32_t* support_y,
                               const int64_t* query_y, float* logits, float* loss, int32_t* pred,
-                              const r3dfs_episode_diag_t* diag, cudaStream_t st) {
+                              const r3dfs_episode_diag_t* diag, cudaStream_t st, bool latency) {
   const int N = cfg->n_points, D = R3DFS_FEAT_DIM;
   StageRec srv{diag ? (cudaEvent_t*)diag->h_stage_events : nullptr};
   const StageRec* sr = srv.ev ? &srv : nullptr;
@@ -613,7 +618,8 @@ int episode_graph_half(const r3dfs_episode_cfg_t* cfg, const EpisodeDims& d, int
                                    w.mval, w.Z, w.X, w.R, w.P, w.AP,
                                    diag ? diag->cg_iters : nullptr,
                                    diag ? diag->cg_resid : nullptr, st, sr, w.D2,
-                                   sizeof(float) * (size_t)E * d.nn * d.nn));  // D2 is dead here
+                                   sizeof(float) * (size_t)E * d.nn * d.nn,  // D2 is dead here
+                                   latency));
   // query rows -> logits / loss / prediction
   R3DFS_TRY(launch_query_head(w.Z, E, d.nn, d.ppad, d.nq_pts, d.nc, query_y, logits, loss, pred, st));
   if (sr) sr->mark(R3DFS_ST_HEAD, st);

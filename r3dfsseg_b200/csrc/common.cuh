@@ -83,6 +83,8 @@ __device__ __forceinline__ float warp_sum(float v) {
 int launch_to_point_major(const float* x, int64_t B, int64_t C, int64_t N, int64_t sb, int64_t sc,
                           int64_t sn, float* out, cudaStream_t st);
 int launch_row_norms(const float* x, int64_t rows, int ld, int C, float* out, cudaStream_t st);
+int launch_row_norms_batched(const float* x, int64_t xs, int batch, int64_t rows, int ld, int C,
+                             float* out, cudaStream_t st);
 int launch_knn(const float* x, int ld, int C, const float* xx, int64_t B, int N, int k,
                int32_t* idx32, int64_t* idx64, cudaStream_t st);
 int launch_knn_tc(const float* x, int ld, int C, const float* xx, int64_t B, int N, int k,

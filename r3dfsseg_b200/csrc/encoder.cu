@@ -45,6 +45,30 @@ __global__ void row_norms_kernel(const float* __restrict__ x, int64_t rows, int 
   if (lane == 0) out[r] = s;
 }
 
+// the same for `batch` matrices `xs` floats apart (out: `rows` norms per matrix, dense) — one launch
+__global__ void row_norms_batched_kernel(const float* __restrict__ x, int64_t xs, int64_t rows,
+                                         int ld, int C, float* __restrict__ out) {
+  int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  int lane = threadIdx.x & 31;
+  if (r >= rows) return;
+  const float* p = x + blockIdx.y * xs + r * (int64_t)ld;
+  float s = 0.f;
+  for (int c = lane; c < C; c += 32) {
+    float v = p[c];
+    s = fmaf(v, v, s);
+  }
+  s = warp_sum(s);
+  if (lane == 0) out[blockIdx.y * rows + r] = s;
+}
+
+int launch_row_norms_batched(const float* x, int64_t xs, int batch, int64_t rows, int ld, int C,
+                             float* out, cudaStream_t st) {
+  row_norms_batched_kernel<<<dim3((unsigned)((rows + 7) / 8), batch), 256, 0, st>>>(x, xs, rows, ld,
+                                                                                  C, out);
+  R3DFS_CHECK_LAUNCH();
+  return 0;
+}
+
 int launch_row_norms(const float* x, int64_t rows, int ld, int C, float* out, cudaStream_t st) {
   int threads = 256;
   int64_t blocks = (rows + 7) / 8;

@@ -59,4 +59,4 @@ int episode_graph_half(const r3dfs_episode_cfg_t* cfg, const EpisodeDims& d, int
                        const EpisodeWs& w, const float* support_x, int64_t s_e, int64_t s_cloud,
                        int64_t s_c, int64_t s_n, const int32_t* support_y, const int64_t* query_y,
                        float* logits, float* loss, int32_t* pred, const r3dfs_episode_diag_t* diag,
-                       cudaStream_t st);
+                       cudaStream_t st, bool latency = false);

@@ -1274,6 +1274,381 @@ static int launch_cg(int CL, int G, size_t smem, cudaStream_t st, const int32_t*
 }
 
 // --------------------------------------------------------------------------------------------
+// Same solve, matrix resident in SHARED memory.  The grid is one CTA per SM, cut into groups of GS
+// CTAs; a group solves one graph at a time (graphs group, group + n_groups, ...).  A CTA owns a
+// slice of the rows and copies their (col, val) lists into its shared memory once — with 37 CTAs
+// per 4416-node graph that is ~190 KB per CTA, so the 60-odd sparse products of the solve never
+// touch L2/HBM again (the cluster kernel streams ~7 MB per graph per iteration and is bound by
+// exactly that).  Rows that do not fit stay in global memory and are streamed as before.
+//   - x, r, Ap of the slice live in shared memory; only P goes through global memory (each CTA
+//     publishes its rows, all CTAs restage the whole vector);
+//   - CTAs of a group meet at a counter barrier in global memory (co-residency comes from the
+//     cooperative launch); dot products go through per-CTA slots and are summed in rank order by
+//     every CTA, so all CTAs see bit-identical scalars and the control flow stays group-uniform.
+// --------------------------------------------------------------------------------------------
+#define GCG_SLOT 8  // floats per CTA slot
+#define GCG_MAX_GS 160
+
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+__device__ __forceinline__ void group_barrier(unsigned* cnt, unsigned& target, int GS) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    target += (unsigned)GS;
+    __threadfence();
+    atomicAdd(cnt, 1u);
+    while (ld_acquire_u32(cnt) < target) {
+    }
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+// sum of every thread's part[] over the CTA -> slot of this CTA; barrier; total over the group
+template <int NCV>
+__device__ __forceinline__ void group_allreduce(float* s_warp, float* s_slot, const float* part,
+                                                float* slots, int rank, int GS, unsigned* cnt,
+                                                unsigned& target, int& phase, float* total) {
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  float v[NCV];
+#pragma unroll
+  for (int c = 0; c < NCV; ++c) v[c] = warp_sum(part[c]);
+  if (lane == 0) {
+#pragma unroll
+    for (int c = 0; c < NCV; ++c) s_warp[w * CG_MAXC + c] = v[c];
+  }
+  __syncthreads();
+  float* my = slots + ((size_t)(phase & 1) * GS + rank) * GCG_SLOT;
+  if (tid < NCV) {
+    float s = 0.f;
+    for (int q = 0; q < CG_THREADS / 32; ++q) s += s_warp[q * CG_MAXC + tid];
+    __stcg(my + tid, s);
+  }
+  group_barrier(cnt, target, GS);
+  // one L2 round trip: thread r fetches CTA r's slot, then everybody sums the copies in rank order
+  const float* all = slots + (size_t)(phase & 1) * GS * GCG_SLOT;
+  if (tid < GS) {
+#pragma unroll
+    for (int q = 0; q < NCV / 4; ++q)
+      reinterpret_cast<float4*>(s_slot + tid * GCG_SLOT)[q] =
+          __ldcg(reinterpret_cast<const float4*>(all + (size_t)tid * GCG_SLOT) + q);
+  }
+  __syncthreads();
+#pragma unroll
+  for (int c = 0; c < NCV; ++c) total[c] = 0.f;
+  for (int r = 0; r < GS; ++r) {
+#pragma unroll
+    for (int q = 0; q < NCV / 4; ++q) {
+      const float4 t4 = reinterpret_cast<const float4*>(s_slot + r * GCG_SLOT)[q];
+      total[4 * q + 0] += t4.x;
+      total[4 * q + 1] += t4.y;
+      total[4 * q + 2] += t4.z;
+      total[4 * q + 3] += t4.w;
+    }
+  }
+  ++phase;
+}
+
+template <int NCV, bool SMEM>
+__device__ __forceinline__ void cg_row_product(const uint16_t* crow, const float* vrow, int L,
+                                               int lane, const float* Ps, float* acc) {
+  int t0 = 0;
+  for (; t0 + 256 <= L; t0 += 256) {
+    int cj[8];
+    float cv[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int t = t0 + lane + 32 * u;
+      cj[u] = (int)crow[t];
+      cv[u] = vrow[t];
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+#pragma unroll
+      for (int q = 0; q < NCV / 4; ++q) {
+        const float4 p4 = *reinterpret_cast<const float4*>(Ps + (int64_t)cj[u] * NCV + 4 * q);
+        acc[4 * q + 0] = fmaf(cv[u], p4.x, acc[4 * q + 0]);
+        acc[4 * q + 1] = fmaf(cv[u], p4.y, acc[4 * q + 1]);
+        acc[4 * q + 2] = fmaf(cv[u], p4.z, acc[4 * q + 2]);
+        acc[4 * q + 3] = fmaf(cv[u], p4.w, acc[4 * q + 3]);
+      }
+    }
+  }
+  for (; t0 < L; t0 += 32) {
+    const int t = t0 + lane;
+    if (t < L) {
+      const int cj = (int)crow[t];
+      const float cv = vrow[t];
+#pragma unroll
+      for (int q = 0; q < NCV / 4; ++q) {
+        const float4 p4 = *reinterpret_cast<const float4*>(Ps + (int64_t)cj * NCV + 4 * q);
+        acc[4 * q + 0] = fmaf(cv, p4.x, acc[4 * q + 0]);
+        acc[4 * q + 1] = fmaf(cv, p4.y, acc[4 * q + 1]);
+        acc[4 * q + 2] = fmaf(cv, p4.z, acc[4 * q + 2]);
+        acc[4 * q + 3] = fmaf(cv, p4.w, acc[4 * q + 3]);
+      }
+    }
+  }
+}
+
+template <int NCV>
+__global__ __launch_bounds__(CG_THREADS, 1) void lp_cg_group_kernel(
+    const int32_t* __restrict__ rowptr, const int32_t* __restrict__ rowlen,
+    const uint16_t* __restrict__ mcol, const float* __restrict__ mval,
+    const uint8_t* __restrict__ valid, int G, int nn, int k, const float* __restrict__ Y, int nc,
+    float alpha, float tol, int max_iter, float* __restrict__ Z, float* __restrict__ Pv,
+    unsigned* __restrict__ counters, float* __restrict__ slots_all, int GS, int rows_max,
+    int cache_entries, int32_t* __restrict__ iters_out, float* __restrict__ resid_out) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  // [Ps nn*NCV f32][xs rows_max*NCV][rs rows_max*NCV][aps rows_max*NCV][off rows_max i32]
+  // [vals cache_entries f32][cols cache_entries u16]
+  float* Ps = reinterpret_cast<float*>(smem_raw);
+  float* xs = Ps + (size_t)nn * NCV;
+  float* rsm = xs + (size_t)rows_max * NCV;
+  float* aps = rsm + (size_t)rows_max * NCV;
+  int* s_off = reinterpret_cast<int*>(aps + (size_t)rows_max * NCV);
+  float* c_val = reinterpret_cast<float*>(s_off + rows_max);
+  uint16_t* c_col = reinterpret_cast<uint16_t*>(c_val + cache_entries);
+  __shared__ float s_warp[(CG_THREADS / 32) * CG_MAXC];
+  __shared__ __align__(16) float s_slot[GCG_MAX_GS * GCG_SLOT];
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int group = blockIdx.x / GS, rank = blockIdx.x % GS, n_groups = gridDim.x / GS;
+  if (group >= n_groups) return;  // leftover CTAs (grid not a multiple of GS)
+  unsigned* cnt = counters + group * 32;  // one counter per 128-byte line
+  float* slots = slots_all + (size_t)group * 2 * GS * GCG_SLOT;
+  unsigned target = 0;
+  int phase = 0;
+  const int chunk = (nn + GS - 1) / GS;
+  const int lo = min(nn, rank * chunk), hi = min(nn, lo + chunk);
+  const int nrows = hi - lo;
+  const float tol2 = tol * tol;
+
+  for (int g = group; g < G; g += n_groups) {
+    const int64_t vb = (int64_t)g * nn;
+    const uint8_t* vg = valid + vb;
+    const float* Yg = Y + vb * nc;
+    float* Zg = Z + vb * nc;
+    float* Pg = Pv + vb * NCV;
+    const int32_t* rp = rowptr + vb;
+    const int32_t* rl = rowlen + vb;
+    const uint16_t* mc = mcol + vb * k * 2;
+    const float* mv = mval + vb * k * 2;
+    // ---- cache my rows' lists: offsets by one warp's scan, then a cooperative copy
+    if (w == 0) {
+      int base = 0;
+      for (int r0 = 0; r0 < nrows; r0 += 32) {
+        const int r = r0 + lane;
+        const int L = (r < nrows && vg[lo + r]) ? rl[lo + r] : 0;
+        int incl = L;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int a = __shfl_up_sync(0xffffffffu, incl, o);
+          if (lane >= o) incl += a;
+        }
+        const int off = base + incl - L;
+        if (r < nrows) s_off[r] = (off + L <= cache_entries) ? off : -1;
+        base += __shfl_sync(0xffffffffu, incl, 31);
+      }
+    }
+    __syncthreads();
+    for (int r = w; r < nrows; r += CG_THREADS / 32) {
+      const int off = s_off[r];
+      if (off < 0 || !vg[lo + r]) continue;
+      const int L = rl[lo + r];
+      const uint16_t* crow = mc + rp[lo + r];
+      const float* vrow = mv + rp[lo + r];
+      for (int t = lane; t < L; t += 32) {
+        c_col[off + t] = crow[t];
+        c_val[off + t] = vrow[t];
+      }
+    }
+    // ---- x = 0, r = p = y
+    float part[NCV], bb[NCV], rs[NCV], tot[NCV];
+#pragma unroll
+    for (int c = 0; c < NCV; ++c) part[c] = 0.f;
+    for (int r = tid; r < nrows; r += CG_THREADS) {
+      const int row = lo + r;
+      const bool ok = vg[row];
+      float y[NCV];
+#pragma unroll
+      for (int c = 0; c < NCV; ++c) {
+        y[c] = (ok && c < nc) ? Yg[(int64_t)row * nc + c] : 0.f;
+        xs[r * NCV + c] = 0.f;
+        rsm[r * NCV + c] = y[c];
+        aps[r * NCV + c] = 0.f;
+        part[c] = fmaf(y[c], y[c], part[c]);
+      }
+#pragma unroll
+      for (int q = 0; q < NCV / 4; ++q)
+        __stcg(reinterpret_cast<float4*>(Pg + (int64_t)row * NCV) + q,
+               make_float4(y[4 * q], y[4 * q + 1], y[4 * q + 2], y[4 * q + 3]));
+    }
+    group_allreduce<NCV>(s_warp, s_slot, part, slots, rank, GS, cnt, target, phase, bb);  // publishes P too
+    bool done[NCV];
+    bool all_done = true;
+#pragma unroll
+    for (int c = 0; c < NCV; ++c) {
+      rs[c] = bb[c];
+      done[c] = !(bb[c] > 0.f);
+      all_done = all_done && done[c];
+    }
+    int it = 0;
+    while (!all_done && it < max_iter) {
+      {  // stage P
+        const float4* src = reinterpret_cast<const float4*>(Pg);
+        float4* dst = reinterpret_cast<float4*>(Ps);
+        const int n4 = nn * (NCV / 4);
+        for (int i4 = tid; i4 < n4; i4 += CG_THREADS) dst[i4] = __ldcg(src + i4);
+      }
+      __syncthreads();
+#pragma unroll
+      for (int c = 0; c < NCV; ++c) part[c] = 0.f;
+      for (int r = w; r < nrows; r += CG_THREADS / 32) {
+        const int row = lo + r;
+        if (!vg[row]) continue;
+        float acc[NCV];
+#pragma unroll
+        for (int c = 0; c < NCV; ++c) acc[c] = 0.f;
+        const int L = rl[row];
+        const int off = s_off[r];
+        if (off >= 0)
+          cg_row_product<NCV, true>(c_col + off, c_val + off, L, lane, Ps, acc);
+        else
+          cg_row_product<NCV, false>(mc + rp[row], mv + rp[row], L, lane, Ps, acc);
+#pragma unroll
+        for (int c = 0; c < NCV; ++c) {
+          const float s = warp_sum(acc[c]);
+          const float p = Ps[(int64_t)row * NCV + c];
+          const float ap = p - alpha * s;
+          if (lane == 0) {
+            aps[r * NCV + c] = ap;
+            part[c] = fmaf(p, ap, part[c]);
+          }
+        }
+      }
+      group_allreduce<NCV>(s_warp, s_slot, part, slots, rank, GS, cnt, target, phase, tot);
+      float a[NCV];
+#pragma unroll
+      for (int c = 0; c < NCV; ++c) a[c] = (!done[c] && tot[c] > 0.f) ? rs[c] / tot[c] : 0.f;
+#pragma unroll
+      for (int c = 0; c < NCV; ++c) part[c] = 0.f;
+      for (int r = tid; r < nrows; r += CG_THREADS) {
+#pragma unroll
+        for (int c = 0; c < NCV; ++c) {
+          const int o = r * NCV + c;
+          const float rr = rsm[o] - a[c] * aps[o];
+          xs[o] = fmaf(a[c], Ps[(int64_t)(lo + r) * NCV + c], xs[o]);
+          rsm[o] = rr;
+          part[c] = fmaf(rr, rr, part[c]);
+        }
+      }
+      group_allreduce<NCV>(s_warp, s_slot, part, slots, rank, GS, cnt, target, phase, tot);
+      float beta[NCV];
+      all_done = true;
+#pragma unroll
+      for (int c = 0; c < NCV; ++c) {
+        beta[c] = (!done[c] && rs[c] > 0.f) ? tot[c] / rs[c] : 0.f;
+        if (!done[c]) {
+          rs[c] = tot[c];
+          if (tot[c] <= tol2 * bb[c]) done[c] = true;
+        }
+        all_done = all_done && done[c];
+      }
+      ++it;
+      if (all_done || it >= max_iter) break;  // group-uniform: nobody needs the next P
+      for (int r = tid; r < nrows; r += CG_THREADS) {
+        const int row = lo + r;
+        float pn[NCV];
+#pragma unroll
+        for (int c = 0; c < NCV; ++c) {
+          const float pold = Ps[(int64_t)row * NCV + c];
+          pn[c] = done[c] ? pold : fmaf(beta[c], pold, rsm[r * NCV + c]);
+        }
+#pragma unroll
+        for (int q = 0; q < NCV / 4; ++q)
+          __stcg(reinterpret_cast<float4*>(Pg + (int64_t)row * NCV) + q,
+                 make_float4(pn[4 * q], pn[4 * q + 1], pn[4 * q + 2], pn[4 * q + 3]));
+      }
+      group_barrier(cnt, target, GS);  // publish P
+    }
+    for (int r = tid; r < nrows; r += CG_THREADS)
+      for (int c = 0; c < nc; ++c) Zg[(int64_t)(lo + r) * nc + c] = xs[r * NCV + c];
+    if (rank == 0 && tid == 0) {
+      if (iters_out) iters_out[g] = it;
+      if (resid_out) {
+        float m = 0.f;
+#pragma unroll
+        for (int c = 0; c < NCV; ++c)
+          if (bb[c] > 0.f) m = fmaxf(m, sqrtf(rs[c] / bb[c]));
+        resid_out[g] = m;
+      }
+    }
+    __syncthreads();  // the slice buffers are reused by the next graph
+  }
+}
+
+// scratch (global): 32 counters lines + slots; taken from the AP buffer the cluster kernel uses
+template <int NCV>
+static int launch_cg_group(int G, cudaStream_t st, const int32_t* rowptr, const int32_t* rowlen,
+                           const uint16_t* mcol, const float* mval, const uint8_t* valid, int nn,
+                           int k, const float* Y, int nc, float alpha, float tol, int max_iter,
+                           float* Z, float* P, float* scratch, size_t scratch_floats,
+                           int32_t* iters_out, float* resid_out) {
+  static int n_sm = 0, coop = 0, smem_max = 0;
+  if (n_sm == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+    cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+  }
+  if (!coop || n_sm < 8) return -1000;
+  static const int gs_env = [] {
+    const char* e = getenv("R3DFS_CG_GROUP");
+    return e ? atoi(e) : 0;
+  }();
+  // CTAs per graph: as few as keep (almost) the whole matrix in shared memory, so that as many
+  // graphs as possible are in flight; never more groups than graphs
+  // measured on the single graph of a training step (4416 nodes): 74 CTAs beat 37, 110 and 148 —
+  // more CTAs shorten the row slices but every CTA restages the whole of P and joins every barrier
+  int n_groups = gs_env > 0 ? min(32, max(1, n_sm / gs_env)) : min(G, 4);
+  int GS = min(GCG_MAX_GS, gs_env > 0 ? gs_env : min(74, n_sm / n_groups));
+  const int rows_max = (nn + GS - 1) / GS;
+  const size_t fixed = sizeof(float) * ((size_t)nn * NCV + 3 * (size_t)rows_max * NCV) +
+                       sizeof(int) * (size_t)rows_max;
+  const size_t smem = (size_t)smem_max - 8 * 1024;  // minus the kernel's static shared memory
+  if (fixed + 6 * 1024 > smem) return -1000;
+  const int cache_entries = (int)(((smem - fixed) / 6) & ~(size_t)7);
+  const size_t need_scratch = 32 * 32 + (size_t)n_groups * 2 * GS * GCG_SLOT;
+  if (need_scratch > scratch_floats) return -1000;
+  cudaError_t e = cudaFuncSetAttribute(lp_cg_group_kernel<NCV>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  e = cudaMemsetAsync(scratch, 0, 32 * 32 * sizeof(unsigned), st);
+  if (e != cudaSuccess) return (int)e;
+  unsigned* counters = reinterpret_cast<unsigned*>(scratch);
+  float* slots = scratch + 32 * 32;
+  int grid = n_groups * GS;
+  void* args[] = {(void*)&rowptr, (void*)&rowlen, (void*)&mcol, (void*)&mval, (void*)&valid,
+                  (void*)&G, (void*)&nn, (void*)&k, (void*)&Y, (void*)&nc, (void*)&alpha,
+                  (void*)&tol, (void*)&max_iter, (void*)&Z, (void*)&P, (void*)&counters,
+                  (void*)&slots, (void*)&GS, (void*)&rows_max, (void*)&cache_entries,
+                  (void*)&iters_out, (void*)&resid_out};
+  e = cudaLaunchCooperativeKernel((const void*)lp_cg_group_kernel<NCV>, dim3(grid), dim3(CG_THREADS),
+                                  args, smem, st);
+  if (e != cudaSuccess) {
+    (void)cudaGetLastError();
+    return -1000;
+  }
+  ++r3dfs_launches;
+  return 0;
+}
+
+// --------------------------------------------------------------------------------------------
 // Query rows of Z -> logits, argmax prediction (models/mpti_learner.py:98) and the mean
 // cross-entropy (models/mpti.py:571).  One CTA per episode, fixed-order reduction.
 // --------------------------------------------------------------------------------------------
@@ -1339,9 +1714,7 @@ int launch_affinity(const float* F, int64_t graph_rows, int64_t row_off, const u
                     int G, int nn, int D, int k, float sigma, float* norms, float* D2, int32_t* nbr,
                     float* sim, cudaStream_t st, const StageRec* sr) {
   if (D % 4 != 0 || D > 32 * LP_MAX_F4 || k > 1024 || nn > 65535) return R3DFS_E_UNSUPPORTED;
-  for (int g = 0; g < G; ++g)
-    R3DFS_TRY(launch_row_norms(F + ((int64_t)g * graph_rows + row_off) * D, nn, D, D,
-                               norms + (int64_t)g * nn, st));
+  R3DFS_TRY(launch_row_norms_batched(F + row_off * D, graph_rows * D, G, nn, D, D, norms, st));
   if (simt_gemm_forced()) {
     dim3 gd((nn + GD_BM - 1) / GD_BM, (nn + GD_BN - 1) / GD_BN, G);
     gram_dist_kernel<<<gd, 256, 0, st>>>(F, graph_rows, row_off, nn, D, norms, D2);
@@ -1386,13 +1759,24 @@ int launch_affinity(const float* F, int64_t graph_rows, int64_t row_off, const u
 int launch_lp_solve(const int32_t* rowptr, const int32_t* rowlen, const uint16_t* mcol,
                     const float* mval, const uint8_t* valid, int G, int nn, int k, const float* Y,
                     int nc, float alpha, float tol, int max_iter, float* Z, float* X, float* R,
-                    float* P, float* AP, int32_t* iters_out, float* resid_out, cudaStream_t st) {
+                    float* P, float* AP, int32_t* iters_out, float* resid_out, cudaStream_t st,
+                    bool latency) {
   if (nc > CG_MAXC || nc < 1 || nn > 8192) return R3DFS_E_UNSUPPORTED;
   // padded vector width: one or two float4 per node
   const int ncv = nc <= 4 ? 4 : 8;
   const size_t smem_cg = sizeof(float) * (size_t)nn * ncv;
   if (smem_cg > 200 * 1024) return R3DFS_E_UNSUPPORTED;
   int rc = -1000;
+  static const bool no_group = getenv("R3DFS_CG_NOGROUP") != nullptr;
+  if (latency && !no_group) {  // matrix resident in shared memory, groups of CTAs (cooperative launch)
+    const size_t scratch_floats = (size_t)G * nn * ncv;
+    rc = ncv == 4 ? launch_cg_group<4>(G, st, rowptr, rowlen, mcol, mval, valid, nn, k, Y, nc, alpha,
+                                       tol, max_iter, Z, P, AP, scratch_floats, iters_out, resid_out)
+                  : launch_cg_group<8>(G, st, rowptr, rowlen, mcol, mval, valid, nn, k, Y, nc, alpha,
+                                       tol, max_iter, Z, P, AP, scratch_floats, iters_out, resid_out);
+    if (rc == 0) return 0;
+    if (rc != -1000) return rc;
+  }
   static const int cl_first = [] {  // A/B switch: R3DFS_CG_CLUSTER = 16 | 8 | 4 | 2
     const char* e = getenv("R3DFS_CG_CLUSTER");
     const int v = e ? atoi(e) : 0;
@@ -1419,7 +1803,7 @@ int launch_label_propagate(const int32_t* nbr, float* sim, const uint8_t* valid,
                            float* dinv, int32_t* rowptr, int32_t* rowlen, int32_t* cursor,
                            uint16_t* mcol, float* mval, float* Z, float* X, float* R, float* P,
                            float* AP, int32_t* iters_out, float* resid_out, cudaStream_t st,
-                           const StageRec* sr, void* scratch, size_t scratch_bytes) {
+                           const StageRec* sr, void* scratch, size_t scratch_bytes, bool latency) {
   if (nc > CG_MAXC || nc < 1 || nn > 8192) return R3DFS_E_UNSUPPORTED;
   cudaError_t e;
   const int64_t edges = (int64_t)nn * k;
@@ -1478,7 +1862,7 @@ int launch_label_propagate(const int32_t* nbr, float* sim, const uint8_t* valid,
   if (sr) sr->mark(R3DFS_ST_SYM, st);
 
   R3DFS_TRY(launch_lp_solve(rowptr, rowlen, mcol, mval, valid, G, nn, k, Y, nc, alpha, tol, max_iter,
-                            Z, X, R, P, AP, iters_out, resid_out, st));
+                            Z, X, R, P, AP, iters_out, resid_out, st, latency));
   if (sr) sr->mark(R3DFS_ST_CG, st);
   return 0;
 }

@@ -12,12 +12,16 @@ int launch_label_propagate(const int32_t* nbr, float* sim, const uint8_t* valid,
                            uint16_t* mcol, float* mval, float* Z, float* X, float* R, float* P,
                            float* AP, int32_t* iters_out, float* resid_out, cudaStream_t st,
                            const StageRec* sr = nullptr, void* scratch = nullptr,
-                           size_t scratch_bytes = 0);
+                           size_t scratch_bytes = 0, bool latency = false);
 // scratch (optional): >= 6 * G * nn * ceil(nn / 32) bytes enables the sort-free in-edge build
 int launch_lp_solve(const int32_t* rowptr, const int32_t* rowlen, const uint16_t* mcol,
                     const float* mval, const uint8_t* valid, int G, int nn, int k, const float* Y,
                     int nc, float alpha, float tol, int max_iter, float* Z, float* X, float* R,
-                    float* P, float* AP, int32_t* iters_out, float* resid_out, cudaStream_t st);
+                    float* P, float* AP, int32_t* iters_out, float* resid_out, cudaStream_t st,
+                    bool latency = false);
+// latency = true (a handful of graphs, e.g. the single episode of a training step): the whole GPU
+// works on min(G, 4) graphs at a time with the matrix resident in shared memory (lp_cg_group_kernel);
+// the default is one thread-block cluster per graph, which has the higher throughput on a batch.
 // X, R, P, AP: (G, nn, 8) scratch; rowptr/rowlen: (G, nn); cursor: (G); mcol/mval: (G, 2*nn*k)
 int launch_query_head(const float* Z, int G, int nn, int q_off, int nq, int nc, const int64_t* qy,
                       float* logits, float* loss, int32_t* pred, cudaStream_t st);

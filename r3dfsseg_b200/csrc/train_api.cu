@@ -460,7 +460,7 @@ int r3dfs_mpti_train_forward(const r3dfs_episode_cfg_t* cfg_in, int in_dim, int 
   r3dfs_episode_diag_t diag = {};
   diag.cg_iters = cg_iters;
   R3DFS_TRY(episode_graph_half(&cfg, d, 1, t.ep, support_x, 0, s_cloud, s_c, s_n, support_y, query_y,
-                               logits, t.loss_way + 7, nullptr, &diag, st));
+                               logits, t.loss_way + 7, nullptr, &diag, st, /*latency=*/true));
   // way-contrast loss on fps_k = 4 prototypes of every shot's foreground (models/mpti.py:226-313);
   // the shots' foreground rows are contiguous sub-ranges of the compacted set buffer
   const int cslot = CONTRAST_FPS_K + 1;
@@ -514,7 +514,7 @@ int r3dfs_mpti_train_backward(const r3dfs_episode_cfg_t* cfg_in, int in_dim, int
   R3DFS_TRY(launch_ce_grad(w.Z, nn, d.ppad, d.nq_pts, nc, query_y, w_lp, t.dZ, st));
   R3DFS_TRY(launch_lp_solve(w.rowptr, w.rowlen, w.mcol, w.mval, w.valid, 1, nn, kc, t.dZ, nc,
                             cfg.alpha, cfg.cg_tol, cfg.cg_max_iter, t.Gm, w.X, w.R, w.P, w.AP,
-                            nullptr, nullptr, st));
+                            nullptr, nullptr, st, /*latency=*/true));
   R3DFS_TRY(launch_lp_adjoint_edges(w.rowptr, w.rowlen, w.mcol, w.mval, w.dinv, w.valid, w.nbr, w.sim,
                                     nn, kc, nc, w.Z, t.Gm, cfg.alpha, cfg.sigma, t.dD, t.gE, st));
   R3DFS_TRY(launch_sim_bwd(w.F, D, w.valid, w.nbr, t.gE, nn, kc, t.dF, st));
