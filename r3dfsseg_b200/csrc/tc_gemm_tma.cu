@@ -61,8 +61,11 @@ __global__ __launch_bounds__(TM_ALL_THREADS, 2) void linear_tma_kernel(
   __shared__ uint32_t tmem_base_s;
   __shared__ float s_sc[BN], s_sh[BN];
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-  const int m0 = blockIdx.x * TM_BM;
-  const int n0 = blockIdx.y * BN;
+  // the n-tiles of one m-tile are neighbours in launch order, so the X tile they all read comes
+  // from DRAM once and from L2 afterwards (with m fastest every n-tile re-read X from DRAM)
+  const int n_tiles = (Nout + BN - 1) / BN;
+  const int m0 = (blockIdx.x / n_tiles) * TM_BM;
+  const int n0 = (blockIdx.x % n_tiles) * BN;
   constexpr int LBO_A = tc::tile_lbo(TM_BM), LBO_B = tc::tile_lbo(BN);
   constexpr uint32_t IDESC = tc::make_idesc_tf32(TM_BM, BN);
   constexpr int A_CH = TM_BM * TM_KC4 / TM_THREADS;  // 2
@@ -241,7 +244,7 @@ static int launch_tma_bn(const CUtensorMap& tx, const CUtensorMap& tw, const flo
   cudaError_t e = cudaFuncSetAttribute(linear_tma_kernel<BN>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
   if (e != cudaSuccess) return (int)e;
-  dim3 grid((unsigned)((M + TM_BM - 1) / TM_BM), (Nout + BN - 1) / BN);
+  dim3 grid((unsigned)(((M + TM_BM - 1) / TM_BM) * ((Nout + BN - 1) / BN)));
   linear_tma_kernel<BN><<<grid, TM_ALL_THREADS, S::TOTAL, st>>>(tx, tw, s, t, act, M, K, Nout, Y, ldy,
                                                             map);
   R3DFS_CHECK_LAUNCH();
