@@ -16,7 +16,7 @@ namespace cg = cooperative_groups;
 // (sum (x - s)^2): the Gram form is not accurate enough to reproduce the pick sequence.
 // --------------------------------------------------------------------------------------------
 #define FPS_THREADS 512
-#define FPS_MAX_CL 8
+#define FPS_MAX_CL 16
 #define FPS_MAX_F4 8  // per-lane float4 fragments -> D <= 256
 
 __device__ __forceinline__ int fps_target_count(int n, int k) {
@@ -161,32 +161,57 @@ __global__ __launch_bounds__(FPS_THREADS) void fps_kernel(const float* __restric
   cluster.sync();
 }
 
-static int fps_cluster_size() { return FPS_MAX_CL; }
+// CTAs per set.  A CTA streams its slice at only ~25-70 GB/s (one round of loads per warp in
+// flight), so a set's sweep time is its bytes over (CTAs x that rate): with a batch of episodes
+// 8-CTA clusters already fill every SM twice over and HBM is the limit, but the handful of sets of
+// a single episode (the training step) leaves most SMs idle — those get 16-CTA clusters.
+static int fps_cluster_size(int n_sets) {
+  static const int forced = [] {  // A/B switch: R3DFS_FPS_CLUSTER = 1..16
+    const char* e = getenv("R3DFS_FPS_CLUSTER");
+    const int v = e ? atoi(e) : 0;
+    return (v >= 1 && v <= FPS_MAX_CL) ? v : 0;
+  }();
+  if (forced) return forced;
+  return n_sets <= 16 ? 16 : 8;
+}
 
 int launch_fps_ex(const float* feat, int D, const int32_t* set_off, const int32_t* set_n,
                   int n_sets, int n_cap, int m_max, int k_for_count, int32_t* idx_out,
                   int32_t* cnt_out, cudaStream_t st) {
   if (D % 4 != 0 || D > 32 * FPS_MAX_F4 || D <= 0) return R3DFS_E_UNSUPPORTED;
-  const int CL = fps_cluster_size();
-  int chunk = (n_cap + CL - 1) / CL;
-  chunk = (chunk + 3) & ~3;
-  size_t smem = sizeof(float) * (size_t)chunk;
-  if (smem > 200 * 1024) return R3DFS_E_UNSUPPORTED;
-  cudaError_t e =
-      cudaFuncSetAttribute(fps_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return (int)e;
+  int CL = fps_cluster_size(n_sets);
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(CL, n_sets, 1);
-  cfg.blockDim = dim3(FPS_THREADS, 1, 1);
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = st;
   cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = CL;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  size_t smem = 0;
+  cudaError_t e;
+  for (;; CL = 8) {
+    int chunk = (n_cap + CL - 1) / CL;
+    chunk = (chunk + 3) & ~3;
+    smem = sizeof(float) * (size_t)chunk;
+    if (smem > 200 * 1024) return R3DFS_E_UNSUPPORTED;
+    e = cudaFuncSetAttribute(fps_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    if (CL > 8) {
+      e = cudaFuncSetAttribute(fps_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+      if (e != cudaSuccess) return (int)e;
+    }
+    cfg = {};
+    cfg.gridDim = dim3(CL, n_sets, 1);
+    cfg.blockDim = dim3(FPS_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (CL <= 8) break;
+    int n_clusters = 0;  // can the device co-schedule a 16-CTA cluster of this kernel at all?
+    e = cudaOccupancyMaxActiveClusters(&n_clusters, fps_kernel, &cfg);
+    if (e == cudaSuccess && n_clusters >= 1) break;
+    (void)cudaGetLastError();
+  }
   e = cudaLaunchKernelEx(&cfg, fps_kernel, feat, D, set_off, set_n, m_max, k_for_count, idx_out,
                          cnt_out);
   if (e != cudaSuccess) return (int)e;
