@@ -736,3 +736,22 @@ def test_protonet_batch_no_mdns_and_bad_method(fixture_sd):
     m.dist_method = "gaussian"
     with pytest.raises(NotImplementedError):
         m.forward_episodes(sx[:1], sy[:1], qx[:1], qy[:1])
+
+
+@pytest.mark.parametrize("n", [1100, 2368, 4416, 6000])
+def test_selection_and_inedge_kernels_equal_their_predecessors(n, tmp_path):
+    """The register-resident selection kernels (warp per row for n <= 2560, CTA per row above) and the
+    sort-free in-edge build must reproduce, bit for bit, what the shared-memory radix select and the
+    atomics + sort build produce (R3DFS_SELECT_BLOCK / R3DFS_INEDGE_SORT) — neighbour lists,
+    similarities and the propagated labels — including exact ties (duplicated rows), a block of
+    invalid nodes and a graph with fewer valid nodes than k.  One process per setting: the switches
+    are read once per process."""
+    import subprocess
+    import sys
+    script = os.path.join(os.path.dirname(os.path.dirname(__file__)), "scripts", "check_select.py")
+    a, b = str(tmp_path / "a.pt"), str(tmp_path / "b.pt")
+    env_old = dict(os.environ, R3DFS_SELECT_BLOCK="1", R3DFS_INEDGE_SORT="1")
+    subprocess.run([sys.executable, script, "run", a, str(n), "3"], check=True, timeout=300)
+    subprocess.run([sys.executable, script, "run", b, str(n), "3"], check=True, timeout=300, env=env_old)
+    r = subprocess.run([sys.executable, script, "cmp", a, b], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
