@@ -1379,18 +1379,31 @@ __device__ __forceinline__ void cg_row_product(const uint16_t* crow, const float
       }
     }
   }
-  for (; t0 < L; t0 += 32) {
-    const int t = t0 + lane;
-    if (t < L) {
-      const int cj = (int)crow[t];
-      const float cv = vrow[t];
+  // remainder in ONE predicated round: a warp owns only a couple of rows per iteration here, so the
+  // 32-entry steps of a row are a latency chain (in the batched cluster kernel, where 16 warps keep
+  // the memory system busy, the same change cost 5 %: there the extra predicated work is what shows)
+  if (t0 < L) {
+    const int nU = (L - t0 + 31) >> 5;
+    int cj[8];
+    float cv[8];
 #pragma unroll
-      for (int q = 0; q < NCV / 4; ++q) {
-        const float4 p4 = *reinterpret_cast<const float4*>(Ps + (int64_t)cj * NCV + 4 * q);
-        acc[4 * q + 0] = fmaf(cv, p4.x, acc[4 * q + 0]);
-        acc[4 * q + 1] = fmaf(cv, p4.y, acc[4 * q + 1]);
-        acc[4 * q + 2] = fmaf(cv, p4.z, acc[4 * q + 2]);
-        acc[4 * q + 3] = fmaf(cv, p4.w, acc[4 * q + 3]);
+    for (int u = 0; u < 8; ++u) {
+      const int t = t0 + lane + 32 * u;
+      const bool ok = u < nU && t < L;
+      cj[u] = ok ? (int)crow[t] : 0;
+      cv[u] = ok ? vrow[t] : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      if (u < nU) {
+#pragma unroll
+        for (int q = 0; q < NCV / 4; ++q) {
+          const float4 p4 = *reinterpret_cast<const float4*>(Ps + (int64_t)cj[u] * NCV + 4 * q);
+          acc[4 * q + 0] = fmaf(cv[u], p4.x, acc[4 * q + 0]);
+          acc[4 * q + 1] = fmaf(cv[u], p4.y, acc[4 * q + 1]);
+          acc[4 * q + 2] = fmaf(cv[u], p4.z, acc[4 * q + 2]);
+          acc[4 * q + 3] = fmaf(cv[u], p4.w, acc[4 * q + 3]);
+        }
       }
     }
   }
