@@ -22,8 +22,9 @@ class SelfAttention(nn.Module):
     def forward(self, x):
         """x (B, in_channel, N) -> (B, out_channel, N)"""
         if self.training:
-            raise NotImplementedError("r3dfsseg_b200: attention dropout / backward not built yet; "
-                                      "call .eval()")
+            raise NotImplementedError(
+                "r3dfsseg_b200: no stand-alone training-mode forward; attention dropout and its "
+                "backward run inside MPTI_SelfAtten.forward(..., train=True) — call .eval()")
         if self.out_channel != 64:
             raise NotImplementedError("the attention kernel is built for out_channel = 64")
         wqkv = torch.cat([self.q_map.weight, self.k_map.weight, self.v_map.weight], 0)

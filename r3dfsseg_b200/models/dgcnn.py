@@ -1,7 +1,8 @@
 """DGCNN encoder with the reference's module surface (reference models/dgcnn.py:17-127), backed by
 libr3dfs.so.  Parameter / buffer names are the reference's (`edge_convs.{i}.layer.{0,1,3,4}.*`,
-`conv.layer.{0,1,3,4}.*`) so its checkpoints load unchanged.  Eval mode only for now: BatchNorm is
-folded into the kernels' per-channel affine; training-mode batch statistics are not built yet.
+`conv.layer.{0,1,3,4}.*`) so its checkpoints load unchanged.  Stand-alone use is eval mode (BatchNorm
+folded into the kernels' per-channel affine); training with batch statistics runs per episode through
+`MPTI_SelfAtten.forward(train=True)` (r3dfsseg_b200/train.py), which reads these parameters.
 """
 from __future__ import annotations
 
@@ -15,8 +16,9 @@ from ..ops import get_edge_feature, get_graph_feature, knn  # noqa: F401  (re-ex
 def _no_training(mod: nn.Module) -> None:
     if mod.training:
         raise NotImplementedError(
-            "r3dfsseg_b200: the training path (batch-statistics BatchNorm + backward kernels) is "
-            "not built yet; call .eval() — there is deliberately no PyTorch fallback")
+            "r3dfsseg_b200: this module has no stand-alone training-mode forward; the training "
+            "step runs whole episodes through MPTI_SelfAtten.forward(..., train=True) — call "
+            ".eval() to use it on its own (there is deliberately no PyTorch fallback)")
 
 
 class _PointwiseStack(nn.Module):

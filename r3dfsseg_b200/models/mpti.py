@@ -34,7 +34,8 @@ class BaseLearner(nn.Module):
 
     def forward(self, x):
         if self.training:
-            raise NotImplementedError("r3dfsseg_b200: training path not built yet; call .eval()")
+            raise NotImplementedError("r3dfsseg_b200: stand-alone call in training mode; use "
+                                      "forward(..., train=True) for the training step or .eval()")
         B, _, N = x.shape
         h = x.transpose(1, 2).reshape(B * N, -1)
         for i, seq in enumerate(self.convs):
@@ -93,7 +94,8 @@ class MPTI_SelfAtten(nn.Module):
     def getFeatures(self, x):
         """(B, C_in, N) -> (B, 192, N)   (reference models/mpti.py:579-589)"""
         if self.training:
-            raise NotImplementedError("r3dfsseg_b200: training path not built yet; call .eval()")
+            raise NotImplementedError("r3dfsseg_b200: stand-alone call in training mode; use "
+                                      "forward(..., train=True) for the training step or .eval()")
         return ops.features(self._weights(), x)
 
     # ---------------------------------------------------------------------------------------
@@ -105,7 +107,8 @@ class MPTI_SelfAtten(nn.Module):
         With `support_feat` (E, n_way*k_shot*N, 192) / `query_feat` (E, n_query*N, 192) given,
         the encoder is skipped and only the graph half runs on those features."""
         if self.training:
-            raise NotImplementedError("r3dfsseg_b200: training path not built yet; call .eval()")
+            raise NotImplementedError("r3dfsseg_b200: stand-alone call in training mode; use "
+                                      "forward(..., train=True) for the training step or .eval()")
         cfg = self._cfg(query_x.shape[1], mdns=bool(eval))
         return ops.mpti_forward(self._weights(), cfg, support_x, support_y, query_x, query_y,
                                 want_diag=want_diag, workspace=workspace,
