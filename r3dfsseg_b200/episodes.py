@@ -6,7 +6,8 @@ the reference's input contract (reference `dataloaders/loader.py:201-219` channe
 leave the cloud point-major in memory) and its noise model for out-of-distribution shots
 (`dataloaders/loader.py:669-680,797-810`: `round(k_shot*ratio)` shots per way are whole
 clouds whose foreground object is a class outside the sampled ways, their ground-truth
-masks are zero, and shot order is shuffled per way).
+masks are zero, and shot order is shuffled per way; `make_episode` also has the reference's
+"sym", "pair" and "partial" noise types).
 """
 from __future__ import annotations
 
@@ -96,18 +97,46 @@ class Episode:
         return [self.support_x, self.support_y, self.query_x, self.query_y, z, zq, self.gt_support_y]
 
 
+NOISE_TYPES = ("ood", "sym", "pair", "partial")
+
+
+def default_pair_dict(dataset: str):
+    """A fixed class -> noise-class pairing over the fold's test classes, in the spirit of the
+    reference's `noise_pair_dict` (dataloaders/loader.py:592-593, 735): mostly a cyclic shift, with one
+    class mapped to itself ("some pair noise don't have noisy class", :797)."""
+    pool = CLASS_POOL[dataset]
+    d = {c: (c + 1) % pool for c in range(pool)}
+    d[pool - 1] = pool - 1
+    return d
+
+
 def make_episode(seed: int, n_way: int = 2, k_shot: int = 5, n_queries: int = 1,
-                 dataset: str = "s3dis", noise_ratio: float = 0.0,
-                 n_pts: int = N_POINTS, noise_type: str = "ood") -> Episode:
-    """noise_type (reference dataloaders/loader.py:675-686): "ood" — a noisy shot's foreground
-    object is a test class outside the sampled ways; "sym" — it is one of the OTHER sampled ways."""
-    if noise_type not in ("ood", "sym"):
-        raise ValueError("noise_type must be 'ood' or 'sym'")
+                 dataset: str = "s3dis", noise_ratio=0.0,
+                 n_pts: int = N_POINTS, noise_type: str = "ood", pair_dict=None) -> Episode:
+    """Synthetic counterpart of `NoiseInMetaTest.generate_one_episode` (reference
+    dataloaders/loader.py:648-890).  `round(k_shot * noise_ratio)` shots per way are noisy (a list of
+    ratios means "draw one per episode", the reference's train mode, :668-670); their ground-truth
+    masks are zero (:798-802), shots are shuffled per way (:806-810) and `support_flag` records every
+    shot's absolute class (:730,795).  noise_type (:675-686,734-747):
+      "ood"     — the noisy shot's foreground object is a test class outside the sampled ways;
+      "sym"     — it is one of the OTHER sampled ways;
+      "pair"    — it is `pair_dict[class of the way]` (may be the class itself);
+      "partial" — the shot shows the way's own class, but the given mask also covers one object of
+                  another class (`sample_pointcloud(partial_noise=True)`, :241-257).
+    A noise class is dropped from a way's range once it has supplied `k_shot - n_noise - 1` shots
+    (:790-793; the reference re-creates its counter inside the loop, so this fires only when that
+    number is 1 — mirrored as executed)."""
+    if noise_type not in NOISE_TYPES:
+        raise ValueError(f"noise_type must be one of {NOISE_TYPES}")
     pool = CLASS_POOL[dataset]
     rng = np.random.default_rng(seed)
     sampled = rng.choice(pool, size=n_way, replace=False)
     others = [c for c in range(pool) if c not in sampled]
+    if isinstance(noise_ratio, (list, tuple)):
+        noise_ratio = float(rng.choice(np.asarray(noise_ratio, dtype=np.float64)))
     n_noise = int(round(k_shot * noise_ratio))
+    if noise_type == "pair" and pair_dict is None:
+        pair_dict = default_pair_dict(dataset)
     sx, sy, gy, flag = [], [], [], []
     qx, qy = [], []
     for w, c in enumerate(sampled):
@@ -125,19 +154,38 @@ def make_episode(seed: int, n_way: int = 2, k_shot: int = 5, n_queries: int = 1,
             qx.append(pts)
             qy.append(lab)
         wx, wy, wg, wf = [], [], [], []
+        if noise_type == "sym" and n_way > 1:
+            noise_range = [int(s_) for s_ in sampled if s_ != c]
+        elif noise_type == "pair":
+            noise_range = [int(pair_dict[int(c)])]
+        elif noise_type == "partial":
+            noise_range = [int(c)]
+        else:
+            noise_range = list(others)
+        single_use = (k_shot - n_noise - 1) == 1 and noise_type in ("ood", "sym")
         for k in range(k_shot):
             noisy = k >= k_shot - n_noise
-            if noisy and noise_type == "sym" and n_way > 1:
-                fg_cls = int(rng.choice([s_ for s_ in sampled if s_ != c]))
+            extra_mask_cls = None
+            if noisy and noise_range:
+                fg_cls = int(rng.choice(noise_range))
+                if single_use and len(noise_range) > 1:
+                    noise_range.remove(fg_cls)
             else:
-                fg_cls = int(rng.choice(others)) if noisy else int(c)
+                fg_cls = int(rng.choice(others)) if (noisy and others) else int(c)
             objs = [fg_cls]
-            if rng.uniform() < 0.3 and others:
+            if noisy and noise_type == "partial":
+                # needs a second object of another class in the block (:754-763)
+                extra_mask_cls = int(rng.choice([x for x in range(pool) if x != fg_cls]))
+                objs.append(extra_mask_cls)
+            elif rng.uniform() < 0.3 and others:
                 extra = int(rng.choice(others))
                 if extra != fg_cls:
                     objs.append(extra)
             pts, cls = make_cloud(rng, objs, n_pts)
-            m = (cls == fg_cls).astype(np.int32)
+            m = (cls == fg_cls)
+            if extra_mask_cls is not None:
+                m = m | (cls == extra_mask_cls)
+            m = m.astype(np.int32)
             wx.append(pts)
             wy.append(m)
             wg.append(np.zeros_like(m) if noisy else m.copy())

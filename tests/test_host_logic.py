@@ -238,3 +238,42 @@ def test_symmetric_noise_episode():
                 assert cls == int(ep.sampled_classes[w])
     clean = make_episode(9, 3, 5, dataset="scannet", noise_ratio=0.4)   # default stays 'ood'
     assert not torch.equal(clean.support_flag, ep.support_flag)
+
+
+def test_pair_and_partial_noise_and_ratio_list():
+    """'pair' / 'partial' noise and the train-mode ratio list of the reference's episode sampler
+    (dataloaders/loader.py:668-670, 734-747, 241-257, 790-802)."""
+    from r3dfsseg_b200.episodes import default_pair_dict, make_episode
+    pd = default_pair_dict("scannet")
+    ep = make_episode(5, 3, 5, dataset="scannet", noise_ratio=0.4, noise_type="pair")
+    noisy = ep.gt_support_y.sum(-1) == 0
+    assert (noisy.sum(1) == 2).all()
+    for w in range(3):
+        c = int(ep.sampled_classes[w])
+        for k in range(5):
+            want = pd[c] if noisy[w, k] else c
+            assert int(ep.support_flag[w, k]) == want
+    # partial: the noisy shots show the way's own class, but their mask covers more than that object
+    ep = make_episode(6, 2, 5, noise_ratio=0.4, noise_type="partial")
+    noisy = ep.gt_support_y.sum(-1) == 0
+    assert (noisy.sum(1) == 2).all()
+    for w in range(2):
+        assert (ep.support_flag[w] == int(ep.sampled_classes[w])).all()
+    clean_frac = ep.support_y[~noisy].float().mean()
+    noisy_frac = ep.support_y[noisy].float().mean()
+    assert noisy_frac > clean_frac               # an extra object is marked foreground
+    assert (ep.gt_support_y[~noisy] == ep.support_y[~noisy]).all()
+    # a list of ratios draws one per episode (train mode); 0.0 and 0.4 both occur over seeds
+    seen = set()
+    for seed in range(12):
+        e = make_episode(seed, 2, 5, noise_ratio=[0.0, 0.4])
+        seen.add(int((e.gt_support_y.sum(-1) == 0).sum(1)[0]))
+    assert seen == {0, 2}
+    # k_shot - n_noise - 1 == 1: a noise class supplies at most one shot of a way (loader.py:790-793)
+    e = make_episode(3, 2, 5, dataset="scannet", noise_ratio=0.6)
+    noisy = e.gt_support_y.sum(-1) == 0
+    for w in range(2):
+        flags = e.support_flag[w][noisy[w]].tolist()
+        assert len(flags) == 3 and len(set(flags)) == 3
+    with pytest.raises(ValueError):
+        make_episode(0, 2, 5, noise_type="bogus")
