@@ -585,14 +585,28 @@ __global__ __launch_bounds__(K2_THREADS, 1) void knn_tc2_kernel(const float* __r
       knn_keys32(v, nq, xs + (j & 3) * K2_TC);
       tc::tc_fence_before();
       mbar_arrive(&bar_tfree[st]);
+      // one comparison per key: v >= tau and v > thr  <=>  v >= max(tau, next float above thr)
       const float thr = lv[KL - 1];
+      const int tb = __float_as_int(thr);  // next float above thr (-inf -> -FLT_MAX, -0 -> denorm min)
+      const float cut = fmaxf(tau, __int_as_float(tb >= 0 ? tb + 1 : (tb == (int)0x80000000 ? 1 : tb - 1)));
       const int nvalid = N - c0;
+      if (nvalid >= 32) {
 #pragma unroll
-      for (int e = 0; e < 32; ++e) {
-        if (v[e] >= tau && v[e] > thr && e < nvalid) {
-          qk[qcnt * 256 + tid] = v[e];
-          qc[qcnt * 256 + tid] = (unsigned short)(c0 + e);
-          ++qcnt;
+        for (int e = 0; e < 32; ++e) {
+          if (v[e] >= cut) {
+            qk[qcnt * 256 + tid] = v[e];
+            qc[qcnt * 256 + tid] = (unsigned short)(c0 + e);
+            ++qcnt;
+          }
+        }
+      } else {
+#pragma unroll
+        for (int e = 0; e < 32; ++e) {
+          if (v[e] >= cut && e < nvalid) {
+            qk[qcnt * 256 + tid] = v[e];
+            qc[qcnt * 256 + tid] = (unsigned short)(c0 + e);
+            ++qcnt;
+          }
         }
       }
       if (__any_sync(0xffffffffu, qcnt > K2_CAP - 32)) drain();
