@@ -306,6 +306,24 @@ class FusedAdam(torch.optim.Optimizer):
                  for p in fs.params]
         return torch.cat(parts)
 
+    # ---- checkpoints in the reference optimizer's layout (torch.optim.Adam over the four groups
+    # of models/mpti_learner.py:26-32), so that a run resumes on either side ---------------------
+    def state_dict(self):
+        from .checkpoint import adam_state_to_reference
+        fs = flat_state(self.model)
+        return adam_state_to_reference(
+            self.exp_avg, self.exp_avg_sq, self.step_count, PARAM_NAMES, [p.shape for p in fs.params],
+            fs.offsets, (self.param_groups[0]["lr"], self.param_groups[1]["lr"]),
+            self.defaults["betas"], self.defaults["eps"])
+
+    def load_state_dict(self, state_dict):
+        from .checkpoint import adam_state_from_reference
+        fs = flat_state(self.model)
+        m, v, step, lrs = adam_state_from_reference(state_dict, PARAM_NAMES,
+                                                    [p.shape for p in fs.params], fs.offsets, fs.flat)
+        self.exp_avg, self.exp_avg_sq, self.step_count = m, v, step
+        self.param_groups[0]["lr"], self.param_groups[1]["lr"] = lrs
+
     @torch.no_grad()
     def step(self, closure=None):
         fs = flat_state(self.model)
@@ -332,11 +350,24 @@ class MPTILearner_V3:
         from .models import MPTI_SelfAtten
         self.model = model if model is not None else MPTI_SelfAtten(args)
         self.model.cuda()
+        from .checkpoint import load_model_checkpoint, load_pretrain_checkpoint
+        model_ckpt = getattr(args, "model_checkpoint_path", None)
+        pretrain_ckpt = getattr(args, "pretrain_checkpoint_path", None)
         if mode == "train":
             self.optimizer = FusedAdam(self.model, lr=args.lr)
             self.lr_scheduler = torch.optim.lr_scheduler.StepLR(
                 self.optimizer, step_size=args.step_size, gamma=args.gamma)
-        elif mode != "test":
+            # reference models/mpti_learner.py:37-43; the only difference: with neither path given
+            # the weights stay as constructed (the reference insists on a pre-trained encoder)
+            if model_ckpt is None:
+                if pretrain_ckpt is not None:
+                    load_pretrain_checkpoint(self.model, pretrain_ckpt)
+            else:
+                load_model_checkpoint(self.model, model_ckpt, optimizer=self.optimizer, mode="train")
+        elif mode == "test":
+            if model_ckpt is not None:
+                load_model_checkpoint(self.model, model_ckpt, mode="test")
+        else:
             raise ValueError("Wrong GraphLearner mode (%s)! Option:train/test" % mode)
 
     def train(self, data, logger=None):

@@ -183,3 +183,54 @@ def test_learner_train_then_test(fixture_sd):
     # the reference's state-dict keys survive the flat re-homing
     sd2 = learner.model.state_dict()
     assert set(sd2.keys()) == set(fixture_sd.keys())
+
+
+def test_learner_resumes_from_reference_format_checkpoint(fixture_sd, tmp_path):
+    """checkpoint.tar in the reference's layout (utils/checkpoint_util.py:26-45,
+    mpti_train_noise.py:137-144): one step, save, resume in a new learner through
+    `args.model_checkpoint_path` — weights, Adam moments, step count and learning rates come back
+    bit for bit, torch.optim.Adam over the reference's four groups accepts the optimizer state, and
+    the next step of the resumed learner equals the next step of the original."""
+    from r3dfsseg_b200 import checkpoint as ck
+    from r3dfsseg_b200 import train as T
+    from r3dfsseg_b200.models import MPTI_SelfAtten
+
+    def data_of(seed):
+        ep = make_episode(seed, 2, 5, noise_ratio=0.2)
+        c = lambda t: t.to(DEV)
+        zq = torch.zeros_like(ep.query_y)
+        return [c(ep.support_x), c(ep.support_y), c(ep.query_x), c(ep.query_y),
+                c(torch.zeros_like(ep.support_y)), c(zq), c(ep.gt_support_y), c(ep.query_y), None,
+                None, c(ep.support_flag)]
+
+    args = default_args(2, 5)
+    model = MPTI_SelfAtten(args)
+    model.load_state_dict(fixture_sd)
+    a = T.MPTILearner_V3(args, mode="train", model=model)
+    a.train(data_of(41))
+    ck.save_model_checkpoint(a.model, a.optimizer, str(tmp_path), iteration=1, iou=0.25)
+    saved = torch.load(str(tmp_path / "checkpoint.tar"))
+    assert set(saved) >= {"iteration", "IoU", "model_state_dict", "optimizer_state_dict"}
+    ref_model = MPTI_SelfAtten(args)
+    ref_opt = torch.optim.Adam([{"params": ref_model.encoder.parameters(), "lr": 1e-4},
+                                {"params": ref_model.base_learner.parameters()},
+                                {"params": ref_model.att_learner.parameters()},
+                                {"params": ref_model.proj.parameters()}], lr=args.lr)
+    ref_opt.load_state_dict(saved["optimizer_state_dict"])          # the reference side can resume
+    args_b = default_args(2, 5, model_checkpoint_path=str(tmp_path))
+    b = T.MPTILearner_V3(args_b, mode="train")
+    assert torch.equal(T.flat_state(b.model).flat, T.flat_state(a.model).flat)
+    assert torch.equal(T.flat_state(b.model).running, T.flat_state(a.model).running)
+    assert torch.equal(b.optimizer.exp_avg, a.optimizer.exp_avg)
+    assert torch.equal(b.optimizer.exp_avg_sq, a.optimizer.exp_avg_sq)
+    assert b.optimizer.step_count == a.optimizer.step_count == 1
+    b.model._train_step = a.model._train_step                      # same dropout counter
+    la = a.train(data_of(42))
+    lb = b.train(data_of(42))
+    assert abs(float(la[0].detach()) - float(lb[0].detach())) <= 1e-4 * abs(float(la[0].detach()))
+    # float atomics in the backward: the two runs are not bit-identical.  Parameters whose true
+    # gradient is exactly zero (the conv biases ahead of a batch-statistics BatchNorm, 192 of 376 896)
+    # receive pure rounding noise, which Adam normalises to steps of +-lr; everything else agrees
+    # far below one update
+    d = (T.flat_state(a.model).flat - T.flat_state(b.model).flat).abs()
+    assert float((d < 1e-6).float().mean()) > 0.995, (float(d.max()), float((d < 1e-6).float().mean()))

@@ -277,3 +277,62 @@ def test_pair_and_partial_noise_and_ratio_list():
         assert len(flags) == 3 and len(set(flags)) == 3
     with pytest.raises(ValueError):
         make_episode(0, 2, 5, noise_type="bogus")
+
+
+def test_checkpoint_formats_round_trip_with_the_reference_optimizer(tmp_path):
+    """r3dfsseg_b200/checkpoint.py: the fused optimizer's flat moments <-> torch.optim.Adam.state_dict()
+    over the reference's four parameter groups (models/mpti_learner.py:26-32), and the reference's
+    checkpoint.tar / pre-training files (utils/checkpoint_util.py:10-45)."""
+    from r3dfsseg_b200 import checkpoint as ck
+    from r3dfsseg_b200.episodes import default_args
+    from r3dfsseg_b200.models import MPTI_SelfAtten
+    from r3dfsseg_b200.train import PARAM_NAMES, param_layout
+    torch.manual_seed(0)
+    m = MPTI_SelfAtten(default_args(2, 5))
+    named = dict(m.named_parameters())
+    assert list(named) == PARAM_NAMES           # reference registration order = optimizer order
+    params = [named[n] for n in PARAM_NAMES]
+    # the reference's optimizer, stepped once on random gradients
+    ref_opt = torch.optim.Adam([{"params": m.encoder.parameters(), "lr": 1e-4},
+                                {"params": m.base_learner.parameters()},
+                                {"params": m.att_learner.parameters()},
+                                {"params": m.proj.parameters()}], lr=1e-3)
+    for p in params:
+        p.grad = torch.randn_like(p)
+    ref_opt.step()
+    sd = ref_opt.state_dict()
+    offsets, _ = param_layout(9)
+    shapes = [p.shape for p in params]
+    like = torch.zeros(offsets[-1])
+    ea, es, step, lrs = ck.adam_state_from_reference(sd, PARAM_NAMES, shapes, offsets, like)
+    assert step == 1 and lrs == (1e-4, 1e-3)
+    for i, (p, o) in enumerate(zip(params, offsets)):
+        assert torch.equal(ea[o:o + p.numel()].view(p.shape), sd["state"][i]["exp_avg"])
+        assert torch.equal(es[o:o + p.numel()].view(p.shape), sd["state"][i]["exp_avg_sq"])
+    back = ck.adam_state_to_reference(ea, es, step, PARAM_NAMES, shapes, offsets, lrs)
+    assert [g["params"] for g in back["param_groups"]] == [g["params"] for g in sd["param_groups"]]
+    assert [g["lr"] for g in back["param_groups"]] == [1e-4, 1e-3, 1e-3, 1e-3]
+    fresh = torch.optim.Adam([{"params": m.encoder.parameters(), "lr": 1e-4},
+                              {"params": m.base_learner.parameters()},
+                              {"params": m.att_learner.parameters()},
+                              {"params": m.proj.parameters()}], lr=1e-3)
+    fresh.load_state_dict(back)                  # torch accepts what we write
+    fs = fresh.state_dict()["state"]
+    assert all(torch.equal(fs[i]["exp_avg"], sd["state"][i]["exp_avg"]) for i in range(len(params)))
+    assert int(float(fs[0]["step"])) == 1
+    # files: checkpoint.tar and the pre-training file
+    ck.save_model_checkpoint(m, ref_opt, str(tmp_path), iteration=7, iou=0.5)
+    m2 = MPTI_SelfAtten(default_args(2, 5))
+    ck.load_model_checkpoint(m2, str(tmp_path), mode="test")
+    assert all(torch.equal(a, b) for a, b in zip(m.state_dict().values(), m2.state_dict().values()))
+    pre = tmp_path / "pre.tar"
+    torch.save({"params": m.encoder.state_dict()}, pre)
+    m3 = MPTI_SelfAtten(default_args(2, 5))
+    ck.load_pretrain_checkpoint(m3, str(pre))
+    assert torch.equal(m3.encoder.state_dict()["conv.layer.0.weight"],
+                       m.encoder.state_dict()["conv.layer.0.weight"])
+    assert not torch.equal(m3.proj.weight, m.proj.weight)      # only the encoder is taken
+    with pytest.raises(ValueError):
+        ck.load_model_checkpoint(m2, str(tmp_path / "nowhere"), mode="test")
+    with pytest.raises(ValueError):
+        ck.load_pretrain_checkpoint(m3, None)
