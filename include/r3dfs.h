@@ -148,6 +148,22 @@ int r3dfs_attention(const float* x, int64_t B, int64_t N, int64_t Cin, const flo
 int r3dfs_fps(const float* feat, int64_t D, const int32_t* set_off, const int32_t* set_n,
               int n_sets, int64_t n_cap, int m_max, int32_t* idx_out, r3dfs_stream_t stream);
 
+/* Same contract and the same picks, with a workspace and a choice of kernel.
+ *   R3DFS_FPS_STREAM  every pick re-reads the FP32 rows of the set (r3dfs_fps);
+ *   R3DFS_FPS_Q8      D = 192 only: rows are kept as bytes in the shared memory of the set's
+ *                     thread-block cluster, an exact integer lower bound on the distance decides
+ *                     which rows can change their running minimum, and only those (3-4 % per
+ *                     pick) are re-read in FP32 — same arithmetic, same sequence;
+ *   R3DFS_FPS_AUTO    Q8 when D = 192 and m_max >= 16, else STREAM.
+ * total_rows = rows of feat (upper bound of set_off[s] + set_n[s]). */
+#define R3DFS_FPS_AUTO 0
+#define R3DFS_FPS_STREAM 1
+#define R3DFS_FPS_Q8 2
+size_t r3dfs_fps_workspace(int64_t total_rows);
+int r3dfs_fps_ex(const float* feat, int64_t D, const int32_t* set_off, const int32_t* set_n,
+                 int n_sets, int64_t n_cap, int64_t total_rows, int m_max, int impl,
+                 int32_t* idx_out, void* ws, size_t ws_bytes, r3dfs_stream_t stream);
+
 /* getMutiplePrototypes(feat, k) — models/mpti.py:597-634, for `n_sets` sets in one call:
  * m = ceil(fp32(n) * fp32(k / n)) FPS seeds (k or k+1), sorted + deduplicated (`.unique()`),
  * assignment = argmin_j || f - seed_j + 1e-6 ||_2 (torch<=1.8 pairwise_distance, first minimum),

@@ -1,4 +1,5 @@
-"""TEST INFRASTRUCTURE.  Builds tests/golden/weights_fixture.pt — the "checkpoint" shared by
+"""TEST INFRASTRUCTURE.  Builds tests/golden/weights_init.pt — the initialisation that scripts/train_fixture.py meta-trains
+into tests/golden/weights_fixture.pt, the "checkpoint" shared by
 the oracle, the reference-under-shims and the CUDA path (SURVEY.md §8d "Weights fixture").
 
 `torch.manual_seed(0)` + the reference's own `MPTI_SelfAtten(args)` constructor, then
@@ -20,7 +21,7 @@ from oracle import ref_shims  # noqa: E402
 from r3dfsseg_b200.episodes import default_args, make_episode  # noqa: E402
 
 OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
-                   "tests", "golden", "weights_fixture.pt")
+                   "tests", "golden", "weights_init.pt")
 
 
 def calibration_clouds():

@@ -7,6 +7,11 @@ Files (small on purpose; episodes are regenerated from their seed, only outputs 
   golden_episodes.pt   MPTI_SelfAtten.forward outputs for the three episode configurations
   golden_protonet.pt   ProtoNet_Contrast.forward (eval) outputs; `python -m oracle.make_golden protonet`
                        writes only this file
+  golden_parity.pt     free-running parity cases (`python -m oracle.make_golden parity`): for the
+                       four episode configurations above plus 10 seeds each of BASELINE.json
+                       configs[2] (S3DIS-shape 2-way 5-shot) and configs[3] (ScanNet-shape 3-way
+                       5-shot, 40 % OOD shots), the reference's FP32 logits and the FP64
+                       adjudicator's logits (oracle.mpti_oracle.forward_episode_fp64)
 """
 import os
 import sys
@@ -61,12 +66,49 @@ def protonet(ref, sd):
     print("golden_protonet.pt written")
 
 
+PARITY_CASES = list(EPISODE_CASES) \
+    + [("s3dis_2way_5shot_seed%d" % s, s, 2, 5, "s3dis", 0.0, True) for s in range(100, 110)] \
+    + [("scannet_3way_5shot_ood_seed%d" % s, s, 3, 5, "scannet", 0.4, True) for s in range(200, 210)]
+
+
+def parity(ref, sd):
+    """Reference FP32 logits + FP64 adjudicator logits per free-running parity case."""
+    from oracle import mpti_oracle as O
+    out = {}
+    for name, seed, n_way, k_shot, ds, noise, ev in PARITY_CASES:
+        m = ref.mpti.MPTI_SelfAtten(default_args(n_way, k_shot))
+        m.load_state_dict(sd)
+        m.eval()
+        ep = make_episode(seed, n_way, k_shot, dataset=ds, noise_ratio=noise)
+        with torch.no_grad(), ref_shims.quiet():
+            pred, loss = m(ep.support_x, ep.support_y, ep.query_x, ep.query_y,
+                           gt_support_y=ep.gt_support_y, eval=ev)
+            adj = O.forward_episode_fp64(sd, ep.support_x, ep.support_y, ep.query_x, ep.query_y,
+                                         eval_mdns=ev)
+        p64 = adj["query_pred"]
+        rel = float((pred.double() - p64).abs().max() / p64.abs().max())
+        agree = float((pred.argmax(1) == p64.argmax(1)).float().mean())
+        out[name] = dict(seed=seed, n_way=n_way, k_shot=k_shot, dataset=ds, noise_ratio=noise,
+                         eval=ev, query_pred=pred.contiguous().clone(), loss=loss.clone(),
+                         query_pred_fp64=p64.float().contiguous().clone(),
+                         loss_fp64=adj["loss"].float().clone(),
+                         clean_flag_fp64=adj["clean_flag"], proto_count_fp64=adj["proto_count"],
+                         num_prototypes=int(m.num_prototypes))
+        print(name, "loss", float(loss), "fp64", float(adj["loss"]), "ref32 vs fp64: max rel",
+              "%.2e" % rel, "labels", "%.5f" % agree, "acc",
+              float((pred.argmax(1) == ep.query_y).float().mean()), flush=True)
+    torch.save(out, os.path.join(GOLD, "golden_parity.pt"))
+    print("golden_parity.pt written")
+
+
 def main():
     ref = ref_shims.load_reference()
     torch.set_num_threads(os.cpu_count())
     sd = torch.load(os.path.join(GOLD, "weights_fixture.pt"))
     if sys.argv[1:] == ["protonet"]:
         return protonet(ref, sd)
+    if sys.argv[1:] == ["parity"]:
+        return parity(ref, sd)
 
     # ---- DGCNN pieces -----------------------------------------------------------------------
     g = torch.Generator().manual_seed(7)

@@ -9,8 +9,8 @@ stand-in for "the reference's CPU path".  Each function cites the reference line
 Pinning: the reference has no tests or golden vectors, and three of its dependencies
 (faiss, torch_cluster, torch<=1.8 pairwise_distance) are absent/unpinned, so their semantics are
 fixed by oracle/ref_shims.py.  This restatement is pinned against the reference's own modules
-imported unmodified under those shims (tests/test_oracle_vs_reference.py, build container only)
-and against tests/golden/*.pt generated from them by oracle/make_golden.py.
+imported unmodified under those shims: tests/test_oracle_golden.py compares it with tests/golden/*.pt,
+which oracle/make_golden.py / make_golden_train.py generate from the reference (build container only).
 
 Third-party arithmetic restated here (not under /root/reference, unpinned there):
   * faiss.IndexFlatL2.search — exact squared-L2 k-NN, ascending, query itself in column 0;
@@ -146,7 +146,7 @@ def multi_prototypes(feat: torch.Tensor, k: int):
         # same values as the reference's (n,192,m) broadcast, evaluated seed by seed to bound memory
         dist = torch.stack([torch.norm(feat - far[j] + 1e-6, 2.0, 1) for j in range(m)], dim=1)
         assign = torch.argmin(dist, dim=1)
-        protos = torch.zeros((m, feat.shape[1]))
+        protos = feat.new_zeros((m, feat.shape[1]))
         for i in range(m):
             protos[i] = feat[torch.nonzero(assign == i).squeeze(1)].mean(0)
         return protos, assign, m, seeds
@@ -194,7 +194,7 @@ def mdns_flags_one_scale(support_feat, support_y, support_x, n_x, n_y, n_z):
             seeds.append(s)
             lens.append(n)
         sn = F.normalize(torch.cat(seeds, dim=0), p=2, dim=1)
-        cos = torch.mm(sn, sn.t()) * (1.0 - torch.eye(sn.shape[0]))
+        cos = torch.mm(sn, sn.t()) * (1.0 - torch.eye(sn.shape[0], dtype=sn.dtype))
         if n_x == 1 and n_y == 1 and n_z == 1:
             cos = cos.pow(3)
         deg = cos.sum(1)
@@ -248,20 +248,22 @@ def affinity_dense(node_feat: torch.Tensor, k: int, sigma: float, I: Optional[to
     n, D = node_feat.shape
     if I is None:
         I, _ = knn_graph_exact(node_feat, k)
-    sim = torch.empty((n, k))
+    sim = node_feat.new_empty((n, k))
     for s in range(0, n, 512):  # same values as the reference's (n,k,D) gather, in row chunks
         nb = node_feat[I[s:s + 512]]                                   # (c, k, D)
         dist = torch.norm(node_feat[s:s + 512, None, :] - nb + 1e-6, 2.0, 2)
         sim[s:s + 512] = torch.exp(-0.5 * (dist / sigma) ** 2)
-    A = torch.zeros((n, n)).scatter_(1, I, sim)
+    A = node_feat.new_zeros((n, n)).scatter_(1, I, sim)
     A = A + A.t()
-    A = A * (1 - torch.eye(n))
+    A = A * (1 - torch.eye(n, dtype=A.dtype))
     return A, I, sim
 
 
-def label_propagate_dense(A: torch.Tensor, Y: torch.Tensor, alpha: float = 0.99, dtype=torch.float32):
-    """models/mpti.py:758-776 (dense inverse).  dtype=float64 gives the high-precision answer."""
+def label_propagate_dense(A: torch.Tensor, Y: torch.Tensor, alpha: float = 0.99, dtype=None):
+    """models/mpti.py:758-776 (dense inverse).  dtype=float64 gives the high-precision answer;
+    default: the dtype of A."""
     eps = np.finfo(float).eps
+    dtype = A.dtype if dtype is None else dtype
     A = A.to(dtype)
     D = A.sum(1)
     Dsi = torch.diag_embed(torch.sqrt(1.0 / (D + eps)))
@@ -301,20 +303,20 @@ def forward_episode(sd: Dict[str, torch.Tensor], support_x, support_y, query_x, 
         if pl is not None:
             f = f[pl[i] == 1]
         p, _, m, s = multi_prototypes(f, n_subprototypes)
-        lab = torch.zeros(p.shape[0], n_cls)
+        lab = p.new_zeros(p.shape[0], n_cls)
         lab[:, i + 1] = 1
         protos.append(p); labels.append(lab); counts.append(m); seed_idx.append(s); sets.append(f)
     # background prototypes (models/mpti.py:690-715)
     fb = support_feat.transpose(2, 3).contiguous().view(-1, D)
     fb = fb[torch.nonzero(torch.logical_not(support_y).reshape(-1)).squeeze(1)]
     pb, _, mb, sb = multi_prototypes(fb, n_subprototypes)
-    lb = torch.zeros(pb.shape[0], n_cls)
+    lb = pb.new_zeros(pb.shape[0], n_cls)
     lb[:, 0] = 1
     prototypes = torch.cat([pb] + protos, 0)
     proto_labels = torch.cat([lb] + labels, 0)
     P = prototypes.shape[0]
     n = P + query_feat.shape[0]
-    Y = torch.zeros(n, n_cls)
+    Y = prototypes.new_zeros(n, n_cls)
     Y[:P] = proto_labels
     node_feat = torch.cat((prototypes, query_feat), 0)
     A, I, sim = affinity_dense(node_feat, k_connect, sigma)
@@ -327,6 +329,19 @@ def forward_episode(sd: Dict[str, torch.Tensor], support_x, support_y, query_x, 
         out.update(support_feat=support_feat, query_feat=query_feat, node_feat=node_feat, A=A, I=I,
                    sim=sim, Y=Y, Z=Z, seed_idx=[sb] + seed_idx, sets=[fb] + sets)
     return out
+
+
+def forward_episode_fp64(sd, support_x, support_y, query_x, query_y, **kw):
+    """The same episode with every floating-point tensor (weights, clouds, features, graph, solve)
+    in float64: the ADJUDICATOR of free-running parity.  Two FP32 implementations of this path
+    (the reference and the CUDA library) legitimately differ where an FP32 distance tie flips a
+    kNN / FPS / argmin decision; how far each of them is from this run is the yardstick
+    (tests/test_gpu_parity.py::test_free_running_parity_fp64_adjudicated)."""
+    sd64 = {k: (v.double() if v.is_floating_point() else v) for k, v in sd.items()}
+    for name in ("support_feat", "query_feat"):
+        if kw.get(name) is not None:
+            kw[name] = kw[name].double()
+    return forward_episode(sd64, support_x.double(), support_y, query_x.double(), query_y, **kw)
 
 
 # ------------------------------------------------------------------------------------------------

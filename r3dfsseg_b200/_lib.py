@@ -8,7 +8,10 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libr3dfs.so")
+# R3DFS_LIB selects another build of the SAME library (the measurement build libr3dfs_ab.so, which
+# has the A/B switches of DESIGN.md §3.1 compiled in); it is read here, never by the library.
+LIB_PATH = os.environ.get("R3DFS_LIB") or os.path.join(_HERE, "libr3dfs.so")
+AB_LIB_PATH = os.path.join(_HERE, "libr3dfs_ab.so")
 
 c_f32p = C.c_void_p
 c_i32p = C.c_void_p
@@ -82,6 +85,8 @@ SIGNATURES = {
     "r3dfs_attention_workspace": (sz, [i64, i64]),
     "r3dfs_attention": (C.c_int, [vp, i64, i64, i64, vp, vp, vp, sz, vp]),
     "r3dfs_fps": (C.c_int, [vp, i64, vp, vp, i32, i64, i32, vp, vp]),
+    "r3dfs_fps_workspace": (sz, [i64]),
+    "r3dfs_fps_ex": (C.c_int, [vp, i64, vp, vp, i32, i64, i64, i32, i32, vp, vp, sz, vp]),
     "r3dfs_multi_prototypes_workspace": (sz, [i64, i32, i32]),
     "r3dfs_multi_prototypes": (C.c_int, [vp, i64, vp, vp, i32, i64, i32, vp, vp, vp, vp, vp, sz,
                                          vp]),

@@ -73,7 +73,7 @@ thread_local long long r3dfs_launches = 0;
 
 bool simt_gemm_forced() {
   static const bool v = [] {
-    const char* e = getenv("R3DFS_SIMT_GEMM");
+    const char* e = R3DFS_GETENV("R3DFS_SIMT_GEMM");
     return e && e[0] == '1';
   }();
   return v;
@@ -374,10 +374,32 @@ int r3dfs_fps(const float* feat, int64_t D, const int32_t* set_off, const int32_
                        nullptr, (cudaStream_t)stream);
 }
 
+size_t r3dfs_fps_workspace(int64_t total_rows) {
+  return total_rows > 0 ? fps_q8_spill_bytes(total_rows) + 256 : 0;
+}
+
+int r3dfs_fps_ex(const float* feat, int64_t D, const int32_t* set_off, const int32_t* set_n,
+                 int n_sets, int64_t n_cap, int64_t total_rows, int m_max, int impl,
+                 int32_t* idx_out, void* wsp, size_t ws_bytes, r3dfs_stream_t stream) {
+  if (!feat || !set_off || !set_n || !idx_out || n_sets <= 0 || m_max <= 0 || n_cap <= 0 ||
+      total_rows <= 0 || impl < R3DFS_FPS_AUTO || impl > R3DFS_FPS_Q8)
+    return R3DFS_E_BADARG;
+  if (n_sets > 65535) return R3DFS_E_UNSUPPORTED;
+  uint8_t* spill = nullptr;
+  if (impl != R3DFS_FPS_STREAM && wsp) {
+    if (ws_bytes < r3dfs_fps_workspace(total_rows)) return R3DFS_E_WORKSPACE;
+    WsBump ws(wsp, ws_bytes);
+    spill = ws.take<uint8_t>(fps_q8_spill_bytes(total_rows));
+  }
+  return launch_fps_ex(feat, (int)D, set_off, set_n, n_sets, (int)n_cap, m_max, 0, idx_out,
+                       nullptr, (cudaStream_t)stream, spill, 1, impl);
+}
+
 // ---- getMutiplePrototypes -------------------------------------------------------------------------
 size_t r3dfs_multi_prototypes_workspace(int64_t total_rows, int n_sets, int k) {
   const size_t ch = multi_prototypes_chunks((int)total_rows);
-  return align_up(sizeof(int32_t) * (size_t)n_sets * (k + 1), 256) +
+  return align_up(fps_q8_spill_bytes(total_rows), 256) +
+         align_up(sizeof(int32_t) * (size_t)n_sets * (k + 1), 256) +
          align_up(sizeof(int32_t) * (size_t)n_sets, 256) +
          align_up(sizeof(float) * (size_t)n_sets * ch * (k + 1) * 256, 256) +
          align_up(sizeof(int32_t) * (size_t)n_sets * ch * (k + 1), 256) +
@@ -401,13 +423,14 @@ int r3dfs_multi_prototypes(const float* feat, int64_t D, const int32_t* set_off,
   float* partial = ws.take<float>((size_t)n_sets * ch * (k + 1) * D);
   int32_t* pcount = ws.take<int32_t>((size_t)n_sets * ch * (k + 1));
   float* seed_stats = ws.take<float>((size_t)n_sets * 256);
+  uint8_t* fps_spill = ws.take<uint8_t>(fps_q8_spill_bytes(total_rows));
   if (!ws.ok()) return R3DFS_E_WORKSPACE;
   // n_cap: no set can be larger than the whole buffer
   return launch_multi_prototypes(feat, (int)D, set_off, set_n, n_sets, (int)total_rows, k, picks,
                                  pick_cnt, seed_idx_out, proto_count, assign_out, partial, pcount,
                                  seed_stats, n_sets,
                                  (int64_t)n_sets * (k + 1), proto_out, (int)D,
-                                 (cudaStream_t)stream);
+                                 (cudaStream_t)stream, nullptr, fps_spill);
 }
 
 // ---- affinity + label propagation -------------------------------------------------------------------
@@ -527,6 +550,7 @@ void carve_episode(WsBump& ws, const r3dfs_episode_cfg_t* c, const EpisodeDims& 
   w.cloud_bg_off = ws.take<int32_t>(G * d.C);
   w.cloud_fg_off = ws.take<int32_t>(G * d.C);
   w.setfeat = ws.take<float>(G * d.ns_pts * R3DFS_FEAT_DIM);
+  w.fps_spill = ws.take<uint8_t>(fps_q8_spill_bytes((int64_t)G * d.ns_pts));
   w.picks = ws.take<int32_t>(G * d.S * d.slot);
   w.pick_cnt = ws.take<int32_t>(G * d.S);
   w.seeds = ws.take<int32_t>(G * d.S * d.slot);
@@ -604,7 +628,7 @@ int episode_graph_half(const r3dfs_episode_cfg_t* cfg, const EpisodeDims& d, int
   R3DFS_TRY(launch_multi_prototypes(w.setfeat, D, w.set_off, w.set_n, E * d.S, d.ns_pts,
                                     cfg->n_subprototypes, w.picks, w.pick_cnt, w.seeds,
                                     w.proto_cnt, w.assign, w.partial, w.pcount, w.seed_stats, d.S,
-                                    d.ep_rows, w.F, D, st, sr));
+                                    d.ep_rows, w.F, D, st, sr, w.fps_spill, d.S));
   if (sr) sr->mark(R3DFS_ST_PROTO, st);
   // graph: nodes = [prototype slots | query points]
   graph_init_kernel<<<dim3(nblk(d.nn), E), 256, 0, st>>>(w.proto_cnt, d.S, d.slot, d.ppad, d.nn,

@@ -11,6 +11,16 @@
 
 extern thread_local long long r3dfs_launches;  // diagnostic: kernels launched by this thread
 
+// A/B switches (alternative kernels kept for re-measuring the claims of DESIGN.md §3.1) exist only
+// in the measurement build `libr3dfs_ab.so` (make ab: -DR3DFS_AB_SWITCHES); the shipped library
+// reads no environment variable and keeps no configuration state.
+#ifdef R3DFS_AB_SWITCHES
+#include <stdlib.h>
+#define R3DFS_GETENV(name) getenv(name)
+#else
+#define R3DFS_GETENV(name) ((const char*)nullptr)
+#endif
+
 #define R3DFS_CHECK_LAUNCH()                       \
   do {                                             \
     cudaError_t e__ = cudaGetLastError();          \

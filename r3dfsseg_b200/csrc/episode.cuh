@@ -29,6 +29,7 @@ struct EpisodeWs {
   float* F;
   int32_t *fg_cnt, *keep, *set_off, *set_n, *cloud_bg_off, *cloud_fg_off;
   float* setfeat;
+  uint8_t* fps_spill;  // fps_q8_spill_bytes(all set rows)
   int32_t *picks, *pick_cnt, *seeds, *proto_cnt, *assign, *pcount;
   float *partial, *seed_stats;
   float* cell_mean;

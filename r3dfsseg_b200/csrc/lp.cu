@@ -1622,7 +1622,7 @@ static int launch_cg_group(int G, cudaStream_t st, const int32_t* rowptr, const 
   }
   if (!coop || n_sm < 8) return -1000;
   static const int gs_env = [] {
-    const char* e = getenv("R3DFS_CG_GROUP");
+    const char* e = R3DFS_GETENV("R3DFS_CG_GROUP");
     return e ? atoi(e) : 0;
   }();
   // CTAs per graph: as few as keep (almost) the whole matrix in shared memory, so that as many
@@ -1737,7 +1737,7 @@ int launch_affinity(const float* F, int64_t graph_rows, int64_t row_off, const u
     R3DFS_TRY(launch_gram_dist_tc(F, graph_rows, row_off, G, nn, D, norms, D2, st));
   }
   if (sr) sr->mark(R3DFS_ST_DIST, st);
-  static const bool sel_block = getenv("R3DFS_SELECT_BLOCK") != nullptr;
+  static const bool sel_block = R3DFS_GETENV("R3DFS_SELECT_BLOCK") != nullptr;
   if (nn <= 32 * 80 && !sel_block) {
     const dim3 gs((nn + SELW_WARPS - 1) / SELW_WARPS, G);
     if (nn <= 32 * 40)
@@ -1781,7 +1781,7 @@ int launch_lp_solve(const int32_t* rowptr, const int32_t* rowlen, const uint16_t
   const size_t smem_cg = sizeof(float) * (size_t)nn * ncv;
   if (smem_cg > 200 * 1024) return R3DFS_E_UNSUPPORTED;
   int rc = -1000;
-  static const bool no_group = getenv("R3DFS_CG_NOGROUP") != nullptr;
+  static const bool no_group = R3DFS_GETENV("R3DFS_CG_NOGROUP") != nullptr;
   if (latency && !no_group) {  // matrix resident in shared memory, groups of CTAs (cooperative launch)
     const size_t scratch_floats = (size_t)G * nn * ncv;
     rc = ncv == 4 ? launch_cg_group<4>(G, st, rowptr, rowlen, mcol, mval, valid, nn, k, Y, nc, alpha,
@@ -1792,7 +1792,7 @@ int launch_lp_solve(const int32_t* rowptr, const int32_t* rowlen, const uint16_t
     if (rc != -1000) return rc;
   }
   static const int cl_first = [] {  // A/B switch: R3DFS_CG_CLUSTER = 16 | 8 | 4 | 2
-    const char* e = getenv("R3DFS_CG_CLUSTER");
+    const char* e = R3DFS_GETENV("R3DFS_CG_CLUSTER");
     const int v = e ? atoi(e) : 0;
     return (v == 16 || v == 8 || v == 4 || v == 2) ? v : 0;
   }();
@@ -1825,7 +1825,7 @@ int launch_label_propagate(const int32_t* nbr, float* sim, const uint8_t* valid,
   const int W = (nn + 31) / 32;
   const size_t bits_bytes = sizeof(uint32_t) * (size_t)G * nn * W;
   const size_t pre_bytes = sizeof(uint16_t) * (size_t)G * nn * W;
-  static const bool force_sort = getenv("R3DFS_INEDGE_SORT") != nullptr;
+  static const bool force_sort = R3DFS_GETENV("R3DFS_INEDGE_SORT") != nullptr;
   if (scratch && scratch_bytes >= bits_bytes + pre_bytes && !force_sort) {
     // sort-free: bit matrix of the transposed adjacency -> ranks -> ordered fill
     uint32_t* bits = reinterpret_cast<uint32_t*>(scratch);

@@ -167,7 +167,7 @@ __global__ __launch_bounds__(FPS_THREADS) void fps_kernel(const float* __restric
 // a single episode (the training step) leaves most SMs idle — those get 16-CTA clusters.
 static int fps_cluster_size(int n_sets) {
   static const int forced = [] {  // A/B switch: R3DFS_FPS_CLUSTER = 1..16
-    const char* e = getenv("R3DFS_FPS_CLUSTER");
+    const char* e = R3DFS_GETENV("R3DFS_FPS_CLUSTER");
     const int v = e ? atoi(e) : 0;
     return (v >= 1 && v <= FPS_MAX_CL) ? v : 0;
   }();
@@ -175,9 +175,12 @@ static int fps_cluster_size(int n_sets) {
   return n_sets <= 16 ? 16 : 8;
 }
 
-int launch_fps_ex(const float* feat, int D, const int32_t* set_off, const int32_t* set_n,
-                  int n_sets, int n_cap, int m_max, int k_for_count, int32_t* idx_out,
-                  int32_t* cnt_out, cudaStream_t st) {
+// The streaming kernel above (every pick re-reads the set): few picks (the fps_k = 4 prototypes of
+// the way-contrast loss), feature widths other than 192, callers without a spill area.
+static int launch_fps_stream(const float* feat, int D, const int32_t* set_off,
+                             const int32_t* set_n, int n_sets, int n_cap, int m_max,
+                             int k_for_count, int32_t* idx_out, int32_t* cnt_out,
+                             cudaStream_t st) {
   if (D % 4 != 0 || D > 32 * FPS_MAX_F4 || D <= 0) return R3DFS_E_UNSUPPORTED;
   int CL = fps_cluster_size(n_sets);
   cudaLaunchConfig_t cfg = {};
@@ -189,7 +192,7 @@ int launch_fps_ex(const float* feat, int D, const int32_t* set_off, const int32_
     chunk = (chunk + 3) & ~3;
     smem = sizeof(float) * (size_t)chunk;
     if (smem > 200 * 1024) return R3DFS_E_UNSUPPORTED;
-    e = cudaFuncSetAttribute(fps_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    e = cudaFuncSetAttribute(fps_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) return (int)e;
     if (CL > 8) {
       e = cudaFuncSetAttribute(fps_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
@@ -217,6 +220,39 @@ int launch_fps_ex(const float* feat, int D, const int32_t* set_off, const int32_
   if (e != cudaSuccess) return (int)e;
   ++r3dfs_launches;
   return 0;
+}
+
+// impl: R3DFS_FPS_AUTO / _STREAM / _Q8.  The int8-filter kernel (fps_q8.cu) needs D = 192, a spill
+// area of fps_q8_spill_bytes(total rows) and pays two extra passes over the set, so AUTO takes it
+// from 16 picks up.  sets_per_group > 1 = the episode layout (set 0 of every group is the large
+// background set, the others are per-way foreground sets): two launches with different cluster
+// sizes, so that the small sets do not occupy 16 SMs each.
+int launch_fps_ex(const float* feat, int D, const int32_t* set_off, const int32_t* set_n,
+                  int n_sets, int n_cap, int m_max, int k_for_count, int32_t* idx_out,
+                  int32_t* cnt_out, cudaStream_t st, uint8_t* spill, int sets_per_group,
+                  int impl) {
+  static const bool force_stream = R3DFS_GETENV("R3DFS_FPS_STREAM") != nullptr;  // A/B
+  const bool q8_ok = spill != nullptr && D == 192;
+  if (impl == R3DFS_FPS_Q8 && !q8_ok) return R3DFS_E_UNSUPPORTED;
+  if (impl == R3DFS_FPS_STREAM || !q8_ok || (impl == R3DFS_FPS_AUTO && (m_max < 16 || force_stream)))
+    return launch_fps_stream(feat, D, set_off, set_n, n_sets, n_cap, m_max, k_for_count, idx_out,
+                             cnt_out, st);
+  if (sets_per_group > 1 && n_sets % sets_per_group == 0) {
+    const int groups = n_sets / sets_per_group, per = sets_per_group - 1;
+    R3DFS_TRY(launch_fps_q8(feat, set_off, set_n, groups, 0, 1, sets_per_group, n_cap, 0, m_max,
+                            k_for_count, spill, idx_out, cnt_out, st));
+    // foreground sets: as many CTAs per set as keep all of them in ONE wave (rows beyond the
+    // cluster's shared memory are swept from the spill area, still as bytes)
+    int dev = 0, n_sm = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    int cl = 8;
+    while (cl > 1 && groups * per * cl > n_sm) cl >>= 1;
+    return launch_fps_q8(feat, set_off, set_n, groups * per, 1, per, sets_per_group, n_cap, cl,
+                         m_max, k_for_count, spill, idx_out, cnt_out, st);
+  }
+  return launch_fps_q8(feat, set_off, set_n, n_sets, 0, 1, 1, n_cap, 0, m_max, k_for_count, spill,
+                       idx_out, cnt_out, st);
 }
 
 // --------------------------------------------------------------------------------------------
@@ -417,10 +453,12 @@ int launch_multi_prototypes(const float* feat, int D, const int32_t* set_off,
                             int32_t* pick_cnt, int32_t* seeds, int32_t* proto_cnt,
                             int32_t* assign, float* partial, int32_t* pcount, float* seed_stats,
                             int sets_per_group, int64_t group_rows, float* proto_out, int ld_out,
-                            cudaStream_t st, const StageRec* sr) {
+                            cudaStream_t st, const StageRec* sr, uint8_t* fps_spill,
+                            int fps_sets_per_group) {
   const int m_max = k + 1;
   if (m_max > 128 || D > MEAN_THREADS) return R3DFS_E_UNSUPPORTED;
-  R3DFS_TRY(launch_fps_ex(feat, D, set_off, set_n, n_sets, n_cap, m_max, k, picks, pick_cnt, st));
+  R3DFS_TRY(launch_fps_ex(feat, D, set_off, set_n, n_sets, n_cap, m_max, k, picks, pick_cnt, st,
+                          fps_spill, fps_sets_per_group, R3DFS_FPS_AUTO));
   if (sr) sr->mark(R3DFS_ST_FPS, st);
   seeds_unique_kernel<<<n_sets, 128, 0, st>>>(picks, pick_cnt, set_n, m_max, k, seeds, proto_cnt);
   R3DFS_CHECK_LAUNCH();

@@ -675,7 +675,7 @@ static int launch_knn_tc_t(const float* x, int ld, int C, const float* xx, int64
 
 static bool knn_single_pass_forced() {  // A/B switch: R3DFS_KNN_SINGLE_PASS=1
   static const bool v = [] {
-    const char* e = getenv("R3DFS_KNN_SINGLE_PASS");
+    const char* e = R3DFS_GETENV("R3DFS_KNN_SINGLE_PASS");
     return e && e[0] == '1';
   }();
   return v;

@@ -229,9 +229,14 @@ def features(pw: PackedWeights, x: torch.Tensor, want_level2: bool = False):
 # ------------------------------------------------------------------------------------------------
 # prototypes / graph
 # ------------------------------------------------------------------------------------------------
+FPS_AUTO, FPS_STREAM, FPS_Q8 = 0, 1, 2
+
+
 def fps(feat: torch.Tensor, set_off: torch.Tensor, set_n: torch.Tensor, m_max: int,
-        n_cap: Optional[int] = None) -> torch.Tensor:
-    """Farthest point sampling from local index 0 for several sets at once -> (n_sets, m_max) int32."""
+        n_cap: Optional[int] = None, impl: int = FPS_AUTO) -> torch.Tensor:
+    """Farthest point sampling from local index 0 for several sets at once -> (n_sets, m_max) int32.
+    impl: FPS_STREAM re-reads the FP32 rows for every pick, FPS_Q8 (D = 192) keeps byte rows on chip
+    and re-reads only the rows an exact bound cannot decide; same picks either way."""
     dev = _need_cuda(feat, set_off, set_n)
     feat = _f32(feat).contiguous()
     set_off = set_off.to(torch.int32).contiguous()
@@ -242,8 +247,14 @@ def fps(feat: torch.Tensor, set_off: torch.Tensor, set_n: torch.Tensor, m_max: i
     out = torch.full((n_sets, m_max), -1, dtype=torch.int32, device=dev)
     L = _lib.lib()
     with torch.cuda.device(dev):
-        check(L.r3dfs_fps(_p(feat), feat.shape[1], _p(set_off), _p(set_n), n_sets, n_cap, m_max,
-                          _p(out), _stream()), "r3dfs_fps")
+        if impl == FPS_STREAM:
+            check(L.r3dfs_fps(_p(feat), feat.shape[1], _p(set_off), _p(set_n), n_sets, n_cap, m_max,
+                              _p(out), _stream()), "r3dfs_fps")
+        else:
+            ws = torch.empty(L.r3dfs_fps_workspace(feat.shape[0]), dtype=torch.uint8, device=dev)
+            check(L.r3dfs_fps_ex(_p(feat), feat.shape[1], _p(set_off), _p(set_n), n_sets, n_cap,
+                                 feat.shape[0], m_max, impl, _p(out), _p(ws), ws.numel(),
+                                 _stream()), "r3dfs_fps_ex")
     return out
 
 

@@ -287,15 +287,69 @@ def _fps_adjudicate(feat, got, ref):
     return abs(a - b) <= 4 * np.spacing(np.float32(max(a, b))), i
 
 
+@pytest.mark.parametrize("impl", [1, 2])  # ops.FPS_STREAM, ops.FPS_Q8
 @pytest.mark.parametrize("n,D,m", [(3000, 192, 100), (15000, 192, 101), (257, 192, 50), (64, 16, 64)])
-def test_fps_sequence(n, D, m):
+def test_fps_sequence(n, D, m, impl):
     from r3dfsseg_b200 import ops
+    if impl == ops.FPS_Q8 and D != 192:
+        pytest.skip("the int8-filter kernel is built for D = 192")
     g = torch.Generator().manual_seed(n)
     feat = torch.randn((n, D), generator=g) * 0.2
-    got = ops.fps(feat.to(DEV), torch.tensor([0], device=DEV), torch.tensor([n], device=DEV), m).cpu()[0]
+    got = ops.fps(feat.to(DEV), torch.tensor([0], device=DEV), torch.tensor([n], device=DEV), m,
+                  impl=impl).cpu()[0]
     ref = O.fps(feat, m)
     ok, where = _fps_adjudicate(feat, got.long(), ref)
     assert ok, f"FPS diverges at pick {where} beyond a tie"
+
+
+def _fps_structured_sets(seed):
+    """Sets that stress the int8 filter of the on-chip FPS kernel: low-rank clustered features (the
+    regime of real episodes), a large common offset (quantisation step >> spread of most
+    dimensions), exact duplicates, a constant set, tiny sets, and sets larger than what one
+    16-CTA cluster keeps in shared memory (rows beyond that are swept from the spill area)."""
+    g = torch.Generator().manual_seed(seed)
+    sets = []
+    basis = torch.randn((12, 192), generator=g)
+    centres = torch.randn((7, 12), generator=g) * 2.0
+    for n in (2300, 15500):
+        c = centres[torch.randint(0, 7, (n,), generator=g)]
+        sets.append((c + 0.3 * torch.randn((n, 12), generator=g)) @ basis * 0.1
+                    + 0.01 * torch.randn((n, 192), generator=g))
+    sets.append(sets[0][:900] + 1000.0)                       # offset: FP32 spacing 6e-5 vs spread ~1
+    dup = torch.randn((40, 192), generator=g)
+    sets.append(dup[torch.randint(0, 40, (1200,), generator=g)])   # many exact ties
+    sets.append(torch.full((300, 192), 0.25))                  # degenerate: every row equal
+    sets.append(torch.randn((1, 192), generator=g))
+    sets.append(torch.randn((37, 192), generator=g))
+    sets.append(torch.randn((20000, 192), generator=g) * 0.2)  # > 16 x 1004 resident rows
+    sets.append(torch.randn((30720, 192), generator=g) * torch.rand((192,), generator=g))
+    return sets
+
+
+def test_fps_int8_filter_equals_streaming_kernel():
+    """r3dfs_fps_ex(R3DFS_FPS_Q8) == r3dfs_fps, pick for pick: the filter only skips rows whose
+    running minimum provably stays, and re-reads the others with the streaming kernel's FP32
+    arithmetic.  Also pinned to the oracle (ties adjudicated in FP64)."""
+    from r3dfsseg_b200 import ops
+    sets = _fps_structured_sets(5)
+    sizes = [int(x.shape[0]) for x in sets]
+    feat = torch.cat(sets, 0)
+    off = torch.tensor([0] + list(np.cumsum(sizes)[:-1]), dtype=torch.int32)
+    n = torch.tensor(sizes, dtype=torch.int32)
+    fd = feat.to(DEV)
+    for m in (101, 16):
+        a = ops.fps(fd, off.to(DEV), n.to(DEV), m, n_cap=max(sizes), impl=ops.FPS_STREAM).cpu()
+        b = ops.fps(fd, off.to(DEV), n.to(DEV), m, n_cap=max(sizes), impl=ops.FPS_Q8).cpu()
+        for s, sz in enumerate(sizes):
+            cnt = min(m, sz)
+            assert torch.equal(a[s, :cnt], b[s, :cnt]), (m, s, sz)
+    for s in (0, 2, 3, 4):
+        f = sets[s]
+        cnt = min(101, sizes[s])
+        ok, where = _fps_adjudicate(f, b0 := ops.fps(
+            f.to(DEV), torch.tensor([0], device=DEV), torch.tensor([sizes[s]], device=DEV), cnt,
+            impl=ops.FPS_Q8).cpu()[0].long(), O.fps(f, cnt))
+        assert ok, (s, where)
 
 
 def test_fps_many_sets_and_prefix_property():

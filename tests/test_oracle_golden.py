@@ -81,10 +81,11 @@ def test_train_oracle_vs_reference_golden(fixture_sd):
             continue  # exactly-zero gradient (bias ahead of batch-stat BN): rounding noise only
         s = p.grad.reshape(-1)[::29]
         ref = g["grad_sample"][k]
-        assert float((s - ref).abs().max()) <= 2e-5 * float(ref.abs().max()) + 1e-9, k
+        assert float((s - ref).abs().max()) <= 2e-5 * float(ref.abs().max()) + 1e-8, k
     for k, v in running.items():
         if v.dtype.is_floating_point:
-            assert float((v - g["running"][k]).abs().max()) < 1e-5, k
+            ref = g["running"][k]
+            assert float((v - ref).abs().max()) < 1e-5 * max(1.0, float(ref.abs().max())), k
         else:
             assert int(v) == int(g["running"][k])
 
