@@ -164,6 +164,31 @@ int r3dfs_fps_ex(const float* feat, int64_t D, const int32_t* set_off, const int
                  int n_sets, int64_t n_cap, int64_t total_rows, int m_max, int impl,
                  int32_t* idx_out, void* ws, size_t ws_bytes, r3dfs_stream_t stream);
 
+/* Multi-scale degree-based noise suppression over support shots, eval only — reference
+ * models/mpti.py:87-223 (Mean_pl_support_y at scales (1,1,1) and (2,2,1), the two-scale vote) with
+ * grid_sampling (:316-371): per shot the bounding box of the foreground xyz (channels 0-2 of
+ * support_x, mask == 1), cells with INCLUSIVE bounds on both sides in the reference's FP32 bound
+ * arithmetic (start = min + i * d, end = start + d), cell seed = mean feature of its points.
+ * support_x: (E, n_way*k_shot, 9, N) by strides; support_y: (E, n_way*k_shot, N) int32;
+ * support_feat: (E, n_way*k_shot*N, 192) point-major rows.
+ * Cells per shot: index 0 = the single cell of scale (1,1,1); 1 + 2*ix + iy = cell (ix, iy) of
+ * scale (2,2,1) (the reference's x-major loop order).
+ *   cell_mean  (E*n_way*k_shot, 5, 192)  mean feature per cell (0 when empty)
+ *   cell_count (E*n_way*k_shot, 5)       points per cell
+ *   cell_mask  (E*n_way*k_shot, N) u8, nullable: bit q set = point lies in cell q (a point on a
+ *              shared face lies in both cells; the reference's `assignments` keeps the later one)
+ *   degree     (E*n_way, 2, 4*k_shot), nullable: row sums of the masked cosine map (cubed at scale
+ *              (1,1,1)) in seed order (shot-major, non-empty cells only), NaN padded
+ *   scale_flag (E*n_way, 2, k_shot), nullable: per-scale majority vote (mean(degree > mean) > 0.5)
+ *   keep       (E*n_way*k_shot) int32: 1 = shot kept (mean of the two flags >= 0.5; a way that
+ *              loses every shot keeps all of them);  clean_flag: same as float, nullable. */
+size_t r3dfs_mdns_workspace(int n_episodes, int n_way, int k_shot);
+int r3dfs_mdns(const float* support_x, int64_t s_e, int64_t s_cloud, int64_t s_c, int64_t s_n,
+               const int32_t* support_y, const float* support_feat, int n_episodes, int n_way,
+               int k_shot, int64_t N, float* cell_mean, int32_t* cell_count, uint8_t* cell_mask,
+               float* degree, float* scale_flag, int32_t* keep, float* clean_flag, void* ws,
+               size_t ws_bytes, r3dfs_stream_t stream);
+
 /* getMutiplePrototypes(feat, k) — models/mpti.py:597-634, for `n_sets` sets in one call:
  * m = ceil(fp32(n) * fp32(k / n)) FPS seeds (k or k+1), sorted + deduplicated (`.unique()`),
  * assignment = argmin_j || f - seed_j + 1e-6 ||_2 (torch<=1.8 pairwise_distance, first minimum),

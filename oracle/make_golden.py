@@ -7,6 +7,7 @@ Files (small on purpose; episodes are regenerated from their seed, only outputs 
   golden_episodes.pt   MPTI_SelfAtten.forward outputs for the three episode configurations
   golden_protonet.pt   ProtoNet_Contrast.forward (eval) outputs; `python -m oracle.make_golden protonet`
                        writes only this file
+  golden_metric.json   evaluate_metric on a seeded random case (`python -m oracle.make_golden metric`)
   golden_parity.pt     free-running parity cases (`python -m oracle.make_golden parity`): for the
                        four episode configurations above plus 10 seeds each of BASELINE.json
                        configs[2] (S3DIS-shape 2-way 5-shot) and configs[3] (ScanNet-shape 3-way
@@ -83,6 +84,12 @@ def parity(ref, sd):
         with torch.no_grad(), ref_shims.quiet():
             pred, loss = m(ep.support_x, ep.support_y, ep.query_x, ep.query_y,
                            gt_support_y=ep.gt_support_y, eval=ev)
+            clean = None
+            if ev:
+                sf = m.getFeatures(ep.support_x.reshape(n_way * k_shot, 9, -1)).view(
+                    n_way, k_shot, 192, -1)
+                _, clean = m.Mean_pl_support_y_multi_scale(sf, ep.support_y, ep.gt_support_y,
+                                                           ep.support_x)
             adj = O.forward_episode_fp64(sd, ep.support_x, ep.support_y, ep.query_x, ep.query_y,
                                          eval_mdns=ev)
         p64 = adj["query_pred"]
@@ -92,7 +99,8 @@ def parity(ref, sd):
                          eval=ev, query_pred=pred.contiguous().clone(), loss=loss.clone(),
                          query_pred_fp64=p64.float().contiguous().clone(),
                          loss_fp64=adj["loss"].float().clone(),
-                         clean_flag_fp64=adj["clean_flag"], proto_count_fp64=adj["proto_count"],
+                         clean_flag=clean, clean_flag_fp64=adj["clean_flag"],
+                         proto_count_fp64=adj["proto_count"],
                          num_prototypes=int(m.num_prototypes))
         print(name, "loss", float(loss), "fp64", float(adj["loss"]), "ref32 vs fp64: max rel",
               "%.2e" % rel, "labels", "%.5f" % agree, "acc",
@@ -101,10 +109,33 @@ def parity(ref, sd):
     print("golden_parity.pt written")
 
 
+def metric(ref):
+    """evaluate_metric (eval_noise.py:23-72) on a seeded random case -> golden_metric.json."""
+    import json
+    import re
+    from tests.test_oracle_golden import _metric_case
+    case = dict(seed=0, n_eps=7, n_way=3, n_q=3, N=257, pool=6)
+    preds, gts, l2c, test_classes = _metric_case(**case)
+
+    class Log:
+        lines = []
+
+        def cprint(self, s):
+            self.lines.append(s)
+
+    miou = float(ref.evaluate_metric(Log(), preds, gts, l2c, test_classes))
+    ious = [float(re.search(r"IoU: ([0-9.]+)", s).group(1)) for s in Log.lines if "IoU:" in s]
+    with open(os.path.join(GOLD, "golden_metric.json"), "w") as f:
+        json.dump(dict(case=case, test_classes=test_classes, mean_iou=miou, iou=ious), f)
+    print("golden_metric.json written", miou)
+
+
 def main():
     ref = ref_shims.load_reference()
     torch.set_num_threads(os.cpu_count())
     sd = torch.load(os.path.join(GOLD, "weights_fixture.pt"))
+    if sys.argv[1:] == ["metric"]:
+        return metric(ref)
     if sys.argv[1:] == ["protonet"]:
         return protonet(ref, sd)
     if sys.argv[1:] == ["parity"]:

@@ -180,24 +180,29 @@ def grid_sampling(spatial, feat, n_x, n_y, n_z):
     return torch.cat(seeds, dim=0), assign, count
 
 
-def mdns_flags_one_scale(support_feat, support_y, support_x, n_x, n_y, n_z):
-    """models/mpti.py:87-176 -> flag (n_way, k_shot)"""
+def mdns_flags_one_scale(support_feat, support_y, support_x, n_x, n_y, n_z, internals=None):
+    """models/mpti.py:87-176 -> flag (n_way, k_shot).  `internals` (a list) receives, per way, the
+    degree vector and the per-shot grid_sampling results (tests of the CUDA kernels' internals)."""
     n_way, k_shot = support_y.shape[:2]
     flag = torch.zeros((n_way, k_shot))
     for way in range(n_way):
         seeds, lens = [], []
+        grids = []
         for k in range(k_shot):
             fg = support_y[way, k] == 1
             f = support_feat[way, k][:, fg].transpose(1, 0)
             sp = support_x[way, k][:, fg].transpose(1, 0)
-            s, _, n = grid_sampling(sp, f, n_x, n_y, n_z)
+            s, a, n = grid_sampling(sp, f, n_x, n_y, n_z)
             seeds.append(s)
             lens.append(n)
+            grids.append((s, a, n))
         sn = F.normalize(torch.cat(seeds, dim=0), p=2, dim=1)
         cos = torch.mm(sn, sn.t()) * (1.0 - torch.eye(sn.shape[0], dtype=sn.dtype))
         if n_x == 1 and n_y == 1 and n_z == 1:
             cos = cos.pow(3)
         deg = cos.sum(1)
+        if internals is not None:
+            internals.append(dict(degree=deg, grids=grids))
         mask = deg > deg.mean()
         c = 0
         for k in range(k_shot):

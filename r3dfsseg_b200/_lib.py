@@ -87,6 +87,9 @@ SIGNATURES = {
     "r3dfs_fps": (C.c_int, [vp, i64, vp, vp, i32, i64, i32, vp, vp]),
     "r3dfs_fps_workspace": (sz, [i64]),
     "r3dfs_fps_ex": (C.c_int, [vp, i64, vp, vp, i32, i64, i64, i32, i32, vp, vp, sz, vp]),
+    "r3dfs_mdns_workspace": (sz, [i32, i32, i32]),
+    "r3dfs_mdns": (C.c_int, [vp, i64, i64, i64, i64, vp, vp, i32, i32, i32, i64, vp, vp, vp, vp, vp,
+                             vp, vp, vp, sz, vp]),
     "r3dfs_multi_prototypes_workspace": (sz, [i64, i32, i32]),
     "r3dfs_multi_prototypes": (C.c_int, [vp, i64, vp, vp, i32, i64, i32, vp, vp, vp, vp, vp, sz,
                                          vp]),

@@ -433,6 +433,31 @@ int r3dfs_multi_prototypes(const float* feat, int64_t D, const int32_t* set_off,
                                  (cudaStream_t)stream, nullptr, fps_spill);
 }
 
+// ---- multi-scale degree-based noise suppression ------------------------------------------------------
+size_t r3dfs_mdns_workspace(int n_episodes, int n_way, int k_shot) {
+  if (n_episodes <= 0 || n_way <= 0 || k_shot <= 0) return 0;
+  return align_up(sizeof(int32_t) * (size_t)n_episodes * n_way * k_shot, 256) + 256;
+}
+
+int r3dfs_mdns(const float* support_x, int64_t s_e, int64_t s_cloud, int64_t s_c, int64_t s_n,
+               const int32_t* support_y, const float* support_feat, int n_episodes, int n_way,
+               int k_shot, int64_t N, float* cell_mean, int32_t* cell_count, uint8_t* cell_mask,
+               float* degree, float* scale_flag, int32_t* keep, float* clean_flag, void* wsp,
+               size_t ws_bytes, r3dfs_stream_t stream) {
+  if (!support_x || !support_y || !support_feat || !cell_mean || !cell_count || !keep || !wsp ||
+      n_episodes <= 0 || n_way <= 0 || k_shot <= 0 || N <= 0)
+    return R3DFS_E_BADARG;
+  if (N > 200 * 1024) return R3DFS_E_UNSUPPORTED;
+  if (ws_bytes < r3dfs_mdns_workspace(n_episodes, n_way, k_shot)) return R3DFS_E_WORKSPACE;
+  WsBump ws(wsp, ws_bytes);
+  int32_t* fg_cnt = ws.take<int32_t>((size_t)n_episodes * n_way * k_shot);
+  if (!ws.ok()) return R3DFS_E_WORKSPACE;
+  return launch_mdns(support_x, s_e, s_cloud, s_c, s_n, support_y, support_feat,
+                     (int64_t)n_way * k_shot * N, 0, n_episodes, n_way, k_shot, (int)N,
+                     R3DFS_FEAT_DIM, cell_mean, cell_count, fg_cnt, keep, clean_flag,
+                     (cudaStream_t)stream, cell_mask, degree, scale_flag);
+}
+
 // ---- affinity + label propagation -------------------------------------------------------------------
 size_t r3dfs_affinity_workspace(int n_graphs, int64_t n_max, int64_t D, int k) {
   (void)D;
@@ -460,7 +485,7 @@ size_t r3dfs_label_propagate_workspace(int n_graphs, int64_t n_max, int k, int n
   (void)n_cls;
   const size_t W = (n + 31) / 32;  // bit matrix + rank prefixes of the sort-free in-edge build
   return align_up(4 * G * n * k, 256) * 3 + align_up(4 * G * (n + 1), 256) * 6 +
-         align_up(4 * G * n * 8, 256) * 4 + align_up(6 * G * n * k * 2, 256) +
+         align_up(4 * G * n * 8, 256) * 4 + align_up(6 * G * n * (size_t)lp_rowcap(k), 256) +
          align_up(6 * G * n * W, 256) + 8192;
 }
 
@@ -485,8 +510,8 @@ int r3dfs_label_propagate(const int32_t* nbr, const float* sim, const uint8_t* v
   int32_t* rowptr = ws.take<int32_t>(G * n);
   int32_t* rowlen = ws.take<int32_t>(G * n);
   int32_t* cursor = ws.take<int32_t>(G);
-  uint16_t* mcol = ws.take<uint16_t>(G * n * k * 2);
-  float* mval = ws.take<float>(G * n * k * 2);
+  uint16_t* mcol = ws.take<uint16_t>(G * n * lp_rowcap(k));
+  float* mval = ws.take<float>(G * n * lp_rowcap(k));
   float* X = ws.take<float>(G * n * 8);
   float* R = ws.take<float>(G * n * 8);
   float* P = ws.take<float>(G * n * 8);
@@ -578,8 +603,8 @@ void carve_episode(WsBump& ws, const r3dfs_episode_cfg_t* c, const EpisodeDims& 
   w.rowptr = ws.take<int32_t>(G * nn);
   w.rowlen = ws.take<int32_t>(G * nn);
   w.cursor = ws.take<int32_t>(G);
-  w.mcol = ws.take<uint16_t>(G * nn * k * 2);
-  w.mval = ws.take<float>(G * nn * k * 2);
+  w.mcol = ws.take<uint16_t>(G * nn * lp_rowcap(k));
+  w.mval = ws.take<float>(G * nn * lp_rowcap(k));
   w.Z = ws.take<float>(G * nn * d.nc);
   w.X = ws.take<float>(G * nn * 8);
   w.R = ws.take<float>(G * nn * 8);

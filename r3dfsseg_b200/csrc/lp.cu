@@ -846,7 +846,7 @@ __global__ __launch_bounds__(256) void in_sort_warp_kernel(const int32_t* __rest
 // its k out-edges in index order (mutual in-weights added in), then the non-mutual in-edges in
 // source order.  One warp per row; each in-edge is looked up in the sorted out-list by bisection.
 // Row segments are handed out with an atomic cursor: their placement may differ run to run, the
-// contents (and so every sum taken over a row) do not.
+// contents (and so every sum taken over a row) do not.  A graph owns lp_rowcap(k) entries per node.
 // --------------------------------------------------------------------------------------------
 __global__ __launch_bounds__(256) void merge_rows_kernel(
     const int32_t* __restrict__ nbr, const float* __restrict__ sim,
@@ -894,10 +894,13 @@ __global__ __launch_bounds__(256) void merge_rows_kernel(
     keep += __popc(__ballot_sync(0xffffffffu, kp));
   }
   const int total = k + keep;
+  // segments are multiples of 4 entries (the solver reads a row as uint2 + float4 groups); the
+  // pad entries are (column 0, weight 0) and lie beyond rowlen
+  const int padded = (total + 3) & ~3;
   int start = 0;
-  if (lane == 0) start = atomicAdd(&cursor[g], total);
+  if (lane == 0) start = atomicAdd(&cursor[g], padded);
   start = __shfl_sync(0xffffffffu, start, 0);
-  const int64_t mb = vb * k * 2 + start;
+  const int64_t mb = vb * lp_rowcap(k) + start;
   // pass 2: fold mutual in-weights into the out entries, append the rest
   int run = 0;
   for (int t0 = e0; t0 < e1; t0 += 32) {
@@ -928,6 +931,10 @@ __global__ __launch_bounds__(256) void merge_rows_kernel(
     mcol[mb + t] = (uint16_t)s_idx[t];
     mval[mb + t] = s_val[t];
   }
+  if (lane < padded - total) {
+    mcol[mb + total + lane] = 0;
+    mval[mb + total + lane] = 0.f;
+  }
   if (lane == 0) {
     rowptr[vb + i] = start;
     rowlen[vb + i] = total;
@@ -947,7 +954,7 @@ __global__ __launch_bounds__(256) void degree_merged_kernel(const int32_t* __res
   const int L = rowlen[vb + i];
   float d = 0.f;
   if (L > 0) {
-    const float* v = mval + vb * k * 2 + rowptr[vb + i];
+    const float* v = mval + vb * lp_rowcap(k) + rowptr[vb + i];
     for (int t = lane; t < L; t += 32) d += v[t];
     d = warp_sum(d);
     d = sqrtf(1.0f / (d + 2.220446049250313e-16f));
@@ -968,7 +975,7 @@ __global__ void normalize_merged_kernel(const int32_t* __restrict__ rowptr,
   const int L = rowlen[vb + i];
   const float* dg = dinv + vb;
   const float di = dg[i];
-  const int64_t mb = vb * k * 2 + rowptr[vb + i];
+  const int64_t mb = vb * lp_rowcap(k) + rowptr[vb + i];
   for (int t = lane; t < L; t += 32) mval[mb + t] = (di * mval[mb + t]) * dg[mcol[mb + t]];
 }
 
@@ -984,7 +991,10 @@ __global__ void normalize_merged_kernel(const int32_t* __restrict__ rowptr,
 //     every CTA sees bit-identical scalars and the control flow stays cluster-uniform.
 // --------------------------------------------------------------------------------------------
 #define CG_THREADS 1024
-#define CGC_THREADS 512  // cluster kernel: 512 threads, two CTAs per SM — all 25 graphs of a call are in flight at once (200 CTAs) instead of 18 + 7 in two waves, and half an SM stays free for other streams (6.93 -> 6.55 ms, bench +2 %; 256 threads: 9.9 ms)
+#define CGC_THREADS 768  // cluster kernel: 24 warps, ONE CTA per SM (85 registers: the queue of row rounds in flight)
+#define CG_WARPS (CGC_THREADS / 32)
+#define CG_Q 4            // rounds (128 matrix entries each) in flight per warp
+#define CG_MAXR 96        // rows per warp in the schedule table -> at most 2304 rows per CTA
 #define CG_CL_MAX 16
 #define CG_MAXC 8
 
@@ -1027,7 +1037,7 @@ __device__ __forceinline__ void cg_allreduce(cg::cluster_group& cluster, CgExcha
 
 // Vectors are stored padded to NCV columns (NCV = 4 or 8) so a node's row is one or two float4.
 template <int NCV>
-__global__ __launch_bounds__(CGC_THREADS, 2) void lp_cg_kernel(
+__global__ __launch_bounds__(CGC_THREADS, 1) void lp_cg_kernel(
     const int32_t* __restrict__ rowptr, const int32_t* __restrict__ rowlen,
     const uint16_t* __restrict__ mcol, const float* __restrict__ mval,
     const uint8_t* __restrict__ valid, int nn, int k,
@@ -1040,6 +1050,7 @@ __global__ __launch_bounds__(CGC_THREADS, 2) void lp_cg_kernel(
   extern __shared__ __align__(16) float Ps[];  // [nn][NCV] staged copy of P
   __shared__ CgExchange ex;
   __shared__ float s_warp[(CGC_THREADS / 32) * CG_MAXC];
+  __shared__ int2 s_meta[CG_WARPS * CG_MAXR];  // per warp: (list offset, groups << 12 | local row)
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const int64_t vb = (int64_t)g * nn;
   const uint8_t* vg = valid + vb;
@@ -1051,8 +1062,8 @@ __global__ __launch_bounds__(CGC_THREADS, 2) void lp_cg_kernel(
   float* APg = AP + vb * NCV;
   const int32_t* rp = rowptr + vb;
   const int32_t* rl = rowlen + vb;
-  const uint16_t* mc = mcol + vb * k * 2;
-  const float* mv = mval + vb * k * 2;
+  const uint16_t* mc = mcol + vb * lp_rowcap(k);
+  const float* mv = mval + vb * lp_rowcap(k);
   const int chunk = (nn + CL - 1) / CL;
   const int lo = min(nn, rank * chunk), hi = min(nn, lo + chunk);
   int xcnt = 0;
@@ -1082,6 +1093,65 @@ __global__ __launch_bounds__(CGC_THREADS, 2) void lp_cg_kernel(
     all_done = all_done && done[c];
   }
   const float tol2 = tol * tol;
+  // ---- row schedule, built once per solve -------------------------------------------------------
+  // The rows of this CTA are sorted by list length and dealt to the warps in snake order, so every
+  // warp streams (nearly) the same number of entries per product; a warp's rows and their list
+  // offsets/lengths sit in a shared-memory table (one broadcast LDS per row instead of dependent
+  // global loads).  The schedule depends only on the row lengths, so it is the same in every run
+  // and every floating-point sum keeps its order.
+  {
+    uint32_t* s_key = reinterpret_cast<uint32_t*>(Ps);  // Ps is not live yet
+    const int nrows = hi - lo;
+    int npow = 32;
+    while (npow < nrows) npow <<= 1;
+    for (int i = tid; i < npow; i += CGC_THREADS) {
+      uint32_t key = 0;  // (groups of 4 entries) << 12 | local row ; 0-length rows sort last
+      if (i < nrows) {
+        const int n4 = vg[lo + i] ? (rl[lo + i] + 3) >> 2 : 0;
+        key = ((uint32_t)n4 << 12) | (uint32_t)i;
+      }
+      s_key[i] = key;
+    }
+    __syncthreads();
+    for (int ksz = 2; ksz <= npow; ksz <<= 1)
+      for (int j = ksz >> 1; j > 0; j >>= 1) {
+        for (int i = tid; i < npow; i += CGC_THREADS) {
+          const int ixj = i ^ j;
+          if (ixj > i) {
+            const uint32_t x = s_key[i], y = s_key[ixj];
+            const bool desc = (i & ksz) == 0;  // descending overall
+            if (desc ? x < y : x > y) {
+              s_key[i] = y;
+              s_key[ixj] = x;
+            }
+          }
+        }
+        __syncthreads();
+      }
+    for (int i = tid; i < CG_WARPS * CG_MAXR; i += CGC_THREADS) s_meta[i] = make_int2(0, 0);
+    __syncthreads();
+    for (int i = tid; i < nrows; i += CGC_THREADS) {
+      const uint32_t key = s_key[i];
+      if ((key >> 12) == 0) continue;
+      const int pass = i / CG_WARPS, pos = i % CG_WARPS;
+      const int ww = (pass & 1) ? CG_WARPS - 1 - pos : pos;
+      s_meta[ww * CG_MAXR + pass] = make_int2(rp[lo + (int)(key & 0xfffu)], (int)key);
+    }
+    __syncthreads();
+  }
+  const int2* my_meta = s_meta + w * CG_MAXR;
+  int nr_w = 0, n_rounds = 0;  // rows of this warp, rounds of 128 entries over all of them
+  for (int j = lane; j < CG_MAXR; j += 32) {
+    const int n4 = (int)((uint32_t)my_meta[j].y >> 12);
+    nr_w += n4 > 0;
+    n_rounds += (n4 + 31) >> 5;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    nr_w += __shfl_xor_sync(0xffffffffu, nr_w, o);
+    n_rounds += __shfl_xor_sync(0xffffffffu, n_rounds, o);
+  }
+  __syncthreads();  // s_key (aliasing Ps) is dead from here on
   int it = 0;
   while (!all_done && it < max_iter) {
     // ---- stage P (written by every CTA of the cluster, published by the last cluster.sync)
@@ -1093,89 +1163,110 @@ __global__ __launch_bounds__(CGC_THREADS, 2) void lp_cg_kernel(
     }
     __syncthreads();
     // ---- AP = P - alpha * S P  on my rows; partial P.AP
+    // The (col, val) lists of the warp's rows are read as ROUNDS of 128 entries (lane = one uint2 of
+    // columns + one float4 of weights) through a queue of CG_Q rounds in flight that runs across
+    // row boundaries: the loads of the next rows are under way while a row is reduced.
 #pragma unroll
     for (int c = 0; c < NCV; ++c) part[c] = 0.f;
-    for (int row = lo + w; row < hi; row += CGC_THREADS / 32) {
-      if (!vg[row]) continue;  // warp-uniform (AP stays 0 from the initialisation)
+    {
       float acc[NCV];
+      float my_part[NCV / 4];  // lanes 0, 8, 16, 24 own components 4g + lane / 8
 #pragma unroll
       for (int c = 0; c < NCV; ++c) acc[c] = 0.f;
-      // one merged row: (col, val) pairs streamed with 8 independent loads in flight per lane
-      const int L = rl[row];
-      const uint16_t* crow = mc + rp[row];
-      const float* vrow = mv + rp[row];
-      // full blocks of 256 entries: 8 unguarded (col, val) pairs per lane in flight; the remainder
-      // (rows average ~264 entries, so usually a handful) goes 32 at a time instead of paying for
-      // another predicated 8-deep block
-      int t0 = 0;
-      for (; t0 + 256 <= L; t0 += 256) {
-        int cj[8];
-        float cv[8];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const int t = t0 + lane + 32 * u;
-          cj[u] = (int)crow[t];
-          cv[u] = vrow[t];
+      for (int q = 0; q < NCV / 4; ++q) my_part[q] = 0.f;
+      int ij = 0, ir = 0, ip = 0, in4 = 0;  // issue pointer: row slot, round, list offset, groups
+      int cj = 0, cr = 0, cn4 = 0, crow = 0;  // consume pointer
+      if (nr_w > 0) {
+        const int2 m0 = my_meta[0];
+        ip = m0.x;
+        in4 = cn4 = (int)((uint32_t)m0.y >> 12);
+        crow = lo + (m0.y & 0xfff);
+      }
+      auto issue = [&](uint2& c, float4& v) {
+        const int gidx = ir * 32 + lane;
+        c = make_uint2(0u, 0u);
+        v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (gidx < in4) {
+          c = __ldcs(reinterpret_cast<const uint2*>(mc + ip) + gidx);
+          v = __ldcs(reinterpret_cast<const float4*>(mv + ip) + gidx);
         }
+        if (++ir * 32 >= in4) {
+          ir = 0;
+          if (++ij < nr_w) {
+            const int2 m = my_meta[ij];
+            ip = m.x;
+            in4 = (int)((uint32_t)m.y >> 12);
+          }
+        }
+      };
+      auto fma4 = [&](float wgt, unsigned byte_off) {
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
+        for (int q = 0; q < NCV / 4; ++q) {
+          const float4 p4 = *reinterpret_cast<const float4*>(
+              reinterpret_cast<const unsigned char*>(Ps) + byte_off + 16 * q);
+          acc[4 * q + 0] = fmaf(wgt, p4.x, acc[4 * q + 0]);
+          acc[4 * q + 1] = fmaf(wgt, p4.y, acc[4 * q + 1]);
+          acc[4 * q + 2] = fmaf(wgt, p4.z, acc[4 * q + 2]);
+          acc[4 * q + 3] = fmaf(wgt, p4.w, acc[4 * q + 3]);
+        }
+      };
+      auto consume = [&](const uint2& c, const float4& v) {
+        constexpr unsigned SH = NCV == 4 ? 4 : 5;  // node -> byte offset of its row of P
+        fma4(v.x, (c.x & 0xffffu) << SH);
+        fma4(v.y, (c.x >> 16) << SH);
+        fma4(v.z, (c.y & 0xffffu) << SH);
+        fma4(v.w, (c.y >> 16) << SH);
+        if (++cr * 32 >= cn4) {  // the row is complete: 4 sums per group with 6 shuffles
 #pragma unroll
           for (int q = 0; q < NCV / 4; ++q) {
-            const float4 p4 = *reinterpret_cast<const float4*>(Ps + (int64_t)cj[u] * NCV + 4 * q);
-            acc[4 * q + 0] = fmaf(cv[u], p4.x, acc[4 * q + 0]);
-            acc[4 * q + 1] = fmaf(cv[u], p4.y, acc[4 * q + 1]);
-            acc[4 * q + 2] = fmaf(cv[u], p4.z, acc[4 * q + 2]);
-            acc[4 * q + 3] = fmaf(cv[u], p4.w, acc[4 * q + 3]);
+            const bool up = lane & 16, up2 = lane & 8;
+            float s0 = up ? acc[4 * q + 2] : acc[4 * q + 0], s1 = up ? acc[4 * q + 3] : acc[4 * q + 1];
+            const float t0 = up ? acc[4 * q + 0] : acc[4 * q + 2],
+                        t1 = up ? acc[4 * q + 1] : acc[4 * q + 3];
+            s0 += __shfl_xor_sync(0xffffffffu, t0, 16);
+            s1 += __shfl_xor_sync(0xffffffffu, t1, 16);
+            float u = up2 ? s1 : s0;
+            const float vv = up2 ? s0 : s1;
+            u += __shfl_xor_sync(0xffffffffu, vv, 8);
+            u += __shfl_xor_sync(0xffffffffu, u, 4);
+            u += __shfl_xor_sync(0xffffffffu, u, 2);
+            u += __shfl_xor_sync(0xffffffffu, u, 1);
+            if ((lane & 7) == 0) {  // lane 8 c holds component 4 q + c
+              const int comp = 4 * q + (lane >> 3);
+              const float pv = Ps[(size_t)crow * NCV + comp];
+              const float ap = pv - alpha * u;
+              APg[(int64_t)crow * NCV + comp] = ap;
+              my_part[q] = fmaf(pv, ap, my_part[q]);
+            }
+            acc[4 * q + 0] = acc[4 * q + 1] = acc[4 * q + 2] = acc[4 * q + 3] = 0.f;
+          }
+          cr = 0;
+          if (++cj < nr_w) {
+            const int2 m = my_meta[cj];
+            cn4 = (int)((uint32_t)m.y >> 12);
+            crow = lo + (m.y & 0xfff);
+          }
+        }
+      };
+      uint2 qc[CG_Q];
+      float4 qv[CG_Q];
+#pragma unroll
+      for (int u = 0; u < CG_Q; ++u)
+        if (u < n_rounds) issue(qc[u], qv[u]);
+      for (int t0 = 0; t0 < n_rounds; t0 += CG_Q) {
+#pragma unroll
+        for (int u = 0; u < CG_Q; ++u) {
+          const int t = t0 + u;
+          if (t < n_rounds) {
+            consume(qc[u], qv[u]);
+            if (t + CG_Q < n_rounds) issue(qc[u], qv[u]);
           }
         }
       }
-      // tail: up to 255 entries, 4 then 1 lane-steps at a time
-      for (; t0 + 128 <= L; t0 += 128) {
-        int cj[4];
-        float cv[4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int t = t0 + lane + 32 * u;
-          cj[u] = (int)crow[t];
-          cv[u] = vrow[t];
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-#pragma unroll
-          for (int q = 0; q < NCV / 4; ++q) {
-            const float4 p4 = *reinterpret_cast<const float4*>(Ps + (int64_t)cj[u] * NCV + 4 * q);
-            acc[4 * q + 0] = fmaf(cv[u], p4.x, acc[4 * q + 0]);
-            acc[4 * q + 1] = fmaf(cv[u], p4.y, acc[4 * q + 1]);
-            acc[4 * q + 2] = fmaf(cv[u], p4.z, acc[4 * q + 2]);
-            acc[4 * q + 3] = fmaf(cv[u], p4.w, acc[4 * q + 3]);
-          }
-        }
-      }
-      for (; t0 < L; t0 += 32) {
-        const int t = t0 + lane;
-        if (t < L) {
-          const int cj = (int)crow[t];
-          const float cv = vrow[t];
-#pragma unroll
-          for (int q = 0; q < NCV / 4; ++q) {
-            const float4 p4 = *reinterpret_cast<const float4*>(Ps + (int64_t)cj * NCV + 4 * q);
-            acc[4 * q + 0] = fmaf(cv, p4.x, acc[4 * q + 0]);
-            acc[4 * q + 1] = fmaf(cv, p4.y, acc[4 * q + 1]);
-            acc[4 * q + 2] = fmaf(cv, p4.z, acc[4 * q + 2]);
-            acc[4 * q + 3] = fmaf(cv, p4.w, acc[4 * q + 3]);
-          }
-        }
-      }
-#pragma unroll
-      for (int c = 0; c < NCV; ++c) {
-        const float s = warp_sum(acc[c]);
-        const float p = Ps[(int64_t)row * NCV + c];
-        const float ap = p - alpha * s;
-        if (lane == 0) {
-          APg[(int64_t)row * NCV + c] = ap;
-          part[c] = fmaf(p, ap, part[c]);
-        }
-      }
+      for (int c = 0; c < NCV; ++c)
+        part[c] = ((lane & 7) == 0 && (lane >> 3) == (c & 3)) ? my_part[c >> 2] : 0.f;
     }
     cg_allreduce<NCV>(cluster, &ex, s_warp, part, xcnt, tot);
     float a[NCV];
@@ -1259,7 +1350,7 @@ static int launch_cg(int CL, int G, size_t smem, cudaStream_t st, const int32_t*
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  if (CL > 8) {  // can the device co-schedule a 16-CTA cluster of this size at all?
+  {  // can the device co-schedule a cluster of this size at all?
     int n_clusters = 0;
     e = cudaOccupancyMaxActiveClusters(&n_clusters, lp_cg_kernel<NCV>, &cfg);
     if (e != cudaSuccess || n_clusters < 1) {
@@ -1449,8 +1540,8 @@ __global__ __launch_bounds__(CG_THREADS, 1) void lp_cg_group_kernel(
     float* Pg = Pv + vb * NCV;
     const int32_t* rp = rowptr + vb;
     const int32_t* rl = rowlen + vb;
-    const uint16_t* mc = mcol + vb * k * 2;
-    const float* mv = mval + vb * k * 2;
+    const uint16_t* mc = mcol + vb * lp_rowcap(k);
+    const float* mv = mval + vb * lp_rowcap(k);
     // ---- cache my rows' lists: offsets by one warp's scan, then a cooperative copy
     if (w == 0) {
       int base = 0;
@@ -1796,10 +1887,19 @@ int launch_lp_solve(const int32_t* rowptr, const int32_t* rowlen, const uint16_t
     const int v = e ? atoi(e) : 0;
     return (v == 16 || v == 8 || v == 4 || v == 2) ? v : 0;
   }();
-  // many graphs: 8-CTA clusters (about twice as many clusters are co-resident as with 16);
-  // a handful of graphs (the training step solves one): 16 CTAs per graph to cut the latency
-  const int cl_start = cl_first ? cl_first : (G <= 4 ? 16 : 8);
-  for (int CL = cl_start; CL >= 2 && rc == -1000; CL >>= 1) {
+  // One CTA per SM (the kernel keeps a queue of matrix rounds in 128 registers per thread), so a
+  // batch of graphs gets as many CTAs per graph as keep ALL graphs in flight in one wave (25 graphs
+  // on 148 SMs: clusters of 5); a handful of graphs gets 16.  A warp keeps the metadata of at most
+  // 32 * CG_MJ rows in registers, which bounds the rows of a CTA from above.
+  int dev = 0, n_sm = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+  const int rows_cta_max = CG_WARPS * CG_MAXR;
+  const int cl_need = (nn + rows_cta_max - 1) / rows_cta_max;
+  int cl_start = cl_first ? cl_first : (G <= 4 ? 16 : max(1, min(8, n_sm / G)));
+  cl_start = max(cl_start, cl_need);
+  for (int CL = cl_start; CL >= cl_need && CL >= 1 && rc == -1000;
+       CL = (CL & (CL - 1)) ? (1 << (31 - __builtin_clz(CL))) : CL >> 1) {
     if (ncv == 4)
       rc = launch_cg<4>(CL, G, smem_cg, st, rowptr, rowlen, mcol, mval, valid, nn, k, Y, nc, alpha,
                         tol, max_iter, Z, X, R, P, AP, iters_out, resid_out);

@@ -634,7 +634,8 @@ __global__ void mdns_cells_kernel(const float* __restrict__ sx, int64_t s_e, int
                                   int64_t s_c, int64_t s_n, const int32_t* __restrict__ sy,
                                   const float* __restrict__ F, int64_t ep_rows,
                                   int64_t sup_row_off, int clouds_per_ep, int N, int D,
-                                  float* __restrict__ cell_mean, int32_t* __restrict__ cell_cnt) {
+                                  float* __restrict__ cell_mean, int32_t* __restrict__ cell_cnt,
+                                  uint8_t* __restrict__ cell_mask_out) {
   extern __shared__ unsigned char s_mask[];  // [N] cell bitmask per point
   __shared__ float s_red[6][32];
   __shared__ float s_bb[6];
@@ -709,6 +710,7 @@ __global__ void mdns_cells_kernel(const float* __restrict__ sx, int64_t s_e, int
             m |= (unsigned char)(2u << (ix * 2 + iy));
     }
     s_mask[i] = m;
+    if (cell_mask_out) cell_mask_out[(int64_t)cloud * N + i] = m;
 #pragma unroll
     for (int q = 0; q < MDNS_CELLS; ++q) lc[q] += (m >> q) & 1;
   }
@@ -757,7 +759,8 @@ __global__ void mdns_cells_kernel(const float* __restrict__ sx, int64_t s_e, int
 __global__ void mdns_vote_kernel(const float* __restrict__ cell_mean,
                                  const int32_t* __restrict__ cell_cnt,
                                  const int32_t* __restrict__ fg_cnt, int k_shot, int D,
-                                 int32_t* __restrict__ keep, float* __restrict__ clean_flag) {
+                                 int32_t* __restrict__ keep, float* __restrict__ clean_flag,
+                                 float* __restrict__ degree_out, float* __restrict__ scale_flag_out) {
   extern __shared__ __align__(16) float s_v[];  // [L][D] normalised seeds
   __shared__ float s_deg[MDNS_MAX_SEEDS];
   __shared__ int s_shot[MDNS_MAX_SEEDS];
@@ -808,6 +811,9 @@ __global__ void mdns_vote_kernel(const float* __restrict__ cell_mean,
       if (lane == 0) s_deg[i] = deg;
     }
     __syncthreads();
+    if (degree_out)  // diagnostic: (way, scale, 4 * k_shot) degrees in seed order, NaN padded
+      for (int i = tid; i < 4 * k_shot; i += blockDim.x)
+        degree_out[((int64_t)ew * 2 + scale) * (4 * k_shot) + i] = i < L ? s_deg[i] : NAN;
     if (tid == 0) {
       float mean = 0.f;
       for (int i = 0; i < L; ++i) mean += s_deg[i];
@@ -825,6 +831,9 @@ __global__ void mdns_vote_kernel(const float* __restrict__ cell_mean,
     }
   }
   __syncthreads();
+  if (scale_flag_out)
+    for (int i = tid; i < 2 * k_shot; i += blockDim.x)
+      scale_flag_out[(int64_t)ew * 2 * k_shot + i] = s_flag[i / k_shot][i % k_shot];
   if (tid == 0) {
     int kept_pts = 0;
     for (int s = 0; s < k_shot; ++s) {
@@ -843,7 +852,8 @@ __global__ void mdns_vote_kernel(const float* __restrict__ cell_mean,
 int launch_mdns(const float* sx, int64_t s_e, int64_t s_cloud, int64_t s_c, int64_t s_n,
                 const int32_t* sy, const float* F, int64_t ep_rows, int64_t sup_row_off, int E,
                 int n_way, int k_shot, int N, int D, float* cell_mean, int32_t* cell_cnt,
-                int32_t* fg_cnt, int32_t* keep, float* clean_flag, cudaStream_t st) {
+                int32_t* fg_cnt, int32_t* keep, float* clean_flag, cudaStream_t st,
+                uint8_t* cell_mask_out, float* degree_out, float* scale_flag_out) {
   const int C = n_way * k_shot;
   if (D > 256 || k_shot > 32 || k_shot * 4 > MDNS_MAX_SEEDS) return R3DFS_E_UNSUPPORTED;
   fg_count_kernel<<<E * C, 256, 0, st>>>(sy, N, fg_cnt);
@@ -851,14 +861,15 @@ int launch_mdns(const float* sx, int64_t s_e, int64_t s_cloud, int64_t s_c, int6
   const int threads = MDNS_GROUPS * D <= 1024 ? MDNS_GROUPS * D : 1024;
   if (threads < MDNS_GROUPS * D) return R3DFS_E_UNSUPPORTED;
   mdns_cells_kernel<<<E * C, threads, N, st>>>(sx, s_e, s_cloud, s_c, s_n, sy, F, ep_rows,
-                                               sup_row_off, C, N, D, cell_mean, cell_cnt);
+                                               sup_row_off, C, N, D, cell_mean, cell_cnt,
+                                               cell_mask_out);
   R3DFS_CHECK_LAUNCH();
   size_t smem = sizeof(float) * (size_t)(4 * k_shot) * D;
   cudaError_t e = cudaFuncSetAttribute(mdns_vote_kernel,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
   mdns_vote_kernel<<<E * n_way, 256, smem, st>>>(cell_mean, cell_cnt, fg_cnt, k_shot, D, keep,
-                                                 clean_flag);
+                                                 clean_flag, degree_out, scale_flag_out);
   R3DFS_CHECK_LAUNCH();
   return 0;
 }

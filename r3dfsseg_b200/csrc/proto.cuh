@@ -34,4 +34,6 @@ int launch_set_compaction(const float* F, int64_t ep_rows, int64_t sup_row_off, 
 int launch_mdns(const float* sx, int64_t s_e, int64_t s_cloud, int64_t s_c, int64_t s_n,
                 const int32_t* sy, const float* F, int64_t ep_rows, int64_t sup_row_off, int E,
                 int n_way, int k_shot, int N, int D, float* cell_mean, int32_t* cell_cnt,
-                int32_t* fg_cnt, int32_t* keep, float* clean_flag, cudaStream_t st);
+                int32_t* fg_cnt, int32_t* keep, float* clean_flag, cudaStream_t st,
+                uint8_t* cell_mask_out = nullptr, float* degree_out = nullptr,
+                float* scale_flag_out = nullptr);

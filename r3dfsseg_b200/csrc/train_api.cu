@@ -581,7 +581,10 @@ int r3dfs_adam_step(float* params, const float* grads, float* exp_avg, float* ex
                     int64_t n_group0, float lr0, float lr1, float beta1, float beta2, float eps,
                     int64_t step, float grad_scale, r3dfs_stream_t stream) {
   if (!params || !grads || !exp_avg || !exp_avg_sq || n <= 0 || step < 1) return R3DFS_E_BADARG;
-  const float bc1 = 1.f - powf(beta1, (float)step), bc2 = 1.f - powf(beta2, (float)step);
+  // bias corrections in double, as torch.optim.Adam computes them (1 - 0.999^t loses ~6e-5
+  // relative in FP32 powf at small t)
+  const float bc1 = (float)(1.0 - pow((double)beta1, (double)step)),
+              bc2 = (float)(1.0 - pow((double)beta2, (double)step));
   return launch_adam(params, grads, exp_avg, exp_avg_sq, n, n_group0, lr0, lr1, beta1, beta2, eps,
                      bc1, bc2, grad_scale, (cudaStream_t)stream);
 }

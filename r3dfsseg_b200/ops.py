@@ -258,6 +258,40 @@ def fps(feat: torch.Tensor, set_off: torch.Tensor, set_n: torch.Tensor, m_max: i
     return out
 
 
+def mdns(support_x: torch.Tensor, support_y: torch.Tensor, support_feat: torch.Tensor,
+         want_internals: bool = False):
+    """Multi-scale degree-based noise suppression (models/mpti.py:87-223, 316-371).
+    support_x (E, n_way, k_shot, 9, N) any strides, support_y (E, n_way, k_shot, N),
+    support_feat (E, n_way*k_shot*N, 192) -> dict(keep (E, n_way, k_shot) int32, clean_flag float,
+    cell_mean (E, n_way, k_shot, 5, 192), cell_count (..., 5) [, cell_mask (E, n_way, k_shot, N) u8,
+    degree (E, n_way, 2, 4*k_shot), scale_flag (E, n_way, 2, k_shot)])."""
+    dev = _need_cuda(support_x, support_y, support_feat)
+    E, n_way, k_shot, Cin, N = support_x.shape
+    sx = _f32(support_x)
+    if sx.stride(1) != k_shot * sx.stride(2):
+        sx = sx.contiguous()
+    sy = support_y.to(torch.int32).contiguous()
+    sf = _f32(support_feat).contiguous()
+    Cn = n_way * k_shot
+    out = dict(keep=torch.empty((E, n_way, k_shot), dtype=torch.int32, device=dev),
+               clean_flag=torch.empty((E, n_way, k_shot), dtype=torch.float32, device=dev),
+               cell_mean=torch.empty((E, n_way, k_shot, 5, 192), dtype=torch.float32, device=dev),
+               cell_count=torch.empty((E, n_way, k_shot, 5), dtype=torch.int32, device=dev))
+    if want_internals:
+        out.update(cell_mask=torch.empty((E, n_way, k_shot, N), dtype=torch.uint8, device=dev),
+                   degree=torch.empty((E, n_way, 2, 4 * k_shot), dtype=torch.float32, device=dev),
+                   scale_flag=torch.empty((E, n_way, 2, k_shot), dtype=torch.float32, device=dev))
+    L = _lib.lib()
+    ws = _ws(L.r3dfs_mdns_workspace(E, n_way, k_shot), dev)
+    with torch.cuda.device(dev):
+        check(L.r3dfs_mdns(_p(sx), sx.stride(0), sx.stride(2), sx.stride(3), sx.stride(4), _p(sy),
+                           _p(sf), E, n_way, k_shot, N, _p(out["cell_mean"]), _p(out["cell_count"]),
+                           _p(out.get("cell_mask")), _p(out.get("degree")),
+                           _p(out.get("scale_flag")), _p(out["keep"]), _p(out["clean_flag"]),
+                           _p(ws), ws.numel(), _stream()), "r3dfs_mdns")
+    return out
+
+
 def multi_prototypes(feat: torch.Tensor, set_off: torch.Tensor, set_n: torch.Tensor, k: int):
     """getMutiplePrototypes (models/mpti.py:597-634) for several sets at once.
     Returns (prototypes (n_sets, k+1, D), counts (n_sets), assignments (rows), seeds (n_sets, k+1))."""

@@ -149,6 +149,10 @@ class _TrainEpisode(torch.autograd.Function):
                 float(p_drop), ops._p(keep_s), ops._p(keep_q), ops._p(logits), ops._p(losses),
                 ops._p(iters), ops._p(ws), ws.numel(), ops._stream()), "r3dfs_mpti_train_forward")
         ctx.model, ctx.fs, ctx.cfg = model, fs, cfg
+        # every saved activation lives in the ONE shared workspace: a later training forward
+        # overwrites it, so this graph's backward is only valid while the stamp still matches
+        model._train_gen = int(getattr(model, "_train_gen", 0)) + 1
+        ctx.gen = model._train_gen
         ctx.saved = (sy, flag, qy, keep_s, keep_q, ws)
         ctx.p_drop = float(p_drop)
         ctx.mark_non_differentiable(logits)
@@ -159,11 +163,20 @@ class _TrainEpisode(torch.autograd.Function):
     def backward(ctx, _g_logits, g_lp, g_ct):
         model, fs, cfg = ctx.model, ctx.fs, ctx.cfg
         sy, flag, qy, keep_s, keep_q, ws = ctx.saved
-        if ws is not model._train_ws:
-            raise RuntimeError("the training workspace was replaced between forward and backward")
-        # the two loss weights are host scalars of the C call (mpti_learner.py:66: 1 and 0.1)
-        w_lp = 0.0 if g_lp is None else float(g_lp)
-        w_ct = 0.0 if g_ct is None else float(g_ct)
+        if ws is not model._train_ws or ctx.gen != model._train_gen:
+            raise RuntimeError(
+                "backward() of a training episode after another training forward of the same model: "
+                "the saved activations live in one shared workspace and have been overwritten. "
+                "Call backward() (or accumulate .grad) before the next forward(train=True).")
+        # the two loss weights are host scalars of the C call (mpti_learner.py:66: 1 and 0.1).
+        # Reading them waits for the forward on this stream; the learner's own train() step passes
+        # them as python floats through `backward_weights` and skips the read-back.
+        bw = getattr(model, "_backward_weights", None)
+        if bw is not None:
+            w_lp, w_ct = bw
+        else:
+            w_lp = 0.0 if g_lp is None else float(g_lp)
+            w_ct = 0.0 if g_ct is None else float(g_ct)
         grads = torch.empty_like(fs.flat)
         with torch.cuda.device(grads.device):
             check(_lib.lib().r3dfs_mpti_train_backward(
@@ -279,6 +292,45 @@ def all_reduce_gradients(flat_grad: torch.Tensor) -> float:
     return 1.0
 
 
+def _world_size() -> int:
+    import torch.distributed as dist
+    return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+
+
+def broadcast_tensors(tensors, src: int = 0) -> None:
+    import torch.distributed as dist
+    for t in tensors:
+        dist.broadcast(t, src)
+
+
+def average_tensor(t: torch.Tensor) -> None:
+    """In-place mean over the ranks (NCCL: one AVG all-reduce; gloo has no AVG: sum, then divide)."""
+    import torch.distributed as dist
+    if t.is_cuda:
+        dist.all_reduce(t, op=dist.ReduceOp.AVG)
+    else:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        t /= dist.get_world_size()
+
+
+def broadcast_state(model: nn.Module, src: int = 0) -> None:
+    """Data-parallel replicas must start from the same weights and BatchNorm statistics: broadcast
+    the flat parameter buffer and the flat running-statistics buffer of rank `src` (no-op when not
+    distributed).  Called when the optimiser is built."""
+    if _world_size() > 1:
+        fs = flat_state(model)
+        broadcast_tensors((fs.flat, fs.running), src)
+        model._packed = None
+
+
+def average_running_stats(model: nn.Module) -> None:
+    """Every rank updates its BatchNorm running statistics from its own episode; the replicas keep
+    ONE set by averaging them (one NCCL AVG all-reduce of the 2 x 1 856-float buffer), so that eval
+    and checkpoints do not depend on the rank.  The reference has no notion of replicas."""
+    if _world_size() > 1:
+        average_tensor(flat_state(model).running)
+
+
 class FusedAdam(torch.optim.Optimizer):
     """torch.optim.Adam as configured at reference models/mpti_learner.py:26-32 (encoder lr 1e-4,
     everything else args.lr; betas (0.9, 0.999), eps 1e-8, no weight decay) as one kernel over the
@@ -295,8 +347,12 @@ class FusedAdam(torch.optim.Optimizer):
         self.exp_avg = torch.zeros_like(fs.flat)
         self.exp_avg_sq = torch.zeros_like(fs.flat)
         self.step_count = 0
+        self.sync_bn_every = 1
+        broadcast_state(model)
 
-    def _flat_grad(self, fs: FlatState) -> torch.Tensor:
+    def _flat_grad(self, fs: FlatState) -> Optional[torch.Tensor]:
+        if all(p.grad is None for p in fs.params):
+            return None  # torch.optim.Adam skips parameters without a gradient
         g = getattr(self.model, "_last_grad_flat", None)
         if g is not None and all(
                 p.grad is not None and p.grad.data_ptr() == g.data_ptr() + 4 * o
@@ -330,7 +386,14 @@ class FusedAdam(torch.optim.Optimizer):
         if self.exp_avg.data_ptr() == 0 or self.exp_avg.numel() != fs.flat.numel():
             raise RuntimeError("optimizer state does not match the model")
         g = self._flat_grad(fs)
+        if g is None:
+            if _world_size() > 1:
+                raise RuntimeError("FusedAdam.step() without gradients on this rank would leave the "
+                                   "other ranks waiting in the gradient all-reduce")
+            return None
         scale = all_reduce_gradients(g)
+        if self.sync_bn_every and (self.step_count + 1) % self.sync_bn_every == 0:
+            average_running_stats(self.model)
         self.step_count += 1
         self.model._packed = None  # folded eval weights are stale after the update
         b1, b2 = self.defaults["betas"]
@@ -380,7 +443,11 @@ class MPTILearner_V3:
         query_logits, lp_loss, contrastive_loss = out[0], out[1], out[2]
         loss = lp_loss + 0.1 * contrastive_loss
         self.optimizer.zero_grad()
-        loss.backward()
+        self.model._backward_weights = (1.0, 0.1)  # d loss / d (lp_loss, contrastive_loss), known here
+        try:
+            loss.backward()
+        finally:
+            self.model._backward_weights = None
         self.optimizer.step()
         self.lr_scheduler.step()
         query_pred = query_logits.argmax(dim=1)

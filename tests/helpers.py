@@ -22,3 +22,26 @@ def knn_sets_match(idx_a, idx_b, scores, largest, rtol=1e-5):
                 bad += 1
                 break
     return bad == 0, bad
+
+
+def mdns_case(seed, n_way=2, k_shot=5, N=512, grid_xyz=True, noisy=(1,)):
+    """A small support set for direct tests of the noise-suppression internals: per-class feature
+    centres + noise (shots listed in `noisy` show another class), xyz on a coarse binary grid so that
+    many foreground points lie EXACTLY on the faces between the cells of scale (2,2,1) and on the
+    bounding box — the inclusive-bounds corner of the reference (models/mpti.py:355-367).
+    Returns support_x (n_way, k_shot, 9, N), support_y (n_way, k_shot, N) int32,
+    support_feat (n_way, k_shot, 192, N)."""
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    centres = torch.randn((n_way + 2, 192), generator=g)
+    sx = torch.rand((n_way, k_shot, 9, N), generator=g)
+    if grid_xyz:
+        sx[:, :, :3] = torch.randint(0, 9, (n_way, k_shot, 3, N), generator=g).float() * 0.125
+    sy = (torch.rand((n_way, k_shot, N), generator=g) < 0.3).to(torch.int32)
+    sy[:, :, 0] = 1
+    sf = torch.empty((n_way, k_shot, 192, N))
+    for w in range(n_way):
+        for k in range(k_shot):
+            c = centres[n_way + (k % 2)] if k in noisy else centres[w]
+            sf[w, k] = (c[:, None] + 0.6 * torch.randn((192, N), generator=g))
+    return sx, sy, sf

@@ -234,3 +234,48 @@ def test_learner_resumes_from_reference_format_checkpoint(fixture_sd, tmp_path):
     # far below one update
     d = (T.flat_state(a.model).flat - T.flat_state(b.model).flat).abs()
     assert float((d < 1e-6).float().mean()) > 0.995, (float(d.max()), float((d < 1e-6).float().mean()))
+
+
+def test_backward_after_a_second_forward_fails_loudly(fixture_sd):
+    """All saved activations of a training forward live in ONE shared workspace; forward(A),
+    forward(B), backward(A) would silently use B's activations — it must raise instead, while the
+    usual forward -> backward per episode (and backward of the LATEST forward) keeps working."""
+    from r3dfsseg_b200 import train as T
+    m = _model(fixture_sd)
+    eps = [make_episode(s, 2, 5, noise_ratio=0.2) for s in (31, 32)]
+    outs = []
+    for ep in eps:
+        _, lp, ct = T.train_episode(m, ep.support_x.to(DEV), ep.support_y.to(DEV), ep.query_x.to(DEV),
+                                    ep.query_y.to(DEV), ep.support_flag.to(DEV), dropout_p=0.0)
+        outs.append(lp + 0.1 * ct)
+    with pytest.raises(RuntimeError, match="overwritten"):
+        outs[0].backward()
+    outs[1].backward()                      # the latest forward is intact
+    assert all(p.grad is not None for p in m.parameters())
+
+
+def test_fused_adam_without_gradients_is_a_no_op(fixture_sd):
+    """torch.optim.Adam skips parameters whose .grad is None; the fused step must not decay moments
+    or move parameters with an all-zero stand-in gradient."""
+    from r3dfsseg_b200 import train as T
+    m = _model(fixture_sd)
+    opt = T.FusedAdam(m, lr=1e-3)
+    before = T.flat_state(m).flat.clone()
+    opt.zero_grad(set_to_none=True)
+    opt.step()
+    assert opt.step_count == 0 and torch.equal(T.flat_state(m).flat, before)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (gpurun --gpus 2)")
+def test_replicas_stay_identical_nccl_world2(tmp_path):
+    """Two NCCL ranks built from DIFFERENT initial weights: after FusedAdam's broadcast and three
+    training steps on different episodes, parameters and BatchNorm running statistics are equal
+    bit for bit on both ranks (gradient all-reduce + running-statistics average)."""
+    import subprocess
+    import sys
+    script = os.path.join(os.path.dirname(os.path.dirname(__file__)), "scripts", "check_replicas.py")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
+                        "--nproc-per-node", "2", "--master-addr", "127.0.0.1", "--master-port",
+                        str(29400 + os.getpid() % 500), script], capture_output=True, text=True,
+                       timeout=600)
+    assert r.returncode == 0 and "REPLICAS_EQUAL" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]

@@ -197,6 +197,44 @@ def test_gradient_bucket_allreduce_gloo_world2():
     assert sorted(results) == [(0, True), (1, True)]
 
 
+def _gloo_replica_worker(rank, world, port, q):
+    import torch.distributed as dist
+    from r3dfsseg_b200.train import average_tensor, broadcast_tensors
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    g = torch.Generator().manual_seed(100 + rank)           # every rank starts from OTHER values
+    flat, running = torch.randn(376896, generator=g), torch.rand(2 * 1344, generator=g)
+    broadcast_tensors((flat, running), 0)
+    g0 = torch.Generator().manual_seed(100)
+    same_start = torch.equal(flat, torch.randn(376896, generator=g0)) and \
+        torch.equal(running, torch.rand(2 * 1344, generator=g0))
+    # a step: every rank moves its running statistics by its own episode, then they are averaged
+    delta = [torch.full((2 * 1344,), float(r + 1)) for r in range(world)]
+    start = running.clone()
+    running += delta[rank]
+    average_tensor(running)
+    ok_avg = torch.allclose(running, start + torch.stack(delta).mean(0))
+    q.put((rank, bool(same_start and ok_avg)))
+    dist.destroy_process_group()
+
+
+def test_replica_state_broadcast_and_bn_average_gloo_world2():
+    """Data-parallel replicas: parameters + BatchNorm statistics are broadcast from rank 0 when the
+    optimiser is built, and the running statistics are averaged over the ranks after each step."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 33500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_gloo_replica_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(results) == [(0, True), (1, True)]
+
+
 def test_episode_file_round_trip(tmp_path):
     """The reference's episode schema (dataloaders/loader.py:1687-1721) survives write -> read, and
     the collate leaves the clouds point-major behind (.., 9, N) views (loader.py:1676-1684)."""
