@@ -12,7 +12,11 @@ One JSON line on stdout (rank 0):
   value      episodes/s with the inputs already resident in HBM (device-timed, max over ranks)
   e2e        the same through the public module API from pinned HOST buffers, H2D + D2H in the
              timed region
-  roofline   the dominant kernel stage: algorithmic FLOPs (or bytes) per launch / CUDA-event time
+  roofline   the dominant kernel: algorithmic DRAM bytes (or FLOPs) per launch / CUDA-event time
+  e2e_driver the same metric through the drop-in driver (evaluate.test_few_shot over episode FILES:
+             disk -> reader threads -> pinned staging -> H2D -> forward -> counters -> mIoU)
+  extra      BASELINE.json configs[3] (ScanNet-shape 3-way, 40 % OOD shots) and configs[4] (the
+             meta-training step, gradient all-reduce included at N > 1) measured in the same run
   cpu_baseline  the CPU oracle (restatement of the reference's path) on this box's host cores
 `--impl reference` times that CPU path alone (the reference is Python: oracle/mpti_oracle.py is
 its restatement; the reference tree itself cannot travel to the GPU box).
@@ -160,7 +164,10 @@ def cpu_episodes_per_s(n_episodes: int, seed0: int, threads: int):
     t0 = time.perf_counter()
     with torch.no_grad():
         for ep in eps:
-            O.forward_episode(sd, ep.support_x, ep.support_y, ep.query_x, ep.query_y, eval_mdns=True)
+            # timing arm: FP32 Gram + topk stands in for faiss (the parity definition — FP64 distances
+            # and a full stable argsort — would be an unfairly slow baseline)
+            O.forward_episode(sd, ep.support_x, ep.support_y, ep.query_x, ep.query_y, eval_mdns=True,
+                              timing_knn=True)
     dt = time.perf_counter() - t0
     return n_episodes / dt, dt
 
@@ -181,7 +188,8 @@ def run_reference_arm(args):
         n_tot += per_step
     v = n_tot / t_tot
     sample = (f"{per_step} episode(s) per step x {args.steps} steps of the same {N_WAY}-way {K_SHOT}-shot "
-              f"workload (MDNS on), torch CPU fp32, {threads} threads")
+              f"workload (MDNS on), torch CPU fp32, {threads} threads of ONE host (under torchrun "
+              f"rank 0 alone runs this arm: at N > 1 it is still one host, not N)")
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_tot / args.steps,
@@ -222,19 +230,145 @@ def stage_work(E: int):
     w["base"] = dict(flops=2.0 * M * (256 * 128 + 128 * 64), bytes=4.0 * M * (256 + 64), bound="tensor")
     w["qkv"] = dict(flops=2.0 * M * 256 * 192, bytes=4.0 * M * (256 + 192), bound="tensor")
     w["att"] = dict(flops=4.0 * B * N_PTS * N_PTS * 64, bytes=4.0 * M * (192 + 64), bound="tensor")
-    # FPS: every pick re-sweeps the set (4*n*D bytes per pick); sets of one episode = all support pts
-    w["fps"] = dict(flops=3.0 * 100 * E * n_sup * 192, bytes=4.0 * 100 * E * n_sup * 192, bound="hbm")
+    # FPS: DRAM-level = two passes over the FP32 rows (distance to the first seed + min/max, then
+    # quantisation) + ~3.5 % of the rows re-read per pick; on-chip = 100 sweeps of the byte rows
+    w["fps"] = dict(flops=3.0 * 100 * E * n_sup * 192,
+                    bytes=(2 + 0.035 * 100) * 4.0 * E * n_sup * 192,
+                    onchip_bytes=100.0 * E * n_sup * 192, bound="hbm")
     w["proto"] = dict(flops=3.0 * 100 * E * n_sup * 192, bytes=2 * 4.0 * E * n_sup * 192, bound="hbm")
     w["mdns"] = dict(flops=2.0 * E * n_sup * 192, bytes=4.0 * E * n_sup * 192, bound="hbm")
     w["sets"] = dict(flops=0.0, bytes=2 * 4.0 * E * n_sup * 192, bound="hbm")
     w["dist"] = dict(flops=2.0 * E * nn * nn * 192, bytes=4.0 * E * nn * (192 + nn), bound="tensor")
     w["select"] = dict(flops=0.0, bytes=4.0 * E * nn * nn + 4.0 * E * nn * 200, bound="hbm")
-    w["sim"] = dict(flops=3.0 * E * nn * 200 * 192, bytes=4.0 * E * nn * 200 * 192, bound="hbm")
+    # edge similarities: compulsory = features once + lists in / similarities out; the gathered
+    # neighbour rows (4*nn*200*192 B) come from L2
+    w["sim"] = dict(flops=3.0 * E * nn * 200 * 192, bytes=4.0 * E * nn * (192 + 2 * 200),
+                    l2_bytes=4.0 * E * nn * 200 * 192, bound="hbm")
     w["sym"] = dict(flops=0.0, bytes=6 * 8.0 * E * nn * 200, bound="hbm")
     w["cg"] = dict(flops=0.0, bytes=None, bound="hbm")  # filled from the measured iteration count
     w["input"] = dict(flops=0.0, bytes=2 * 4.0 * M * 9, bound="hbm")
     w["head"] = dict(flops=0.0, bytes=2 * 4.0 * E * N_QUERY * N_PTS * (N_WAY + 1), bound="hbm")
     return w
+
+
+# ------------------------------------------------------------------------------------------------
+# extra legs: the drop-in driver over episode files, BASELINE.json configs[3] and configs[4]
+# ------------------------------------------------------------------------------------------------
+def driver_leg(model, dev, dist, rank, world, host_batch, chunk, steps, test_classes):
+    """MPTI episodes/s through evaluate.EpisodeEvaluator / test_few_shot's loop over an
+    episode_io.EpisodeFolder: files on disk -> reader threads -> persistent pinned staging buffers ->
+    H2D -> forward_episodes on several streams -> confusion counters (+ the NCCL sum at N > 1) ->
+    mIoU.  Wall clock around the call, device synchronised on both sides, max over ranks."""
+    import shutil
+    import tempfile
+    from r3dfsseg_b200 import episode_io as IO
+    from r3dfsseg_b200.evaluate import EpisodeEvaluator
+    h_sx, h_sy, h_qx, h_qy, classes = host_batch
+    E = h_sx.shape[0]
+    d = tempfile.mkdtemp(prefix="r3dfs_bench_eps_r%d_" % rank)
+    try:
+        for i in range(E):
+            zs = np.zeros(tuple(h_sy[i].shape), np.int32)
+            zq = np.zeros(tuple(h_qy[i].shape), np.int32)
+            IO.write_episode(os.path.join(d, "%05d.h5" % i),
+                             (h_sx[i].numpy(), h_sy[i].numpy(), h_qx[i].numpy(), h_qy[i].numpy(),
+                              classes[i], zs, zq, h_sy[i].numpy()))
+        folder = IO.EpisodeFolder(d)
+        ev = EpisodeEvaluator(model, test_classes, batch=chunk, eval_mdns=True, n_inflight=4)
+        res = ev.run(folder)  # warm-up: staging buffers, workspaces, page cache
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            res = ev.run(folder)  # every rank streams its own folder; counters are summed over ranks
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if dist is not None:
+            t = torch.tensor([dt], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t[0])
+        nbytes = sum(os.path.getsize(f) for f in folder.file_names)
+        return {"value": world * E * steps / dt, "unit": UNIT,
+                "path": "episode files (reference schema, %s) -> evaluate.EpisodeEvaluator.run: "
+                        "%d reader threads, 4 batches of %d episodes in flight" % (
+                            os.path.splitext(folder.file_names[0])[1], ev.n_readers, chunk),
+                "file_bytes_per_step": int(nbytes), "mean_iou": res["mean_iou"],
+                "timing": "wall clock, device synchronised on both sides, max over ranks"}
+    finally:
+        shutil.rmtree(d, ignore_errors=True)
+
+
+def resident_leg(dev, dist, rank, world, workload, E_step, chunk, n_streams, steps, warmup):
+    """Device-resident episodes/s of another workload (same timing rules as the main line)."""
+    label = set_workload(workload)
+    from r3dfsseg_b200 import _lib
+    from r3dfsseg_b200.episodes import default_args
+    from r3dfsseg_b200.models import MPTI_SelfAtten
+    sd = torch.load(os.path.join(ROOT, "tests", "golden", "weights_fixture.pt"))
+    model = MPTI_SelfAtten(default_args(N_WAY, K_SHOT))
+    model.load_state_dict(sd)
+    model = model.to(dev).eval()
+    h = build_host_batch(E_step, seed0=50_000 * (rank + 1))
+    d_sx, d_sy, d_qx, d_qy = (t.to(dev) for t in h[:4])
+    cfg = model._cfg(N_QUERY, mdns=True)
+    need = _lib.lib().r3dfs_mpti_workspace(cfg, chunk)
+    wss = [torch.empty(need, dtype=torch.uint8, device=dev) for _ in range(n_streams)]
+    streams = [torch.cuda.Stream(device=dev) for _ in range(n_streams)]
+    chunks = [(s, min(s + chunk, E_step)) for s in range(0, E_step, chunk)]
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
+    acc = []
+
+    def step():
+        cur = torch.cuda.current_stream()
+        for st in streams:
+            st.wait_stream(cur)
+        for ci, (a, b) in enumerate(chunks):
+            with torch.cuda.stream(streams[ci % n_streams]):
+                out = model.forward_episodes(d_sx[a:b].transpose(3, 4), d_sy[a:b],
+                                             d_qx[a:b].transpose(2, 3), d_qy[a:b], eval=True,
+                                             workspace=wss[ci % n_streams])
+                acc.append(out["pred"])
+        for st in streams:
+            cur.wait_stream(st)
+
+    for _ in range(warmup):
+        step()
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+          for _ in range(steps)]
+    for s_ in range(steps):
+        flush.zero_()
+        ev[s_][0].record()
+        step()
+        ev[s_][1].record()
+    torch.cuda.synchronize()
+    ms = float(sum(a.elapsed_time(b) for a, b in ev))
+    if dist is not None:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t[0])
+    pred = torch.cat([p.reshape(-1) for p in acc[-len(chunks):]]).cpu()
+    acc_pts = float((pred == h[3].reshape(-1).to(torch.int32)).float().mean())
+    return {"metric": METRIC, "value": world * E_step * steps / (ms * 1e-3), "unit": UNIT,
+            "ms_per_step": ms / steps, "workload": label, "episodes_per_step_per_gpu": E_step,
+            "episodes_per_call": chunk, "streams": n_streams, "point_accuracy_synthetic": acc_pts}
+
+
+def train_leg(dev, dist, rank, world, steps, warmup):
+    import importlib.util
+    spec = importlib.util.spec_from_file_location(
+        "bench_train", os.path.join(ROOT, "scripts", "bench_train.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    line = mod.measure(dev, dist, rank, world, steps, warmup, n_episodes=8, cpu_steps=0)
+    keep = ("metric", "value", "unit", "ms_per_step", "phases_ms", "allreduce_us_1p5MB",
+            "gpu_launches", "final_loss")
+    out = {k: line[k] for k in keep}
+    out["workload"] = line["config"]["workload"]
+    return out
 
 
 # ------------------------------------------------------------------------------------------------
@@ -248,8 +382,10 @@ def main():
     ap.add_argument("--chunk", type=int, default=25, help="episodes per C-ABI call")
     ap.add_argument("--streams", type=int, default=4,
                     help="CUDA streams the chunks of a step are spread over (independent episodes)")
-    ap.add_argument("--cpu-episodes", type=int, default=3, help="cpu_baseline sample size")
-    ap.add_argument("--ref-episodes-per-step", type=int, default=1)
+    ap.add_argument("--cpu-episodes", type=int, default=5, help="cpu_baseline sample size")
+    ap.add_argument("--ref-episodes-per-step", type=int, default=2)
+    ap.add_argument("--no-extra", action="store_true",
+                    help="skip the configs[3] / configs[4] / driver legs (profiling runs)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--workload", default="s3dis_2way_5shot", choices=sorted(WORKLOADS))
     args = ap.parse_args()
@@ -450,8 +586,15 @@ def main():
     work = stage_work(chunk)
     nn = node_slots()
     # CG: per iteration 6 B (u16 column + fp32 value) per stored non-zero of the merged symmetric
-    # rows (<= 2*nn*200, mutual pairs stored once per row: ~0.66 of that) + the padded vectors
+    # rows (<= 2*nn*200, mutual pairs stored once per row: ~0.66 of that) + the padded vectors.
+    # The 25 matrices of a call (175 MB) do not stay in L2, so this is DRAM traffic (ncu: 9.8 GB).
     work["cg"]["bytes"] = chunk * cg_iters * (6.0 * 0.66 * 2 * nn * 200 + 7 * 4.0 * nn * 4)
+    work["cg"]["compulsory_bytes"] = chunk * (6.0 * 0.66 * 2 * nn * 200 + 7 * 4.0 * nn * 4)
+    # 3xTF32 ceiling: measured 2047 TF32 MAC/clk/SM (scripts/microbench/mma_rate.cu) x SMs x the SM
+    # clock seen during this run / 3 products per reference-math product
+    sm_clock_hz = 1e6 * (clocks.get("sm_mhz") or 1965.0)
+    n_sm = torch.cuda.get_device_properties(dev).multi_processor_count
+    tf32x3_tflops = 2.0 * 2047 * n_sm * sm_clock_hz / 3.0 / 1e12
     stages = {}
     for name, ms in stage_ms.items():
         wk = work.get(name)
@@ -460,13 +603,14 @@ def main():
         ent = {"ms_per_call": round(ms, 4), "bound": wk["bound"]}
         if wk["bound"] == "tensor":
             ent["tflops"] = round(wk["flops"] / (ms * 1e-3) / 1e12, 3)
-            ent["frac"] = round(ent["tflops"] / peaks["bf16_tflops_sustained"], 5)
+            ent["frac"] = round(ent["tflops"] / tf32x3_tflops, 5)
+            ent["frac_of_bf16_peak"] = round(ent["tflops"] / peaks["bf16_tflops_sustained"], 5)
         else:
-            ent["gbs"] = round(wk["bytes"] / (ms * 1e-3) / 1e9, 2)
+            ent["gbs"] = round(wk["bytes"] / (ms * 1e-3) / 1e9, 2)   # DRAM-level algorithmic bytes
             ent["frac"] = round(ent["gbs"] / peaks["hbm_gbs"], 5)
-            if name in ("sim", "cg", "fps"):
-                ent["note"] = "algorithmic bytes are L2-level (re-swept / gathered data that partly " \
-                              "or wholly stays in L2); frac is relative to the HBM copy peak"
+            for key, label in (("l2_bytes", "l2_gbs"), ("onchip_bytes", "onchip_gbs")):
+                if key in wk:  # re-swept data that lives in L2 / shared memory: NOT a roofline fraction
+                    ent[label] = round(wk[key] / (ms * 1e-3) / 1e9, 2)
         stages[name] = ent
     # dominant KERNEL = the kernel with the largest summed device time per call (several stages
     # are launches of the same kernel)
@@ -475,7 +619,7 @@ def main():
                  "edge0": "edge_tc_kernel", "edge1": "edge_tc_kernel", "edge2": "edge_tc_kernel",
                  "pq0": "linear_tc_kernel", "pq1": "linear_tc_kernel", "pq2": "linear_tc_kernel",
                  "mlp": "linear_tc_kernel", "base": "linear_tc_kernel", "qkv": "linear_tc_kernel",
-                 "att": "attention_tc_kernel", "fps": "fps_kernel", "cg": "lp_cg_kernel",
+                 "att": "attention_tc_kernel", "fps": "fps_q8_kernel", "cg": "lp_cg_kernel",
                  "dist": "linear_tc_kernel<DIST>", "select": "knn_select_reg_kernel",
                  "proto": "assign_kernel+proto_mean_kernel",
                  "sym": "in_bits/in_rank/in_fill_rank/merge_rows kernels",
@@ -498,12 +642,12 @@ def main():
     step_ms = sum(stage_ms.values())
     if gt["bound"] == "tensor":
         ach = gt["flops"] / (gt["ms"] * 1e-3) / 1e12
-        roof = {"bound": "tensor", "achieved": round(ach, 3), "peak": peaks["bf16_tflops_sustained"],
-                "unit": "TFLOP/s", "frac": round(ach / peaks["bf16_tflops_sustained"], 5),
+        roof = {"bound": "tensor", "achieved": round(ach, 3), "peak": round(tf32x3_tflops, 1),
+                "unit": "TFLOP/s", "frac": round(ach / tf32x3_tflops, 5),
+                "frac_of_bf16_peak": round(ach / peaks["bf16_tflops_sustained"], 5),
                 "traffic": None,
-                "note": "reference-math FLOPs (3xTF32 issues 3x that on the tensor pipe) vs the "
-                        "measured sustained BF16 peak; the kernel's CUDA-core side (top-k merge / "
-                        "operand split) is what limits it today"}
+                "note": "reference-math FLOPs vs the 3xTF32 ceiling (measured TF32 issue rate x SMs "
+                        "x clock / 3)"}
     else:
         ach = gt["bytes"] / (gt["ms"] * 1e-3) / 1e9
         roof = {"bound": "hbm", "achieved": round(ach, 2), "peak": peaks["hbm_gbs"], "unit": "GB/s",
@@ -529,6 +673,22 @@ def main():
     h2d = int(sum(t.numel() * t.element_size() for t in (h_sx, h_sy, h_qx, h_qy)))
     d2h = int(h_pred.numel() * 4 + h_loss.numel() * 4)
 
+    # ---- the other legs (all ranks take part) -----------------------------------------------------
+    e2e_driver, extra = None, {}
+    if not args.no_extra:
+        del wss, ws, flush, d_sx, d_sy, d_qx, d_qy
+        torch.cuda.empty_cache()
+        e2e_driver = driver_leg(model, dev, dist, rank, world, (h_sx, h_sy, h_qx, h_qy, classes),
+                                chunk, args.steps, test_classes)
+        torch.cuda.empty_cache()
+        main_workload = args.workload
+        other = "scannet_3way_5shot_ood" if main_workload == "s3dis_2way_5shot" else "s3dis_2way_5shot"
+        extra[other] = resident_leg(dev, dist, rank, world, other, E_step, chunk, n_streams,
+                                    args.steps, args.warmup)
+        set_workload(main_workload)
+        torch.cuda.empty_cache()
+        extra["train_step"] = train_leg(dev, dist, rank, world, max(10, 2 * args.steps), args.warmup)
+
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
@@ -552,6 +712,8 @@ def main():
                        "streams": n_streams},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h},
+            "e2e_driver": e2e_driver,
+            "extra": extra,
             "gpu_launches": int(launches),
             "roofline": roof,
             "cpu_baseline": cpu_base,

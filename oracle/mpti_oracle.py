@@ -248,6 +248,16 @@ def knn_graph_exact(X: torch.Tensor, k: int):
     return order[:, 1:], d2
 
 
+def knn_graph_fp32_topk(X: torch.Tensor, k: int) -> torch.Tensor:
+    """Speed stand-in for the faiss search in the TIMING arm of bench.py only (cpu_baseline /
+    --impl reference): FP32 Gram form + topk, what faiss.IndexFlatL2 does with BLAS, instead of the
+    parity definition above (FP64 distances + a full stable argsort of n^2 keys)."""
+    sq = (X * X).sum(1)
+    d2 = sq[:, None] + sq[None, :] - 2.0 * (X @ X.t())
+    d2.fill_diagonal_(-1.0)
+    return d2.topk(k + 1, dim=1, largest=False)[1][:, 1:]
+
+
 def affinity_dense(node_feat: torch.Tensor, k: int, sigma: float, I: Optional[torch.Tensor] = None):
     """models/mpti.py:717-756 -> dense A (n, n)"""
     n, D = node_feat.shape
@@ -282,9 +292,11 @@ def label_propagate_dense(A: torch.Tensor, Y: torch.Tensor, alpha: float = 0.99,
 # ------------------------------------------------------------------------------------------------
 def forward_episode(sd: Dict[str, torch.Tensor], support_x, support_y, query_x, query_y,
                     n_subprototypes=100, k_connect=200, sigma=1.0, dgcnn_k=20, eval_mdns=True,
-                    keep: bool = False, support_feat=None, query_feat=None) -> Dict[str, object]:
+                    keep: bool = False, support_feat=None, query_feat=None,
+                    timing_knn: bool = False) -> Dict[str, object]:
     """`support_feat` (n_way*k_shot, D, N) / `query_feat` (n_query, D, N), when given, replace the
-    getFeatures calls (used to check the graph half on features produced elsewhere)."""
+    getFeatures calls (used to check the graph half on features produced elsewhere).
+    timing_knn: FP32 topk stand-in for faiss (bench.py's CPU timing arm; never in parity tests)."""
     n_way, k_shot = support_y.shape[:2]
     N = support_y.shape[-1]
     n_cls = n_way + 1
@@ -324,7 +336,8 @@ def forward_episode(sd: Dict[str, torch.Tensor], support_x, support_y, query_x, 
     Y = prototypes.new_zeros(n, n_cls)
     Y[:P] = proto_labels
     node_feat = torch.cat((prototypes, query_feat), 0)
-    A, I, sim = affinity_dense(node_feat, k_connect, sigma)
+    A, I, sim = affinity_dense(node_feat, k_connect, sigma,
+                               I=knn_graph_fp32_topk(node_feat, k_connect) if timing_knn else None)
     Z = label_propagate_dense(A, Y)
     query_pred = Z[P:].view(-1, N, n_cls).transpose(1, 2)
     loss = F.cross_entropy(query_pred, query_y) if query_y is not None else None

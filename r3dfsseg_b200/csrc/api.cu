@@ -480,13 +480,20 @@ int r3dfs_affinity_knn(const float* node_feat, const uint8_t* valid, int n_graph
                          D2, nbr, sim, (cudaStream_t)stream);
 }
 
+// scratch shared by the sort-free in-edge build (bit matrix + rank prefixes) and, after it, by the
+// solver (row schedule table of up to 16 CTAs per graph + the row lists re-packed in schedule order)
+static size_t lp_scratch_bytes(size_t G, size_t n, int k) {
+  const size_t inedge = 6 * G * n * ((n + 31) / 32);
+  const size_t solver = G * 16 * 2304 * 8 + 6 * G * n * (size_t)lp_rowcap(k) + 1024;
+  return inedge > solver ? inedge : solver;
+}
+
 size_t r3dfs_label_propagate_workspace(int n_graphs, int64_t n_max, int k, int n_cls) {
   const size_t G = n_graphs, n = n_max;
   (void)n_cls;
-  const size_t W = (n + 31) / 32;  // bit matrix + rank prefixes of the sort-free in-edge build
   return align_up(4 * G * n * k, 256) * 3 + align_up(4 * G * (n + 1), 256) * 6 +
          align_up(4 * G * n * 8, 256) * 4 + align_up(6 * G * n * (size_t)lp_rowcap(k), 256) +
-         align_up(6 * G * n * W, 256) + 8192;
+         align_up(lp_scratch_bytes(G, n, k), 256) + 8192;
 }
 
 int r3dfs_label_propagate(const int32_t* nbr, const float* sim, const uint8_t* valid, int n_graphs,
@@ -516,7 +523,7 @@ int r3dfs_label_propagate(const int32_t* nbr, const float* sim, const uint8_t* v
   float* R = ws.take<float>(G * n * 8);
   float* P = ws.take<float>(G * n * 8);
   float* AP = ws.take<float>(G * n * 8);
-  const size_t scratch_bytes = 6 * G * n * ((n + 31) / 32);
+  const size_t scratch_bytes = lp_scratch_bytes(G, n, k);
   unsigned char* scratch = ws.take<unsigned char>(scratch_bytes);
   if (!ws.ok()) return R3DFS_E_WORKSPACE;
   cudaError_t ce = cudaMemcpyAsync(sv, sim, sizeof(float) * G * n * k, cudaMemcpyDeviceToDevice, st);

@@ -45,7 +45,8 @@ struct StageRec {
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 // merged symmetric rows (lp.cu): entries a graph owns per node; row segments are multiples of 4
-__host__ __device__ inline int lp_rowcap(int k) { return (2 * k + 3) & ~3; }
+// (a graph's rows hold at most 2 k nn entries in total; every row is padded to a multiple of 4)
+__host__ __device__ inline int lp_rowcap(int k) { return ((2 * k + 3) & ~3) + 4; }
 
 // Bump allocator over the caller's workspace.  Never owns memory.
 struct WsBump {

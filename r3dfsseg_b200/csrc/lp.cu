@@ -1035,6 +1035,124 @@ __device__ __forceinline__ void cg_allreduce(cg::cluster_group& cluster, CgExcha
   ++xcnt;
 }
 
+// Row schedule of the cluster kernel below, built once per solve by one CTA per (graph, rank), and
+// the row lists RE-PACKED in that order.  merge_rows_kernel places rows wherever its atomic cursor
+// lands, so 3 000 warps streaming their own rows hit HBM as small scattered reads (measured: the
+// solve saturated at 1.6 TB/s with ~9 MB in flight).  Packed, the 24 warps of a CTA read 24
+// neighbouring lists at any time and move through the CTA's region front to back.
+//   sched[(g * CL + rank)][warp][slot] = (list offset in the packed arrays, groups << 12 | local row)
+__global__ __launch_bounds__(CGC_THREADS) void cg_schedule_kernel(
+    const int32_t* __restrict__ rowptr, const int32_t* __restrict__ rowlen,
+    const uint8_t* __restrict__ valid, const uint16_t* __restrict__ mcol,
+    const float* __restrict__ mval, int nn, int k, int2* __restrict__ sched,
+    uint16_t* __restrict__ mcol2, float* __restrict__ mval2) {
+  __shared__ uint32_t s_key[CG_WARPS * CG_MAXR * 2];  // >= next power of two of the rows of a CTA
+  __shared__ int s_off[CG_WARPS * CG_MAXR * 2];
+  const int CL = gridDim.x, rank = blockIdx.x, g = blockIdx.y;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int64_t vb = (int64_t)g * nn;
+  const uint8_t* vg = valid + vb;
+  const int32_t* rp = rowptr + vb;
+  const int32_t* rl = rowlen + vb;
+  const int64_t mb = vb * lp_rowcap(k);
+  // (dealing the rows to the CTAs round-robin instead of in contiguous chunks balances the long
+  // prototype rows better but makes every vector update strided: measured 6.6 -> 7.5 ms)
+  const int chunk = (nn + CL - 1) / CL;
+  const int lo = min(nn, rank * chunk), hi = min(nn, lo + chunk);
+  const int nrows = hi - lo;
+  __shared__ int s_red[CGC_THREADS / 32];
+  __shared__ int s_base;
+  int npow = 32;
+  while (npow < nrows) npow <<= 1;
+  for (int i = tid; i < npow; i += CGC_THREADS) {
+    uint32_t key = 0;
+    if (i < nrows) {
+      const int row = lo + i;
+      const int n4 = vg[row] ? (rl[row] + 3) >> 2 : 0;
+      key = ((uint32_t)n4 << 12) | (uint32_t)i;
+    }
+    s_key[i] = key;
+  }
+  // start of this CTA's region of the packed arrays: everything owned by lower ranks (a row can be
+  // much longer than 2 k — hub nodes — so regions cannot be sized per row)
+  {
+    int below = 0;
+    for (int row = tid; row < lo; row += CGC_THREADS)
+      if (vg[row]) below += ((rl[row] + 3) >> 2) * 4;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) below += __shfl_xor_sync(0xffffffffu, below, o);
+    if (lane == 0) s_red[w] = below;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    int t = 0;
+    for (int q = 0; q < CGC_THREADS / 32; ++q) t += s_red[q];
+    s_base = t;
+  }
+  __syncthreads();
+  for (int ksz = 2; ksz <= npow; ksz <<= 1)
+    for (int j = ksz >> 1; j > 0; j >>= 1) {
+      for (int i = tid; i < npow; i += CGC_THREADS) {
+        const int ixj = i ^ j;
+        if (ixj > i) {
+          const uint32_t x = s_key[i], y = s_key[ixj];
+          const bool desc = (i & ksz) == 0;
+          if (desc ? x < y : x > y) {
+            s_key[i] = y;
+            s_key[ixj] = x;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  // exclusive scan of the list lengths (entries) in schedule order: warp 0, a segment per lane
+  if (w == 0) {
+    const int seg = npow / 32;
+    int sum = 0;
+    for (int i = lane * seg; i < (lane + 1) * seg; ++i) sum += (int)(s_key[i] >> 12) * 4;
+    int incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int a = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += a;
+    }
+    int run = incl - sum;
+    for (int i = lane * seg; i < (lane + 1) * seg; ++i) {
+      s_off[i] = run;
+      run += (int)(s_key[i] >> 12) * 4;
+    }
+  }
+  int2* tab = sched + (size_t)(g * CL + rank) * (CG_WARPS * CG_MAXR);
+  for (int i = tid; i < CG_WARPS * CG_MAXR; i += CGC_THREADS) tab[i] = make_int2(0, 0);
+  __syncthreads();
+  const bool pack = mcol2 != nullptr;
+  const int base = s_base;
+  for (int i = tid; i < nrows; i += CGC_THREADS) {
+    const uint32_t key = s_key[i];
+    if ((key >> 12) == 0) continue;
+    const int pass = i / CG_WARPS, pos = i % CG_WARPS;
+    const int ww = (pass & 1) ? CG_WARPS - 1 - pos : pos;
+    tab[ww * CG_MAXR + pass] =
+        make_int2(pack ? base + s_off[i] : rp[lo + (int)(key & 0xfffu)], (int)key);
+  }
+  if (pack) {
+    for (int i = w; i < nrows; i += CG_WARPS) {
+      const uint32_t key = s_key[i];
+      const int n4 = (int)(key >> 12);
+      if (n4 == 0) break;  // sorted: only empty rows follow
+      const int64_t src = mb + rp[lo + (int)(key & 0xfffu)], dst = mb + base + s_off[i];
+      const uint2* sc = reinterpret_cast<const uint2*>(mcol + src);
+      const float4* sv = reinterpret_cast<const float4*>(mval + src);
+      uint2* dc = reinterpret_cast<uint2*>(mcol2 + dst);
+      float4* dv = reinterpret_cast<float4*>(mval2 + dst);
+      for (int q = lane; q < n4; q += 32) {
+        dc[q] = sc[q];
+        dv[q] = sv[q];
+      }
+    }
+  }
+}
+
 // Vectors are stored padded to NCV columns (NCV = 4 or 8) so a node's row is one or two float4.
 template <int NCV>
 __global__ __launch_bounds__(CGC_THREADS, 1) void lp_cg_kernel(
@@ -1043,7 +1161,8 @@ __global__ __launch_bounds__(CGC_THREADS, 1) void lp_cg_kernel(
     const uint8_t* __restrict__ valid, int nn, int k,
     const float* __restrict__ Y, int nc, float alpha, float tol, int max_iter,
     float* __restrict__ Z, float* __restrict__ X, float* __restrict__ R, float* __restrict__ Pv,
-    float* __restrict__ AP, int32_t* __restrict__ iters_out, float* __restrict__ resid_out) {
+    float* __restrict__ AP, int32_t* __restrict__ iters_out, float* __restrict__ resid_out,
+    const int2* __restrict__ sched) {
   cg::cluster_group cluster = cg::this_cluster();
   const int CL = cluster.num_blocks(), rank = cluster.block_rank();
   const int g = blockIdx.y;
@@ -1066,12 +1185,14 @@ __global__ __launch_bounds__(CGC_THREADS, 1) void lp_cg_kernel(
   const float* mv = mval + vb * lp_rowcap(k);
   const int chunk = (nn + CL - 1) / CL;
   const int lo = min(nn, rank * chunk), hi = min(nn, lo + chunk);
+  const int nloc = hi - lo;  // this CTA's rows: lo + j
   int xcnt = 0;
 
   float part[NCV], bb[NCV], rs[NCV], tot[NCV];
 #pragma unroll
   for (int c = 0; c < NCV; ++c) part[c] = 0.f;
-  for (int row = lo + tid; row < hi; row += CGC_THREADS) {
+  for (int jj = tid; jj < nloc; jj += CGC_THREADS) {
+    const int row = lo + jj;
     const bool ok = vg[row];
 #pragma unroll
     for (int c = 0; c < NCV; ++c) {
@@ -1099,9 +1220,13 @@ __global__ __launch_bounds__(CGC_THREADS, 1) void lp_cg_kernel(
   // offsets/lengths sit in a shared-memory table (one broadcast LDS per row instead of dependent
   // global loads).  The schedule depends only on the row lengths, so it is the same in every run
   // and every floating-point sum keeps its order.
-  {
+  if (sched) {  // built (and the lists re-packed in this order) by cg_schedule_kernel
+    const int2* src = sched + (size_t)(g * CL + rank) * (CG_WARPS * CG_MAXR);
+    for (int i = tid; i < CG_WARPS * CG_MAXR; i += CGC_THREADS) s_meta[i] = src[i];
+    __syncthreads();
+  } else {
     uint32_t* s_key = reinterpret_cast<uint32_t*>(Ps);  // Ps is not live yet
-    const int nrows = hi - lo;
+    const int nrows = nloc;
     int npow = 32;
     while (npow < nrows) npow <<= 1;
     for (int i = tid; i < npow; i += CGC_THREADS) {
@@ -1275,7 +1400,8 @@ __global__ __launch_bounds__(CGC_THREADS, 1) void lp_cg_kernel(
     // ---- X += a P ; R -= a AP ; partial R.R      (own rows; P from the staged copy)
 #pragma unroll
     for (int c = 0; c < NCV; ++c) part[c] = 0.f;
-    for (int row = lo + tid; row < hi; row += CGC_THREADS) {
+    for (int jj = tid; jj < nloc; jj += CGC_THREADS) {
+      const int row = lo + jj;
 #pragma unroll
       for (int c = 0; c < NCV; ++c) {
         const int64_t o = (int64_t)row * NCV + c;
@@ -1298,7 +1424,8 @@ __global__ __launch_bounds__(CGC_THREADS, 1) void lp_cg_kernel(
       all_done = all_done && done[c];
     }
     // ---- P = R + beta P   (frozen for finished columns)
-    for (int row = lo + tid; row < hi; row += CGC_THREADS) {
+    for (int jj = tid; jj < nloc; jj += CGC_THREADS) {
+      const int row = lo + jj;
 #pragma unroll
       for (int c = 0; c < NCV; ++c)
         if (!done[c]) {
@@ -1310,8 +1437,10 @@ __global__ __launch_bounds__(CGC_THREADS, 1) void lp_cg_kernel(
     cluster.sync();  // publish P (and make sure nobody still reads Ps before it is restaged)
   }
   // Z (unpadded) from my rows
-  for (int row = lo + tid; row < hi; row += CGC_THREADS)
+  for (int jj = tid; jj < nloc; jj += CGC_THREADS) {
+    const int row = lo + jj;
     for (int c = 0; c < nc; ++c) Zg[(int64_t)row * nc + c] = Xg[(int64_t)row * NCV + c];
+  }
   if (rank == 0 && tid == 0) {
     if (iters_out) iters_out[g] = it;
     if (resid_out) {
@@ -1330,7 +1459,8 @@ static int launch_cg(int CL, int G, size_t smem, cudaStream_t st, const int32_t*
                      const int32_t* rowlen, const uint16_t* mcol, const float* mval,
                      const uint8_t* valid, int nn, int k, const float* Y, int nc,
                      float alpha, float tol, int max_iter, float* Z, float* X, float* R, float* P,
-                     float* AP, int32_t* iters_out, float* resid_out) {
+                     float* AP, int32_t* iters_out, float* resid_out, void* scratch,
+                     size_t scratch_bytes) {
   cudaError_t e = cudaFuncSetAttribute(lp_cg_kernel<NCV>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
@@ -1358,8 +1488,33 @@ static int launch_cg(int CL, int G, size_t smem, cudaStream_t st, const int32_t*
       return -1000;
     }
   }
+  // scratch: the schedule table, and (if it is large enough) the row lists re-packed in its order
+  const int2* sched = nullptr;
+  const size_t tab_bytes = align_up(sizeof(int2) * (size_t)G * CL * CG_WARPS * CG_MAXR, 256);
+  const size_t col_bytes = align_up(sizeof(uint16_t) * (size_t)G * nn * lp_rowcap(k), 256);
+  const size_t val_bytes = align_up(sizeof(float) * (size_t)G * nn * lp_rowcap(k), 256);
+  static const bool no_sched = R3DFS_GETENV("R3DFS_CG_NOSCHED") != nullptr;  // A/B: in-kernel schedule
+  static const bool no_pack = R3DFS_GETENV("R3DFS_CG_NOPACK") != nullptr;    // A/B: lists left in place
+  if (scratch && scratch_bytes >= tab_bytes && !no_sched) {
+    unsigned char* sp = reinterpret_cast<unsigned char*>(scratch);
+    int2* tab = reinterpret_cast<int2*>(sp);
+    uint16_t* mcol2 = nullptr;
+    float* mval2 = nullptr;
+    if (scratch_bytes >= tab_bytes + col_bytes + val_bytes && !no_pack) {
+      mcol2 = reinterpret_cast<uint16_t*>(sp + tab_bytes);
+      mval2 = reinterpret_cast<float*>(sp + tab_bytes + col_bytes);
+    }
+    cg_schedule_kernel<<<dim3(CL, G), CGC_THREADS, 0, st>>>(rowptr, rowlen, valid, mcol, mval, nn, k,
+                                                           tab, mcol2, mval2);
+    R3DFS_CHECK_LAUNCH();
+    sched = tab;
+    if (mcol2) {
+      mcol = mcol2;
+      mval = mval2;
+    }
+  }
   e = cudaLaunchKernelEx(&cfg, lp_cg_kernel<NCV>, rowptr, rowlen, mcol, mval, valid, nn, k, Y, nc,
-                         alpha, tol, max_iter, Z, X, R, P, AP, iters_out, resid_out);
+                         alpha, tol, max_iter, Z, X, R, P, AP, iters_out, resid_out, sched);
   if (e != cudaSuccess) return (int)e;
   ++r3dfs_launches;
   return 0;
@@ -1865,7 +2020,7 @@ int launch_lp_solve(const int32_t* rowptr, const int32_t* rowlen, const uint16_t
                     const float* mval, const uint8_t* valid, int G, int nn, int k, const float* Y,
                     int nc, float alpha, float tol, int max_iter, float* Z, float* X, float* R,
                     float* P, float* AP, int32_t* iters_out, float* resid_out, cudaStream_t st,
-                    bool latency) {
+                    bool latency, void* scratch, size_t scratch_bytes) {
   if (nc > CG_MAXC || nc < 1 || nn > 8192) return R3DFS_E_UNSUPPORTED;
   // padded vector width: one or two float4 per node
   const int ncv = nc <= 4 ? 4 : 8;
@@ -1902,10 +2057,10 @@ int launch_lp_solve(const int32_t* rowptr, const int32_t* rowlen, const uint16_t
        CL = (CL & (CL - 1)) ? (1 << (31 - __builtin_clz(CL))) : CL >> 1) {
     if (ncv == 4)
       rc = launch_cg<4>(CL, G, smem_cg, st, rowptr, rowlen, mcol, mval, valid, nn, k, Y, nc, alpha,
-                        tol, max_iter, Z, X, R, P, AP, iters_out, resid_out);
+                        tol, max_iter, Z, X, R, P, AP, iters_out, resid_out, scratch, scratch_bytes);
     else
       rc = launch_cg<8>(CL, G, smem_cg, st, rowptr, rowlen, mcol, mval, valid, nn, k, Y, nc, alpha,
-                        tol, max_iter, Z, X, R, P, AP, iters_out, resid_out);
+                        tol, max_iter, Z, X, R, P, AP, iters_out, resid_out, scratch, scratch_bytes);
   }
   if (rc != 0) return rc == -1000 ? R3DFS_E_UNSUPPORTED : rc;
   return 0;
@@ -1975,8 +2130,10 @@ int launch_label_propagate(const int32_t* nbr, float* sim, const uint8_t* valid,
   R3DFS_CHECK_LAUNCH();
   if (sr) sr->mark(R3DFS_ST_SYM, st);
 
+  // the in-edge scratch (bit matrix, ranks) is dead by now: the solver re-uses it
   R3DFS_TRY(launch_lp_solve(rowptr, rowlen, mcol, mval, valid, G, nn, k, Y, nc, alpha, tol, max_iter,
-                            Z, X, R, P, AP, iters_out, resid_out, st, latency));
+                            Z, X, R, P, AP, iters_out, resid_out, st, latency, scratch,
+                            scratch_bytes));
   if (sr) sr->mark(R3DFS_ST_CG, st);
   return 0;
 }

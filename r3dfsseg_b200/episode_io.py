@@ -98,6 +98,11 @@ class EpisodeFolder:
     def __getitem__(self, index):
         return read_episode(self.file_names[index])
 
+    def item(self, index):
+        """(data, sampled_classes) of episode `index` — what iterating yields; thread-safe, so the
+        evaluation driver reads several files at once."""
+        return collate_test(self[index])
+
     def __iter__(self):
         for i in range(len(self)):
             yield collate_test(self[i])

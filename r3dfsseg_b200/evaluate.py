@@ -50,55 +50,170 @@ def all_reduce_eval_state(counters: torch.Tensor, loss_sum: torch.Tensor, n_epis
     return counters, loss_sum, n_episodes
 
 
+class _Slot:
+    """One in-flight batch: pinned host staging buffers (written by the prefetch threads), their
+    device twins, a workspace and a stream.  `copied` says when the host side may be refilled."""
+
+    def __init__(self, model, batch, n_query, device):
+        nw, ks, N, C = model.n_way, model.k_shot, model.n_points, model.in_channels
+        pin = dict(pin_memory=True)
+        self.h_sx = torch.empty((batch, nw, ks, N, C), dtype=torch.float32, **pin)
+        self.h_sy = torch.empty((batch, nw, ks, N), dtype=torch.int32, **pin)
+        self.h_qx = torch.empty((batch, n_query, N, C), dtype=torch.float32, **pin)
+        self.h_qy = torch.empty((batch, n_query, N), dtype=torch.int64, **pin)
+        self.h_slot = torch.empty((batch, nw), dtype=torch.int32, **pin)
+        self.d = [torch.empty_like(t, device=device) for t in
+                  (self.h_sx, self.h_sy, self.h_qx, self.h_qy, self.h_slot)]
+        self.stream = torch.cuda.Stream(device=device)
+        self.copied = torch.cuda.Event()
+        self.ws = None
+        self.counters = None   # per-slot partial results: slots run on different streams
+        self.loss_sum = None
+
+
 class EpisodeEvaluator:
-    """Runs a list of episodes (r3dfsseg_b200.episodes.Episode-like objects) through the model.
+    """Runs episodes through the model, `batch` per C-ABI call.
 
     model         r3dfsseg_b200.models.MPTI_SelfAtten on a CUDA device, eval mode
     test_classes  the fold's test class ids (defines the counter slots)
     batch         episodes per C-ABI call
+    n_inflight    batches in flight: each has its own persistent pinned staging buffers, device
+                  buffers, workspace and stream; host threads fill the next batch's buffers (file
+                  reads included) while the GPU runs the previous ones
     """
 
-    def __init__(self, model, test_classes: Sequence[int], batch: int = 16, eval_mdns: bool = True):
+    def __init__(self, model, test_classes: Sequence[int], batch: int = 16, eval_mdns: bool = True,
+                 n_inflight: int = 3, n_readers: int = 4):
         self.model = model
         self.test_classes = list(test_classes)
         self.batch = int(batch)
         self.eval_mdns = eval_mdns
         self.device = next(model.parameters()).device
+        self.n_inflight = max(1, int(n_inflight))
+        self.n_readers = max(1, int(n_readers))
+        self._slots = None
+        self._slots_key = None
 
-    def _stage(self, eps):
-        """Pinned, point-major batch (the reference's .h5 layout, loader.py:1687-1721) -> device."""
-        sx = torch.stack([e.support_x.transpose(2, 3) for e in eps]).pin_memory()
-        sy = torch.stack([e.support_y for e in eps]).pin_memory()
-        qx = torch.stack([e.query_x.transpose(1, 2) for e in eps]).pin_memory()
-        qy = torch.stack([e.query_y for e in eps]).pin_memory()
-        slot = torch.tensor([class_slots(e.sampled_classes, self.test_classes) for e in eps],
-                            dtype=torch.int32).pin_memory()
-        dev = self.device
-        return (sx.to(dev, non_blocking=True).transpose(3, 4), sy.to(dev, non_blocking=True),
-                qx.to(dev, non_blocking=True).transpose(2, 3), qy.to(dev, non_blocking=True),
-                slot.to(dev, non_blocking=True))
+    # ---- staging --------------------------------------------------------------------------------
+    def _get_slots(self, n_query):
+        key = (self.batch, n_query, self.n_inflight)
+        if self._slots is None or self._slots_key != key:
+            self._slots = [_Slot(self.model, self.batch, n_query, self.device)
+                           for _ in range(self.n_inflight)]
+            self._slots_key = key
+        return self._slots
 
-    def run(self, episodes: Sequence, rank: int = 0, world: int = 1, logger=None,
+    def _fill(self, slot: "_Slot", i: int, data, classes):
+        """One episode (the reference's collate output, loader.py:1676-1684: (.., 9, N) views over
+        point-major memory) into row i of the pinned staging buffers: plain memcpys."""
+        nw, ks = self.model.n_way, self.model.k_shot
+        sx = data[0].reshape(nw, ks, data[0].shape[-2], data[0].shape[-1])
+        slot.h_sx[i].copy_(sx.transpose(2, 3))
+        slot.h_sy[i].copy_(data[1].reshape(nw, ks, -1))
+        slot.h_qx[i].copy_(data[2].transpose(1, 2))
+        slot.h_qy[i].copy_(data[3])
+        slot.h_slot[i].copy_(torch.tensor(class_slots(np.asarray(classes).reshape(-1),
+                                                      self.test_classes), dtype=torch.int32))
+
+    def _batches(self, source, rank, world):
+        """Yields lists of (data, classes) of this rank's shard, `batch` at a time, produced by
+        background threads: an indexable source (EpisodeFolder: `len`, `source.item(i)`) is read by
+        `n_readers` threads, any other iterable by one."""
+        import queue
+        import threading
+        from concurrent.futures import ThreadPoolExecutor
+        q: "queue.Queue" = queue.Queue(maxsize=2 * self.n_inflight)
+
+        def produce():
+            try:
+                if hasattr(source, "item") and hasattr(source, "__len__"):
+                    mine = shard_indices(len(source), rank, world)
+                    with ThreadPoolExecutor(self.n_readers) as pool:
+                        for s in range(0, len(mine), self.batch):
+                            q.put(list(pool.map(source.item, mine[s:s + self.batch])))
+                else:
+                    cur = []
+                    for i, item in enumerate(source):
+                        if i % world != rank:
+                            continue
+                        cur.append(item)
+                        if len(cur) == self.batch:
+                            q.put(cur)
+                            cur = []
+                    if cur:
+                        q.put(cur)
+                q.put(None)
+            except BaseException as e:  # surface reader errors in the consumer
+                q.put(e)
+
+        threading.Thread(target=produce, daemon=True).start()
+        while True:
+            b = q.get()
+            if b is None:
+                return
+            if isinstance(b, BaseException):
+                raise b
+            yield b
+
+    # ---- the loop ---------------------------------------------------------------------------------
+    def run(self, episodes, rank: int = 0, world: int = 1, logger=None,
             log_every: int = 50) -> Dict[str, object]:
-        """logger: optional object with `.cprint(str)` (the reference's utils.logger); it gets the
+        """episodes: a sequence of Episode-like objects, an EpisodeFolder, or any iterable of
+        (data, sampled_classes) as the reference's test loader yields them — consumed as a stream.
+        logger: optional object with `.cprint(str)` (the reference's utils.logger); it gets the
         reference's progress line every `log_every` episodes (eval_noise.py:94-95) and the
         per-class IoU printout at the end (:64-68)."""
-        from . import ops
-        mine = [episodes[i] for i in shard_indices(len(episodes), rank, world)]
+        from . import _lib, ops
+        if isinstance(episodes, (list, tuple)) and episodes and hasattr(episodes[0], "support_x"):
+            episodes = _EpisodeList(episodes)
         n_slots = len(self.test_classes) + 1
-        counters = torch.zeros((3, n_slots), dtype=torch.int64, device=self.device)
-        loss_sum = torch.zeros((), dtype=torch.float64, device=self.device)
-        for s in range(0, len(mine), self.batch):
-            sx, sy, qx, qy, slot = self._stage(mine[s:s + self.batch])
-            out = self.model.forward_episodes(sx, sy, qx, qy, eval=self.eval_mdns)
-            ops.confusion_accumulate(out["pred"], qy, slot, counters)
-            loss_sum += out["loss"].double().sum()
-            done = min(s + self.batch, len(mine))
-            if logger is not None and done // log_every > s // log_every:
+        dev = self.device
+        counters = torch.zeros((3, n_slots), dtype=torch.int64, device=dev)
+        loss_sum = torch.zeros((), dtype=torch.float64, device=dev)
+        last_loss = None
+        slots = None
+        done = 0
+        cur = torch.cuda.current_stream(dev)
+        for bi, items in enumerate(self._batches(episodes, rank, world)):
+            n_query = int(items[0][0][2].shape[0])
+            if slots is None:
+                slots = self._get_slots(n_query)
+                cfg = self.model._cfg(n_query, mdns=bool(self.eval_mdns))
+                need = _lib.lib().r3dfs_mpti_workspace(cfg, self.batch)
+                for sl in slots:
+                    if sl.ws is None or sl.ws.numel() < need:
+                        sl.ws = torch.empty(need, dtype=torch.uint8, device=dev)
+                    sl.counters = torch.zeros_like(counters)
+                    sl.loss_sum = torch.zeros_like(loss_sum)
+                    sl.stream.wait_stream(cur)
+            sl = slots[bi % len(slots)]
+            sl.copied.synchronize()  # the H2D copies of this slot's previous batch are done
+            for i, (data, classes) in enumerate(items):
+                self._fill(sl, i, data, classes)
+            n = len(items)
+            with torch.cuda.stream(sl.stream):
+                for h, d in zip((sl.h_sx, sl.h_sy, sl.h_qx, sl.h_qy, sl.h_slot), sl.d):
+                    d[:n].copy_(h[:n], non_blocking=True)
+                sl.copied.record(sl.stream)
+                sx, sy, qx, qy, slot = (d[:n] for d in sl.d)
+                out = self.model.forward_episodes(sx.transpose(3, 4), sy, qx.transpose(2, 3), qy,
+                                                  eval=self.eval_mdns, workspace=sl.ws)
+                ops.confusion_accumulate(out["pred"], qy, slot, sl.counters)
+                sl.loss_sum += out["loss"].double().sum()
+                last_loss = out["loss"]
+                for t in (out["pred"], out["loss"], out["logits"]):
+                    t.record_stream(sl.stream)
+            if logger is not None and (done + n) // log_every > done // log_every:
                 from datetime import datetime
                 logger.cprint("[Eval] Iter: %d | Loss: %.4f | %s" % (
-                    done, float(out["loss"][-1]), str(datetime.now())))
-        n = torch.tensor(float(len(mine)), dtype=torch.float64, device=self.device)
+                    done + n, float(last_loss[-1]), str(datetime.now())))
+            done += n
+        if slots is not None:
+            for sl in slots:
+                cur.wait_stream(sl.stream)
+                counters += sl.counters
+                loss_sum += sl.loss_sum
+        n = torch.tensor(float(done), dtype=torch.float64, device=dev)
         all_reduce_eval_state(counters, loss_sum, n)
         res = iou_from_counters(counters)
         res.update(counters=counters.cpu(), mean_loss=float(loss_sum / n), n_episodes=int(n))
@@ -109,24 +224,38 @@ class EpisodeEvaluator:
         return res
 
 
-class _ItemEpisode:
-    """Adapter: (data list, sampled_classes) as the reference's test loader yields them."""
+class _EpisodeList:
+    """Adapter: Episode-like objects (support_x, support_y, query_x, query_y, sampled_classes) as an
+    indexable source of (data, sampled_classes)."""
 
-    def __init__(self, data, sampled_classes):
-        self.support_x, self.support_y, self.query_x, self.query_y = data[0], data[1], data[2], data[3]
-        self.sampled_classes = np.asarray(sampled_classes).reshape(-1)
+    def __init__(self, eps):
+        self.eps = eps
+
+    def __len__(self):
+        return len(self.eps)
+
+    def item(self, i):
+        e = self.eps[i]
+        return [e.support_x, e.support_y, e.query_x, e.query_y], e.sampled_classes
 
 
-def test_few_shot(test_loader, learner, logger, test_classes, path=None, eval=False, batch: int = 16):
+def test_few_shot(test_loader, learner, logger, test_classes, path=None, eval=False, batch: int = 16,
+                  n_inflight: int = 3):
     """Drop-in for reference eval_noise.py:75-113: same arguments, returns (mean_loss, mean_IoU).
     `test_loader` yields (data, sampled_classes) per episode exactly as the reference's DataLoader
-    (batch_size 1, `batch_test_task_collate_test`); episodes are run `batch` at a time through one
-    C-ABI call each and — under torch.distributed — sharded over the ranks."""
+    (batch_size 1, `batch_test_task_collate_test`); it is consumed as a STREAM (never materialised):
+    background threads read/collate ahead into persistent pinned buffers, episodes run `batch` at a
+    time through one C-ABI call each on `n_inflight` streams, and — under torch.distributed — are
+    sharded over the ranks.  An `episode_io.EpisodeFolder` is read by several threads."""
     import torch.distributed as dist
     rank = dist.get_rank() if dist.is_available() and dist.is_initialized() else 0
     world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
-    episodes = [_ItemEpisode(data, classes) for data, classes in test_loader]
     learner.model.eval()
-    ev = EpisodeEvaluator(learner.model, test_classes, batch=batch, eval_mdns=bool(eval))
-    res = ev.run(episodes, rank, world, logger=logger)
+    ev = getattr(learner, "_evaluator", None)
+    key = (tuple(test_classes), batch, bool(eval), n_inflight)
+    if ev is None or getattr(learner, "_evaluator_key", None) != key:
+        ev = EpisodeEvaluator(learner.model, test_classes, batch=batch, eval_mdns=bool(eval),
+                              n_inflight=n_inflight)
+        learner._evaluator, learner._evaluator_key = ev, key
+    res = ev.run(test_loader, rank, world, logger=logger)
     return res["mean_loss"], res["mean_iou"]

@@ -66,6 +66,19 @@ def main():
             sys.stdout.flush()
             os.dup2(saved, 1)
             os.close(saved)
+    line = measure(dev, dist, rank, world, args.steps, args.warmup, args.episodes, args.cpu_steps)
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def measure(dev, dist, rank, world, steps, warmup, n_episodes=8, cpu_steps=0):
+    """One timed run of the training step on this rank (all ranks call it); returns the JSON line
+    (a dict) on every rank.  Used by main() and by bench.py (`extra.train_step`)."""
+    import types
+    args = types.SimpleNamespace(steps=steps, warmup=warmup, episodes=n_episodes,
+                                 cpu_steps=cpu_steps)
     from r3dfsseg_b200 import _lib, train as T
     from r3dfsseg_b200.episodes import default_args, make_episode
     from r3dfsseg_b200.models import MPTI_SelfAtten
@@ -147,7 +160,7 @@ def main():
         cpu = {"value": 1.0 / sec, "unit": "steps/s", "cores": threads, "kind": "port",
                "sample": f"{args.cpu_steps} steps (forward + autograd backward + torch Adam) of "
                          f"oracle/mpti_train_oracle.py, torch fp32, {threads} threads"}
-    if rank == 0:
+    if True:
         line = {"metric": "MPTI meta-training episodes/s (2-way 5-shot, way-contrast loss)",
                 "value": world * args.steps / (total_ms * 1e-3), "unit": "episodes/s",
                 "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -161,9 +174,7 @@ def main():
                               "allreduce_plus_adam": round(upd, 3)},
                 "allreduce_us_1p5MB": ar_us, "gpu_launches": int(launches),
                 "final_loss": float(loss.detach()), "cpu_baseline": cpu}
-        print(json.dumps(line), flush=True)
-    if dist is not None:
-        dist.destroy_process_group()
+    return line
 
 
 if __name__ == "__main__":

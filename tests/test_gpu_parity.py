@@ -869,6 +869,45 @@ def test_drop_in_test_few_shot_matches_per_episode_loop(model, fixture_sd):
     assert any("mean IoU" in s for s in lines)
 
 
+def test_episode_folder_streaming_driver_and_stage_batch(model, tmp_path):
+    """The file-backed path of SURVEY §8(f) ranks 1-2: episode files in the reference's schema ->
+    EpisodeFolder -> evaluate.test_few_shot (reader threads, persistent pinned staging buffers,
+    several batches in flight, a partial last batch) == per-episode forward + the oracle's metric;
+    and episode_io.stage_batch(pin=True) -> one H2D copy -> forward_episodes == the same logits."""
+    from r3dfsseg_b200 import episode_io as IO
+    from r3dfsseg_b200.evaluate import test_few_shot
+    from r3dfsseg_b200.train import MPTILearner_V3
+    m = model(2, 5)
+    learner = MPTILearner_V3(default_args(2, 5), mode="test", model=m)
+    eps = [make_episode(400 + i, 2, 5, noise_ratio=0.4 if i % 2 else 0.0) for i in range(7)]
+    for i, e in enumerate(eps):
+        IO.write_episode(str(tmp_path / ("%04d.h5" % i)), IO.episode_arrays(e))
+    folder = IO.EpisodeFolder(str(tmp_path))
+    assert len(folder) == 7
+    test_classes = list(range(6))
+    mean_loss, mean_iou = test_few_shot(folder, learner, None, test_classes, eval=True, batch=3,
+                                        n_inflight=2)
+    again = test_few_shot(folder, learner, None, test_classes, eval=True, batch=3, n_inflight=2)
+    assert again == (mean_loss, mean_iou)              # buffers are re-used: same answer
+    preds, gts, l2c, losses, logits = [], [], [], [], []
+    for e in eps:
+        pred, loss = m(e.support_x.to(DEV), e.support_y.to(DEV), e.query_x.to(DEV),
+                       e.query_y.to(DEV), eval=True)
+        logits.append(pred.cpu())
+        preds.append(pred.argmax(1).cpu().numpy()); gts.append(e.query_y.numpy())
+        l2c.append(e.sampled_classes); losses.append(float(loss))
+    assert abs(mean_iou - O.mean_iou(O.confusion_counts(preds, gts, l2c, test_classes))) < 1e-9
+    assert abs(mean_loss - float(np.mean(losses))) < 1e-5
+    # stage_batch: pinned, point-major, one copy per tensor
+    sx, sy, qx, qy, classes = IO.stage_batch([folder[i] for i in range(4)], pin=True)
+    assert sx.is_pinned() and qx.is_pinned() and sx.shape == (4, 2, 5, 2048, 9)
+    out = m.forward_episodes(sx.to(DEV, non_blocking=True).transpose(3, 4), sy.to(DEV),
+                             qx.to(DEV, non_blocking=True).transpose(2, 3), qy.to(DEV), eval=True)
+    for i in range(4):
+        assert torch.equal(out["logits"][i].transpose(1, 2).cpu(), logits[i])
+        assert np.array_equal(classes[i].numpy(), eps[i].sampled_classes)
+
+
 # ---- ProtoNet + MDNS (reference models/protonet.py:357-945, eval) ------------------------------
 @pytest.mark.parametrize("name", ["s3dis_2way_5shot_noisy", "scannet_3way_5shot_ood",
                                   "s3dis_2way_1shot"])
