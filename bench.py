@@ -270,7 +270,7 @@ def driver_leg(model, dev, dist, rank, world, host_batch, chunk, steps, test_cla
         for i in range(E):
             zs = np.zeros(tuple(h_sy[i].shape), np.int32)
             zq = np.zeros(tuple(h_qy[i].shape), np.int32)
-            IO.write_episode(os.path.join(d, "%05d.h5" % i),
+            IO.write_episode(os.path.join(d, "%05d.r3ep" % i),
                              (h_sx[i].numpy(), h_sy[i].numpy(), h_qx[i].numpy(), h_qy[i].numpy(),
                               classes[i], zs, zq, h_sy[i].numpy()))
         folder = IO.EpisodeFolder(d)

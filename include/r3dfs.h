@@ -418,6 +418,14 @@ int r3dfs_mpti_train_backward(const r3dfs_episode_cfg_t* h_cfg, int in_dim, int 
                               float w_contrast, float* grads, void* ws, size_t ws_bytes,
                               r3dfs_stream_t stream);
 
+/* The reference's logging-only diagnostics of a training forward (models/mpti.py:514-552), from
+ * the workspace of the last r3dfs_mpti_train_forward: ratios[0] = clean_ratio_LP_avg (foreground
+ * support points whose prototype's propagated label agrees with the ground-truth mask, averaged
+ * over ways), ratios[1] = clean_ratio_original_avg.  gt_support_y: (n_way, k_shot, N) int32. */
+int r3dfs_mpti_train_clean_ratio(const r3dfs_episode_cfg_t* h_cfg, int in_dim, int dgcnn_k,
+                                 const int32_t* support_y, const int32_t* gt_support_y,
+                                 float* ratios, void* ws, size_t ws_bytes, r3dfs_stream_t stream);
+
 /* Diagnostics for the parity tests: copies the discrete decisions of the last
  * r3dfs_mpti_train_forward out of its workspace, so that a reference implementation can be run
  * with the same neighbour lists / cluster assignments (they carry no gradient, but FP32 ties in

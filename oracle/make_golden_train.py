@@ -38,6 +38,7 @@ def run_reference(ref, sd, ep, n_way, k_shot):
                 gt_query_y=ep.query_y, train=True, logger=ref_shims.QuietLogger(),
                 support_flag=ep.support_flag)
     query_pred, lp_loss, contrast = out[0], out[1], out[2]
+    run_reference.diag = tuple(float(x) for x in out[3:7])  # acc_LP, acc_orig, clean_LP, clean_orig
     loss = lp_loss + 0.1 * contrast
     loss.backward()
     grads = {k: p.grad.detach().clone() for k, p in m.named_parameters()}
@@ -55,7 +56,7 @@ def main():
         qp, lp, ct, grads, buffers = run_reference(ref, sd, ep, n_way, k_shot)
         out[name] = dict(
             seed=seed, n_way=n_way, k_shot=k_shot, dataset=ds, noise_ratio=noise,
-            lp_loss=lp.clone(), contrast_loss=ct.clone(),
+            lp_loss=lp.clone(), contrast_loss=ct.clone(), diagnostics=run_reference.diag,
             query_pred_sub=qp[:, :, ::16].contiguous().clone(),
             grad_norm={k: g.norm().clone() for k, g in grads.items()},
             grad_sample={k: g.reshape(-1)[::GRAD_SAMPLE_STRIDE].clone() for k, g in grads.items()},

@@ -121,6 +121,8 @@ SIGNATURES = {
                                            f32, vp, vp, vp, vp, vp, vp, sz, vp]),
     "r3dfs_mpti_train_backward": (C.c_int, [C.POINTER(EpisodeCfg), i32, i32, vp, vp, vp, vp,
                                             f32, vp, vp, f32, f32, vp, vp, sz, vp]),
+    "r3dfs_mpti_train_clean_ratio": (C.c_int, [C.POINTER(EpisodeCfg), i32, i32, vp, vp, vp, vp, sz,
+                                               vp]),
     "r3dfs_mpti_train_export": (C.c_int, [C.POINTER(EpisodeCfg), i32, i32, C.POINTER(TrainExport), vp,
                                           sz, vp]),
     "r3dfs_adam_step": (C.c_int, [vp, vp, vp, vp, i64, i64, f32, f32, f32, f32, f32, i64, f32, vp]),

@@ -544,6 +544,101 @@ int r3dfs_mpti_train_backward(const r3dfs_episode_cfg_t* cfg_in, int in_dim, int
   return 0;
 }
 
+// --------------------------------------------------------------------------------------------
+// The reference's logging-only diagnostics of a training forward (models/mpti.py:514-552):
+// per way, every foreground support point takes the label-propagation verdict of its prototype
+// (argmax of the prototype's Z row == way + 1) and is compared with the ground-truth mask;
+// clean_ratio_LP = fraction of agreeing points, clean_ratio_original = fraction whose GIVEN mask
+// (always 1 on these points) agrees.  One CTA; integer counts, so the result is exact.
+// --------------------------------------------------------------------------------------------
+__global__ __launch_bounds__(1024) void clean_ratio_kernel(
+    const int32_t* __restrict__ support_y, const int32_t* __restrict__ gt_support_y,
+    const int32_t* __restrict__ cloud_fg_off, const int32_t* __restrict__ assign,
+    const float* __restrict__ Z, int n_way, int k_shot, int N, int slot, int nc,
+    float* __restrict__ out) {
+  __shared__ int s_warp[32];
+  __shared__ int s_cnt[3];
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  float ratio_lp = 0.f, ratio_orig = 0.f;
+  for (int way = 0; way < n_way; ++way) {
+    int ok_lp = 0, ok_orig = 0, total = 0;
+    for (int shot = 0; shot < k_shot; ++shot) {
+      const int cloud = way * k_shot + shot;
+      const int32_t* y = support_y + (int64_t)cloud * N;
+      const int32_t* g = gt_support_y + (int64_t)cloud * N;
+      int base = cloud_fg_off[cloud];  // row of the cloud's first foreground point in the set buffer
+      for (int p0 = 0; p0 < N; p0 += 1024) {
+        const int p = p0 + tid;
+        const bool fg = p < N && y[p] != 0;
+        const unsigned bal = __ballot_sync(0xffffffffu, fg);
+        if (lane == 0) s_warp[w] = __popc(bal);
+        __syncthreads();
+        int before = 0, all = 0;
+        for (int q = 0; q < 32; ++q) {
+          const int c = s_warp[q];
+          before += q < w ? c : 0;
+          all += c;
+        }
+        if (fg) {
+          const int row = base + before + __popc(bal & ((1u << lane) - 1));
+          const float* z = Z + (int64_t)((1 + way) * slot + assign[row]) * nc;
+          int arg = 0;
+          float best = z[0];
+          for (int c = 1; c < nc; ++c)
+            if (z[c] > best) {
+              best = z[c];
+              arg = c;
+            }
+          const int gt = g[p];
+          ok_lp += ((arg == way + 1) ? 1 : 0) == gt;
+          ok_orig += 1 == gt;
+          total += 1;
+        }
+        base += all;
+        __syncthreads();
+      }
+    }
+    // block sums
+    int v[3] = {ok_lp, ok_orig, total};
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+      for (int o = 16; o > 0; o >>= 1) v[q] += __shfl_xor_sync(0xffffffffu, v[q], o);
+      if (lane == 0) s_warp[w] = v[q];
+      __syncthreads();
+      if (tid == 0) {
+        int t = 0;
+        for (int i = 0; i < 32; ++i) t += s_warp[i];
+        s_cnt[q] = t;
+      }
+      __syncthreads();
+    }
+    ratio_lp += (float)s_cnt[0] / (float)s_cnt[2];   // 0/0 = nan, as in the reference
+    ratio_orig += (float)s_cnt[1] / (float)s_cnt[2];
+  }
+  if (tid == 0) {
+    out[0] = ratio_lp / (float)n_way;
+    out[1] = ratio_orig / (float)n_way;
+  }
+}
+
+int r3dfs_mpti_train_clean_ratio(const r3dfs_episode_cfg_t* cfg_in, int in_dim, int dgcnn_k,
+                                 const int32_t* support_y, const int32_t* gt_support_y,
+                                 float* ratios, void* wsp, size_t ws_bytes, r3dfs_stream_t stream) {
+  EpisodeDims d;
+  R3DFS_TRY(episode_dims(cfg_in, d));
+  if (!support_y || !gt_support_y || !ratios || !wsp) return R3DFS_E_BADARG;
+  if (ws_bytes < r3dfs_mpti_train_workspace(cfg_in, in_dim, dgcnn_k)) return R3DFS_E_WORKSPACE;
+  cudaStream_t st = (cudaStream_t)stream;
+  WsBump ws(wsp, ws_bytes);
+  TrainWs t;
+  carve_train(ws, cfg_in, d, in_dim, dgcnn_k, t);
+  clean_ratio_kernel<<<1, 1024, 0, st>>>(support_y, gt_support_y, t.ep.cloud_fg_off, t.ep.assign,
+                                         t.ep.Z, cfg_in->n_way, cfg_in->k_shot, cfg_in->n_points,
+                                         d.slot, d.nc, ratios);
+  R3DFS_CHECK_LAUNCH();
+  return 0;
+}
+
 int r3dfs_mpti_train_export(const r3dfs_episode_cfg_t* cfg_in, int in_dim, int dgcnn_k,
                             const r3dfs_train_export_t* o, void* wsp, size_t ws_bytes,
                             r3dfs_stream_t stream) {

@@ -6,7 +6,9 @@ clouds point-major in memory (`batch_test_task_collate_test`, :1676-1684).  Here
 
 * `write_episode` / `read_episode` keep that schema (same dataset names, dtypes and shapes).  The
   container is HDF5 when `h5py` is importable (it is not in this image) and a NumPy `.npz` with the
-  same keys otherwise — the arrays are identical either way;
+  same keys otherwise — the arrays are identical either way; `.r3ep` is the same eight datasets as
+  one flat, 64-byte-aligned file that reader threads `readinto()` pinned staging memory directly
+  (`convert_folder` converts a folder once);
 * `collate_test` is the reference's collate: tensors as `MPTILearner_V3.test` expects them;
 * `stage_batch` packs a list of episodes into ONE pinned, point-major host buffer per tensor, the
   layout `r3dfs_mpti_forward` consumes directly (E episodes per call, no per-episode H2D copies,
@@ -51,6 +53,8 @@ def episode_arrays(ep) -> Tuple[np.ndarray, ...]:
 def write_episode(out_filename: str, data: Sequence[np.ndarray]) -> str:
     """reference dataloaders/loader.py:1687-1706.  Returns the path written (the extension is
     switched to .npz when HDF5 is unavailable)."""
+    if out_filename.endswith(RAW_EXT):
+        return write_episode_raw(out_filename, data)
     arrays = {k: np.asarray(v, dtype=SCHEMA[k]) for k, v in zip(ORDER, data)}
     if _h5 is not None and out_filename.endswith(".h5"):
         with _h5.File(out_filename, "w") as f:
@@ -62,8 +66,98 @@ def write_episode(out_filename: str, data: Sequence[np.ndarray]) -> str:
     return path
 
 
+# ---- raw container -------------------------------------------------------------------------------
+# The same eight datasets (names, dtypes, shapes of the reference's schema) as ONE flat file:
+#   8-byte magic | uint32 header length | JSON header {name: [dtype, shape, byte offset]} | arrays,
+# each 64-byte aligned.  A reader thread `readinto()`s an array straight into the pinned staging
+# buffer the H2D copy starts from — no parsing, no intermediate copy (the .h5 / .npz containers
+# need both).  `convert_folder` turns a folder of .h5 / .npz episodes into this form once.
+RAW_MAGIC = b"R3EP0001"
+RAW_EXT = ".r3ep"
+
+
+def write_episode_raw(out_filename: str, data: Sequence[np.ndarray]) -> str:
+    import json
+    arrays = {k: np.ascontiguousarray(np.asarray(v, dtype=SCHEMA[k])) for k, v in zip(ORDER, data)}
+    path = os.path.splitext(out_filename)[0] + RAW_EXT
+    # two passes: offsets depend on the header length
+    header, blob_len = {}, 0
+    for guess in range(2):
+        hdr = json.dumps(header).encode() if header else b"{}" + b" " * 1024
+        start = (8 + 4 + len(hdr) + 63) // 64 * 64
+        off, header = start, {}
+        for k, v in arrays.items():
+            header[k] = [SCHEMA[k], list(v.shape), off]
+            off = (off + v.nbytes + 63) // 64 * 64
+        blob_len = off
+        hdr2 = json.dumps(header).encode()
+        if (8 + 4 + len(hdr2) + 63) // 64 * 64 == start:
+            break
+    hdr = json.dumps(header).encode()
+    with open(path, "wb") as f:
+        f.write(RAW_MAGIC)
+        f.write(np.uint32(len(hdr)).tobytes())
+        f.write(hdr)
+        for k, v in arrays.items():
+            f.seek(header[k][2])
+            f.write(v.tobytes())
+        f.truncate(blob_len)
+    return path
+
+
+def _raw_header(f) -> Dict[str, list]:
+    import json
+    if f.read(8) != RAW_MAGIC:
+        raise ValueError("not an R3EP episode file")
+    n = int(np.frombuffer(f.read(4), dtype=np.uint32)[0])
+    return json.loads(f.read(n).decode())
+
+
+def read_episode_raw(file_name: str) -> Tuple[np.ndarray, ...]:
+    with open(file_name, "rb") as f:
+        hdr = _raw_header(f)
+        out = []
+        for k in ORDER:
+            dt, shape, off = hdr[k]
+            f.seek(off)
+            a = np.empty(shape, dtype=dt)
+            f.readinto(memoryview(a).cast("B"))
+            out.append(a)
+    return tuple(out)
+
+
+def read_episode_raw_into(file_name: str, dst: Dict[str, np.ndarray]) -> np.ndarray:
+    """Reads the datasets named in `dst` straight into those (C-contiguous, writable) arrays —
+    e.g. rows of pinned staging tensors — and returns sampled_classes."""
+    with open(file_name, "rb") as f:
+        hdr = _raw_header(f)
+        for k, a in dst.items():
+            dt, shape, off = hdr[k]
+            if a.dtype != np.dtype(dt) or list(a.shape) != list(shape):
+                raise ValueError(f"{file_name}: {k} is {dt}{shape}, staging buffer is "
+                                 f"{a.dtype}{list(a.shape)}")
+            f.seek(off)
+            f.readinto(memoryview(a).cast("B"))
+        dt, shape, off = hdr["sampled_classes"]
+        f.seek(off)
+        return np.frombuffer(f.read(int(np.prod(shape)) * np.dtype(dt).itemsize), dtype=dt).copy()
+
+
+def convert_folder(src: str, dst: str) -> int:
+    """.h5 / .npz episodes of `src` -> raw episode files in `dst`; returns the number converted."""
+    os.makedirs(dst, exist_ok=True)
+    n = 0
+    for name in sorted(os.listdir(src)):
+        if name.endswith((".h5", ".npz")):
+            write_episode_raw(os.path.join(dst, name), read_episode(os.path.join(src, name)))
+            n += 1
+    return n
+
+
 def read_episode(file_name: str) -> Tuple[np.ndarray, ...]:
     """reference dataloaders/loader.py:1709-1721: the 8-tuple in ORDER."""
+    if file_name.endswith(RAW_EXT):
+        return read_episode_raw(file_name)
     if file_name.endswith(".h5"):
         if _h5 is None:
             raise RuntimeError("reading .h5 episodes needs h5py (not installed); use the .npz twin")
@@ -89,7 +183,7 @@ class EpisodeFolder:
     episode files; iterating yields what its DataLoader yields: (data, sampled_classes)."""
 
     def __init__(self, folder: str):
-        names = sorted(n for n in os.listdir(folder) if n.endswith((".h5", ".npz")))
+        names = sorted(n for n in os.listdir(folder) if n.endswith((".h5", ".npz", RAW_EXT)))
         self.file_names = [os.path.join(folder, n) for n in names]
 
     def __len__(self):
@@ -102,6 +196,17 @@ class EpisodeFolder:
         """(data, sampled_classes) of episode `index` — what iterating yields; thread-safe, so the
         evaluation driver reads several files at once."""
         return collate_test(self[index])
+
+    def read_into(self, index, dst: Dict[str, np.ndarray]) -> np.ndarray:
+        """Episode `index` into staging arrays keyed by dataset name (point-major, the on-disk
+        layout); returns sampled_classes.  Raw files are read in place, the others via a copy."""
+        name = self.file_names[index]
+        if name.endswith(RAW_EXT):
+            return read_episode_raw_into(name, dst)
+        item = dict(zip(ORDER, read_episode(name)))
+        for k, a in dst.items():
+            np.copyto(a, item[k].astype(a.dtype, copy=False).reshape(a.shape))
+        return np.asarray(item["sampled_classes"], np.int32)
 
     def __iter__(self):
         for i in range(len(self)):

@@ -51,10 +51,13 @@ def all_reduce_eval_state(counters: torch.Tensor, loss_sum: torch.Tensor, n_epis
 
 
 class _Slot:
-    """One in-flight batch: pinned host staging buffers (written by the prefetch threads), their
-    device twins, a workspace and a stream.  `copied` says when the host side may be refilled."""
+    """One in-flight batch: pinned host staging buffers (filled by the reader threads), their device
+    twins, a workspace, a stream and partial results.  Hand-over: the producer fills the host side
+    and queues the slot; the consumer enqueues the H2D copies + the forward on the slot's stream,
+    records `copied` and sets `issued`; the producer waits for both before it refills the slot."""
 
     def __init__(self, model, batch, n_query, device):
+        import threading
         nw, ks, N, C = model.n_way, model.k_shot, model.n_points, model.in_channels
         pin = dict(pin_memory=True)
         self.h_sx = torch.empty((batch, nw, ks, N, C), dtype=torch.float32, **pin)
@@ -62,10 +65,16 @@ class _Slot:
         self.h_qx = torch.empty((batch, n_query, N, C), dtype=torch.float32, **pin)
         self.h_qy = torch.empty((batch, n_query, N), dtype=torch.int64, **pin)
         self.h_slot = torch.empty((batch, nw), dtype=torch.int32, **pin)
+        # numpy views of the same pinned memory, keyed by the episode-file dataset names
+        self.np = {"support_ptclouds": self.h_sx.numpy(), "support_masks": self.h_sy.numpy(),
+                   "query_ptclouds": self.h_qx.numpy(), "query_labels": self.h_qy.numpy()}
+        self.np_slot = self.h_slot.numpy()
         self.d = [torch.empty_like(t, device=device) for t in
                   (self.h_sx, self.h_sy, self.h_qx, self.h_qy, self.h_slot)]
         self.stream = torch.cuda.Stream(device=device)
         self.copied = torch.cuda.Event()
+        self.issued = threading.Event()
+        self.issued.set()
         self.ws = None
         self.counters = None   # per-slot partial results: slots run on different streams
         self.loss_sum = None
@@ -78,18 +87,19 @@ class EpisodeEvaluator:
     test_classes  the fold's test class ids (defines the counter slots)
     batch         episodes per C-ABI call
     n_inflight    batches in flight: each has its own persistent pinned staging buffers, device
-                  buffers, workspace and stream; host threads fill the next batch's buffers (file
-                  reads included) while the GPU runs the previous ones
+                  buffers, workspace and stream; reader threads fill the next batches' buffers
+                  (straight from the episode files when the source can `read_into`) while the GPU
+                  runs the previous ones
     """
 
     def __init__(self, model, test_classes: Sequence[int], batch: int = 16, eval_mdns: bool = True,
-                 n_inflight: int = 3, n_readers: int = 4):
+                 n_inflight: int = 3, n_readers: int = 6):
         self.model = model
         self.test_classes = list(test_classes)
         self.batch = int(batch)
         self.eval_mdns = eval_mdns
         self.device = next(model.parameters()).device
-        self.n_inflight = max(1, int(n_inflight))
+        self.n_inflight = max(2, int(n_inflight))
         self.n_readers = max(1, int(n_readers))
         self._slots = None
         self._slots_key = None
@@ -112,48 +122,58 @@ class EpisodeEvaluator:
         slot.h_sy[i].copy_(data[1].reshape(nw, ks, -1))
         slot.h_qx[i].copy_(data[2].transpose(1, 2))
         slot.h_qy[i].copy_(data[3])
-        slot.h_slot[i].copy_(torch.tensor(class_slots(np.asarray(classes).reshape(-1),
-                                                      self.test_classes), dtype=torch.int32))
+        slot.np_slot[i] = class_slots(np.asarray(classes).reshape(-1), self.test_classes)
 
-    def _batches(self, source, rank, world):
-        """Yields lists of (data, classes) of this rank's shard, `batch` at a time, produced by
-        background threads: an indexable source (EpisodeFolder: `len`, `source.item(i)`) is read by
-        `n_readers` threads, any other iterable by one."""
-        import queue
-        import threading
+    def _read_into(self, source, slot: "_Slot", i: int, index: int):
+        classes = source.read_into(index, {k: v[i] for k, v in slot.np.items()})
+        slot.np_slot[i] = class_slots(classes, self.test_classes)
+
+    def _produce(self, source, rank, world, n_query_hint, q):
+        """Producer thread: this rank's shard, `batch` episodes at a time, into the slots in turn."""
         from concurrent.futures import ThreadPoolExecutor
-        q: "queue.Queue" = queue.Queue(maxsize=2 * self.n_inflight)
+        try:
+            torch.cuda.set_device(self.device)  # this thread allocates pinned memory and streams
+            slots, bi = None, 0
 
-        def produce():
-            try:
+            def next_slot(n_query):
+                nonlocal slots, bi
+                if slots is None:
+                    slots = self._get_slots(n_query)
+                sl = slots[bi % len(slots)]
+                bi += 1
+                sl.issued.wait()            # the consumer has enqueued this slot's previous batch
+                sl.copied.synchronize()     # ... and its H2D copies have left the host buffers
+                sl.issued.clear()
+                return sl
+
+            if hasattr(source, "read_into") and hasattr(source, "__len__"):
+                mine = shard_indices(len(source), rank, world)
+                with ThreadPoolExecutor(self.n_readers) as pool:
+                    for s in range(0, len(mine), self.batch):
+                        idx = mine[s:s + self.batch]
+                        sl = next_slot(n_query_hint(source, idx[0]))
+                        list(pool.map(lambda t: self._read_into(source, sl, t[0], t[1]),
+                                      enumerate(idx)))
+                        q.put((sl, len(idx)))
+            else:
                 if hasattr(source, "item") and hasattr(source, "__len__"):
-                    mine = shard_indices(len(source), rank, world)
-                    with ThreadPoolExecutor(self.n_readers) as pool:
-                        for s in range(0, len(mine), self.batch):
-                            q.put(list(pool.map(source.item, mine[s:s + self.batch])))
+                    it = (source.item(i) for i in shard_indices(len(source), rank, world))
                 else:
-                    cur = []
-                    for i, item in enumerate(source):
-                        if i % world != rank:
-                            continue
-                        cur.append(item)
-                        if len(cur) == self.batch:
-                            q.put(cur)
-                            cur = []
-                    if cur:
-                        q.put(cur)
-                q.put(None)
-            except BaseException as e:  # surface reader errors in the consumer
-                q.put(e)
-
-        threading.Thread(target=produce, daemon=True).start()
-        while True:
-            b = q.get()
-            if b is None:
-                return
-            if isinstance(b, BaseException):
-                raise b
-            yield b
+                    it = (item for i, item in enumerate(source) if i % world == rank)
+                sl, n = None, 0
+                for data, classes in it:
+                    if sl is None:
+                        sl, n = next_slot(int(data[2].shape[0])), 0
+                    self._fill(sl, n, data, classes)
+                    n += 1
+                    if n == self.batch:
+                        q.put((sl, n))
+                        sl = None
+                if sl is not None:
+                    q.put((sl, n))
+            q.put(None)
+        except BaseException as e:  # surface reader errors in the consumer
+            q.put(e)
 
     # ---- the loop ---------------------------------------------------------------------------------
     def run(self, episodes, rank: int = 0, world: int = 1, logger=None,
@@ -163,6 +183,8 @@ class EpisodeEvaluator:
         logger: optional object with `.cprint(str)` (the reference's utils.logger); it gets the
         reference's progress line every `log_every` episodes (eval_noise.py:94-95) and the
         per-class IoU printout at the end (:64-68)."""
+        import queue
+        import threading
         from . import _lib, ops
         if isinstance(episodes, (list, tuple)) and episodes and hasattr(episodes[0], "support_x"):
             episodes = _EpisodeList(episodes)
@@ -170,31 +192,37 @@ class EpisodeEvaluator:
         dev = self.device
         counters = torch.zeros((3, n_slots), dtype=torch.int64, device=dev)
         loss_sum = torch.zeros((), dtype=torch.float64, device=dev)
-        last_loss = None
-        slots = None
-        done = 0
         cur = torch.cuda.current_stream(dev)
-        for bi, items in enumerate(self._batches(episodes, rank, world)):
-            n_query = int(items[0][0][2].shape[0])
-            if slots is None:
-                slots = self._get_slots(n_query)
-                cfg = self.model._cfg(n_query, mdns=bool(self.eval_mdns))
+        q: "queue.Queue" = queue.Queue()
+
+        def n_query_hint(source, index):
+            return int(source[index][2].shape[0])  # query_ptclouds of the first episode
+
+        with torch.cuda.device(dev):
+            threading.Thread(target=self._produce, args=(episodes, rank, world, n_query_hint, q),
+                             daemon=True).start()
+        prepared, last_loss, done = set(), None, 0
+        while True:
+            got = q.get()
+            if got is None:
+                break
+            if isinstance(got, BaseException):
+                raise got
+            sl, n = got
+            if id(sl) not in prepared:   # first use in this run: workspace, zeroed partial results
+                cfg = self.model._cfg(int(sl.h_qx.shape[1]), mdns=bool(self.eval_mdns))
                 need = _lib.lib().r3dfs_mpti_workspace(cfg, self.batch)
-                for sl in slots:
-                    if sl.ws is None or sl.ws.numel() < need:
-                        sl.ws = torch.empty(need, dtype=torch.uint8, device=dev)
-                    sl.counters = torch.zeros_like(counters)
-                    sl.loss_sum = torch.zeros_like(loss_sum)
-                    sl.stream.wait_stream(cur)
-            sl = slots[bi % len(slots)]
-            sl.copied.synchronize()  # the H2D copies of this slot's previous batch are done
-            for i, (data, classes) in enumerate(items):
-                self._fill(sl, i, data, classes)
-            n = len(items)
+                if sl.ws is None or sl.ws.numel() < need:
+                    sl.ws = torch.empty(need, dtype=torch.uint8, device=dev)
+                sl.counters = torch.zeros_like(counters)
+                sl.loss_sum = torch.zeros_like(loss_sum)
+                sl.stream.wait_stream(cur)
+                prepared.add(id(sl))
             with torch.cuda.stream(sl.stream):
                 for h, d in zip((sl.h_sx, sl.h_sy, sl.h_qx, sl.h_qy, sl.h_slot), sl.d):
                     d[:n].copy_(h[:n], non_blocking=True)
                 sl.copied.record(sl.stream)
+                sl.issued.set()
                 sx, sy, qx, qy, slot = (d[:n] for d in sl.d)
                 out = self.model.forward_episodes(sx.transpose(3, 4), sy, qx.transpose(2, 3), qy,
                                                   eval=self.eval_mdns, workspace=sl.ws)
@@ -208,8 +236,8 @@ class EpisodeEvaluator:
                 logger.cprint("[Eval] Iter: %d | Loss: %.4f | %s" % (
                     done + n, float(last_loss[-1]), str(datetime.now())))
             done += n
-        if slots is not None:
-            for sl in slots:
+        for sl in (self._slots or []):
+            if id(sl) in prepared:
                 cur.wait_stream(sl.stream)
                 counters += sl.counters
                 loss_sum += sl.loss_sum

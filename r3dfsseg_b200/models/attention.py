@@ -28,5 +28,5 @@ class SelfAttention(nn.Module):
         if self.out_channel != 64:
             raise NotImplementedError("the attention kernel is built for out_channel = 64")
         wqkv = torch.cat([self.q_map.weight, self.k_map.weight, self.v_map.weight], 0)
-        y = ops.attention(x.transpose(1, 2), wqkv.reshape(192, -1))
+        y = ops.op.attention(x.transpose(1, 2), wqkv.reshape(192, -1))
         return y.transpose(1, 2)

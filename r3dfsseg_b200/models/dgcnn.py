@@ -66,7 +66,7 @@ class _PointwiseStack(nn.Module):
             else:
                 s = None
                 t = cv.bias.detach().float().contiguous() if cv.bias is not None else None
-            h = ops.linear(h, w, s, t, act)
+            h = ops.op.linear(h.contiguous(), w, s, t, act)
         return h.reshape(lead, -1, h.shape[1]).transpose(1, 2).reshape(lead, h.shape[1], *spatial)
 
 
@@ -111,7 +111,7 @@ class DGCNN(nn.Module):
             (c1, b1, _), (c2, b2, _) = stages
             s1, t1 = ops.fold_bn(b1)
             s2, t2 = ops.fold_bn(b2)
-            x = ops.edgeconv(x, c1.weight, s1, t1, c2.weight, s2, t2, self.k)
+            x = ops.op.edgeconv(x, c1.weight, s1, t1, c2.weight, s2, t2, self.k).transpose(1, 2)
             outs.append(x)
         out = self.conv(torch.cat(outs, dim=1))
         if self.return_edgeconvs:

@@ -41,7 +41,7 @@ class BaseLearner(nn.Module):
         for i, seq in enumerate(self.convs):
             s, t = ops.fold_bn(seq[1], seq[0].bias)
             act = ops.ACT_RELU if i != self.num_convs - 1 else ops.ACT_NONE
-            h = ops.linear(h, seq[0].weight.reshape(seq[0].weight.shape[0], -1), s, t, act)
+            h = ops.op.linear(h.contiguous(), seq[0].weight.reshape(seq[0].weight.shape[0], -1), s, t, act)
         return h.reshape(B, N, -1).transpose(1, 2)
 
 
@@ -80,11 +80,22 @@ class MPTI_SelfAtten(nn.Module):
 
     # ---------------------------------------------------------------------------------------
     def _weights(self) -> ops.PackedWeights:
+        if torch.compiler.is_compiling():
+            # tracing (torch.compile / export): the packed tensors are graph inputs, built beforehand
+            if self._packed is None:
+                raise RuntimeError("call model.pack_weights() once before tracing the module")
+            return self._packed
         sig = tuple((t.data_ptr(), t._version) for t in self.state_dict(keep_vars=True).values())
         if self._packed is None or sig != self._packed_sig:
             self._packed = ops.PackedWeights(self)
             self._packed_sig = sig
         return self._packed
+
+    def pack_weights(self) -> ops.PackedWeights:
+        """Folds the BatchNorm statistics into per-channel scale/shift and packs the 31 weight
+        tensors the kernels read (done lazily in eager mode; call it once before torch.compile)."""
+        self._packed = None
+        return self._weights()
 
     def _cfg(self, n_query: int, mdns: bool):
         return ops.make_cfg(self.n_way, self.k_shot, n_query, self.n_points, self.n_subprototypes,
@@ -96,7 +107,8 @@ class MPTI_SelfAtten(nn.Module):
         if self.training:
             raise NotImplementedError("r3dfsseg_b200: stand-alone call in training mode; use "
                                       "forward(..., train=True) for the training step or .eval()")
-        return ops.features(self._weights(), x)
+        pw = self._weights()
+        return ops.op.features(x, pw.tensors, self.in_channels, int(self.encoder.k)).transpose(1, 2)
 
     # ---------------------------------------------------------------------------------------
     def forward_episodes(self, support_x, support_y, query_x, query_y=None, eval=True,
@@ -109,6 +121,18 @@ class MPTI_SelfAtten(nn.Module):
         if self.training:
             raise NotImplementedError("r3dfsseg_b200: stand-alone call in training mode; use "
                                       "forward(..., train=True) for the training step or .eval()")
+        if support_feat is None and stage_events is None and query_y is not None:
+            # the registered op r3dfs::mpti_forward (traceable: torch.compile, fake tensors)
+            pw = self._weights()
+            r = ops.op.mpti_forward(pw.tensors, self.in_channels, int(self.encoder.k), support_x,
+                                    support_y, query_x, query_y, self.n_subprototypes,
+                                    self.k_connect, float(self.sigma), self.lp_alpha, bool(eval),
+                                    self.cg_max_iter, self.cg_tol, workspace)
+            out = {"logits": r[0], "loss": r[1], "pred": r[2]}
+            if want_diag:
+                out["diag"] = {"proto_count": r[3], "clean_flag": r[4], "cg_iters": r[5],
+                               "cg_resid": r[6]}
+            return out
         cfg = self._cfg(query_x.shape[1], mdns=bool(eval))
         return ops.mpti_forward(self._weights(), cfg, support_x, support_y, query_x, query_y,
                                 want_diag=want_diag, workspace=workspace,
@@ -125,7 +149,7 @@ class MPTI_SelfAtten(nn.Module):
         contrast_loss, query_acc_LP, query_acc_original, clean_ratio_LP_avg,
         clean_ratio_original_avg); lp_loss / contrast_loss carry gradients to the parameters through
         r3dfs_mpti_train_backward.  The two clean-ratio entries are logging-only diagnostics in the
-        reference (:520-546); clean_ratio_original is computed, clean_ratio_LP is reported as NaN."""
+        reference (:514-552); both come from r3dfs_mpti_train_clean_ratio (NaN without gt_support_y)."""
         if train:
             if not self.training:
                 raise RuntimeError("forward(train=True) needs the module in .train() mode "
@@ -141,13 +165,10 @@ class MPTI_SelfAtten(nn.Module):
                 denom = float(self.n_way * self.n_points)
                 acc_lp = (pl == gq).sum().float() / denom
                 acc_orig = (query_y == gq).sum().float() / denom
-                ratio_orig = torch.zeros((), device=query_pred.device)
-                if gt_support_y is not None:
-                    for w in range(self.n_way):
-                        given = support_y[w].reshape(-1) == 1
-                        ratio_orig += (gt_support_y[w].reshape(-1)[given] == 1).float().mean()
-                    ratio_orig /= self.n_way
-                ratio_lp = torch.full((), float("nan"), device=query_pred.device)
+                ratio_lp = ratio_orig = torch.full((), float("nan"), device=query_pred.device)
+                if gt_support_y is not None:  # models/mpti.py:514-552 (logging-only diagnostics)
+                    from ..train import clean_ratios
+                    ratio_lp, ratio_orig = clean_ratios(self, support_y, gt_support_y)
             return query_pred, lp_loss, contrast, acc_lp, acc_orig, ratio_lp, ratio_orig
         if self.training:
             raise RuntimeError("call forward(..., train=True) in training mode, or .eval() first")

@@ -203,6 +203,7 @@ class PackedWeights:
         self.struct = w
         self.device = dev
         self._keep = keep
+        self.tensors = keep  # the 31 packed tensors in r3dfs_weights_t order (see _weights_struct)
 
 
 def features(pw: PackedWeights, x: torch.Tensor, want_level2: bool = False):
@@ -363,7 +364,7 @@ def make_cfg(n_way: int, k_shot: int, n_query: int, n_points: int, n_subprototyp
                       float(alpha), int(bool(mdns)), int(cg_max_iter), float(cg_tol))
 
 
-def mpti_forward(pw: Optional[PackedWeights], cfg: EpisodeCfg, support_x: torch.Tensor,
+def _mpti_forward_raw(pw: Optional[PackedWeights], cfg: EpisodeCfg, support_x: torch.Tensor,
                  support_y: torch.Tensor, query_x: torch.Tensor, query_y: Optional[torch.Tensor],
                  want_diag: bool = False, workspace: Optional[torch.Tensor] = None,
                  support_feat: Optional[torch.Tensor] = None,
@@ -535,9 +536,189 @@ def _(x, idx):
 @torch.library.custom_op("r3dfs::edgeconv", mutates_args=(), device_types="cuda")
 def _edgeconv_op(x: torch.Tensor, w1: torch.Tensor, s1: torch.Tensor, t1: torch.Tensor,
                  w2: torch.Tensor, s2: torch.Tensor, t2: torch.Tensor, k: int) -> torch.Tensor:
-    return edgeconv(x, w1, s1, t1, w2, s2, t2, k).contiguous()
+    """-> POINT-MAJOR (B, N, 64) (the kernel's layout; module code takes the transposed view)."""
+    return edgeconv(x, w1, s1, t1, w2, s2, t2, k).transpose(1, 2)
 
 
 @_edgeconv_op.register_fake
 def _(x, w1, s1, t1, w2, s2, t2, k):
-    return x.new_empty((x.shape[0], 64, x.shape[2]))
+    return x.new_empty((x.shape[0], x.shape[2], 64))
+
+
+@torch.library.custom_op("r3dfs::linear", mutates_args=(), device_types="cuda")
+def _linear_op(x: torch.Tensor, w: torch.Tensor, s: Optional[torch.Tensor],
+               t: Optional[torch.Tensor], act: int) -> torch.Tensor:
+    return linear(x, w, s, t, act)
+
+
+@_linear_op.register_fake
+def _(x, w, s, t, act):
+    return x.new_empty((x.shape[0], w.shape[0]))
+
+
+@torch.library.custom_op("r3dfs::attention", mutates_args=(), device_types="cuda")
+def _attention_op(x_pm: torch.Tensor, wqkv: torch.Tensor) -> torch.Tensor:
+    return attention(x_pm, wqkv)
+
+
+@_attention_op.register_fake
+def _(x_pm, wqkv):
+    return x_pm.new_empty((x_pm.shape[0], x_pm.shape[1], 64))
+
+
+def _weights_struct(tensors: Sequence[torch.Tensor], in_dim: int, dgcnn_k: int) -> Weights:
+    """r3dfs_weights_t over the 31 packed tensors in PackedWeights order."""
+    if len(tensors) != 31:
+        raise ValueError("expected the 31 packed weight tensors of PackedWeights")
+    w = Weights()
+    w.in_dim, w.dgcnn_k = int(in_dim), int(dgcnn_k)
+    it = iter(int(t.data_ptr()) for t in tensors)
+    for i in range(3):
+        w.ec_w1[i], w.ec_s1[i], w.ec_t1[i] = next(it), next(it), next(it)
+        w.ec_w2[i], w.ec_s2[i], w.ec_t2[i] = next(it), next(it), next(it)
+    for i in range(2):
+        w.mlp_w[i], w.mlp_s[i], w.mlp_t[i] = next(it), next(it), next(it)
+    for i in range(2):
+        w.bl_w[i], w.bl_s[i], w.bl_t[i] = next(it), next(it), next(it)
+    w.att_wqkv = next(it)
+    return w
+
+
+class _WeightsView:
+    """What `features` / `mpti_forward` need of a PackedWeights, rebuilt from tensors inside an op."""
+
+    def __init__(self, tensors, in_dim, dgcnn_k):
+        self.struct = _weights_struct(tensors, in_dim, dgcnn_k)
+        self._keep = list(tensors)
+
+
+@torch.library.custom_op("r3dfs::features", mutates_args=(), device_types="cuda")
+def _features_op(x: torch.Tensor, weights: Sequence[torch.Tensor], in_dim: int,
+                 dgcnn_k: int) -> torch.Tensor:
+    """getFeatures -> POINT-MAJOR (B, N, 192)."""
+    return features(_WeightsView(weights, in_dim, dgcnn_k), x).transpose(1, 2)
+
+
+@_features_op.register_fake
+def _(x, weights, in_dim, dgcnn_k):
+    return x.new_empty((x.shape[0], x.shape[2], 192))
+
+
+@torch.library.custom_op("r3dfs::fps", mutates_args=(), device_types="cuda")
+def _fps_op(feat: torch.Tensor, set_off: torch.Tensor, set_n: torch.Tensor, m_max: int,
+            n_cap: int, impl: int) -> torch.Tensor:
+    return fps(feat, set_off, set_n, m_max, n_cap if n_cap > 0 else None, impl)
+
+
+@_fps_op.register_fake
+def _(feat, set_off, set_n, m_max, n_cap, impl):
+    return feat.new_empty((set_off.numel(), m_max), dtype=torch.int32)
+
+
+@torch.library.custom_op("r3dfs::multi_prototypes", mutates_args=(), device_types="cuda")
+def _multi_prototypes_op(feat: torch.Tensor, set_off: torch.Tensor, set_n: torch.Tensor,
+                         k: int) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
+    return multi_prototypes(feat, set_off, set_n, k)
+
+
+@_multi_prototypes_op.register_fake
+def _(feat, set_off, set_n, k):
+    n = set_off.numel()
+    i32 = dict(dtype=torch.int32)
+    return (feat.new_empty((n, k + 1, feat.shape[1])), feat.new_empty((n,), **i32),
+            feat.new_empty((feat.shape[0],), **i32), feat.new_empty((n, k + 1), **i32))
+
+
+@torch.library.custom_op("r3dfs::mdns", mutates_args=(), device_types="cuda")
+def _mdns_op(support_x: torch.Tensor, support_y: torch.Tensor, support_feat: torch.Tensor
+             ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
+    o = mdns(support_x, support_y, support_feat)
+    return o["keep"], o["clean_flag"], o["cell_mean"], o["cell_count"]
+
+
+@_mdns_op.register_fake
+def _(support_x, support_y, support_feat):
+    E, nw, ks = support_x.shape[:3]
+    return (support_x.new_empty((E, nw, ks), dtype=torch.int32), support_x.new_empty((E, nw, ks)),
+            support_x.new_empty((E, nw, ks, 5, 192)),
+            support_x.new_empty((E, nw, ks, 5), dtype=torch.int32))
+
+
+@torch.library.custom_op("r3dfs::affinity_knn", mutates_args=(), device_types="cuda")
+def _affinity_knn_op(node_feat: torch.Tensor, valid: torch.Tensor, k: int,
+                     sigma: float) -> Tuple[torch.Tensor, torch.Tensor]:
+    return affinity_knn(node_feat, valid, k, sigma)
+
+
+@_affinity_knn_op.register_fake
+def _(node_feat, valid, k, sigma):
+    G, n = node_feat.shape[:2]
+    return node_feat.new_empty((G, n, k), dtype=torch.int32), node_feat.new_empty((G, n, k))
+
+
+@torch.library.custom_op("r3dfs::label_propagate", mutates_args=(), device_types="cuda")
+def _label_propagate_op(nbr: torch.Tensor, sim: torch.Tensor, valid: torch.Tensor, Y: torch.Tensor,
+                        alpha: float, tol: float, max_iter: int
+                        ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    return label_propagate(nbr, sim, valid, Y, alpha, tol, max_iter)
+
+
+@_label_propagate_op.register_fake
+def _(nbr, sim, valid, Y, alpha, tol, max_iter):
+    G = nbr.shape[0]
+    return (sim.new_empty(Y.shape), sim.new_empty((G,), dtype=torch.int32), sim.new_empty((G,)))
+
+
+@torch.library.custom_op("r3dfs::mpti_forward", mutates_args=("workspace",), device_types="cuda")
+def _mpti_forward_op(weights: Sequence[torch.Tensor], in_dim: int, dgcnn_k: int,
+                     support_x: torch.Tensor, support_y: torch.Tensor, query_x: torch.Tensor,
+                     query_y: torch.Tensor, n_subprototypes: int, k_connect: int, sigma: float,
+                     alpha: float, mdns: bool, cg_max_iter: int, cg_tol: float,
+                     workspace: Optional[torch.Tensor]
+                     ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor,
+                                torch.Tensor, torch.Tensor, torch.Tensor]:
+    """The whole episode batch (reference models/mpti.py:414-577, eval) as ONE op:
+    -> (logits (E, n_query, N, n_way+1), loss (E), pred (E, n_query, N) int32, proto_count (E, n_way+1)
+    int32, clean_flag (E, n_way, k_shot), cg_iters (E) int32, cg_resid (E))."""
+    E, n_way, k_shot, _, N = support_x.shape
+    cfg = make_cfg(n_way, k_shot, query_x.shape[1], N, n_subprototypes, k_connect, sigma, alpha,
+                   mdns, cg_max_iter, cg_tol)
+    out = _mpti_forward_raw(_WeightsView(weights, in_dim, dgcnn_k), cfg, support_x, support_y,
+                            query_x, query_y, want_diag=True, workspace=workspace)
+    d = out["diag"]
+    return (out["logits"], out["loss"], out["pred"], d["proto_count"], d["clean_flag"],
+            d["cg_iters"], d["cg_resid"])
+
+
+@_mpti_forward_op.register_fake
+def _(weights, in_dim, dgcnn_k, support_x, support_y, query_x, query_y, n_subprototypes, k_connect,
+      sigma, alpha, mdns, cg_max_iter, cg_tol, workspace):
+    E, n_way, k_shot, _, N = support_x.shape
+    nq = query_x.shape[1]
+    f, i32 = support_x.new_empty, dict(dtype=torch.int32)
+    return (f((E, nq, N, n_way + 1)), f((E,)), f((E, nq, N), **i32), f((E, n_way + 1), **i32),
+            f((E, n_way, k_shot)), f((E,), **i32), f((E,)))
+
+
+# the registered ops, for module code (traceable by torch.compile / fake tensors)
+op = torch.ops.r3dfs
+
+
+def mpti_forward(pw: Optional[PackedWeights], cfg: EpisodeCfg, support_x: torch.Tensor,
+                 support_y: torch.Tensor, query_x: torch.Tensor, query_y: Optional[torch.Tensor],
+                 want_diag: bool = False, workspace: Optional[torch.Tensor] = None,
+                 support_feat: Optional[torch.Tensor] = None,
+                 query_feat: Optional[torch.Tensor] = None,
+                 stage_events: Optional[Sequence["torch.cuda.Event"]] = None):
+    """E episodes in one call (see _mpti_forward_raw).  The plain case goes through the registered
+    op `r3dfs::mpti_forward`; stage events and precomputed features are eager-only diagnostics."""
+    if stage_events is not None or support_feat is not None or query_y is None or pw is None:
+        return _mpti_forward_raw(pw, cfg, support_x, support_y, query_x, query_y, want_diag,
+                                 workspace, support_feat, query_feat, stage_events)
+    r = op.mpti_forward(pw.tensors, pw.struct.in_dim, pw.struct.dgcnn_k, support_x, support_y,
+                        query_x, query_y, cfg.n_subprototypes, cfg.k_connect, cfg.sigma, cfg.alpha,
+                        bool(cfg.mdns), cfg.cg_max_iter, cfg.cg_tol, workspace)
+    out = {"logits": r[0], "loss": r[1], "pred": r[2]}
+    if want_diag:
+        out["diag"] = {"proto_count": r[3], "clean_flag": r[4], "cg_iters": r[5], "cg_resid": r[6]}
+    return out

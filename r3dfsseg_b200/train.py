@@ -223,6 +223,23 @@ def train_episode(model, support_x, support_y, query_x, query_y, support_flag,
     return logits.transpose(1, 2), lp, ct
 
 
+def clean_ratios(model, support_y: torch.Tensor, gt_support_y: torch.Tensor):
+    """(clean_ratio_LP_avg, clean_ratio_original_avg) of the model's last training forward
+    (reference models/mpti.py:514-552), as 0-d device tensors."""
+    fs = flat_state(model)
+    ws = model._train_ws
+    dev = ws.device
+    cfg = model._cfg(model._last_n_query, mdns=False)
+    sy = support_y.to(device=dev, dtype=torch.int32).contiguous()
+    gy = gt_support_y.to(device=dev, dtype=torch.int32).contiguous()
+    out = torch.empty(2, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        check(_lib.lib().r3dfs_mpti_train_clean_ratio(
+            C.byref(cfg), fs.in_dim, int(model.encoder.k), ops._p(sy), ops._p(gy), ops._p(out),
+            ops._p(ws), ws.numel(), ops._stream()), "r3dfs_mpti_train_clean_ratio")
+    return out[0], out[1]
+
+
 def export_decisions(model) -> Dict[str, object]:
     """Discrete decisions of the model's last training forward (r3dfs_mpti_train_export), as CPU
     tensors in the reference's own numbering — what a teacher-forced parity run needs:

@@ -707,6 +707,27 @@ def _cuda_features(fixture_sd, c, ep):
     return sf, qf
 
 
+def test_module_traces_under_torch_compile_fullgraph(fixture_sd):
+    """The whole drop-in surface is registered as `r3dfs::` custom ops with fake kernels:
+    torch.compile(fullgraph=True) traces MPTI_SelfAtten.forward (eval) and the stand-alone
+    getFeatures without a graph break, and the compiled module returns the eager results."""
+    from r3dfsseg_b200.models import MPTI_SelfAtten
+    m = MPTI_SelfAtten(default_args(2, 5))
+    m.load_state_dict(fixture_sd)
+    m = m.to(DEV).eval()
+    ep = make_episode(21, 2, 5, noise_ratio=0.4)
+    args = [t.to(DEV) for t in (ep.support_x, ep.support_y, ep.query_x, ep.query_y)]
+    with torch.no_grad():
+        ref_pred, ref_loss = m(*args, gt_support_y=ep.gt_support_y.to(DEV), eval=True)
+        ref_feat = m.getFeatures(args[2])
+        m.pack_weights()
+        fwd = torch.compile(lambda sx, sy, qx, qy: m(sx, sy, qx, qy, eval=True), fullgraph=True)
+        pred, loss = fwd(*args)
+        feat = torch.compile(m.getFeatures, fullgraph=True)(args[2])
+    assert torch.equal(pred, ref_pred) and torch.equal(loss, ref_loss)
+    assert torch.equal(feat, ref_feat)
+
+
 def test_episode_batch_equals_single_and_is_deterministic(model):
     m = model(2, 5)
     eps = [make_episode(s, 2, 5, noise_ratio=0.4 if s % 2 else 0.0) for s in (11, 12, 13)]
@@ -880,8 +901,9 @@ def test_episode_folder_streaming_driver_and_stage_batch(model, tmp_path):
     m = model(2, 5)
     learner = MPTILearner_V3(default_args(2, 5), mode="test", model=m)
     eps = [make_episode(400 + i, 2, 5, noise_ratio=0.4 if i % 2 else 0.0) for i in range(7)]
-    for i, e in enumerate(eps):
-        IO.write_episode(str(tmp_path / ("%04d.h5" % i)), IO.episode_arrays(e))
+    for i, e in enumerate(eps):  # both containers: .npz (the .h5 stand-in) and the raw .r3ep
+        IO.write_episode(str(tmp_path / ("%04d%s" % (i, ".h5" if i % 2 else ".r3ep"))),
+                         IO.episode_arrays(e))
     folder = IO.EpisodeFolder(str(tmp_path))
     assert len(folder) == 7
     test_classes = list(range(6))

@@ -55,13 +55,27 @@ def test_train_step_teacher_forced(fixture_sd, seed, n_way, noise, p_drop):
         kq = T.dropout_mask(99, (n_way, 2048, 2048), p_drop, DEV)
         assert abs(float(ks.float().mean()) - (1 - p_drop)) < 1e-3
     qp, lp, ct = _run_cuda(m, ep, p_drop, ks, kq)
+    ratio_lp, ratio_orig = (float(x) for x in T.clean_ratios(m, ep.support_y, ep.gt_support_y))
     forced = T.export_decisions(m)
     P, running = TO.split_state_dict(fixture_sd)
     out = TO.forward_train(P, ep.support_x, ep.support_y, ep.query_x, ep.query_y, ep.support_flag,
                            running=running, keep_mask_support=None if ks is None else ks.cpu(),
                            keep_mask_query=None if kq is None else kq.cpu(), dropout_p=p_drop,
-                           forced=forced)
+                           forced=forced, keep=True)
     (out["lp_loss"] + 0.1 * out["contrast_loss"]).backward()
+    # the reference's logging diagnostics (models/mpti.py:514-552) from the oracle's Z and the
+    # exported assignments: exact up to argmax ties on the prototype rows
+    Zp, pc, acc_lp, acc_or = out["Z"].detach(), forced["proto_cnt"], [], []
+    for w in range(n_way):
+        rows = Zp[sum(pc[:1 + w]):sum(pc[:2 + w])]
+        proto_pred = (rows.argmax(1) == w + 1).long()
+        point_pred = proto_pred[forced["assign"][1 + w]]
+        fg = ep.support_y[w].reshape(-1) == 1
+        gt = ep.gt_support_y[w].reshape(-1)[fg].long()
+        acc_lp.append(float((point_pred == gt).float().mean()))
+        acc_or.append(float((gt == 1).float().mean()))
+    assert abs(ratio_lp - sum(acc_lp) / n_way) < 2e-3, (ratio_lp, acc_lp)
+    assert abs(ratio_orig - sum(acc_or) / n_way) < 1e-6, (ratio_orig, acc_or)
     assert abs(lp - float(out["lp_loss"])) <= 1e-4 * abs(float(out["lp_loss"]))
     assert abs(ct - float(out["contrast_loss"])) <= 1e-4 * abs(float(out["contrast_loss"]))
     ref_q = out["query_pred"].detach()
@@ -81,6 +95,24 @@ def test_train_step_teacher_forced(fixture_sd, seed, n_way, noise, p_drop):
             assert float((v.cpu() - running[k]).abs().max()) < 1e-4, k
         else:
             assert int(v) == int(running[k]), k
+
+
+def test_forward_train_tuple_matches_reference_diagnostics(fixture_sd):
+    """The drop-in 7-tuple of forward(train=True) (models/mpti.py:575): the four logging diagnostics
+    against the numbers the reference itself printed for the same episode (golden_train.pt)."""
+    gold = torch.load(os.path.join(os.path.dirname(__file__), "golden", "golden_train.pt"))
+    g = gold["train_s3dis_2way_5shot_noisy"]
+    ep = make_episode(g["seed"], g["n_way"], g["k_shot"], dataset=g["dataset"], noise_ratio=g["noise_ratio"])
+    m = _model(fixture_sd)
+    m.att_learner.dropout.p = 0.0
+    out = m(ep.support_x.to(DEV), ep.support_y.to(DEV), ep.query_x.to(DEV), ep.query_y.to(DEV),
+            gt_support_y=ep.gt_support_y.to(DEV), gt_query_y=ep.query_y.to(DEV), train=True,
+            support_flag=ep.support_flag.to(DEV))
+    assert len(out) == 7
+    got = [float(x) for x in out[3:7]]
+    assert not any(v != v for v in got)                       # no NaN placeholder any more
+    for a, b in zip(got, g["diagnostics"]):
+        assert abs(a - b) < 5e-3, (got, g["diagnostics"])     # free-running: ties may move a prototype
 
 
 def test_train_step_free_running_vs_reference_golden(fixture_sd):

@@ -235,6 +235,34 @@ def test_replica_state_broadcast_and_bn_average_gloo_world2():
     assert sorted(results) == [(0, True), (1, True)]
 
 
+def test_raw_episode_container_round_trip_and_read_into(tmp_path):
+    """`.r3ep`: the reference's eight datasets as one flat file that reader threads read straight
+    into (pinned) staging rows; converting a folder of .npz/.h5 episodes keeps every array."""
+    from r3dfsseg_b200 import episode_io as IO
+    from r3dfsseg_b200.episodes import make_episode
+    eps = [make_episode(s, 3, 5, dataset="scannet", noise_ratio=0.4) for s in (1, 2)]
+    src, dst = tmp_path / "npz", tmp_path / "raw"
+    src.mkdir()
+    for i, e in enumerate(eps):
+        IO.write_episode(str(src / ("%d.h5" % i)), IO.episode_arrays(e))
+    assert IO.convert_folder(str(src), str(dst)) == 2
+    a, b = IO.EpisodeFolder(str(src)), IO.EpisodeFolder(str(dst))
+    assert all(n.endswith(IO.RAW_EXT) for n in b.file_names)
+    for i in range(2):
+        for x, y in zip(a[i], b[i]):
+            assert x.dtype == y.dtype and np.array_equal(x, y)
+        stage = {"support_ptclouds": np.zeros((4, 3, 5, 2048, 9), np.float32),
+                 "query_labels": np.zeros((4, 3, 2048), np.int64)}
+        for folder in (a, b):
+            cls = folder.read_into(i, {k: v[2] for k, v in stage.items()})
+            assert np.array_equal(cls, eps[i].sampled_classes)
+            assert np.array_equal(stage["support_ptclouds"][2], a[i][0])
+            assert np.array_equal(stage["query_labels"][2], a[i][3])
+            assert not stage["support_ptclouds"][1].any()
+    with pytest.raises(ValueError):
+        b.read_into(0, {"support_ptclouds": np.zeros((2, 5, 2048, 9), np.float32)})
+
+
 def test_episode_file_round_trip(tmp_path):
     """The reference's episode schema (dataloaders/loader.py:1687-1721) survives write -> read, and
     the collate leaves the clouds point-major behind (.., 9, N) views (loader.py:1676-1684)."""
@@ -374,3 +402,39 @@ def test_checkpoint_formats_round_trip_with_the_reference_optimizer(tmp_path):
         ck.load_model_checkpoint(m2, str(tmp_path / "nowhere"), mode="test")
     with pytest.raises(ValueError):
         ck.load_pretrain_checkpoint(m3, None)
+
+
+def test_custom_ops_have_fake_kernels_for_shape_inference():
+    """Every op of the `r3dfs::` namespace carries a fake (meta) kernel, so the module code can be
+    traced without touching a GPU: shapes/dtypes under FakeTensorMode with CUDA-device fakes."""
+    from torch._subclasses.fake_tensor import FakeTensorMode
+    from r3dfsseg_b200 import ops  # noqa: F401  (registers the ops)
+    op = torch.ops.r3dfs
+    with FakeTensorMode():
+        dev = "cuda"
+        f = lambda *s, dt=torch.float32: torch.empty(s, dtype=dt, device=dev)
+        E, nw, ks, N, nq = 3, 2, 5, 2048, 2
+        w = [f(4)] * 31
+        r = op.mpti_forward(w, 9, 20, f(E, nw, ks, 9, N), f(E, nw, ks, N, dt=torch.int32),
+                            f(E, nq, 9, N), f(E, nq, N, dt=torch.int64), 100, 200, 1.0, 0.99, True,
+                            200, 1e-6, None)
+        assert [tuple(t.shape) for t in r] == [(E, nq, N, 3), (E,), (E, nq, N), (E, 3), (E, nw, ks),
+                                               (E,), (E,)]
+        assert r[2].dtype == torch.int32 and r[0].device.type == "cuda"
+        assert op.knn(f(4, 9, 100), 20).shape == (4, 100, 20)
+        assert op.edge_feature(f(4, 9, 100), f(4, 100, 20, dt=torch.int64)).shape == (4, 18, 100, 20)
+        assert op.edgeconv(f(4, 9, 100), f(64, 18), f(64), f(64), f(64, 64), f(64), f(64), 20).shape \
+            == (4, 100, 64)
+        assert op.linear(f(1000, 192), f(512, 192), f(512), f(512), 2).shape == (1000, 512)
+        assert op.attention(f(4, 100, 256), f(192, 256)).shape == (4, 100, 64)
+        assert op.features(f(4, 9, 100), w, 9, 20).shape == (4, 100, 192)
+        i32 = torch.int32
+        assert op.fps(f(500, 192), f(2, dt=i32), f(2, dt=i32), 101, 0, 0).shape == (2, 101)
+        p, c, a, sd = op.multi_prototypes(f(500, 192), f(2, dt=i32), f(2, dt=i32), 100)
+        assert p.shape == (2, 101, 192) and c.shape == (2,) and a.shape == (500,) and sd.shape == (2, 101)
+        k, cf, cm, cc = op.mdns(f(E, nw, ks, 9, N), f(E, nw, ks, N, dt=i32), f(E, nw * ks * N, 192))
+        assert k.shape == (E, nw, ks) and cm.shape == (E, nw, ks, 5, 192) and cc.dtype == i32
+        nb, sm = op.affinity_knn(f(2, 700, 192), f(2, 700, dt=torch.uint8), 200, 1.0)
+        assert nb.shape == (2, 700, 200) and nb.dtype == i32 and sm.shape == (2, 700, 200)
+        z, it, rs = op.label_propagate(nb, sm, f(2, 700, dt=torch.uint8), f(2, 700, 3), 0.99, 1e-6, 200)
+        assert z.shape == (2, 700, 3) and it.dtype == i32 and rs.shape == (2,)
