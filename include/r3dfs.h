@@ -228,6 +228,16 @@ int r3dfs_label_propagate(const int32_t* nbr, const float* sim, const uint8_t* v
                           int max_iter, float* Z, int32_t* iters_out, float* resid_out, void* ws,
                           size_t ws_bytes, r3dfs_stream_t stream);
 
+/* The same system (I - alpha S) Z = Y solved by a DENSE FP64 Cholesky factorisation on the GPU —
+ * the in-library cross-check of the conjugate-gradient solve above (BASELINE.json north_star item 4;
+ * the reference inverts the dense matrix, models/mpti.py:775).  Same graph inputs; Z (G, n, n_cls)
+ * fp32 (rounded from the FP64 solution); info (G) int32, nullable: 0, or 1 + the first pivot that
+ * was not positive.  n <= 8192; needs 8 n^2 bytes per graph: not meant for the timed path. */
+size_t r3dfs_lp_cholesky_workspace(int n_graphs, int64_t n_max, int k, int n_cls);
+int r3dfs_lp_cholesky(const int32_t* nbr, const float* sim, const uint8_t* valid, int n_graphs,
+                      int64_t n_max, int k, const float* Y, int n_cls, float alpha, float* Z,
+                      int32_t* info, void* ws, size_t ws_bytes, r3dfs_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * Whole episode(s): MPTI_SelfAtten.forward, eval path (reference models/mpti.py:414-577)
  * ---------------------------------------------------------------------------------------- */

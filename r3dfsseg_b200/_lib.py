@@ -98,6 +98,8 @@ SIGNATURES = {
     "r3dfs_label_propagate_workspace": (sz, [i32, i64, i32, i32]),
     "r3dfs_label_propagate": (C.c_int, [vp, vp, vp, i32, i64, i32, vp, i32, f32, f32, i32, vp, vp,
                                         vp, vp, sz, vp]),
+    "r3dfs_lp_cholesky_workspace": (sz, [i32, i64, i32, i32]),
+    "r3dfs_lp_cholesky": (C.c_int, [vp, vp, vp, i32, i64, i32, vp, i32, f32, vp, vp, vp, sz, vp]),
     "r3dfs_mpti_workspace": (sz, [C.POINTER(EpisodeCfg), i32]),
     "r3dfs_mpti_forward": (C.c_int, [C.POINTER(EpisodeCfg), C.POINTER(Weights), i32,
                                      vp, i64, i64, i64, i64, vp,

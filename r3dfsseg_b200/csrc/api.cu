@@ -534,6 +534,46 @@ int r3dfs_label_propagate(const int32_t* nbr, const float* sim, const uint8_t* v
                                 scratch, scratch_bytes);
 }
 
+// ---- dense FP64 Cholesky solve of the same system (cross-check of the CG solve) -----------------------
+size_t r3dfs_lp_cholesky_workspace(int n_graphs, int64_t n_max, int k, int n_cls) {
+  if (n_graphs <= 0 || n_max <= 0 || k <= 0) return 0;
+  return r3dfs_label_propagate_workspace(n_graphs, n_max, k, n_cls) +
+         lp_cholesky_scratch_bytes(n_graphs, (int)n_max) + 1024;
+}
+
+int r3dfs_lp_cholesky(const int32_t* nbr, const float* sim, const uint8_t* valid, int n_graphs,
+                      int64_t n_max, int k, const float* Y, int n_cls, float alpha, float* Z,
+                      int32_t* info_out, void* wsp, size_t ws_bytes, r3dfs_stream_t stream) {
+  if (!nbr || !sim || !valid || !Y || !Z || !wsp || n_graphs <= 0 || n_max <= 0 || k <= 0)
+    return R3DFS_E_BADARG;
+  if (n_graphs > 65535 || n_max > 8192) return R3DFS_E_UNSUPPORTED;
+  if (ws_bytes < r3dfs_lp_cholesky_workspace(n_graphs, n_max, k, n_cls)) return R3DFS_E_WORKSPACE;
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t G = n_graphs, n = n_max;
+  WsBump ws(wsp, ws_bytes);
+  float* sv = ws.take<float>(G * n * k);
+  int32_t* in_src = ws.take<int32_t>(G * n * k);
+  float* in_w = ws.take<float>(G * n * k);
+  int32_t* in_cnt = ws.take<int32_t>(G * (n + 1));
+  int32_t* in_ptr = ws.take<int32_t>(G * (n + 1));
+  float* dinv = ws.take<float>(G * (n + 1));
+  int32_t* rowptr = ws.take<int32_t>(G * n);
+  int32_t* rowlen = ws.take<int32_t>(G * n);
+  int32_t* cursor = ws.take<int32_t>(G);
+  uint16_t* mcol = ws.take<uint16_t>(G * n * lp_rowcap(k));
+  float* mval = ws.take<float>(G * n * lp_rowcap(k));
+  const size_t scratch_bytes = lp_scratch_bytes(G, n, k);
+  unsigned char* scratch = ws.take<unsigned char>(scratch_bytes);
+  unsigned char* dense = ws.take<unsigned char>(lp_cholesky_scratch_bytes(n_graphs, (int)n_max));
+  if (!ws.ok()) return R3DFS_E_WORKSPACE;
+  cudaError_t ce = cudaMemcpyAsync(sv, sim, sizeof(float) * G * n * k, cudaMemcpyDeviceToDevice, st);
+  if (ce != cudaSuccess) return (int)ce;
+  return launch_label_propagate(nbr, sv, valid, n_graphs, (int)n_max, k, Y, n_cls, alpha, 0.f, 0,
+                                in_cnt, in_ptr, in_src, in_w, dinv, rowptr, rowlen, cursor, mcol,
+                                mval, Z, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, st,
+                                nullptr, scratch, scratch_bytes, false, dense, info_out);
+}
+
 // ---- confusion counters ----------------------------------------------------------------------------
 int r3dfs_confusion_accumulate(const int32_t* pred, const int64_t* gt, const int32_t* class_slot,
                                int n_episodes, int n_way, int64_t pts_per_episode, int n_slots,

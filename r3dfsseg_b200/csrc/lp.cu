@@ -2072,7 +2072,8 @@ int launch_label_propagate(const int32_t* nbr, float* sim, const uint8_t* valid,
                            float* dinv, int32_t* rowptr, int32_t* rowlen, int32_t* cursor,
                            uint16_t* mcol, float* mval, float* Z, float* X, float* R, float* P,
                            float* AP, int32_t* iters_out, float* resid_out, cudaStream_t st,
-                           const StageRec* sr, void* scratch, size_t scratch_bytes, bool latency) {
+                           const StageRec* sr, void* scratch, size_t scratch_bytes, bool latency,
+                           void* dense_scratch, int32_t* dense_info) {
   if (nc > CG_MAXC || nc < 1 || nn > 8192) return R3DFS_E_UNSUPPORTED;
   cudaError_t e;
   const int64_t edges = (int64_t)nn * k;
@@ -2130,6 +2131,12 @@ int launch_label_propagate(const int32_t* nbr, float* sim, const uint8_t* valid,
   R3DFS_CHECK_LAUNCH();
   if (sr) sr->mark(R3DFS_ST_SYM, st);
 
+  if (dense_scratch) {
+    R3DFS_TRY(launch_lp_cholesky_solve(rowptr, rowlen, mcol, mval, valid, G, nn, k, Y, nc, alpha, Z,
+                                       dense_scratch, dense_info, st));
+    if (sr) sr->mark(R3DFS_ST_CG, st);
+    return 0;
+  }
   // the in-edge scratch (bit matrix, ranks) is dead by now: the solver re-uses it
   R3DFS_TRY(launch_lp_solve(rowptr, rowlen, mcol, mval, valid, G, nn, k, Y, nc, alpha, tol, max_iter,
                             Z, X, R, P, AP, iters_out, resid_out, st, latency, scratch,

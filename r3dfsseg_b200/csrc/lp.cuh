@@ -12,7 +12,15 @@ int launch_label_propagate(const int32_t* nbr, float* sim, const uint8_t* valid,
                            uint16_t* mcol, float* mval, float* Z, float* X, float* R, float* P,
                            float* AP, int32_t* iters_out, float* resid_out, cudaStream_t st,
                            const StageRec* sr = nullptr, void* scratch = nullptr,
-                           size_t scratch_bytes = 0, bool latency = false);
+                           size_t scratch_bytes = 0, bool latency = false,
+                           void* dense_scratch = nullptr, int32_t* dense_info = nullptr);
+// dense_scratch (lp_cholesky_scratch_bytes(G, nn) bytes): solve by the dense FP64 Cholesky of
+// lp_dense.cu instead of conjugate gradients (cross-check; dense_info[g] != 0: not positive definite)
+size_t lp_cholesky_scratch_bytes(int G, int nn);
+int launch_lp_cholesky_solve(const int32_t* rowptr, const int32_t* rowlen, const uint16_t* mcol,
+                             const float* mval, const uint8_t* valid, int G, int nn, int k,
+                             const float* Y, int nc, float alpha, float* Z, void* scratch,
+                             int32_t* info_out, cudaStream_t st);
 // scratch (optional): >= 6 * G * nn * ceil(nn / 32) bytes enables the sort-free in-edge build
 int launch_lp_solve(const int32_t* rowptr, const int32_t* rowlen, const uint16_t* mcol,
                     const float* mval, const uint8_t* valid, int G, int nn, int k, const float* Y,

@@ -354,6 +354,28 @@ def label_propagate(nbr: torch.Tensor, sim: torch.Tensor, valid: torch.Tensor, Y
     return Z, iters, resid
 
 
+def lp_cholesky(nbr: torch.Tensor, sim: torch.Tensor, valid: torch.Tensor, Y: torch.Tensor,
+                alpha: float = 0.99):
+    """The label-propagation system solved by a dense FP64 Cholesky factorisation on the GPU — the
+    cross-check of `label_propagate`'s conjugate gradients.  Returns (Z fp32, info int32 (G))."""
+    dev = _need_cuda(nbr, sim, valid, Y)
+    nbr = nbr.to(torch.int32).contiguous()
+    sim = _f32(sim).contiguous()
+    valid = valid.to(torch.uint8).contiguous()
+    Y = _f32(Y).contiguous()
+    G, n, k = nbr.shape
+    nc = Y.shape[-1]
+    Z = torch.empty((G, n, nc), dtype=torch.float32, device=dev)
+    info = torch.zeros((G,), dtype=torch.int32, device=dev)
+    L = _lib.lib()
+    ws = _ws(L.r3dfs_lp_cholesky_workspace(G, n, k, nc), dev)
+    with torch.cuda.device(dev):
+        check(L.r3dfs_lp_cholesky(_p(nbr), _p(sim), _p(valid), G, n, k, _p(Y), nc, float(alpha),
+                                  _p(Z), _p(info), _p(ws), ws.numel(), _stream()),
+              "r3dfs_lp_cholesky")
+    return Z, info
+
+
 # ------------------------------------------------------------------------------------------------
 # whole episodes
 # ------------------------------------------------------------------------------------------------
@@ -667,6 +689,17 @@ def _label_propagate_op(nbr: torch.Tensor, sim: torch.Tensor, valid: torch.Tenso
 def _(nbr, sim, valid, Y, alpha, tol, max_iter):
     G = nbr.shape[0]
     return (sim.new_empty(Y.shape), sim.new_empty((G,), dtype=torch.int32), sim.new_empty((G,)))
+
+
+@torch.library.custom_op("r3dfs::lp_cholesky", mutates_args=(), device_types="cuda")
+def _lp_cholesky_op(nbr: torch.Tensor, sim: torch.Tensor, valid: torch.Tensor, Y: torch.Tensor,
+                    alpha: float) -> Tuple[torch.Tensor, torch.Tensor]:
+    return lp_cholesky(nbr, sim, valid, Y, alpha)
+
+
+@_lp_cholesky_op.register_fake
+def _(nbr, sim, valid, Y, alpha):
+    return sim.new_empty(Y.shape), sim.new_empty((nbr.shape[0],), dtype=torch.int32)
 
 
 @torch.library.custom_op("r3dfs::mpti_forward", mutates_args=("workspace",), device_types="cuda")

@@ -474,6 +474,38 @@ def test_label_propagate_vs_dense_solve():
     assert err_cg < 1e-4, (err_cg, err_ref)
     assert (Z[vi].argmax(1) == Z64.argmax(1)).float().mean() > 0.999
     assert (Z[valid == 0] == 0).all()
+    # the in-library cross-check: dense FP64 Cholesky on the GPU (r3dfs_lp_cholesky) — equals the
+    # CPU FP64 solve to FP32 output rounding, and brackets the CG answer the same way
+    Zc, info = ops.lp_cholesky(nbr, sim, valid[None].to(DEV), Y[None].to(DEV))
+    Zc = Zc.cpu()[0]
+    assert int(info[0]) == 0
+    # (the library normalises S = D^-1/2 W D^-1/2 in FP32 before the FP64 factorisation, the CPU
+    # reference normalises in FP64: 1e-6 is that input rounding, not the solver)
+    assert (Zc[vi].double() - Z64).abs().max() / scale < 5e-6
+    assert (Z - Zc).abs().max() / scale < 1e-4
+    assert (Zc[valid == 0] == 0).all()
+    Zop, _ = torch.ops.r3dfs.lp_cholesky(nbr, sim, valid[None].to(DEV), Y[None].to(DEV), 0.99)
+    assert torch.equal(Zop.cpu()[0], Zc)
+
+
+def test_lp_cholesky_batch_and_episode_size():
+    """r3dfs_lp_cholesky on two graphs of the episode size (n = 4416, odd block tail) against the CG
+    solve of the same graphs."""
+    from r3dfsseg_b200 import ops
+    n, k, nc = 4416 - 37, 200, 3
+    g = torch.Generator().manual_seed(9)
+    feat = torch.randn((2, n, 192), generator=g) * 0.12
+    valid = torch.ones((2, n), dtype=torch.uint8)
+    valid[1, 5:25] = 0
+    Y = torch.zeros((2, n, nc))
+    Y[:, 100:400].scatter_(2, torch.randint(0, nc, (2, 300, 1), generator=g), 1.0)
+    nbr, sim = ops.affinity_knn(feat.to(DEV), valid.to(DEV), k, 1.0)
+    Z, iters, resid = ops.label_propagate(nbr, sim, valid.to(DEV), Y.to(DEV))
+    Zc, info = ops.lp_cholesky(nbr, sim, valid.to(DEV), Y.to(DEV))
+    assert info.tolist() == [0, 0]
+    err = float((Z - Zc).abs().max() / Zc.abs().max())
+    assert err < 1e-4, err
+    assert float((Z.argmax(2) == Zc.argmax(2)).float().mean()) > 0.999
 
 
 # ---------------------------------------------------------------------------------------------
