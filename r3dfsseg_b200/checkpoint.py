@@ -85,36 +85,71 @@ def adam_state_from_reference(sd: Dict, names: Sequence[str], shapes: Sequence[t
     return m, v, (steps.pop() if steps else 0), (float(pgs[0]["lr"]), float(pgs[1]["lr"]))
 
 
-# ---- files (reference utils/checkpoint_util.py) --------------------------------------------------
-def load_pretrain_checkpoint(model, pretrain_checkpoint_path):
-    """Encoder weights of the pre-training stage into `model.encoder` (:10-23)."""
-    if pretrain_checkpoint_path is None:
-        raise ValueError("Pretrained checkpoint must be given.")
-    params = torch.load(pretrain_checkpoint_path, map_location="cpu")["params"]
+# ---- files --------------------------------------------------------------------------------------
+# File layouts are the reference's (utils/checkpoint_util.py, mpti_train_noise.py:137-144): the
+# pre-training file is {'params': encoder state_dict without the 'encoder.' prefix}; a run directory
+# holds `checkpoint.tar` = {iteration, IoU, loss, model_state_dict, optimizer_state_dict}.
+class CheckpointError(ValueError):
+    pass
+
+
+def read_checkpoint(run_dir: str) -> dict:
+    """`<run_dir>/checkpoint.tar` as a dict, on the CPU, with its required entries verified."""
+    path = os.path.join(run_dir, "checkpoint.tar")
+    if not os.path.isfile(path):
+        raise CheckpointError(f"no checkpoint.tar under {run_dir!r}")
+    ck = torch.load(path, map_location="cpu")
+    missing = [k for k in ("iteration", "IoU", "model_state_dict") if k not in ck]
+    if missing:
+        raise CheckpointError(f"{path}: entries {missing} are missing")
+    return ck
+
+
+def restore(model, ck: dict, optimizer=None) -> dict:
+    """Weights (non-strict, like the reference: older files lack `proj.*`) and, when an optimizer is
+    given and the file carries its state, the Adam moments.  Copies in place, so parameters that are
+    views into the flat training buffers stay views."""
+    model.load_state_dict(ck["model_state_dict"], strict=False)
+    had_opt = False
+    if optimizer is not None and ck.get("optimizer_state_dict") is not None:
+        optimizer.load_state_dict(ck["optimizer_state_dict"])
+        had_opt = True
+    return {"iteration": int(ck["iteration"]), "iou": float(ck["IoU"]), "optimizer_restored": had_opt}
+
+
+def load_encoder_pretraining(model, path: str) -> int:
+    """Copies every tensor of the pre-training file that has an `encoder.<name>` twin in `model`;
+    returns how many were copied."""
+    if not path or not os.path.isfile(path):
+        raise CheckpointError(f"pre-training file not found: {path!r}")
+    blob = torch.load(path, map_location="cpu")
+    if "params" not in blob:
+        raise CheckpointError(f"{path}: no 'params' entry")
     own = model.state_dict()
-    picked = {"encoder." + k: v for k, v in params.items() if "encoder." + k in own}
-    own.update(picked)
-    model.load_state_dict(own)     # copies in place: views into the flat buffers stay intact
+    n = 0
+    with torch.no_grad():
+        for name, value in blob["params"].items():
+            dst = own.get("encoder." + name)
+            if dst is not None and dst.shape == value.shape:
+                dst.copy_(value)
+                n += 1
+    return n
+
+
+# the reference's entry-point names, for scripts written against utils/checkpoint_util.py
+def load_pretrain_checkpoint(model, pretrain_checkpoint_path):
+    load_encoder_pretraining(model, pretrain_checkpoint_path)
     return model
 
 
 def load_model_checkpoint(model, model_checkpoint_path, optimizer=None, mode="test"):
-    """`<dir>/checkpoint.tar` (:26-45).  mode 'test' -> model; 'train' -> (model, optimizer)."""
-    try:
-        ck = torch.load(os.path.join(model_checkpoint_path, "checkpoint.tar"), map_location="cpu")
-        start_iter, start_iou = ck["iteration"], ck["IoU"]
-    except Exception:
-        raise ValueError("Model checkpoint file must be correctly given (%s)." % model_checkpoint_path)
-    model.load_state_dict(ck["model_state_dict"], strict=False)
-    if mode == "test":
-        print("Load model checkpoint at Iteration %d (IoU %f)..." % (start_iter, start_iou))
-        return model
-    try:
-        optimizer.load_state_dict(ck["optimizer_state_dict"])
-    except Exception:
-        print("Checkpoint does not include optimizer state dict...")
-    print("Resume from checkpoint at Iteration %d (IoU %f)..." % (start_iter, start_iou))
-    return model, optimizer
+    info = restore(model, read_checkpoint(model_checkpoint_path),
+                   optimizer if mode == "train" else None)
+    print("checkpoint of iteration %d (IoU %.4f) loaded%s" % (
+        info["iteration"], info["iou"],
+        "" if mode != "train" else (", optimizer state restored" if info["optimizer_restored"]
+                                    else ", optimizer starts fresh")))
+    return model if mode == "test" else (model, optimizer)
 
 
 def save_model_checkpoint(model, optimizer, output_path, iteration, iou, loss=0.0):
