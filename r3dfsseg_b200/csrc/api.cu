@@ -484,7 +484,7 @@ int r3dfs_affinity_knn(const float* node_feat, const uint8_t* valid, int n_graph
 // solver (row schedule table of up to 16 CTAs per graph + the row lists re-packed in schedule order)
 static size_t lp_scratch_bytes(size_t G, size_t n, int k) {
   const size_t inedge = 6 * G * n * ((n + 31) / 32);
-  const size_t solver = G * 16 * 2304 * 8 + 6 * G * n * (size_t)lp_rowcap(k) + 1024;
+  const size_t solver = lp_solver_scratch_bytes(G, n, k);
   return inedge > solver ? inedge : solver;
 }
 
@@ -639,7 +639,8 @@ void carve_episode(WsBump& ws, const r3dfs_episode_cfg_t* c, const EpisodeDims& 
   w.valid = ws.take<uint8_t>(G * nn);
   w.Y = ws.take<float>(G * nn * d.nc);
   w.norms = ws.take<float>(G * nn);
-  w.D2 = ws.take<float>(G * nn * nn);
+  // dense squared distances; afterwards scratch of the in-edge build and of the solver's packed rows
+  w.D2 = ws.take<float>(episode_d2_floats(G, nn, k));
   w.nbr = ws.take<int32_t>(G * nn * k);
   w.sim = ws.take<float>(G * nn * k);
   w.in_cnt = ws.take<int32_t>(G * (nn + 1));
@@ -657,6 +658,12 @@ void carve_episode(WsBump& ws, const r3dfs_episode_cfg_t* c, const EpisodeDims& 
   w.R = ws.take<float>(G * nn * 8);
   w.P = ws.take<float>(G * nn * 8);
   w.AP = ws.take<float>(G * nn * 8);
+}
+
+// floats of the D2 area of G graphs: the n x n distance matrix, or the solver scratch if that is larger
+size_t episode_d2_floats(size_t G, size_t nn, int k) {
+  const size_t dense = G * nn * nn, solver = (lp_solver_scratch_bytes(G, nn, k) + 3) / 4;
+  return dense > solver ? dense : solver;
 }
 
 size_t r3dfs_mpti_workspace(const r3dfs_episode_cfg_t* cfg, int n_episodes) {
@@ -714,7 +721,7 @@ int episode_graph_half(const r3dfs_episode_cfg_t* cfg, const EpisodeDims& d, int
                                    w.mval, w.Z, w.X, w.R, w.P, w.AP,
                                    diag ? diag->cg_iters : nullptr,
                                    diag ? diag->cg_resid : nullptr, st, sr, w.D2,
-                                   sizeof(float) * (size_t)E * d.nn * d.nn,  // D2 is dead here
+                                   sizeof(float) * episode_d2_floats(E, d.nn, cfg->k_connect),  // D2 is dead here
                                    latency));
   // query rows -> logits / loss / prediction
   R3DFS_TRY(launch_query_head(w.Z, E, d.nn, d.ppad, d.nq_pts, d.nc, query_y, logits, loss, pred, st));

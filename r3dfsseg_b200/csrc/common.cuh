@@ -47,6 +47,16 @@ static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; 
 // merged symmetric rows (lp.cu): entries a graph owns per node; row segments are multiples of 4
 // (a graph's rows hold at most 2 k nn entries in total; every row is padded to a multiple of 4)
 __host__ __device__ inline int lp_rowcap(int k) { return ((2 * k + 3) & ~3) + 4; }
+// packed form of those rows for the cluster CG kernel (cg_pack_kernel): groups of 4 entries a graph
+// may occupy — 1.6 x its entries (measured need: 1.34 x) plus 64 per node
+__host__ __device__ inline int64_t lp_pack_groups(int64_t nn, int k) {
+  return (nn * (int64_t)(2 * k) * 2 / 5 + 64 * nn + 63) / 64 * 64;
+}
+// bytes of solver scratch for G graphs (tables for up to 16 CTAs per graph + flags + packed lists)
+static inline size_t lp_solver_scratch_bytes(size_t G, size_t nn, int k) {
+  return G * 16 * (4 + 32 * 3 * 2 + 3 * 1024 * 2) * 4 + 256 + 4 * G * (1 + nn) + 256 +
+         (8 + 16) * G * (size_t)lp_pack_groups(nn, k) + 512;
+}
 
 // Bump allocator over the caller's workspace.  Never owns memory.
 struct WsBump {

@@ -52,6 +52,7 @@ int encoder_forward(const r3dfs_weights_t* w, const float* xp, int64_t B, int N,
                     float* F, RowMap map, float* level2, cudaStream_t st,
                     const StageRec* sr = nullptr);
 int episode_dims(const r3dfs_episode_cfg_t* c, EpisodeDims& d);
+size_t episode_d2_floats(size_t G, size_t nn, int k);
 void carve_episode(WsBump& ws, const r3dfs_episode_cfg_t* c, const EpisodeDims& d, int E, int in_dim,
                    int dg_k, EpisodeWs& w);
 // everything after getFeatures (models/mpti.py:440-571); F rows [ppad, nn) = query features,

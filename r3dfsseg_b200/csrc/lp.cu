@@ -991,12 +991,15 @@ __global__ void normalize_merged_kernel(const int32_t* __restrict__ rowptr,
 //     every CTA sees bit-identical scalars and the control flow stays cluster-uniform.
 // --------------------------------------------------------------------------------------------
 #define CG_THREADS 1024
-#define CGC_THREADS 768  // cluster kernel: 24 warps, ONE CTA per SM (85 registers: the queue of row rounds in flight)
-#define CG_WARPS (CGC_THREADS / 32)
-#define CG_Q 4            // rounds (128 matrix entries each) in flight per warp
-#define CG_MAXR 96        // rows per warp in the schedule table -> at most 2304 rows per CTA
+#define CGC_MAXT 1024     // cluster kernel: up to 32 warps, ONE CTA per SM, one matrix row per thread
 #define CG_CL_MAX 16
 #define CG_MAXC 8
+#define CG_MAXPASS 3      // matrix rows (or row segments) per thread -> at most 3072 per CTA
+#define CG_SEGR 48        // residue ranks per row segment: 8 * 48 = 384 entries = 96 rounds
+#define CG_MAXPART 1024   // segments of split rows a CTA can combine through shared memory
+#define CG_TAB_HDR 4      // lo, hi, passes, segments of split rows
+#define CG_TAB_INTS (CG_TAB_HDR + 32 * CG_MAXPASS * 2 + CG_MAXPASS * CGC_MAXT * 2)
+#define CG_PK_SMEM (4096 * 4 + 8192 * 4 * 2)
 
 struct CgExchange {
   float slot[2][CG_CL_MAX][CG_MAXC];
@@ -1008,6 +1011,7 @@ __device__ __forceinline__ void cg_allreduce(cg::cluster_group& cluster, CgExcha
                                              float* total) {
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const int rank = cluster.block_rank(), CL = cluster.num_blocks();
+  const int n_warps = blockDim.x >> 5;
   float v[NCV];
 #pragma unroll
   for (int c = 0; c < NCV; ++c) v[c] = warp_sum(part[c]);
@@ -1019,7 +1023,7 @@ __device__ __forceinline__ void cg_allreduce(cg::cluster_group& cluster, CgExcha
   const int par = xcnt & 1;
   if (tid < NCV) {
     float s = 0.f;
-    for (int q = 0; q < CGC_THREADS / 32; ++q) s += s_warp[q * CG_MAXC + tid];
+    for (int q = 0; q < n_warps; ++q) s += s_warp[q * CG_MAXC + tid];
     for (int r = 0; r < CL; ++r) {
       float* dst = cluster.map_shared_rank(&ex->slot[par][rank][tid], r);
       *dst = s;
@@ -1035,142 +1039,311 @@ __device__ __forceinline__ void cg_allreduce(cg::cluster_group& cluster, CgExcha
   ++xcnt;
 }
 
-// Row schedule of the cluster kernel below, built once per solve by one CTA per (graph, rank), and
-// the row lists RE-PACKED in that order.  merge_rows_kernel places rows wherever its atomic cursor
-// lands, so 3 000 warps streaming their own rows hit HBM as small scattered reads (measured: the
-// solve saturated at 1.6 TB/s with ~9 MB in flight).  Packed, the 24 warps of a CTA read 24
-// neighbouring lists at any time and move through the CTA's region front to back.
-//   sched[(g * CL + rank)][warp][slot] = (list offset in the packed arrays, groups << 12 | local row)
-__global__ __launch_bounds__(CGC_THREADS) void cg_schedule_kernel(
+// --------------------------------------------------------------------------------------------
+// Packing for the cluster kernel below, once per solve.
+//
+// The product y = S p gathers one float4 of the shared-memory copy of p per matrix entry.  The
+// first versions walked a row with a whole warp (entries in arbitrary order: 9.3 wavefronts per
+// LDS.128 instead of 4, a shuffle reduction per row, ~130 instructions per 128 entries) and ran at
+// one entry per clock per SM however the loads were arranged.  Here ONE THREAD OWNS ONE ROW:
+//   * no reduction, ~35 instructions per 128 entries;
+//   * the 32 rows of a warp are stored interleaved (lane-major groups of 4 entries: one uint2 of
+//     columns + one float4 of weights per lane and round): a warp streams 768 contiguous bytes per
+//     round;
+//   * bank conflicts are designed out: the row owned by lane l is re-ordered so that its entry
+//     number t has column residue (l + t) mod 8 — at every step the 8 lanes of a quarter-warp
+//     gather from 8 different 16-byte bank groups.  Missing residues are padded with
+//     (column (l + t) mod 8, weight 0), which adds 0 to the sum;
+//   * row lengths range from 200 to 3 000 entries (hub prototypes), so a row is cut into SEGMENTS
+//     of at most 384 entries (48 ranks of every residue); the segments of a split row are added
+//     in order through shared memory.  Segments are sorted by length before they are dealt to the
+//     threads, so the 32 segments of a warp are equally long, and the CTAs of a cluster own
+//     contiguous row ranges with (almost) the same number of segments.
+// A graph that does not fit its share of the scratch area (very skewed residues) is flagged and
+// solved by the plain warp-per-row path of the kernel.
+//   tab[(g * CL + rank)] = {lo, hi, passes, split segments} | slice[32 warps][CG_MAXPASS]{first
+//   group, rounds} | thread[CG_MAXPASS][1024]{row - lo << 8 | segment, segments << 16 | part slot}
+// --------------------------------------------------------------------------------------------
+__global__ __launch_bounds__(256) void cg_hist_kernel(const int32_t* __restrict__ rowptr,
+                                                      const int32_t* __restrict__ rowlen,
+                                                      const uint8_t* __restrict__ valid,
+                                                      const uint16_t* __restrict__ mcol, int nn,
+                                                      int k, int32_t* __restrict__ rowmax) {
+  const int g = blockIdx.y;
+  const int i = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (i >= nn) return;
+  const int lane = threadIdx.x & 31;
+  const int64_t vb = (int64_t)g * nn;
+  int mx = 0;
+  if (valid[vb + i]) {
+    const int L = rowlen[vb + i];
+    const uint16_t* c = mcol + vb * lp_rowcap(k) + rowptr[vb + i];
+    int cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int t0 = 0; t0 < L; t0 += 32) {
+      const int t = t0 + lane;
+      const int res = t < L ? (int)(c[t] & 7) : -1;
+#pragma unroll
+      for (int b = 0; b < 8; ++b) cnt[b] += __popc(__ballot_sync(0xffffffffu, res == b));
+    }
+#pragma unroll
+    for (int b = 0; b < 8; ++b) mx = max(mx, cnt[b]);
+  }
+  if (lane == 0) rowmax[vb + i] = mx;  // largest residue class of the row (0: invalid node)
+}
+
+__global__ __launch_bounds__(1024) void cg_pack_kernel(
     const int32_t* __restrict__ rowptr, const int32_t* __restrict__ rowlen,
-    const uint8_t* __restrict__ valid, const uint16_t* __restrict__ mcol,
-    const float* __restrict__ mval, int nn, int k, int2* __restrict__ sched,
-    uint16_t* __restrict__ mcol2, float* __restrict__ mval2) {
-  __shared__ uint32_t s_key[CG_WARPS * CG_MAXR * 2];  // >= next power of two of the rows of a CTA
-  __shared__ int s_off[CG_WARPS * CG_MAXR * 2];
+    const int32_t* __restrict__ rowmax, const uint16_t* __restrict__ mcol,
+    const float* __restrict__ mval, int nn, int k, int64_t pk_cap, int32_t* __restrict__ tab_all,
+    int32_t* __restrict__ flags, uint2* __restrict__ pcol, float4* __restrict__ pval) {
+  extern __shared__ __align__(16) unsigned char pk_smem[];
+  uint32_t* s_key = reinterpret_cast<uint32_t*>(pk_smem);  // [4096] rounds << 21 | row - lo << 8 | seg
+  int* s_pre = reinterpret_cast<int*>(s_key + 4096);       // [nn] segments before row i (whole graph)
+  int* s_prx = s_pre + 8192;                               // [nn] segments of split rows before row i
+  __shared__ int s_scan[2][32];
+  __shared__ int s_tot[2];
+  __shared__ int s_rng[2];
+  __shared__ int s_wtot[32], s_wbase[32];
   const int CL = gridDim.x, rank = blockIdx.x, g = blockIdx.y;
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const int64_t vb = (int64_t)g * nn;
-  const uint8_t* vg = valid + vb;
   const int32_t* rp = rowptr + vb;
   const int32_t* rl = rowlen + vb;
-  const int64_t mb = vb * lp_rowcap(k);
-  // (dealing the rows to the CTAs round-robin instead of in contiguous chunks balances the long
-  // prototype rows better but makes every vector update strided: measured 6.6 -> 7.5 ms)
-  const int chunk = (nn + CL - 1) / CL;
-  const int lo = min(nn, rank * chunk), hi = min(nn, lo + chunk);
-  const int nrows = hi - lo;
-  __shared__ int s_red[CGC_THREADS / 32];
-  __shared__ int s_base;
-  int npow = 32;
-  while (npow < nrows) npow <<= 1;
-  for (int i = tid; i < npow; i += CGC_THREADS) {
-    uint32_t key = 0;
-    if (i < nrows) {
-      const int row = lo + i;
-      const int n4 = vg[row] ? (rl[row] + 3) >> 2 : 0;
-      key = ((uint32_t)n4 << 12) | (uint32_t)i;
-    }
-    s_key[i] = key;
-  }
-  // start of this CTA's region of the packed arrays: everything owned by lower ranks (a row can be
-  // much longer than 2 k — hub nodes — so regions cannot be sized per row)
+  const int32_t* rmx = rowmax + vb;
+  const uint16_t* mc = mcol + vb * lp_rowcap(k);
+  const float* mv = mval + vb * lp_rowcap(k);
+  int32_t* tab = tab_all + (size_t)(g * CL + rank) * CG_TAB_INTS;
+  for (int e = tid; e < CG_TAB_HDR + 32 * CG_MAXPASS * 2; e += 1024) tab[e] = 0;
+  // ---- segments per row, prefix over the whole graph (8 rows per thread, nn <= 8192)
   {
-    int below = 0;
-    for (int row = tid; row < lo; row += CGC_THREADS)
-      if (vg[row]) below += ((rl[row] + 3) >> 2) * 4;
+    int nseg[8], run = 0, runx = 0;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) below += __shfl_xor_sync(0xffffffffu, below, o);
-    if (lane == 0) s_red[w] = below;
-  }
-  __syncthreads();
-  if (tid == 0) {
-    int t = 0;
-    for (int q = 0; q < CGC_THREADS / 32; ++q) t += s_red[q];
-    s_base = t;
-  }
-  __syncthreads();
-  for (int ksz = 2; ksz <= npow; ksz <<= 1)
-    for (int j = ksz >> 1; j > 0; j >>= 1) {
-      for (int i = tid; i < npow; i += CGC_THREADS) {
-        const int ixj = i ^ j;
-        if (ixj > i) {
-          const uint32_t x = s_key[i], y = s_key[ixj];
-          const bool desc = (i & ksz) == 0;
-          if (desc ? x < y : x > y) {
-            s_key[i] = y;
-            s_key[ixj] = x;
-          }
-        }
-      }
-      __syncthreads();
+    for (int u = 0; u < 8; ++u) {
+      const int i = tid * 8 + u;
+      nseg[u] = i < nn ? (rmx[i] + CG_SEGR - 1) / CG_SEGR : 0;
+      run += nseg[u];
+      runx += nseg[u] > 1 ? nseg[u] : 0;
     }
-  // exclusive scan of the list lengths (entries) in schedule order: warp 0, a segment per lane
-  if (w == 0) {
-    const int seg = npow / 32;
-    int sum = 0;
-    for (int i = lane * seg; i < (lane + 1) * seg; ++i) sum += (int)(s_key[i] >> 12) * 4;
-    int incl = sum;
+    int inc = run, incx = runx;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-      const int a = __shfl_up_sync(0xffffffffu, incl, o);
-      if (lane >= o) incl += a;
-    }
-    int run = incl - sum;
-    for (int i = lane * seg; i < (lane + 1) * seg; ++i) {
-      s_off[i] = run;
-      run += (int)(s_key[i] >> 12) * 4;
-    }
-  }
-  int2* tab = sched + (size_t)(g * CL + rank) * (CG_WARPS * CG_MAXR);
-  for (int i = tid; i < CG_WARPS * CG_MAXR; i += CGC_THREADS) tab[i] = make_int2(0, 0);
-  __syncthreads();
-  const bool pack = mcol2 != nullptr;
-  const int base = s_base;
-  for (int i = tid; i < nrows; i += CGC_THREADS) {
-    const uint32_t key = s_key[i];
-    if ((key >> 12) == 0) continue;
-    const int pass = i / CG_WARPS, pos = i % CG_WARPS;
-    const int ww = (pass & 1) ? CG_WARPS - 1 - pos : pos;
-    tab[ww * CG_MAXR + pass] =
-        make_int2(pack ? base + s_off[i] : rp[lo + (int)(key & 0xfffu)], (int)key);
-  }
-  if (pack) {
-    for (int i = w; i < nrows; i += CG_WARPS) {
-      const uint32_t key = s_key[i];
-      const int n4 = (int)(key >> 12);
-      if (n4 == 0) break;  // sorted: only empty rows follow
-      const int64_t src = mb + rp[lo + (int)(key & 0xfffu)], dst = mb + base + s_off[i];
-      const uint2* sc = reinterpret_cast<const uint2*>(mcol + src);
-      const float4* sv = reinterpret_cast<const float4*>(mval + src);
-      uint2* dc = reinterpret_cast<uint2*>(mcol2 + dst);
-      float4* dv = reinterpret_cast<float4*>(mval2 + dst);
-      for (int q = lane; q < n4; q += 32) {
-        dc[q] = sc[q];
-        dv[q] = sv[q];
+      const int a = __shfl_up_sync(0xffffffffu, inc, o), ax = __shfl_up_sync(0xffffffffu, incx, o);
+      if (lane >= o) {
+        inc += a;
+        incx += ax;
       }
     }
+    if (lane == 31) {
+      s_scan[0][w] = inc;
+      s_scan[1][w] = incx;
+    }
+    __syncthreads();
+    if (w == 0) {
+      int v = s_scan[0][lane], vx = s_scan[1][lane];
+      int i2 = v, ix2 = vx;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int a = __shfl_up_sync(0xffffffffu, i2, o), ax = __shfl_up_sync(0xffffffffu, ix2, o);
+        if (lane >= o) {
+          i2 += a;
+          ix2 += ax;
+        }
+      }
+      s_scan[0][lane] = i2 - v;
+      s_scan[1][lane] = ix2 - vx;
+      if (lane == 31) {
+        s_tot[0] = i2;
+        s_tot[1] = ix2;
+      }
+    }
+    if (tid == 0) {
+      s_rng[0] = nn;
+      s_rng[1] = 0;
+    }
+    __syncthreads();
+    int pre = s_scan[0][w] + inc - run, prex = s_scan[1][w] + incx - runx;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int i = tid * 8 + u;
+      if (i < nn) {
+        s_pre[i] = pre;
+        s_prx[i] = prex;
+      }
+      pre += nseg[u];
+      prex += nseg[u] > 1 ? nseg[u] : 0;
+    }
+  }
+  __syncthreads();
+  // ---- this CTA's contiguous row range: rows whose first segment falls into its share
+  const int NV = s_tot[0];
+  for (int i = tid; i < nn; i += 1024) {
+    const int owner = NV > 0 ? min(CL - 1, (int)((int64_t)s_pre[i] * CL / NV)) : (i * CL) / nn;
+    if (owner == rank) {
+      atomicMin(&s_rng[0], i);
+      atomicMax(&s_rng[1], i + 1);
+    }
+  }
+  __syncthreads();
+  const int lo = min(s_rng[0], s_rng[1]), hi = s_rng[1];
+  const int pre_lo = lo < nn ? s_pre[lo] : NV, prx_lo = lo < nn ? s_prx[lo] : s_tot[1];
+  const int nv = (hi < nn ? s_pre[hi] : NV) - pre_lo;           // segments of this CTA
+  const int nx = (hi < nn ? s_prx[hi] : s_tot[1]) - prx_lo;    // ... of which belong to split rows
+  const int passes = (nv + CGC_MAXT - 1) / CGC_MAXT;
+  const int64_t share = pk_cap / CL;
+  bool bad = passes > CG_MAXPASS || nx > CG_MAXPART || hi - lo > 8191;
+  // ---- keys of the segments, sorted by length (descending)
+  int npow = 32;
+  while (npow < nv) npow <<= 1;
+  if (!bad) {
+    for (int i = tid; i < npow; i += 1024) s_key[i] = 0;
+    __syncthreads();
+    for (int i = lo + tid; i < hi; i += 1024) {
+      const int mx = rmx[i];
+      const int ns = (mx + CG_SEGR - 1) / CG_SEGR;
+      if (ns > 255) bad = true;
+      for (int sg = 0; sg < ns && sg < 256; ++sg) {
+        const int ranks = min(CG_SEGR, mx - sg * CG_SEGR);
+        s_key[s_pre[i] - pre_lo + sg] =
+            ((uint32_t)(2 * ranks) << 21) | ((uint32_t)(i - lo) << 8) | (uint32_t)sg;
+      }
+    }
+  }
+  bad = __syncthreads_or(bad);
+  if (!bad) {
+    for (int ksz = 2; ksz <= npow; ksz <<= 1)
+      for (int j = ksz >> 1; j > 0; j >>= 1) {
+        for (int i = tid; i < npow; i += 1024) {
+          const int ixj = i ^ j;
+          if (ixj > i) {
+            const uint32_t x = s_key[i], y = s_key[ixj];
+            const bool desc = (i & ksz) == 0;
+            if (desc ? x < y : x > y) {
+              s_key[i] = y;
+              s_key[ixj] = x;
+            }
+          }
+        }
+        __syncthreads();
+      }
+    // slices: (pass, warp) holds sorted segments pass * 1024 + warp * 32 + lane; as long as its first
+    if (tid < 32) {
+      int tot = 0;
+      for (int p = 0; p < passes; ++p) {
+        const int i0 = p * CGC_MAXT + tid * 32;
+        tot += i0 < nv ? (int)(s_key[i0] >> 21) * 32 : 0;
+      }
+      s_wtot[tid] = tot;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      int run = 0;
+      for (int q = 0; q < 32; ++q) {
+        s_wbase[q] = run;
+        run += s_wtot[q];
+      }
+      s_tot[0] = run;
+    }
+    __syncthreads();
+    if (s_tot[0] > share) bad = true;
+  }
+  if (tid == 0) {
+    tab[0] = lo;
+    tab[1] = hi;
+    tab[2] = bad ? 0 : passes;
+    tab[3] = nx;
+    if (bad) atomicOr(&flags[g], 1);
+  }
+  if (bad) return;
+  // ---- per-thread table: which segment thread t works on in pass p
+  for (int e = tid; e < CG_MAXPASS * CGC_MAXT; e += 1024) {
+    const int p = e / CGC_MAXT, t = e % CGC_MAXT;
+    const int i = p * CGC_MAXT + t;
+    int m0 = -1, m1 = 0;
+    if (p < passes && i < nv) {
+      const uint32_t key = s_key[i];
+      const int rloc = (int)((key >> 8) & 0x1fffu), sg = (int)(key & 0xffu);
+      const int ns = (rmx[lo + rloc] + CG_SEGR - 1) / CG_SEGR;
+      m0 = (rloc << 8) | sg;
+      m1 = (ns << 16) | (ns > 1 ? s_prx[lo + rloc] - prx_lo : 0);
+    }
+    tab[CG_TAB_HDR + 32 * CG_MAXPASS * 2 + 2 * e + 0] = m0;
+    tab[CG_TAB_HDR + 32 * CG_MAXPASS * 2 + 2 * e + 1] = m1;
+  }
+  // ---- every pack warp fills and scatters the slices of the consumer warp with its number
+  uint2* gc = pcol + (int64_t)g * pk_cap + rank * share;
+  float4* gv = pval + (int64_t)g * pk_cap + rank * share;
+  int base = s_wbase[w];
+  for (int p = 0; p < passes; ++p) {
+    const int i0 = p * CGC_MAXT + w * 32;
+    const int rounds = i0 < nv ? (int)(s_key[i0] >> 21) : 0;
+    if (lane == 0) {
+      tab[CG_TAB_HDR + (w * CG_MAXPASS + p) * 2 + 0] = (int)(rank * share) + base;
+      tab[CG_TAB_HDR + (w * CG_MAXPASS + p) * 2 + 1] = rounds;
+    }
+    // pads everywhere first: entry t of lane l has column (l + t) mod 8 and weight 0
+    for (int r = 0; r < rounds; ++r) {
+      const unsigned t0 = (unsigned)(lane + 4 * r);
+      uint2 c2;
+      c2.x = (t0 & 7u) | (((t0 + 1) & 7u) << 16);
+      c2.y = ((t0 + 2) & 7u) | (((t0 + 3) & 7u) << 16);
+      gc[base + r * 32 + lane] = c2;
+      gv[base + r * 32 + lane] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    __syncwarp();
+    uint16_t* c16 = reinterpret_cast<uint16_t*>(gc + base);
+    float* v32 = reinterpret_cast<float*>(gv + base);
+    for (int l = 0; l < 32; ++l) {  // the segment owned by lane l of the consumer warp
+      const int i = i0 + l;
+      if (i >= nv) break;
+      const uint32_t key = s_key[i];
+      const int row = lo + (int)((key >> 8) & 0x1fffu), sg = (int)(key & 0xffu), L = rl[row];
+      const int r_lo = sg * CG_SEGR, r_hi = r_lo + CG_SEGR;  // ranks of every residue in this segment
+      const uint16_t* c = mc + rp[row];
+      const float* v = mv + rp[row];
+      int seen[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      for (int t0 = 0; t0 < L; t0 += 32) {
+        const int t = t0 + lane;
+        const int col = t < L ? (int)c[t] : -1;
+        const int res = t < L ? (col & 7) : -1;
+        int rho = -1;
+#pragma unroll
+        for (int b = 0; b < 8; ++b) {
+          const uint32_t m = __ballot_sync(0xffffffffu, res == b);
+          if (res == b) rho = seen[b] + __popc(m & ((1u << lane) - 1));
+          seen[b] += __popc(m);
+        }
+        if (rho >= r_lo && rho < r_hi) {
+          const int step = 8 * (rho - r_lo) + ((res - l) & 7);  // residue (l + step) mod 8 == res
+          const int64_t d = ((int64_t)(step >> 2) * 32 + l) * 4 + (step & 3);
+          c16[d] = (uint16_t)col;
+          v32[d] = v[t];
+        }
+      }
+    }
+    __syncwarp();
+    base += rounds * 32;
   }
 }
 
 // Vectors are stored padded to NCV columns (NCV = 4 or 8) so a node's row is one or two float4.
 template <int NCV>
-__global__ __launch_bounds__(CGC_THREADS, 1) void lp_cg_kernel(
+__global__ __launch_bounds__(CGC_MAXT, 1) void lp_cg_kernel(
     const int32_t* __restrict__ rowptr, const int32_t* __restrict__ rowlen,
     const uint16_t* __restrict__ mcol, const float* __restrict__ mval,
     const uint8_t* __restrict__ valid, int nn, int k,
     const float* __restrict__ Y, int nc, float alpha, float tol, int max_iter,
     float* __restrict__ Z, float* __restrict__ X, float* __restrict__ R, float* __restrict__ Pv,
     float* __restrict__ AP, int32_t* __restrict__ iters_out, float* __restrict__ resid_out,
-    const int2* __restrict__ sched) {
+    const int32_t* __restrict__ tab_all, const int32_t* __restrict__ flags,
+    const uint2* __restrict__ pcol, const float4* __restrict__ pval, int64_t pk_cap) {
   cg::cluster_group cluster = cg::this_cluster();
   const int CL = cluster.num_blocks(), rank = cluster.block_rank();
   const int g = blockIdx.y;
   extern __shared__ __align__(16) float Ps[];  // [nn][NCV] staged copy of P
   __shared__ CgExchange ex;
-  __shared__ float s_warp[(CGC_THREADS / 32) * CG_MAXC];
-  __shared__ int2 s_meta[CG_WARPS * CG_MAXR];  // per warp: (list offset, groups << 12 | local row)
-  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  __shared__ float s_warp[(CGC_MAXT / 32) * CG_MAXC];
+  float* s_split = Ps + (size_t)nn * NCV;  // [CG_MAXPART][NCV] partial sums of split rows
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, T = blockDim.x;
   const int64_t vb = (int64_t)g * nn;
   const uint8_t* vg = valid + vb;
   const float* Yg = Y + vb * nc;
@@ -1179,19 +1352,16 @@ __global__ __launch_bounds__(CGC_THREADS, 1) void lp_cg_kernel(
   float* Rg = R + vb * NCV;
   float* Pg = Pv + vb * NCV;
   float* APg = AP + vb * NCV;
-  const int32_t* rp = rowptr + vb;
-  const int32_t* rl = rowlen + vb;
-  const uint16_t* mc = mcol + vb * lp_rowcap(k);
-  const float* mv = mval + vb * lp_rowcap(k);
-  const int chunk = (nn + CL - 1) / CL;
-  const int lo = min(nn, rank * chunk), hi = min(nn, lo + chunk);
+  // this CTA's contiguous row range (cg_pack_kernel balanced the ranges by row segments)
+  const int32_t* tab = tab_all + (size_t)(g * CL + rank) * CG_TAB_INTS;
+  const int lo = tab[0], hi = tab[1];
   const int nloc = hi - lo;  // this CTA's rows: lo + j
   int xcnt = 0;
 
   float part[NCV], bb[NCV], rs[NCV], tot[NCV];
 #pragma unroll
   for (int c = 0; c < NCV; ++c) part[c] = 0.f;
-  for (int jj = tid; jj < nloc; jj += CGC_THREADS) {
+  for (int jj = tid; jj < nloc; jj += T) {
     const int row = lo + jj;
     const bool ok = vg[row];
 #pragma unroll
@@ -1214,69 +1384,16 @@ __global__ __launch_bounds__(CGC_THREADS, 1) void lp_cg_kernel(
     all_done = all_done && done[c];
   }
   const float tol2 = tol * tol;
-  // ---- row schedule, built once per solve -------------------------------------------------------
-  // The rows of this CTA are sorted by list length and dealt to the warps in snake order, so every
-  // warp streams (nearly) the same number of entries per product; a warp's rows and their list
-  // offsets/lengths sit in a shared-memory table (one broadcast LDS per row instead of dependent
-  // global loads).  The schedule depends only on the row lengths, so it is the same in every run
-  // and every floating-point sum keeps its order.
-  if (sched) {  // built (and the lists re-packed in this order) by cg_schedule_kernel
-    const int2* src = sched + (size_t)(g * CL + rank) * (CG_WARPS * CG_MAXR);
-    for (int i = tid; i < CG_WARPS * CG_MAXR; i += CGC_THREADS) s_meta[i] = src[i];
-    __syncthreads();
-  } else {
-    uint32_t* s_key = reinterpret_cast<uint32_t*>(Ps);  // Ps is not live yet
-    const int nrows = nloc;
-    int npow = 32;
-    while (npow < nrows) npow <<= 1;
-    for (int i = tid; i < npow; i += CGC_THREADS) {
-      uint32_t key = 0;  // (groups of 4 entries) << 12 | local row ; 0-length rows sort last
-      if (i < nrows) {
-        const int n4 = vg[lo + i] ? (rl[lo + i] + 3) >> 2 : 0;
-        key = ((uint32_t)n4 << 12) | (uint32_t)i;
-      }
-      s_key[i] = key;
-    }
-    __syncthreads();
-    for (int ksz = 2; ksz <= npow; ksz <<= 1)
-      for (int j = ksz >> 1; j > 0; j >>= 1) {
-        for (int i = tid; i < npow; i += CGC_THREADS) {
-          const int ixj = i ^ j;
-          if (ixj > i) {
-            const uint32_t x = s_key[i], y = s_key[ixj];
-            const bool desc = (i & ksz) == 0;  // descending overall
-            if (desc ? x < y : x > y) {
-              s_key[i] = y;
-              s_key[ixj] = x;
-            }
-          }
-        }
-        __syncthreads();
-      }
-    for (int i = tid; i < CG_WARPS * CG_MAXR; i += CGC_THREADS) s_meta[i] = make_int2(0, 0);
-    __syncthreads();
-    for (int i = tid; i < nrows; i += CGC_THREADS) {
-      const uint32_t key = s_key[i];
-      if ((key >> 12) == 0) continue;
-      const int pass = i / CG_WARPS, pos = i % CG_WARPS;
-      const int ww = (pass & 1) ? CG_WARPS - 1 - pos : pos;
-      s_meta[ww * CG_MAXR + pass] = make_int2(rp[lo + (int)(key & 0xfffu)], (int)key);
-    }
-    __syncthreads();
-  }
-  const int2* my_meta = s_meta + w * CG_MAXR;
-  int nr_w = 0, n_rounds = 0;  // rows of this warp, rounds of 128 entries over all of them
-  for (int j = lane; j < CG_MAXR; j += 32) {
-    const int n4 = (int)((uint32_t)my_meta[j].y >> 12);
-    nr_w += n4 > 0;
-    n_rounds += (n4 + 31) >> 5;
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    nr_w += __shfl_xor_sync(0xffffffffu, nr_w, o);
-    n_rounds += __shfl_xor_sync(0xffffffffu, n_rounds, o);
-  }
-  __syncthreads();  // s_key (aliasing Ps) is dead from here on
+  // ---- this thread's row segments (cg_pack_kernel): one per pass
+  const bool packed = flags[g] == 0;
+  const int passes = packed ? tab[2] : 0;
+  const bool any_split = packed && tab[3] > 0;
+  // (the per-pass entries of the table are re-read from L1/L2 where they are used: keeping them in
+  // registers for the whole solve spills at the 64-register cap of a 1024-thread CTA)
+  const int32_t* t_slice = tab + CG_TAB_HDR + w * CG_MAXPASS * 2;
+  const int32_t* t_thread = tab + CG_TAB_HDR + 32 * CG_MAXPASS * 2 + 2 * tid;
+  const uint2* gc = pcol + (int64_t)g * pk_cap;
+  const float4* gv = pval + (int64_t)g * pk_cap;
   int it = 0;
   while (!all_done && it < max_iter) {
     // ---- stage P (written by every CTA of the cluster, published by the last cluster.sync)
@@ -1284,114 +1401,124 @@ __global__ __launch_bounds__(CGC_THREADS, 1) void lp_cg_kernel(
       const float4* src = reinterpret_cast<const float4*>(Pg);
       float4* dst = reinterpret_cast<float4*>(Ps);
       const int n4 = nn * (NCV / 4);
-      for (int i = tid; i < n4; i += CGC_THREADS) dst[i] = __ldcg(src + i);
+      for (int i = tid; i < n4; i += T) dst[i] = __ldcg(src + i);
     }
     __syncthreads();
     // ---- AP = P - alpha * S P  on my rows; partial P.AP
-    // The (col, val) lists of the warp's rows are read as ROUNDS of 128 entries (lane = one uint2 of
-    // columns + one float4 of weights) through a queue of CG_Q rounds in flight that runs across
-    // row boundaries: the loads of the next rows are under way while a row is reduced.
 #pragma unroll
     for (int c = 0; c < NCV; ++c) part[c] = 0.f;
-    {
-      float acc[NCV];
-      float my_part[NCV / 4];  // lanes 0, 8, 16, 24 own components 4g + lane / 8
+    if (packed) {
+      constexpr unsigned SH = NCV == 4 ? 4 : 5;  // node -> byte offset of its row of P
+      const unsigned char* Pb = reinterpret_cast<const unsigned char*>(Ps);
 #pragma unroll
-      for (int c = 0; c < NCV; ++c) acc[c] = 0.f;
+      for (int p = 0; p < passes; ++p) {
+        const int rounds = __ldg(t_slice + 2 * p + 1);
+        if (rounds == 0) continue;  // warp-uniform
+        const int sbase = __ldg(t_slice + 2 * p);
+        const uint2* c2 = gc + sbase + lane;
+        const float4* v4 = gv + sbase + lane;
+        float acc[NCV];
 #pragma unroll
-      for (int q = 0; q < NCV / 4; ++q) my_part[q] = 0.f;
-      int ij = 0, ir = 0, ip = 0, in4 = 0;  // issue pointer: row slot, round, list offset, groups
-      int cj = 0, cr = 0, cn4 = 0, crow = 0;  // consume pointer
-      if (nr_w > 0) {
-        const int2 m0 = my_meta[0];
-        ip = m0.x;
-        in4 = cn4 = (int)((uint32_t)m0.y >> 12);
-        crow = lo + (m0.y & 0xfff);
-      }
-      auto issue = [&](uint2& c, float4& v) {
-        const int gidx = ir * 32 + lane;
-        c = make_uint2(0u, 0u);
-        v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (gidx < in4) {
-          c = __ldcs(reinterpret_cast<const uint2*>(mc + ip) + gidx);
-          v = __ldcs(reinterpret_cast<const float4*>(mv + ip) + gidx);
-        }
-        if (++ir * 32 >= in4) {
-          ir = 0;
-          if (++ij < nr_w) {
-            const int2 m = my_meta[ij];
-            ip = m.x;
-            in4 = (int)((uint32_t)m.y >> 12);
-          }
-        }
-      };
-      auto fma4 = [&](float wgt, unsigned byte_off) {
-#pragma unroll
-        for (int q = 0; q < NCV / 4; ++q) {
-          const float4 p4 = *reinterpret_cast<const float4*>(
-              reinterpret_cast<const unsigned char*>(Ps) + byte_off + 16 * q);
-          acc[4 * q + 0] = fmaf(wgt, p4.x, acc[4 * q + 0]);
-          acc[4 * q + 1] = fmaf(wgt, p4.y, acc[4 * q + 1]);
-          acc[4 * q + 2] = fmaf(wgt, p4.z, acc[4 * q + 2]);
-          acc[4 * q + 3] = fmaf(wgt, p4.w, acc[4 * q + 3]);
-        }
-      };
-      auto consume = [&](const uint2& c, const float4& v) {
-        constexpr unsigned SH = NCV == 4 ? 4 : 5;  // node -> byte offset of its row of P
-        fma4(v.x, (c.x & 0xffffu) << SH);
-        fma4(v.y, (c.x >> 16) << SH);
-        fma4(v.z, (c.y & 0xffffu) << SH);
-        fma4(v.w, (c.y >> 16) << SH);
-        if (++cr * 32 >= cn4) {  // the row is complete: 4 sums per group with 6 shuffles
+        for (int c = 0; c < NCV; ++c) acc[c] = 0.f;
+        auto fma4 = [&](float wgt, unsigned byte_off) {
 #pragma unroll
           for (int q = 0; q < NCV / 4; ++q) {
-            const bool up = lane & 16, up2 = lane & 8;
-            float s0 = up ? acc[4 * q + 2] : acc[4 * q + 0], s1 = up ? acc[4 * q + 3] : acc[4 * q + 1];
-            const float t0 = up ? acc[4 * q + 0] : acc[4 * q + 2],
-                        t1 = up ? acc[4 * q + 1] : acc[4 * q + 3];
-            s0 += __shfl_xor_sync(0xffffffffu, t0, 16);
-            s1 += __shfl_xor_sync(0xffffffffu, t1, 16);
-            float u = up2 ? s1 : s0;
-            const float vv = up2 ? s0 : s1;
-            u += __shfl_xor_sync(0xffffffffu, vv, 8);
-            u += __shfl_xor_sync(0xffffffffu, u, 4);
-            u += __shfl_xor_sync(0xffffffffu, u, 2);
-            u += __shfl_xor_sync(0xffffffffu, u, 1);
-            if ((lane & 7) == 0) {  // lane 8 c holds component 4 q + c
-              const int comp = 4 * q + (lane >> 3);
-              const float pv = Ps[(size_t)crow * NCV + comp];
-              const float ap = pv - alpha * u;
-              APg[(int64_t)crow * NCV + comp] = ap;
-              my_part[q] = fmaf(pv, ap, my_part[q]);
-            }
-            acc[4 * q + 0] = acc[4 * q + 1] = acc[4 * q + 2] = acc[4 * q + 3] = 0.f;
+            const float4 p4 = *reinterpret_cast<const float4*>(Pb + byte_off + 16 * q);
+            acc[4 * q + 0] = fmaf(wgt, p4.x, acc[4 * q + 0]);
+            acc[4 * q + 1] = fmaf(wgt, p4.y, acc[4 * q + 1]);
+            acc[4 * q + 2] = fmaf(wgt, p4.z, acc[4 * q + 2]);
+            acc[4 * q + 3] = fmaf(wgt, p4.w, acc[4 * q + 3]);
           }
-          cr = 0;
-          if (++cj < nr_w) {
-            const int2 m = my_meta[cj];
-            cn4 = (int)((uint32_t)m.y >> 12);
-            crow = lo + (m.y & 0xfff);
-          }
+        };
+        auto consume = [&](const uint2& c, const float4& v) {
+          fma4(v.x, (c.x & 0xffffu) << SH);
+          fma4(v.y, (c.x >> 16) << SH);
+          fma4(v.z, (c.y & 0xffffu) << SH);
+          fma4(v.w, (c.y >> 16) << SH);
+        };
+        // rounds is even (padded lengths are multiples of 8): two rounds in flight, two consumed
+        uint2 ca = __ldcs(c2), cb = __ldcs(c2 + 32);
+        float4 va = __ldcs(v4), vb4 = __ldcs(v4 + 32);
+        for (int r = 2; r < rounds; r += 2) {
+          const uint2 na = __ldcs(c2 + r * 32), nb = __ldcs(c2 + r * 32 + 32);
+          const float4 wa = __ldcs(v4 + r * 32), wb = __ldcs(v4 + r * 32 + 32);
+          consume(ca, va);
+          consume(cb, vb4);
+          ca = na;
+          cb = nb;
+          va = wa;
+          vb4 = wb;
         }
-      };
-      uint2 qc[CG_Q];
-      float4 qv[CG_Q];
+        consume(ca, va);
+        consume(cb, vb4);
+        const int m0 = __ldg(t_thread + 2 * p * CGC_MAXT), m1 = __ldg(t_thread + 2 * p * CGC_MAXT + 1);
+        if (m0 >= 0) {
+          if ((m1 >> 16) == 1) {  // a whole row: done
+            const int row = lo + (m0 >> 8);
 #pragma unroll
-      for (int u = 0; u < CG_Q; ++u)
-        if (u < n_rounds) issue(qc[u], qv[u]);
-      for (int t0 = 0; t0 < n_rounds; t0 += CG_Q) {
+            for (int c = 0; c < NCV; ++c) {
+              const float pv = Ps[(size_t)row * NCV + c];
+              const float ap = pv - alpha * acc[c];
+              APg[(int64_t)row * NCV + c] = ap;
+              part[c] = fmaf(pv, ap, part[c]);
+            }
+          } else {  // a segment of a split row: parked in shared memory, added in order below
+            float* dst = s_split + (size_t)((m1 & 0xffff) + (m0 & 0xff)) * NCV;
 #pragma unroll
-        for (int u = 0; u < CG_Q; ++u) {
-          const int t = t0 + u;
-          if (t < n_rounds) {
-            consume(qc[u], qv[u]);
-            if (t + CG_Q < n_rounds) issue(qc[u], qv[u]);
+            for (int c = 0; c < NCV; ++c) dst[c] = acc[c];
           }
         }
       }
+      if (any_split) {  // CTA-uniform
+        __syncthreads();
+        for (int p = 0; p < passes; ++p) {
+          const int m0 = __ldg(t_thread + 2 * p * CGC_MAXT), m1 = __ldg(t_thread + 2 * p * CGC_MAXT + 1);
+          if (m0 >= 0 && (m1 >> 16) > 1 && (m0 & 0xff) == 0) {  // owner of segment 0
+            const int row = lo + (m0 >> 8), ns = m1 >> 16;
+            const float* src = s_split + (size_t)(m1 & 0xffff) * NCV;
 #pragma unroll
-      for (int c = 0; c < NCV; ++c)
-        part[c] = ((lane & 7) == 0 && (lane >> 3) == (c & 3)) ? my_part[c >> 2] : 0.f;
+            for (int c = 0; c < NCV; ++c) {
+              float sum = 0.f;
+              for (int sg = 0; sg < ns; ++sg) sum += src[sg * NCV + c];
+              const float pv = Ps[(size_t)row * NCV + c];
+              const float ap = pv - alpha * sum;
+              APg[(int64_t)row * NCV + c] = ap;
+              part[c] = fmaf(pv, ap, part[c]);
+            }
+          }
+        }
+      }
+    } else {
+      // plain path (a graph whose packed rows did not fit): a warp per row over the merged lists
+      const int32_t* rp = rowptr + vb;
+      const int32_t* rl = rowlen + vb;
+      const uint16_t* mc = mcol + vb * lp_rowcap(k);
+      const float* mv = mval + vb * lp_rowcap(k);
+      for (int row = lo + w; row < hi; row += T >> 5) {
+        if (!vg[row]) continue;
+        float acc[NCV];
+#pragma unroll
+        for (int c = 0; c < NCV; ++c) acc[c] = 0.f;
+        const int L = rl[row];
+        const uint16_t* crow = mc + rp[row];
+        const float* vrow = mv + rp[row];
+        for (int t = lane; t < L; t += 32) {
+          const int cj = (int)crow[t];
+          const float cv = vrow[t];
+#pragma unroll
+          for (int c = 0; c < NCV; ++c) acc[c] = fmaf(cv, Ps[(size_t)cj * NCV + c], acc[c]);
+        }
+#pragma unroll
+        for (int c = 0; c < NCV; ++c) {
+          const float sum = warp_sum(acc[c]);
+          const float pv = Ps[(size_t)row * NCV + c];
+          const float ap = pv - alpha * sum;
+          if (lane == 0) {
+            APg[(int64_t)row * NCV + c] = ap;
+            part[c] = fmaf(pv, ap, part[c]);
+          }
+        }
+      }
     }
     cg_allreduce<NCV>(cluster, &ex, s_warp, part, xcnt, tot);
     float a[NCV];
@@ -1400,7 +1527,7 @@ __global__ __launch_bounds__(CGC_THREADS, 1) void lp_cg_kernel(
     // ---- X += a P ; R -= a AP ; partial R.R      (own rows; P from the staged copy)
 #pragma unroll
     for (int c = 0; c < NCV; ++c) part[c] = 0.f;
-    for (int jj = tid; jj < nloc; jj += CGC_THREADS) {
+    for (int jj = tid; jj < nloc; jj += T) {
       const int row = lo + jj;
 #pragma unroll
       for (int c = 0; c < NCV; ++c) {
@@ -1424,7 +1551,7 @@ __global__ __launch_bounds__(CGC_THREADS, 1) void lp_cg_kernel(
       all_done = all_done && done[c];
     }
     // ---- P = R + beta P   (frozen for finished columns)
-    for (int jj = tid; jj < nloc; jj += CGC_THREADS) {
+    for (int jj = tid; jj < nloc; jj += T) {
       const int row = lo + jj;
 #pragma unroll
       for (int c = 0; c < NCV; ++c)
@@ -1437,7 +1564,7 @@ __global__ __launch_bounds__(CGC_THREADS, 1) void lp_cg_kernel(
     cluster.sync();  // publish P (and make sure nobody still reads Ps before it is restaged)
   }
   // Z (unpadded) from my rows
-  for (int jj = tid; jj < nloc; jj += CGC_THREADS) {
+  for (int jj = tid; jj < nloc; jj += T) {
     const int row = lo + jj;
     for (int c = 0; c < nc; ++c) Zg[(int64_t)row * nc + c] = Xg[(int64_t)row * NCV + c];
   }
@@ -1462,15 +1589,17 @@ static int launch_cg(int CL, int G, size_t smem, cudaStream_t st, const int32_t*
                      float* AP, int32_t* iters_out, float* resid_out, void* scratch,
                      size_t scratch_bytes) {
   cudaError_t e = cudaFuncSetAttribute(lp_cg_kernel<NCV>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   if (e != cudaSuccess) return (int)e;
   if (CL > 8) {
     e = cudaFuncSetAttribute(lp_cg_kernel<NCV>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
     if (e != cudaSuccess) return (int)e;
   }
+  const int T = CGC_MAXT;
+  smem += sizeof(float) * (size_t)CG_MAXPART * NCV;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(CL, G, 1);
-  cfg.blockDim = dim3(CGC_THREADS, 1, 1);
+  cfg.blockDim = dim3(T, 1, 1);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
@@ -1488,33 +1617,36 @@ static int launch_cg(int CL, int G, size_t smem, cudaStream_t st, const int32_t*
       return -1000;
     }
   }
-  // scratch: the schedule table, and (if it is large enough) the row lists re-packed in its order
-  const int2* sched = nullptr;
-  const size_t tab_bytes = align_up(sizeof(int2) * (size_t)G * CL * CG_WARPS * CG_MAXR, 256);
-  const size_t col_bytes = align_up(sizeof(uint16_t) * (size_t)G * nn * lp_rowcap(k), 256);
-  const size_t val_bytes = align_up(sizeof(float) * (size_t)G * nn * lp_rowcap(k), 256);
-  static const bool no_sched = R3DFS_GETENV("R3DFS_CG_NOSCHED") != nullptr;  // A/B: in-kernel schedule
-  static const bool no_pack = R3DFS_GETENV("R3DFS_CG_NOPACK") != nullptr;    // A/B: lists left in place
-  if (scratch && scratch_bytes >= tab_bytes && !no_sched) {
-    unsigned char* sp = reinterpret_cast<unsigned char*>(scratch);
-    int2* tab = reinterpret_cast<int2*>(sp);
-    uint16_t* mcol2 = nullptr;
-    float* mval2 = nullptr;
-    if (scratch_bytes >= tab_bytes + col_bytes + val_bytes && !no_pack) {
-      mcol2 = reinterpret_cast<uint16_t*>(sp + tab_bytes);
-      mval2 = reinterpret_cast<float*>(sp + tab_bytes + col_bytes);
-    }
-    cg_schedule_kernel<<<dim3(CL, G), CGC_THREADS, 0, st>>>(rowptr, rowlen, valid, mcol, mval, nn, k,
-                                                           tab, mcol2, mval2);
-    R3DFS_CHECK_LAUNCH();
-    sched = tab;
-    if (mcol2) {
-      mcol = mcol2;
-      mval = mval2;
-    }
-  }
+  // scratch: per-CTA tables | per-graph flags + row maxima | packed columns | packed weights
+  const int64_t pk_cap = lp_pack_groups(nn, k);  // groups of 4 entries per graph
+  const size_t tab_bytes = align_up(sizeof(int32_t) * (size_t)G * CL * CG_TAB_INTS, 256);
+  const size_t flg_bytes = align_up(sizeof(int32_t) * (size_t)G * (1 + nn), 256);
+  const size_t col_bytes = align_up(sizeof(uint2) * (size_t)G * pk_cap, 256);
+  const size_t val_bytes = align_up(sizeof(float4) * (size_t)G * pk_cap, 256);
+  if (!scratch || scratch_bytes < tab_bytes + flg_bytes + col_bytes + val_bytes)
+    return R3DFS_E_WORKSPACE;
+  unsigned char* sp = reinterpret_cast<unsigned char*>(scratch);
+  int32_t* tab = reinterpret_cast<int32_t*>(sp);
+  int32_t* flags = reinterpret_cast<int32_t*>(sp + tab_bytes);
+  uint2* pcol = reinterpret_cast<uint2*>(sp + tab_bytes + flg_bytes);
+  float4* pval = reinterpret_cast<float4*>(sp + tab_bytes + flg_bytes + col_bytes);
+  e = cudaMemsetAsync(flags, 0, sizeof(int32_t) * (size_t)G, st);
+  if (e != cudaSuccess) return (int)e;
+  e = cudaFuncSetAttribute(cg_pack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CG_PK_SMEM);
+  if (e != cudaSuccess) return (int)e;
+  int32_t* rowmax = flags + G;
+  cg_hist_kernel<<<dim3((nn + 7) / 8, G), 256, 0, st>>>(rowptr, rowlen, valid, mcol, nn, k, rowmax);
+  R3DFS_CHECK_LAUNCH();
+  cg_pack_kernel<<<dim3(CL, G), 1024, CG_PK_SMEM, st>>>(rowptr, rowlen, rowmax, mcol, mval, nn, k,
+                                                       pk_cap, tab, flags, pcol, pval);
+  R3DFS_CHECK_LAUNCH();
+  const int32_t* tabc = tab;
+  const int32_t* flc = flags;
+  const uint2* pc = pcol;
+  const float4* pv = pval;
   e = cudaLaunchKernelEx(&cfg, lp_cg_kernel<NCV>, rowptr, rowlen, mcol, mval, valid, nn, k, Y, nc,
-                         alpha, tol, max_iter, Z, X, R, P, AP, iters_out, resid_out, sched);
+                         alpha, tol, max_iter, Z, X, R, P, AP, iters_out, resid_out, tabc, flc, pc,
+                         pv, pk_cap);
   if (e != cudaSuccess) return (int)e;
   ++r3dfs_launches;
   return 0;
@@ -2049,7 +2181,7 @@ int launch_lp_solve(const int32_t* rowptr, const int32_t* rowlen, const uint16_t
   int dev = 0, n_sm = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-  const int rows_cta_max = CG_WARPS * CG_MAXR;
+  const int rows_cta_max = CGC_MAXT * CG_MAXPASS;
   const int cl_need = (nn + rows_cta_max - 1) / rows_cta_max;
   int cl_start = cl_first ? cl_first : (G <= 4 ? 16 : max(1, min(8, n_sm / G)));
   cl_start = max(cl_start, cl_need);

@@ -514,7 +514,8 @@ int r3dfs_mpti_train_backward(const r3dfs_episode_cfg_t* cfg_in, int in_dim, int
   R3DFS_TRY(launch_ce_grad(w.Z, nn, d.ppad, d.nq_pts, nc, query_y, w_lp, t.dZ, st));
   R3DFS_TRY(launch_lp_solve(w.rowptr, w.rowlen, w.mcol, w.mval, w.valid, 1, nn, kc, t.dZ, nc,
                             cfg.alpha, cfg.cg_tol, cfg.cg_max_iter, t.Gm, w.X, w.R, w.P, w.AP,
-                            nullptr, nullptr, st, /*latency=*/true));
+                            nullptr, nullptr, st, /*latency=*/true, w.D2,
+                            sizeof(float) * episode_d2_floats(1, nn, kc)));
   R3DFS_TRY(launch_lp_adjoint_edges(w.rowptr, w.rowlen, w.mcol, w.mval, w.dinv, w.valid, w.nbr, w.sim,
                                     nn, kc, nc, w.Z, t.Gm, cfg.alpha, cfg.sigma, t.dD, t.gE, st));
   R3DFS_TRY(launch_sim_bwd(w.F, D, w.valid, w.nbr, t.gE, nn, kc, t.dF, st));
