@@ -1292,19 +1292,33 @@ __global__ __launch_bounds__(1024) void cg_pack_kernel(
     __syncwarp();
     uint16_t* c16 = reinterpret_cast<uint16_t*>(gc + base);
     float* v32 = reinterpret_cast<float*>(gv + base);
-    for (int l = 0; l < 32; ++l) {  // the segment owned by lane l of the consumer warp
-      const int i = i0 + l;
-      if (i >= nv) break;
-      const uint32_t key = s_key[i];
-      const int row = lo + (int)((key >> 8) & 0x1fffu), sg = (int)(key & 0xffu), L = rl[row];
+    // metadata of the slice's 32 segments: lane l fetches segment l's, the loop broadcasts them
+    int my_L = 0, my_ptr = 0, my_sg = 0;
+    if (i0 + lane < nv) {
+      const uint32_t key = s_key[i0 + lane];
+      const int row = lo + (int)((key >> 8) & 0x1fffu);
+      my_L = rl[row];
+      my_ptr = rp[row];
+      my_sg = (int)(key & 0xffu);
+    }
+    const int n_here = min(32, nv - i0);
+    for (int l = 0; l < n_here; ++l) {  // the segment owned by lane l of the consumer warp
+      const int L = __shfl_sync(0xffffffffu, my_L, l), sg = __shfl_sync(0xffffffffu, my_sg, l);
+      const int ptr = __shfl_sync(0xffffffffu, my_ptr, l);
       const int r_lo = sg * CG_SEGR, r_hi = r_lo + CG_SEGR;  // ranks of every residue in this segment
-      const uint16_t* c = mc + rp[row];
-      const float* v = mv + rp[row];
+      const uint16_t* c = mc + ptr;
+      const float* v = mv + ptr;
       int seen[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      // one chunk of 32 entries ahead in flight
+      int col_n = lane < L ? (int)c[lane] : -1;
+      float val_n = lane < L ? v[lane] : 0.f;
       for (int t0 = 0; t0 < L; t0 += 32) {
-        const int t = t0 + lane;
-        const int col = t < L ? (int)c[t] : -1;
-        const int res = t < L ? (col & 7) : -1;
+        const int col = col_n;
+        const float val = val_n;
+        const int tn = t0 + 32 + lane;
+        col_n = tn < L ? (int)c[tn] : -1;
+        val_n = tn < L ? v[tn] : 0.f;
+        const int res = col >= 0 ? (col & 7) : -1;
         int rho = -1;
 #pragma unroll
         for (int b = 0; b < 8; ++b) {
@@ -1316,8 +1330,13 @@ __global__ __launch_bounds__(1024) void cg_pack_kernel(
           const int step = 8 * (rho - r_lo) + ((res - l) & 7);  // residue (l + step) mod 8 == res
           const int64_t d = ((int64_t)(step >> 2) * 32 + l) * 4 + (step & 3);
           c16[d] = (uint16_t)col;
-          v32[d] = v[t];
+          v32[d] = val;
         }
+        // every residue class is past this segment: the rest of the row belongs to later segments
+        int done_all = 1;
+#pragma unroll
+        for (int b = 0; b < 8; ++b) done_all &= seen[b] >= r_hi;
+        if (done_all) break;
       }
     }
     __syncwarp();

@@ -62,8 +62,6 @@ __global__ __launch_bounds__(AS_THREADS, 3) void assign_tc_kernel(
   __shared__ uint64_t bar_mma[2];
   __shared__ uint32_t tmem_base_s;
   __shared__ int s_seed[128];
-  __shared__ float s_best[2][128], s_second[2][128];
-  __shared__ int s_arg[2][128];
   const int set = blockIdx.y;
   const int n = set_n[set];
   const int p0 = blockIdx.x * 128;
@@ -146,65 +144,76 @@ __global__ __launch_bounds__(AS_THREADS, 3) void assign_tc_kernel(
   tc::mbar_wait(&bar_mma[(KB - 1) & 1], ((KB - 1) >> 1) & 1);
   tc::tc_fence_after();
 
-  // thread = (point row, column half): best / second-best score over its 64 seed slots
-  const int row = 32 * (w & 3) + lane;
-  const int half = w >> 2;
-  float best = INFINITY, second = INFINITY;
-  int arg = 0;
+  // All MMAs are complete (the last commit covers every earlier one), so the operand stages are
+  // free: they become the 128 x 128 matrix of approximate scores, element j of row r at
+  // r * 128 + ((j + r) & 127) (the rotation keeps a warp's column-wise accesses conflict-free).
+  __syncthreads();
+  float* s_score = reinterpret_cast<float*>(smem);
+  {
+    const int row = 32 * (w & 3) + lane;
+    const int half = w >> 2;
 #pragma unroll
-  for (int cc = 0; cc < 64; cc += 32) {
-    float v[32];
-    tc::tmem_ld32(tmem_d + ((uint32_t)(32 * (w & 3)) << 16) + (uint32_t)(64 * half + cc), v);
+    for (int cc = 0; cc < 64; cc += 32) {
+      float v[32];
+      tc::tmem_ld32(tmem_d + ((uint32_t)(32 * (w & 3)) << 16) + (uint32_t)(64 * half + cc), v);
 #pragma unroll
-    for (int e = 0; e < 32; ++e) {
-      const int j = 64 * half + cc + e;
-      if (j < m) {
-        const float sc = fmaf(-2.f, v[e], sn[set * 128 + j]) - 2e-6f * ss[set * 128 + j];
-        if (sc < best) {
-          second = best;
-          best = sc;
-          arg = j;
-        } else if (sc < second) {
-          second = sc;
-        }
+      for (int e = 0; e < 32; ++e) {
+        const int j = 64 * half + cc + e;
+        const float sc = j < m ? fmaf(-2.f, v[e], sn[set * 128 + j]) - 2e-6f * ss[set * 128 + j]
+                               : INFINITY;
+        s_score[row * 128 + ((j + row) & 127)] = sc;
       }
     }
   }
-  s_best[half][row] = best;
-  s_second[half][row] = second;
-  s_arg[half][row] = arg;
   tc::tc_fence_before();
   __syncthreads();
   if (w == 0) tc::tmem_dealloc(tmem_d, 128);
+  // thread = point: the best approximate score; every seed within a safety margin of it (far above
+  // the Gram-vs-direct rounding difference: 3xTF32 products + FP32 accumulation of 192 terms stay
+  // below 1.2e-5 of |f||s|) is re-evaluated with the reference's direct FP32 arithmetic
+  // (sum (f - s + 1e-6)^2, sqrt, strict <, seeds in index order), so the result equals the direct
+  // evaluation over all seeds.  Usually there is exactly one candidate and nothing is re-evaluated.
   if (tid < 128) {
     const int p = p0 + tid;
     if (p < n) {
-      const float b0 = s_best[0][tid], b1 = s_best[1][tid];
-      const bool first = b0 <= b1;
-      const float bb = first ? b0 : b1;
-      const int ba = first ? s_arg[0][tid] : s_arg[1][tid];
-      const float runner = fminf(first ? b1 : b0, fminf(s_second[0][tid], s_second[1][tid]));
+      const float* sr = s_score + tid * 128;
+      float bb = INFINITY;
+      int ba = 0;
+      for (int j = 0; j < m; ++j) {
+        const float sc = sr[(j + tid) & 127];
+        if (sc < bb) {
+          bb = sc;
+          ba = j;
+        }
+      }
+      const float margin = 5e-5f * fmaxf(1.f, sn[set * 128 + ba] + fabsf(bb));
+      int n_cand = 0;
+      for (int j = 0; j < m; ++j) n_cand += sr[(j + tid) & 127] <= bb + margin;
       int result = ba;
-      const float margin = 1e-3f * fmaxf(1.f, fabsf(bb));
-      if (!(runner - bb > margin)) {
-        // ambiguous: the reference's direct arithmetic over every seed (rare)
-        const float* f = feat + (row0 + p) * (int64_t)D;
+      if (n_cand > 1) {
+        const float4* f4 = reinterpret_cast<const float4*>(feat + (row0 + p) * (int64_t)D);
         float bestd = INFINITY;
-        int bj = 0;
         for (int j = 0; j < m; ++j) {
-          const float* sp = feat + (row0 + s_seed[j]) * (int64_t)D;
+          if (!(sr[(j + tid) & 127] <= bb + margin)) continue;
+          const float4* s4 = reinterpret_cast<const float4*>(feat + (row0 + s_seed[j]) * (int64_t)D);
           float acc = 0.f;
-          for (int d = 0; d < D; ++d) {
-            const float dv = __fadd_rn(f[d] - sp[d], 1e-6f);
+          for (int d4 = 0; d4 < (D >> 2); ++d4) {  // same order as the scalar loop: d ascending
+            const float4 a = f4[d4], b = s4[d4];
+            float dv = __fadd_rn(a.x - b.x, 1e-6f);
+            acc = fmaf(dv, dv, acc);
+            dv = __fadd_rn(a.y - b.y, 1e-6f);
+            acc = fmaf(dv, dv, acc);
+            dv = __fadd_rn(a.z - b.z, 1e-6f);
+            acc = fmaf(dv, dv, acc);
+            dv = __fadd_rn(a.w - b.w, 1e-6f);
             acc = fmaf(dv, dv, acc);
           }
           const float dn = sqrtf(acc);
           if (dn < bestd) {
             bestd = dn;
-            bj = j;
+            result = j;
           }
         }
-        result = bj;
       }
       assign[row0 + p] = result;
     }
