@@ -480,26 +480,53 @@ __global__ __launch_bounds__(K2_THREADS, 1) void knn_tc2_kernel(const float* __r
     }
   } else if (w >= 8) {
     // ------------------------------ loaders: every tile twice ----------------------------------
+    // Two tiles of global loads are in flight per thread (two register sets, prefetch distance 2):
+    // with one, every tile paid a full L2 round trip between "registers free again" and "data
+    // there" (ncu: the loaders' first use of the loaded data was the hottest loader instruction and
+    // the tensor pipe idled 70 % of the time waiting for operands).
     const int lt = tid - 256;
-    TileRegs<KC4, K2_TC, 128> tr;
+    TileRegs<KC4, K2_TC, 128> trA, trB;
     float* xs = reinterpret_cast<float*>(smem + S::XS_OFF);
-    tile_load(tr, x, ld, C, base, base + N, lt, vec_ok);
-    float xn = (lt < K2_TC && lt < N) ? __ldg(xx + base + lt) : 0.f;
-    for (int j = 0; j < 2 * T; ++j) {
-      const int st = j & 1;
-      if (j >= 2) tc::mbar_wait(&bar_full[st], ((j >> 1) - 1) & 1);  // stage's previous MMAs done
-      unsigned char* hi = smem + S::B_OFF + st * 2 * S::TB;
-      unsigned char* lo = hi + S::TB;
-      tile_store(tr, hi, lo, lt);
-      if (lt < K2_TC) xs[(j & 3) * K2_TC + lt] = xn;  // ring of 4, see knn_tc_kernel
-      if (j + 1 < 2 * T) {
-        const int jn = j + 1 < T ? j + 1 : j + 1 - T;
-        tile_load(tr, x, ld, C, base + (int64_t)jn * K2_TC, base + N, lt, vec_ok);
-        const int cn_ = jn * K2_TC + lt;
-        xn = (lt < K2_TC && cn_ < N) ? __ldg(xx + base + cn_) : 0.f;
+    auto tile_of = [&](int j) { return j < T ? j : j - T; };
+    auto norm_of = [&](int j) {
+      const int cn_ = tile_of(j) * K2_TC + lt;
+      return (lt < K2_TC && cn_ < N) ? __ldg(xx + base + cn_) : 0.f;
+    };
+    tile_load(trA, x, ld, C, base, base + N, lt, vec_ok);
+    float xnA = norm_of(0), xnB = 0.f;
+    if (2 * T > 1) {
+      tile_load(trB, x, ld, C, base + (int64_t)tile_of(1) * K2_TC, base + N, lt, vec_ok);
+      xnB = norm_of(1);
+    }
+    for (int j = 0; j < 2 * T; j += 2) {  // 2 T is even
+      {
+        const int st = 0;
+        if (j >= 2) tc::mbar_wait(&bar_full[st], ((j >> 1) - 1) & 1);  // stage's previous MMAs done
+        unsigned char* hi = smem + S::B_OFF + st * 2 * S::TB;
+        unsigned char* lo = hi + S::TB;
+        tile_store(trA, hi, lo, lt);
+        if (lt < K2_TC) xs[(j & 3) * K2_TC + lt] = xnA;  // ring of 4, see knn_tc_kernel
+        if (j + 2 < 2 * T) {
+          tile_load(trA, x, ld, C, base + (int64_t)tile_of(j + 2) * K2_TC, base + N, lt, vec_ok);
+          xnA = norm_of(j + 2);
+        }
+        tc::fence_async_smem();
+        mbar_arrive(&bar_sfull[st]);
       }
-      tc::fence_async_smem();
-      mbar_arrive(&bar_sfull[st]);
+      {
+        const int st = 1, j1 = j + 1;
+        if (j1 >= 2) tc::mbar_wait(&bar_full[st], ((j1 >> 1) - 1) & 1);
+        unsigned char* hi = smem + S::B_OFF + st * 2 * S::TB;
+        unsigned char* lo = hi + S::TB;
+        tile_store(trB, hi, lo, lt);
+        if (lt < K2_TC) xs[(j1 & 3) * K2_TC + lt] = xnB;
+        if (j1 + 2 < 2 * T) {
+          tile_load(trB, x, ld, C, base + (int64_t)tile_of(j1 + 2) * K2_TC, base + N, lt, vec_ok);
+          xnB = norm_of(j1 + 2);
+        }
+        tc::fence_async_smem();
+        mbar_arrive(&bar_sfull[st]);
+      }
     }
   } else {
     // ------------------------------ selectors ------------------------------------------------
