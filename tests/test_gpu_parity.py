@@ -894,6 +894,30 @@ def test_episode_ragged_shapes_vs_oracle(fixture_sd, n_way, k_shot, n_pts, n_sub
     assert abs(float(loss) - float(ref["loss"])) < 1e-4
 
 
+@pytest.mark.parametrize("noise_type,n_way,ratio", [("sym", 2, 0.4), ("pair", 3, 0.4),
+                                                    ("partial", 2, 0.2), ("ood", 3, 0.2)])
+def test_noisy_episode_types_vs_oracle(fixture_sd, model, noise_type, n_way, ratio):
+    """The four noise models of the reference's episode sampler (dataloaders/loader.py:669-810:
+    symmetric, pair, partial and out-of-distribution shots) through the whole CUDA episode: clean
+    flags, prototype counts and logits against the oracle's graph half on the CUDA features."""
+    ds = "scannet" if n_way == 3 else "s3dis"
+    ep = make_episode(60 + n_way, n_way, 5, dataset=ds, noise_ratio=ratio, noise_type=noise_type)
+    m = model(n_way, 5)
+    pred, loss = m(ep.support_x.to(DEV), ep.support_y.to(DEV), ep.query_x.to(DEV),
+                   ep.query_y.to(DEV), gt_support_y=ep.gt_support_y.to(DEV), eval=True)
+    sf = m.getFeatures(ep.support_x.reshape(n_way * 5, 9, -1).to(DEV)).cpu()
+    qf = m.getFeatures(ep.query_x.to(DEV)).cpu()
+    with torch.no_grad():
+        ref = O.forward_episode(fixture_sd, ep.support_x, ep.support_y, ep.query_x, ep.query_y,
+                                eval_mdns=True, support_feat=sf, query_feat=qf)
+    assert torch.equal(m._last_diag["clean_flag"][0].cpu(), ref["clean_flag"])
+    assert m._last_diag["proto_count"][0].cpu().tolist() == ref["proto_count"]
+    rp, pred = ref["query_pred"], pred.cpu()
+    assert float((pred - rp).abs().max() / rp.abs().max()) < 1e-3
+    assert float((pred.argmax(1) == rp.argmax(1)).float().mean()) >= 0.999
+    assert abs(float(loss) - float(ref["loss"])) < 1e-4
+
+
 def test_drop_in_test_few_shot_matches_per_episode_loop(model, fixture_sd):
     """evaluate.test_few_shot (reference eval_noise.py:75-113 signature) on a loader of collated
     episodes == the reference's own loop: learner.test per episode + evaluate_metric."""
