@@ -80,10 +80,12 @@ bool simt_gemm_forced() {
 }
 
 int launch_knn_auto(const float* x, int ld, int C, const float* xx, int64_t B, int N, int k,
-                    int32_t* idx32, int64_t* idx64, int impl, cudaStream_t st) {
-  if (impl == 2) return launch_knn_tc(x, ld, C, xx, B, N, k, idx32, idx64, st);
+                    int32_t* idx32, int64_t* idx64, int impl, cudaStream_t st, void* split_ws,
+                    size_t split_bytes) {
+  if (impl == 2)
+    return launch_knn_tc(x, ld, C, xx, B, N, k, idx32, idx64, st, split_ws, split_bytes);
   if (impl == 0 && !simt_gemm_forced() && C <= 64)
-    return launch_knn_tc(x, ld, C, xx, B, N, k, idx32, idx64, st);
+    return launch_knn_tc(x, ld, C, xx, B, N, k, idx32, idx64, st, split_ws, split_bytes);
   return launch_knn(x, ld, C, xx, B, N, k, idx32, idx64, st);
 }
 
@@ -157,7 +159,9 @@ int encoder_forward(const r3dfs_weights_t* w, const float* xp, int64_t B, int N,
     const int ld = i == 0 ? w->in_dim : 192;
     const int C = i == 0 ? w->in_dim : 64;
     R3DFS_TRY(launch_row_norms(in, M, ld, C, e.xx, st));
-    R3DFS_TRY(launch_knn_auto(in, ld, C, e.xx, B, N, k, e.idx, nullptr, 0, st));
+    // h512 is idle until the MLP: it holds the kNN kernel's pre-split candidate tiles
+    R3DFS_TRY(launch_knn_auto(in, ld, C, e.xx, B, N, k, e.idx, nullptr, 0, st, e.h512,
+                              sizeof(float) * (size_t)M * 512));
     if (sr) sr->mark(R3DFS_ST_KNN0 + 3 * i, st);
     R3DFS_TRY(launch_fold_edge_w1(w->ec_w1[i], w->ec_s1[i], w->ec_t1[i], C, e.wpq, e.spq, e.tpq, st));
     R3DFS_TRY(launch_linear_auto(in, ld, e.wpq, e.spq, e.tpq, ACT_NONE, M, C, 128, e.PQ, 128,
@@ -217,8 +221,8 @@ const char* r3dfs_strerror(int code) {
 
 // ---- knn -------------------------------------------------------------------------------------
 size_t r3dfs_knn_workspace(int64_t B, int64_t C, int64_t N, int k) {
-  (void)k;
-  return align_up(sizeof(float) * B * N * C, 256) + align_up(sizeof(float) * B * N, 256) + 512;
+  return align_up(sizeof(float) * B * N * C, 256) + align_up(sizeof(float) * B * N, 256) +
+         align_up(knn_split_bytes((int)C, B, (int)N, k), 256) + 768;
 }
 
 int r3dfs_knn(const float* x, int64_t B, int64_t C, int64_t N, int64_t sb, int64_t sc, int64_t sn,
@@ -236,10 +240,14 @@ int r3dfs_knn_ex(const float* x, int64_t B, int64_t C, int64_t N, int64_t sb, in
   WsBump ws(wsp, ws_bytes);
   float* xp = ws.take<float>(B * N * C);
   float* xx = ws.take<float>(B * N);
+  const size_t split_bytes = knn_split_bytes((int)C, B, (int)N, k);
+  unsigned char* split = split_bytes ? ws.take<unsigned char>(split_bytes) : nullptr;
+  if (!ws.ok()) return R3DFS_E_WORKSPACE;
   R3DFS_TRY(launch_to_point_major(x, B, C, N, sb, sc, sn, xp, st));
   R3DFS_TRY(launch_row_norms(xp, B * N, (int)C, (int)C, xx, st));
   if (impl < 0 || impl > 2) return R3DFS_E_UNSUPPORTED;
-  return launch_knn_auto(xp, (int)C, (int)C, xx, B, (int)N, k, nullptr, idx_out, impl, st);
+  return launch_knn_auto(xp, (int)C, (int)C, xx, B, (int)N, k, nullptr, idx_out, impl, st, split,
+                         split_bytes);
 }
 
 // ---- get_edge_feature --------------------------------------------------------------------------
@@ -288,7 +296,8 @@ size_t r3dfs_edgeconv_workspace(int64_t B, int64_t C, int64_t N, int k) {
   const int64_t M = B * N;
   return align_up(sizeof(float) * M * C, 256) + align_up(sizeof(float) * M, 256) +
          align_up(sizeof(int32_t) * M * k, 256) + align_up(sizeof(float) * 128 * C, 256) +
-         2 * 512 + align_up(sizeof(float) * M * 128, 256) + 1024;
+         2 * 512 + align_up(sizeof(float) * M * 128, 256) +
+         align_up(knn_split_bytes((int)C, B, (int)N, k), 256) + 1280;
 }
 
 int r3dfs_edgeconv(const float* x, int64_t B, int64_t C, int64_t N, int64_t sb, int64_t sc,
@@ -310,10 +319,13 @@ int r3dfs_edgeconv(const float* x, int64_t B, int64_t C, int64_t N, int64_t sb, 
   float* spq = ws.take<float>(128);
   float* tpq = ws.take<float>(128);
   float* PQ = ws.take<float>(M * 128);
+  const size_t split_bytes = knn_split_bytes((int)C, B, (int)N, k);
+  unsigned char* split = split_bytes ? ws.take<unsigned char>(split_bytes) : nullptr;
   if (!ws.ok()) return R3DFS_E_WORKSPACE;
   R3DFS_TRY(launch_to_point_major(x, B, C, N, sb, sc, sn, xp, st));
   R3DFS_TRY(launch_row_norms(xp, M, (int)C, (int)C, xx, st));
-  R3DFS_TRY(launch_knn_auto(xp, (int)C, (int)C, xx, B, (int)N, k, idx, idx_out, 0, st));
+  R3DFS_TRY(launch_knn_auto(xp, (int)C, (int)C, xx, B, (int)N, k, idx, idx_out, 0, st, split,
+                            split_bytes));
   R3DFS_TRY(launch_fold_edge_w1(w1, s1, t1, (int)C, wpq, spq, tpq, st));
   R3DFS_TRY(launch_linear_auto(xp, (int)C, wpq, spq, tpq, ACT_NONE, M, (int)C, 128, PQ, 128,
                                identity_map(), st));

@@ -112,10 +112,14 @@ int launch_row_norms_batched(const float* x, int64_t xs, int batch, int64_t rows
 int launch_knn(const float* x, int ld, int C, const float* xx, int64_t B, int N, int k,
                int32_t* idx32, int64_t* idx64, cudaStream_t st);
 int launch_knn_tc(const float* x, int ld, int C, const float* xx, int64_t B, int N, int k,
-                  int32_t* idx32, int64_t* idx64, cudaStream_t st);
+                  int32_t* idx32, int64_t* idx64, cudaStream_t st, void* split_ws = nullptr,
+                  size_t split_bytes = 0);
+// scratch the TMA-fed kNN kernel wants for the pre-split candidate tiles (0: shape not served)
+size_t knn_split_bytes(int C, int64_t B, int N, int k);
 // impl 0: tensor cores when the shape allows (and R3DFS_SIMT_GEMM is unset), 1: CUDA cores, 2: tensor cores
 int launch_knn_auto(const float* x, int ld, int C, const float* xx, int64_t B, int N, int k,
-                    int32_t* idx32, int64_t* idx64, int impl, cudaStream_t st);
+                    int32_t* idx32, int64_t* idx64, int impl, cudaStream_t st,
+                    void* split_ws = nullptr, size_t split_bytes = 0);
 int launch_linear(const float* X, int ldx, const float* W, const float* s, const float* t, int act,
                   int64_t M, int K, int Nout, float* Y, int ldy, RowMap map, cudaStream_t st);
 int launch_linear_tc(const float* X, int ldx, const float* W, const float* s, const float* t,

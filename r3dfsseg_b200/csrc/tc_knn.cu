@@ -687,6 +687,476 @@ static int launch_knn_tc2_t(const float* x, int ld, int C, const float* xx, int6
   return 0;
 }
 
+// ---------------------------------------------------------------------------------------------
+// TMA-fed two-pass variant with the query operand in TMEM.
+// What bounded knn_tc2_kernel (per-tile clock64 timeline of one CTA, scripts/microbench/knn_trace.cu,
+// and scripts/microbench/mma_rate.cu):
+//  * tcgen05.mma kind::tf32 with both operands in shared memory reads 32 B per operand row per
+//    instruction: at N = 64 that is 6 KB in the 48 cycles the instruction takes alone — the whole
+//    128 B/clk of the SM's shared memory — so every other shared-memory access (the loaders' tile
+//    stores, the selectors' queue) stretched the MMAs to 59 (pass 1) / 80 (pass 2) cycles each;
+//    and a 128x64x8 instruction never goes below ~45 cycles (1460 MAC/clk) whereas 128x128x8 runs
+//    at 64 cycles = 2047 MAC/clk, the TF32 peak;
+//  * the issuing thread is effectively synchronous (the accumulator is complete ~25 cycles after
+//    the last issue returns), so its ~400 cycles of barrier round trips per tile idle the pipe;
+//  * the four loader warps re-split every candidate tile in every one of a cloud's 16 CTAs, twice.
+// Here:  the 128 query rows live in TMEM (hi and lo halves, written once with tcgen05.st) and are
+// the MMA's A operand, so an instruction reads only its 4 KB B tile from shared memory; candidate
+// tiles are 128 wide (full-rate MMAs, half as many barrier round trips per candidate); the split
+// happens ONCE per point — knn_split_kernel writes every 128-candidate tile of a cloud to global
+// memory exactly as the MMA wants it in shared memory (hi tile, lo tile, then the 128 squared
+// norms) and one cp.async.bulk per stage brings it in: no loader warps.  Same split arithmetic,
+// same accumulation order, same selection: neighbour lists are bit-identical to knn_tc2_kernel's.
+//   warps 0-7 selectors (TMEM lane quarter, 64-column half), warp 8 lane 0 = copy producer,
+//   warp 9 lane 0 = MMA issue; NST operand stages, 3 accumulators of 128 columns behind the
+//   128 columns of Q (512 TMEM columns), norms in a ring of 8.
+// ---------------------------------------------------------------------------------------------
+// per-tile timestamps of one CTA (scripts/microbench/knn_trace.cu compiles this file with KNN_TRACE)
+#ifdef KNN_TRACE
+__device__ long long g_knn_trace[8 * 4096];
+#define KNN_TR(slot, j) \
+  do { if (blockIdx.x == KNN_TRACE_BX && blockIdx.y == KNN_TRACE_BY) g_knn_trace[(slot) * 4096 + (j)] = clock64(); } while (0)
+#else
+#define KNN_TR(slot, j) do { } while (0)
+#endif
+#define K3_THREADS 576  // warps 0-15 selectors, 16 copy producer, 17 MMA issue
+#define K3_TC 128
+#define K3_NACC 3
+#define K3_NR 8
+#define K3_G 16   // group maxima per selector thread (64 per row)
+
+template <int KC4>
+struct KnnSplit {
+  static constexpr int TB = tc::tile_bytes(K3_TC, KC4);
+  static constexpr int BLK = 2 * TB + K3_TC * 4;  // hi, lo, norms
+};
+
+template <int KC4>
+__global__ __launch_bounds__(256) void knn_split_kernel(const float* __restrict__ x, int ld, int C,
+                                                        const float* __restrict__ xx, int N,
+                                                        unsigned char* __restrict__ out) {
+  extern __shared__ __align__(128) unsigned char sm[];
+  using P = KnnSplit<KC4>;
+  constexpr int LBO = tc::tile_lbo(K3_TC);
+  const int t = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+  const int T = gridDim.x;
+  const int64_t base = (int64_t)b * N;
+  const bool vec_ok = ((ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
+  knn_store_tile_r<KC4, K3_TC>(sm, sm + P::TB, x, ld, C, base + (int64_t)t * K3_TC, base + N, tid,
+                               256, vec_ok);
+  if (tid < K3_TC) {
+    const int cn = t * K3_TC + tid;
+    reinterpret_cast<float*>(sm + 2 * P::TB)[tid] = cn < N ? xx[base + cn] : 0.f;
+  }
+  if (tid < 2 * KC4)  // the 16 bytes of padding behind every chunk column (never read by the MMA)
+    *reinterpret_cast<float4*>(sm + (tid / KC4) * P::TB + (tid % KC4) * LBO + K3_TC * 16) =
+        make_float4(0.f, 0.f, 0.f, 0.f);
+  __syncthreads();
+  float4* dst = reinterpret_cast<float4*>(out + ((int64_t)b * T + t) * P::BLK);
+  const float4* src = reinterpret_cast<const float4*>(sm);
+  for (int i = tid; i < P::BLK / 16; i += 256) dst[i] = src[i];
+}
+
+template <int KC4, int NST, int CAP>
+struct Knn3Smem {
+  static constexpr int TB = tc::tile_bytes(K3_TC, KC4);
+  static constexpr int B_OFF = 0;                            // NST stages x (hi, lo)
+  static constexpr int XS_OFF = B_OFF + NST * 2 * TB;        // |x_j|^2 ring [K3_NR][128]
+  static constexpr int QK_OFF = XS_OFF + K3_NR * K3_TC * 4;  // queue keys [CAP][512] float
+  static constexpr int QC_OFF = QK_OFF + CAP * 512 * 4;      // queue columns [CAP][512] u16
+  static constexpr int TOTAL = QC_OFF + CAP * 512 * 2;
+  static_assert(CAP >= K3_G + 1 && CAP >= 17, "queue region: pass-1 group maxima / half a chunk");
+  static_assert(NST * 2 * TB >= 3 * 20 * 128 * 8, "the final merge borrows the operand stages");
+};
+
+// descending bitonic sort of 16 registers
+__device__ __forceinline__ void sort16_desc(float (&v)[16]) {
+#pragma unroll
+  for (int size = 2; size <= 16; size <<= 1) {
+#pragma unroll
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const int j = i ^ stride;
+        if (j > i) {
+          const bool desc = (i & size) == 0;
+          const float a = v[i], b = v[j];
+          v[i] = desc ? fmaxf(a, b) : fminf(a, b);
+          v[j] = desc ? fminf(a, b) : fmaxf(a, b);
+        }
+      }
+    }
+  }
+}
+
+template <int KC4, int NST, int CAP>
+__global__ __launch_bounds__(K3_THREADS, 1) void knn_tc3_kernel(
+    const float* __restrict__ x, int ld, int C, const float* __restrict__ xx,
+    const unsigned char* __restrict__ split, int N, int k, int32_t* __restrict__ idx32,
+    int64_t* __restrict__ idx64) {
+  constexpr int KL = 20;
+  constexpr int QCOLS = 8 * KC4;  // TMEM columns of the query operand (hi + lo)
+  constexpr int ACC0 = 128;       // first accumulator column
+  extern __shared__ __align__(128) unsigned char smem[];
+  using S = Knn3Smem<KC4, NST, CAP>;
+  using P = KnnSplit<KC4>;
+  static_assert(QCOLS <= ACC0, "query operand overlaps the accumulators");
+  __shared__ uint64_t bar_sfull[NST];       // operand stage s landed (bulk-copy bytes)
+  __shared__ uint64_t bar_sfree[NST];       // operand stage s read by its MMAs
+  __shared__ uint64_t bar_full[K3_NACC];    // accumulator a complete
+  __shared__ uint64_t bar_tfree[K3_NACC];   // accumulator a drained by the 512 selector threads
+  __shared__ uint64_t bar_q[2];             // query tile landed / moved on into TMEM
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int b = blockIdx.y;
+  const int q0 = blockIdx.x * KT_TQ;
+  const int64_t base = (int64_t)b * N;
+  constexpr int LBOB = tc::tile_lbo(K3_TC);
+  constexpr uint32_t IDESC = tc::make_idesc_tf32(128, K3_TC);
+  const int T = (N + K3_TC - 1) / K3_TC;
+  const int ksteps = (min(C, 4 * KC4) + 7) / 8;
+  if (tid == 0) KNN_TR(6, 4000);
+
+  if (tid == 0) {
+    for (int i = 0; i < NST; ++i) {
+      tc::mbar_init(&bar_sfull[i], 1);
+      tc::mbar_init(&bar_sfree[i], 1);
+    }
+    for (int i = 0; i < K3_NACC; ++i) {
+      tc::mbar_init(&bar_full[i], 1);
+      tc::mbar_init(&bar_tfree[i], 512);
+    }
+    tc::mbar_init(&bar_q[0], 1);
+    tc::mbar_init(&bar_q[1], 128);
+    tc::mbar_fence_init();
+  }
+  if (w == 0) tc::tmem_alloc(&tmem_base_s, 512);
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_d = tmem_base_s;
+  if (tid == 0) KNN_TR(6, 4001);
+
+  if (w == 16) {
+    // ------------------------------ copy producer: every tile twice --------------------------
+    // The CTA's 128 query rows are candidate tile blockIdx.x of the same cloud: their pre-split
+    // copy goes through the last operand stage on its way into TMEM (thread-per-row global loads
+    // took 7000 cycles here; this takes the latency of one bulk copy).
+    if (lane == 0) {
+      const unsigned char* src0 = split + (int64_t)b * T * P::BLK;
+      tc::mbar_arrive_expect_tx(&bar_q[0], (uint32_t)(2 * S::TB));
+      tc::bulk_g2s(smem + S::B_OFF + (NST - 1) * 2 * S::TB, src0 + (int64_t)blockIdx.x * P::BLK,
+                   2 * S::TB, &bar_q[0]);
+      for (int j = 0; j < 2 * T; ++j) {
+        const int s = j % NST;
+        if (j >= NST) tc::mbar_wait(&bar_sfree[s], ((j / NST) - 1) & 1);
+        if (j == NST - 1) tc::mbar_wait(&bar_q[1], 0);  // the query tile has left the stage
+        KNN_TR(0, j);
+        const unsigned char* src = src0 + (int64_t)(j < T ? j : j - T) * P::BLK;
+        tc::mbar_arrive_expect_tx(&bar_sfull[s], (uint32_t)P::BLK);
+        tc::bulk_g2s(smem + S::B_OFF + s * 2 * S::TB, src, 2 * S::TB, &bar_sfull[s]);
+        // norm ring of 8: slot j is rewritten by tile j + 8, whose copy waits for MMA j + 8 - NST
+        // (>= j + 4), which was issued after the selectors released tile j + 4 - K3_NACC >= j
+        tc::bulk_g2s(smem + S::XS_OFF + (j & (K3_NR - 1)) * K3_TC * 4, src + 2 * S::TB, K3_TC * 4,
+                     &bar_sfull[s]);
+      }
+    }
+  } else if (w < 4) {  // query rows -> TMEM (a warp can only touch its own lane quarter)
+    const int row = 32 * w + lane;
+    const unsigned char* qh = smem + S::B_OFF + (NST - 1) * 2 * S::TB + row * 16;
+    const uint32_t trow = tmem_d + ((uint32_t)(32 * w) << 16);
+    tc::mbar_wait(&bar_q[0], 0);
+#pragma unroll
+    for (int c4 = 0; c4 < KC4; c4 += 4) {
+      float hi[16], lo[16];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float4 h = *reinterpret_cast<const float4*>(qh + (c4 + u) * LBOB);
+        const float4 l = *reinterpret_cast<const float4*>(qh + S::TB + (c4 + u) * LBOB);
+        hi[4 * u] = h.x; hi[4 * u + 1] = h.y; hi[4 * u + 2] = h.z; hi[4 * u + 3] = h.w;
+        lo[4 * u] = l.x; lo[4 * u + 1] = l.y; lo[4 * u + 2] = l.z; lo[4 * u + 3] = l.w;
+      }
+      tc::tmem_st16(trow + (uint32_t)(4 * c4), hi);
+      tc::tmem_st16(trow + (uint32_t)(4 * KC4 + 4 * c4), lo);
+    }
+    mbar_arrive(&bar_q[1]);
+    tc::tmem_st_wait();
+  }
+  if (w != 16) {  // all but the producer warp: the query operand is in TMEM
+    tc::tc_fence_before();
+    asm volatile("bar.sync 3, %0;" ::"n"(K3_THREADS - 32) : "memory");
+    tc::tc_fence_after();
+  }
+
+  if (w == 16) {
+    // (done above)
+  } else if (w == 17) {
+    // ------------------------------ MMA issue: the whole warp walks the loop, one elected lane
+    // issues (tc::mma_tf32_ts_elect) ----------------------------------------------------------
+    const uint32_t aq_hi = tmem_d, aq_lo = tmem_d + 4 * KC4;
+    constexpr uint64_t KB = tc::desc_kstep(LBOB);
+    for (int j = 0; j < 2 * T; ++j) {
+      const int s = j % NST, a = j % K3_NACC;
+      tc::mbar_wait(&bar_sfull[s], (j / NST) & 1);
+      if (lane == 0) KNN_TR(1, j);
+      if (j >= K3_NACC) tc::mbar_wait(&bar_tfree[a], ((j / K3_NACC) - 1) & 1);
+      if (lane == 0) KNN_TR(2, j);
+      tc::tc_fence_after();
+      const uint32_t b_hi = tc::smem_u32(smem + S::B_OFF + s * 2 * S::TB), b_lo = b_hi + S::TB;
+      const uint32_t d = tmem_d + ACC0 + a * K3_TC;
+      const uint64_t dbh = tc::make_desc(b_hi, LBOB, 128), dbl = tc::make_desc(b_lo, LBOB, 128);
+      tc::mma_tf32_ts_elect<false>(d, aq_lo, dbh, IDESC);
+      tc::mma_tf32_ts_elect<true>(d, aq_hi, dbl, IDESC);
+      tc::mma_tf32_ts_elect<true>(d, aq_hi, dbh, IDESC);
+#pragma unroll
+      for (int ks = 1; ks < 2 * KC4 / 4; ++ks) {
+        if (ks < ksteps) {
+          tc::mma_tf32_ts_elect<true>(d, aq_lo + 8 * ks, dbh + ks * KB, IDESC);
+          tc::mma_tf32_ts_elect<true>(d, aq_hi + 8 * ks, dbl + ks * KB, IDESC);
+          tc::mma_tf32_ts_elect<true>(d, aq_hi + 8 * ks, dbh + ks * KB, IDESC);
+        }
+      }
+      tc::mma_commit_elect(&bar_sfree[s]);
+      tc::mma_commit_elect(&bar_full[a]);
+      if (lane == 0) KNN_TR(3, j);
+    }
+  } else {
+    // ------------------------------ selectors --------------------------------------------------
+    // thread = (query row, 32-column quarter of every 128-candidate tile): 16 warps, four per
+    // scheduler — with eight the selection was latency-bound at half an instruction per cycle and
+    // scheduler, and slower than the MMAs in pass 2
+    float* qk = reinterpret_cast<float*>(smem + S::QK_OFF);
+    unsigned short* qc = reinterpret_cast<unsigned short*>(smem + S::QC_OFF);
+    const int row = 32 * (w & 3) + lane;
+    const int cq = w >> 2;
+    const int q = q0 + row;
+    const float nq = (q < N) ? -xx[base + q] : 0.f;
+    const float* xs = reinterpret_cast<const float*>(smem + S::XS_OFF) + 32 * cq;
+    const uint32_t taddr = tmem_d + ((uint32_t)(32 * (w & 3)) << 16) + (uint32_t)(ACC0 + 32 * cq);
+    // ---- pass 1: group maxima (16 per thread, 64 per row) ------------------------------------
+#pragma unroll 1
+    for (int s = 0; s < K3_G; ++s) qk[s * 512 + tid] = -INFINITY;
+#pragma unroll 1
+    for (int j = 0; j < T; ++j) {
+      const int a = j % K3_NACC;
+      if (tid == 0) KNN_TR(7, j);
+      // (the tile's norms landed before its MMAs were issued: the issuing thread waited for the
+      // copy barrier.  The selectors must NOT wait on that barrier themselves — a stage can be
+      // refilled for tile j + NST before they reach tile j, and a parity wait two phases behind
+      // never returns)
+      tc::mbar_wait(&bar_full[a], (j / K3_NACC) & 1);
+      if (tid == 0) KNN_TR(4, j);
+      tc::tc_fence_after();
+      float v[32];
+      tc::tmem_ld32(taddr + (uint32_t)(a * K3_TC), v);
+      if (tid == 0) KNN_TR(5, j);
+      const int c0 = j * K3_TC + 32 * cq;
+      knn_keys32(v, nq, xs + (j & (K3_NR - 1)) * K3_TC);
+      tc::tc_fence_before();
+      mbar_arrive(&bar_tfree[a]);  // accumulator and the tile's norms are consumed
+      if (tid == 0) KNN_TR(6, j);
+      float m = -INFINITY;
+      if (c0 + 32 <= N) {
+#pragma unroll
+        for (int e = 0; e < 32; ++e) m = fmaxf(m, v[e]);
+      } else {
+#pragma unroll
+        for (int e = 0; e < 32; ++e)
+          if (c0 + e < N) m = fmaxf(m, v[e]);
+      }
+      float* g = qk + (j & (K3_G - 1)) * 512 + tid;
+      *g = fmaxf(*g, m);
+    }
+    // ---- bound.  Any lower bound of the row's k-th best key is valid; the tightest one from the 64
+    // group maxima is their k-th largest, but selecting it (a 64-element sort, or a 4-way merge of
+    // the four threads' sorted runs) took 8000-9000 cycles in which the tensor pipe ran dry after
+    // three tiles.  Branch-free instead: every thread sorts its 16 maxima, the two threads of a
+    // 64-column half combine their runs into the ceil(k/2)-th largest of the half's 32 maxima
+    // (k-th of two sorted runs = max_i min(A[i-1], B[k-i-1])), and tau = the smaller of the two
+    // halves' values: 2 ceil(k/2) >= k keys lie at or above it.  ~17 % more candidates reach the
+    // queue (28 instead of 24 per row at k = 20). ------------------------------------------------
+    float tau;
+    {
+      float gm[K3_G];
+#pragma unroll
+      for (int s = 0; s < K3_G; ++s) gm[s] = qk[s * 512 + tid];
+      sort16_desc(gm);
+#pragma unroll
+      for (int s = 0; s < K3_G; ++s) qk[s * 512 + tid] = gm[s];
+      asm volatile("bar.sync 2, 512;" ::: "memory");
+      const int kh = (k + 1) >> 1;          // <= 10
+      const float* pb = qk + (tid ^ 128);   // the other 32-column quarter of this half, same row
+      float th = -INFINITY;
+#pragma unroll
+      for (int i = 0; i <= (KL + 1) / 2; ++i) {
+        if (i <= kh) {
+          const float av = i == 0 ? INFINITY : gm[i - 1];
+          const int bi = kh - i - 1;
+          const float bv = bi < 0 ? INFINITY : pb[bi * 512];
+          th = fmaxf(th, fminf(av, bv));
+        }
+      }
+      float* tx = reinterpret_cast<float*>(qc);  // the column queue is idle until pass 2
+      tx[tid] = th;
+      asm volatile("bar.sync 2, 512;" ::: "memory");
+      tau = fminf(th, tx[tid ^ 256]);
+    }
+    asm volatile("bar.sync 2, 512;" ::: "memory");  // the maxima are read: the region becomes the queue
+    // ---- pass 2: queue everything that reaches the bound, build the lists lazily -------------------
+    float lv[KL];
+    int li[KL];
+#pragma unroll
+    for (int i = 0; i < KL; ++i) {
+      lv[i] = -INFINITY;
+      li[i] = 0;
+    }
+    int qcnt = 0;
+    auto drain = [&]() {
+      const int mx = __reduce_max_sync(0xffffffffu, qcnt);
+      for (int e = 0; e < mx; ++e) {
+        if (e < qcnt) {
+          const float key = qk[e * 512 + tid];
+          if (key > lv[KL - 1]) list_insert<KL>(lv, li, key, (int)qc[e * 512 + tid]);
+        }
+      }
+      qcnt = 0;
+    };
+#pragma unroll 1
+    for (int j2 = 0; j2 < T; ++j2) {
+      const int j = T + j2;
+      const int a = j % K3_NACC;
+      if (tid == 0) KNN_TR(7, j);
+      tc::mbar_wait(&bar_full[a], (j / K3_NACC) & 1);
+      if (tid == 0) KNN_TR(4, j);
+      tc::tc_fence_after();
+      float v[32];
+      tc::tmem_ld32(taddr + (uint32_t)(a * K3_TC), v);
+      if (tid == 0) KNN_TR(5, j);
+      const int c0 = j2 * K3_TC + 32 * cq;
+      knn_keys32(v, nq, xs + (j & (K3_NR - 1)) * K3_TC);
+      tc::tc_fence_before();
+      mbar_arrive(&bar_tfree[a]);
+      if (tid == 0) KNN_TR(6, j);
+      const int nvalid = N - c0;
+#pragma unroll
+      for (int hh = 0; hh < 32; hh += 16) {  // a queue holds half a chunk at least
+        if (__any_sync(0xffffffffu, qcnt > CAP - 16)) drain();
+        // one comparison per key: v >= tau and v > thr  <=>  v >= max(tau, next float above thr)
+        const float thr = lv[KL - 1];
+        const int tb = __float_as_int(thr);  // next float above thr (-inf -> -FLT_MAX, -0 -> denorm min)
+        const float cut = fmaxf(tau, __int_as_float(tb >= 0 ? tb + 1 : (tb == (int)0x80000000 ? 1 : tb - 1)));
+        if (nvalid >= 32) {
+#pragma unroll
+          for (int e = hh; e < hh + 16; ++e) {
+            if (v[e] >= cut) {
+              qk[qcnt * 512 + tid] = v[e];
+              qc[qcnt * 512 + tid] = (unsigned short)(c0 + e);
+              ++qcnt;
+            }
+          }
+        } else {
+#pragma unroll
+          for (int e = hh; e < hh + 16; ++e) {
+            if (v[e] >= cut && e < nvalid) {
+              qk[qcnt * 512 + tid] = v[e];
+              qc[qcnt * 512 + tid] = (unsigned short)(c0 + e);
+              ++qcnt;
+            }
+          }
+        }
+      }
+    }
+    if (tid == 0) KNN_TR(6, 4002);
+    drain();
+    if (tid == 0) KNN_TR(6, 4003);
+    // merge the four column quarters of every row, pairwise (1 -> 0 and 3 -> 2, then 2 -> 0); the
+    // published lists are sorted, so a merge stops at the first entry that does not make the list.
+    // Every copy has landed and every MMA has completed by now: the operand stages are free.
+    float* mv = reinterpret_cast<float*>(smem + S::B_OFF);      // [3][KL][128]
+    int* mi = reinterpret_cast<int*>(smem + S::B_OFF) + 3 * KL * 128;
+    asm volatile("bar.sync 2, 512;" ::: "memory");
+    if (cq & 1) {
+#pragma unroll
+      for (int i = 0; i < KL; ++i) {
+        mv[((cq >> 1) * KL + i) * 128 + row] = lv[i];
+        mi[((cq >> 1) * KL + i) * 128 + row] = li[i];
+      }
+    }
+    asm volatile("bar.sync 2, 512;" ::: "memory");
+    if (!(cq & 1)) {
+#pragma unroll 1
+      for (int i = 0; i < KL; ++i) {
+        const float key = mv[((cq >> 1) * KL + i) * 128 + row];
+        if (!(key > lv[KL - 1])) break;
+        list_insert<KL>(lv, li, key, mi[((cq >> 1) * KL + i) * 128 + row]);
+      }
+      if (cq == 2) {
+#pragma unroll
+        for (int i = 0; i < KL; ++i) {
+          mv[(2 * KL + i) * 128 + row] = lv[i];
+          mi[(2 * KL + i) * 128 + row] = li[i];
+        }
+      }
+    }
+    asm volatile("bar.sync 2, 512;" ::: "memory");
+    if (cq == 0) {
+#pragma unroll 1
+      for (int i = 0; i < KL; ++i) {
+        const float key = mv[(2 * KL + i) * 128 + row];
+        if (!(key > lv[KL - 1])) break;
+        list_insert<KL>(lv, li, key, mi[(2 * KL + i) * 128 + row]);
+      }
+      if (q < N) {
+#pragma unroll
+        for (int i = 0; i < KL; ++i) {
+          if (i < k) {
+            const int64_t o = (base + q) * k + i;
+            if (idx32) idx32[o] = li[i];
+            if (idx64) idx64[o] = li[i];
+          }
+        }
+      }
+    }
+  }
+  if (tid == 0) KNN_TR(6, 4004);
+  tc::tc_fence_before();
+  __syncthreads();
+  if (w == 0) tc::tmem_dealloc(tmem_d, 512);
+  if (tid == 0) KNN_TR(6, 4005);
+}
+
+template <int KC4, int NST, int CAP>
+static int launch_knn_tc3_t(const float* x, int ld, int C, const float* xx, int64_t B, int N, int k,
+                            int32_t* idx32, int64_t* idx64, void* split_ws, cudaStream_t st) {
+  using S = Knn3Smem<KC4, NST, CAP>;
+  using P = KnnSplit<KC4>;
+  static_assert(S::TOTAL <= 232448 - 256, "shared memory budget");
+  const int T = (N + K3_TC - 1) / K3_TC;
+  cudaError_t e = cudaFuncSetAttribute(knn_split_kernel<KC4>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, P::BLK);
+  if (e != cudaSuccess) return (int)e;
+  knn_split_kernel<KC4><<<dim3(T, (unsigned)B), 256, P::BLK, st>>>(x, ld, C, xx, N,
+                                                                   (unsigned char*)split_ws);
+  R3DFS_CHECK_LAUNCH();
+  e = cudaFuncSetAttribute(knn_tc3_kernel<KC4, NST, CAP>,
+                           cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
+  if (e != cudaSuccess) return (int)e;
+  dim3 grid((N + KT_TQ - 1) / KT_TQ, (unsigned)B);
+  knn_tc3_kernel<KC4, NST, CAP><<<grid, K3_THREADS, S::TOTAL, st>>>(
+      x, ld, C, xx, (const unsigned char*)split_ws, N, k, idx32, idx64);
+  R3DFS_CHECK_LAUNCH();
+  return 0;
+}
+
+// bytes of the pre-split candidate tiles of B clouds of N points (0: shape not served by the
+// TMA-fed kernel)
+size_t knn_split_bytes(int C, int64_t B, int N, int k) {
+  if (k < 1 || k > 20 || C > 64 || N < 1024 || N > 65535 || N < k) return 0;
+  const size_t T = (size_t)(N + K3_TC - 1) / K3_TC;
+  const size_t blk = C <= 16 ? KnnSplit<4>::BLK : KnnSplit<16>::BLK;
+  return (size_t)B * T * blk;
+}
+
 template <int KC4, int KL>
 static int launch_knn_tc_t(const float* x, int ld, int C, const float* xx, int64_t B, int N, int k,
                            int32_t* idx32, int64_t* idx64, cudaStream_t st) {
@@ -708,10 +1178,28 @@ static bool knn_single_pass_forced() {  // A/B switch: R3DFS_KNN_SINGLE_PASS=1
   return v;
 }
 
+static bool knn_tc2_forced() {  // A/B switch: R3DFS_KNN_TC2=1 (register-fed two-pass kernel)
+  static const bool v = [] {
+    const char* e = R3DFS_GETENV("R3DFS_KNN_TC2");
+    return e && e[0] == '1';
+  }();
+  return v;
+}
+
 // returns R3DFS_E_UNSUPPORTED for shapes the tensor-core kernel is not built for (C > 64)
 int launch_knn_tc(const float* x, int ld, int C, const float* xx, int64_t B, int N, int k,
-                  int32_t* idx32, int64_t* idx64, cudaStream_t st) {
+                  int32_t* idx32, int64_t* idx64, cudaStream_t st, void* split_ws,
+                  size_t split_bytes) {
   if (k < 1 || k > 32 || C > 64 || N < k) return R3DFS_E_UNSUPPORTED;
+  // TMA-fed kernel when the caller lends scratch for the pre-split tiles
+  if (split_ws && !knn_single_pass_forced() && !knn_tc2_forced()) {
+    const size_t need = knn_split_bytes(C, B, N, k);
+    if (need && split_bytes >= need && (reinterpret_cast<uintptr_t>(split_ws) & 15) == 0) {
+      if (C <= 16)
+        return launch_knn_tc3_t<4, 4, 30>(x, ld, C, xx, B, N, k, idx32, idx64, split_ws, st);
+      return launch_knn_tc3_t<16, 2, 30>(x, ld, C, xx, B, N, k, idx32, idx64, split_ws, st);
+    }
+  }
   // two-pass selection (measured per 300 clouds of 2048 points: C = 9: 2.03 vs 3.05 ms single
   // pass, C = 64: 3.20 vs 3.43 ms); R3DFS_KNN_SINGLE_PASS=1 switches it off (A/B measurements).
   if (k <= 20 && N >= 1024 && N <= 65535 && !knn_single_pass_forced()) {

@@ -39,6 +39,12 @@ __global__ void mma_rate_kernel(int iters, long long* out) {
         const uint32_t d = tmem_d + ((it * 8 + ks) % NACC) * N;
         if (KIND == 0) {
           tc::mma_tf32(d, da, db, idesc, 1);
+        } else if (KIND == 2) {  // A operand from TMEM (columns 448..511), B from shared memory
+          asm volatile(
+              "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+              "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(d),
+              "r"(tmem_d + 448 + ks * 8), "l"(db), "r"(idesc), "r"(1)
+              : "memory");
         } else {
           asm volatile(
               "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
@@ -74,7 +80,7 @@ void run(const char* name, int grid) {
   double mx = 0;
   for (int i = 0; i < grid; ++i) mx = h[i] > mx ? h[i] : mx;
   const double per = mx / (iters * 8.0);
-  const double kk = KIND == 0 ? 8 : 16;
+  const double kk = KIND == 1 ? 16 : 8;
   printf("%-28s grid %4d  clk/MMA %7.1f  MAC/clk/SM %7.1f  (%s)\n", name, grid, per,
          128.0 * N * kk / per * (grid > 148 ? 2 : 1), cudaGetErrorString(e));
   cudaFree(d);
@@ -91,6 +97,10 @@ int main() {
   run<256, 2, 0>("tf32 N=256 2 acc", 148);
   run<128, 1, 0>("tf32 N=128 1 acc 2 CTA/SM", 296);
   run<64, 1, 0>("tf32 N=64  1 acc 2 CTA/SM", 296);
+  run<64, 1, 2>("tf32 N=64  A in TMEM", 148);
+  run<64, 4, 2>("tf32 N=64  A in TMEM 4 acc", 148);
+  run<128, 1, 2>("tf32 N=128 A in TMEM", 148);
+  run<128, 2, 2>("tf32 N=128 A in TMEM 2 acc", 148);
   run<128, 1, 1>("bf16 N=128 1 acc", 148);
   run<256, 1, 1>("bf16 N=256 1 acc", 148);
   run<256, 2, 1>("bf16 N=256 2 acc", 148);

@@ -1084,3 +1084,21 @@ def test_selection_and_inedge_kernels_equal_their_predecessors(n, tmp_path):
     subprocess.run([sys.executable, script, "run", b, str(n), "3"], check=True, timeout=300, env=env_old)
     r = subprocess.run([sys.executable, script, "cmp", a, b], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
+
+
+def test_tma_fed_knn_equals_register_fed_kernel(tmp_path):
+    """knn_tc3_kernel (candidate tiles pre-split once per point by knn_split_kernel and brought in by
+    cp.async.bulk) must return, bit for bit, the neighbour lists of knn_tc2_kernel (loader warps that
+    fetch and split every tile in every CTA; R3DFS_KNN_TC2=1 in the measurement build): C = 9 / 64,
+    ragged last tiles, k < 20, duplicate points."""
+    import subprocess
+    import sys
+    script = os.path.join(os.path.dirname(os.path.dirname(__file__)), "scripts", "check_knn.py")
+    a, b = str(tmp_path / "a.pt"), str(tmp_path / "b.pt")
+    from r3dfsseg_b200 import _lib
+    assert os.path.isfile(_lib.AB_LIB_PATH), "measurement build missing: make -C r3dfsseg_b200/csrc ab"
+    env_old = dict(os.environ, R3DFS_LIB=_lib.AB_LIB_PATH, R3DFS_KNN_TC2="1")
+    subprocess.run([sys.executable, script, "run", a], check=True, timeout=300)
+    subprocess.run([sys.executable, script, "run", b], check=True, timeout=300, env=env_old)
+    r = subprocess.run([sys.executable, script, "cmp", a, b], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
