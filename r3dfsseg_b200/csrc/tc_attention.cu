@@ -178,7 +178,7 @@ __global__ __launch_bounds__(AT_ALL_THREADS, 1) void attention_tc_kernel(const f
   tc::tc_fence_after();
   const uint32_t tmem_s = tmem_base_s, tmem_o = tmem_base_s + 128;
   const bool worker = w < 16;             // warps 0-15 move data; warp 16 only issues MMAs
-  const bool issuer = tid == AT_THREADS;  // lane 0 of warp 16
+  const bool issuer = w == 16;  // the whole warp walks the issue code, one elected lane issues
   const uint32_t q_hi = tc::smem_u32(smem + S::Q_OFF), q_lo = q_hi + S::Q_TILE;
   unsigned char* k_hi_p = smem + S::K_OFF;
   unsigned char* k_lo_p = k_hi_p + S::K_TILE;
@@ -197,20 +197,20 @@ __global__ __launch_bounds__(AT_ALL_THREADS, 1) void attention_tc_kernel(const f
       const uint64_t dql = tc::make_desc(q_lo + ks * 2 * LBO_Q, LBO_Q, 128);
       const uint64_t dkh = tc::make_desc(k_hi + ks * 2 * LBO_K, LBO_K, 128);
       const uint64_t dkl = tc::make_desc(k_lo + ks * 2 * LBO_K, LBO_K, 128);
-      tc::mma_tf32(tmem_s, dql, dkh, IDESC, ks != 0);
-      tc::mma_tf32(tmem_s, dqh, dkl, IDESC, 1);
-      tc::mma_tf32(tmem_s, dqh, dkh, IDESC, 1);
+      tc::mma_tf32_elect(tmem_s, dql, dkh, IDESC, ks != 0);
+      tc::mma_tf32_elect(tmem_s, dqh, dkl, IDESC, 1);
+      tc::mma_tf32_elect(tmem_s, dqh, dkh, IDESC, 1);
     }
-    tc::mma_commit(&bar_s);
+    tc::mma_commit_elect(&bar_s);
   };
 
   auto issue_s_hi = [&]() {  // S ~= Qhi . Khi^T only (1 of the 3 TF32 products): row-max estimate
     const uint64_t dqh = tc::make_desc(q_hi, LBO_Q, 128), dkh = tc::make_desc(k_hi, LBO_K, 128);
     constexpr uint64_t KQ = tc::desc_kstep(LBO_Q), KK = tc::desc_kstep(LBO_K);
-    tc::mma_tf32_c<false>(tmem_s, dqh, dkh, IDESC);
+    tc::mma_tf32_elect(tmem_s, dqh, dkh, IDESC, 0);
 #pragma unroll
-    for (int ks = 1; ks < 8; ++ks) tc::mma_tf32_c<true>(tmem_s, dqh + ks * KQ, dkh + ks * KK, IDESC);
-    tc::mma_commit(&bar_s);
+    for (int ks = 1; ks < 8; ++ks) tc::mma_tf32_elect(tmem_s, dqh + ks * KQ, dkh + ks * KK, IDESC, 1);
+    tc::mma_commit_elect(&bar_s);
   };
 
   uint32_t ph_s = 0, ph_pv = 0;
@@ -366,17 +366,16 @@ __global__ __launch_bounds__(AT_ALL_THREADS, 1) void attention_tc_kernel(const f
         const uint64_t dvh = tc::make_desc(v_hi, LBO_K, 128), dvl = tc::make_desc(v_lo, LBO_K, 128);
         constexpr uint64_t KP = tc::desc_kstep(LBO_Q), KV = tc::desc_kstep(LBO_K);
         // O[128 x 64] += P[128 x 64 keys] . V[64 keys x 64]
-        if (j == 0) tc::mma_tf32_c<false>(tmem_o, dpl, dvh, IDESC);
-        else tc::mma_tf32_c<true>(tmem_o, dpl, dvh, IDESC);
-        tc::mma_tf32_c<true>(tmem_o, dph, dvl, IDESC);
-        tc::mma_tf32_c<true>(tmem_o, dph, dvh, IDESC);
+        tc::mma_tf32_elect(tmem_o, dpl, dvh, IDESC, j != 0);
+        tc::mma_tf32_elect(tmem_o, dph, dvl, IDESC, 1);
+        tc::mma_tf32_elect(tmem_o, dph, dvh, IDESC, 1);
 #pragma unroll
         for (int ks = 1; ks < 8; ++ks) {
-          tc::mma_tf32_c<true>(tmem_o, dpl + ks * KP, dvh + ks * KV, IDESC);
-          tc::mma_tf32_c<true>(tmem_o, dph + ks * KP, dvl + ks * KV, IDESC);
-          tc::mma_tf32_c<true>(tmem_o, dph + ks * KP, dvh + ks * KV, IDESC);
+          tc::mma_tf32_elect(tmem_o, dpl + ks * KP, dvh + ks * KV, IDESC, 1);
+          tc::mma_tf32_elect(tmem_o, dph + ks * KP, dvl + ks * KV, IDESC, 1);
+          tc::mma_tf32_elect(tmem_o, dph + ks * KP, dvh + ks * KV, IDESC, 1);
         }
-        tc::mma_commit(&bar_pv);
+        tc::mma_commit_elect(&bar_pv);
       }
     }
   }

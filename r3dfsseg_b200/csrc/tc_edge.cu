@@ -92,7 +92,9 @@ __global__ __launch_bounds__(ET_THREADS, 1) void edge_tc_kernel(
     // --------------------------- MMA issue: its own warp ----------------------------------------
     // (a producer thread issuing the MMAs holds its whole producer group at the tile barrier for
     // as long as the tensor pipe takes to accept them, so staging and MMAs could not overlap)
-    if (lane == 0) {
+    // the whole warp walks the loop and one elected lane issues (warp-uniform control flow: the
+    // compiler wraps every MMA issued under `if (lane == 0)` in a convergence loop)
+    {
       const uint32_t wh = tc::smem_u32(smem + S::W_OFF), wl = wh + S::W_TILE;
       const uint64_t dwh = tc::make_desc(wh, LBO_W, 128), dwl = tc::make_desc(wl, LBO_W, 128);
       constexpr uint64_t KA = tc::desc_kstep(LBO_A), KW = tc::desc_kstep(LBO_W);
@@ -104,16 +106,16 @@ __global__ __launch_bounds__(ET_THREADS, 1) void edge_tc_kernel(
         const uint32_t ah = tc::smem_u32(smem + S::A_OFF + st * 2 * S::A_TILE), al = ah + S::A_TILE;
         const uint32_t d = tmem_d + st * 64;
         const uint64_t dah = tc::make_desc(ah, LBO_A, 128), dal = tc::make_desc(al, LBO_A, 128);
-        tc::mma_tf32_c<false>(d, dal, dwh, IDESC);
-        tc::mma_tf32_c<true>(d, dah, dwl, IDESC);
-        tc::mma_tf32_c<true>(d, dah, dwh, IDESC);
+        tc::mma_tf32_elect(d, dal, dwh, IDESC, 0);
+        tc::mma_tf32_elect(d, dah, dwl, IDESC, 1);
+        tc::mma_tf32_elect(d, dah, dwh, IDESC, 1);
 #pragma unroll
         for (int ks = 1; ks < 8; ++ks) {
-          tc::mma_tf32_c<true>(d, dal + ks * KA, dwh + ks * KW, IDESC);
-          tc::mma_tf32_c<true>(d, dah + ks * KA, dwl + ks * KW, IDESC);
-          tc::mma_tf32_c<true>(d, dah + ks * KA, dwh + ks * KW, IDESC);
+          tc::mma_tf32_elect(d, dal + ks * KA, dwh + ks * KW, IDESC, 1);
+          tc::mma_tf32_elect(d, dah + ks * KA, dwl + ks * KW, IDESC, 1);
+          tc::mma_tf32_elect(d, dah + ks * KA, dwh + ks * KW, IDESC, 1);
         }
-        tc::mma_commit(&bar_full[st]);
+        tc::mma_commit_elect(&bar_full[st]);
       }
     }
   } else if (w >= 4) {

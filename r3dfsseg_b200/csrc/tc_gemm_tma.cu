@@ -103,30 +103,33 @@ __global__ __launch_bounds__(TM_ALL_THREADS, 2) void linear_tma_kernel(
     // ---- TMA + MMA issue: one thread of its own warp, so the converters never stand still while
     // the tensor pipe accepts a k-block's MMAs (they used to wait for the issuing thread at a
     // CTA-wide barrier every k-block)
-    if (lane == 0) {
-      for (int kb = 0; kb < min(KB, TM_RAW_STAGES); ++kb) issue_tma(kb);
+    // (the whole warp walks the loop; lane 0 starts the copies, one elected lane issues the MMAs)
+    {
+      if (lane == 0)
+        for (int kb = 0; kb < min(KB, TM_RAW_STAGES); ++kb) issue_tma(kb);
+      __syncwarp();
       constexpr uint64_t KA = tc::desc_kstep(LBO_A), KBs = tc::desc_kstep(LBO_B);
       for (int kb = 0; kb < KB; ++kb) {
         const int os = kb & 1;
         tc::mbar_wait(&bar_op[os], (kb >> 1) & 1);  // stage converted; raw stage kb fully read
         tc::tc_fence_after();
-        if (kb + TM_RAW_STAGES < KB) issue_tma(kb + TM_RAW_STAGES);
+        if (lane == 0 && kb + TM_RAW_STAGES < KB) issue_tma(kb + TM_RAW_STAGES);
+        __syncwarp();
         unsigned char* a_hi = smem + S::OP_OFF + os * S::OP_STAGE;
         const uint32_t ah = tc::smem_u32(a_hi), al = ah + S::OP_A;
         const uint32_t bh = al + S::OP_A, bl = bh + S::OP_B;
         const uint64_t dah = tc::make_desc(ah, LBO_A, 128), dal = tc::make_desc(al, LBO_A, 128);
         const uint64_t dbh = tc::make_desc(bh, LBO_B, 128), dbl = tc::make_desc(bl, LBO_B, 128);
         const int ksteps = min(TM_BK, K - kb * TM_BK + 7) / 8;
-        if (kb == 0) tc::mma_tf32_c<false>(tmem_d, dal, dbh, IDESC);
-        else tc::mma_tf32_c<true>(tmem_d, dal, dbh, IDESC);
-        tc::mma_tf32_c<true>(tmem_d, dah, dbl, IDESC);
-        tc::mma_tf32_c<true>(tmem_d, dah, dbh, IDESC);
+        tc::mma_tf32_elect(tmem_d, dal, dbh, IDESC, kb != 0);
+        tc::mma_tf32_elect(tmem_d, dah, dbl, IDESC, 1);
+        tc::mma_tf32_elect(tmem_d, dah, dbh, IDESC, 1);
         if (ksteps > 1) {
-          tc::mma_tf32_c<true>(tmem_d, dal + KA, dbh + KBs, IDESC);
-          tc::mma_tf32_c<true>(tmem_d, dah + KA, dbl + KBs, IDESC);
-          tc::mma_tf32_c<true>(tmem_d, dah + KA, dbh + KBs, IDESC);
+          tc::mma_tf32_elect(tmem_d, dal + KA, dbh + KBs, IDESC, 1);
+          tc::mma_tf32_elect(tmem_d, dah + KA, dbl + KBs, IDESC, 1);
+          tc::mma_tf32_elect(tmem_d, dah + KA, dbh + KBs, IDESC, 1);
         }
-        tc::mma_commit(&bar_mma[os]);
+        tc::mma_commit_elect(&bar_mma[os]);
       }
     }
   } else {
