@@ -98,9 +98,10 @@ int launch_edge_mlp_auto(const float* PQ, const int32_t* idx, const float* w2, c
 }
 
 int launch_attention_auto(const float* qkv, int ld, int64_t B, int N, float* Y, int ldy,
-                          RowMap map, cudaStream_t st, float* kmax_ws) {
+                          RowMap map, cudaStream_t st, float* kmax_ws, void* split_ws,
+                          size_t split_bytes) {
   if (simt_gemm_forced()) return launch_attention(qkv, ld, B, N, Y, ldy, map, st);
-  return launch_attention_tc(qkv, ld, B, N, Y, ldy, map, st, kmax_ws);
+  return launch_attention_tc(qkv, ld, B, N, Y, ldy, map, st, kmax_ws, split_ws, split_bytes);
 }
 
 int launch_linear_auto(const float* X, int ldx, const float* W, const float* s, const float* t,
@@ -192,7 +193,9 @@ int encoder_forward(const r3dfs_weights_t* w, const float* xp, int64_t B, int N,
   R3DFS_TRY(launch_linear_auto(e.l2, 256, w->att_wqkv, nullptr, nullptr, ACT_NONE, M, 256, 192, e.qkv,
                           192, identity_map(), st));
   if (sr) sr->mark(R3DFS_ST_QKV, st);
-  R3DFS_TRY(launch_attention_auto(e.qkv, 192, B, N, F + 64, 192, map, st, e.xx));  // xx: free scratch
+  // xx: free scratch for the key-norm maxima; h512 (idle after the MLP) holds the pre-split K / V^T
+  R3DFS_TRY(launch_attention_auto(e.qkv, 192, B, N, F + 64, 192, map, st, e.xx, e.h512,
+                                  sizeof(float) * (size_t)M * 512));
   if (sr) sr->mark(R3DFS_ST_ATT, st);
   return 0;
 }
@@ -334,7 +337,8 @@ int r3dfs_edgeconv(const float* x, int64_t B, int64_t C, int64_t N, int64_t sb, 
 
 // ---- attention ----------------------------------------------------------------------------------
 size_t r3dfs_attention_workspace(int64_t B, int64_t N) {
-  return align_up(sizeof(float) * B * N * 192, 256) + align_up(sizeof(float) * B, 256) + 256;
+  return align_up(sizeof(float) * B * N * 192, 256) + align_up(sizeof(float) * B, 256) +
+         align_up(attention_split_bytes(B, (int)N), 256) + 512;
 }
 
 int r3dfs_attention(const float* x, int64_t B, int64_t N, int64_t Cin, const float* wqkv, float* y,
@@ -346,9 +350,13 @@ int r3dfs_attention(const float* x, int64_t B, int64_t N, int64_t Cin, const flo
   WsBump ws(wsp, ws_bytes);
   float* qkv = ws.take<float>(B * N * 192);
   float* kmax = ws.take<float>(B);
+  const size_t split_bytes = attention_split_bytes(B, (int)N);
+  unsigned char* split = ws.take<unsigned char>(split_bytes);
+  if (!ws.ok()) return R3DFS_E_WORKSPACE;
   R3DFS_TRY(launch_linear_auto(x, (int)Cin, wqkv, nullptr, nullptr, ACT_NONE, B * N, (int)Cin, 192,
                                qkv, 192, identity_map(), st));
-  return launch_attention_auto(qkv, 192, B, (int)N, y, 64, identity_map(), st, kmax);
+  return launch_attention_auto(qkv, 192, B, (int)N, y, 64, identity_map(), st, kmax, split,
+                               split_bytes);
 }
 
 // ---- getFeatures --------------------------------------------------------------------------------

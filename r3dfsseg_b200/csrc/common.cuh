@@ -151,9 +151,13 @@ size_t edge_feature_scratch_bytes(int64_t B, int64_t C, int64_t N);
 int launch_attention(const float* qkv, int ld, int64_t B, int N, float* Y, int ldy, RowMap map,
                      cudaStream_t st);
 int launch_attention_tc(const float* qkv, int ld, int64_t B, int N, float* Y, int ldy, RowMap map,
-                        cudaStream_t st, float* kmax_ws = nullptr);
+                        cudaStream_t st, float* kmax_ws = nullptr, void* split_ws = nullptr,
+                        size_t split_bytes = 0);
 int launch_attention_auto(const float* qkv, int ld, int64_t B, int N, float* Y, int ldy,
-                          RowMap map, cudaStream_t st, float* kmax_ws = nullptr);
+                          RowMap map, cudaStream_t st, float* kmax_ws = nullptr,
+                          void* split_ws = nullptr, size_t split_bytes = 0);
+// scratch for the pre-split K / V^T tiles of the TMA-fed attention kernel
+size_t attention_split_bytes(int64_t B, int N);
 int launch_fold_edge_w1(const float* w1, const float* s1, const float* t1, int C, float* wpq,
                         float* spq, float* tpq, cudaStream_t st);
 

@@ -240,6 +240,19 @@ __device__ __forceinline__ void mma_tf32_elect(uint32_t tmem_d, uint64_t a_desc,
       "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// A in TMEM, B in shared memory, elected lane of a converged warp, runtime accumulate flag
+__device__ __forceinline__ void mma_tf32_ts_e(uint32_t tmem_d, uint32_t tmem_a, uint64_t b_desc,
+                                              uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p, pe;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 __device__ __forceinline__ void mma_commit_elect(uint64_t* bar) {
   asm volatile(
       "{\n\t"

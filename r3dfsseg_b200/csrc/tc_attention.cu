@@ -402,13 +402,385 @@ __global__ __launch_bounds__(AT_ALL_THREADS, 1) void attention_tc_kernel(const f
   if (w == 0) tc::tmem_dealloc(tmem_base_s, 256);
 }
 
+// ---------------------------------------------------------------------------------------------
+// TMA-fed variant, operands in TMEM  (what the per-tile trace of the kNN kernel showed applies
+// here unchanged: an MMA whose A and B both come from shared memory saturates the SM's 128 B/clk
+// at N <= 128, an N = 64 instruction never runs below ~45 cycles, the issuing thread is
+// synchronous, and the 16 worker warps of attention_tc_kernel spend most of a tile fetching,
+// splitting and storing K, V^T and P behind three CTA-wide barriers).
+//   att_split_kernel  splits K and V^T of every cloud ONCE into 128-key UMMA tiles in global
+//                     memory (every query block of a cloud used to redo it, twice);
+//   attention_tc2_kernel, one CTA = 128 queries:
+//     Q/8 (hi, lo) lives in TMEM and is the A operand of S = Q K^T (128 x 128 x 8 instructions,
+//     full rate, B tiles arrive by cp.async.bulk);  the workers (thread = row x 16-column
+//     quarter of a 64-key half) read S from TMEM, form P = exp(S - m), and write P's hi part over
+//     the S columns it came from and its lo part next to O — P never touches shared memory and is
+//     the A operand of O += P V;  S is double-buffered in TMEM so S(j+1) runs while P(j) is
+//     formed;  one producer lane, one elected MMA lane, mbarriers instead of CTA-wide barriers.
+//   TMEM (512 columns): Q hi 0-63 | Q lo 64-127 | S0 / P0 hi 128-255 | S1 / P1 hi 256-383 |
+//                       O 384-447 | P lo (one 64-key half) 448-511.
+//   Same split arithmetic, same k-step and key order as attention_tc_kernel: bit-identical output.
+// ---------------------------------------------------------------------------------------------
+#define A2_THREADS 576  // warps 0-15 workers, 16 copy producer, 17 MMA issue
+struct Att2 {
+  static constexpr int K_TILE = tc::tile_bytes(128, 16);  // 128 keys x 64 (d), hi or lo
+  static constexpr int V_HALF = tc::tile_bytes(64, 16);   // 64 (d) rows x 64 keys (V^T), hi or lo
+  static constexpr int BLK = 2 * K_TILE + 4 * V_HALF;     // K hi, K lo, V0 hi, V0 lo, V1 hi, V1 lo
+  static constexpr int K_OFF = 0;                         // 2 stages x (hi, lo)
+  static constexpr int V_OFF = K_OFF + 4 * K_TILE;        // 2 half buffers x (hi, lo)
+  static constexpr int X_OFF = V_OFF + 4 * V_HALF;        // exchange: 4 x 128 floats
+  static constexpr int TOTAL = X_OFF + 4 * 128 * 4 + 64;
+};
+
+__global__ __launch_bounds__(256) void att_split_kernel(const float* __restrict__ qkv, int ld, int N,
+                                                        unsigned char* __restrict__ out) {
+  extern __shared__ __align__(128) unsigned char sm[];
+  constexpr int LBO_K = tc::tile_lbo(128), LBO_V = tc::tile_lbo(64);
+  const int t = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+  const int T = gridDim.x;
+  const int64_t base = (int64_t)b * N, row0 = (int64_t)t * 128;
+  float4* dst = reinterpret_cast<float4*>(out + ((int64_t)b * T + t) * Att2::BLK);
+  // ---- K tile: row r, chunk kc -> kc * LBO + r * 16
+  for (int c = tid; c < 128 * 16; c += 256) {
+    const int r = c >> 4, kc = c & 15;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (row0 + r < N)
+      v = *reinterpret_cast<const float4*>(qkv + (base + row0 + r) * (int64_t)ld + 64 + 4 * kc);
+    float4 h, l;
+    tc::split4(v, h, l);
+    *reinterpret_cast<float4*>(sm + kc * LBO_K + r * 16) = h;
+    *reinterpret_cast<float4*>(sm + Att2::K_TILE + kc * LBO_K + r * 16) = l;
+  }
+  if (tid < 32)
+    *reinterpret_cast<float4*>(sm + (tid >> 4) * Att2::K_TILE + (tid & 15) * LBO_K + 128 * 16) =
+        make_float4(0.f, 0.f, 0.f, 0.f);
+  __syncthreads();
+  for (int i = tid; i < 2 * Att2::K_TILE / 16; i += 256) dst[i] = reinterpret_cast<float4*>(sm)[i];
+  __syncthreads();
+  // ---- V^T halves: element (d, key) of half h -> (key / 4) * LBO + d * 16 + (key % 4) * 4
+  for (int c = tid; c < 128 * 16; c += 256) {
+    const int key = c & 127, d4 = c >> 7;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (row0 + key < N)
+      v = *reinterpret_cast<const float4*>(qkv + (base + row0 + key) * (int64_t)ld + 128 + 4 * d4);
+    float4 h, l;
+    tc::split4(v, h, l);
+    const int half = key >> 6, kk = key & 63;
+    unsigned char* hi = sm + half * 2 * Att2::V_HALF;
+    unsigned char* lo = hi + Att2::V_HALF;
+    const int o = (kk >> 2) * LBO_V + (kk & 3) * 4 + (4 * d4) * 16;
+    *reinterpret_cast<float*>(hi + o) = h.x;
+    *reinterpret_cast<float*>(hi + o + 16) = h.y;
+    *reinterpret_cast<float*>(hi + o + 32) = h.z;
+    *reinterpret_cast<float*>(hi + o + 48) = h.w;
+    *reinterpret_cast<float*>(lo + o) = l.x;
+    *reinterpret_cast<float*>(lo + o + 16) = l.y;
+    *reinterpret_cast<float*>(lo + o + 32) = l.z;
+    *reinterpret_cast<float*>(lo + o + 48) = l.w;
+  }
+  if (tid < 64)
+    *reinterpret_cast<float4*>(sm + (tid >> 4) * Att2::V_HALF + (tid & 15) * LBO_V + 64 * 16) =
+        make_float4(0.f, 0.f, 0.f, 0.f);
+  __syncthreads();
+  dst += 2 * Att2::K_TILE / 16;
+  for (int i = tid; i < 4 * Att2::V_HALF / 16; i += 256) dst[i] = reinterpret_cast<float4*>(sm)[i];
+}
+
+__device__ __forceinline__ void a2_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc::smem_u32(bar)) : "memory");
+}
+
+__global__ __launch_bounds__(A2_THREADS, 1) void attention_tc2_kernel(
+    const float* __restrict__ qkv, int ld, int N, const unsigned char* __restrict__ split,
+    float* __restrict__ Y, int ldy, RowMap map, const float* __restrict__ kmax2) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  using S = Att2;
+  __shared__ uint64_t bar_kfull[2], bar_kfree[2];    // K stage landed / read by its S MMAs
+  __shared__ uint64_t bar_vfull[2], bar_vfree[2];    // V^T half buffer landed / read by its PV MMAs
+  __shared__ uint64_t bar_sfull[2], bar_sfree[2];    // S buffer complete / read by the workers (sweep 1)
+  __shared__ uint64_t bar_pfull[2], bar_pvdone[2];   // P half written / its PV MMAs complete
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int b = blockIdx.y;
+  const int q0 = blockIdx.x * 128;
+  const int64_t base = (int64_t)b * N;
+  constexpr int LBO_K = tc::tile_lbo(128), LBO_V = tc::tile_lbo(64);
+  constexpr uint32_t IDESC_S = tc::make_idesc_tf32(128, 128), IDESC_O = tc::make_idesc_tf32(128, 64);
+  constexpr uint32_t COL_QH = 0, COL_QL = 64, COL_S = 128, COL_O = 384, COL_PL = 448;
+  const int T = (N + 127) / 128;
+  const bool worker = w < 16;
+  const int row = 32 * (w & 3) + lane;  // TMEM lane = query row
+  const int cq = (w >> 2) & 3;          // 16-column quarter of every 64-key half
+  float* xch = reinterpret_cast<float*>(smem + S::X_OFF);
+
+  if (tid == 0) {
+    for (int i = 0; i < 2; ++i) {
+      tc::mbar_init(&bar_kfull[i], 1);
+      tc::mbar_init(&bar_kfree[i], 1);
+      tc::mbar_init(&bar_vfull[i], 1);
+      tc::mbar_init(&bar_vfree[i], 1);
+      tc::mbar_init(&bar_sfull[i], 1);
+      tc::mbar_init(&bar_sfree[i], 512);
+      tc::mbar_init(&bar_pfull[i], 512);
+      tc::mbar_init(&bar_pvdone[i], 1);
+    }
+    tc::mbar_fence_init();
+  }
+  if (w == 0) tc::tmem_alloc(&tmem_base_s, 512);
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+  const uint32_t trow = tmem + ((uint32_t)(32 * (w & 3)) << 16);
+
+  // ---- Q/8 -> TMEM (exact division, as the reference), |q/8|^2 for the row bound ----------------
+  float qs = 0.f;
+  if (worker) {
+    float hi[16], lo[16];
+    const bool ok = q0 + row < N;
+    const float4* qp = reinterpret_cast<const float4*>(qkv + (base + q0 + row) * (int64_t)ld + 16 * cq);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      float4 v = ok ? __ldg(qp + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      v.x /= 8.f; v.y /= 8.f; v.z /= 8.f; v.w /= 8.f;
+      qs = fmaf(v.x, v.x, qs);
+      qs = fmaf(v.y, v.y, qs);
+      qs = fmaf(v.z, v.z, qs);
+      qs = fmaf(v.w, v.w, qs);
+      float4 h, l;
+      tc::split4(v, h, l);
+      hi[4 * c] = h.x; hi[4 * c + 1] = h.y; hi[4 * c + 2] = h.z; hi[4 * c + 3] = h.w;
+      lo[4 * c] = l.x; lo[4 * c + 1] = l.y; lo[4 * c + 2] = l.z; lo[4 * c + 3] = l.w;
+    }
+    tc::tmem_st16(trow + COL_QH + 16 * cq, hi);
+    tc::tmem_st16(trow + COL_QL + 16 * cq, lo);
+    tc::tmem_st_wait();
+    xch[cq * 128 + row] = qs;
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  // ---- row bound m' = |q/8| max|k| (see attention_tc_kernel) ---------------------------------------
+  float m_row = 0.f, margin = 0.f;
+  bool sweep1 = true;
+  const bool approx = kmax2 != nullptr;
+  if (approx) {
+    const int xr = worker ? row : 0;
+    const float q2 = (xch[xr] + xch[128 + xr]) + (xch[256 + xr] + xch[384 + xr]);
+    m_row = sqrtf(q2) * sqrtf(__ldg(kmax2 + b)) * 1.0001f + 1e-6f;
+    margin = m_row * (1.0f / 1024.0f) * 1.01f + 1e-6f;
+    sweep1 = __syncthreads_or(!(m_row <= 60.f));
+  }
+  const int T1 = sweep1 ? T : 0;  // tiles of the first sweep; global tile index g = T1 + j in sweep 2
+  const unsigned char* src0 = split + (int64_t)b * T * S::BLK;
+
+  if (w == 16) {
+    // ------------------------------ copy producer ---------------------------------------------
+    // K runs one tile ahead of the V^T halves: a V half buffer is free only when the previous
+    // tile's PV MMAs are done, and waiting for that must not delay the next K tile
+    if (lane == 0) {
+      const int G = T1 + T;
+      auto load_k = [&](int g) {
+        const int kb = g & 1;
+        if (g >= 2) tc::mbar_wait(&bar_kfree[kb], ((g >> 1) - 1) & 1);
+        const bool s1 = g < T1;
+        const int t = s1 ? g : g - T1;
+        const uint32_t kbytes = (s1 && approx) ? S::K_TILE : 2 * S::K_TILE;  // hi only: approximate sweep
+        tc::mbar_arrive_expect_tx(&bar_kfull[kb], kbytes);
+        tc::bulk_g2s(smem + S::K_OFF + kb * 2 * S::K_TILE, src0 + (int64_t)t * S::BLK, kbytes,
+                     &bar_kfull[kb]);
+      };
+      if (G > 0) load_k(0);
+      for (int g = 0; g < G; ++g) {
+        if (g + 1 < G) load_k(g + 1);
+        if (g >= T1) {
+          const int t = g - T1;
+#pragma unroll 1
+          for (int h = 0; h < 2; ++h) {
+            if (t >= 1) tc::mbar_wait(&bar_vfree[h], (t - 1) & 1);
+            tc::mbar_arrive_expect_tx(&bar_vfull[h], 2 * S::V_HALF);
+            tc::bulk_g2s(smem + S::V_OFF + h * 2 * S::V_HALF,
+                         src0 + (int64_t)t * S::BLK + 2 * S::K_TILE + h * 2 * S::V_HALF,
+                         2 * S::V_HALF, &bar_vfull[h]);
+          }
+        }
+      }
+    }
+  } else if (w == 17) {
+    // ------------------------------ MMA issue (whole warp, elected lane) ----------------------
+    constexpr uint64_t KK = tc::desc_kstep(LBO_K), KV = tc::desc_kstep(LBO_V);
+    auto issue_s = [&](int g) {  // S(g) = Q K^T into S buffer g & 1
+      const int kb = g & 1;
+      tc::mbar_wait(&bar_kfull[kb], (g >> 1) & 1);
+      // the buffer's previous content was read by the workers (sweep 1) — in sweep 2 it holds P hi
+      // of tile g - 2, whose PV MMAs were issued before this point and execute in issue order
+      if (g >= 2 && g - 2 < T1) tc::mbar_wait(&bar_sfree[kb], ((g >> 1) - 1) & 1);
+      tc::tc_fence_after();
+      const uint32_t k_hi = tc::smem_u32(smem + S::K_OFF + kb * 2 * S::K_TILE), k_lo = k_hi + S::K_TILE;
+      const uint64_t dkh = tc::make_desc(k_hi, LBO_K, 128), dkl = tc::make_desc(k_lo, LBO_K, 128);
+      const uint32_t d = tmem + COL_S + kb * 128;
+      if (g < T1 && approx) {
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks)
+          tc::mma_tf32_ts_e(d, tmem + COL_QH + 8 * ks, dkh + ks * KK, IDESC_S, ks != 0);
+      } else {
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {
+          tc::mma_tf32_ts_e(d, tmem + COL_QL + 8 * ks, dkh + ks * KK, IDESC_S, ks != 0);
+          tc::mma_tf32_ts_e(d, tmem + COL_QH + 8 * ks, dkl + ks * KK, IDESC_S, 1);
+          tc::mma_tf32_ts_e(d, tmem + COL_QH + 8 * ks, dkh + ks * KK, IDESC_S, 1);
+        }
+      }
+      tc::mma_commit_elect(&bar_kfree[kb]);
+      tc::mma_commit_elect(&bar_sfull[kb]);
+    };
+    for (int g = 0; g < T1; ++g) issue_s(g);
+    if (T > 0) issue_s(T1);
+    for (int j = 0; j < T; ++j) {
+      if (j + 1 < T) issue_s(T1 + j + 1);
+      const uint32_t p_hi = tmem + COL_S + ((T1 + j) & 1) * 128;
+#pragma unroll 1
+      for (int h = 0; h < 2; ++h) {
+        tc::mbar_wait(&bar_pfull[h], j & 1);
+        tc::mbar_wait(&bar_vfull[h], j & 1);
+        tc::tc_fence_after();
+        const uint32_t v_hi = tc::smem_u32(smem + S::V_OFF + h * 2 * S::V_HALF), v_lo = v_hi + S::V_HALF;
+        const uint64_t dvh = tc::make_desc(v_hi, LBO_V, 128), dvl = tc::make_desc(v_lo, LBO_V, 128);
+        const uint32_t ah = p_hi + 64 * h, al = tmem + COL_PL;
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {
+          tc::mma_tf32_ts_e(tmem + COL_O, al + 8 * ks, dvh + ks * KV, IDESC_O, (j | h | ks) != 0);
+          tc::mma_tf32_ts_e(tmem + COL_O, ah + 8 * ks, dvl + ks * KV, IDESC_O, 1);
+          tc::mma_tf32_ts_e(tmem + COL_O, ah + 8 * ks, dvh + ks * KV, IDESC_O, 1);
+        }
+        tc::mma_commit_elect(&bar_vfree[h]);
+        tc::mma_commit_elect(&bar_pvdone[h]);
+      }
+    }
+  } else {
+    // ------------------------------ workers ---------------------------------------------------
+    if (sweep1) {
+      float m_run = -INFINITY;
+      for (int g = 0; g < T1; ++g) {
+        const int sb = g & 1;
+        tc::mbar_wait(&bar_sfull[sb], (g >> 1) & 1);
+        tc::tc_fence_after();
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          float v[16];
+          tc::tmem_ld16(trow + COL_S + sb * 128 + 64 * h + 16 * cq, v);
+          const int c0 = g * 128 + 64 * h + 16 * cq;
+#pragma unroll
+          for (int e = 0; e < 16; ++e)
+            if (c0 + e < N) m_run = fmaxf(m_run, v[e]);
+        }
+        tc::tc_fence_before();
+        a2_arrive(&bar_sfree[sb]);
+      }
+      asm volatile("bar.sync 1, 512;" ::: "memory");  // xch (the |q|^2 partials) has been read
+      xch[cq * 128 + row] = m_run;
+      asm volatile("bar.sync 1, 512;" ::: "memory");
+      m_row = fmaxf(fmaxf(xch[row], xch[128 + row]), fmaxf(xch[256 + row], xch[384 + row])) + margin;
+      asm volatile("bar.sync 1, 512;" ::: "memory");  // read before the row sums reuse xch
+    }
+    float l_run = 0.f;
+    for (int j = 0; j < T; ++j) {
+      const int g = T1 + j, sb = g & 1;
+      tc::mbar_wait(&bar_sfull[sb], (g >> 1) & 1);
+      tc::tc_fence_after();
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        float v[16], lo[16];
+        const uint32_t col = COL_S + sb * 128 + 64 * h + 16 * cq;
+        tc::tmem_ld16(trow + col, v);
+        const int c0 = j * 128 + 64 * h + 16 * cq;
+#pragma unroll
+        for (int e = 0; e < 16; e += 4) {
+          float4 p;
+          p.x = (c0 + e + 0 < N) ? expf(v[e + 0] - m_row) : 0.f;
+          p.y = (c0 + e + 1 < N) ? expf(v[e + 1] - m_row) : 0.f;
+          p.z = (c0 + e + 2 < N) ? expf(v[e + 2] - m_row) : 0.f;
+          p.w = (c0 + e + 3 < N) ? expf(v[e + 3] - m_row) : 0.f;
+          l_run += (p.x + p.y) + (p.z + p.w);
+          float4 ph, pl;
+          tc::split4(p, ph, pl);
+          v[e] = ph.x; v[e + 1] = ph.y; v[e + 2] = ph.z; v[e + 3] = ph.w;
+          lo[e] = pl.x; lo[e + 1] = pl.y; lo[e + 2] = pl.z; lo[e + 3] = pl.w;
+        }
+        tc::tmem_st16(trow + col, v);  // P hi over the S columns it came from
+        // the single P lo buffer is free once the PV MMAs of the previous half have completed
+        if (h == 0) {
+          if (j >= 1) tc::mbar_wait(&bar_pvdone[1], (j - 1) & 1);
+        } else {
+          tc::mbar_wait(&bar_pvdone[0], j & 1);
+        }
+        tc::tc_fence_after();
+        tc::tmem_st16(trow + COL_PL + 16 * cq, lo);
+        tc::tmem_st_wait();
+        tc::tc_fence_before();
+        a2_arrive(&bar_pfull[h]);
+      }
+    }
+    // ---------------- epilogue: O / l ----------------------------------------------------------
+    asm volatile("bar.sync 1, 512;" ::: "memory");
+    xch[cq * 128 + row] = l_run;
+    asm volatile("bar.sync 1, 512;" ::: "memory");
+    const float inv = 1.f / ((xch[row] + xch[128 + row]) + (xch[256 + row] + xch[384 + row]));
+    tc::mbar_wait(&bar_pvdone[1], (T - 1) & 1);
+    tc::tc_fence_after();
+    float v[16];
+    tc::tmem_ld16(trow + COL_O + 16 * cq, v);
+    const int q = q0 + row;
+    if (q < N) {
+      float* y = Y + map(base + q) * (int64_t)ldy + 16 * cq;
+#pragma unroll
+      for (int e = 0; e < 16; e += 4)
+        *reinterpret_cast<float4*>(y + e) =
+            make_float4(v[e] * inv, v[e + 1] * inv, v[e + 2] * inv, v[e + 3] * inv);
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (w == 0) tc::tmem_dealloc(tmem, 512);
+}
+
+size_t attention_split_bytes(int64_t B, int N) {
+  return (size_t)B * (size_t)((N + 127) / 128) * Att2::BLK;
+}
+
+static bool att_v1_forced() {  // A/B switch: R3DFS_ATT_V1=1 (register-fed kernel)
+  static const bool v = [] {
+    const char* e = R3DFS_GETENV("R3DFS_ATT_V1");
+    return e && e[0] == '1';
+  }();
+  return v;
+}
+
 // kmax_ws: B floats of scratch for the per-cloud key-norm maxima; nullptr -> always two sweeps
 int launch_attention_tc(const float* qkv, int ld, int64_t B, int N, float* Y, int ldy, RowMap map,
-                        cudaStream_t st, float* kmax_ws) {
+                        cudaStream_t st, float* kmax_ws, void* split_ws, size_t split_bytes) {
   if ((ld & 3) != 0 || (ldy & 3) != 0) return R3DFS_E_UNSUPPORTED;
   if (kmax_ws) {
     att_kmax_kernel<<<(unsigned)B, 256, 0, st>>>(qkv, ld, N, kmax_ws);
     R3DFS_CHECK_LAUNCH();
+  }
+  if (split_ws && split_bytes >= attention_split_bytes(B, N) && N >= 1 && !att_v1_forced() &&
+      (reinterpret_cast<uintptr_t>(split_ws) & 15) == 0 &&
+      (reinterpret_cast<uintptr_t>(qkv) & 15) == 0) {
+    const int T = (N + 127) / 128;
+    cudaError_t e = cudaFuncSetAttribute(att_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         4 * Att2::V_HALF);
+    if (e != cudaSuccess) return (int)e;
+    att_split_kernel<<<dim3(T, (unsigned)B), 256, 4 * Att2::V_HALF, st>>>(qkv, ld, N,
+                                                                        (unsigned char*)split_ws);
+    R3DFS_CHECK_LAUNCH();
+    e = cudaFuncSetAttribute(attention_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             Att2::TOTAL);
+    if (e != cudaSuccess) return (int)e;
+    attention_tc2_kernel<<<dim3(T, (unsigned)B), A2_THREADS, Att2::TOTAL, st>>>(
+        qkv, ld, N, (const unsigned char*)split_ws, Y, ldy, map, kmax_ws);
+    R3DFS_CHECK_LAUNCH();
+    return 0;
   }
   cudaError_t e = cudaFuncSetAttribute(attention_tc_kernel,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -1102,3 +1102,21 @@ def test_tma_fed_knn_equals_register_fed_kernel(tmp_path):
     subprocess.run([sys.executable, script, "run", b], check=True, timeout=300, env=env_old)
     r = subprocess.run([sys.executable, script, "cmp", a, b], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
+
+
+def test_tma_fed_attention_equals_register_fed_kernel(tmp_path):
+    """attention_tc2_kernel (K / V^T pre-split once per cloud and brought in by cp.async.bulk, Q and P
+    as TMEM operands, 128-key tiles) keeps the split arithmetic and the k-step / key order of
+    attention_tc_kernel (R3DFS_ATT_V1=1 in the measurement build): outputs must be bit-identical —
+    with and without the first sweep, ragged N, N below one tile."""
+    import subprocess
+    import sys
+    script = os.path.join(os.path.dirname(os.path.dirname(__file__)), "scripts", "check_attention.py")
+    a, b = str(tmp_path / "a.pt"), str(tmp_path / "b.pt")
+    from r3dfsseg_b200 import _lib
+    assert os.path.isfile(_lib.AB_LIB_PATH), "measurement build missing: make -C r3dfsseg_b200/csrc ab"
+    env_old = dict(os.environ, R3DFS_LIB=_lib.AB_LIB_PATH, R3DFS_ATT_V1="1")
+    subprocess.run([sys.executable, script, "run", a], check=True, timeout=300)
+    subprocess.run([sys.executable, script, "run", b], check=True, timeout=300, env=env_old)
+    r = subprocess.run([sys.executable, script, "cmp", a, b], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
