@@ -1120,3 +1120,20 @@ def test_tma_fed_attention_equals_register_fed_kernel(tmp_path):
     subprocess.run([sys.executable, script, "run", b], check=True, timeout=300, env=env_old)
     r = subprocess.run([sys.executable, script, "cmp", a, b], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
+
+
+def test_tmem_operand_linear_equals_shared_memory_operand_kernel(tmp_path):
+    """linear_ts_kernel (X tile split straight into TMEM, 64B-swizzled raw tiles) against
+    linear_tma_kernel (hi / lo operand tiles in shared memory; R3DFS_LINEAR_SMEM_A=1 in the
+    measurement build): same split, same MMA order -> bit-identical outputs, ragged shapes included."""
+    import subprocess
+    import sys
+    script = os.path.join(os.path.dirname(os.path.dirname(__file__)), "scripts", "check_linear.py")
+    a, b = str(tmp_path / "a.pt"), str(tmp_path / "b.pt")
+    from r3dfsseg_b200 import _lib
+    assert os.path.isfile(_lib.AB_LIB_PATH), "measurement build missing: make -C r3dfsseg_b200/csrc ab"
+    env_old = dict(os.environ, R3DFS_LIB=_lib.AB_LIB_PATH, R3DFS_LINEAR_SMEM_A="1")
+    subprocess.run([sys.executable, script, "run", a], check=True, timeout=300)
+    subprocess.run([sys.executable, script, "run", b], check=True, timeout=300, env=env_old)
+    r = subprocess.run([sys.executable, script, "cmp", a, b], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
