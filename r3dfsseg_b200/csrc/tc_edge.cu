@@ -20,6 +20,14 @@
 #include "common.cuh"
 #include "tc.cuh"
 
+// per-tile timestamps of one CTA (scripts/microbench/edge_trace.cu compiles this file with EDGE_TRACE)
+#ifdef EDGE_TRACE
+__device__ long long g_edge_trace[8 * 256];
+#define EDGE_TR(slot, j) \
+  do { if (blockIdx.x == EDGE_TRACE_BX && blockIdx.y == EDGE_TRACE_BY) g_edge_trace[(slot) * 256 + (j)] = clock64(); } while (0)
+#else
+#define EDGE_TR(slot, j) do { } while (0)
+#endif
 #define ET_THREADS 416  // warps 0-3 epilogue, 4-11 producers, 12 MMA issue
 #define ET_PRODUCERS 256
 #define ET_GROUP 128  // points per group (= MMA rows)
@@ -101,7 +109,9 @@ __global__ __launch_bounds__(ET_THREADS, 1) void edge_tc_kernel(
       for (int u = 0; u < U; ++u) {
         const int st = u & 1;
         tc::mbar_wait(&bar_sfull[st], (u >> 1) & 1);                      // A tile staged
+        if (lane == 0) EDGE_TR(0, u);
         if (u >= 2) tc::mbar_wait(&bar_tfree[st], ((u >> 1) - 1) & 1);    // accumulator drained
+        if (lane == 0) EDGE_TR(1, u);
         tc::tc_fence_after();
         const uint32_t ah = tc::smem_u32(smem + S::A_OFF + st * 2 * S::A_TILE), al = ah + S::A_TILE;
         const uint32_t d = tmem_d + st * 64;
@@ -116,6 +126,7 @@ __global__ __launch_bounds__(ET_THREADS, 1) void edge_tc_kernel(
           tc::mma_tf32_elect(d, dah + ks * KA, dwh + ks * KW, IDESC, 1);
         }
         tc::mma_commit_elect(&bar_full[st]);
+        if (lane == 0) EDGE_TR(2, u);
       }
     }
   } else if (w >= 4) {
@@ -155,6 +166,7 @@ __global__ __launch_bounds__(ET_THREADS, 1) void edge_tc_kernel(
     for (int u = 0; u < U; ++u) {
       const int st = u & 1;
       const int g = g_begin + u / k;
+      if (lt == 0) EDGE_TR(3, u);
       if (u % k == 0) {  // new group: this thread's Q cells stay in registers for all k tiles
 #pragma unroll
         for (int i = 0; i < NCH; ++i) {
@@ -175,7 +187,9 @@ __global__ __launch_bounds__(ET_THREADS, 1) void edge_tc_kernel(
         }
         hv[i] = h;
       }
+      if (lt == 0) EDGE_TR(4, u);
       if (u >= 2) tc::mbar_wait(&bar_full[st], ((u >> 1) - 1) & 1);  // stage's MMAs finished
+      if (lt == 0) EDGE_TR(5, u);
       unsigned char* a_hi = smem + S::A_OFF + st * 2 * S::A_TILE;
       unsigned char* a_lo = a_hi + S::A_TILE;
 #pragma unroll
@@ -192,6 +206,7 @@ __global__ __launch_bounds__(ET_THREADS, 1) void edge_tc_kernel(
       }
       tc::fence_async_smem();
       et_mbar_arrive(&bar_sfull[st]);
+      if (lt == 0) EDGE_TR(6, u);
     }
   } else {
     // --------------------------- epilogue: thread = point row, all 64 channels ------------------
@@ -213,6 +228,7 @@ __global__ __launch_bounds__(ET_THREADS, 1) void edge_tc_kernel(
         if (hh == 1) {  // both halves are in registers: the accumulator buffer is free
           tc::tc_fence_before();
           et_mbar_arrive(&bar_tfree[st]);
+          if (tid == 0) EDGE_TR(7, u);
         }
 #pragma unroll
         for (int c = 0; c < 32; ++c) {
