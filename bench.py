@@ -614,12 +614,12 @@ def main():
         stages[name] = ent
     # dominant KERNEL = the kernel with the largest summed device time per call (several stages
     # are launches of the same kernel)
-    kernel_of = {"knn0": "knn_tc2_kernel<4>", "knn1": "knn_tc2_kernel<16>",
-                 "knn2": "knn_tc2_kernel<16>",
+    kernel_of = {"knn0": "knn_tc3_kernel<4>", "knn1": "knn_tc3_kernel<16>",
+                 "knn2": "knn_tc3_kernel<16>",
                  "edge0": "edge_tc_kernel", "edge1": "edge_tc_kernel", "edge2": "edge_tc_kernel",
-                 "pq0": "linear_tc_kernel", "pq1": "linear_tc_kernel", "pq2": "linear_tc_kernel",
-                 "mlp": "linear_tc_kernel", "base": "linear_tc_kernel", "qkv": "linear_tc_kernel",
-                 "att": "attention_tc_kernel", "fps": "fps_q8_kernel", "cg": "lp_cg_kernel",
+                 "pq0": "linear_tc_kernel", "pq1": "linear_ts_kernel", "pq2": "linear_ts_kernel",
+                 "mlp": "linear_ts_kernel", "base": "linear_ts_kernel", "qkv": "linear_ts_kernel",
+                 "att": "attention_tc2_kernel", "fps": "fps_q8_kernel", "cg": "lp_cg_kernel",
                  "dist": "linear_tc_kernel<DIST>", "select": "knn_select_reg_kernel",
                  "proto": "assign_kernel+proto_mean_kernel",
                  "sym": "in_bits/in_rank/in_fill_rank/merge_rows kernels",
