@@ -728,7 +728,8 @@ __device__ long long g_knn_trace[8 * 4096];
 template <int KC4>
 struct KnnSplit {
   static constexpr int TB = tc::tile_bytes(K3_TC, KC4);
-  static constexpr int BLK = 2 * TB + K3_TC * 4;  // hi, lo, norms
+  static constexpr int NORMS = K3_TC * 4 + 16;  // 128 squared norms + their maximum
+  static constexpr int BLK = 2 * TB + NORMS;    // hi, lo, norms
 };
 
 template <int KC4>
@@ -746,7 +747,13 @@ __global__ __launch_bounds__(256) void knn_split_kernel(const float* __restrict_
                                256, vec_ok);
   if (tid < K3_TC) {
     const int cn = t * K3_TC + tid;
-    reinterpret_cast<float*>(sm + 2 * P::TB)[tid] = cn < N ? xx[base + cn] : 0.f;
+    const float nv = cn < N ? xx[base + cn] : 0.f;
+    float* nrm = reinterpret_cast<float*>(sm + 2 * P::TB);
+    nrm[tid] = nv;
+    float mx = nv;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if ((tid & 31) == 0) nrm[K3_TC + (tid >> 5)] = mx;  // four partial maxima (the tile's 16 spare bytes)
   }
   if (tid < 2 * KC4)  // the 16 bytes of padding behind every chunk column (never read by the MMA)
     *reinterpret_cast<float4*>(sm + (tid / KC4) * P::TB + (tid % KC4) * LBO + K3_TC * 16) =
@@ -762,7 +769,7 @@ struct Knn3Smem {
   static constexpr int TB = tc::tile_bytes(K3_TC, KC4);
   static constexpr int B_OFF = 0;                            // NST stages x (hi, lo)
   static constexpr int XS_OFF = B_OFF + NST * 2 * TB;        // |x_j|^2 ring [K3_NR][128]
-  static constexpr int QK_OFF = XS_OFF + K3_NR * K3_TC * 4;  // queue keys [CAP][512] float
+  static constexpr int QK_OFF = XS_OFF + K3_NR * (K3_TC * 4 + 16);  // queue keys [CAP][512] float
   static constexpr int QC_OFF = QK_OFF + CAP * 512 * 4;      // queue columns [CAP][512] u16
   static constexpr int TOTAL = QC_OFF + CAP * 512 * 2;
   static_assert(CAP >= K3_G + 1 && CAP >= 17, "queue region: pass-1 group maxima / half a chunk");
@@ -853,11 +860,13 @@ __global__ __launch_bounds__(K3_THREADS, 1) void knn_tc3_kernel(
         if (j == NST - 1) tc::mbar_wait(&bar_q[1], 0);  // the query tile has left the stage
         KNN_TR(0, j);
         const unsigned char* src = src0 + (int64_t)(j < T ? j : j - T) * P::BLK;
-        tc::mbar_arrive_expect_tx(&bar_sfull[s], (uint32_t)P::BLK);
-        tc::bulk_g2s(smem + S::B_OFF + s * 2 * S::TB, src, 2 * S::TB, &bar_sfull[s]);
+        // pass 1 works on the single product Qhi.Bhi (see the MMA warp): only the hi tile travels
+        const uint32_t tbytes = j < T ? S::TB : 2 * S::TB;
+        tc::mbar_arrive_expect_tx(&bar_sfull[s], tbytes + P::NORMS);
+        tc::bulk_g2s(smem + S::B_OFF + s * 2 * S::TB, src, tbytes, &bar_sfull[s]);
         // norm ring of 8: slot j is rewritten by tile j + 8, whose copy waits for MMA j + 8 - NST
         // (>= j + 4), which was issued after the selectors released tile j + 4 - K3_NACC >= j
-        tc::bulk_g2s(smem + S::XS_OFF + (j & (K3_NR - 1)) * K3_TC * 4, src + 2 * S::TB, K3_TC * 4,
+        tc::bulk_g2s(smem + S::XS_OFF + (j & (K3_NR - 1)) * P::NORMS, src + 2 * S::TB, P::NORMS,
                      &bar_sfull[s]);
       }
     }
@@ -905,15 +914,25 @@ __global__ __launch_bounds__(K3_THREADS, 1) void knn_tc3_kernel(
       const uint32_t b_hi = tc::smem_u32(smem + S::B_OFF + s * 2 * S::TB), b_lo = b_hi + S::TB;
       const uint32_t d = tmem_d + ACC0 + a * K3_TC;
       const uint64_t dbh = tc::make_desc(b_hi, LBOB, 128), dbl = tc::make_desc(b_lo, LBOB, 128);
-      tc::mma_tf32_ts_elect<false>(d, aq_lo, dbh, IDESC);
-      tc::mma_tf32_ts_elect<true>(d, aq_hi, dbl, IDESC);
-      tc::mma_tf32_ts_elect<true>(d, aq_hi, dbh, IDESC);
+      if (j < T) {
+        // pass 1 only has to bound the k-th best key: ONE TF32 product (a third of the MMAs, half
+        // of the tile bytes); the selectors subtract a rigorous bound of what the two dropped
+        // products can contribute
+        tc::mma_tf32_ts_elect<false>(d, aq_hi, dbh, IDESC);
 #pragma unroll
-      for (int ks = 1; ks < 2 * KC4 / 4; ++ks) {
-        if (ks < ksteps) {
-          tc::mma_tf32_ts_elect<true>(d, aq_lo + 8 * ks, dbh + ks * KB, IDESC);
-          tc::mma_tf32_ts_elect<true>(d, aq_hi + 8 * ks, dbl + ks * KB, IDESC);
-          tc::mma_tf32_ts_elect<true>(d, aq_hi + 8 * ks, dbh + ks * KB, IDESC);
+        for (int ks = 1; ks < 2 * KC4 / 4; ++ks)
+          if (ks < ksteps) tc::mma_tf32_ts_elect<true>(d, aq_hi + 8 * ks, dbh + ks * KB, IDESC);
+      } else {
+        tc::mma_tf32_ts_elect<false>(d, aq_lo, dbh, IDESC);
+        tc::mma_tf32_ts_elect<true>(d, aq_hi, dbl, IDESC);
+        tc::mma_tf32_ts_elect<true>(d, aq_hi, dbh, IDESC);
+#pragma unroll
+        for (int ks = 1; ks < 2 * KC4 / 4; ++ks) {
+          if (ks < ksteps) {
+            tc::mma_tf32_ts_elect<true>(d, aq_lo + 8 * ks, dbh + ks * KB, IDESC);
+            tc::mma_tf32_ts_elect<true>(d, aq_hi + 8 * ks, dbl + ks * KB, IDESC);
+            tc::mma_tf32_ts_elect<true>(d, aq_hi + 8 * ks, dbh + ks * KB, IDESC);
+          }
         }
       }
       tc::mma_commit_elect(&bar_sfree[s]);
@@ -931,9 +950,10 @@ __global__ __launch_bounds__(K3_THREADS, 1) void knn_tc3_kernel(
     const int cq = w >> 2;
     const int q = q0 + row;
     const float nq = (q < N) ? -xx[base + q] : 0.f;
-    const float* xs = reinterpret_cast<const float*>(smem + S::XS_OFF) + 32 * cq;
+    const unsigned char* xs_ring = smem + S::XS_OFF;  // slot stride P::NORMS
     const uint32_t taddr = tmem_d + ((uint32_t)(32 * (w & 3)) << 16) + (uint32_t)(ACC0 + 32 * cq);
-    // ---- pass 1: group maxima (16 per thread, 64 per row) ------------------------------------
+    // ---- pass 1: group maxima (16 per thread, 64 per row) of the APPROXIMATE keys (Qhi.Bhi) ---
+    float kmax2 = 0.f;  // largest squared candidate norm
 #pragma unroll 1
     for (int s = 0; s < K3_G; ++s) qk[s * 512 + tid] = -INFINITY;
 #pragma unroll 1
@@ -951,7 +971,12 @@ __global__ __launch_bounds__(K3_THREADS, 1) void knn_tc3_kernel(
       tc::tmem_ld32(taddr + (uint32_t)(a * K3_TC), v);
       if (tid == 0) KNN_TR(5, j);
       const int c0 = j * K3_TC + 32 * cq;
-      knn_keys32(v, nq, xs + (j & (K3_NR - 1)) * K3_TC);
+      {
+        const float* xs = reinterpret_cast<const float*>(xs_ring + (j & (K3_NR - 1)) * P::NORMS);
+        knn_keys32(v, nq, xs + 32 * cq);
+        const float4 tm = *reinterpret_cast<const float4*>(xs + K3_TC);
+        kmax2 = fmaxf(kmax2, fmaxf(fmaxf(tm.x, tm.y), fmaxf(tm.z, tm.w)));
+      }
       tc::tc_fence_before();
       mbar_arrive(&bar_tfree[a]);  // accumulator and the tile's norms are consumed
       if (tid == 0) KNN_TR(6, j);
@@ -1000,6 +1025,14 @@ __global__ __launch_bounds__(K3_THREADS, 1) void knn_tc3_kernel(
       tx[tid] = th;
       asm volatile("bar.sync 2, 512;" ::: "memory");
       tau = fminf(th, tx[tid ^ 256]);
+      // The bound came from keys with Qlo.Bhi + Qhi.Blo missing: |q_lo| <= 2^-11 |q| (TF32 round to
+      // nearest), so the two dot products are below 2^-10 |q||k| (1 + 2^-11), the FP32 accumulation
+      // of the 3 x 64 products differs by < 2e-5 |q||k|, and the key doubles the dot product:
+      // |key - approximate key| < 2^-9 * 1.02 |q| max|k| (+ the rounding of the key's own two
+      // operations).  k approximate keys are >= the approximate bound, so k exact keys are >= it
+      // minus the margin.
+      const float q2 = -nq;
+      tau -= 1.05f * (1.0f / 512.0f) * sqrtf(q2 * kmax2) + (1.0f / 524288.0f) * (q2 + kmax2);
     }
     asm volatile("bar.sync 2, 512;" ::: "memory");  // the maxima are read: the region becomes the queue
     // ---- pass 2: queue everything that reaches the bound, build the lists lazily -------------------
@@ -1033,7 +1066,7 @@ __global__ __launch_bounds__(K3_THREADS, 1) void knn_tc3_kernel(
       tc::tmem_ld32(taddr + (uint32_t)(a * K3_TC), v);
       if (tid == 0) KNN_TR(5, j);
       const int c0 = j2 * K3_TC + 32 * cq;
-      knn_keys32(v, nq, xs + (j & (K3_NR - 1)) * K3_TC);
+      knn_keys32(v, nq, reinterpret_cast<const float*>(xs_ring + (j & (K3_NR - 1)) * P::NORMS) + 32 * cq);
       tc::tc_fence_before();
       mbar_arrive(&bar_tfree[a]);
       if (tid == 0) KNN_TR(6, j);
