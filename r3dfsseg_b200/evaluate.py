@@ -192,6 +192,7 @@ class EpisodeEvaluator:
         dev = self.device
         counters = torch.zeros((3, n_slots), dtype=torch.int64, device=dev)
         loss_sum = torch.zeros((), dtype=torch.float64, device=dev)
+        cg_bad = torch.zeros((), dtype=torch.float64, device=dev)
         cur = torch.cuda.current_stream(dev)
         q: "queue.Queue" = queue.Queue()
 
@@ -216,6 +217,7 @@ class EpisodeEvaluator:
                     sl.ws = torch.empty(need, dtype=torch.uint8, device=dev)
                 sl.counters = torch.zeros_like(counters)
                 sl.loss_sum = torch.zeros_like(loss_sum)
+                sl.cg_bad = None
                 sl.stream.wait_stream(cur)
                 prepared.add(id(sl))
             with torch.cuda.stream(sl.stream):
@@ -225,9 +227,14 @@ class EpisodeEvaluator:
                 sl.issued.set()
                 sx, sy, qx, qy, slot = (d[:n] for d in sl.d)
                 out = self.model.forward_episodes(sx.transpose(3, 4), sy, qx.transpose(2, 3), qy,
-                                                  eval=self.eval_mdns, workspace=sl.ws)
+                                                  eval=self.eval_mdns, workspace=sl.ws,
+                                                  want_diag=True)
                 ops.confusion_accumulate(out["pred"], qy, slot, sl.counters)
                 sl.loss_sum += out["loss"].double().sum()
+                # label-propagation solves that hit cg_max_iter without reaching cg_tol (no sync:
+                # counted on the device, reported with the result)
+                nc_bad = (out["diag"]["cg_iters"] >= int(self.model.cg_max_iter)).sum().double()
+                sl.cg_bad = nc_bad if getattr(sl, "cg_bad", None) is None else sl.cg_bad + nc_bad
                 last_loss = out["loss"]
                 for t in (out["pred"], out["loss"], out["logits"]):
                     t.record_stream(sl.stream)
@@ -241,10 +248,18 @@ class EpisodeEvaluator:
                 cur.wait_stream(sl.stream)
                 counters += sl.counters
                 loss_sum += sl.loss_sum
+                if getattr(sl, "cg_bad", None) is not None:
+                    cg_bad += sl.cg_bad
         n = torch.tensor(float(done), dtype=torch.float64, device=dev)
         all_reduce_eval_state(counters, loss_sum, n)
         res = iou_from_counters(counters)
-        res.update(counters=counters.cpu(), mean_loss=float(loss_sum / n), n_episodes=int(n))
+        res.update(counters=counters.cpu(), mean_loss=float(loss_sum / n), n_episodes=int(n),
+                   cg_not_converged=int(cg_bad))
+        if res["cg_not_converged"]:
+            import warnings
+            warnings.warn("%d label-propagation solve(s) on this rank stopped at cg_max_iter=%d "
+                          "before reaching cg_tol=%g" % (res["cg_not_converged"],
+                                                         self.model.cg_max_iter, self.model.cg_tol))
         if logger is not None and rank == 0:
             for c in range(n_slots):
                 logger.cprint("class %d: iou %f" % (c, res["iou"][c]))

@@ -414,7 +414,13 @@ def _mpti_forward_raw(pw: Optional[PackedWeights], cfg: EpisodeCfg, support_x: t
     L = _lib.lib()
     need = L.r3dfs_mpti_workspace(C.byref(cfg), E)
     if need == 0:
-        raise _lib.R3dfsError("episode configuration not supported by libr3dfs")
+        raise _lib.R3dfsError(
+            "episode configuration outside what libr3dfs is built for: n_way 1..7, k_shot 1..32, "
+            "n_points >= 64, n_subprototypes 1..127, k_connect 1..1024 and < n_queries * n_points, "
+            "graph nodes = roundup64((n_way + 1) * (n_subprototypes + 1)) + n_queries * n_points <= 8192 "
+            "(the merged rows index columns with 16 bits and the CG kernels stage 8192 nodes); got "
+            f"n_way={cfg.n_way} k_shot={cfg.k_shot} n_query={cfg.n_query} n_points={cfg.n_points} "
+            f"n_subprototypes={cfg.n_subprototypes} k_connect={cfg.k_connect}")
     ws = workspace if workspace is not None and workspace.numel() >= need else _ws(need, dev)
     diag = None
     dstruct = None
@@ -502,7 +508,13 @@ def protonet_forward(pw: PackedWeights, cfg: EpisodeCfg, support_x: torch.Tensor
     L = _lib.lib()
     need = L.r3dfs_mpti_workspace(C.byref(cfg), E)
     if need == 0:
-        raise _lib.R3dfsError("episode configuration not supported by libr3dfs")
+        raise _lib.R3dfsError(
+            "episode configuration outside what libr3dfs is built for: n_way 1..7, k_shot 1..32, "
+            "n_points >= 64, n_subprototypes 1..127, k_connect 1..1024 and < n_queries * n_points, "
+            "graph nodes = roundup64((n_way + 1) * (n_subprototypes + 1)) + n_queries * n_points <= 8192 "
+            "(the merged rows index columns with 16 bits and the CG kernels stage 8192 nodes); got "
+            f"n_way={cfg.n_way} k_shot={cfg.k_shot} n_query={cfg.n_query} n_points={cfg.n_points} "
+            f"n_subprototypes={cfg.n_subprototypes} k_connect={cfg.k_connect}")
     ws = workspace if workspace is not None and workspace.numel() >= need else _ws(need, dev)
     with torch.cuda.device(dev):
         check(L.r3dfs_protonet_forward(
