@@ -28,17 +28,20 @@ __device__ long long g_edge_trace[8 * 256];
 #else
 #define EDGE_TR(slot, j) do { } while (0)
 #endif
-#define ET_THREADS 416  // warps 0-3 epilogue, 4-11 producers, 12 MMA issue
-#define ET_PRODUCERS 256
+#define ET_THREADS 416  // warps 0-3 epilogue, 4-7 gather, 8-11 convert, 12 MMA issue
+#define ET_GATHERERS 128
 #define ET_GROUP 128  // points per group (= MMA rows)
 
+#define ET_RAW 4  // gathered P tiles in flight (cp.async ring)
 struct EdgeTcSmem {
-  static constexpr int A_TILE = tc::tile_bytes(128, 16);  // one of hi / lo, K = 64
   static constexpr int W_TILE = tc::tile_bytes(64, 16);
-  static constexpr int A_OFF = 0;           // 2 stages x (hi, lo)
-  static constexpr int W_OFF = 4 * A_TILE;  // W2 hi, lo
+  static constexpr int RAW_TILE = 128 * 64 * 4;  // gathered P rows, FP32: [row][16 chunks], XOR-swizzled
+  static constexpr int RAW_OFF = 0;              // ET_RAW stages
+  static constexpr int W_OFF = ET_RAW * RAW_TILE;  // W2 hi, lo (the split A operand lives in TMEM)
   static constexpr int TOTAL = W_OFF + 2 * W_TILE + 64;
 };
+// TMEM columns: accumulators 0-63 | 64-127, A stage s at 128 + 128 s (hi 64 columns, lo 64 columns)
+#define ET_COL_A 128
 
 __device__ __forceinline__ void et_mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc::smem_u32(bar)) : "memory");
@@ -53,7 +56,9 @@ __global__ __launch_bounds__(ET_THREADS, 1) void edge_tc_kernel(
   __shared__ uint64_t bar_full[2];   // accumulator b ready (also: operand stage b free again)
   __shared__ uint64_t bar_tfree[2];  // accumulator b drained by the 128 epilogue threads
   __shared__ float s_aff[128];       // BN scale (0..63) and shift (64..127) of the second conv
-  __shared__ uint64_t bar_sfull[2];  // operand stage b written by the 256 producer threads
+  __shared__ uint64_t bar_sfull[2];  // TMEM operand stage b written by the 128 converter threads
+  __shared__ uint64_t bar_raw[ET_RAW];    // gathered tile landed (cp.async arrivals of the 128 gather threads)
+  __shared__ uint64_t bar_rfree[ET_RAW];  // gathered tile read back by the 128 converter threads
   __shared__ uint32_t tmem_base_s;
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const int b = blockIdx.y;
@@ -62,7 +67,7 @@ __global__ __launch_bounds__(ET_THREADS, 1) void edge_tc_kernel(
   const int g_begin = blockIdx.x * groups_per_cta;
   const int g_end = min(n_groups, g_begin + groups_per_cta);
   const int U = (g_end - g_begin) * k;  // one tile per (group, neighbour slot)
-  constexpr int LBO_A = tc::tile_lbo(128), LBO_W = tc::tile_lbo(64);
+  constexpr int LBO_W = tc::tile_lbo(64);
   constexpr uint32_t IDESC = tc::make_idesc_tf32(128, 64);
 
   if (tid == 0) {
@@ -70,11 +75,15 @@ __global__ __launch_bounds__(ET_THREADS, 1) void edge_tc_kernel(
     tc::mbar_init(&bar_full[1], 1);
     tc::mbar_init(&bar_tfree[0], 128);
     tc::mbar_init(&bar_tfree[1], 128);
-    tc::mbar_init(&bar_sfull[0], ET_PRODUCERS);
-    tc::mbar_init(&bar_sfull[1], ET_PRODUCERS);
+    tc::mbar_init(&bar_sfull[0], 128);
+    tc::mbar_init(&bar_sfull[1], 128);
+    for (int i = 0; i < ET_RAW; ++i) {
+      tc::mbar_init(&bar_raw[i], ET_GATHERERS);
+      tc::mbar_init(&bar_rfree[i], 128);
+    }
     tc::mbar_fence_init();
   }
-  if (w == 0) tc::tmem_alloc(&tmem_base_s, 128);
+  if (w == 0) tc::tmem_alloc(&tmem_base_s, 512);
   if (tid < 64) s_aff[tid] = __ldg(s2 + tid);
   else if (tid < 128) s_aff[tid] = __ldg(t2 + tid - 64);
   // resident W2 (64 x 64, row-major [c][kk] = K-major) as hi / lo tiles
@@ -92,7 +101,7 @@ __global__ __launch_bounds__(ET_THREADS, 1) void edge_tc_kernel(
   tc::tc_fence_after();
   const uint32_t tmem_d = tmem_base_s;
   if (U <= 0) {
-    if (w == 0) tc::tmem_dealloc(tmem_d, 128);
+    if (w == 0) tc::tmem_dealloc(tmem_d, 512);
     return;
   }
 
@@ -105,25 +114,24 @@ __global__ __launch_bounds__(ET_THREADS, 1) void edge_tc_kernel(
     {
       const uint32_t wh = tc::smem_u32(smem + S::W_OFF), wl = wh + S::W_TILE;
       const uint64_t dwh = tc::make_desc(wh, LBO_W, 128), dwl = tc::make_desc(wl, LBO_W, 128);
-      constexpr uint64_t KA = tc::desc_kstep(LBO_A), KW = tc::desc_kstep(LBO_W);
+      constexpr uint64_t KW = tc::desc_kstep(LBO_W);
       for (int u = 0; u < U; ++u) {
         const int st = u & 1;
-        tc::mbar_wait(&bar_sfull[st], (u >> 1) & 1);                      // A tile staged
+        tc::mbar_wait(&bar_sfull[st], (u >> 1) & 1);                      // A stage written (TMEM)
         if (lane == 0) EDGE_TR(0, u);
         if (u >= 2) tc::mbar_wait(&bar_tfree[st], ((u >> 1) - 1) & 1);    // accumulator drained
         if (lane == 0) EDGE_TR(1, u);
         tc::tc_fence_after();
-        const uint32_t ah = tc::smem_u32(smem + S::A_OFF + st * 2 * S::A_TILE), al = ah + S::A_TILE;
+        const uint32_t ah = tmem_d + ET_COL_A + st * 128, al = ah + 64;
         const uint32_t d = tmem_d + st * 64;
-        const uint64_t dah = tc::make_desc(ah, LBO_A, 128), dal = tc::make_desc(al, LBO_A, 128);
-        tc::mma_tf32_elect(d, dal, dwh, IDESC, 0);
-        tc::mma_tf32_elect(d, dah, dwl, IDESC, 1);
-        tc::mma_tf32_elect(d, dah, dwh, IDESC, 1);
+        tc::mma_tf32_ts_e(d, al, dwh, IDESC, 0);
+        tc::mma_tf32_ts_e(d, ah, dwl, IDESC, 1);
+        tc::mma_tf32_ts_e(d, ah, dwh, IDESC, 1);
 #pragma unroll
         for (int ks = 1; ks < 8; ++ks) {
-          tc::mma_tf32_elect(d, dal + ks * KA, dwh + ks * KW, IDESC, 1);
-          tc::mma_tf32_elect(d, dah + ks * KA, dwl + ks * KW, IDESC, 1);
-          tc::mma_tf32_elect(d, dah + ks * KA, dwh + ks * KW, IDESC, 1);
+          tc::mma_tf32_ts_e(d, al + 8 * ks, dwh + ks * KW, IDESC, 1);
+          tc::mma_tf32_ts_e(d, ah + 8 * ks, dwl + ks * KW, IDESC, 1);
+          tc::mma_tf32_ts_e(d, ah + 8 * ks, dwh + ks * KW, IDESC, 1);
         }
         tc::mma_commit_elect(&bar_full[st]);
         if (lane == 0) EDGE_TR(2, u);
@@ -131,82 +139,117 @@ __global__ __launch_bounds__(ET_THREADS, 1) void edge_tc_kernel(
     }
   } else if (w >= 4) {
     // --------------------------- producers -----------------------------------------------------
-    const int lt = tid - 128;
-    constexpr int NCH = 128 * 16 / ET_PRODUCERS;  // 8 cells per thread: rows (lt>>4) + 16 i
-    const int kc = lt & 15;
-    const int r0 = lt >> 4;
-    int nb[NCH];
-    float4 qv4[NCH];
-    auto load_nb = [&](int u2) {  // neighbour indices of tile u2 (prefetched one tile ahead)
-      const int g2 = g_begin + u2 / k, j = u2 % k;
-#pragma unroll
-      for (int i = 0; i < NCH; ++i) {
-        const int p = g2 * ET_GROUP + r0 + 16 * i;
-        nb[i] = (u2 < U && p < N) ? idx[(base + p) * k + j] : -1;
-      }
-    };
-    // Software pipeline: the gathers of tile u + 1 are issued as soon as tile u has been written
-    // to its stage (their registers are free again), so their L2 round trip overlaps the fence,
-    // the producers' barrier, the MMA issue and the wait for the next stage; the neighbour
-    // indices run one tile further ahead.
-    float4 hv[NCH];
-    int live = 0;
-    auto issue_gather = [&]() {  // rows nb[] of P -> hv (all loads in flight together)
-      live = 0;
-#pragma unroll
-      for (int i = 0; i < NCH; ++i) {
-        const int nbi = nb[i] >= 0 ? nb[i] : 0;
-        live |= (nb[i] >= 0) << i;
-        hv[i] = __ldg(reinterpret_cast<const float4*>(PQ + (base + nbi) * 128 + 4 * kc));
-      }
-    };
-    load_nb(0);
-    issue_gather();
-    load_nb(1);
-    for (int u = 0; u < U; ++u) {
-      const int st = u & 1;
-      const int g = g_begin + u / k;
-      if (lt == 0) EDGE_TR(3, u);
-      if (u % k == 0) {  // new group: this thread's Q cells stay in registers for all k tiles
+    // Two producer roles, decoupled by a ring of ET_RAW gathered tiles in shared memory:
+    //  warps 4-7  GATHER: cp.async, up to ET_RAW tiles ahead, no registers.  A thread copies 16
+    //             fixed (row, 16-byte chunk) cells of every tile — half a warp fetches one contiguous
+    //             256-byte row of P — to chunk c of row r at r * 256 + ((c ^ (r & 15)) * 16
+    //             (conflict-free for this mapping and for the converters') and lets the copies
+    //             arrive on the tile's mbarrier; the neighbour indices run one tile ahead.
+    //  warps 8-11 CONVERT: thread = point row (a warp owns TMEM lane quarter w % 4): reads its row
+    //             back, adds Q (in registers for the whole group), LeakyReLU, TF32 hi / lo split,
+    //             and writes both parts into the TMEM A stage (tcgen05.st).
+    // The MMA reads only W2 from shared memory.  Before: every producer thread gathered into
+    // registers one tile ahead, converted, and stored hi / lo operand tiles to shared memory (64 KB
+    // written + 96 KB read by the MMAs per tile next to 48 KB of W2 reads): that serial chain per
+    // tile — wait for the gather + add 900, stores 1200, next gather 500 cycles — set the pace at
+    // 2850 cycles per tile with 1150 of MMAs.  Measured and dropped on the way: a lane-per-row
+    // register gather (8x the L1 wavefronts), staging through shared memory behind a producer-wide
+    // barrier, 12 / 16 producer warps and 8 gather warps with setmaxnreg (no gain: the copies of a
+    // tile take ~1800 cycles however many warps issue them), one 256-byte cp.async.bulk per row (the
+    // TMA engine needs ~23 cycles per small copy: 3000 cycles per tile), and all eight warps doing
+    // both roles in lockstep (2400: the LSU idles while everybody converts and vice versa).
+    if (w < 8) {
+      const int gt = tid - 128;
+      constexpr int NCH = 16;  // cells per thread: rows (gt >> 4) + 8 i
+      const int kc = gt & 15;
+      const int r0 = gt >> 4;
+      // neighbour indices run TWO tiles ahead of their copies (two register sets): loaded one tile
+      // ahead, their L2 round trip sat in front of every tile's copies
+      int nbA[NCH], nbB[NCH];
+      auto load_nb = [&](int (&nb)[NCH], int u2) {
+        const int g2 = g_begin + u2 / k, j = u2 % k;
 #pragma unroll
         for (int i = 0; i < NCH; ++i) {
-          const int p = min(g * ET_GROUP + r0 + 16 * i, N - 1);
-          qv4[i] = __ldg(reinterpret_cast<const float4*>(PQ + (base + p) * 128 + 64 + 4 * kc));
+          const int p = g2 * ET_GROUP + r0 + 8 * i;
+          nb[i] = (u2 < U && p < N) ? idx[(base + p) * k + j] : 0;  // rows beyond N are never stored
+        }
+      };
+      auto copy_tile = [&](const int (&nb)[NCH], int u) {
+        const int rs = u % ET_RAW;
+        if (u >= ET_RAW) tc::mbar_wait(&bar_rfree[rs], ((u / ET_RAW) - 1) & 1);
+        if (gt == 0) EDGE_TR(3, u);
+        const uint32_t dst0 = tc::smem_u32(smem + S::RAW_OFF + rs * S::RAW_TILE);
+#pragma unroll
+        for (int i = 0; i < NCH; ++i) {
+          const int r = r0 + 8 * i;
+          const float* src = PQ + (base + nb[i]) * 128 + 4 * kc;
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(
+                           dst0 + r * 256 + ((kc ^ (r & 15)) << 4)),
+                       "l"(src)
+                       : "memory");
+        }
+        asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(
+                         tc::smem_u32(&bar_raw[rs]))
+                     : "memory");
+      };
+      load_nb(nbA, 0);
+      load_nb(nbB, 1);
+      for (int u = 0; u < U; u += 2) {
+        copy_tile(nbA, u);
+        load_nb(nbA, u + 2);
+        if (gt == 0) EDGE_TR(4, u);
+        if (u + 1 < U) {
+          copy_tile(nbB, u + 1);
+          load_nb(nbB, u + 3);
+          if (gt == 0) EDGE_TR(4, u + 1);
         }
       }
+    } else {
+      const int row = 32 * (w & 3) + lane;
+      const uint32_t trow = tmem_d + ((uint32_t)(32 * (w & 3)) << 16) + ET_COL_A;
+      float4 qv4[16];
+      for (int u = 0; u < U; ++u) {
+        const int st = u & 1, rs = u % ET_RAW;
+        const int g = g_begin + u / k;
+        if (u % k == 0) {  // new group: this row's Q values stay in registers for all k tiles
+          const int p = min(g * ET_GROUP + row, N - 1);
+          const float4* src = reinterpret_cast<const float4*>(PQ + (base + p) * 128 + 64);
 #pragma unroll
-      for (int i = 0; i < NCH; ++i) {
-        float4 h = make_float4(0.f, 0.f, 0.f, 0.f);
-        if ((live >> i) & 1) {
-          h.x = hv[i].x + qv4[i].x; h.y = hv[i].y + qv4[i].y;
-          h.z = hv[i].z + qv4[i].z; h.w = hv[i].w + qv4[i].w;
-          h.x = h.x > 0.f ? h.x : 0.2f * h.x;
-          h.y = h.y > 0.f ? h.y : 0.2f * h.y;
-          h.z = h.z > 0.f ? h.z : 0.2f * h.z;
-          h.w = h.w > 0.f ? h.w : 0.2f * h.w;
+          for (int i = 0; i < 16; ++i) qv4[i] = __ldg(src + i);
         }
-        hv[i] = h;
-      }
-      if (lt == 0) EDGE_TR(4, u);
-      if (u >= 2) tc::mbar_wait(&bar_full[st], ((u >> 1) - 1) & 1);  // stage's MMAs finished
-      if (lt == 0) EDGE_TR(5, u);
-      unsigned char* a_hi = smem + S::A_OFF + st * 2 * S::A_TILE;
-      unsigned char* a_lo = a_hi + S::A_TILE;
+        tc::mbar_wait(&bar_raw[rs], (u / ET_RAW) & 1);  // the gathered tile has landed
+        if (u >= 2) tc::mbar_wait(&bar_full[st], ((u >> 1) - 1) & 1);  // TMEM A stage: its MMAs finished
+        tc::tc_fence_after();
+        if (tid == 256) EDGE_TR(5, u);
+        const unsigned char* raw = smem + S::RAW_OFF + rs * S::RAW_TILE + row * 256;
 #pragma unroll
-      for (int i = 0; i < NCH; ++i) {
-        const int r = r0 + 16 * i;
-        float4 hi, lo;
-        tc::split4(hv[i], hi, lo);
-        *reinterpret_cast<float4*>(a_hi + kc * LBO_A + r * 16) = hi;
-        *reinterpret_cast<float4*>(a_lo + kc * LBO_A + r * 16) = lo;
+        for (int q = 0; q < 4; ++q) {  // 16 channels at a time
+          float hi[16], lo[16];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int c = 4 * q + i;
+            const float4 g4 = *reinterpret_cast<const float4*>(raw + ((c ^ (row & 15)) << 4));
+            const float4 q4 = qv4[c];
+            float4 h;
+            h.x = g4.x + q4.x; h.y = g4.y + q4.y; h.z = g4.z + q4.z; h.w = g4.w + q4.w;
+            h.x = h.x > 0.f ? h.x : 0.2f * h.x;
+            h.y = h.y > 0.f ? h.y : 0.2f * h.y;
+            h.z = h.z > 0.f ? h.z : 0.2f * h.z;
+            h.w = h.w > 0.f ? h.w : 0.2f * h.w;
+            float4 ph, pl;
+            tc::split4(h, ph, pl);
+            hi[4 * i] = ph.x; hi[4 * i + 1] = ph.y; hi[4 * i + 2] = ph.z; hi[4 * i + 3] = ph.w;
+            lo[4 * i] = pl.x; lo[4 * i + 1] = pl.y; lo[4 * i + 2] = pl.z; lo[4 * i + 3] = pl.w;
+          }
+          tc::tmem_st16(trow + st * 128 + 16 * q, hi);
+          tc::tmem_st16(trow + st * 128 + 64 + 16 * q, lo);
+        }
+        et_mbar_arrive(&bar_rfree[rs]);  // (the loads above have returned: their values were used)
+        tc::tmem_st_wait();
+        tc::tc_fence_before();
+        et_mbar_arrive(&bar_sfull[st]);
+        if (tid == 256) EDGE_TR(6, u);
       }
-      if (u + 1 < U) {
-        issue_gather();  // nb holds the indices of tile u + 1
-        load_nb(u + 2);
-      }
-      tc::fence_async_smem();
-      et_mbar_arrive(&bar_sfull[st]);
-      if (lt == 0) EDGE_TR(6, u);
     }
   } else {
     // --------------------------- epilogue: thread = point row, all 64 channels ------------------
@@ -250,7 +293,7 @@ __global__ __launch_bounds__(ET_THREADS, 1) void edge_tc_kernel(
   }
   tc::tc_fence_before();
   __syncthreads();
-  if (w == 0) tc::tmem_dealloc(tmem_d, 128);
+  if (w == 0) tc::tmem_dealloc(tmem_d, 512);
 }
 
 int launch_edge_mlp_tc(const float* PQ, const int32_t* idx, const float* w2, const float* s2,
