@@ -723,6 +723,9 @@ __device__ long long g_knn_trace[8 * 4096];
 #define K3_TC 128
 #define K3_NACC 3
 #define K3_NR 8
+// single-product pass 1 pays where the MMAs dominate a tile (C = 64: 24 -> 8 per tile); at C <= 16 a
+// tile has 6 MMAs anyway and the looser bound only adds candidates (knn0 1.47 -> 1.58 ms)
+#define K3_APPROX1(kc4) ((kc4) >= 16)
 #define K3_G 16   // group maxima per selector thread (64 per row)
 
 template <int KC4>
@@ -861,7 +864,7 @@ __global__ __launch_bounds__(K3_THREADS, 1) void knn_tc3_kernel(
         KNN_TR(0, j);
         const unsigned char* src = src0 + (int64_t)(j < T ? j : j - T) * P::BLK;
         // pass 1 works on the single product Qhi.Bhi (see the MMA warp): only the hi tile travels
-        const uint32_t tbytes = j < T ? S::TB : 2 * S::TB;
+        const uint32_t tbytes = (K3_APPROX1(KC4) && j < T) ? S::TB : 2 * S::TB;
         tc::mbar_arrive_expect_tx(&bar_sfull[s], tbytes + P::NORMS);
         tc::bulk_g2s(smem + S::B_OFF + s * 2 * S::TB, src, tbytes, &bar_sfull[s]);
         // norm ring of 8: slot j is rewritten by tile j + 8, whose copy waits for MMA j + 8 - NST
@@ -914,7 +917,7 @@ __global__ __launch_bounds__(K3_THREADS, 1) void knn_tc3_kernel(
       const uint32_t b_hi = tc::smem_u32(smem + S::B_OFF + s * 2 * S::TB), b_lo = b_hi + S::TB;
       const uint32_t d = tmem_d + ACC0 + a * K3_TC;
       const uint64_t dbh = tc::make_desc(b_hi, LBOB, 128), dbl = tc::make_desc(b_lo, LBOB, 128);
-      if (j < T) {
+      if (K3_APPROX1(KC4) && j < T) {
         // pass 1 only has to bound the k-th best key: ONE TF32 product (a third of the MMAs, half
         // of the tile bytes); the selectors subtract a rigorous bound of what the two dropped
         // products can contribute
@@ -974,8 +977,10 @@ __global__ __launch_bounds__(K3_THREADS, 1) void knn_tc3_kernel(
       {
         const float* xs = reinterpret_cast<const float*>(xs_ring + (j & (K3_NR - 1)) * P::NORMS);
         knn_keys32(v, nq, xs + 32 * cq);
-        const float4 tm = *reinterpret_cast<const float4*>(xs + K3_TC);
-        kmax2 = fmaxf(kmax2, fmaxf(fmaxf(tm.x, tm.y), fmaxf(tm.z, tm.w)));
+        if (K3_APPROX1(KC4)) {
+          const float4 tm = *reinterpret_cast<const float4*>(xs + K3_TC);
+          kmax2 = fmaxf(kmax2, fmaxf(fmaxf(tm.x, tm.y), fmaxf(tm.z, tm.w)));
+        }
       }
       tc::tc_fence_before();
       mbar_arrive(&bar_tfree[a]);  // accumulator and the tile's norms are consumed
@@ -1032,7 +1037,8 @@ __global__ __launch_bounds__(K3_THREADS, 1) void knn_tc3_kernel(
       // operations).  k approximate keys are >= the approximate bound, so k exact keys are >= it
       // minus the margin.
       const float q2 = -nq;
-      tau -= 1.05f * (1.0f / 512.0f) * sqrtf(q2 * kmax2) + (1.0f / 524288.0f) * (q2 + kmax2);
+      if (K3_APPROX1(KC4))
+        tau -= 1.05f * (1.0f / 512.0f) * sqrtf(q2 * kmax2) + (1.0f / 524288.0f) * (q2 + kmax2);
     }
     asm volatile("bar.sync 2, 512;" ::: "memory");  // the maxima are read: the region becomes the queue
     // ---- pass 2: queue everything that reaches the bound, build the lists lazily -------------------
