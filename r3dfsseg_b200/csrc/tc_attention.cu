@@ -421,6 +421,14 @@ __global__ __launch_bounds__(AT_ALL_THREADS, 1) void attention_tc_kernel(const f
 //                       O 384-447 | P lo (one 64-key half) 448-511.
 //   Same split arithmetic, same k-step and key order as attention_tc_kernel: bit-identical output.
 // ---------------------------------------------------------------------------------------------
+// per-tile timestamps of one CTA (scripts/microbench/att_trace.cu compiles this file with ATT_TRACE)
+#ifdef ATT_TRACE
+__device__ long long g_att_trace[8 * 256];
+#define ATT_TR(slot, j) \
+  do { if (blockIdx.x == ATT_TRACE_BX && blockIdx.y == ATT_TRACE_BY) g_att_trace[(slot) * 256 + (j)] = clock64(); } while (0)
+#else
+#define ATT_TR(slot, j) do { } while (0)
+#endif
 #define A2_THREADS 576  // warps 0-15 workers, 16 copy producer, 17 MMA issue
 struct Att2 {
   static constexpr int K_TILE = tc::tile_bytes(128, 16);  // 128 keys x 64 (d), hi or lo
@@ -609,53 +617,68 @@ __global__ __launch_bounds__(A2_THREADS, 1) void attention_tc2_kernel(
   } else if (w == 17) {
     // ------------------------------ MMA issue (whole warp, elected lane) ----------------------
     constexpr uint64_t KK = tc::desc_kstep(LBO_K), KV = tc::desc_kstep(LBO_V);
-    auto issue_s = [&](int g) {  // S(g) = Q K^T into S buffer g & 1
+    // S(g) = Q K^T into S buffer g & 1, in two halves of four k-steps (part 0 waits for the operands,
+    // part 1 commits).  In sweep 2 the halves are interleaved with the two P.V halves of the previous
+    // tile — S(j+1) a | PV(j, A) | S(j+1) b | PV(j, B): the single P lo buffer can only be rewritten
+    // for half B once PV(j, A) has completed, and with S(j+1) issued in one piece in front of both
+    // PV halves the pipe idled ~650 cycles per tile waiting for that hand-over (trace:
+    // scripts/microbench/att_trace.cu); now S(j+1) b runs meanwhile.  Same MMA order per accumulator.
+    auto issue_s = [&](int g, int part) {
       const int kb = g & 1;
-      tc::mbar_wait(&bar_kfull[kb], (g >> 1) & 1);
-      // the buffer's previous content was read by the workers (sweep 1) — in sweep 2 it holds P hi
-      // of tile g - 2, whose PV MMAs were issued before this point and execute in issue order
-      if (g >= 2 && g - 2 < T1) tc::mbar_wait(&bar_sfree[kb], ((g >> 1) - 1) & 1);
-      tc::tc_fence_after();
+      if (part != 1) {
+        tc::mbar_wait(&bar_kfull[kb], (g >> 1) & 1);
+        if (lane == 0) ATT_TR(0, g);
+        // the buffer's previous content was read by the workers (sweep 1) — in sweep 2 it holds P hi
+        // of tile g - 2, whose PV MMAs were issued before this point and execute in issue order
+        if (g >= 2 && g - 2 < T1) tc::mbar_wait(&bar_sfree[kb], ((g >> 1) - 1) & 1);
+        tc::tc_fence_after();
+      }
       const uint32_t k_hi = tc::smem_u32(smem + S::K_OFF + kb * 2 * S::K_TILE), k_lo = k_hi + S::K_TILE;
       const uint64_t dkh = tc::make_desc(k_hi, LBO_K, 128), dkl = tc::make_desc(k_lo, LBO_K, 128);
       const uint32_t d = tmem + COL_S + kb * 128;
+      const int ks0 = part == 1 ? 4 : 0, ks1 = part == 0 ? 4 : 8;  // part 2: all eight k-steps
       if (g < T1 && approx) {
-#pragma unroll
-        for (int ks = 0; ks < 8; ++ks)
+        for (int ks = ks0; ks < ks1; ++ks)
           tc::mma_tf32_ts_e(d, tmem + COL_QH + 8 * ks, dkh + ks * KK, IDESC_S, ks != 0);
       } else {
-#pragma unroll
-        for (int ks = 0; ks < 8; ++ks) {
+        for (int ks = ks0; ks < ks1; ++ks) {
           tc::mma_tf32_ts_e(d, tmem + COL_QL + 8 * ks, dkh + ks * KK, IDESC_S, ks != 0);
           tc::mma_tf32_ts_e(d, tmem + COL_QH + 8 * ks, dkl + ks * KK, IDESC_S, 1);
           tc::mma_tf32_ts_e(d, tmem + COL_QH + 8 * ks, dkh + ks * KK, IDESC_S, 1);
         }
       }
-      tc::mma_commit_elect(&bar_kfree[kb]);
-      tc::mma_commit_elect(&bar_sfull[kb]);
-    };
-    for (int g = 0; g < T1; ++g) issue_s(g);
-    if (T > 0) issue_s(T1);
-    for (int j = 0; j < T; ++j) {
-      if (j + 1 < T) issue_s(T1 + j + 1);
-      const uint32_t p_hi = tmem + COL_S + ((T1 + j) & 1) * 128;
-#pragma unroll 1
-      for (int h = 0; h < 2; ++h) {
-        tc::mbar_wait(&bar_pfull[h], j & 1);
-        tc::mbar_wait(&bar_vfull[h], j & 1);
-        tc::tc_fence_after();
-        const uint32_t v_hi = tc::smem_u32(smem + S::V_OFF + h * 2 * S::V_HALF), v_lo = v_hi + S::V_HALF;
-        const uint64_t dvh = tc::make_desc(v_hi, LBO_V, 128), dvl = tc::make_desc(v_lo, LBO_V, 128);
-        const uint32_t ah = p_hi + 64 * h, al = tmem + COL_PL;
-#pragma unroll
-        for (int ks = 0; ks < 8; ++ks) {
-          tc::mma_tf32_ts_e(tmem + COL_O, al + 8 * ks, dvh + ks * KV, IDESC_O, (j | h | ks) != 0);
-          tc::mma_tf32_ts_e(tmem + COL_O, ah + 8 * ks, dvl + ks * KV, IDESC_O, 1);
-          tc::mma_tf32_ts_e(tmem + COL_O, ah + 8 * ks, dvh + ks * KV, IDESC_O, 1);
-        }
-        tc::mma_commit_elect(&bar_vfree[h]);
-        tc::mma_commit_elect(&bar_pvdone[h]);
+      if (part != 0) {
+        tc::mma_commit_elect(&bar_kfree[kb]);
+        tc::mma_commit_elect(&bar_sfull[kb]);
+        if (lane == 0) ATT_TR(1, g);
       }
+    };
+    auto issue_pv = [&](int j, int h) {
+      const uint32_t p_hi = tmem + COL_S + ((T1 + j) & 1) * 128;
+      tc::mbar_wait(&bar_pfull[h], j & 1);
+      if (lane == 0) ATT_TR(2 + h, j);
+      tc::mbar_wait(&bar_vfull[h], j & 1);
+      tc::tc_fence_after();
+      const uint32_t v_hi = tc::smem_u32(smem + S::V_OFF + h * 2 * S::V_HALF), v_lo = v_hi + S::V_HALF;
+      const uint64_t dvh = tc::make_desc(v_hi, LBO_V, 128), dvl = tc::make_desc(v_lo, LBO_V, 128);
+      const uint32_t ah = p_hi + 64 * h, al = tmem + COL_PL;
+#pragma unroll
+      for (int ks = 0; ks < 8; ++ks) {
+        tc::mma_tf32_ts_e(tmem + COL_O, al + 8 * ks, dvh + ks * KV, IDESC_O, (j | h | ks) != 0);
+        tc::mma_tf32_ts_e(tmem + COL_O, ah + 8 * ks, dvl + ks * KV, IDESC_O, 1);
+        tc::mma_tf32_ts_e(tmem + COL_O, ah + 8 * ks, dvh + ks * KV, IDESC_O, 1);
+      }
+      tc::mma_commit_elect(&bar_vfree[h]);
+      tc::mma_commit_elect(&bar_pvdone[h]);
+      if (lane == 0) ATT_TR(4 + h, j);
+    };
+    for (int g = 0; g < T1; ++g) issue_s(g, 2);
+    if (T > 0) issue_s(T1, 2);
+    for (int j = 0; j < T; ++j) {
+      if (j + 1 < T) issue_s(T1 + j + 1, 0);
+      issue_pv(j, 0);
+      if (j + 1 < T) issue_s(T1 + j + 1, 1);
+      issue_pv(j, 1);
     }
   } else {
     // ------------------------------ workers ---------------------------------------------------
@@ -687,6 +710,7 @@ __global__ __launch_bounds__(A2_THREADS, 1) void attention_tc2_kernel(
     for (int j = 0; j < T; ++j) {
       const int g = T1 + j, sb = g & 1;
       tc::mbar_wait(&bar_sfull[sb], (g >> 1) & 1);
+      if (tid == 0) ATT_TR(6, j);
       tc::tc_fence_after();
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
@@ -694,13 +718,21 @@ __global__ __launch_bounds__(A2_THREADS, 1) void attention_tc2_kernel(
         const uint32_t col = COL_S + sb * 128 + 64 * h + 16 * cq;
         tc::tmem_ld16(trow + col, v);
         const int c0 = j * 128 + 64 * h + 16 * cq;
+        const bool full = (j + 1) * 128 <= N;  // CTA-uniform: no key of this tile lies beyond N
 #pragma unroll
         for (int e = 0; e < 16; e += 4) {
           float4 p;
-          p.x = (c0 + e + 0 < N) ? expf(v[e + 0] - m_row) : 0.f;
-          p.y = (c0 + e + 1 < N) ? expf(v[e + 1] - m_row) : 0.f;
-          p.z = (c0 + e + 2 < N) ? expf(v[e + 2] - m_row) : 0.f;
-          p.w = (c0 + e + 3 < N) ? expf(v[e + 3] - m_row) : 0.f;
+          if (full) {
+            p.x = expf(v[e + 0] - m_row);
+            p.y = expf(v[e + 1] - m_row);
+            p.z = expf(v[e + 2] - m_row);
+            p.w = expf(v[e + 3] - m_row);
+          } else {
+            p.x = (c0 + e + 0 < N) ? expf(v[e + 0] - m_row) : 0.f;
+            p.y = (c0 + e + 1 < N) ? expf(v[e + 1] - m_row) : 0.f;
+            p.z = (c0 + e + 2 < N) ? expf(v[e + 2] - m_row) : 0.f;
+            p.w = (c0 + e + 3 < N) ? expf(v[e + 3] - m_row) : 0.f;
+          }
           l_run += (p.x + p.y) + (p.z + p.w);
           float4 ph, pl;
           tc::split4(p, ph, pl);
@@ -719,6 +751,7 @@ __global__ __launch_bounds__(A2_THREADS, 1) void attention_tc2_kernel(
         tc::tmem_st_wait();
         tc::tc_fence_before();
         a2_arrive(&bar_pfull[h]);
+        if (tid == 0 && h == 1) ATT_TR(7, j);
       }
     }
     // ---------------- epilogue: O / l ----------------------------------------------------------
