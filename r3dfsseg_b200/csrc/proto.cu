@@ -239,7 +239,11 @@ int launch_fps_ex(const float* feat, int D, const int32_t* set_off, const int32_
                              cnt_out, st);
   if (sets_per_group > 1 && n_sets % sets_per_group == 0) {
     const int groups = n_sets / sets_per_group, per = sets_per_group - 1;
-    R3DFS_TRY(launch_fps_q8(feat, set_off, set_n, groups, 0, 1, sets_per_group, n_cap, 0, m_max,
+    static const int bg_cl = [] {  // A/B switch: R3DFS_FPS_BG_CL = CTAs per background set (0: fit the set)
+      const char* e = R3DFS_GETENV("R3DFS_FPS_BG_CL");
+      return e ? atoi(e) : 0;
+    }();
+    R3DFS_TRY(launch_fps_q8(feat, set_off, set_n, groups, 0, 1, sets_per_group, n_cap, bg_cl, m_max,
                             k_for_count, spill, idx_out, cnt_out, st));
     // foreground sets: as many CTAs per set as keep all of them in ONE wave (rows beyond the
     // cluster's shared memory are swept from the spill area, still as bytes)
