@@ -9,8 +9,10 @@
 // Softmax is shift invariant, so sweep 1 only has to deliver SOME m' >= max_j S_ij that keeps
 // exp(S - m') in the normal FP32 range:
 //   - if b = |q_i / 8| * max_j |k_j| (Cauchy-Schwarz; the per-cloud key-norm maximum comes from a
-//     small pre-kernel) is <= 60 for every row of the CTA, m' = b and sweep 1 is skipped
-//     (exp(-60) = 9e-27 is far above FP32's 1e-38);
+//     small pre-kernel) is <= 43 for every row of the CTA, m' = b and sweep 1 is skipped: every
+//     S_ij lies in [-b, b], so exp(S - b) >= exp(-2 b) >= exp(-86) = 4.5e-38 stays a normal FP32
+//     number even for a row whose keys are all anti-aligned with its query (the row sum cannot
+//     underflow);
 //   - otherwise sweep 1 runs with ONE TF32 product per k-step (Qhi.Khi, a third of the MMAs, no lo
 //     tiles) and m' = its row maximum + 2^-10 b, which bounds what the dropped products can add.
 // The (N, N) attention map exists only as 128 x 64 tiles in TMEM / shared memory.
@@ -242,7 +244,7 @@ __global__ __launch_bounds__(AT_ALL_THREADS, 1) void attention_tc_kernel(const f
     m_row = sqrtf(q2) * sqrtf(__ldg(kmax2 + b)) * 1.0001f + 1e-6f;
     // Qhi.Khi drops q_lo.k + q_hi.k_lo: |error| <= 2 * 2^-11 |q||k|  (TF32 rounding is 2^-11 relative)
     margin = m_row * (1.0f / 1024.0f) * 1.01f + 1e-6f;
-    sweep1 = __syncthreads_or(!(m_row <= 60.f));
+    sweep1 = __syncthreads_or(!(m_row <= 43.f));
   }
   if (sweep1) {
     // ---------------- sweep 1: row maxima (approximate + safety margin, or exact) ----------------
@@ -577,7 +579,7 @@ __global__ __launch_bounds__(A2_THREADS, 1) void attention_tc2_kernel(
     const float q2 = (xch[xr] + xch[128 + xr]) + (xch[256 + xr] + xch[384 + xr]);
     m_row = sqrtf(q2) * sqrtf(__ldg(kmax2 + b)) * 1.0001f + 1e-6f;
     margin = m_row * (1.0f / 1024.0f) * 1.01f + 1e-6f;
-    sweep1 = __syncthreads_or(!(m_row <= 60.f));
+    sweep1 = __syncthreads_or(!(m_row <= 43.f));
   }
   const int T1 = sweep1 ? T : 0;  // tiles of the first sweep; global tile index g = T1 + j in sweep 2
   const unsigned char* src0 = split + (int64_t)b * T * S::BLK;
