@@ -687,7 +687,11 @@ def main():
                                     args.steps, args.warmup)
         set_workload(main_workload)
         torch.cuda.empty_cache()
-        extra["train_step"] = train_leg(dev, dist, rank, world, max(10, 2 * args.steps), args.warmup)
+        # (20+ timed steps after 8 warm-up steps: with 3 + 10 the 4-GPU run still had NCCL's lazy
+        # set-up of the two new message sizes and the 3.4 GB workspace allocation inside the timed
+        # region — 26.3 ms per step against 17.9 for scripts/bench_train.py alone)
+        extra["train_step"] = train_leg(dev, dist, rank, world, max(20, 2 * args.steps),
+                                        max(8, args.warmup))
 
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
