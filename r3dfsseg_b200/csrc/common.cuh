@@ -132,6 +132,8 @@ int launch_linear_tma(const float* X, int ldx, const float* W, const float* s, c
 int launch_linear_auto(const float* X, int ldx, const float* W, const float* s, const float* t,
                        int act, int64_t M, int K, int Nout, float* Y, int ldy, RowMap map,
                        cudaStream_t st);
+int launch_gram_dist_ts(const float* F, int64_t graph_rows, int64_t row_off, int G, int nn, int D,
+                        const float* norms, float* D2, cudaStream_t st);
 int launch_gram_dist_tc(const float* F, int64_t graph_rows, int64_t row_off, int G, int nn, int D,
                         const float* norms, float* D2, cudaStream_t st);
 int launch_edge_mlp_tc(const float* PQ, const int32_t* idx, const float* w2, const float* s2,

@@ -2131,7 +2131,14 @@ int launch_affinity(const float* F, int64_t graph_rows, int64_t row_off, const u
     gram_dist_kernel<<<gd, 256, 0, st>>>(F, graph_rows, row_off, nn, D, norms, D2);
     R3DFS_CHECK_LAUNCH();
   } else {
-    R3DFS_TRY(launch_gram_dist_tc(F, graph_rows, row_off, G, nn, D, norms, D2, st));
+    // TMEM-operand kernel (linear_ts_kernel<128, true>); the register-fed one when TMA cannot
+    // address the feature matrix, or under R3DFS_DIST_TC=1 in the measurement build
+    static const bool dist_tc = R3DFS_GETENV("R3DFS_DIST_TC") != nullptr;
+    int rc = dist_tc ? R3DFS_E_UNSUPPORTED
+                     : launch_gram_dist_ts(F, graph_rows, row_off, G, nn, D, norms, D2, st);
+    if (rc == R3DFS_E_UNSUPPORTED)
+      rc = launch_gram_dist_tc(F, graph_rows, row_off, G, nn, D, norms, D2, st);
+    R3DFS_TRY(rc);
   }
   if (sr) sr->mark(R3DFS_ST_DIST, st);
   static const bool sel_block = R3DFS_GETENV("R3DFS_SELECT_BLOCK") != nullptr;

@@ -259,11 +259,17 @@ __device__ __forceinline__ float4 ts_raw_chunk(const unsigned char* tile, int r,
   return *reinterpret_cast<const float4*>(tile + r * 64 + ((c ^ ((r >> 1) & 3)) << 4));
 }
 
-template <int BN>
+// DIST = true is the squared-distance form of the affinity graph (the epilogue of
+// linear_tc_kernel<128, true>, which this replaces): X = W = the node features of graph blockIdx.z
+// (rows zrow * z + row0 .. of the matrix behind tmX), Y[m][n] = (s[m] + s[n]) - 2 acc with s the
+// squared row norms; only the tiles on and above the diagonal are computed, an off-diagonal tile
+// is stored twice (as is, and mirrored).
+template <int BN, bool DIST = false>
 __global__ __launch_bounds__(TM_ALL_THREADS, 2) void linear_ts_kernel(
     const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
     const float* __restrict__ s, const float* __restrict__ t, int act, int64_t M, int K, int Nout,
-    float* __restrict__ Y, int ldy, RowMap map) {
+    float* __restrict__ Y, int ldy, RowMap map, int64_t zrow = 0, int64_t row0 = 0) {
+  if (DIST && blockIdx.y < blockIdx.x) return;
   extern __shared__ unsigned char smem_raw[];
   using S = TsSmem<BN>;
   unsigned char* smem = reinterpret_cast<unsigned char*>(
@@ -275,14 +281,20 @@ __global__ __launch_bounds__(TM_ALL_THREADS, 2) void linear_ts_kernel(
   __shared__ float s_sc[BN], s_sh[BN];
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const int n_tiles = (Nout + BN - 1) / BN;
-  const int m0 = (blockIdx.x / n_tiles) * TM_BM;
-  const int n0 = (blockIdx.x % n_tiles) * BN;
+  const int m0 = DIST ? blockIdx.x * TM_BM : (blockIdx.x / n_tiles) * TM_BM;
+  const int n0 = DIST ? blockIdx.y * BN : (blockIdx.x % n_tiles) * BN;
+  // DIST: this graph's rows inside the feature matrix, its norms and its output matrix
+  const int tma_row = DIST ? (int)(zrow * blockIdx.z + row0) : 0;
+  if (DIST) {
+    s += (int64_t)blockIdx.z * M;
+    Y += (int64_t)blockIdx.z * M * (int64_t)ldy;
+  }
   constexpr int LBO_B = tc::tile_lbo(BN);
   constexpr uint32_t IDESC = tc::make_idesc_tf32(TM_BM, BN);
   constexpr uint32_t COL_A = 128;
   const int KB = (K + TM_BK - 1) / TM_BK;
 
-  if (tid < BN) {
+  if (!DIST && tid < BN) {
     const int n = n0 + tid;
     s_sc[tid] = (s && n < Nout) ? s[n] : 1.f;
     s_sh[tid] = (t && n < Nout) ? t[n] : 0.f;
@@ -305,8 +317,8 @@ __global__ __launch_bounds__(TM_ALL_THREADS, 2) void linear_ts_kernel(
     const int rs = kb % TS_RAW_STAGES;
     unsigned char* ra = smem + S::RAW_OFF + rs * S::RAW_STAGE;
     mbar_expect_tx(&bar_full[rs], S::RAW_STAGE);
-    tma_load_2d(ra, &tmX, kb * TM_BK, m0, &bar_full[rs]);
-    tma_load_2d(ra + S::RAW_A, &tmW, kb * TM_BK, n0, &bar_full[rs]);
+    tma_load_2d(ra, &tmX, kb * TM_BK, tma_row + m0, &bar_full[rs]);
+    tma_load_2d(ra + S::RAW_A, &tmW, kb * TM_BK, tma_row + n0, &bar_full[rs]);
   };
 
   if (w == 8) {
@@ -394,9 +406,23 @@ __global__ __launch_bounds__(TM_ALL_THREADS, 2) void linear_ts_kernel(
       float v[32];
       tc::tmem_ld32(tmem_d + ((uint32_t)rbase << 16) + (uint32_t)(cbase + cc), v);
       const int nb = n0 + cbase + cc;
+      if (DIST) {
+        const int64_t m = (int64_t)m0 + rbase + lane;
+        const float sm = (m < M) ? s[m] : 0.f;
 #pragma unroll
-      for (int j = 0; j < 32; ++j)
-        v[j] = apply_act(fmaf(s_sc[cbase + cc + j], v[j], s_sh[cbase + cc + j]), act);
+        for (int j = 0; j < 32; ++j) v[j] = (sm + ((nb + j < Nout) ? s[nb + j] : 0.f)) - 2.f * v[j];
+        if (blockIdx.y > blockIdx.x && m < M) {
+          // mirrored tile: a lane holds one row, so for a fixed column the warp's 32 values are
+          // consecutive in the transposed row — coalesced as they stand
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (nb + j < Nout) Y[(int64_t)(nb + j) * ldy + m] = v[j];
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          v[j] = apply_act(fmaf(s_sc[cbase + cc + j], v[j], s_sh[cbase + cc + j]), act);
+      }
       tc::store_chunk_coalesced(wbuf, v, lane, Nout - nb, vec_y, [&](int r) -> float* {
         const int64_t m = (int64_t)m0 + rbase + r;
         return (m < M) ? Y + map(m) * (int64_t)ldy + nb : nullptr;
@@ -467,6 +493,26 @@ static int launch_ts_bn(const CUtensorMap& tx, const CUtensorMap& tw, const floa
   dim3 grid((unsigned)(((M + TM_BM - 1) / TM_BM) * ((Nout + BN - 1) / BN)));
   linear_ts_kernel<BN><<<grid, TM_ALL_THREADS, S::TOTAL, st>>>(tx, tw, s, t, act, M, K, Nout, Y, ldy,
                                                            map);
+  R3DFS_CHECK_LAUNCH();
+  return 0;
+}
+
+// D2[g][i][j] = |f_i|^2 + |f_j|^2 - 2 f_i.f_j for G graphs of nn nodes (rows of D floats) on the
+// TMEM-operand kernel; R3DFS_E_UNSUPPORTED when TMA cannot address the feature matrix
+int launch_gram_dist_ts(const float* F, int64_t graph_rows, int64_t row_off, int G, int nn, int D,
+                        const float* norms, float* D2, cudaStream_t st) {
+  if ((D & 3) != 0 || (reinterpret_cast<uintptr_t>(F) & 15) != 0 ||
+      (int64_t)G * graph_rows >= (1ll << 31))
+    return R3DFS_E_UNSUPPORTED;
+  CUtensorMap tf;
+  if (!make_map(&tf, F, (int64_t)G * graph_rows, D, D, TM_BM, true)) return R3DFS_E_UNSUPPORTED;
+  using S = TsSmem<128>;
+  cudaError_t e = cudaFuncSetAttribute(linear_ts_kernel<128, true>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
+  if (e != cudaSuccess) return (int)e;
+  dim3 grid((nn + TM_BM - 1) / TM_BM, (nn + 127) / 128, G);
+  linear_ts_kernel<128, true><<<grid, TM_ALL_THREADS, S::TOTAL, st>>>(
+      tf, tf, norms, nullptr, 0, nn, D, nn, D2, nn, identity_map(), graph_rows, row_off);
   R3DFS_CHECK_LAUNCH();
   return 0;
 }

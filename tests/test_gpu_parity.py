@@ -1079,7 +1079,7 @@ def test_selection_and_inedge_kernels_equal_their_predecessors(n, tmp_path):
     from r3dfsseg_b200 import _lib
     assert os.path.isfile(_lib.AB_LIB_PATH), "measurement build missing: make -C r3dfsseg_b200/csrc ab"
     env_old = dict(os.environ, R3DFS_LIB=_lib.AB_LIB_PATH, R3DFS_SELECT_BLOCK="1",
-                   R3DFS_INEDGE_SORT="1")
+                   R3DFS_INEDGE_SORT="1", R3DFS_DIST_TC="1")  # + the register-fed distance GEMM
     subprocess.run([sys.executable, script, "run", a, str(n), "3"], check=True, timeout=300)
     subprocess.run([sys.executable, script, "run", b, str(n), "3"], check=True, timeout=300, env=env_old)
     r = subprocess.run([sys.executable, script, "cmp", a, b], capture_output=True, text=True, timeout=300)
