@@ -620,7 +620,7 @@ def main():
                  "pq0": "linear_tc_kernel", "pq1": "linear_ts_kernel", "pq2": "linear_ts_kernel",
                  "mlp": "linear_ts_kernel", "base": "linear_ts_kernel", "qkv": "linear_ts_kernel",
                  "att": "attention_tc2_kernel", "fps": "fps_q8_kernel", "cg": "lp_cg_kernel",
-                 "dist": "linear_tc_kernel<DIST>", "select": "knn_select_reg_kernel",
+                 "dist": "linear_ts_kernel<DIST>", "select": "knn_select_reg_kernel",
                  "proto": "assign_kernel+proto_mean_kernel",
                  "sym": "in_bits/in_rank/in_fill_rank/merge_rows kernels",
                  "sim": "edge_sim_kernel"}
