@@ -381,15 +381,15 @@ __global__ __launch_bounds__(SELW_WARPS * 32) void knn_select_warp_kernel(
 // contiguous run of the row's keys in registers (staged through shared memory so the global loads
 // stay coalesced), the same range narrowing with ONE barrier per pass (three rotating histograms,
 // every warp scans the bins for itself), then the ordered compaction of knn_select_kernel.
-template <int KPT>
-__global__ __launch_bounds__(SEL_THREADS, KPT <= 20 ? 4 : 2) void knn_select_reg_kernel(
+template <int KPT, int NT = SEL_THREADS>
+__global__ __launch_bounds__(NT, (KPT <= 20 ? 1024 : 512) / NT) void knn_select_reg_kernel(
     const float* __restrict__ D2, const uint8_t* __restrict__ valid, int nn, int k,
     int32_t* __restrict__ nbr) {
   extern __shared__ unsigned s_key[];  // [nn]
   __shared__ int s_hist[3][256];
-  __shared__ unsigned s_lo[SEL_THREADS / 32], s_hi[SEL_THREADS / 32];
-  __shared__ int s_cnt[SEL_THREADS / 32];
-  __shared__ int s_w[2][SEL_THREADS / 32];
+  __shared__ unsigned s_lo[NT / 32], s_hi[NT / 32];
+  __shared__ int s_cnt[NT / 32];
+  __shared__ int s_w[2][NT / 32];
   const int g = blockIdx.y, i = blockIdx.x;
   const uint8_t* vg = valid + (int64_t)g * nn;
   if (!vg[i]) return;
@@ -397,7 +397,7 @@ __global__ __launch_bounds__(SEL_THREADS, KPT <= 20 ? 4 : 2) void knn_select_reg
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   unsigned lo = 0xffffffffu, hi = 0u;
   int n_real = 0;
-  for (int j = tid; j < nn; j += SEL_THREADS) {
+  for (int j = tid; j < nn; j += NT) {
     const float v = __ldcs(row + j);
     const bool real = vg[j] != 0 && j != i;
     unsigned kk = f2key(v);
@@ -418,17 +418,17 @@ __global__ __launch_bounds__(SEL_THREADS, KPT <= 20 ? 4 : 2) void knn_select_reg
     s_hi[w] = hi;
     s_cnt[w] = n_real;
   }
-  s_hist[0][tid] = 0;  // SEL_THREADS == 256
+  if (tid < 256) s_hist[0][tid] = 0;
   __syncthreads();
   n_real = 0;
 #pragma unroll
-  for (int q = 0; q < SEL_THREADS / 32; ++q) {
+  for (int q = 0; q < NT / 32; ++q) {
     lo = min(lo, s_lo[q]);
     hi = max(hi, s_hi[q]);
     n_real += s_cnt[q];
   }
   // my contiguous run (odd length -> conflict-free shared-memory reads)
-  int per = (nn + SEL_THREADS - 1) / SEL_THREADS;
+  int per = (nn + NT - 1) / NT;
   per |= 1;
   const int j0 = tid * per;
   unsigned key[KPT];
@@ -450,7 +450,7 @@ __global__ __launch_bounds__(SEL_THREADS, KPT <= 20 ? 4 : 2) void knn_select_reg
       }
       const int sh = max(0, 24 - (int)__clz(range));
       int* hist = s_hist[p % 3];
-      s_hist[(p + 1) % 3][tid] = 0;  // last read two passes ago
+      if (tid < 256) s_hist[(p + 1) % 3][tid] = 0;  // last read two passes ago
 #pragma unroll
       for (int t = 0; t < KPT; ++t)
         if (key[t] >= lo && key[t] <= hi) atomicAdd(&hist[(key[t] - lo) >> sh], 1);
@@ -2151,8 +2151,12 @@ int launch_affinity(const float* F, int64_t graph_rows, int64_t row_off, const u
     R3DFS_CHECK_LAUNCH();
   } else if (nn <= 31 * SEL_THREADS && !sel_block) {
     const size_t smem = sizeof(unsigned) * (size_t)nn;  // <= 31 KB
+    static const bool sel_256 = R3DFS_GETENV("R3DFS_SELECT_256") != nullptr;  // A/B: 256-thread CTAs only
     if (nn <= 19 * SEL_THREADS)
       knn_select_reg_kernel<20><<<dim3(nn, G), SEL_THREADS, smem, st>>>(D2, valid, nn, k, nbr);
+    else if (!sel_256)  // 512 threads keep 20 keys per thread and 1024 threads per SM in flight
+      knn_select_reg_kernel<20, 512><<<dim3(nn, G), 512, smem, st>>>(D2, valid, nn, k, nbr);  // (32 keys
+                                                            // per thread on 256 threads: half the occupancy)
     else
       knn_select_reg_kernel<32><<<dim3(nn, G), SEL_THREADS, smem, st>>>(D2, valid, nn, k, nbr);
     R3DFS_CHECK_LAUNCH();
