@@ -2152,7 +2152,8 @@ int launch_affinity(const float* F, int64_t graph_rows, int64_t row_off, const u
   } else if (nn <= 31 * SEL_THREADS && !sel_block) {
     const size_t smem = sizeof(unsigned) * (size_t)nn;  // <= 31 KB
     static const bool sel_256 = R3DFS_GETENV("R3DFS_SELECT_256") != nullptr;  // A/B: 256-thread CTAs only
-    if (nn <= 19 * SEL_THREADS)
+    static const bool sel_512 = R3DFS_GETENV("R3DFS_SELECT_512") != nullptr;  // A/B: 512-thread CTAs always
+    if (nn <= 19 * SEL_THREADS && !sel_512)
       knn_select_reg_kernel<20><<<dim3(nn, G), SEL_THREADS, smem, st>>>(D2, valid, nn, k, nbr);
     else if (!sel_256)  // 512 threads keep 20 keys per thread and 1024 threads per SM in flight
       knn_select_reg_kernel<20, 512><<<dim3(nn, G), 512, smem, st>>>(D2, valid, nn, k, nbr);  // (32 keys
